@@ -1,0 +1,105 @@
+// Device-side state shared by all kernels of the exact simplex engine.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "bigint.cuh"
+
+namespace rg {
+
+enum DevStatus { ST_RUN = 0, ST_OPTIMAL = 1, ST_UNBOUNDED = 2, ST_PROMOTE = 3, ST_FATAL = 4 };
+
+// Scalars of the iteration in flight; written by 1-thread kernels, read by all others.
+struct Scalars {
+    int status;          // DevStatus
+    int q;               // entering provider column id
+    int p;               // pivot row as carry row index (1..m)
+    int leaving;         // column id leaving the basis
+    int sgn;             // sign of the pivot element numerator a = u[p]
+    int t, E;            // ctz(D) and ceil(t/64): extra limbs the exact division needs
+    int t2, E2;          // same for D^2 (steepest-edge recurrence)
+    int maxbits_carry;   // max |numerator| bit length in the carry (all rows known to this rank)
+    int maxbits_new;     // being accumulated by the update kernel
+    int maxbits_u;       // of the current pivot column (incl. the cost row entry)
+    int maxbits_rowp;    // of the staged pivot row
+    int maxbits_tmp;     // scratch (phase switch)
+    int bits_D;
+    int predicted;       // predicted bit length of the update's results
+    int last_selected;   // FirstProfitableWithMemory state (-1 = none)
+    int found;           // generic "search hit" index (-1 = none)
+    int bp_nonzero;      // remove_artificial: is b_p != 0
+    int pad;
+    u64 D[RG_MAXL];          // current denominator (positive)
+    u64 Dnew[RG_MAXL];       // |a|: denominator after the pivot
+    u64 Dinv[2 * RG_MAXL + 2];   // inverse of odd(D) mod 2^(64 (L+E)), E <= L
+    u64 A[2 * RG_MAXL + 2];      // |a| * Dinv mod 2^(64 (L+E))
+    u64 up[2 * RG_MAXL + 2];     // replacement for u[p]: a - D (makes the pivot row uniform)
+    u64 Gq[RG_MAXW];         // steepest edge: Ghat of the entering column
+    u64 S1[RG_MAXW], S2[RG_MAXW], S3[RG_MAXW];   // a^2/D^2, 2a/D^2, Gq/D^2 (2-adic)
+};
+
+// what the host reads back after every iteration (pinned)
+struct HostMirror {
+    int status, q, p, leaving;          // device status; NEXT entering column; last pivot row; last leaving
+    int t_next, bits_D, maxbits_carry, predicted;
+    int found, sgn, maxbits_tmp, pivoted;   // pivoted: a basis change happened since the host cleared it
+    int q_done, p_done, leaving_done, pad;  // the pivot that was performed (written by k_finalize)
+};
+
+struct Csc {
+    long long* colptr = nullptr;   // n+1
+    int* rowidx = nullptr;         // nnz
+    long long* vals = nullptr;     // nnz
+    long long nnz = 0;
+};
+
+// widths derived from the carry limb count L
+__host__ __device__ constexpr int LU_of(int L) { return L + 2; }          // pivot column, costs, row dots
+__host__ __device__ constexpr int LW_of(int L) { return 2 * L + 4; }      // work vector
+__host__ __device__ constexpr int LS_of(int L) { return 2 * L + 6; }      // work vector . column
+__host__ __device__ constexpr int LG_of(int L) { return 2 * L + 5; }      // Ghat = gamma * D^2
+
+}  // namespace rg
+
+struct rg_context {
+    int device = 0;
+    int rank = 0, world = 1;
+    cudaStream_t stream = nullptr;
+    int m = 0, n = 0;
+    int ld = 0;                 // carry leading dimension in entries (multiple of 16)
+    int L = 2;                  // current limb count
+    size_t plane = 0;           // entries per carry plane = (m+1) * ld
+    u64* carry = nullptr;       // L planes
+    u64* u = nullptr;           // LU planes x ld      current pivot column (rows 0..m)
+    u64* rowp = nullptr;        // L  planes x ld      staged pivot row
+    u64* omega = nullptr;       // LW planes x ld      work vector
+    u64* omega_part = nullptr;  // chunks x LW planes x ld
+    int work_chunks = 0;
+    u64* tmprow = nullptr;      // LU planes x ld      phase-switch row
+    u64* svec = nullptr;        // 1 plane x ld        basic costs (phase switch)
+    rg::Csc A;
+    long long* cost = nullptr;  // n
+    long long* rhs = nullptr;   // m
+    int* basis = nullptr;       // m column ids
+    unsigned char* inbasis = nullptr;  // n
+    u64* kappa = nullptr;       // LU planes x n  relative cost numerators
+    u64* nu = nullptr;          // LU planes x n  pivot-row . column
+    u64* sigma = nullptr;       // LS planes x n  work-vector . column
+    u64* G = nullptr;           // LG planes x n  Ghat
+    int* cand = nullptr;        // block winners scratch
+    rg::Scalars* sc = nullptr;
+    rg::HostMirror* hm = nullptr;      // pinned host
+    rg::HostMirror* hm_dev = nullptr;  // device alias of hm
+    int rule = 2;
+    bool rule_ready = false;
+    bool have_column = false;
+    bool selected = false;             // sc->q holds the entering column chosen for the current basis
+    bool identity_carry = false;       // B^-1 == I and D == 1 (fresh init)
+    int t_cur = 0;                     // ctz(D) of the current denominator (host copy)
+    long long pivots = 0, promotions = 0, launches = 0;
+    long long pivots_at[5] = {0, 0, 0, 0, 0};
+    std::string err;
+};

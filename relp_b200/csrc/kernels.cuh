@@ -1,0 +1,970 @@
+// Hand-written sm_100a kernels of the exact simplex iteration.  See DESIGN.md for the maths.
+//
+// Layout: the carry is limb-planar -- plane l holds limb l of every entry, entry (i,k) at
+// i*ld + k -- so a warp walking k reads 256 B (one column per thread) or 512 B (two columns per
+// thread, 128-bit loads) per plane, fully coalesced.  Vectors (pivot column u, staged pivot row,
+// work vector, per-column pricing data) use the same planar scheme.
+#pragma once
+#include "engine.cuh"
+
+namespace rg {
+
+// ---------------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------------
+template <int LN>
+__device__ __forceinline__ void load_planar(u64 (&x)[LN], const u64* __restrict__ base, size_t stride,
+                                            size_t idx) {
+#pragma unroll
+    for (int l = 0; l < LN; ++l) x[l] = base[l * stride + idx];
+}
+template <int LN>
+__device__ __forceinline__ void store_planar(u64* __restrict__ base, size_t stride, size_t idx,
+                                             const u64 (&x)[LN]) {
+#pragma unroll
+    for (int l = 0; l < LN; ++l) base[l * stride + idx] = x[l];
+}
+__device__ inline void rt_load_planar(u64* x, int nl, const u64* base, size_t stride, size_t idx) {
+    for (int l = 0; l < nl; ++l) x[l] = base[l * stride + idx];
+}
+__device__ inline void rt_store_planar(u64* base, size_t stride, size_t idx, const u64* x, int nl) {
+    for (int l = 0; l < nl; ++l) base[l * stride + idx] = x[l];
+}
+__device__ __forceinline__ int warp_max(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// number of significant limbs of an unsigned magnitude
+__device__ inline int rt_trim(const u64* x, int n) {
+    while (n > 0 && x[n - 1] == 0) --n;
+    return n;
+}
+// sign of (a*b - c*d) for two's complement operands; ws: 4*RG_MAXW limbs of scratch
+__device__ inline int rt_cmp_prod(const u64* a, int na, const u64* b, int nb, const u64* c, int nc,
+                                  const u64* d, int nd, u64* ws) {
+    u64* ma = ws;
+    u64* mb = ws + RG_MAXW;
+    u64* p1 = ws + 2 * RG_MAXW;
+    u64* p2 = ws + 3 * RG_MAXW;
+    int s1 = rt_abs(ma, a, na) * rt_abs(mb, b, nb);
+    int la = rt_trim(ma, na), lb = rt_trim(mb, nb);
+    rt_mul_full(p1, ma, la, mb, lb);
+    int l1 = la + lb;
+    int s2 = rt_abs(ma, c, nc) * rt_abs(mb, d, nd);
+    la = rt_trim(ma, nc); lb = rt_trim(mb, nd);
+    rt_mul_full(p2, ma, la, mb, lb);
+    int l2 = la + lb;
+    if (s1 != s2) return s1 < s2 ? -1 : 1;
+    if (s1 == 0) return 0;
+    int n = l1 > l2 ? l1 : l2;
+    for (int k = l1; k < n; ++k) p1[k] = 0;
+    for (int k = l2; k < n; ++k) p2[k] = 0;
+    int c0 = rt_cmp_u(p1, p2, n);
+    return s1 > 0 ? c0 : -c0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// init: identity carry  (Carry::create_for_*_artificial, carry/mod.rs:374-442)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_zero(u64* p, size_t n) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    size_t s = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += s) p[i] = 0;
+}
+
+// rows 1..m: b in column 0, 1 on the diagonal.  Row 0: -1 under artificial rows, -sum b(art) in (0,0).
+__global__ void k_init_identity(u64* C, size_t ps, int ld, int m, int L, const long long* rhs,
+                                const int* basis, Scalars* sc) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;   // constraint row 0..m-1
+    if (i >= m) return;
+    size_t r = (size_t)(i + 1) * ld;
+    long long b = rhs[i];
+    C[r + 0] = (u64)b;
+    for (int l = 1; l < L; ++l) C[l * ps + r + 0] = b < 0 ? ~0ull : 0ull;
+    C[r + (i + 1)] = 1;
+    if (basis[i] < 0) {
+        for (int l = 0; l < L; ++l) C[l * ps + (i + 1)] = ~0ull;   // -1
+    }
+}
+// (0,0) = -sum_{artificial rows} b   and scalar state
+__global__ void k_init_scalars(u64* C, size_t ps, int m, int L, const long long* rhs, const int* basis,
+                               Scalars* sc) {
+    if (threadIdx.x || blockIdx.x) return;
+    u64 buf[3 * RG_MAXL];
+    u64* acc = buf; u64* t = buf + RG_MAXL; u64* mg = buf + 2 * RG_MAXL;
+    for (int l = 0; l < L; ++l) acc[l] = 0;
+    int maxbits = 1;
+    for (int i = 0; i < m; ++i) {
+        long long b = rhs[i];
+        u64 mag = b < 0 ? (u64)(-b) : (u64)b;
+        int bl = mag ? 64 - __clzll(mag) : 0;
+        if (bl > maxbits) maxbits = bl;
+        if (basis[i] < 0) {
+            for (int l = 0; l < L; ++l) t[l] = l == 0 ? (u64)b : (b < 0 ? ~0ull : 0ull);
+            rt_sub(acc, t, L);
+        }
+    }
+    for (int l = 0; l < L; ++l) C[l * ps] = acc[l];
+    rt_abs(mg, acc, L);
+    int bl = rt_bitlen_u(mg, L);
+    if (bl > maxbits) maxbits = bl;
+    sc->status = ST_RUN;
+    sc->q = -1; sc->p = -1; sc->leaving = 0; sc->sgn = 1;
+    sc->t = 0; sc->E = 0; sc->t2 = 0; sc->E2 = 0;
+    sc->maxbits_carry = maxbits; sc->maxbits_new = 0; sc->maxbits_u = 0; sc->maxbits_rowp = 0;
+    sc->bits_D = 1; sc->predicted = 0; sc->last_selected = -1; sc->found = -1;
+    for (int l = 0; l < RG_MAXL; ++l) { sc->D[l] = l == 0; sc->Dnew[l] = 0; }
+}
+
+__global__ void k_set_inbasis(unsigned char* inbasis, const int* basis, int m) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m && basis[i] >= 0) inbasis[basis[i]] = 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K9: limb-width promotion.  Planar two's complement => the old planes are kept verbatim (one
+// device copy) and the new planes are pure sign extension.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_sign_extend(u64* dst, size_t ps, size_t count, int Lold, int Lnew) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    size_t s = (size_t)gridDim.x * blockDim.x;
+    for (; i < count; i += s) {
+        u64 sg = (i64)dst[(size_t)(Lold - 1) * ps + i] < 0 ? ~0ull : 0ull;
+        for (int l = Lold; l < Lnew; ++l) dst[(size_t)l * ps + i] = sg;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4 pricing / generic column dots:  out_j = cmul * cost_j * D + vec[1 + row] . a_j
+// (Tableau::relative_cost, tableau/mod.rs:106-112 with cmul = 1; row dots with cmul = 0)
+// One thread per provider column; `vec` is an (m+1)-vector whose entry k+1 pairs with row k.
+// ---------------------------------------------------------------------------------------------
+template <int LV, int LO>
+__global__ void __launch_bounds__(256)
+k_coldot(const u64* __restrict__ vec, size_t vs, int n, const long long* __restrict__ colptr,
+         const int* __restrict__ rowidx, const long long* __restrict__ vals,
+         const unsigned char* __restrict__ inbasis, const long long* __restrict__ cost, int cmul,
+         int LD, u64* __restrict__ out, const Scalars* __restrict__ sc) {
+    if (sc->status != ST_RUN) return;
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    u64 acc[LO];
+#pragma unroll
+    for (int l = 0; l < LO; ++l) acc[l] = 0;
+    if (!inbasis[j]) {
+        if (cmul) {
+            long long c = cost[j];
+            if (c) {
+                u64 d[LV];
+#pragma unroll
+                for (int l = 0; l < LV; ++l) d[l] = l < LD ? sc->D[l] : 0;
+                mac_small<LO, LV>(acc, d, c);
+            }
+        }
+        long long k0 = colptr[j], k1 = colptr[j + 1];
+        for (long long k = k0; k < k1; ++k) {
+            int r = rowidx[k];
+            u64 x[LV];
+            load_planar<LV>(x, vec, vs, (size_t)(r + 1));
+            mac_small<LO, LV>(acc, x, vals[k]);
+        }
+    }
+    store_planar<LO>(out, (size_t)n, (size_t)j, acc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// index reductions (pivot column choice, ratio test, artificial-removal search)
+// ---------------------------------------------------------------------------------------------
+// Comparators expose eligible(j) and better(j,k) (strict total order: key then index rule).
+
+struct PriceView {
+    const u64* kappa; int LU; int n;
+    const unsigned char* inbasis;
+    __device__ bool negative(int j) const { return (i64)kappa[(size_t)(LU - 1) * n + j] < 0; }
+};
+
+// FirstProfitable (pivot_rule.rs:95-108): lowest j with negative cost
+struct CmpFirst {
+    PriceView v;
+    __device__ bool eligible(int j) const { return !v.inbasis[j] && v.negative(j); }
+    __device__ bool better(int j, int k) const { return j < k; }
+};
+// FirstProfitableWithMemory (pivot_rule.rs:126-149): first after `last`, wrapping, never `last`
+struct CmpFirstMem {
+    PriceView v; const Scalars* sc;
+    __device__ bool eligible(int j) const { return j != sc->last_selected && !v.inbasis[j] && v.negative(j); }
+    __device__ int key(int j) const { int last = sc->last_selected; return j > last ? j - last : j + v.n - last; }
+    __device__ bool better(int j, int k) const { return key(j) < key(k); }
+};
+// Dantzig (pivot_rule.rs:163-186): most negative, strict < => lowest index on ties
+struct CmpDantzig {
+    PriceView v;
+    __device__ bool eligible(int j) const { return !v.inbasis[j] && v.negative(j); }
+    __device__ bool better(int j, int k) const {
+        u64 buf[2 * (RG_MAXL + 2)];
+        u64* a = buf; u64* b = buf + RG_MAXL + 2;
+        rt_load_planar(a, v.LU, v.kappa, v.n, j);
+        rt_load_planar(b, v.LU, v.kappa, v.n, k);
+        int c = rt_cmp_s(a, b, v.LU);
+        return c < 0 || (c == 0 && j < k);
+    }
+};
+// Steepest edge (pivot_rule.rs:221-241): max cost^2/gamma, max_by_key => highest index on ties.
+// cost_j^2/gamma_j = kappa_j^2 W^2 / Ghat_j  =>  compare kappa_j^2 Ghat_k with kappa_k^2 Ghat_j.
+struct CmpSteepest {
+    PriceView v; const u64* G; int LG;
+    __device__ bool eligible(int j) const { return !v.inbasis[j] && v.negative(j); }
+    __device__ bool better(int j, int k) const {
+        u64 buf[6 * RG_MAXW];
+        u64* x = buf; u64* y = buf + RG_MAXW; u64* sj = buf + 2 * RG_MAXW; u64* sk = buf + 3 * RG_MAXW;
+        u64* pj = buf + 4 * RG_MAXW; u64* pk = buf + 5 * RG_MAXW;
+        rt_load_planar(x, v.LU, v.kappa, v.n, j);
+        rt_abs(y, x, v.LU);
+        int ly = rt_trim(y, v.LU);
+        rt_mul_full(sj, y, ly, y, ly);
+        int lsj = rt_trim(sj, 2 * ly);
+        rt_load_planar(x, v.LU, v.kappa, v.n, k);
+        rt_abs(y, x, v.LU);
+        ly = rt_trim(y, v.LU);
+        rt_mul_full(sk, y, ly, y, ly);
+        int lsk = rt_trim(sk, 2 * ly);
+        rt_load_planar(x, LG, G, v.n, k);
+        int lg = rt_trim(x, LG);
+        rt_mul_full(pj, sj, lsj, x, lg);
+        int lpj = lsj + lg;
+        rt_load_planar(x, LG, G, v.n, j);
+        lg = rt_trim(x, LG);
+        rt_mul_full(pk, sk, lsk, x, lg);
+        int lpk = lsk + lg;
+        int nn = lpj > lpk ? lpj : lpk;
+        for (int i = lpj; i < nn; ++i) pj[i] = 0;
+        for (int i = lpk; i < nn; ++i) pk[i] = 0;
+        int c = rt_cmp_u(pj, pk, nn);
+        return c > 0 || (c == 0 && j > k);
+    }
+};
+// ratio test (tableau/mod.rs:287-313): rows with u_i > 0, min b_i/u_i, ties -> lowest leaving column.
+// Index space: carry rows 1..m mapped to 0..m-1.
+struct CmpRatio {
+    const u64* C; size_t ps; int ld; int L;
+    const u64* u; size_t us; int LU;
+    const int* basis;
+    __device__ bool eligible(int r) const {
+        size_t i = (size_t)r + 1;
+        if ((i64)u[(size_t)(LU - 1) * us + i] < 0) return false;
+        u64 o = 0;
+        for (int l = 0; l < LU; ++l) o |= u[(size_t)l * us + i];
+        return o != 0;
+    }
+    __device__ bool better(int r, int s) const {
+        u64 buf[4 * (RG_MAXL + 2) + 4 * RG_MAXW];
+        u64* bi = buf; u64* bk = buf + (RG_MAXL + 2); u64* ui = buf + 2 * (RG_MAXL + 2);
+        u64* uk = buf + 3 * (RG_MAXL + 2); u64* ws = buf + 4 * (RG_MAXL + 2);
+        rt_load_planar(bi, L, C, ps, (size_t)(r + 1) * ld);
+        rt_load_planar(bk, L, C, ps, (size_t)(s + 1) * ld);
+        rt_load_planar(ui, LU, u, us, (size_t)r + 1);
+        rt_load_planar(uk, LU, u, us, (size_t)s + 1);
+        int c = rt_cmp_prod(bi, L, uk, LU, bk, L, ui, LU, ws);   // b_r/u_r ? b_s/u_s
+        return c < 0 || (c == 0 && basis[r] < basis[s]);
+    }
+};
+// remove_artificial_basis_variables search (phase_one.rs:245-261): first j (ascending)
+struct CmpArtificial {
+    PriceView v; const u64* nu; const Scalars* sc;
+    __device__ bool eligible(int j) const {
+        if (v.inbasis[j]) return false;
+        u64 o = 0;
+        for (int l = 0; l < v.LU; ++l) o |= nu[(size_t)l * v.n + j];
+        bool neg = (i64)nu[(size_t)(v.LU - 1) * v.n + j] < 0;
+        if (sc->bp_nonzero) {
+            u64 c = 0;
+            for (int l = 0; l < v.LU; ++l) c |= v.kappa[(size_t)l * v.n + j];
+            return c == 0 && o != 0 && !neg;
+        }
+        return o != 0;
+    }
+    __device__ bool better(int j, int k) const { return j < k; }
+};
+
+template <class Cmp>
+__device__ __forceinline__ int block_best(int best, const Cmp& cmp, int* sm) {
+    int tid = threadIdx.x;
+    sm[tid] = best;
+    __syncthreads();
+    for (int s = blockDim.x >> 1; s > 0; s >>= 1) {
+        if (tid < s) {
+            int a = sm[tid], b = sm[tid + s];
+            if (b >= 0 && (a < 0 || cmp.better(b, a))) sm[tid] = b;
+        }
+        __syncthreads();
+    }
+    return sm[0];
+}
+
+template <class Cmp>
+__global__ void __launch_bounds__(256) k_argbest1(int n, Cmp cmp, int* cand, const Scalars* sc) {
+    __shared__ int sm[256];
+    if (sc->status != ST_RUN) return;
+    int best = -1;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        if (cmp.eligible(j) && (best < 0 || cmp.better(j, best))) best = j;
+    }
+    best = block_best(best, cmp, sm);
+    if (threadIdx.x == 0) cand[blockIdx.x] = best;
+}
+// mode 0: entering column -> sc->q (none => ST_OPTIMAL); mode 1: pivot row -> sc->p (none =>
+// ST_UNBOUNDED); mode 2: generic search -> sc->found
+template <class Cmp>
+__global__ void __launch_bounds__(256) k_argbest2(int nblocks, Cmp cmp, const int* cand, int mode,
+                                                  Scalars* sc) {
+    __shared__ int sm[256];
+    if (sc->status != ST_RUN) return;
+    int best = -1;
+    for (int b = threadIdx.x; b < nblocks; b += blockDim.x) {
+        int j = cand[b];
+        if (j >= 0 && (best < 0 || cmp.better(j, best))) best = j;
+    }
+    best = block_best(best, cmp, sm);
+    if (threadIdx.x == 0) {
+        if (mode == 0) {
+            sc->q = best;
+            if (best < 0) sc->status = ST_OPTIMAL; else sc->last_selected = best;
+        } else if (mode == 1) {
+            sc->p = best + 1;
+            if (best < 0) sc->status = ST_UNBOUNDED;
+        } else {
+            sc->found = best;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2 FTRAN: u_i = sum_k a_kq C[i][1 + row_k]   for every carry row i (row 0: + c_q D = kappa_q)
+// (Carry::generate_column, carry/mod.rs:613-621).  One warp per row, lanes over the column's
+// nonzeros, multi-limb warp reduction.
+// ---------------------------------------------------------------------------------------------
+template <int L>
+__global__ void __launch_bounds__(256)
+k_ftran(const u64* __restrict__ C, size_t ps, int ld, int nrows, const long long* __restrict__ colptr,
+        const int* __restrict__ rowidx, const long long* __restrict__ vals,
+        const long long* __restrict__ cost, int qarg, u64* __restrict__ u, size_t us, Scalars* sc) {
+    constexpr int LU = L + 2;
+    if (sc->status != ST_RUN) return;
+    int q = qarg >= 0 ? qarg : sc->q;
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (warp >= nrows) return;
+    size_t row = (size_t)warp * ld;
+    u64 acc[LU];
+#pragma unroll
+    for (int l = 0; l < LU; ++l) acc[l] = 0;
+    long long k0 = colptr[q], k1 = colptr[q + 1];
+    for (long long k = k0 + lane; k < k1; k += 32) {
+        int r = rowidx[k];
+        u64 x[L];
+        load_planar<L>(x, C, ps, row + 1 + r);
+        mac_small<LU, L>(acc, x, vals[k]);
+    }
+    if (warp == 0 && lane == 0) {
+        long long c = cost[q];
+        if (c) {
+            u64 d[L];
+#pragma unroll
+            for (int l = 0; l < L; ++l) d[l] = sc->D[l];
+            mac_small<LU, L>(acc, d, c);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        u64 other[LU];
+#pragma unroll
+        for (int l = 0; l < LU; ++l) other[l] = __shfl_down_sync(0xffffffffu, acc[l], o);
+        add_n<LU>(acc, other);
+    }
+    if (lane == 0) {
+        store_planar<LU>(u, us, (size_t)warp, acc);
+        int bl = bitlen_signed<LU>(acc);
+        atomicMax(&sc->maxbits_u, bl);
+    }
+}
+
+__global__ void k_reset_iter(Scalars* sc) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) { sc->maxbits_u = 0; sc->maxbits_rowp = 0; sc->maxbits_new = 0; }
+}
+__global__ void k_set_pq(Scalars* sc, int q, int p) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        if (q >= -1) sc->q = q;
+        if (p >= 0) sc->p = p;
+    }
+}
+__global__ void k_set_status(Scalars* sc, int st) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) sc->status = st;
+}
+
+// stage the pivot row (old values) so the update can run in place
+template <int L>
+__global__ void __launch_bounds__(256)
+k_copyrow(const u64* __restrict__ C, size_t ps, int ld, u64* __restrict__ rowp, size_t rs,
+          Scalars* sc) {
+    if (sc->status != ST_RUN) return;
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    int bl = 0;
+    if (k < ld) {
+        u64 x[L];
+        load_planar<L>(x, C, ps, (size_t)sc->p * ld + k);
+        store_planar<L>(rowp, rs, (size_t)k, x);
+        bl = bitlen_signed<L>(x);
+    }
+    bl = warp_max(bl);
+    if ((threadIdx.x & 31) == 0 && bl) atomicMax(&sc->maxbits_rowp, bl);
+}
+
+// ---------------------------------------------------------------------------------------------
+// pivot scalars (one thread): overflow prediction, 2-adic inverse of D, A = |a|/D, u_p' = a - D,
+// steepest-edge scalars.  Sets ST_PROMOTE / ST_FATAL when the update would not fit L limbs.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_scalars(const u64* __restrict__ u, size_t us, int L, int want_se,
+                          const u64* __restrict__ G, int n, int E_host, Scalars* sc) {
+    if (threadIdx.x || blockIdx.x) return;
+    if (sc->status != ST_RUN) return;
+    const int LU = L + 2;
+    u64 buf[17 * RG_MAXW];     // ONE local buffer, sliced by hand (see bigint.cuh rt_inv_odd)
+    u64* a = buf;               u64* am = buf + RG_MAXW;        u64* dodd = buf + 2 * RG_MAXW;
+    u64* inv = buf + 3 * RG_MAXW;  u64* tmp = buf + 4 * RG_MAXW;   u64* ext = buf + 5 * RG_MAXW;
+    u64* upv = buf + 6 * RG_MAXW;  u64* dext = buf + 7 * RG_MAXW;  u64* i1 = buf + 8 * RG_MAXW;
+    u64* i2 = buf + 9 * RG_MAXW;   u64* ax = buf + 10 * RG_MAXW;   u64* a2 = buf + 11 * RG_MAXW;
+    u64* gq = buf + 12 * RG_MAXW;  u64* ws = buf + 13 * RG_MAXW;   // ws: 3 slots (+1 spare)
+    rt_load_planar(a, LU, u, us, (size_t)sc->p);
+    int sgn = rt_abs(am, a, LU);
+    sc->sgn = sgn;
+    int bits_a = rt_bitlen_u(am, LU);
+    int bits_D = rt_bitlen_u(sc->D, L);
+    sc->bits_D = bits_D;
+    int bu = max(sc->maxbits_u, bits_D) + 1;
+    int pred = max(bits_a + sc->maxbits_carry, bu + sc->maxbits_rowp) + 2 - bits_D;
+    sc->predicted = pred;
+    if (pred > 64 * L - 1) {
+        sc->status = (L >= RG_MAXL) ? ST_FATAL : ST_PROMOTE;
+        return;
+    }
+    int t = rt_ctz(sc->D, L);
+    int E = (t + 63) >> 6;
+    int W = L + E;
+    sc->t = t; sc->E = E;
+    if (E != E_host) { sc->status = ST_FATAL; return; }   // host picked the wrong kernel variant
+    for (int l = 0; l < L; ++l) dodd[l] = sc->D[l];
+    rt_shr(dodd, L, t);
+    rt_inv_odd(inv, dodd, L, W, ws);
+#ifdef RG_DEBUG_PRINT
+    printf("scalars: right after inv: inv0=%llu dodd0=%llu L=%d W=%d\n", inv[0], dodd[0], L, W);
+#endif
+    for (int l = 0; l < W; ++l) sc->Dinv[l] = inv[l];
+    for (int l = 0; l < W; ++l) ext[l] = l < LU ? am[l] : 0;
+    rt_mul_lo(tmp, ext, inv, W);
+    for (int l = 0; l < W; ++l) sc->A[l] = tmp[l];
+#ifdef RG_DEBUG_PRINT
+    printf("scalars: L=%d t=%d E=%d W=%d D0=%llu dodd0=%llu inv0=%llu am0=%llu A0=%llu\n", L, t, E, W, sc->D[0], dodd[0], inv[0], am[0], tmp[0]);
+#endif
+    for (int l = 0; l < L; ++l) sc->Dnew[l] = am[l];
+    // up = a - D  (two's complement, max(W, LU) limbs kept)
+    int WU = W > LU ? W : LU;
+    rt_sext(upv, WU, a, LU);
+    for (int l = 0; l < WU; ++l) dext[l] = l < L ? sc->D[l] : 0;
+    rt_sub(upv, dext, WU);
+    for (int l = 0; l < WU; ++l) sc->up[l] = upv[l];
+    sc->maxbits_new = 0;
+    if (want_se) {
+        // Ghat' = [a^2 Ghat - 2 a nu sigma + nu^2 Gq] / D^2, evaluated mod 2^(64 WX) with the 2-adic
+        // inverse of odd(D)^2 and a final shift by 2t (pivot_rule.rs:243-296 in integer form).
+        const int LG = 2 * L + 5;
+        int t2 = 2 * t, E2 = (t2 + 63) >> 6, WX = LG + E2;
+        sc->t2 = t2; sc->E2 = E2;
+        rt_inv_odd(i1, dodd, L, WX, ws);
+        rt_mul_lo(i2, i1, i1, WX);
+        for (int l = 0; l < WX; ++l) ax[l] = l < LU ? am[l] : 0;     // a > 0 whenever the rule updates
+        rt_mul_lo(a2, ax, ax, WX);
+        rt_mul_lo(tmp, a2, i2, WX);
+        for (int l = 0; l < WX; ++l) sc->S1[l] = tmp[l];
+        rt_add(ax, ax, WX);                                          // 2a
+        rt_mul_lo(tmp, ax, i2, WX);
+        for (int l = 0; l < WX; ++l) sc->S2[l] = tmp[l];
+        for (int l = 0; l < WX; ++l) gq[l] = l < LG ? G[(size_t)l * n + sc->q] : 0;
+        for (int l = 0; l < LG; ++l) sc->Gq[l] = gq[l];
+        rt_mul_lo(tmp, gq, i2, WX);
+        for (int l = 0; l < WX; ++l) sc->S3[l] = tmp[l];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1: rank-1 integer-preserving pivot of the whole carry, in place:
+//        C'[i][k] = ( |a| C[i][k] - sgn(a) u_i C[p][k] ) / D          (u_p replaced by a - D)
+//               = ( A C[i][k] + Bn_i rowp[k]  mod 2^(64 (L+E)) ) >> t
+// with A = |a| inv(odd D), Bn_i = -sgn(a) u_i inv(odd D): the exact division is fused into two low
+// products.  (Carry::change_basis + update_b + update_minus_pi_and_obj, carry/mod.rs:561-604,295-349;
+// BasisInverseRows::{normalize_pivot_row,row_reduce}, basis_inverse_rows.rs:43-84.)
+// Thread = CP adjacent columns (CP = 2: 128-bit loads/stores); block = 256*CP columns x RT rows.
+// ---------------------------------------------------------------------------------------------
+template <int L, int E, int CP>
+__global__ void __launch_bounds__(256)
+k_update(u64* __restrict__ C, size_t ps, int ld, int nrows, const u64* __restrict__ u, size_t us,
+         const u64* __restrict__ rowp, size_t rs, Scalars* sc) {
+    constexpr int W = L + E;
+    constexpr int LU = L + 2;
+    constexpr int RT = 32;
+    __shared__ u64 sBn[RT][W];
+    __shared__ u64 sA[W];
+    if (sc->status != ST_RUN) return;
+    if (sc->E != E) return;
+    const int tid = threadIdx.x;
+    const int row0 = blockIdx.y * RT;
+    if (tid < RT) {
+        int i = row0 + tid;
+        if (i < nrows) {
+            u64 ui[W], dinv[W], bn[W];
+            if (i == sc->p) {
+#pragma unroll
+                for (int l = 0; l < W; ++l) ui[l] = sc->up[l];
+            } else {
+                u64 top = u[(size_t)(LU - 1) * us + i];
+                u64 sg = (i64)top < 0 ? ~0ull : 0ull;
+#pragma unroll
+                for (int l = 0; l < W; ++l) ui[l] = l < LU ? u[(size_t)l * us + i] : sg;
+            }
+#pragma unroll
+            for (int l = 0; l < W; ++l) dinv[l] = sc->Dinv[l];
+            mul_lo<W>(bn, ui, dinv);
+            if (sc->sgn > 0) {   // Bn = -u Dinv
+                u64 c = 1;
+#pragma unroll
+                for (int l = 0; l < W; ++l) { u64 v = ~bn[l] + c; c = (c && v == 0) ? 1 : 0; bn[l] = v; }
+            }
+#pragma unroll
+            for (int l = 0; l < W; ++l) sBn[tid][l] = bn[l];
+        }
+    }
+    if (tid < W) sA[tid] = sc->A[tid];
+    __syncthreads();
+    const int col = (blockIdx.x * 256 + tid) * CP;
+    int maxb = 0;
+    if (col < ld) {
+        const int t = sc->t;
+        const int tw = t >> 6, tb = t & 63;
+        u64 A[W];
+#pragma unroll
+        for (int l = 0; l < W; ++l) A[l] = sA[l];
+        u64 rp[CP][W];
+#pragma unroll
+        for (int c = 0; c < CP; ++c) {
+#pragma unroll
+            for (int l = 0; l < L; ++l) rp[c][l] = rowp[(size_t)l * rs + col + c];
+            u64 sg = (i64)rp[c][L - 1] < 0 ? ~0ull : 0ull;
+#pragma unroll
+            for (int l = L; l < W; ++l) rp[c][l] = sg;
+        }
+        const int rend = min(RT, nrows - row0);
+        for (int r = 0; r < rend; ++r) {
+            size_t off = (size_t)(row0 + r) * ld + col;
+            u64 cv[CP][W];
+            if (CP == 2) {
+#pragma unroll
+                for (int l = 0; l < L; ++l) {
+                    ulonglong2 v = *reinterpret_cast<const ulonglong2*>(C + (size_t)l * ps + off);
+                    cv[0][l] = v.x; cv[CP - 1][l] = v.y;
+                }
+            } else {
+#pragma unroll
+                for (int l = 0; l < L; ++l) cv[0][l] = C[(size_t)l * ps + off];
+            }
+            u64 bn[W];
+#pragma unroll
+            for (int l = 0; l < W; ++l) bn[l] = sBn[r][l];
+            u64 res[CP][L];
+#pragma unroll
+            for (int c = 0; c < CP; ++c) {
+                u64 sg = (i64)cv[c][L - 1] < 0 ? ~0ull : 0ull;
+#pragma unroll
+                for (int l = L; l < W; ++l) cv[c][l] = sg;
+                u64 X[W];
+                mul2_lo<W>(X, A, cv[c], bn, rp[c]);
+                if (E == 0) {
+#pragma unroll
+                    for (int l = 0; l < L; ++l) res[c][l] = X[l];
+                } else {
+#pragma unroll
+                    for (int w = 0; w <= E; ++w) {
+                        if (tw == w) {
+#pragma unroll
+                            for (int l = 0; l < L; ++l) {
+                                u64 lo = X[l + w < W ? l + w : W - 1];
+                                u64 hi = (l + w + 1 < W) ? X[l + w + 1 < W ? l + w + 1 : W - 1] : 0;
+                                res[c][l] = tb ? ((lo >> tb) | (hi << (64 - tb))) : lo;
+                            }
+                        }
+                    }
+                }
+                maxb = max(maxb, bitlen_signed<L>(res[c]));
+            }
+            if (CP == 2) {
+#pragma unroll
+                for (int l = 0; l < L; ++l) {
+                    ulonglong2 v; v.x = res[0][l]; v.y = res[CP - 1][l];
+                    *reinterpret_cast<ulonglong2*>(C + (size_t)l * ps + off) = v;
+                }
+            } else {
+#pragma unroll
+                for (int l = 0; l < L; ++l) C[(size_t)l * ps + off] = res[0][l];
+            }
+        }
+    }
+    maxb = warp_max(maxb);
+    if ((tid & 31) == 0 && maxb) atomicMax(&sc->maxbits_new, maxb);
+}
+
+// Generic-width fallback of K1 for E > 2 (D divisible by 2^129 or more): run-time widths.
+__global__ void __launch_bounds__(128)
+k_update_generic(u64* __restrict__ C, size_t ps, int ld, int nrows, int L, const u64* __restrict__ u,
+                 size_t us, const u64* __restrict__ rowp, size_t rs, Scalars* sc) {
+    if (sc->status != ST_RUN) return;
+    const int E = sc->E;
+    if (E <= 2) return;
+    const int W = L + E, LU = L + 2;
+    int col = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = blockIdx.y;
+    int maxb = 0;
+    if (col < ld && i < nrows) {
+        u64 buf[8 * RG_MAXW];
+        u64* ui = buf; u64* bn = buf + RG_MAXW; u64* cv = buf + 2 * RG_MAXW; u64* rp = buf + 3 * RG_MAXW;
+        u64* x1 = buf + 4 * RG_MAXW; u64* x2 = buf + 5 * RG_MAXW; u64* raw = buf + 6 * RG_MAXW; u64* mg = buf + 7 * RG_MAXW;
+        if (i == sc->p) { for (int l = 0; l < W; ++l) ui[l] = sc->up[l]; }
+        else { rt_load_planar(raw, LU, u, us, i); rt_sext(ui, W, raw, LU); }
+        rt_mul_lo(bn, ui, sc->Dinv, W);
+        if (sc->sgn > 0) rt_neg(bn, W);
+        rt_load_planar(raw, L, C, ps, (size_t)i * ld + col); rt_sext(cv, W, raw, L);
+        rt_load_planar(raw, L, rowp, rs, col); rt_sext(rp, W, raw, L);
+        rt_mul_lo(x1, sc->A, cv, W);
+        rt_mul_lo(x2, bn, rp, W);
+        rt_add(x1, x2, W);
+        rt_shr(x1, W, sc->t);
+        rt_store_planar(C, ps, (size_t)i * ld + col, x1, L);
+        rt_abs(mg, x1, L);
+        maxb = rt_bitlen_u(mg, L) + 1;
+    }
+    maxb = warp_max(maxb);
+    if ((threadIdx.x & 31) == 0 && maxb) atomicMax(&sc->maxbits_new, maxb);
+}
+
+// after the update: basis bookkeeping, D <- |a|, steepest-edge weight of the leaving column
+__global__ void k_finalize(int* basis, unsigned char* inbasis, int L, u64* G, int n, int LG,
+                           int want_se, Scalars* sc, HostMirror* hm) {
+    if (threadIdx.x || blockIdx.x) return;
+    if (sc->status == ST_RUN) {
+        int r = sc->p - 1;
+        int leaving = basis[r];
+        sc->leaving = leaving;
+        basis[r] = sc->q;
+        inbasis[sc->q] = 1;
+        if (leaving >= 0) {
+            inbasis[leaving] = 0;
+            if (want_se) for (int l = 0; l < LG; ++l) G[(size_t)l * n + leaving] = sc->Gq[l];
+        }
+        for (int l = 0; l < L; ++l) sc->D[l] = sc->Dnew[l];
+        sc->maxbits_carry = sc->maxbits_new;
+        sc->bits_D = rt_bitlen_u(sc->D, L);
+        hm->pivoted = 1; hm->q_done = sc->q; hm->p_done = sc->p; hm->leaving_done = leaving;
+    }
+}
+
+__global__ void k_mirror(Scalars* sc, HostMirror* hm, int L) {
+    if (threadIdx.x || blockIdx.x) return;
+    hm->status = sc->status; hm->q = sc->q; hm->p = sc->p; hm->leaving = sc->leaving;
+    hm->t_next = rt_ctz(sc->D, L);
+    hm->bits_D = sc->bits_D; hm->maxbits_carry = sc->maxbits_carry; hm->predicted = sc->predicted;
+    hm->found = sc->found; hm->sgn = sc->sgn; hm->maxbits_tmp = sc->maxbits_tmp;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K6 work vector  omega_k = sum_{i=1..m} s_i C[i][k]    (w = alpha^T B^-1, carry/mod.rs:575-576;
+// with s = basic costs it is the phase switch -pi = -c_B^T B^-1, carry/mod.rs:226-283)
+// Stage 1: thread = column, loops a chunk of rows, skips rows with s_i = 0; stage 2 sums chunks.
+// ---------------------------------------------------------------------------------------------
+template <int LA, int LB>
+__device__ __forceinline__ void mul_full_ct(u64 (&r)[LA + LB], const u64 (&a)[LA], const u64 (&b)[LB]) {
+    u64 c0 = 0, c1 = 0, c2 = 0;
+#pragma unroll
+    for (int k = 0; k < LA + LB - 1; ++k) {
+#pragma unroll
+        for (int i = 0; i < LA; ++i) {
+            int j = k - i;
+            if (j >= 0 && j < LB) mac3(c0, c1, c2, a[i], b[j]);
+        }
+        r[k] = c0;
+        c0 = c1; c1 = c2; c2 = 0;
+    }
+    r[LA + LB - 1] = c0;
+}
+
+template <int L, int LSRC, int LOUT>
+__global__ void __launch_bounds__(128)
+k_colsum1(const u64* __restrict__ C, size_t ps, int ld, int m, int rows_per_chunk,
+          const u64* __restrict__ s, size_t ss, u64* __restrict__ part, const Scalars* sc) {
+    __shared__ u64 sMag[LSRC];
+    __shared__ int sSign;
+    if (sc->status != ST_RUN) return;
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    int r0 = 1 + blockIdx.y * rows_per_chunk;
+    int r1 = min(m + 1, r0 + rows_per_chunk);
+    u64 acc[LOUT];
+#pragma unroll
+    for (int l = 0; l < LOUT; ++l) acc[l] = 0;
+    for (int i = r0; i < r1; ++i) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            u64 x[LSRC];
+            load_planar<LSRC>(x, s, ss, (size_t)i);
+            bool neg = (i64)x[LSRC - 1] < 0;
+            u64 o = 0;
+            if (neg) {
+                u64 c = 1;
+#pragma unroll
+                for (int l = 0; l < LSRC; ++l) { u64 v = ~x[l] + c; c = (c && v == 0) ? 1 : 0; x[l] = v; }
+            }
+#pragma unroll
+            for (int l = 0; l < LSRC; ++l) { sMag[l] = x[l]; o |= x[l]; }
+            sSign = o == 0 ? 0 : (neg ? -1 : 1);
+        }
+        __syncthreads();
+        int sgn = sSign;
+        if (sgn == 0 || k >= ld) continue;
+        u64 sm[LSRC];
+#pragma unroll
+        for (int l = 0; l < LSRC; ++l) sm[l] = sMag[l];
+        u64 x[L];
+        load_planar<L>(x, C, ps, (size_t)i * ld + k);
+        bool neg = (i64)x[L - 1] < 0;
+        if (neg) {
+            u64 c = 1;
+#pragma unroll
+            for (int l = 0; l < L; ++l) { u64 v = ~x[l] + c; c = (c && v == 0) ? 1 : 0; x[l] = v; }
+            sgn = -sgn;
+        }
+        u64 pr[LSRC + L];
+        mul_full_ct<LSRC, L>(pr, sm, x);
+        // acc +/-= pr (zero extended)
+        if (sgn > 0) {
+            u64 cf = 0;
+#pragma unroll
+            for (int l = 0; l < LOUT; ++l) {
+                u64 b = l < LSRC + L ? pr[l] : 0;
+                u64 v = acc[l] + b; u64 c1 = v < b; u64 v2 = v + cf; u64 c2 = v2 < v;
+                acc[l] = v2; cf = c1 + c2;
+            }
+        } else {
+            u64 bf = 0;
+#pragma unroll
+            for (int l = 0; l < LOUT; ++l) {
+                u64 b = l < LSRC + L ? pr[l] : 0;
+                u64 v = acc[l] - b; u64 b1 = acc[l] < b; u64 v2 = v - bf; u64 b2 = v < bf;
+                acc[l] = v2; bf = b1 + b2;
+            }
+        }
+    }
+    if (k < ld) store_planar<LOUT>(part + (size_t)blockIdx.y * LOUT * ld, (size_t)ld, (size_t)k, acc);
+}
+
+template <int LOUT>
+__global__ void __launch_bounds__(256)
+k_colsum2(const u64* __restrict__ part, int ld, int chunks, int negate, u64* __restrict__ out,
+          Scalars* sc) {
+    if (sc->status != ST_RUN) return;
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    int bl = 0;
+    if (k < ld) {
+        u64 acc[LOUT];
+#pragma unroll
+        for (int l = 0; l < LOUT; ++l) acc[l] = 0;
+        for (int c = 0; c < chunks; ++c) {
+            u64 x[LOUT];
+            load_planar<LOUT>(x, part + (size_t)c * LOUT * ld, (size_t)ld, (size_t)k);
+            add_n<LOUT>(acc, x);
+        }
+        if (negate) {
+            u64 c = 1;
+#pragma unroll
+            for (int l = 0; l < LOUT; ++l) { u64 v = ~acc[l] + c; c = (c && v == 0) ? 1 : 0; acc[l] = v; }
+        }
+        store_planar<LOUT>(out, (size_t)ld, (size_t)k, acc);
+        bl = bitlen_signed<LOUT>(acc);
+    }
+    bl = warp_max(bl);
+    if ((threadIdx.x & 31) == 0 && bl) atomicMax(&sc->maxbits_tmp, bl);
+}
+
+// basic cost of every row as an (m+1)-vector of LSRC = 1 limb (artificial / inert rows: 0)
+__global__ void k_basic_costs(const int* basis, const long long* cost, int m, u64* s) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > m) return;
+    long long c = 0;
+    if (i >= 1) { int j = basis[i - 1]; c = j >= 0 ? cost[j] : 0; }
+    s[i] = (u64)c;
+}
+// row 0 of the carry <- tmprow (truncated to L limbs; caller has checked it fits)
+__global__ void k_store_row0(u64* C, size_t ps, int ld, int L, const u64* tmp, int LT) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= ld) return;
+    for (int l = 0; l < L; ++l) C[(size_t)l * ps + k] = tmp[(size_t)l * ld + k];
+}
+__global__ void k_max_into_carrybits(Scalars* sc) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) sc->maxbits_carry = max(sc->maxbits_carry, sc->maxbits_tmp);
+}
+__global__ void k_reset_tmpbits(Scalars* sc) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) sc->maxbits_tmp = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5 steepest-edge weights.
+//   init (identity carry):  Ghat_j = 1 + |a_j|^2                       (initial_gamma, pivot_rule.rs:299-305)
+//   init (general carry):   Ghat_j = D^2 + sum_i (C[i][1..m] . a_j)^2  block per column
+//   update: Ghat'_j = [a^2 Ghat_j - 2 a nu_j sigma_j + nu_j^2 Ghat_q] / D^2   (after_basis_update :243-296)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_gamma_init_identity(int n, const long long* colptr, const long long* vals,
+                                      const unsigned char* inbasis, u64* G, int LG) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    u64 acc[3] = {0, 0, 0};
+    if (!inbasis[j]) {
+        acc[0] = 1;
+        for (long long k = colptr[j]; k < colptr[j + 1]; ++k) {
+            long long v = vals[k];
+            u64 mg = v < 0 ? (u64)(-v) : (u64)v;
+            mac3(acc[0], acc[1], acc[2], mg, mg);
+        }
+    }
+    for (int l = 0; l < LG; ++l) G[(size_t)l * n + j] = l < 3 ? acc[l] : 0;
+}
+
+template <int L>
+__global__ void __launch_bounds__(128)
+k_gamma_init_general(const u64* __restrict__ C, size_t ps, int ld, int m, int n,
+                     const long long* __restrict__ colptr, const int* __restrict__ rowidx,
+                     const long long* __restrict__ vals, const unsigned char* __restrict__ inbasis,
+                     u64* __restrict__ G, const Scalars* sc) {
+    constexpr int LU = L + 2, LG = 2 * L + 5;
+    __shared__ u64 sAcc[4][LG];
+    int j = blockIdx.x;
+    if (j >= n) return;
+    if (inbasis[j]) {
+        if (threadIdx.x < LG) G[(size_t)threadIdx.x * n + j] = 0;
+        return;
+    }
+    long long k0 = colptr[j], k1 = colptr[j + 1];
+    u64 acc[LG];
+#pragma unroll
+    for (int l = 0; l < LG; ++l) acc[l] = 0;
+    for (int i = 1 + threadIdx.x; i <= m; i += blockDim.x) {
+        u64 nu[LU];
+#pragma unroll
+        for (int l = 0; l < LU; ++l) nu[l] = 0;
+        for (long long k = k0; k < k1; ++k) {
+            u64 x[L];
+            load_planar<L>(x, C, ps, (size_t)i * ld + 1 + rowidx[k]);
+            mac_small<LU, L>(nu, x, vals[k]);
+        }
+        if ((i64)nu[LU - 1] < 0) {
+            u64 c = 1;
+#pragma unroll
+            for (int l = 0; l < LU; ++l) { u64 v = ~nu[l] + c; c = (c && v == 0) ? 1 : 0; nu[l] = v; }
+        }
+        u64 sq[2 * LU];
+        mul_full_ct<LU, LU>(sq, nu, nu);
+        u64 cf = 0;
+#pragma unroll
+        for (int l = 0; l < LG; ++l) {
+            u64 b = l < 2 * LU ? sq[l] : 0;
+            u64 v = acc[l] + b; u64 c1 = v < b; u64 v2 = v + cf; u64 c2 = v2 < v;
+            acc[l] = v2; cf = c1 + c2;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        u64 other[LG];
+#pragma unroll
+        for (int l = 0; l < LG; ++l) other[l] = __shfl_down_sync(0xffffffffu, acc[l], o);
+        add_n<LG>(acc, other);
+    }
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+#pragma unroll
+        for (int l = 0; l < LG; ++l) sAcc[warp][l] = acc[l];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (blockDim.x >> 5); ++w) {
+            u64 other[LG];
+#pragma unroll
+            for (int l = 0; l < LG; ++l) other[l] = sAcc[w][l];
+            add_n<LG>(acc, other);
+        }
+        u64 d[L], d2[2 * L];
+#pragma unroll
+        for (int l = 0; l < L; ++l) d[l] = sc->D[l];
+        mul_full_ct<L, L>(d2, d, d);
+        u64 cf = 0;
+#pragma unroll
+        for (int l = 0; l < LG; ++l) {
+            u64 b = l < 2 * L ? d2[l] : 0;
+            u64 v = acc[l] + b; u64 c1 = v < b; u64 v2 = v + cf; u64 c2 = v2 < v;
+            acc[l] = v2; cf = c1 + c2;
+        }
+        store_planar<LG>(G, (size_t)n, (size_t)j, acc);
+    }
+}
+
+// per-column steepest-edge recurrence (run-time widths: O(n) work, not the hot spot)
+__global__ void __launch_bounds__(128)
+k_gamma_update(int n, int L, const unsigned char* __restrict__ inbasis, const u64* __restrict__ nu,
+               const u64* __restrict__ sigma, u64* __restrict__ G, const Scalars* sc) {
+    if (sc->status != ST_RUN) return;
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    if (inbasis[j] || j == sc->leaving) return;   // entering: None; leaving: set by k_finalize
+    const int LU = L + 2, LS = 2 * L + 6, LG = 2 * L + 5;
+    const int WX = LG + sc->E2;
+    u64 buf[7 * RG_MAXW];
+    u64* raw = buf; u64* nv = buf + RG_MAXW; u64* sg = buf + 2 * RG_MAXW; u64* g = buf + 3 * RG_MAXW;
+    u64* x = buf + 4 * RG_MAXW; u64* y = buf + 5 * RG_MAXW; u64* z = buf + 6 * RG_MAXW;
+    rt_load_planar(raw, LU, nu, n, j);
+    if (rt_is_zero(raw, LU)) {
+        // alpha_j_bar == 0: gamma unchanged, so Ghat' = Ghat * a^2 / D^2
+        rt_load_planar(raw, LG, G, n, j);
+        for (int l = 0; l < WX; ++l) g[l] = l < LG ? raw[l] : 0;
+        rt_mul_lo(x, sc->S1, g, WX);
+        rt_shr(x, WX, sc->t2);
+        rt_store_planar(G, n, j, x, LG);
+        return;
+    }
+    rt_sext(nv, WX, raw, LU);
+    rt_load_planar(raw, LS, sigma, n, j);
+    rt_sext(sg, WX, raw, LS);
+    rt_load_planar(raw, LG, G, n, j);
+    for (int l = 0; l < WX; ++l) g[l] = l < LG ? raw[l] : 0;
+    rt_mul_lo(x, sc->S1, g, WX);          // a^2/D^2 Ghat
+    rt_mul_lo(y, nv, sg, WX);             // nu sigma
+    rt_mul_lo(z, sc->S2, y, WX);          // 2a/D^2 nu sigma
+    rt_sub(x, z, WX);
+    rt_mul_lo(y, nv, nv, WX);             // nu^2
+    rt_mul_lo(z, sc->S3, y, WX);          // Gq/D^2 nu^2
+    rt_add(x, z, WX);
+    rt_shr(x, WX, sc->t2);
+    rt_store_planar(G, n, j, x, LG);
+}
+
+// b_p != 0 ?  (remove_artificial_basis_variables, phase_one.rs:250)
+__global__ void k_bp_nonzero(const u64* C, size_t ps, int ld, int L, Scalars* sc) {
+    if (threadIdx.x || blockIdx.x) return;
+    u64 o = 0;
+    for (int l = 0; l < L; ++l) o |= C[(size_t)l * ps + (size_t)sc->p * ld];
+    sc->bp_nonzero = o != 0;
+}
+
+}  // namespace rg

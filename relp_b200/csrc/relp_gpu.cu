@@ -1,0 +1,697 @@
+// C-ABI implementation of the B200-native exact simplex engine (include/relp_gpu.h).
+// Host orchestration only: every arithmetic step runs in the kernels of kernels.cuh.
+#include <cstdio>
+#include <cstring>
+#include <algorithm>
+#include <vector>
+
+#include "../../include/relp_gpu.h"
+#include "kernels.cuh"
+
+using namespace rg;
+
+#define CK(call)                                                                        \
+    do {                                                                                \
+        cudaError_t e__ = (call);                                                       \
+        if (e__ != cudaSuccess) {                                                       \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);             \
+            return RG_ERR_CUDA;                                                         \
+        }                                                                               \
+    } while (0)
+
+#define RG_TRY(call)                     \
+    do {                                 \
+        int r__ = (call);                \
+        if (r__ != RG_OK) return r__;    \
+    } while (0)
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+static inline int log2i(int L) { int k = 0; while ((1 << k) < L) ++k; return k; }
+
+#define DISPATCH_L(Lv, FN, ...)                                   \
+    switch (Lv) {                                                 \
+        case 1: FN<1>(__VA_ARGS__); break;                        \
+        case 2: FN<2>(__VA_ARGS__); break;                        \
+        case 4: FN<4>(__VA_ARGS__); break;                        \
+        case 8: FN<8>(__VA_ARGS__); break;                        \
+        case 16: FN<16>(__VA_ARGS__); break;                      \
+        default: break;                                           \
+    }
+
+// ------------------------------------------------------------------------------------------------
+// allocation
+// ------------------------------------------------------------------------------------------------
+static void free_dev(void* p) { if (p) cudaFree(p); }
+
+static int alloc_width_buffers(rg_context* ctx, int L) {
+    const size_t ld = ctx->ld;
+    const size_t n = ctx->n;
+    CK(cudaMalloc(&ctx->u, sizeof(u64) * LU_of(L) * ld));
+    CK(cudaMalloc(&ctx->rowp, sizeof(u64) * L * ld));
+    CK(cudaMalloc(&ctx->omega, sizeof(u64) * LW_of(L) * ld));
+    CK(cudaMalloc(&ctx->omega_part, sizeof(u64) * ctx->work_chunks * LW_of(L) * ld));
+    CK(cudaMalloc(&ctx->tmprow, sizeof(u64) * LU_of(L) * ld));
+    CK(cudaMalloc(&ctx->kappa, sizeof(u64) * LU_of(L) * n));
+    CK(cudaMalloc(&ctx->nu, sizeof(u64) * LU_of(L) * n));
+    CK(cudaMalloc(&ctx->sigma, sizeof(u64) * LS_of(L) * n));
+    CK(cudaMemsetAsync(ctx->u, 0, sizeof(u64) * LU_of(L) * ld, ctx->stream));
+    CK(cudaMemsetAsync(ctx->rowp, 0, sizeof(u64) * L * ld, ctx->stream));
+    CK(cudaMemsetAsync(ctx->kappa, 0, sizeof(u64) * LU_of(L) * n, ctx->stream));
+    return RG_OK;
+}
+static void free_width_buffers(rg_context* ctx) {
+    free_dev(ctx->u); free_dev(ctx->rowp); free_dev(ctx->omega); free_dev(ctx->omega_part);
+    free_dev(ctx->tmprow); free_dev(ctx->kappa); free_dev(ctx->nu); free_dev(ctx->sigma);
+    ctx->u = ctx->rowp = ctx->omega = ctx->omega_part = ctx->tmprow = nullptr;
+    ctx->kappa = ctx->nu = ctx->sigma = nullptr;
+}
+
+extern "C" int rg_create(const rg_options* opts, rg_context** out) {
+    if (!out) return RG_ERR_ARG;
+    rg_context* ctx = new rg_context();
+    ctx->device = opts ? opts->device : 0;
+    ctx->rank = opts ? opts->rank : 0;
+    ctx->world = (opts && opts->world > 0) ? opts->world : 1;
+    int L = (opts && opts->initial_limbs) ? opts->initial_limbs : 2;
+    if (!(L == 1 || L == 2 || L == 4 || L == 8 || L == 16)) { delete ctx; return RG_ERR_ARG; }
+    ctx->L = L;
+    *out = ctx;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamCreate(&ctx->stream));   // blocking: orders with the synchronous copies on the null stream
+    CK(cudaMalloc(&ctx->sc, sizeof(Scalars)));
+    CK(cudaMemset(ctx->sc, 0, sizeof(Scalars)));
+    CK(cudaHostAlloc(&ctx->hm, sizeof(HostMirror), cudaHostAllocMapped));
+    memset(ctx->hm, 0, sizeof(HostMirror));
+    CK(cudaHostGetDevicePointer((void**)&ctx->hm_dev, ctx->hm, 0));
+    return RG_OK;
+}
+
+extern "C" int rg_destroy(rg_context* ctx) {
+    if (!ctx) return RG_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    free_width_buffers(ctx);
+    free_dev(ctx->carry); free_dev(ctx->A.colptr); free_dev(ctx->A.rowidx); free_dev(ctx->A.vals);
+    free_dev(ctx->cost); free_dev(ctx->rhs); free_dev(ctx->basis); free_dev(ctx->inbasis);
+    free_dev(ctx->G); free_dev(ctx->cand); free_dev(ctx->sc); free_dev(ctx->svec);
+    if (ctx->hm) cudaFreeHost(ctx->hm);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return RG_OK;
+}
+
+extern "C" const char* rg_last_error(const rg_context* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int rg_load_csc(rg_context* ctx, int32_t m, int32_t n, const int64_t* colptr,
+                           const int32_t* rowidx, const int64_t* vals) {
+    if (!ctx || m <= 0 || n <= 0 || !colptr) return RG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->carry) { ctx->err = "rg_load_csc: context already holds a problem"; return RG_ERR_STATE; }
+    ctx->m = m; ctx->n = n;
+    ctx->ld = ((m + 1 + 15) / 16) * 16;
+    ctx->plane = (size_t)(m + 1) * ctx->ld;
+    long long nnz = colptr[n];
+    ctx->A.nnz = nnz;
+    for (long long j = 0; j < n; ++j)
+        for (long long k = colptr[j]; k < colptr[j + 1]; ++k)
+            if (rowidx[k] < 0 || rowidx[k] >= m) { ctx->err = "rg_load_csc: row index out of range"; return RG_ERR_ARG; }
+    CK(cudaMalloc(&ctx->A.colptr, sizeof(long long) * (n + 1)));
+    CK(cudaMalloc(&ctx->A.rowidx, sizeof(int) * std::max<long long>(nnz, 1)));
+    CK(cudaMalloc(&ctx->A.vals, sizeof(long long) * std::max<long long>(nnz, 1)));
+    CK(cudaMemcpy(ctx->A.colptr, colptr, sizeof(long long) * (n + 1), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->A.rowidx, rowidx, sizeof(int) * nnz, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->A.vals, vals, sizeof(long long) * nnz, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&ctx->cost, sizeof(long long) * n));
+    CK(cudaMemset(ctx->cost, 0, sizeof(long long) * n));
+    CK(cudaMalloc(&ctx->rhs, sizeof(long long) * m));
+    CK(cudaMemset(ctx->rhs, 0, sizeof(long long) * m));
+    CK(cudaMalloc(&ctx->basis, sizeof(int) * m));
+    CK(cudaMalloc(&ctx->inbasis, n));
+    CK(cudaMalloc(&ctx->cand, sizeof(int) * 1024));
+    CK(cudaMalloc(&ctx->svec, sizeof(u64) * ctx->ld));
+    ctx->work_chunks = std::max(1, std::min(64, cdiv(m, 64)));
+    CK(cudaMalloc(&ctx->carry, sizeof(u64) * ctx->L * ctx->plane));
+    CK(cudaMalloc(&ctx->G, sizeof(u64) * LG_of(ctx->L) * n));
+    CK(cudaMemset(ctx->G, 0, sizeof(u64) * LG_of(ctx->L) * n));
+    RG_TRY(alloc_width_buffers(ctx, ctx->L));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return RG_OK;
+}
+
+extern "C" int rg_set_rhs(rg_context* ctx, const int64_t* b) {
+    if (!ctx || !ctx->rhs || !b) return RG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpy(ctx->rhs, b, sizeof(long long) * ctx->m, cudaMemcpyHostToDevice));
+    return RG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch helpers
+// ------------------------------------------------------------------------------------------------
+#define LAUNCH(kernel, grid, block, ...)                                   \
+    do {                                                                   \
+        kernel<<<grid, block, 0, ctx->stream>>>(__VA_ARGS__);              \
+        ctx->launches++;                                                   \
+    } while (0)
+
+static int sync_mirror(rg_context* ctx) {
+    LAUNCH(k_mirror, 1, 1, ctx->sc, ctx->hm_dev, ctx->L);
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    ctx->t_cur = ctx->hm->t_next;
+    return RG_OK;
+}
+
+static void set_status(rg_context* ctx, int st) { LAUNCH(k_set_status, 1, 1, ctx->sc, st); }
+
+template <int L>
+static void launch_price_t(rg_context* ctx) {
+    constexpr int LU = L + 2;
+    LAUNCH((k_coldot<L, LU>), cdiv(ctx->n, 256), 256, ctx->carry, ctx->plane, ctx->n, ctx->A.colptr,
+           ctx->A.rowidx, ctx->A.vals, ctx->inbasis, ctx->cost, 1, L, ctx->kappa, ctx->sc);
+}
+static void launch_price(rg_context* ctx) { DISPATCH_L(ctx->L, launch_price_t, ctx); }
+
+template <class Cmp>
+static void launch_argbest(rg_context* ctx, int count, const Cmp& cmp, int mode) {
+    int nb = std::max(1, std::min(1024, cdiv(count, 256)));
+    LAUNCH((k_argbest1<Cmp>), nb, 256, count, cmp, ctx->cand, ctx->sc);
+    LAUNCH((k_argbest2<Cmp>), 1, 256, nb, cmp, ctx->cand, mode, ctx->sc);
+}
+
+static void launch_select(rg_context* ctx) {
+    PriceView v{ctx->kappa, LU_of(ctx->L), ctx->n, ctx->inbasis};
+    switch (ctx->rule) {
+        case RG_RULE_FIRST_PROFITABLE: launch_argbest(ctx, ctx->n, CmpFirst{v}, 0); break;
+        case RG_RULE_FIRST_PROFITABLE_WITH_MEMORY: launch_argbest(ctx, ctx->n, CmpFirstMem{v, ctx->sc}, 0); break;
+        case RG_RULE_DANTZIG: launch_argbest(ctx, ctx->n, CmpDantzig{v}, 0); break;
+        default: launch_argbest(ctx, ctx->n, CmpSteepest{v, ctx->G, LG_of(ctx->L)}, 0); break;
+    }
+}
+
+template <int L>
+static void launch_ftran_t(rg_context* ctx, int q) {
+    LAUNCH((k_ftran<L>), cdiv((long long)(ctx->m + 1) * 32, 256), 256, ctx->carry, ctx->plane, ctx->ld,
+           ctx->m + 1, ctx->A.colptr, ctx->A.rowidx, ctx->A.vals, ctx->cost, q, ctx->u, (size_t)ctx->ld,
+           ctx->sc);
+}
+static void launch_ftran(rg_context* ctx, int q) { DISPATCH_L(ctx->L, launch_ftran_t, ctx, q); }
+
+static void launch_ratio(rg_context* ctx) {
+    CmpRatio c{ctx->carry, ctx->plane, ctx->ld, ctx->L, ctx->u, (size_t)ctx->ld, LU_of(ctx->L), ctx->basis};
+    launch_argbest(ctx, ctx->m, c, 1);
+}
+
+template <int L>
+static void launch_copyrow_t(rg_context* ctx) {
+    LAUNCH((k_copyrow<L>), cdiv(ctx->ld, 256), 256, ctx->carry, ctx->plane, ctx->ld, ctx->rowp,
+           (size_t)ctx->ld, ctx->sc);
+}
+static void launch_copyrow(rg_context* ctx) { DISPATCH_L(ctx->L, launch_copyrow_t, ctx); }
+
+template <int L>
+static void launch_work_t(rg_context* ctx) {
+    constexpr int LU = L + 2, LW = 2 * L + 4;
+    int rpc = cdiv(ctx->m, ctx->work_chunks);
+    dim3 grid(cdiv(ctx->ld, 128), ctx->work_chunks);
+    LAUNCH((k_colsum1<L, LU, LW>), grid, 128, ctx->carry, ctx->plane, ctx->ld, ctx->m, rpc, ctx->u,
+           (size_t)ctx->ld, ctx->omega_part, ctx->sc);
+    LAUNCH((k_colsum2<LW>), cdiv(ctx->ld, 256), 256, ctx->omega_part, ctx->ld, ctx->work_chunks, 0,
+           ctx->omega, ctx->sc);
+}
+static void launch_work(rg_context* ctx) { DISPATCH_L(ctx->L, launch_work_t, ctx); }
+
+template <int L>
+static void launch_update_t(rg_context* ctx, int E) {
+    constexpr int CP = L <= 4 ? 2 : 1;
+    dim3 grid(cdiv(ctx->ld, 256 * CP), cdiv(ctx->m + 1, 32));
+    if (E == 0) {
+        LAUNCH((k_update<L, 0, CP>), grid, 256, ctx->carry, ctx->plane, ctx->ld, ctx->m + 1, ctx->u,
+               (size_t)ctx->ld, ctx->rowp, (size_t)ctx->ld, ctx->sc);
+    } else if (E == 1) {
+        LAUNCH((k_update<L, 1, CP>), grid, 256, ctx->carry, ctx->plane, ctx->ld, ctx->m + 1, ctx->u,
+               (size_t)ctx->ld, ctx->rowp, (size_t)ctx->ld, ctx->sc);
+    } else if (E == 2) {
+        LAUNCH((k_update<L, 2, CP>), grid, 256, ctx->carry, ctx->plane, ctx->ld, ctx->m + 1, ctx->u,
+               (size_t)ctx->ld, ctx->rowp, (size_t)ctx->ld, ctx->sc);
+    } else {
+        dim3 g2(cdiv(ctx->ld, 128), ctx->m + 1);
+        LAUNCH(k_update_generic, g2, 128, ctx->carry, ctx->plane, ctx->ld, ctx->m + 1, L, ctx->u,
+               (size_t)ctx->ld, ctx->rowp, (size_t)ctx->ld, ctx->sc);
+    }
+}
+static void launch_update(rg_context* ctx, int E) { DISPATCH_L(ctx->L, launch_update_t, ctx, E); }
+
+template <int L>
+static void launch_se_dots_t(rg_context* ctx) {
+    constexpr int LU = L + 2, LW = 2 * L + 4, LS = 2 * L + 6;
+    LAUNCH((k_coldot<L, LU>), cdiv(ctx->n, 256), 256, ctx->rowp, (size_t)ctx->ld, ctx->n, ctx->A.colptr,
+           ctx->A.rowidx, ctx->A.vals, ctx->inbasis, ctx->cost, 0, L, ctx->nu, ctx->sc);
+    LAUNCH((k_coldot<LW, LS>), cdiv(ctx->n, 256), 256, ctx->omega, (size_t)ctx->ld, ctx->n, ctx->A.colptr,
+           ctx->A.rowidx, ctx->A.vals, ctx->inbasis, ctx->cost, 0, L, ctx->sigma, ctx->sc);
+}
+static void launch_se_update(rg_context* ctx) {
+    DISPATCH_L(ctx->L, launch_se_dots_t, ctx);
+    LAUNCH(k_gamma_update, cdiv(ctx->n, 128), 128, ctx->n, ctx->L, ctx->inbasis, ctx->nu, ctx->sigma, ctx->G,
+           ctx->sc);
+}
+
+template <int L>
+static void launch_rowdot_t(rg_context* ctx) {   // nu_j = rowp . a_j
+    constexpr int LU = L + 2;
+    LAUNCH((k_coldot<L, LU>), cdiv(ctx->n, 256), 256, ctx->rowp, (size_t)ctx->ld, ctx->n, ctx->A.colptr,
+           ctx->A.rowidx, ctx->A.vals, ctx->inbasis, ctx->cost, 0, L, ctx->nu, ctx->sc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K9 promotion
+// ------------------------------------------------------------------------------------------------
+static int promote(rg_context* ctx) {
+    int Lold = ctx->L, Lnew = Lold * 2;
+    if (Lnew > RG_MAXL) { ctx->err = "numerators exceed 16 limbs"; return RG_ERR_OVERFLOW; }
+    u64* nc = nullptr;
+    CK(cudaMalloc(&nc, sizeof(u64) * Lnew * ctx->plane));
+    CK(cudaMemcpyAsync(nc, ctx->carry, sizeof(u64) * Lold * ctx->plane, cudaMemcpyDeviceToDevice, ctx->stream));
+    LAUNCH(k_sign_extend, 148 * 8, 256, nc, ctx->plane, ctx->plane, Lold, Lnew);
+    u64* ng = nullptr;
+    CK(cudaMalloc(&ng, sizeof(u64) * LG_of(Lnew) * ctx->n));
+    CK(cudaMemsetAsync(ng, 0, sizeof(u64) * LG_of(Lnew) * ctx->n, ctx->stream));
+    CK(cudaMemcpyAsync(ng, ctx->G, sizeof(u64) * LG_of(Lold) * ctx->n, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    free_dev(ctx->carry); ctx->carry = nc;
+    free_dev(ctx->G); ctx->G = ng;
+    free_width_buffers(ctx);
+    ctx->L = Lnew;
+    RG_TRY(alloc_width_buffers(ctx, Lnew));
+    ctx->promotions++;
+    ctx->have_column = false;
+    return RG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// one basis change on the device.  q < 0: use the selected column sc->q.  fixed_row < 0: ratio test.
+// ------------------------------------------------------------------------------------------------
+static int do_pivot(rg_context* ctx, int q, int fixed_row, bool want_se, bool reselect) {
+    for (;;) {
+        ctx->hm->pivoted = 0;
+        LAUNCH(k_reset_iter, 1, 1, ctx->sc);
+        launch_ftran(ctx, q);
+        if (fixed_row < 0) launch_ratio(ctx);
+        else LAUNCH(k_set_pq, 1, 1, ctx->sc, -2, fixed_row + 1);
+        launch_copyrow(ctx);
+        if (want_se) launch_work(ctx);
+        int E = (ctx->t_cur + 63) / 64;
+        LAUNCH(k_scalars, 1, 1, ctx->u, (size_t)ctx->ld, ctx->L, want_se ? 1 : 0, ctx->G, ctx->n, E, ctx->sc);
+        launch_update(ctx, E);
+        LAUNCH(k_finalize, 1, 1, ctx->basis, ctx->inbasis, ctx->L, ctx->G, ctx->n, LG_of(ctx->L),
+               want_se ? 1 : 0, ctx->sc, ctx->hm_dev);
+        if (want_se) launch_se_update(ctx);
+        if (reselect) { launch_price(ctx); launch_select(ctx); }
+        RG_TRY(sync_mirror(ctx));
+        if (ctx->hm->status == ST_PROMOTE) {
+            RG_TRY(promote(ctx));
+            if (q < 0) {
+                // the selection lives in sc->q and survives; pricing data is rebuilt after the pivot
+            }
+            set_status(ctx, ST_RUN);
+            continue;
+        }
+        if (ctx->hm->status == ST_FATAL) {
+            ctx->err = "numerators exceed 16 limbs (or kernel variant mismatch)";
+            return RG_ERR_OVERFLOW;
+        }
+        if (ctx->hm->pivoted) {
+            ctx->pivots++;
+            ctx->pivots_at[log2i(ctx->L)]++;
+            ctx->identity_carry = false;
+        }
+        return RG_OK;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// constructors
+// ------------------------------------------------------------------------------------------------
+extern "C" int rg_init_identity_basis(rg_context* ctx, const int32_t* basis, const int64_t* cost) {
+    if (!ctx || !ctx->carry || !basis) return RG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const int m = ctx->m, n = ctx->n;
+    for (int i = 0; i < m; ++i)
+        if (basis[i] >= n) { ctx->err = "rg_init_identity_basis: column id out of range"; return RG_ERR_ARG; }
+    CK(cudaMemcpy(ctx->basis, basis, sizeof(int) * m, cudaMemcpyHostToDevice));
+    if (cost) CK(cudaMemcpy(ctx->cost, cost, sizeof(long long) * n, cudaMemcpyHostToDevice));
+    else CK(cudaMemset(ctx->cost, 0, sizeof(long long) * n));
+    CK(cudaMemsetAsync(ctx->inbasis, 0, n, ctx->stream));
+    LAUNCH(k_zero, 148 * 8, 256, ctx->carry, (size_t)ctx->L * ctx->plane);
+    LAUNCH(k_init_identity, cdiv(m, 256), 256, ctx->carry, ctx->plane, ctx->ld, m, ctx->L, ctx->rhs,
+           ctx->basis, ctx->sc);
+    LAUNCH(k_init_scalars, 1, 1, ctx->carry, ctx->plane, m, ctx->L, ctx->rhs, ctx->basis, ctx->sc);
+    LAUNCH(k_set_inbasis, cdiv(m, 256), 256, ctx->inbasis, ctx->basis, m);
+    ctx->identity_carry = true;
+    ctx->rule_ready = false; ctx->have_column = false; ctx->selected = false;
+    ctx->t_cur = 0;
+    RG_TRY(sync_mirror(ctx));
+    if (cost) {
+        // starting directly in phase two: -pi = -c_B^T I, -obj = -c_B b
+        bool any = false;
+        for (int i = 0; i < m; ++i) if (basis[i] >= 0 && cost[basis[i]] != 0) any = true;
+        if (any) return rg_phase_switch(ctx, cost);
+    }
+    return RG_OK;
+}
+
+template <int L>
+static void launch_phase_sums_t(rg_context* ctx) {
+    constexpr int LU = L + 2;
+    int rpc = cdiv(ctx->m, ctx->work_chunks);
+    dim3 grid(cdiv(ctx->ld, 128), ctx->work_chunks);
+    LAUNCH((k_colsum1<L, 1, LU>), grid, 128, ctx->carry, ctx->plane, ctx->ld, ctx->m, rpc, ctx->svec,
+           (size_t)ctx->ld, ctx->omega_part, ctx->sc);
+    LAUNCH((k_colsum2<LU>), cdiv(ctx->ld, 256), 256, ctx->omega_part, ctx->ld, ctx->work_chunks, 1,
+           ctx->tmprow, ctx->sc);
+}
+
+extern "C" int rg_phase_switch(rg_context* ctx, const int64_t* cost) {
+    if (!ctx || !ctx->carry || !cost) return RG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpy(ctx->cost, cost, sizeof(long long) * ctx->n, cudaMemcpyHostToDevice));
+    set_status(ctx, ST_RUN);
+    for (;;) {
+        LAUNCH(k_basic_costs, cdiv(ctx->m + 1, 256), 256, ctx->basis, ctx->cost, ctx->m, ctx->svec);
+        LAUNCH(k_reset_tmpbits, 1, 1, ctx->sc);
+        DISPATCH_L(ctx->L, launch_phase_sums_t, ctx);
+        RG_TRY(sync_mirror(ctx));
+        if (ctx->hm->maxbits_tmp > 64 * ctx->L - 1) { RG_TRY(promote(ctx)); continue; }
+        break;
+    }
+    LAUNCH(k_store_row0, cdiv(ctx->ld, 256), 256, ctx->carry, ctx->plane, ctx->ld, ctx->L, ctx->tmprow,
+           LU_of(ctx->L));
+    LAUNCH(k_max_into_carrybits, 1, 1, ctx->sc);
+    ctx->rule_ready = false; ctx->have_column = false; ctx->selected = false;
+    RG_TRY(sync_mirror(ctx));
+    return RG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pivot rule
+// ------------------------------------------------------------------------------------------------
+template <int L>
+static void launch_gamma_general_t(rg_context* ctx) {
+    LAUNCH((k_gamma_init_general<L>), ctx->n, 128, ctx->carry, ctx->plane, ctx->ld, ctx->m, ctx->n,
+           ctx->A.colptr, ctx->A.rowidx, ctx->A.vals, ctx->inbasis, ctx->G, ctx->sc);
+}
+
+extern "C" int rg_rule_new(rg_context* ctx, int32_t rule) {
+    if (!ctx || !ctx->carry || rule < 0 || rule > 3) return RG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    ctx->rule = rule;
+    set_status(ctx, ST_RUN);
+    LAUNCH(k_set_pq, 1, 1, ctx->sc, -1, -1);
+    if (rule == RG_RULE_STEEPEST_EDGE) {
+        if (ctx->identity_carry) {
+            LAUNCH(k_gamma_init_identity, cdiv(ctx->n, 256), 256, ctx->n, ctx->A.colptr, ctx->A.vals,
+                   ctx->inbasis, ctx->G, LG_of(ctx->L));
+        } else {
+            DISPATCH_L(ctx->L, launch_gamma_general_t, ctx);
+        }
+    }
+    cudaMemsetAsync(&ctx->sc->last_selected, 0xff, sizeof(int), ctx->stream);
+    ctx->rule_ready = true;
+    ctx->selected = false;
+    RG_TRY(sync_mirror(ctx));
+    return RG_OK;
+}
+
+static int to_step_status(int dev) {
+    return dev == ST_OPTIMAL ? RG_STEP_OPTIMAL : (dev == ST_UNBOUNDED ? RG_STEP_UNBOUNDED : RG_STEP_PIVOTED);
+}
+
+extern "C" int rg_select_primal_pivot_column(rg_context* ctx, int32_t* status, int32_t* q) {
+    if (!ctx || !ctx->carry || !status || !q) return RG_ERR_ARG;
+    if (!ctx->rule_ready) { ctx->err = "rg_rule_new has not been called for this phase"; return RG_ERR_STATE; }
+    CK(cudaSetDevice(ctx->device));
+    set_status(ctx, ST_RUN);
+    launch_price(ctx);
+    launch_select(ctx);
+    RG_TRY(sync_mirror(ctx));
+    *status = to_step_status(ctx->hm->status);
+    *q = ctx->hm->q;
+    ctx->selected = ctx->hm->status == ST_RUN;
+    return RG_OK;
+}
+
+extern "C" int rg_generate_column(rg_context* ctx, int32_t q) {
+    if (!ctx || !ctx->carry || q < 0 || q >= ctx->n) return RG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    set_status(ctx, ST_RUN);
+    LAUNCH(k_reset_iter, 1, 1, ctx->sc);
+    LAUNCH(k_set_pq, 1, 1, ctx->sc, q, -1);
+    launch_ftran(ctx, q);
+    RG_TRY(sync_mirror(ctx));
+    ctx->have_column = true;
+    return RG_OK;
+}
+
+extern "C" int rg_select_primal_pivot_row(rg_context* ctx, int32_t* status, int32_t* row) {
+    if (!ctx || !ctx->carry || !status || !row) return RG_ERR_ARG;
+    if (!ctx->have_column) { ctx->err = "no pivot column generated"; return RG_ERR_STATE; }
+    CK(cudaSetDevice(ctx->device));
+    set_status(ctx, ST_RUN);
+    launch_ratio(ctx);
+    RG_TRY(sync_mirror(ctx));
+    *status = ctx->hm->status == ST_UNBOUNDED ? RG_STEP_UNBOUNDED : RG_STEP_PIVOTED;
+    *row = ctx->hm->p - 1;
+    return RG_OK;
+}
+
+extern "C" int rg_bring_into_basis(rg_context* ctx, int32_t q, int32_t row, int32_t update_rule,
+                                   rg_pivot_info* info) {
+    if (!ctx || !ctx->carry || q < 0 || q >= ctx->n || row < 0 || row >= ctx->m) return RG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    set_status(ctx, ST_RUN);
+    LAUNCH(k_set_pq, 1, 1, ctx->sc, q, -1);
+    bool want_se = update_rule && ctx->rule == RG_RULE_STEEPEST_EDGE && ctx->rule_ready;
+    RG_TRY(do_pivot(ctx, q, row, want_se, false));
+    ctx->have_column = false; ctx->selected = false;
+    if (info) {
+        info->status = RG_STEP_PIVOTED;
+        info->entering = ctx->hm->q_done; info->row = ctx->hm->p_done - 1; info->leaving = ctx->hm->leaving_done;
+    }
+    return RG_OK;
+}
+
+extern "C" int rg_iterate(rg_context* ctx, int64_t max_pivots, rg_pivot_info* trace, int64_t* n_done,
+                          int32_t* status) {
+    if (!ctx || !ctx->carry || !n_done || !status) return RG_ERR_ARG;
+    if (!ctx->rule_ready) { ctx->err = "rg_rule_new has not been called for this phase"; return RG_ERR_STATE; }
+    CK(cudaSetDevice(ctx->device));
+    *n_done = 0;
+    const bool want_se = ctx->rule == RG_RULE_STEEPEST_EDGE;
+    if (!ctx->selected) {
+        set_status(ctx, ST_RUN);
+        launch_price(ctx);
+        launch_select(ctx);
+        RG_TRY(sync_mirror(ctx));
+        if (ctx->hm->status != ST_RUN) { *status = to_step_status(ctx->hm->status); return RG_OK; }
+        ctx->selected = true;
+    }
+    while (*n_done < max_pivots) {
+        RG_TRY(do_pivot(ctx, -1, -1, want_se, true));
+        if (ctx->hm->pivoted) {
+            if (trace) {
+                rg_pivot_info& t = trace[*n_done];
+                t.status = RG_STEP_PIVOTED; t.entering = ctx->hm->q_done; t.row = ctx->hm->p_done - 1;
+                t.leaving = ctx->hm->leaving_done;
+            }
+            (*n_done)++;
+        }
+        if (ctx->hm->status != ST_RUN) {
+            ctx->selected = false;
+            *status = to_step_status(ctx->hm->status);
+            return RG_OK;
+        }
+    }
+    *status = RG_STEP_PIVOTED;
+    return RG_OK;
+}
+
+extern "C" int rg_remove_artificial_row(rg_context* ctx, int32_t row, rg_pivot_info* info) {
+    if (!ctx || !ctx->carry || row < 0 || row >= ctx->m || !info) return RG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    set_status(ctx, ST_RUN);
+    LAUNCH(k_reset_iter, 1, 1, ctx->sc);
+    LAUNCH(k_set_pq, 1, 1, ctx->sc, -2, row + 1);
+    LAUNCH(k_bp_nonzero, 1, 1, ctx->carry, ctx->plane, ctx->ld, ctx->L, ctx->sc);
+    launch_price(ctx);
+    launch_copyrow(ctx);
+    DISPATCH_L(ctx->L, launch_rowdot_t, ctx);
+    PriceView v{ctx->kappa, LU_of(ctx->L), ctx->n, ctx->inbasis};
+    launch_argbest(ctx, ctx->n, CmpArtificial{v, ctx->nu, ctx->sc}, 2);
+    RG_TRY(sync_mirror(ctx));
+    int q = ctx->hm->found;
+    ctx->selected = false; ctx->have_column = false;
+    if (q < 0) {
+        info->status = RG_STEP_OPTIMAL; info->entering = -1; info->row = row; info->leaving = 0;
+        return RG_OK;
+    }
+    LAUNCH(k_set_pq, 1, 1, ctx->sc, q, -1);
+    RG_TRY(do_pivot(ctx, q, row, false, false));
+    info->status = RG_STEP_PIVOTED;
+    info->entering = ctx->hm->q_done; info->row = ctx->hm->p_done - 1; info->leaving = ctx->hm->leaving_done;
+    return RG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// exports
+// ------------------------------------------------------------------------------------------------
+__global__ void k_gather(u64* out, const u64* base, size_t stride, size_t idx0, size_t step, int count,
+                         int nl) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    for (int l = 0; l < nl; ++l) out[(size_t)i * nl + l] = base[(size_t)l * stride + idx0 + (size_t)i * step];
+}
+
+static int export_planar(rg_context* ctx, const u64* base, size_t stride, size_t idx0, size_t step,
+                         int count, int nl, uint64_t* out) {
+    u64* tmp = nullptr;
+    CK(cudaMalloc(&tmp, sizeof(u64) * (size_t)count * nl));
+    LAUNCH(k_gather, cdiv(count, 256), 256, tmp, base, stride, idx0, step, count, nl);
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy(out, tmp, sizeof(u64) * (size_t)count * nl, cudaMemcpyDeviceToHost));
+    cudaFree(tmp);
+    return RG_OK;
+}
+
+extern "C" int rg_get_limbs(rg_context* ctx, int32_t* limbs) {
+    if (!ctx || !limbs) return RG_ERR_ARG;
+    *limbs = ctx->L;
+    return RG_OK;
+}
+extern "C" int rg_get_denominator(rg_context* ctx, uint64_t* out) {
+    if (!ctx || !ctx->carry || !out) return RG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy(out, ctx->sc->D, sizeof(u64) * ctx->L, cudaMemcpyDeviceToHost));
+    return RG_OK;
+}
+extern "C" int rg_get_basis(rg_context* ctx, int32_t* basis) {
+    if (!ctx || !ctx->carry || !basis) return RG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy(basis, ctx->basis, sizeof(int) * ctx->m, cudaMemcpyDeviceToHost));
+    return RG_OK;
+}
+extern "C" int rg_get_b(rg_context* ctx, uint64_t* out) {
+    if (!ctx || !ctx->carry || !out) return RG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    return export_planar(ctx, ctx->carry, ctx->plane, (size_t)ctx->ld, (size_t)ctx->ld, ctx->m, ctx->L, out);
+}
+extern "C" int rg_get_minus_objective(rg_context* ctx, uint64_t* out) {
+    if (!ctx || !ctx->carry || !out) return RG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    return export_planar(ctx, ctx->carry, ctx->plane, 0, 1, 1, ctx->L, out);
+}
+extern "C" int rg_get_minus_pi(rg_context* ctx, uint64_t* out) {
+    if (!ctx || !ctx->carry || !out) return RG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    return export_planar(ctx, ctx->carry, ctx->plane, 1, 1, ctx->m, ctx->L, out);
+}
+extern "C" int rg_get_basis_inverse_row(rg_context* ctx, int32_t row, uint64_t* out) {
+    if (!ctx || !ctx->carry || !out || row < 0 || row >= ctx->m) return RG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    return export_planar(ctx, ctx->carry, ctx->plane, (size_t)(row + 1) * ctx->ld + 1, 1, ctx->m, ctx->L, out);
+}
+extern "C" int rg_get_pivot_column(rg_context* ctx, uint64_t* out) {
+    if (!ctx || !ctx->carry || !out) return RG_ERR_ARG;
+    if (!ctx->have_column) { ctx->err = "no pivot column generated"; return RG_ERR_STATE; }
+    CK(cudaSetDevice(ctx->device));
+    return export_planar(ctx, ctx->u, (size_t)ctx->ld, 1, 1, ctx->m, LU_of(ctx->L), out);
+}
+extern "C" int rg_get_relative_costs(rg_context* ctx, uint64_t* out) {
+    if (!ctx || !ctx->carry || !out) return RG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    set_status(ctx, ST_RUN);
+    launch_price(ctx);
+    ctx->selected = false;
+    return export_planar(ctx, ctx->kappa, (size_t)ctx->n, 0, 1, ctx->n, LU_of(ctx->L), out);
+}
+extern "C" int rg_get_gamma(rg_context* ctx, uint64_t* out) {
+    if (!ctx || !ctx->carry || !out) return RG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    return export_planar(ctx, ctx->G, (size_t)ctx->n, 0, 1, ctx->n, LG_of(ctx->L), out);
+}
+extern "C" int rg_get_stats(rg_context* ctx, rg_stats* out) {
+    if (!ctx || !out) return RG_ERR_ARG;
+    memset(out, 0, sizeof(*out));
+    out->pivots = ctx->pivots; out->promotions = ctx->promotions; out->limbs = ctx->L;
+    out->kernel_launches = ctx->launches;
+    if (ctx->hm) { out->max_bits = ctx->hm->maxbits_carry; out->denominator_bits = ctx->hm->bits_D; }
+    for (int k = 0; k < 5; ++k) out->pivots_at_limbs[k] = ctx->pivots_at[k];
+    return RG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// debug / self-test hooks (used by tests/test_gpu_bigint.py and scripts/debug_gpu.py only)
+// ------------------------------------------------------------------------------------------------
+extern "C" int rg_debug_scalars(rg_context* ctx, void* out, int64_t bytes) {
+    if (!ctx || !out) return RG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    size_t nbytes = std::min<size_t>((size_t)bytes, sizeof(Scalars));
+    CK(cudaMemcpy(out, ctx->sc, nbytes, cudaMemcpyDeviceToHost));
+    return (int)sizeof(Scalars);
+}
+extern "C" int rg_debug_vector(rg_context* ctx, int32_t which, uint64_t* out) {
+    if (!ctx || !ctx->carry || !out) return RG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (which == 0) return export_planar(ctx, ctx->u, (size_t)ctx->ld, 0, 1, ctx->m + 1, LU_of(ctx->L), out);
+    if (which == 1) return export_planar(ctx, ctx->rowp, (size_t)ctx->ld, 0, 1, ctx->m + 1, ctx->L, out);
+    if (which == 2) return export_planar(ctx, ctx->omega, (size_t)ctx->ld, 0, 1, ctx->m + 1, LW_of(ctx->L), out);
+    return RG_ERR_ARG;
+}
+
+// op 0: mul_lo<W>(a,b); 1: mul2_lo<W>(a,b,c,d); 2: acc(c, W limbs) += a(W-2 limbs.. see below) * s;
+// 3: rt_inv_odd(a) mod 2^(64W); 4: mul_full_ct<W,W>(a,b) -> 2W limbs; 5: rt_cmp_prod sign(a*b - c*d)
+template <int W>
+__global__ void k_selftest(int op, const u64* a, const u64* b, const u64* c, const u64* d, long long s,
+                           u64* out) {
+    u64 x[W], y[W], z[W], w[W], r[2 * W];
+    u64 big[5 * RG_MAXW];
+    for (int l = 0; l < W; ++l) { x[l] = a[l]; y[l] = b[l]; z[l] = c[l]; w[l] = d[l]; }
+    for (int l = 0; l < 2 * W; ++l) r[l] = 0;
+    if (op == 0) { u64 o[W]; mul_lo<W>(o, x, y); for (int l = 0; l < W; ++l) r[l] = o[l]; }
+    else if (op == 1) { u64 o[W]; mul2_lo<W>(o, x, y, z, w); for (int l = 0; l < W; ++l) r[l] = o[l]; }
+    else if (op == 2) {
+        u64 acc[W + 2];
+        for (int l = 0; l < W + 2; ++l) acc[l] = l < W ? z[l] : ((i64)z[W - 1] < 0 ? ~0ull : 0ull);
+        mac_small<W + 2, W>(acc, x, s);
+        for (int l = 0; l < W + 2 && l < 2 * W; ++l) r[l] = acc[l];
+    } else if (op == 3) { u64* o = big; rt_inv_odd(o, x, W, W, big + RG_MAXW); for (int l = 0; l < W; ++l) r[l] = o[l]; }
+    else if (op == 4) { mul_full_ct<W, W>(r, x, y); }
+    else if (op == 5) { r[0] = (u64)(i64)rt_cmp_prod(x, W, y, W, z, W, w, W, big); }
+    for (int l = 0; l < 2 * W; ++l) out[l] = r[l];
+}
+
+extern "C" int rg_selftest(int32_t op, int32_t W, const uint64_t* a, const uint64_t* b, const uint64_t* c,
+                           const uint64_t* d, int64_t s, uint64_t* out /* 2W words */) {
+    u64* dev = nullptr;
+    if (cudaMalloc(&dev, sizeof(u64) * 6 * W) != cudaSuccess) return RG_ERR_CUDA;
+    cudaMemcpy(dev, a, sizeof(u64) * W, cudaMemcpyHostToDevice);
+    cudaMemcpy(dev + W, b, sizeof(u64) * W, cudaMemcpyHostToDevice);
+    cudaMemcpy(dev + 2 * W, c, sizeof(u64) * W, cudaMemcpyHostToDevice);
+    cudaMemcpy(dev + 3 * W, d, sizeof(u64) * W, cudaMemcpyHostToDevice);
+    switch (W) {
+        case 1: k_selftest<1><<<1, 1>>>(op, dev, dev + W, dev + 2 * W, dev + 3 * W, s, dev + 4 * W); break;
+        case 2: k_selftest<2><<<1, 1>>>(op, dev, dev + W, dev + 2 * W, dev + 3 * W, s, dev + 4 * W); break;
+        case 3: k_selftest<3><<<1, 1>>>(op, dev, dev + W, dev + 2 * W, dev + 3 * W, s, dev + 4 * W); break;
+        case 4: k_selftest<4><<<1, 1>>>(op, dev, dev + W, dev + 2 * W, dev + 3 * W, s, dev + 4 * W); break;
+        case 5: k_selftest<5><<<1, 1>>>(op, dev, dev + W, dev + 2 * W, dev + 3 * W, s, dev + 4 * W); break;
+        case 9: k_selftest<9><<<1, 1>>>(op, dev, dev + W, dev + 2 * W, dev + 3 * W, s, dev + 4 * W); break;
+        case 17: k_selftest<17><<<1, 1>>>(op, dev, dev + W, dev + 2 * W, dev + 3 * W, s, dev + 4 * W); break;
+        default: cudaFree(dev); return RG_ERR_ARG;
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaMemcpy(out, dev + 4 * W, sizeof(u64) * 2 * W, cudaMemcpyDeviceToHost);
+    cudaFree(dev);
+    return e == cudaSuccess ? RG_OK : RG_ERR_CUDA;
+}

@@ -1,0 +1,159 @@
+"""GPU parity: the CUDA engine (through the C ABI) against the CPU oracle, bit-exact.
+
+Compared per case: status, the full pivot trace (phase, entering, row, leaving), iteration count,
+exact objective and exact primal solution -- for all four pivot rules, through both the fused
+`rg_iterate` loop and the trait-shaped call sequence.
+"""
+from fractions import Fraction as F
+
+import numpy as np
+import pytest
+
+from oracle import relp_oracle as ro
+from tests.common import oracle_trace, problem_from_provider, provider_from_problem
+
+pytestmark = pytest.mark.gpu
+
+RULE_NAMES = ["first_profitable", "first_profitable_with_memory", "dantzig", "steepest_edge"]
+
+
+def check(provider=None, problem=None, rules=RULE_NAMES, modes=(True, False), initial_limbs=0):
+    import relp_b200
+    if problem is None:
+        problem = problem_from_provider(provider)
+    if provider is None:
+        provider = provider_from_problem(problem)
+    for rule in rules:
+        ores, otrace = oracle_trace(provider, rule)
+        for fused in modes:
+            g = relp_b200.solve_relaxation(problem, rule=rule, fused=fused, initial_limbs=initial_limbs)
+            tag = f"rule={rule} fused={fused}"
+            assert g.status == ores.status, tag
+            assert g.trace == otrace, tag
+            assert g.pivots == len(otrace), tag
+            if ores.status == "optimal":
+                assert g.objective == ores.objective, tag
+                assert g.bfs == ores.bfs, tag
+            assert sorted(g.rows_removed) == sorted(ores.rows_removed), tag
+    return g
+
+
+def test_problem_2():
+    from tests.test_oracle_golden import problem_2
+    g = check(problem_2())
+    assert g.objective == F(9, 2)
+    assert g.bfs == [(1, F(1, 2)), (3, F(5, 2)), (4, F(3, 2))]
+
+
+def test_problem_1():
+    from tests.test_oracle_golden import problem_1
+    g = check(problem_1())
+    assert g.objective == 58
+    assert g.bfs == [(0, F(4)), (2, F(6)), (5, F(2))]
+
+
+def test_max_flow_example():
+    adj = ro.adjacency_from_rows([[0, 0, 0, 0], [2, 0, 0, 0], [1, 1, 0, 0], [0, 1, 2, 0]])
+    g = check(ro.MaxFlowPrimal(adj, 0, 3))
+    dense = [0] * 10
+    for j, v in g.bfs:
+        dense[j] = v
+    assert dense == [2, 1, 1, 1, 2, 0, 0, 0, 0, 0]
+
+
+def test_shortest_path_example_fully_artificial():
+    adj = ro.adjacency_from_rows([[0, 0, 0, 0], [1, 0, 0, 0], [2, 2, 0, 0], [0, 3, 1, 0]])
+    g = check(ro.ShortestPathPrimal(adj, 0, 3))
+    dense = [0] * 5
+    for j, v in g.bfs:
+        dense[j] = v
+    assert dense == [0, 1, 0, 0, 1]
+
+
+def random_matrix_data(rng, nv, counts, density=0.6, ub_prob=0.3, lo=-9, hi=9):
+    """A random integer MatrixData (reference matrix_data.rs layout): eq, range, <=, >= rows."""
+    n_eq, n_rng, n_up, n_lo = counts
+    mc = n_eq + n_rng + n_up + n_lo
+    rows = []
+    for _ in range(mc):
+        row = [int(rng.integers(lo, hi + 1)) if rng.random() < density else 0 for _ in range(nv)]
+        rows.append(row)
+    x0 = [int(rng.integers(0, 4)) for _ in range(nv)]       # a feasible point => feasible LP (mostly)
+    b = []
+    for i, row in enumerate(rows):
+        ax = sum(a * x for a, x in zip(row, x0))
+        if i < n_eq:
+            v = ax
+        elif i < n_eq + n_rng:
+            v = ax + int(rng.integers(0, 3))
+        elif i < n_eq + n_rng + n_up:
+            v = ax + int(rng.integers(0, 5))
+        else:
+            v = ax - int(rng.integers(0, 5))
+        if v < 0:                                           # make_b_non_negative
+            rows[i] = [-a for a in row]
+            v = -v
+            # flipping an inequality swaps its type; keep the row in its group by re-drawing slack sign
+            if i >= n_eq + n_rng:
+                rows[i] = [-a for a in rows[i]]
+                v = abs(ax) + 1 if i < n_eq + n_rng + n_up else max(0, abs(ax) - 1)
+        b.append(v)
+    ranges = [int(rng.integers(1, 6)) for _ in range(n_rng)]
+    variables = [ro.Variable(int(rng.integers(-9, 10)),
+                             int(rng.integers(1, 8)) if rng.random() < ub_prob else None)
+                 for _ in range(nv)]
+    cols = ro.columns_from_rows(rows, nv)
+    return ro.MatrixData(cols, b, ranges, n_eq, n_rng, n_up, n_lo, variables)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_small_lps(seed):
+    rng = np.random.default_rng(1000 + seed)
+    nv = int(rng.integers(3, 9))
+    counts = tuple(int(rng.integers(0, 4)) for _ in range(4))
+    if sum(counts) == 0:
+        counts = (1, 0, 1, 0)
+    check(random_matrix_data(rng, nv, counts))
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_random_rank_deficient(seed):
+    rng = np.random.default_rng(2000 + seed)
+    md = random_matrix_data(rng, 5, (3, 0, 1, 1), ub_prob=0.0)
+    # duplicate an equality row => redundant constraint (Rank::Deficient path)
+    cols = [[(i, v) for i, v in c] for c in md.constraint_columns]
+    rows = [[0] * 5 for _ in range(len(md.b))]
+    for j, c in enumerate(cols):
+        for i, v in c:
+            rows[i][j] = v
+    rows.insert(1, list(rows[0]))
+    b = list(md.b)
+    b.insert(1, b[0])
+    md2 = ro.MatrixData(ro.columns_from_rows(rows, 5), b, [], 4, 0, 1, 1, md.variables)
+    check(md2)
+
+
+@pytest.mark.parametrize("limbs", [1, 2, 4, 8, 16])
+def test_all_limb_widths_agree(limbs):
+    rng = np.random.default_rng(77)
+    check(random_matrix_data(rng, 7, (2, 1, 2, 1)), rules=["steepest_edge", "dantzig"], modes=(True,),
+          initial_limbs=limbs)
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_bounded_lp_small_with_promotions(seed):
+    """Synthetic recipe of configs 4/5 at oracle-sized dimensions; starts at 1 limb so the run
+    crosses several width promotions (K9)."""
+    from relp_b200.generators import bounded_lp
+    import relp_b200
+    prob = bounded_lp(40, 60, k_bounding=12, nnz_per_col=4, seed=seed)
+    g = check(problem=prob, rules=["steepest_edge", "dantzig"], modes=(True,), initial_limbs=1)
+    assert g.stats["promotions"] >= 1
+    prob = bounded_lp(30, 40, k_bounding=10, dense=True, seed=seed)
+    check(problem=prob, rules=["steepest_edge"], modes=(True,), initial_limbs=1)
+
+
+def test_max_flow_random_graph():
+    from relp_b200.generators import max_flow
+    prob = max_flow(n_vertices=24, out_degree=3, seed=3, max_capacity=9)
+    check(problem=prob, rules=["steepest_edge", "dantzig"], modes=(True,))
