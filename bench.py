@@ -1,0 +1,293 @@
+#!/usr/bin/env python
+"""Benchmark of the exact simplex hot path (BASELINE.json metric: exact simplex pivots/sec).
+
+One "step" = one complete exact solve (time-to-optimal) of the workload's LP: every pivot runs the
+full hot path (pricing, pivot column, ratio test, rank-1 carry update, steepest-edge update).
+`value` = pivots / device time with the problem resident in HBM; `e2e` = the same solve through the
+C ABI from host buffers (create, upload, solve, result download inside the timed region).
+
+  python bench.py --gpus N --steps K --warmup W [--workload sparse4k] [--impl reference]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (m, n_struct, K bounding rows, dense, rule)
+    "sparse4k": dict(m=4096, n_struct=8192, k_bounding=90, dense=False, nnz_per_col=8),      # config 4
+    "dense16k": dict(m=16384, n_struct=32768, k_bounding=160, dense=True, nnz_per_col=0),    # config 5
+    "sparse1k": dict(m=1024, n_struct=2048, k_bounding=60, dense=False, nnz_per_col=8),      # quick check
+}
+
+
+def make_problem(name, seed):
+    from relp_b200.generators import bounded_lp
+    w = WORKLOADS[name]
+    return bounded_lp(w["m"], w["n_struct"], k_bounding=w["k_bounding"], nnz_per_col=w["nnz_per_col"],
+                      dense=w["dense"], seed=seed)
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                               f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_baseline(problem, rule, budget_s=15.0):
+    """The oracle port timed on this box's host cores (1 thread: relp is single-threaded) on a
+    bounded sample: the first P pivots of the same workload and trace."""
+    try:
+        from oracle import fast_oracle
+        if fast_oracle.available():
+            return fast_oracle.timed_sample(problem, rule, budget_s)
+    except ImportError:
+        pass
+    from oracle import relp_oracle as ro
+    from tests.common import provider_from_problem
+    provider = provider_from_problem(problem)
+    t0 = time.perf_counter()
+    probe = 3
+    trace = ro.Trace(limit=probe)
+    try:
+        ro.solve_relaxation(provider, rule, trace)
+    except ro.PivotLimit:
+        pass
+    t_probe = time.perf_counter() - t0
+    done = len(trace.pivots)
+    per = max(t_probe / max(done, 1), 1e-6)
+    P = int(max(probe, min(10000, budget_s / per)))
+    t0 = time.perf_counter()
+    trace = ro.Trace(limit=P)
+    try:
+        ro.solve_relaxation(provider, rule, trace)
+    except ro.PivotLimit:
+        pass
+    dt = time.perf_counter() - t0
+    n = len(trace.pivots)
+    return {"value": n / dt, "unit": "pivots/s", "cores": 1, "kind": "port",
+            "sample": f"first {n} pivots of the same LP and trace (incl. rule initialisation), "
+                      f"Python fractions.Fraction oracle, {dt:.1f} s"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port; the Rust reference cannot be built in
+    this image) on the box's host cores, same config/metric."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    prob = make_problem(args.workload, 0)
+    total_p, total_t, last = 0.0, 0.0, None
+    for step in range(args.warmup + args.steps):
+        budget = 10.0 if step >= args.warmup else 2.0
+        t0 = time.perf_counter()
+        last = cpu_baseline(prob, args.rule, budget_s=budget)
+        dt = time.perf_counter() - t0
+        if step >= args.warmup:
+            total_t += dt
+            total_p += last["value"]
+    value = total_p / max(args.steps, 1)
+    line = {
+        "impl": "reference", "metric": "exact simplex pivots/sec", "value": value, "unit": "pivots/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1000.0 * total_t / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "exact rational (arbitrary precision)", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": dict(last, value=value),
+        "e2e": {"value": value, "unit": "pivots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, world):
+    w = WORKLOADS[args.workload]
+    return {"workload": f"{args.workload}: synthetic bounded integer LP m={w['m']} n={w['n_struct']}+{w['m']} "
+                        f"slacks, K={w['k_bounding']} bounding rows, coefficients in [-100,100], "
+                        f"{'dense' if w['dense'] else '8 nnz/col sparse'} never-binding rows, seed=rank",
+            "pivot_rule": args.rule, "step": "one exact solve to optimality (time-to-optimal)",
+            "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (row sharding: see DESIGN.md)",
+            "l2": "carry (>= 268 MB at 2 limbs) exceeds the 126 MB L2; no flush needed"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="sparse4k", choices=sorted(WORKLOADS))
+    ap.add_argument("--rule", default="steepest_edge")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import relp_b200
+    from relp_b200 import _lib
+    _lib.load()   # fails loudly when the CUDA library is missing: there is no fallback
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    prob = make_problem(args.workload, rank)
+    # pinned host buffers for the end-to-end leg
+    for name in ("colptr", "rowidx", "vals", "cost", "rhs"):
+        t = torch.from_numpy(getattr(prob, name)).pin_memory()
+        setattr(prob, name, t.numpy())
+        setattr(prob, "_pin_" + name, t)
+    h2d = sum(getattr(prob, n).nbytes for n in ("colptr", "rowidx", "vals", "cost", "rhs"))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        return relp_b200.solve_relaxation(prob, rule=args.rule, device=local, profile=True)
+
+    for _ in range(args.warmup):
+        g = step()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    pivots = 0
+    dev_ms = 0.0
+    e2e_s = 0.0
+    launches = 0
+    k1_ms = [0.0] * 5
+    k1_n = [0] * 5
+    for _ in range(args.steps):
+        g = step()
+        assert g.status == "optimal"
+        pivots += g.pivots
+        dev_ms += g.device_ms
+        e2e_s += g.seconds_total
+        launches += g.stats["kernel_launches"]
+        for k in range(5):
+            k1_ms[k] += g.stats["k1_ms_at_limbs"][k]
+            k1_n[k] += g.stats["k1_launches_at_limbs"][k]
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    d2h = g.stats["limbs"] * 8 * (prob.m + 2) + 4 * prob.m
+
+    stats = torch.tensor([dev_ms, e2e_s, float(pivots), float(launches)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = stats.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        dev_ms_max, e2e_max = mx[0].item(), mx[1].item()
+        pivots_all, launches_all = sm[2].item(), sm[3].item()
+    else:
+        dev_ms_max, e2e_max, pivots_all, launches_all = dev_ms, e2e_s, float(pivots), float(launches)
+
+    if rank == 0:
+        peak, peak_src = measured_peak_hbm()
+        w = WORKLOADS[args.workload]
+        entries = (w["m"] + 1) ** 2
+        by_limbs = {}
+        dom, dom_ms = None, -1.0
+        for k in range(5):
+            if k1_n[k]:
+                L = 1 << k
+                avg = k1_ms[k] / k1_n[k]
+                gbs = 16.0 * L * entries / (avg * 1e-3) / 1e9
+                by_limbs[str(L)] = {"launches": k1_n[k], "avg_ms": avg, "GB/s": gbs, "frac": gbs / peak}
+                if k1_ms[k] > dom_ms:
+                    dom, dom_ms = L, k1_ms[k]
+        roof = {"bound": "hbm", "kernel": f"k_update<L={dom}> (rank-1 Bareiss pivot of the carry)",
+                "achieved": by_limbs[str(dom)]["GB/s"], "peak": peak, "unit": "GB/s",
+                "frac": by_limbs[str(dom)]["GB/s"] / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": 16 * dom * entries, "by_limbs": by_limbs,
+                "share_of_step": sum(k1_ms) / dev_ms if dev_ms else None}
+        line = {
+            "metric": "exact simplex pivots/sec", "value": pivots_all / (dev_ms_max * 1e-3), "unit": "pivots/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int (two's complement multi-limb u64, 2-16 limbs)",
+            "data": "synthetic", "config": workload_config(args, world),
+            "time_to_optimal_ms": dev_ms_max / args.steps, "pivots_per_solve": pivots / args.steps,
+            "limb_histogram": g.stats["pivots_at_limbs"],
+            "e2e": {"value": pivots_all / e2e_max, "unit": "pivots/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches_all), "clocks": clocks, "roofline": roof, "wall_s": wall,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(prob, args.rule)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

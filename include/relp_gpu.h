@@ -77,6 +77,10 @@ typedef struct rg_stats {
     int32_t reserved;
     int64_t kernel_launches;     /* kernels launched by this context so far */
     int64_t pivots_at_limbs[5];  /* pivots performed at L = 1,2,4,8,16 */
+    /* profiling (rg_set_profile): CUDA-event time of the rank-1 update kernel (K1) per limb width */
+    int64_t k1_launches_at_limbs[5];
+    double k1_ms_at_limbs[5];
+    double timer_ms;             /* rg_timer_start .. rg_timer_stop on the engine's stream */
 } rg_stats;
 
 typedef struct rg_pivot_info {   /* BasisChangeComputationInfo, tableau/mod.rs:205-234 (indices only) */
@@ -166,6 +170,10 @@ int rg_get_relative_costs(rg_context* ctx, uint64_t* out);
  * basic columns) */
 int rg_get_gamma(rg_context* ctx, uint64_t* out);
 int rg_get_stats(rg_context* ctx, rg_stats* out);
+/* measurement hooks (no reference counterpart): per-launch CUDA events around K1, and a stream timer */
+int rg_set_profile(rg_context* ctx, int32_t on);
+int rg_timer_start(rg_context* ctx);
+int rg_timer_stop(rg_context* ctx);
 
 /* ---- test hooks (no reference counterpart; used by tests/ and scripts/ only) -------------------- */
 int rg_debug_scalars(rg_context* ctx, void* out, int64_t bytes);

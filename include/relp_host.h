@@ -46,6 +46,8 @@ typedef struct rh_options {
     int32_t rule;                 /* RG_RULE_*; the reference hard-codes RG_RULE_STEEPEST_EDGE */
     int32_t fused;                /* 1: rg_iterate (one host sync per pivot); 0: trait-shaped calls */
     int64_t max_pivots;           /* 0 = unlimited */
+    int32_t profile;              /* 1: CUDA events around every K1 launch (rg_set_profile) */
+    int32_t reserved;
 } rh_options;
 
 typedef struct rh_result rh_result;   /* opaque; owns its buffers */
@@ -71,6 +73,7 @@ int32_t rh_result_rows_removed_len(const rh_result* r);
 const int32_t* rh_result_rows_removed(const rh_result* r);   /* Rank::Deficient rows (phase_one.rs:213-219) */
 void rh_result_stats(const rh_result* r, rg_stats* out);
 double rh_result_seconds(const rh_result* r);            /* wall time of the loops (excl. upload) */
+double rh_result_device_ms(const rh_result* r);          /* same region, CUDA events on the engine's stream */
 double rh_result_seconds_total(const rh_result* r);      /* create -> result exported */
 
 #ifdef __cplusplus

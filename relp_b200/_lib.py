@@ -17,7 +17,9 @@ class rg_options(C.Structure):
 class rg_stats(C.Structure):
     _fields_ = [("pivots", C.c_int64), ("promotions", C.c_int64), ("limbs", C.c_int32),
                 ("max_bits", C.c_int32), ("denominator_bits", C.c_int32), ("reserved", C.c_int32),
-                ("kernel_launches", C.c_int64), ("pivots_at_limbs", C.c_int64 * 5)]
+                ("kernel_launches", C.c_int64), ("pivots_at_limbs", C.c_int64 * 5),
+                ("k1_launches_at_limbs", C.c_int64 * 5), ("k1_ms_at_limbs", C.c_double * 5),
+                ("timer_ms", C.c_double)]
 
 
 class rg_pivot_info(C.Structure):
@@ -41,7 +43,8 @@ class rh_trace_entry(C.Structure):
 
 class rh_options(C.Structure):
     _fields_ = [("device", C.c_int32), ("initial_limbs", C.c_int32), ("rule", C.c_int32),
-                ("fused", C.c_int32), ("max_pivots", C.c_int64)]
+                ("fused", C.c_int32), ("max_pivots", C.c_int64), ("profile", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 # every symbol include/*.h declares: name -> (restype, argtypes)
@@ -74,6 +77,9 @@ SYMBOLS = {
     "rg_get_relative_costs": (C.c_int, [P, C.POINTER(C.c_uint64)]),
     "rg_get_gamma": (C.c_int, [P, C.POINTER(C.c_uint64)]),
     "rg_get_stats": (C.c_int, [P, C.POINTER(rg_stats)]),
+    "rg_set_profile": (C.c_int, [P, C.c_int32]),
+    "rg_timer_start": (C.c_int, [P]),
+    "rg_timer_stop": (C.c_int, [P]),
     "rg_debug_scalars": (C.c_int, [P, C.c_void_p, C.c_int64]),
     "rg_debug_vector": (C.c_int, [P, C.c_int32, C.POINTER(C.c_uint64)]),
     "rg_selftest": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
@@ -96,6 +102,7 @@ SYMBOLS = {
     "rh_result_rows_removed": (C.POINTER(C.c_int32), [P]),
     "rh_result_stats": (None, [P, C.POINTER(rg_stats)]),
     "rh_result_seconds": (C.c_double, [P]),
+    "rh_result_device_ms": (C.c_double, [P]),
     "rh_result_seconds_total": (C.c_double, [P]),
 }
 

@@ -101,5 +101,10 @@ struct rg_context {
     int t_cur = 0;                     // ctz(D) of the current denominator (host copy)
     long long pivots = 0, promotions = 0, launches = 0;
     long long pivots_at[5] = {0, 0, 0, 0, 0};
+    bool profile = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evt0 = nullptr, evt1 = nullptr;
+    long long k1_launches[5] = {0, 0, 0, 0, 0};
+    double k1_ms[5] = {0, 0, 0, 0, 0};
+    double timer_ms = 0;
     std::string err;
 };

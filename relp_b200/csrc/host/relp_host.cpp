@@ -242,8 +242,11 @@ extern "C" int rh_solve_relaxation(const rh_problem* problem, const rh_options* 
     try {
         relp::MatrixProvider mp{problem};
         relp::GpuCarry im(mp, *options);
+        if (options->profile) rg_set_profile(im.ctx, 1);
         auto t1 = clk::now();
+        rg_timer_start(im.ctx);
         relp::solve_relaxation(mp, *options, im, res->out);
+        rg_timer_stop(im.ctx);
         auto t2 = clk::now();
         res->seconds = std::chrono::duration<double>(t2 - t1).count();
         relp::check(im.ctx, rg_get_limbs(im.ctx, &res->limbs), "rg_get_limbs");
@@ -280,4 +283,5 @@ extern "C" int32_t rh_result_rows_removed_len(const rh_result* r) { return (int3
 extern "C" const int32_t* rh_result_rows_removed(const rh_result* r) { return r->out.rows_removed.data(); }
 extern "C" void rh_result_stats(const rh_result* r, rg_stats* out) { *out = r->stats; }
 extern "C" double rh_result_seconds(const rh_result* r) { return r->seconds; }
+extern "C" double rh_result_device_ms(const rh_result* r) { return r->stats.timer_ms; }
 extern "C" double rh_result_seconds_total(const rh_result* r) { return r->seconds_total; }

@@ -95,6 +95,8 @@ extern "C" int rg_destroy(rg_context* ctx) {
     free_dev(ctx->cost); free_dev(ctx->rhs); free_dev(ctx->basis); free_dev(ctx->inbasis);
     free_dev(ctx->G); free_dev(ctx->cand); free_dev(ctx->sc); free_dev(ctx->svec);
     if (ctx->hm) cudaFreeHost(ctx->hm);
+    if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); }
+    if (ctx->evt0) { cudaEventDestroy(ctx->evt0); cudaEventDestroy(ctx->evt1); }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return RG_OK;
@@ -302,7 +304,9 @@ static int do_pivot(rg_context* ctx, int q, int fixed_row, bool want_se, bool re
         if (want_se) launch_work(ctx);
         int E = (ctx->t_cur + 63) / 64;
         LAUNCH(k_scalars, 1, 1, ctx->u, (size_t)ctx->ld, ctx->L, want_se ? 1 : 0, ctx->G, ctx->n, E, ctx->sc);
+        if (ctx->profile) cudaEventRecord(ctx->ev0, ctx->stream);
         launch_update(ctx, E);
+        if (ctx->profile) cudaEventRecord(ctx->ev1, ctx->stream);
         LAUNCH(k_finalize, 1, 1, ctx->basis, ctx->inbasis, ctx->L, ctx->G, ctx->n, LG_of(ctx->L),
                want_se ? 1 : 0, ctx->sc, ctx->hm_dev);
         if (want_se) launch_se_update(ctx);
@@ -323,6 +327,13 @@ static int do_pivot(rg_context* ctx, int q, int fixed_row, bool want_se, bool re
         if (ctx->hm->pivoted) {
             ctx->pivots++;
             ctx->pivots_at[log2i(ctx->L)]++;
+            if (ctx->profile) {
+                float ms = 0;
+                if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) {
+                    ctx->k1_ms[log2i(ctx->L)] += ms;
+                    ctx->k1_launches[log2i(ctx->L)]++;
+                }
+            }
             ctx->identity_carry = false;
         }
         return RG_OK;
@@ -626,7 +637,37 @@ extern "C" int rg_get_stats(rg_context* ctx, rg_stats* out) {
     out->pivots = ctx->pivots; out->promotions = ctx->promotions; out->limbs = ctx->L;
     out->kernel_launches = ctx->launches;
     if (ctx->hm) { out->max_bits = ctx->hm->maxbits_carry; out->denominator_bits = ctx->hm->bits_D; }
-    for (int k = 0; k < 5; ++k) out->pivots_at_limbs[k] = ctx->pivots_at[k];
+    for (int k = 0; k < 5; ++k) {
+        out->pivots_at_limbs[k] = ctx->pivots_at[k];
+        out->k1_launches_at_limbs[k] = ctx->k1_launches[k];
+        out->k1_ms_at_limbs[k] = ctx->k1_ms[k];
+    }
+    out->timer_ms = ctx->timer_ms;
+    return RG_OK;
+}
+
+extern "C" int rg_set_profile(rg_context* ctx, int32_t on) {
+    if (!ctx) return RG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (on && !ctx->ev0) { CK(cudaEventCreate(&ctx->ev0)); CK(cudaEventCreate(&ctx->ev1)); }
+    ctx->profile = on != 0;
+    return RG_OK;
+}
+extern "C" int rg_timer_start(rg_context* ctx) {
+    if (!ctx) return RG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->evt0) { CK(cudaEventCreate(&ctx->evt0)); CK(cudaEventCreate(&ctx->evt1)); }
+    CK(cudaEventRecord(ctx->evt0, ctx->stream));
+    return RG_OK;
+}
+extern "C" int rg_timer_stop(rg_context* ctx) {
+    if (!ctx || !ctx->evt0) return RG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventRecord(ctx->evt1, ctx->stream));
+    CK(cudaEventSynchronize(ctx->evt1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ctx->evt0, ctx->evt1));
+    ctx->timer_ms = ms;
     return RG_OK;
 }
 

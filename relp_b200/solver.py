@@ -106,14 +106,16 @@ class GpuResult:
         self.stats = {}
         self.seconds = 0.0
         self.seconds_total = 0.0
+        self.device_ms = 0.0
 
 
 def solve_relaxation(problem, rule="steepest_edge", fused=True, initial_limbs=0, device=0,
-                     max_pivots=0):
+                     max_pivots=0, profile=False):
     lib = _lib.load()
     cprob, keep = problem._as_c()
     opts = _lib.rh_options(device=device, initial_limbs=initial_limbs, rule=RULES[rule],
-                           fused=1 if fused else 0, max_pivots=max_pivots)
+                           fused=1 if fused else 0, max_pivots=max_pivots,
+                           profile=1 if profile else 0)
     handle = C.c_void_p()
     rc = lib.rh_solve_relaxation(C.byref(cprob), C.byref(opts), C.byref(handle))
     try:
@@ -150,7 +152,10 @@ def solve_relaxation(problem, rule="steepest_edge", fused=True, initial_limbs=0,
         res.stats = dict(pivots=st.pivots, promotions=st.promotions, limbs=st.limbs,
                          max_bits=st.max_bits, denominator_bits=st.denominator_bits,
                          kernel_launches=st.kernel_launches,
-                         pivots_at_limbs=[st.pivots_at_limbs[k] for k in range(5)])
+                         pivots_at_limbs=[st.pivots_at_limbs[k] for k in range(5)],
+                         k1_launches_at_limbs=[st.k1_launches_at_limbs[k] for k in range(5)],
+                         k1_ms_at_limbs=[st.k1_ms_at_limbs[k] for k in range(5)])
+        res.device_ms = lib.rh_result_device_ms(handle)
         res.seconds = lib.rh_result_seconds(handle)
         res.seconds_total = lib.rh_result_seconds_total(handle)
         return res
