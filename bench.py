@@ -225,6 +225,7 @@ def main():
     launches = 0
     k1_ms = [0.0] * 5
     k1_n = [0] * 5
+    phase = [0.0] * 8
     for _ in range(args.steps):
         g = step()
         assert g.status == "optimal"
@@ -235,6 +236,8 @@ def main():
         for k in range(5):
             k1_ms[k] += g.stats["k1_ms_at_limbs"][k]
             k1_n[k] += g.stats["k1_launches_at_limbs"][k]
+        for k in range(8):
+            phase[k] += g.stats["phase_ms"][k]
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
@@ -281,6 +284,8 @@ def main():
             "e2e": {"value": pivots_all / e2e_max, "unit": "pivots/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches_all), "clocks": clocks, "roofline": roof, "wall_s": wall,
+            "phase_ms_per_step": dict(zip(["column+ratio", "work_vector", "scalars", "k1_update", "se_update",
+                                           "price+select"], [p / args.steps for p in phase[:6]])),
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(prob, args.rule)

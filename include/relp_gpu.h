@@ -81,6 +81,10 @@ typedef struct rg_stats {
     int64_t k1_launches_at_limbs[5];
     double k1_ms_at_limbs[5];
     double timer_ms;             /* rg_timer_start .. rg_timer_stop on the engine's stream */
+    /* profiling: CUDA-event time per iteration phase: 0 pivot column + ratio test + row staging,
+     * 1 work vector, 2 pivot scalars, 3 K1 update, 4 bookkeeping + steepest-edge update,
+     * 5 pricing + column selection */
+    double phase_ms[8];
 } rg_stats;
 
 typedef struct rg_pivot_info {   /* BasisChangeComputationInfo, tableau/mod.rs:205-234 (indices only) */

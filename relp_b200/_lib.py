@@ -19,7 +19,7 @@ class rg_stats(C.Structure):
                 ("max_bits", C.c_int32), ("denominator_bits", C.c_int32), ("reserved", C.c_int32),
                 ("kernel_launches", C.c_int64), ("pivots_at_limbs", C.c_int64 * 5),
                 ("k1_launches_at_limbs", C.c_int64 * 5), ("k1_ms_at_limbs", C.c_double * 5),
-                ("timer_ms", C.c_double)]
+                ("timer_ms", C.c_double), ("phase_ms", C.c_double * 8)]
 
 
 class rg_pivot_info(C.Structure):

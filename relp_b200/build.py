@@ -12,6 +12,7 @@ SOURCES = [
 ]
 HEADERS = [
     os.path.join(HERE, "csrc", "bigint.cuh"),
+    os.path.join(HERE, "csrc", "mp32.cuh"),
     os.path.join(HERE, "csrc", "engine.cuh"),
     os.path.join(HERE, "csrc", "kernels.cuh"),
     os.path.join(ROOT, "include", "relp_gpu.h"),

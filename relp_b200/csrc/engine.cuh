@@ -90,6 +90,7 @@ struct rg_context {
     u64* sigma = nullptr;       // LS planes x n  work-vector . column
     u64* G = nullptr;           // LG planes x n  Ghat
     int* cand = nullptr;        // block winners scratch
+    double* score = nullptr;    // max(n, m) filter scores
     rg::Scalars* sc = nullptr;
     rg::HostMirror* hm = nullptr;      // pinned host
     rg::HostMirror* hm_dev = nullptr;  // device alias of hm
@@ -103,6 +104,8 @@ struct rg_context {
     long long pivots_at[5] = {0, 0, 0, 0, 0};
     bool profile = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evt0 = nullptr, evt1 = nullptr;
+    cudaEvent_t evp[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    double phase_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // ftran+ratio+copyrow, work, scalars, K1, finalize+SE update, price+select, mirror
     long long k1_launches[5] = {0, 0, 0, 0, 0};
     double k1_ms[5] = {0, 0, 0, 0, 0};
     double timer_ms = 0;

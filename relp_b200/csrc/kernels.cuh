@@ -6,6 +6,7 @@
 // work vector, per-column pricing data) use the same planar scheme.
 #pragma once
 #include "engine.cuh"
+#include "mp32.cuh"
 
 namespace rg {
 
@@ -287,6 +288,116 @@ struct CmpArtificial {
     __device__ bool better(int j, int k) const { return j < k; }
 };
 
+// ---------------------------------------------------------------------------------------------
+// floating-point pre-filter for the index reductions.  Every candidate gets a log2-domain score
+// accurate to ~1e-12; only candidates within SCORE_EPS of the best score are compared exactly, so
+// the exact multi-limb cross-multiplications run on a handful of columns / rows instead of all.
+// The exact winner is always inside the candidate set (|score error| << SCORE_EPS / 2).
+// ---------------------------------------------------------------------------------------------
+#define SCORE_EPS 1e-8
+#define SCORE_NONE (-1.0e308)
+
+// log2 of the magnitude of a planar two's complement number (sign returned separately)
+__device__ inline double planar_log2_abs(const u64* base, size_t stride, size_t idx, int nl, int* sign) {
+    bool neg = (i64)base[(size_t)(nl - 1) * stride + idx] < 0;
+    u64 hi = 0, lo = 0, prev = 0, c = neg ? 1 : 0;
+    int k = -1;
+    for (int l = 0; l < nl; ++l) {
+        u64 v = base[(size_t)l * stride + idx];
+        if (neg) { v = ~v + c; c = (c && v == 0) ? 1 : 0; }   // |x| = ~x + 1, limb by limb
+        if (v) { k = l; hi = v; lo = prev; }
+        prev = v;
+    }
+    if (k < 0) { *sign = 0; return SCORE_NONE; }
+    int sh = __clzll((long long)hi);
+    u64 top = sh ? ((hi << sh) | (lo >> (64 - sh))) : hi;
+    *sign = neg ? -1 : 1;
+    return (double)(64 * k - sh) + log2((double)top);
+}
+
+// mode 2: Dantzig  score = log2|kappa|;  mode 3: steepest edge  score = 2 log2|kappa| - log2 Ghat
+__global__ void __launch_bounds__(256)
+k_score_columns(int n, int mode, const u64* __restrict__ kappa, int LU, const u64* __restrict__ G, int LG,
+                const unsigned char* __restrict__ inbasis, double* __restrict__ score, const Scalars* sc) {
+    if (sc->status != ST_RUN) return;
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    double s = SCORE_NONE;
+    if (!inbasis[j]) {
+        int sg;
+        double lk = planar_log2_abs(kappa, n, j, LU, &sg);
+        if (sg < 0) {
+            if (mode == 2) s = lk;
+            else { int sg2; s = 2.0 * lk - planar_log2_abs(G, n, j, LG, &sg2); }
+        }
+    }
+    score[j] = s;
+}
+// ratio test: rows with u_i > 0; score = -(log2 b_i - log2 u_i) so that "best" is the maximum
+__global__ void __launch_bounds__(256)
+k_score_rows(int m, const u64* __restrict__ C, size_t ps, int ld, int L, const u64* __restrict__ u,
+             size_t us, int LU, double* __restrict__ score, const Scalars* sc) {
+    if (sc->status != ST_RUN) return;
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= m) return;
+    int su, sb;
+    double lu = planar_log2_abs(u, us, (size_t)r + 1, LU, &su);
+    double s = SCORE_NONE;
+    if (su > 0) {
+        double lb = planar_log2_abs(C, ps, (size_t)(r + 1) * ld, L, &sb);
+        s = sb == 0 ? 1.0e300 : -(lb - lu);
+        if (sb < 0) s = 1.0e300;   // b >= 0 always holds for a basic feasible solution
+    }
+    score[r] = s;
+}
+
+// single block: max score, then exact comparison among the candidates within SCORE_EPS
+template <class Cmp>
+__global__ void __launch_bounds__(1024) k_select_scored(int count, Cmp cmp, const double* __restrict__ score,
+                                                        int mode, Scalars* sc) {
+    __shared__ double sd[1024];
+    __shared__ int sm[1024];
+    if (sc->status != ST_RUN) return;
+    int tid = threadIdx.x;
+    double best = SCORE_NONE;
+    for (int j = tid; j < count; j += blockDim.x) best = fmax(best, score[j]);
+    sd[tid] = best;
+    __syncthreads();
+    for (int s = blockDim.x >> 1; s > 0; s >>= 1) {
+        if (tid < s) sd[tid] = fmax(sd[tid], sd[tid + s]);
+        __syncthreads();
+    }
+    double top = sd[0];
+    int cand = -1;
+    if (top > SCORE_NONE) {
+        double thr = top >= 1.0e299 ? 1.0e299 : top - SCORE_EPS;
+        for (int j = tid; j < count; j += blockDim.x) {
+            if (score[j] >= thr && (cand < 0 || cmp.better(j, cand))) cand = j;
+        }
+    }
+    sm[tid] = cand;
+    __syncthreads();
+    for (int s = blockDim.x >> 1; s > 0; s >>= 1) {
+        if (tid < s) {
+            int a = sm[tid], b = sm[tid + s];
+            if (b >= 0 && (a < 0 || cmp.better(b, a))) sm[tid] = b;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        int bestj = sm[0];
+        if (mode == 0) {
+            sc->q = bestj;
+            if (bestj < 0) sc->status = ST_OPTIMAL; else sc->last_selected = bestj;
+        } else if (mode == 1) {
+            sc->p = bestj + 1;
+            if (bestj < 0) sc->status = ST_UNBOUNDED;
+        } else {
+            sc->found = bestj;
+        }
+    }
+}
+
 template <class Cmp>
 __device__ __forceinline__ int block_best(int best, const Cmp& cmp, int* sm) {
     int tid = threadIdx.x;
@@ -510,100 +621,114 @@ __global__ void __launch_bounds__(256)
 k_update(u64* __restrict__ C, size_t ps, int ld, int nrows, const u64* __restrict__ u, size_t us,
          const u64* __restrict__ rowp, size_t rs, Scalars* sc) {
     constexpr int W = L + E;
+    constexpr int N = 2 * W;          // 32-bit limbs of the working width
     constexpr int LU = L + 2;
     constexpr int RT = 32;
-    __shared__ u64 sBn[RT][W];
-    __shared__ u64 sA[W];
+    __shared__ u32 sBn[RT][N];
+    __shared__ u32 sA[N];
     if (sc->status != ST_RUN) return;
     if (sc->E != E) return;
     const int tid = threadIdx.x;
     const int row0 = blockIdx.y * RT;
+    if (tid < N) sA[tid] = reinterpret_cast<const u32*>(sc->A)[tid];
     if (tid < RT) {
         int i = row0 + tid;
         if (i < nrows) {
-            u64 ui[W], dinv[W], bn[W];
+            u32 ui[N], bn[N];
             if (i == sc->p) {
 #pragma unroll
-                for (int l = 0; l < W; ++l) ui[l] = sc->up[l];
+                for (int l = 0; l < W; ++l) { u64 v = sc->up[l]; ui[2 * l] = (u32)v; ui[2 * l + 1] = (u32)(v >> 32); }
             } else {
                 u64 top = u[(size_t)(LU - 1) * us + i];
                 u64 sg = (i64)top < 0 ? ~0ull : 0ull;
 #pragma unroll
-                for (int l = 0; l < W; ++l) ui[l] = l < LU ? u[(size_t)l * us + i] : sg;
+                for (int l = 0; l < W; ++l) {
+                    u64 v = l < LU ? u[(size_t)l * us + i] : sg;
+                    ui[2 * l] = (u32)v; ui[2 * l + 1] = (u32)(v >> 32);
+                }
             }
-#pragma unroll
-            for (int l = 0; l < W; ++l) dinv[l] = sc->Dinv[l];
-            mul_lo<W>(bn, ui, dinv);
+            mp_mul_lo<N>(bn, ui, reinterpret_cast<const u32*>(sc->Dinv));
             if (sc->sgn > 0) {   // Bn = -u Dinv
-                u64 c = 1;
+                u32 c = 1;
 #pragma unroll
-                for (int l = 0; l < W; ++l) { u64 v = ~bn[l] + c; c = (c && v == 0) ? 1 : 0; bn[l] = v; }
+                for (int k = 0; k < N; ++k) { u32 v = ~bn[k] + c; c = (c && v == 0) ? 1u : 0u; bn[k] = v; }
             }
 #pragma unroll
-            for (int l = 0; l < W; ++l) sBn[tid][l] = bn[l];
+            for (int k = 0; k < N; ++k) sBn[tid][k] = bn[k];
         }
     }
-    if (tid < W) sA[tid] = sc->A[tid];
     __syncthreads();
     const int col = (blockIdx.x * 256 + tid) * CP;
     int maxb = 0;
     if (col < ld) {
         const int t = sc->t;
-        const int tw = t >> 6, tb = t & 63;
-        u64 A[W];
-#pragma unroll
-        for (int l = 0; l < W; ++l) A[l] = sA[l];
-        u64 rp[CP][W];
+        const int tw = t >> 5, tb = t & 31;
+        u32 rp[CP][N];
 #pragma unroll
         for (int c = 0; c < CP; ++c) {
 #pragma unroll
-            for (int l = 0; l < L; ++l) rp[c][l] = rowp[(size_t)l * rs + col + c];
-            u64 sg = (i64)rp[c][L - 1] < 0 ? ~0ull : 0ull;
+            for (int l = 0; l < L; ++l) {
+                u64 v = rowp[(size_t)l * rs + col + c];
+                rp[c][2 * l] = (u32)v; rp[c][2 * l + 1] = (u32)(v >> 32);
+            }
+            u32 sg = (int)rp[c][2 * L - 1] < 0 ? ~0u : 0u;
 #pragma unroll
-            for (int l = L; l < W; ++l) rp[c][l] = sg;
+            for (int k = 2 * L; k < N; ++k) rp[c][k] = sg;
         }
         const int rend = min(RT, nrows - row0);
         for (int r = 0; r < rend; ++r) {
             size_t off = (size_t)(row0 + r) * ld + col;
-            u64 cv[CP][W];
+            u32 cv[CP][N];
             if (CP == 2) {
 #pragma unroll
                 for (int l = 0; l < L; ++l) {
                     ulonglong2 v = *reinterpret_cast<const ulonglong2*>(C + (size_t)l * ps + off);
-                    cv[0][l] = v.x; cv[CP - 1][l] = v.y;
+                    cv[0][2 * l] = (u32)v.x; cv[0][2 * l + 1] = (u32)(v.x >> 32);
+                    cv[CP - 1][2 * l] = (u32)v.y; cv[CP - 1][2 * l + 1] = (u32)(v.y >> 32);
                 }
             } else {
 #pragma unroll
-                for (int l = 0; l < L; ++l) cv[0][l] = C[(size_t)l * ps + off];
+                for (int l = 0; l < L; ++l) {
+                    u64 v = C[(size_t)l * ps + off];
+                    cv[0][2 * l] = (u32)v; cv[0][2 * l + 1] = (u32)(v >> 32);
+                }
             }
-            u64 bn[W];
-#pragma unroll
-            for (int l = 0; l < W; ++l) bn[l] = sBn[r][l];
             u64 res[CP][L];
 #pragma unroll
             for (int c = 0; c < CP; ++c) {
-                u64 sg = (i64)cv[c][L - 1] < 0 ? ~0ull : 0ull;
+                u32 sg = (int)cv[c][2 * L - 1] < 0 ? ~0u : 0u;
 #pragma unroll
-                for (int l = L; l < W; ++l) cv[c][l] = sg;
-                u64 X[W];
-                mul2_lo<W>(X, A, cv[c], bn, rp[c]);
+                for (int k = 2 * L; k < N; ++k) cv[c][k] = sg;
+                u32 X[N];
+                mp_mul2_lo<N>(X, cv[c], sA, rp[c], sBn[r]);
+                u32 o[2 * L];
                 if (E == 0) {
 #pragma unroll
-                    for (int l = 0; l < L; ++l) res[c][l] = X[l];
+                    for (int k = 0; k < 2 * L; ++k) o[k] = X[k];
                 } else {
 #pragma unroll
-                    for (int w = 0; w <= E; ++w) {
+                    for (int w = 0; w <= 2 * E; ++w) {
                         if (tw == w) {
 #pragma unroll
-                            for (int l = 0; l < L; ++l) {
-                                u64 lo = X[l + w < W ? l + w : W - 1];
-                                u64 hi = (l + w + 1 < W) ? X[l + w + 1 < W ? l + w + 1 : W - 1] : 0;
-                                res[c][l] = tb ? ((lo >> tb) | (hi << (64 - tb))) : lo;
+                            for (int k = 0; k < 2 * L; ++k) {
+                                u32 lo = X[k + w < N ? k + w : N - 1];
+                                u32 hi = (k + w + 1 < N) ? X[k + w + 1 < N ? k + w + 1 : N - 1] : 0u;
+                                o[k] = __funnelshift_r(lo, hi, tb);
                             }
                         }
                     }
                 }
-                maxb = max(maxb, bitlen_signed<L>(res[c]));
+                // bit length of |result|
+                u32 sgn = (int)o[2 * L - 1] < 0 ? ~0u : 0u;
+                int bl = 0;
+#pragma unroll
+                for (int k = 0; k < 2 * L; ++k) {
+                    u32 v = o[k] ^ sgn;
+                    if (v) bl = 32 * k + 32 - __clz(v);
+                }
+                maxb = max(maxb, bl + (sgn ? 1 : 0));
+#pragma unroll
+                for (int l = 0; l < L; ++l) res[c][l] = (u64)o[2 * l] | ((u64)o[2 * l + 1] << 32);
             }
             if (CP == 2) {
 #pragma unroll

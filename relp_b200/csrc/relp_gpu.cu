@@ -93,9 +93,9 @@ extern "C" int rg_destroy(rg_context* ctx) {
     free_width_buffers(ctx);
     free_dev(ctx->carry); free_dev(ctx->A.colptr); free_dev(ctx->A.rowidx); free_dev(ctx->A.vals);
     free_dev(ctx->cost); free_dev(ctx->rhs); free_dev(ctx->basis); free_dev(ctx->inbasis);
-    free_dev(ctx->G); free_dev(ctx->cand); free_dev(ctx->sc); free_dev(ctx->svec);
+    free_dev(ctx->G); free_dev(ctx->cand); free_dev(ctx->score); free_dev(ctx->sc); free_dev(ctx->svec);
     if (ctx->hm) cudaFreeHost(ctx->hm);
-    if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); }
+    if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); for (int k = 0; k < 8; ++k) cudaEventDestroy(ctx->evp[k]); }
     if (ctx->evt0) { cudaEventDestroy(ctx->evt0); cudaEventDestroy(ctx->evt1); }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -130,6 +130,7 @@ extern "C" int rg_load_csc(rg_context* ctx, int32_t m, int32_t n, const int64_t*
     CK(cudaMalloc(&ctx->basis, sizeof(int) * m));
     CK(cudaMalloc(&ctx->inbasis, n));
     CK(cudaMalloc(&ctx->cand, sizeof(int) * 1024));
+    CK(cudaMalloc(&ctx->score, sizeof(double) * std::max(m, n)));
     CK(cudaMalloc(&ctx->svec, sizeof(u64) * ctx->ld));
     ctx->work_chunks = std::max(1, std::min(64, cdiv(m, 64)));
     CK(cudaMalloc(&ctx->carry, sizeof(u64) * ctx->L * ctx->plane));
@@ -186,8 +187,17 @@ static void launch_select(rg_context* ctx) {
     switch (ctx->rule) {
         case RG_RULE_FIRST_PROFITABLE: launch_argbest(ctx, ctx->n, CmpFirst{v}, 0); break;
         case RG_RULE_FIRST_PROFITABLE_WITH_MEMORY: launch_argbest(ctx, ctx->n, CmpFirstMem{v, ctx->sc}, 0); break;
-        case RG_RULE_DANTZIG: launch_argbest(ctx, ctx->n, CmpDantzig{v}, 0); break;
-        default: launch_argbest(ctx, ctx->n, CmpSteepest{v, ctx->G, LG_of(ctx->L)}, 0); break;
+        case RG_RULE_DANTZIG:
+            LAUNCH(k_score_columns, cdiv(ctx->n, 256), 256, ctx->n, 2, ctx->kappa, LU_of(ctx->L), ctx->G,
+                   LG_of(ctx->L), ctx->inbasis, ctx->score, ctx->sc);
+            LAUNCH((k_select_scored<CmpDantzig>), 1, 1024, ctx->n, CmpDantzig{v}, ctx->score, 0, ctx->sc);
+            break;
+        default:
+            LAUNCH(k_score_columns, cdiv(ctx->n, 256), 256, ctx->n, 3, ctx->kappa, LU_of(ctx->L), ctx->G,
+                   LG_of(ctx->L), ctx->inbasis, ctx->score, ctx->sc);
+            LAUNCH((k_select_scored<CmpSteepest>), 1, 1024, ctx->n, CmpSteepest{v, ctx->G, LG_of(ctx->L)},
+                   ctx->score, 0, ctx->sc);
+            break;
     }
 }
 
@@ -201,7 +211,9 @@ static void launch_ftran(rg_context* ctx, int q) { DISPATCH_L(ctx->L, launch_ftr
 
 static void launch_ratio(rg_context* ctx) {
     CmpRatio c{ctx->carry, ctx->plane, ctx->ld, ctx->L, ctx->u, (size_t)ctx->ld, LU_of(ctx->L), ctx->basis};
-    launch_argbest(ctx, ctx->m, c, 1);
+    LAUNCH(k_score_rows, cdiv(ctx->m, 256), 256, ctx->m, ctx->carry, ctx->plane, ctx->ld, ctx->L, ctx->u,
+           (size_t)ctx->ld, LU_of(ctx->L), ctx->score, ctx->sc);
+    LAUNCH((k_select_scored<CmpRatio>), 1, 1024, ctx->m, c, ctx->score, 1, ctx->sc);
 }
 
 template <int L>
@@ -296,21 +308,27 @@ static int promote(rg_context* ctx) {
 static int do_pivot(rg_context* ctx, int q, int fixed_row, bool want_se, bool reselect) {
     for (;;) {
         ctx->hm->pivoted = 0;
+        const bool prof = ctx->profile;
+        if (prof) cudaEventRecord(ctx->evp[0], ctx->stream);
         LAUNCH(k_reset_iter, 1, 1, ctx->sc);
         launch_ftran(ctx, q);
         if (fixed_row < 0) launch_ratio(ctx);
         else LAUNCH(k_set_pq, 1, 1, ctx->sc, -2, fixed_row + 1);
         launch_copyrow(ctx);
+        if (prof) cudaEventRecord(ctx->evp[1], ctx->stream);
         if (want_se) launch_work(ctx);
+        if (prof) cudaEventRecord(ctx->evp[2], ctx->stream);
         int E = (ctx->t_cur + 63) / 64;
         LAUNCH(k_scalars, 1, 1, ctx->u, (size_t)ctx->ld, ctx->L, want_se ? 1 : 0, ctx->G, ctx->n, E, ctx->sc);
-        if (ctx->profile) cudaEventRecord(ctx->ev0, ctx->stream);
+        if (prof) cudaEventRecord(ctx->ev0, ctx->stream);
         launch_update(ctx, E);
-        if (ctx->profile) cudaEventRecord(ctx->ev1, ctx->stream);
+        if (prof) cudaEventRecord(ctx->ev1, ctx->stream);
         LAUNCH(k_finalize, 1, 1, ctx->basis, ctx->inbasis, ctx->L, ctx->G, ctx->n, LG_of(ctx->L),
                want_se ? 1 : 0, ctx->sc, ctx->hm_dev);
         if (want_se) launch_se_update(ctx);
+        if (prof) cudaEventRecord(ctx->evp[3], ctx->stream);
         if (reselect) { launch_price(ctx); launch_select(ctx); }
+        if (prof) cudaEventRecord(ctx->evp[4], ctx->stream);
         RG_TRY(sync_mirror(ctx));
         if (ctx->hm->status == ST_PROMOTE) {
             RG_TRY(promote(ctx));
@@ -332,7 +350,13 @@ static int do_pivot(rg_context* ctx, int q, int fixed_row, bool want_se, bool re
                 if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) {
                     ctx->k1_ms[log2i(ctx->L)] += ms;
                     ctx->k1_launches[log2i(ctx->L)]++;
+                    ctx->phase_ms[3] += ms;
                 }
+                cudaEvent_t seq[7] = {ctx->evp[0], ctx->evp[1], ctx->evp[2], ctx->ev0, ctx->ev1, ctx->evp[3], ctx->evp[4]};
+                const int slot[6] = {0, 1, 2, -1, 4, 5};
+                for (int k = 0; k < 6; ++k)
+                    if (slot[k] >= 0 && cudaEventElapsedTime(&ms, seq[k], seq[k + 1]) == cudaSuccess)
+                        ctx->phase_ms[slot[k]] += ms;
             }
             ctx->identity_carry = false;
         }
@@ -643,13 +667,17 @@ extern "C" int rg_get_stats(rg_context* ctx, rg_stats* out) {
         out->k1_ms_at_limbs[k] = ctx->k1_ms[k];
     }
     out->timer_ms = ctx->timer_ms;
+    for (int k = 0; k < 8; ++k) out->phase_ms[k] = ctx->phase_ms[k];
     return RG_OK;
 }
 
 extern "C" int rg_set_profile(rg_context* ctx, int32_t on) {
     if (!ctx) return RG_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
-    if (on && !ctx->ev0) { CK(cudaEventCreate(&ctx->ev0)); CK(cudaEventCreate(&ctx->ev1)); }
+    if (on && !ctx->ev0) {
+        CK(cudaEventCreate(&ctx->ev0)); CK(cudaEventCreate(&ctx->ev1));
+        for (int k = 0; k < 8; ++k) CK(cudaEventCreate(&ctx->evp[k]));
+    }
     ctx->profile = on != 0;
     return RG_OK;
 }
@@ -710,6 +738,12 @@ __global__ void k_selftest(int op, const u64* a, const u64* b, const u64* c, con
     } else if (op == 3) { u64* o = big; rt_inv_odd(o, x, W, W, big + RG_MAXW); for (int l = 0; l < W; ++l) r[l] = o[l]; }
     else if (op == 4) { mul_full_ct<W, W>(r, x, y); }
     else if (op == 5) { r[0] = (u64)(i64)rt_cmp_prod(x, W, y, W, z, W, w, W, big); }
+    else if (op == 6) {   // 32-bit limb path used by K1: x*y + z*w mod 2^(64W)
+        u32 xx[2 * W], zz[2 * W], oo[2 * W];
+        for (int l = 0; l < W; ++l) { xx[2 * l] = (u32)x[l]; xx[2 * l + 1] = (u32)(x[l] >> 32); zz[2 * l] = (u32)z[l]; zz[2 * l + 1] = (u32)(z[l] >> 32); }
+        mp_mul2_lo<2 * W>(oo, xx, reinterpret_cast<const u32*>(b), zz, reinterpret_cast<const u32*>(d));
+        for (int l = 0; l < W; ++l) r[l] = (u64)oo[2 * l] | ((u64)oo[2 * l + 1] << 32);
+    }
     for (int l = 0; l < 2 * W; ++l) out[l] = r[l];
 }
 

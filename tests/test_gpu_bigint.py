@@ -39,6 +39,8 @@ def test_primitives(W):
         assert to_int(out, W) == (a * b) % M
         assert lib.rg_selftest(1, W, words(a, W), words(b, W), words(c, W), words(d, W), 0, out) == 0
         assert to_int(out, W) == (a * b + c * d) % M
+        assert lib.rg_selftest(6, W, words(a, W), words(b, W), words(c, W), words(d, W), 0, out) == 0
+        assert to_int(out, W) == (a * b + c * d) % M
         s = signed_rand(rng, 63)
         assert lib.rg_selftest(2, W, words(a, W), words(b, W), words(c, W), words(d, W), s, out) == 0
         n = min(W + 2, 2 * W)
