@@ -68,6 +68,8 @@ struct rg_context {
     int device = 0;
     int rank = 0, world = 1;
     cudaStream_t stream = nullptr;
+    cudaStream_t side = nullptr;          // side stream: steepest-edge scalars overlap the K1 update
+    cudaEvent_t ev_side0 = nullptr, ev_side1 = nullptr;
     int m = 0, n = 0;
     int ld = 0;                 // carry leading dimension in entries (multiple of 16)
     int L = 2;                  // current limb count

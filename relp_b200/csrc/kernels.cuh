@@ -535,17 +535,14 @@ k_copyrow(const u64* __restrict__ C, size_t ps, int ld, u64* __restrict__ rowp, 
 // pivot scalars (one thread): overflow prediction, 2-adic inverse of D, A = |a|/D, u_p' = a - D,
 // steepest-edge scalars.  Sets ST_PROMOTE / ST_FATAL when the update would not fit L limbs.
 // ---------------------------------------------------------------------------------------------
-__global__ void k_scalars(const u64* __restrict__ u, size_t us, int L, int want_se,
-                          const u64* __restrict__ G, int n, int E_host, Scalars* sc) {
+__global__ void k_scalars(const u64* __restrict__ u, size_t us, int L, int E_host, Scalars* sc) {
     if (threadIdx.x || blockIdx.x) return;
     if (sc->status != ST_RUN) return;
     const int LU = L + 2;
-    u64 buf[17 * RG_MAXW];     // ONE local buffer, sliced by hand (see bigint.cuh rt_inv_odd)
+    u64 buf[11 * RG_MAXW];     // ONE local buffer, sliced by hand (see bigint.cuh rt_inv_odd)
     u64* a = buf;               u64* am = buf + RG_MAXW;        u64* dodd = buf + 2 * RG_MAXW;
     u64* inv = buf + 3 * RG_MAXW;  u64* tmp = buf + 4 * RG_MAXW;   u64* ext = buf + 5 * RG_MAXW;
-    u64* upv = buf + 6 * RG_MAXW;  u64* dext = buf + 7 * RG_MAXW;  u64* i1 = buf + 8 * RG_MAXW;
-    u64* i2 = buf + 9 * RG_MAXW;   u64* ax = buf + 10 * RG_MAXW;   u64* a2 = buf + 11 * RG_MAXW;
-    u64* gq = buf + 12 * RG_MAXW;  u64* ws = buf + 13 * RG_MAXW;   // ws: 3 slots (+1 spare)
+    u64* upv = buf + 6 * RG_MAXW;  u64* dext = buf + 7 * RG_MAXW;  u64* ws = buf + 8 * RG_MAXW;   // 3 slots
     rt_load_planar(a, LU, u, us, (size_t)sc->p);
     int sgn = rt_abs(am, a, LU);
     sc->sgn = sgn;
@@ -585,26 +582,86 @@ __global__ void k_scalars(const u64* __restrict__ u, size_t us, int L, int want_
     rt_sub(upv, dext, WU);
     for (int l = 0; l < WU; ++l) sc->up[l] = upv[l];
     sc->maxbits_new = 0;
-    if (want_se) {
-        // Ghat' = [a^2 Ghat - 2 a nu sigma + nu^2 Gq] / D^2, evaluated mod 2^(64 WX) with the 2-adic
-        // inverse of odd(D)^2 and a final shift by 2t (pivot_rule.rs:243-296 in integer form).
-        const int LG = 2 * L + 5;
-        int t2 = 2 * t, E2 = (t2 + 63) >> 6, WX = LG + E2;
-        sc->t2 = t2; sc->E2 = E2;
-        rt_inv_odd(i1, dodd, L, WX, ws);
-        rt_mul_lo(i2, i1, i1, WX);
-        for (int l = 0; l < WX; ++l) ax[l] = l < LU ? am[l] : 0;     // a > 0 whenever the rule updates
-        rt_mul_lo(a2, ax, ax, WX);
-        rt_mul_lo(tmp, a2, i2, WX);
-        for (int l = 0; l < WX; ++l) sc->S1[l] = tmp[l];
-        rt_add(ax, ax, WX);                                          // 2a
-        rt_mul_lo(tmp, ax, i2, WX);
-        for (int l = 0; l < WX; ++l) sc->S2[l] = tmp[l];
-        for (int l = 0; l < WX; ++l) gq[l] = l < LG ? G[(size_t)l * n + sc->q] : 0;
-        for (int l = 0; l < LG; ++l) sc->Gq[l] = gq[l];
-        rt_mul_lo(tmp, gq, i2, WX);
-        for (int l = 0; l < WX; ++l) sc->S3[l] = tmp[l];
+}
+
+// warp-cooperative low product in shared memory: r = a*b mod 2^(64 n).  Lane k sums column k into a
+// 3-word accumulator, lane 0 propagates the carries.  r must not alias a or b; cols: 3*n words.
+__device__ inline void warp_mul_lo(u64* r, const u64* a, const u64* b, int n, u64* cols) {
+    const int lane = threadIdx.x & 31;
+    for (int k = lane; k < n; k += 32) {
+        u64 c0 = 0, c1 = 0, c2 = 0;
+        for (int i = 0; i <= k; ++i) mac3(c0, c1, c2, a[i], b[k - i]);
+        cols[3 * k] = c0; cols[3 * k + 1] = c1; cols[3 * k + 2] = c2;
     }
+    __syncwarp();
+    if (lane == 0) {
+        u64 carry = 0;
+        for (int k = 0; k < n; ++k) {
+            // limb k = c0[k] + c1[k-1] + c2[k-2] + carry
+            u64 v = cols[3 * k], c = 0;
+            u64 t = v + carry; c += t < v; v = t;
+            if (k >= 1) { t = v + cols[3 * (k - 1) + 1]; c += t < v; v = t; }
+            if (k >= 2) { t = v + cols[3 * (k - 2) + 2]; c += t < v; v = t; }
+            r[k] = v; carry = c;
+        }
+    }
+    __syncwarp();
+}
+
+// steepest-edge scalars of the pivot (one warp, runs on a side stream concurrently with K1):
+// Ghat' = [a^2 Ghat - 2 a nu sigma + nu^2 Gq] / D^2 is evaluated mod 2^(64 WX) with the 2-adic inverse of
+// odd(D)^2 and a final shift by 2t (pivot_rule.rs:243-296 in integer form).  WX = LG + max(E2, 4) so that
+// the fixed-width update kernel can be used whenever D^2 has at most 256 trailing zero bits.
+__global__ void __launch_bounds__(32) k_scalars_se(int L, const u64* __restrict__ G, int n, Scalars* sc) {
+    __shared__ u64 am[RG_MAXW], dodd[RG_MAXW], x[RG_MAXW], tt[RG_MAXW], xn[RG_MAXW], i2[RG_MAXW],
+        ax[RG_MAXW], tmp[RG_MAXW], cols[3 * RG_MAXW];
+    if (sc->status != ST_RUN) return;
+    const int lane = threadIdx.x;
+    const int LU = L + 2, LG = 2 * L + 5;
+    const int t = sc->t;
+    const int t2 = 2 * t;
+    int E2 = (t2 + 63) >> 6;
+    if (E2 < 4) E2 = 4;
+    const int WX = LG + E2;
+    if (lane == 0) {
+        sc->t2 = t2; sc->E2 = E2;
+        for (int l = 0; l < WX; ++l) { am[l] = l < L ? sc->Dnew[l] : 0; dodd[l] = l < L ? sc->D[l] : 0; }
+        rt_shr(dodd, L, t);
+        u64 d0 = dodd[0], y = d0;
+        for (int it = 0; it < 6; ++it) y *= 2 - d0 * y;
+        for (int l = 0; l < WX; ++l) x[l] = 0;
+        x[0] = y;
+    }
+    __syncwarp();
+    // Newton: x <- x (2 - d x), doubling the number of correct limbs
+    for (int have = 1; have < WX; have *= 2) {
+        int want = have * 2 < WX ? have * 2 : WX;
+        warp_mul_lo(tt, dodd, x, want, cols);
+        if (lane == 0) {
+            rt_neg(tt, want);
+            u64 v = tt[0] + 2; u64 c = v < tt[0]; tt[0] = v;
+            for (int k = 1; k < want && c; ++k) { tt[k] += 1; c = tt[k] == 0; }
+        }
+        __syncwarp();
+        warp_mul_lo(xn, x, tt, want, cols);
+        for (int k = lane; k < want; k += 32) x[k] = xn[k];
+        __syncwarp();
+    }
+    warp_mul_lo(i2, x, x, WX, cols);                 // 1 / odd(D)^2
+    for (int k = lane; k < WX; k += 32) ax[k] = k < LU ? am[k] : 0;
+    __syncwarp();
+    warp_mul_lo(xn, ax, ax, WX, cols);               // a^2
+    warp_mul_lo(tmp, xn, i2, WX, cols);
+    for (int k = lane; k < WX; k += 32) sc->S1[k] = tmp[k];
+    __syncwarp();
+    if (lane == 0) rt_add(ax, ax, WX);               // 2a
+    __syncwarp();
+    warp_mul_lo(tmp, ax, i2, WX, cols);
+    for (int k = lane; k < WX; k += 32) sc->S2[k] = tmp[k];
+    for (int k = lane; k < WX; k += 32) { u64 v = k < LG ? G[(size_t)k * n + sc->q] : 0; xn[k] = v; if (k < LG) sc->Gq[k] = v; }
+    __syncwarp();
+    warp_mul_lo(tmp, xn, i2, WX, cols);
+    for (int k = lane; k < WX; k += 32) sc->S3[k] = tmp[k];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -675,6 +732,11 @@ k_update(u64* __restrict__ C, size_t ps, int ld, int nrows, const u64* __restric
 #pragma unroll
             for (int k = 2 * L; k < N; ++k) rp[c][k] = sg;
         }
+        u32 rpnz = 0;
+#pragma unroll
+        for (int c = 0; c < CP; ++c)
+#pragma unroll
+            for (int k = 0; k < 2 * L; ++k) rpnz |= rp[c][k];
         const int rend = min(RT, nrows - row0);
         for (int r = 0; r < rend; ++r) {
             size_t off = (size_t)(row0 + r) * ld + col;
@@ -693,6 +755,13 @@ k_update(u64* __restrict__ C, size_t ps, int ld, int nrows, const u64* __restric
                     cv[0][2 * l] = (u32)v; cv[0][2 * l + 1] = (u32)(v >> 32);
                 }
             }
+            // zero skip: C[i][k] == 0 and C[p][k] == 0  =>  C'[i][k] == 0: nothing to compute or store
+            u32 nzc = rpnz;
+#pragma unroll
+            for (int c = 0; c < CP; ++c)
+#pragma unroll
+                for (int k = 0; k < 2 * L; ++k) nzc |= cv[c][k];
+            if (nzc == 0) continue;
             u64 res[CP][L];
 #pragma unroll
             for (int c = 0; c < CP; ++c) {
@@ -833,64 +902,77 @@ template <int L, int LSRC, int LOUT>
 __global__ void __launch_bounds__(128)
 k_colsum1(const u64* __restrict__ C, size_t ps, int ld, int m, int rows_per_chunk,
           const u64* __restrict__ s, size_t ss, u64* __restrict__ part, const Scalars* sc) {
-    __shared__ u64 sMag[LSRC];
-    __shared__ int sSign;
+    constexpr int RB = 64;                 // rows whose factors are staged in shared memory at a time
+    __shared__ u64 sMag[RB][LSRC];
+    __shared__ int sSign[RB];
     if (sc->status != ST_RUN) return;
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    int r0 = 1 + blockIdx.y * rows_per_chunk;
-    int r1 = min(m + 1, r0 + rows_per_chunk);
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r0 = 1 + blockIdx.y * rows_per_chunk;
+    const int r1 = min(m + 1, r0 + rows_per_chunk);
     u64 acc[LOUT];
 #pragma unroll
     for (int l = 0; l < LOUT; ++l) acc[l] = 0;
-    for (int i = r0; i < r1; ++i) {
+    for (int base = r0; base < r1; base += RB) {
         __syncthreads();
-        if (threadIdx.x == 0) {
-            u64 x[LSRC];
-            load_planar<LSRC>(x, s, ss, (size_t)i);
-            bool neg = (i64)x[LSRC - 1] < 0;
-            u64 o = 0;
+        if (threadIdx.x < RB) {
+            int i = base + threadIdx.x;
+            int sg = 0;
+            if (i < r1) {
+                u64 x[LSRC];
+                load_planar<LSRC>(x, s, ss, (size_t)i);
+                bool neg = (i64)x[LSRC - 1] < 0;
+                u64 o = 0;
+                if (neg) {
+                    u64 c = 1;
+#pragma unroll
+                    for (int l = 0; l < LSRC; ++l) { u64 v = ~x[l] + c; c = (c && v == 0) ? 1 : 0; x[l] = v; }
+                }
+#pragma unroll
+                for (int l = 0; l < LSRC; ++l) { sMag[threadIdx.x][l] = x[l]; o |= x[l]; }
+                sg = o == 0 ? 0 : (neg ? -1 : 1);
+            }
+            sSign[threadIdx.x] = sg;
+        }
+        __syncthreads();
+        if (k >= ld) continue;
+        const int rn = min(RB, r1 - base);
+        for (int r = 0; r < rn; ++r) {
+            int sgn = sSign[r];
+            if (sgn == 0) continue;        // rows with a zero factor are never read
+            u64 x[L];
+            load_planar<L>(x, C, ps, (size_t)(base + r) * ld + k);
+            u64 any = 0;
+#pragma unroll
+            for (int l = 0; l < L; ++l) any |= x[l];
+            if (any == 0) continue;        // zero entries contribute nothing
+            u64 sm[LSRC];
+#pragma unroll
+            for (int l = 0; l < LSRC; ++l) sm[l] = sMag[r][l];
+            bool neg = (i64)x[L - 1] < 0;
             if (neg) {
                 u64 c = 1;
 #pragma unroll
-                for (int l = 0; l < LSRC; ++l) { u64 v = ~x[l] + c; c = (c && v == 0) ? 1 : 0; x[l] = v; }
+                for (int l = 0; l < L; ++l) { u64 v = ~x[l] + c; c = (c && v == 0) ? 1 : 0; x[l] = v; }
+                sgn = -sgn;
             }
+            u64 pr[LSRC + L];
+            mul_full_ct<LSRC, L>(pr, sm, x);
+            if (sgn > 0) {
+                u64 cf = 0;
 #pragma unroll
-            for (int l = 0; l < LSRC; ++l) { sMag[l] = x[l]; o |= x[l]; }
-            sSign = o == 0 ? 0 : (neg ? -1 : 1);
-        }
-        __syncthreads();
-        int sgn = sSign;
-        if (sgn == 0 || k >= ld) continue;
-        u64 sm[LSRC];
+                for (int l = 0; l < LOUT; ++l) {
+                    u64 b = l < LSRC + L ? pr[l] : 0;
+                    u64 v = acc[l] + b; u64 c1 = v < b; u64 v2 = v + cf; u64 c2 = v2 < v;
+                    acc[l] = v2; cf = c1 + c2;
+                }
+            } else {
+                u64 bf = 0;
 #pragma unroll
-        for (int l = 0; l < LSRC; ++l) sm[l] = sMag[l];
-        u64 x[L];
-        load_planar<L>(x, C, ps, (size_t)i * ld + k);
-        bool neg = (i64)x[L - 1] < 0;
-        if (neg) {
-            u64 c = 1;
-#pragma unroll
-            for (int l = 0; l < L; ++l) { u64 v = ~x[l] + c; c = (c && v == 0) ? 1 : 0; x[l] = v; }
-            sgn = -sgn;
-        }
-        u64 pr[LSRC + L];
-        mul_full_ct<LSRC, L>(pr, sm, x);
-        // acc +/-= pr (zero extended)
-        if (sgn > 0) {
-            u64 cf = 0;
-#pragma unroll
-            for (int l = 0; l < LOUT; ++l) {
-                u64 b = l < LSRC + L ? pr[l] : 0;
-                u64 v = acc[l] + b; u64 c1 = v < b; u64 v2 = v + cf; u64 c2 = v2 < v;
-                acc[l] = v2; cf = c1 + c2;
-            }
-        } else {
-            u64 bf = 0;
-#pragma unroll
-            for (int l = 0; l < LOUT; ++l) {
-                u64 b = l < LSRC + L ? pr[l] : 0;
-                u64 v = acc[l] - b; u64 b1 = acc[l] < b; u64 v2 = v - bf; u64 b2 = v < bf;
-                acc[l] = v2; bf = b1 + b2;
+                for (int l = 0; l < LOUT; ++l) {
+                    u64 b = l < LSRC + L ? pr[l] : 0;
+                    u64 v = acc[l] - b; u64 b1 = acc[l] < b; u64 v2 = v - bf; u64 b2 = v < bf;
+                    acc[l] = v2; bf = b1 + b2;
+                }
             }
         }
     }
@@ -898,7 +980,7 @@ k_colsum1(const u64* __restrict__ C, size_t ps, int ld, int m, int rows_per_chun
 }
 
 template <int LOUT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(64)
 k_colsum2(const u64* __restrict__ part, int ld, int chunks, int negate, u64* __restrict__ out,
           Scalars* sc) {
     if (sc->status != ST_RUN) return;
@@ -1042,6 +1124,81 @@ k_gamma_init_general(const u64* __restrict__ C, size_t ps, int ld, int m, int n,
             acc[l] = v2; cf = c1 + c2;
         }
         store_planar<LG>(G, (size_t)n, (size_t)j, acc);
+    }
+}
+
+// per-column steepest-edge recurrence, fixed width WX = LG + 4 limbs (register resident, 32-bit limb
+// IMAD chains); used whenever D^2 has at most 256 trailing zero bits (E2 <= 4).
+template <int L>
+__global__ void __launch_bounds__(128)
+k_gamma_update_t(int n, const unsigned char* __restrict__ inbasis, const u64* __restrict__ nu,
+                 const u64* __restrict__ sigma, u64* __restrict__ G, const Scalars* sc) {
+    constexpr int LU = L + 2, LS = 2 * L + 6, LG = 2 * L + 5, WX = LG + 4, N = 2 * WX;
+    if (sc->status != ST_RUN) return;
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    if (inbasis[j] || j == sc->leaving) return;   // entering: None; leaving: set by k_finalize
+    u32 nv[N], x[N];
+    {
+        u64 top = nu[(size_t)(LU - 1) * n + j];
+        u64 sgx = (i64)top < 0 ? ~0ull : 0ull;
+        u64 any = 0;
+#pragma unroll
+        for (int l = 0; l < WX; ++l) {
+            u64 v = l < LU ? nu[(size_t)l * n + j] : sgx;
+            if (l < LU) any |= v;
+            nv[2 * l] = (u32)v; nv[2 * l + 1] = (u32)(v >> 32);
+        }
+        u32 g[N];
+#pragma unroll
+        for (int l = 0; l < WX; ++l) {
+            u64 v = l < LG ? G[(size_t)l * n + j] : 0;
+            g[2 * l] = (u32)v; g[2 * l + 1] = (u32)(v >> 32);
+        }
+        mp_mul_lo<N>(x, g, reinterpret_cast<const u32*>(sc->S1));        // a^2/D^2 Ghat
+        if (any != 0) {
+            u32 sg[N], y[N], z[N];
+            u64 tops = sigma[(size_t)(LS - 1) * n + j];
+            u64 sgs = (i64)tops < 0 ? ~0ull : 0ull;
+#pragma unroll
+            for (int l = 0; l < WX; ++l) {
+                u64 v = l < LS ? sigma[(size_t)l * n + j] : sgs;
+                sg[2 * l] = (u32)v; sg[2 * l + 1] = (u32)(v >> 32);
+            }
+            mp_mul_lo<N>(y, nv, sg);                                          // nu sigma
+            mp_mul_lo<N>(z, y, reinterpret_cast<const u32*>(sc->S2));       // 2a/D^2 nu sigma
+            {
+                u32 bf = 0;
+#pragma unroll
+                for (int k = 0; k < N; ++k) {
+                    u32 v = x[k] - z[k]; u32 b1 = x[k] < z[k]; u32 v2 = v - bf; u32 b2 = v < bf;
+                    x[k] = v2; bf = b1 + b2;
+                }
+            }
+            mp_mul_lo<N>(y, nv, nv);                                          // nu^2
+            mp_mul_lo<N>(z, y, reinterpret_cast<const u32*>(sc->S3));       // Gq/D^2 nu^2
+            {
+                u32 cf = 0;
+#pragma unroll
+                for (int k = 0; k < N; ++k) {
+                    u32 v = x[k] + z[k]; u32 c1 = v < z[k]; u32 v2 = v + cf; u32 c2 = v2 < v;
+                    x[k] = v2; cf = c1 + c2;
+                }
+            }
+        }
+    }
+    // shift right by t2 (run-time word offset: go through a small local array)
+    const int t2 = sc->t2;
+    const int tw = t2 >> 5, tb = t2 & 31;
+    u32 xs[N + 1];
+#pragma unroll
+    for (int k = 0; k < N; ++k) xs[k] = x[k];
+    xs[N] = 0;
+#pragma unroll
+    for (int l = 0; l < LG; ++l) {
+        u32 a0 = xs[min(2 * l + tw, N)], a1 = xs[min(2 * l + tw + 1, N)], a2 = xs[min(2 * l + tw + 2, N)];
+        u32 lo = __funnelshift_r(a0, a1, tb), hi = __funnelshift_r(a1, a2, tb);
+        G[(size_t)l * n + j] = (u64)lo | ((u64)hi << 32);
     }
 }
 

@@ -41,27 +41,43 @@ static inline int log2i(int L) { int k = 0; while ((1 << k) < L) ++k; return k; 
 // ------------------------------------------------------------------------------------------------
 // allocation
 // ------------------------------------------------------------------------------------------------
-static void free_dev(void* p) { if (p) cudaFree(p); }
+// Device memory comes from the stream-ordered pool of the device with an unlimited release threshold:
+// after the first solve of a process, allocation and promotion (K9) never reach the driver allocator.
+static void pool_setup(int device) {
+    static bool done[64] = {false};
+    if (device < 0 || device >= 64 || done[device]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    done[device] = true;
+}
+template <class T>
+static cudaError_t dev_alloc(T** p, size_t bytes, cudaStream_t st) {
+    return cudaMallocAsync((void**)p, bytes ? bytes : 8, st);
+}
+static void free_dev_on(void* p, cudaStream_t st) { if (p) cudaFreeAsync(p, st); }
 
 static int alloc_width_buffers(rg_context* ctx, int L) {
     const size_t ld = ctx->ld;
     const size_t n = ctx->n;
-    CK(cudaMalloc(&ctx->u, sizeof(u64) * LU_of(L) * ld));
-    CK(cudaMalloc(&ctx->rowp, sizeof(u64) * L * ld));
-    CK(cudaMalloc(&ctx->omega, sizeof(u64) * LW_of(L) * ld));
-    CK(cudaMalloc(&ctx->omega_part, sizeof(u64) * ctx->work_chunks * LW_of(L) * ld));
-    CK(cudaMalloc(&ctx->tmprow, sizeof(u64) * LU_of(L) * ld));
-    CK(cudaMalloc(&ctx->kappa, sizeof(u64) * LU_of(L) * n));
-    CK(cudaMalloc(&ctx->nu, sizeof(u64) * LU_of(L) * n));
-    CK(cudaMalloc(&ctx->sigma, sizeof(u64) * LS_of(L) * n));
+    CK(dev_alloc(&ctx->u, sizeof(u64) * LU_of(L) * ld, ctx->stream));
+    CK(dev_alloc(&ctx->rowp, sizeof(u64) * L * ld, ctx->stream));
+    CK(dev_alloc(&ctx->omega, sizeof(u64) * LW_of(L) * ld, ctx->stream));
+    CK(dev_alloc(&ctx->omega_part, sizeof(u64) * ctx->work_chunks * LW_of(L) * ld, ctx->stream));
+    CK(dev_alloc(&ctx->tmprow, sizeof(u64) * LU_of(L) * ld, ctx->stream));
+    CK(dev_alloc(&ctx->kappa, sizeof(u64) * LU_of(L) * n, ctx->stream));
+    CK(dev_alloc(&ctx->nu, sizeof(u64) * LU_of(L) * n, ctx->stream));
+    CK(dev_alloc(&ctx->sigma, sizeof(u64) * LS_of(L) * n, ctx->stream));
     CK(cudaMemsetAsync(ctx->u, 0, sizeof(u64) * LU_of(L) * ld, ctx->stream));
     CK(cudaMemsetAsync(ctx->rowp, 0, sizeof(u64) * L * ld, ctx->stream));
     CK(cudaMemsetAsync(ctx->kappa, 0, sizeof(u64) * LU_of(L) * n, ctx->stream));
     return RG_OK;
 }
 static void free_width_buffers(rg_context* ctx) {
-    free_dev(ctx->u); free_dev(ctx->rowp); free_dev(ctx->omega); free_dev(ctx->omega_part);
-    free_dev(ctx->tmprow); free_dev(ctx->kappa); free_dev(ctx->nu); free_dev(ctx->sigma);
+    free_dev_on(ctx->u, ctx->stream); free_dev_on(ctx->rowp, ctx->stream); free_dev_on(ctx->omega, ctx->stream); free_dev_on(ctx->omega_part, ctx->stream);
+    free_dev_on(ctx->tmprow, ctx->stream); free_dev_on(ctx->kappa, ctx->stream); free_dev_on(ctx->nu, ctx->stream); free_dev_on(ctx->sigma, ctx->stream);
     ctx->u = ctx->rowp = ctx->omega = ctx->omega_part = ctx->tmprow = nullptr;
     ctx->kappa = ctx->nu = ctx->sigma = nullptr;
 }
@@ -77,8 +93,12 @@ extern "C" int rg_create(const rg_options* opts, rg_context** out) {
     ctx->L = L;
     *out = ctx;
     CK(cudaSetDevice(ctx->device));
+    pool_setup(ctx->device);
     CK(cudaStreamCreate(&ctx->stream));   // blocking: orders with the synchronous copies on the null stream
-    CK(cudaMalloc(&ctx->sc, sizeof(Scalars)));
+    CK(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ctx->ev_side0, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->ev_side1, cudaEventDisableTiming));
+    CK(dev_alloc(&ctx->sc, sizeof(Scalars), ctx->stream));
     CK(cudaMemset(ctx->sc, 0, sizeof(Scalars)));
     CK(cudaHostAlloc(&ctx->hm, sizeof(HostMirror), cudaHostAllocMapped));
     memset(ctx->hm, 0, sizeof(HostMirror));
@@ -91,12 +111,15 @@ extern "C" int rg_destroy(rg_context* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     free_width_buffers(ctx);
-    free_dev(ctx->carry); free_dev(ctx->A.colptr); free_dev(ctx->A.rowidx); free_dev(ctx->A.vals);
-    free_dev(ctx->cost); free_dev(ctx->rhs); free_dev(ctx->basis); free_dev(ctx->inbasis);
-    free_dev(ctx->G); free_dev(ctx->cand); free_dev(ctx->score); free_dev(ctx->sc); free_dev(ctx->svec);
+    free_dev_on(ctx->carry, ctx->stream); free_dev_on(ctx->A.colptr, ctx->stream); free_dev_on(ctx->A.rowidx, ctx->stream); free_dev_on(ctx->A.vals, ctx->stream);
+    free_dev_on(ctx->cost, ctx->stream); free_dev_on(ctx->rhs, ctx->stream); free_dev_on(ctx->basis, ctx->stream); free_dev_on(ctx->inbasis, ctx->stream);
+    free_dev_on(ctx->G, ctx->stream); free_dev_on(ctx->cand, ctx->stream); free_dev_on(ctx->score, ctx->stream); free_dev_on(ctx->sc, ctx->stream); free_dev_on(ctx->svec, ctx->stream);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->hm) cudaFreeHost(ctx->hm);
     if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); for (int k = 0; k < 8; ++k) cudaEventDestroy(ctx->evp[k]); }
     if (ctx->evt0) { cudaEventDestroy(ctx->evt0); cudaEventDestroy(ctx->evt1); }
+    if (ctx->ev_side0) { cudaEventDestroy(ctx->ev_side0); cudaEventDestroy(ctx->ev_side1); }
+    if (ctx->side) cudaStreamDestroy(ctx->side);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return RG_OK;
@@ -117,24 +140,24 @@ extern "C" int rg_load_csc(rg_context* ctx, int32_t m, int32_t n, const int64_t*
     for (long long j = 0; j < n; ++j)
         for (long long k = colptr[j]; k < colptr[j + 1]; ++k)
             if (rowidx[k] < 0 || rowidx[k] >= m) { ctx->err = "rg_load_csc: row index out of range"; return RG_ERR_ARG; }
-    CK(cudaMalloc(&ctx->A.colptr, sizeof(long long) * (n + 1)));
-    CK(cudaMalloc(&ctx->A.rowidx, sizeof(int) * std::max<long long>(nnz, 1)));
-    CK(cudaMalloc(&ctx->A.vals, sizeof(long long) * std::max<long long>(nnz, 1)));
+    CK(dev_alloc(&ctx->A.colptr, sizeof(long long) * (n + 1), ctx->stream));
+    CK(dev_alloc(&ctx->A.rowidx, sizeof(int) * std::max<long long>(nnz, 1), ctx->stream));
+    CK(dev_alloc(&ctx->A.vals, sizeof(long long) * std::max<long long>(nnz, 1), ctx->stream));
     CK(cudaMemcpy(ctx->A.colptr, colptr, sizeof(long long) * (n + 1), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->A.rowidx, rowidx, sizeof(int) * nnz, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->A.vals, vals, sizeof(long long) * nnz, cudaMemcpyHostToDevice));
-    CK(cudaMalloc(&ctx->cost, sizeof(long long) * n));
+    CK(dev_alloc(&ctx->cost, sizeof(long long) * n, ctx->stream));
     CK(cudaMemset(ctx->cost, 0, sizeof(long long) * n));
-    CK(cudaMalloc(&ctx->rhs, sizeof(long long) * m));
+    CK(dev_alloc(&ctx->rhs, sizeof(long long) * m, ctx->stream));
     CK(cudaMemset(ctx->rhs, 0, sizeof(long long) * m));
-    CK(cudaMalloc(&ctx->basis, sizeof(int) * m));
-    CK(cudaMalloc(&ctx->inbasis, n));
-    CK(cudaMalloc(&ctx->cand, sizeof(int) * 1024));
-    CK(cudaMalloc(&ctx->score, sizeof(double) * std::max(m, n)));
-    CK(cudaMalloc(&ctx->svec, sizeof(u64) * ctx->ld));
-    ctx->work_chunks = std::max(1, std::min(64, cdiv(m, 64)));
-    CK(cudaMalloc(&ctx->carry, sizeof(u64) * ctx->L * ctx->plane));
-    CK(cudaMalloc(&ctx->G, sizeof(u64) * LG_of(ctx->L) * n));
+    CK(dev_alloc(&ctx->basis, sizeof(int) * m, ctx->stream));
+    CK(dev_alloc(&ctx->inbasis, n, ctx->stream));
+    CK(dev_alloc(&ctx->cand, sizeof(int) * 1024, ctx->stream));
+    CK(dev_alloc(&ctx->score, sizeof(double) * std::max(m, n), ctx->stream));
+    CK(dev_alloc(&ctx->svec, sizeof(u64) * ctx->ld, ctx->stream));
+    ctx->work_chunks = std::max(1, std::min(16, cdiv(m, 256)));
+    CK(dev_alloc(&ctx->carry, sizeof(u64) * ctx->L * ctx->plane, ctx->stream));
+    CK(dev_alloc(&ctx->G, sizeof(u64) * LG_of(ctx->L) * n, ctx->stream));
     CK(cudaMemset(ctx->G, 0, sizeof(u64) * LG_of(ctx->L) * n));
     RG_TRY(alloc_width_buffers(ctx, ctx->L));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -230,7 +253,7 @@ static void launch_work_t(rg_context* ctx) {
     dim3 grid(cdiv(ctx->ld, 128), ctx->work_chunks);
     LAUNCH((k_colsum1<L, LU, LW>), grid, 128, ctx->carry, ctx->plane, ctx->ld, ctx->m, rpc, ctx->u,
            (size_t)ctx->ld, ctx->omega_part, ctx->sc);
-    LAUNCH((k_colsum2<LW>), cdiv(ctx->ld, 256), 256, ctx->omega_part, ctx->ld, ctx->work_chunks, 0,
+    LAUNCH((k_colsum2<LW>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, ctx->work_chunks, 0,
            ctx->omega, ctx->sc);
 }
 static void launch_work(rg_context* ctx) { DISPATCH_L(ctx->L, launch_work_t, ctx); }
@@ -264,10 +287,25 @@ static void launch_se_dots_t(rg_context* ctx) {
     LAUNCH((k_coldot<LW, LS>), cdiv(ctx->n, 256), 256, ctx->omega, (size_t)ctx->ld, ctx->n, ctx->A.colptr,
            ctx->A.rowidx, ctx->A.vals, ctx->inbasis, ctx->cost, 0, L, ctx->sigma, ctx->sc);
 }
+template <int L>
+static void launch_gamma_update_t(rg_context* ctx) {
+    LAUNCH((k_gamma_update_t<L>), cdiv(ctx->n, 128), 128, ctx->n, ctx->inbasis, ctx->nu, ctx->sigma, ctx->G,
+           ctx->sc);
+}
 static void launch_se_update(rg_context* ctx) {
     DISPATCH_L(ctx->L, launch_se_dots_t, ctx);
-    LAUNCH(k_gamma_update, cdiv(ctx->n, 128), 128, ctx->n, ctx->L, ctx->inbasis, ctx->nu, ctx->sigma, ctx->G,
-           ctx->sc);
+    int E2 = (2 * ctx->t_cur + 63) / 64;
+    if (E2 <= 4 && ctx->L <= 8) {
+        switch (ctx->L) {
+            case 1: launch_gamma_update_t<1>(ctx); break;
+            case 2: launch_gamma_update_t<2>(ctx); break;
+            case 4: launch_gamma_update_t<4>(ctx); break;
+            default: launch_gamma_update_t<8>(ctx); break;
+        }
+    } else {
+        LAUNCH(k_gamma_update, cdiv(ctx->n, 128), 128, ctx->n, ctx->L, ctx->inbasis, ctx->nu, ctx->sigma, ctx->G,
+               ctx->sc);
+    }
 }
 
 template <int L>
@@ -284,16 +322,16 @@ static int promote(rg_context* ctx) {
     int Lold = ctx->L, Lnew = Lold * 2;
     if (Lnew > RG_MAXL) { ctx->err = "numerators exceed 16 limbs"; return RG_ERR_OVERFLOW; }
     u64* nc = nullptr;
-    CK(cudaMalloc(&nc, sizeof(u64) * Lnew * ctx->plane));
+    CK(dev_alloc(&nc, sizeof(u64) * Lnew * ctx->plane, ctx->stream));
     CK(cudaMemcpyAsync(nc, ctx->carry, sizeof(u64) * Lold * ctx->plane, cudaMemcpyDeviceToDevice, ctx->stream));
     LAUNCH(k_sign_extend, 148 * 8, 256, nc, ctx->plane, ctx->plane, Lold, Lnew);
     u64* ng = nullptr;
-    CK(cudaMalloc(&ng, sizeof(u64) * LG_of(Lnew) * ctx->n));
+    CK(dev_alloc(&ng, sizeof(u64) * LG_of(Lnew) * ctx->n, ctx->stream));
     CK(cudaMemsetAsync(ng, 0, sizeof(u64) * LG_of(Lnew) * ctx->n, ctx->stream));
     CK(cudaMemcpyAsync(ng, ctx->G, sizeof(u64) * LG_of(Lold) * ctx->n, cudaMemcpyDeviceToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    free_dev(ctx->carry); ctx->carry = nc;
-    free_dev(ctx->G); ctx->G = ng;
+    free_dev_on(ctx->carry, ctx->stream); ctx->carry = nc;
+    free_dev_on(ctx->G, ctx->stream); ctx->G = ng;
     free_width_buffers(ctx);
     ctx->L = Lnew;
     RG_TRY(alloc_width_buffers(ctx, Lnew));
@@ -319,10 +357,18 @@ static int do_pivot(rg_context* ctx, int q, int fixed_row, bool want_se, bool re
         if (want_se) launch_work(ctx);
         if (prof) cudaEventRecord(ctx->evp[2], ctx->stream);
         int E = (ctx->t_cur + 63) / 64;
-        LAUNCH(k_scalars, 1, 1, ctx->u, (size_t)ctx->ld, ctx->L, want_se ? 1 : 0, ctx->G, ctx->n, E, ctx->sc);
+        LAUNCH(k_scalars, 1, 1, ctx->u, (size_t)ctx->ld, ctx->L, E, ctx->sc);
+        if (want_se) {   // steepest-edge scalars on the side stream, overlapped with K1
+            cudaEventRecord(ctx->ev_side0, ctx->stream);
+            cudaStreamWaitEvent(ctx->side, ctx->ev_side0, 0);
+            k_scalars_se<<<1, 32, 0, ctx->side>>>(ctx->L, ctx->G, ctx->n, ctx->sc);
+            ctx->launches++;
+            cudaEventRecord(ctx->ev_side1, ctx->side);
+        }
         if (prof) cudaEventRecord(ctx->ev0, ctx->stream);
         launch_update(ctx, E);
         if (prof) cudaEventRecord(ctx->ev1, ctx->stream);
+        if (want_se) cudaStreamWaitEvent(ctx->stream, ctx->ev_side1, 0);
         LAUNCH(k_finalize, 1, 1, ctx->basis, ctx->inbasis, ctx->L, ctx->G, ctx->n, LG_of(ctx->L),
                want_se ? 1 : 0, ctx->sc, ctx->hm_dev);
         if (want_se) launch_se_update(ctx);
@@ -402,7 +448,7 @@ static void launch_phase_sums_t(rg_context* ctx) {
     dim3 grid(cdiv(ctx->ld, 128), ctx->work_chunks);
     LAUNCH((k_colsum1<L, 1, LU>), grid, 128, ctx->carry, ctx->plane, ctx->ld, ctx->m, rpc, ctx->svec,
            (size_t)ctx->ld, ctx->omega_part, ctx->sc);
-    LAUNCH((k_colsum2<LU>), cdiv(ctx->ld, 256), 256, ctx->omega_part, ctx->ld, ctx->work_chunks, 1,
+    LAUNCH((k_colsum2<LU>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, ctx->work_chunks, 1,
            ctx->tmprow, ctx->sc);
 }
 
@@ -589,11 +635,11 @@ __global__ void k_gather(u64* out, const u64* base, size_t stride, size_t idx0, 
 static int export_planar(rg_context* ctx, const u64* base, size_t stride, size_t idx0, size_t step,
                          int count, int nl, uint64_t* out) {
     u64* tmp = nullptr;
-    CK(cudaMalloc(&tmp, sizeof(u64) * (size_t)count * nl));
+    CK(dev_alloc(&tmp, sizeof(u64) * (size_t)count * nl, ctx->stream));
     LAUNCH(k_gather, cdiv(count, 256), 256, tmp, base, stride, idx0, step, count, nl);
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaMemcpy(out, tmp, sizeof(u64) * (size_t)count * nl, cudaMemcpyDeviceToHost));
-    cudaFree(tmp);
+    cudaFreeAsync(tmp, ctx->stream);
     return RG_OK;
 }
 
