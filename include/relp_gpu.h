@@ -66,6 +66,8 @@ typedef struct rg_options {
     int32_t initial_limbs;   /* 1, 2, 4, 8 or 16; 0 = default (2) */
     int32_t rank;            /* row-shard rank (0 when single GPU) */
     int32_t world;           /* number of row shards (1 when single GPU) */
+    const void* nccl_unique_id;  /* world > 1: the 128-byte ncclUniqueId shared by all ranks (rg_nccl_unique_id
+                                    on rank 0, broadcast by the host, e.g. torch.distributed) */
 } rg_options;
 
 typedef struct rg_stats {
@@ -98,6 +100,11 @@ typedef struct rg_pivot_info {   /* BasisChangeComputationInfo, tableau/mod.rs:2
 int rg_create(const rg_options* opts, rg_context** out);   /* `IM::create_*` allocate; Drop <-> rg_destroy */
 int rg_destroy(rg_context* ctx);
 const char* rg_last_error(const rg_context* ctx);
+/* Row-sharded operation (one process per GPU): every rank creates a context with the same `world` and the
+ * same NCCL id and then issues the SAME sequence of calls; the carry rows are block-distributed, the cost
+ * row, pricing data and all scalars are replicated, and every call returns identical results on every
+ * rank.  Returns the id size (128) or an error. */
+int rg_nccl_unique_id(void* out, int32_t bytes);
 
 /* ---- problem upload: MatrixProvider (matrix_provider/mod.rs:37-134) ---------------------------- */
 /* All provider columns as integer CSC (column(j), :52), row indices ascending within a column.  */

@@ -47,7 +47,10 @@ typedef struct rh_options {
     int32_t fused;                /* 1: rg_iterate (one host sync per pivot); 0: trait-shaped calls */
     int64_t max_pivots;           /* 0 = unlimited */
     int32_t profile;              /* 1: CUDA events around every K1 launch (rg_set_profile) */
+    int32_t rank;                 /* row-shard rank / world (world <= 1: single GPU) */
+    int32_t world;
     int32_t reserved;
+    const void* nccl_unique_id;   /* world > 1: see rg_options */
 } rh_options;
 
 typedef struct rh_result rh_result;   /* opaque; owns its buffers */

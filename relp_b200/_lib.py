@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(HERE, "librelp_gpu.so")
 
 class rg_options(C.Structure):
     _fields_ = [("device", C.c_int32), ("initial_limbs", C.c_int32), ("rank", C.c_int32),
-                ("world", C.c_int32)]
+                ("world", C.c_int32), ("nccl_unique_id", C.c_void_p)]
 
 
 class rg_stats(C.Structure):
@@ -44,7 +44,8 @@ class rh_trace_entry(C.Structure):
 class rh_options(C.Structure):
     _fields_ = [("device", C.c_int32), ("initial_limbs", C.c_int32), ("rule", C.c_int32),
                 ("fused", C.c_int32), ("max_pivots", C.c_int64), ("profile", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("rank", C.c_int32), ("world", C.c_int32), ("reserved", C.c_int32),
+                ("nccl_unique_id", C.c_void_p)]
 
 
 # every symbol include/*.h declares: name -> (restype, argtypes)
@@ -53,6 +54,7 @@ SYMBOLS = {
     "rg_create": (C.c_int, [C.POINTER(rg_options), C.POINTER(P)]),
     "rg_destroy": (C.c_int, [P]),
     "rg_last_error": (C.c_char_p, [P]),
+    "rg_nccl_unique_id": (C.c_int, [C.c_void_p, C.c_int32]),
     "rg_load_csc": (C.c_int, [P, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int32),
                               C.POINTER(C.c_int64)]),
     "rg_set_rhs": (C.c_int, [P, C.POINTER(C.c_int64)]),

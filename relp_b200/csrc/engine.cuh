@@ -16,7 +16,7 @@ enum DevStatus { ST_RUN = 0, ST_OPTIMAL = 1, ST_UNBOUNDED = 2, ST_PROMOTE = 3, S
 struct Scalars {
     int status;          // DevStatus
     int q;               // entering provider column id
-    int p;               // pivot row as carry row index (1..m)
+    int p;               // pivot row as LOCAL carry row index (1..nloc), -1 when another rank owns it
     int leaving;         // column id leaving the basis
     int sgn;             // sign of the pivot element numerator a = u[p]
     int t, E;            // ctz(D) and ceil(t/64): extra limbs the exact division needs
@@ -31,8 +31,12 @@ struct Scalars {
     int last_selected;   // FirstProfitableWithMemory state (-1 = none)
     int found;           // generic "search hit" index (-1 = none)
     int bp_nonzero;      // remove_artificial: is b_p != 0
+    int pg;              // pivot row as global carry row index (1..m)
+    int row_lo, nloc;    // this rank's block of constraint rows [row_lo, row_lo + nloc)
+    int rank, world;
     int pad;
     u64 D[RG_MAXL];          // current denominator (positive)
+    u64 a[RG_MAXL + 2];      // pivot element numerator u[p] (replicated on every rank)
     u64 Dnew[RG_MAXL];       // |a|: denominator after the pivot
     u64 Dinv[2 * RG_MAXL + 2];   // inverse of odd(D) mod 2^(64 (L+E)), E <= L
     u64 A[2 * RG_MAXL + 2];      // |a| * Dinv mod 2^(64 (L+E))
@@ -67,6 +71,11 @@ __host__ __device__ constexpr int LG_of(int L) { return 2 * L + 5; }      // Gha
 struct rg_context {
     int device = 0;
     int rank = 0, world = 1;
+    int row_lo = 0, nloc = 0;          // constraint rows owned by this rank
+    void* nccl_comm = nullptr;         // ncclComm_t (world > 1)
+    u64* xsend = nullptr;              // exchange buffers (world > 1)
+    u64* xrecv = nullptr;
+    size_t xbytes = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t side = nullptr;          // side stream: steepest-edge scalars overlap the K1 update
     cudaEvent_t ev_side0 = nullptr, ev_side1 = nullptr;

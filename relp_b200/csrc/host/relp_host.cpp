@@ -44,7 +44,9 @@ public:
         rg_options opts{};
         opts.device = o.device;
         opts.initial_limbs = o.initial_limbs;
-        opts.world = 1;
+        opts.world = o.world > 1 ? o.world : 1;
+        opts.rank = o.world > 1 ? o.rank : 0;
+        opts.nccl_unique_id = o.nccl_unique_id;
         check(nullptr, rg_create(&opts, &ctx), "rg_create");
         check(ctx, rg_load_csc(ctx, m, n, mp.p->colptr, mp.p->rowidx, mp.p->vals), "rg_load_csc");
         check(ctx, rg_set_rhs(ctx, mp.p->rhs), "rg_set_rhs");

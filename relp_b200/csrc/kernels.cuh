@@ -74,23 +74,26 @@ __global__ void k_zero(u64* p, size_t n) {
     for (; i < n; i += s) p[i] = 0;
 }
 
-// rows 1..m: b in column 0, 1 on the diagonal.  Row 0: -1 under artificial rows, -sum b(art) in (0,0).
-__global__ void k_init_identity(u64* C, size_t ps, int ld, int m, int L, const long long* rhs,
-                                const int* basis, Scalars* sc) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;   // constraint row 0..m-1
-    if (i >= m) return;
+// local rows: b in column 0, 1 on the diagonal (global column index).
+__global__ void k_init_identity(u64* C, size_t ps, int ld, int nloc, int row_lo, int L, const long long* rhs) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;   // local constraint row
+    if (i >= nloc) return;
+    int g = row_lo + i;
     size_t r = (size_t)(i + 1) * ld;
-    long long b = rhs[i];
+    long long b = rhs[g];
     C[r + 0] = (u64)b;
     for (int l = 1; l < L; ++l) C[l * ps + r + 0] = b < 0 ? ~0ull : 0ull;
-    C[r + (i + 1)] = 1;
-    if (basis[i] < 0) {
-        for (int l = 0; l < L; ++l) C[l * ps + (i + 1)] = ~0ull;   // -1
-    }
+    C[r + (g + 1)] = 1;
+}
+// cost row (replicated on every rank): -1 under artificial rows
+__global__ void k_init_row0(u64* C, size_t ps, int m, int L, const int* basis) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= m) return;
+    if (basis[g] < 0) for (int l = 0; l < L; ++l) C[l * ps + (g + 1)] = ~0ull;   // -1
 }
 // (0,0) = -sum_{artificial rows} b   and scalar state
 __global__ void k_init_scalars(u64* C, size_t ps, int m, int L, const long long* rhs, const int* basis,
-                               Scalars* sc) {
+                               int row_lo, int nloc, int rank, int world, Scalars* sc) {
     if (threadIdx.x || blockIdx.x) return;
     u64 buf[3 * RG_MAXL];
     u64* acc = buf; u64* t = buf + RG_MAXL; u64* mg = buf + 2 * RG_MAXL;
@@ -111,7 +114,8 @@ __global__ void k_init_scalars(u64* C, size_t ps, int m, int L, const long long*
     int bl = rt_bitlen_u(mg, L);
     if (bl > maxbits) maxbits = bl;
     sc->status = ST_RUN;
-    sc->q = -1; sc->p = -1; sc->leaving = 0; sc->sgn = 1;
+    sc->q = -1; sc->p = -1; sc->pg = -1; sc->leaving = 0; sc->sgn = 1;
+    sc->row_lo = row_lo; sc->nloc = nloc; sc->rank = rank; sc->world = world;
     sc->t = 0; sc->E = 0; sc->t2 = 0; sc->E2 = 0;
     sc->maxbits_carry = maxbits; sc->maxbits_new = 0; sc->maxbits_u = 0; sc->maxbits_rowp = 0;
     sc->bits_D = 1; sc->predicted = 0; sc->last_selected = -1; sc->found = -1;
@@ -250,7 +254,7 @@ struct CmpSteepest {
 struct CmpRatio {
     const u64* C; size_t ps; int ld; int L;
     const u64* u; size_t us; int LU;
-    const int* basis;
+    const int* basis; int row_lo;
     __device__ bool eligible(int r) const {
         size_t i = (size_t)r + 1;
         if ((i64)u[(size_t)(LU - 1) * us + i] < 0) return false;
@@ -267,7 +271,7 @@ struct CmpRatio {
         rt_load_planar(ui, LU, u, us, (size_t)r + 1);
         rt_load_planar(uk, LU, u, us, (size_t)s + 1);
         int c = rt_cmp_prod(bi, L, uk, LU, bk, L, ui, LU, ws);   // b_r/u_r ? b_s/u_s
-        return c < 0 || (c == 0 && basis[r] < basis[s]);
+        return c < 0 || (c == 0 && basis[row_lo + r] < basis[row_lo + s]);
     }
 };
 // remove_artificial_basis_variables search (phase_one.rs:245-261): first j (ascending)
@@ -390,12 +394,74 @@ __global__ void __launch_bounds__(1024) k_select_scored(int count, Cmp cmp, cons
             sc->q = bestj;
             if (bestj < 0) sc->status = ST_OPTIMAL; else sc->last_selected = bestj;
         } else if (mode == 1) {
-            sc->p = bestj + 1;
+            sc->p = bestj < 0 ? -1 : bestj + 1;
+            sc->pg = bestj < 0 ? -1 : sc->row_lo + bestj + 1;
             if (bestj < 0) sc->status = ST_UNBOUNDED;
+        } else if (mode == 3) {          // local candidate of a row-sharded ratio test
+            sc->p = bestj < 0 ? -1 : bestj + 1;
+            sc->pg = bestj < 0 ? -1 : sc->row_lo + bestj + 1;
         } else {
             sc->found = bestj;
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// row-sharded ratio test: every rank packs its local candidate, an all-gather exchanges them and
+// every rank reduces them identically (deterministic Bland tie-break), SURVEY section 8e.
+// candidate layout (u64 words): 0 valid, 1 global carry row, 2 basis id, 3 maxbits_u, 4 maxbits_carry,
+// 5.. b numerator (RG_MAXL), then pivot column entry (RG_MAXL + 2)
+// ---------------------------------------------------------------------------------------------
+#define RG_CAND_WORDS (5 + RG_MAXL + RG_MAXL + 2)
+__global__ void k_ratio_pack(const u64* __restrict__ C, size_t ps, int ld, int L, const u64* __restrict__ u,
+                             size_t us, const int* __restrict__ basis, u64* __restrict__ send, const Scalars* sc) {
+    if (threadIdx.x || blockIdx.x) return;
+    for (int k = 0; k < RG_CAND_WORDS; ++k) send[k] = 0;
+    if (sc->status != ST_RUN) return;
+    const int LU = L + 2;
+    send[3] = (u64)sc->maxbits_u;
+    send[4] = (u64)sc->maxbits_carry;
+    int p = sc->p;
+    if (p < 1) return;
+    send[0] = 1;
+    send[1] = (u64)sc->pg;
+    send[2] = (u64)(i64)basis[sc->pg - 1];
+    for (int l = 0; l < L; ++l) send[5 + l] = C[(size_t)l * ps + (size_t)p * ld];
+    for (int l = 0; l < LU; ++l) send[5 + RG_MAXL + l] = u[(size_t)l * us + p];
+}
+__global__ void k_ratio_merge(const u64* __restrict__ recv, int world, int L, Scalars* sc) {
+    if (threadIdx.x || blockIdx.x) return;
+    if (sc->status != ST_RUN) return;
+    const int LU = L + 2;
+    u64 ws[4 * RG_MAXW];
+    int best = -1;
+    int mu = 0, mc = 0;
+    for (int r = 0; r < world; ++r) {
+        const u64* c = recv + (size_t)r * RG_CAND_WORDS;
+        mu = max(mu, (int)c[3]);
+        mc = max(mc, (int)c[4]);
+        if (!c[0]) continue;
+        if (best < 0) { best = r; continue; }
+        const u64* b = recv + (size_t)best * RG_CAND_WORDS;
+        // ratio_r ? ratio_best :  b_r * u_best  vs  b_best * u_r
+        int cmpv = rt_cmp_prod(c + 5, L, b + 5 + RG_MAXL, LU, b + 5, L, c + 5 + RG_MAXL, LU, ws);
+        if (cmpv < 0 || (cmpv == 0 && (i64)c[2] < (i64)b[2])) best = r;
+    }
+    sc->maxbits_u = mu;
+    sc->maxbits_carry = mc;
+    if (best < 0) { sc->status = ST_UNBOUNDED; sc->p = -1; sc->pg = -1; return; }
+    const u64* b = recv + (size_t)best * RG_CAND_WORDS;
+    int pg = (int)b[1];
+    sc->pg = pg;
+    int lo = sc->row_lo;
+    sc->p = (pg - 1 >= lo && pg - 1 < lo + sc->nloc) ? pg - lo : -1;
+    for (int l = 0; l < LU; ++l) sc->a[l] = b[5 + RG_MAXL + l];
+}
+// single GPU: the pivot element is local
+__global__ void k_take_a(const u64* __restrict__ u, size_t us, int L, Scalars* sc) {
+    if (threadIdx.x || blockIdx.x) return;
+    if (sc->status != ST_RUN || sc->p < 1) return;
+    for (int l = 0; l < L + 2; ++l) sc->a[l] = u[(size_t)l * us + sc->p];
 }
 
 template <class Cmp>
@@ -509,22 +575,39 @@ __global__ void k_set_pq(Scalars* sc, int q, int p) {
         if (p >= 0) sc->p = p;
     }
 }
+__global__ void k_set_rows(Scalars* sc, int p_local, int pg) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) { sc->p = p_local; sc->pg = pg; }
+}
 __global__ void k_set_status(Scalars* sc, int st) {
     if (threadIdx.x == 0 && blockIdx.x == 0) sc->status = st;
 }
 
-// stage the pivot row (old values) so the update can run in place
+// stage the pivot row (old values) so the update can run in place.  Row-sharded: the owner copies,
+// the other ranks zero-fill and a sum all-reduce (exact: one non-zero contributor) replicates it.
 template <int L>
 __global__ void __launch_bounds__(256)
 k_copyrow(const u64* __restrict__ C, size_t ps, int ld, u64* __restrict__ rowp, size_t rs,
           Scalars* sc) {
     if (sc->status != ST_RUN) return;
     int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < ld) {
+        u64 x[L];
+        if (sc->p >= 1) load_planar<L>(x, C, ps, (size_t)sc->p * ld + k);
+        else {
+#pragma unroll
+            for (int l = 0; l < L; ++l) x[l] = 0;
+        }
+        store_planar<L>(rowp, rs, (size_t)k, x);
+    }
+}
+template <int L>
+__global__ void __launch_bounds__(256) k_rowbits(const u64* __restrict__ rowp, size_t rs, int ld, Scalars* sc) {
+    if (sc->status != ST_RUN) return;
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
     int bl = 0;
     if (k < ld) {
         u64 x[L];
-        load_planar<L>(x, C, ps, (size_t)sc->p * ld + k);
-        store_planar<L>(rowp, rs, (size_t)k, x);
+        load_planar<L>(x, rowp, rs, (size_t)k);
         bl = bitlen_signed<L>(x);
     }
     bl = warp_max(bl);
@@ -535,7 +618,7 @@ k_copyrow(const u64* __restrict__ C, size_t ps, int ld, u64* __restrict__ rowp, 
 // pivot scalars (one thread): overflow prediction, 2-adic inverse of D, A = |a|/D, u_p' = a - D,
 // steepest-edge scalars.  Sets ST_PROMOTE / ST_FATAL when the update would not fit L limbs.
 // ---------------------------------------------------------------------------------------------
-__global__ void k_scalars(const u64* __restrict__ u, size_t us, int L, int E_host, Scalars* sc) {
+__global__ void k_scalars(int L, int E_host, Scalars* sc) {
     if (threadIdx.x || blockIdx.x) return;
     if (sc->status != ST_RUN) return;
     const int LU = L + 2;
@@ -543,7 +626,7 @@ __global__ void k_scalars(const u64* __restrict__ u, size_t us, int L, int E_hos
     u64* a = buf;               u64* am = buf + RG_MAXW;        u64* dodd = buf + 2 * RG_MAXW;
     u64* inv = buf + 3 * RG_MAXW;  u64* tmp = buf + 4 * RG_MAXW;   u64* ext = buf + 5 * RG_MAXW;
     u64* upv = buf + 6 * RG_MAXW;  u64* dext = buf + 7 * RG_MAXW;  u64* ws = buf + 8 * RG_MAXW;   // 3 slots
-    rt_load_planar(a, LU, u, us, (size_t)sc->p);
+    for (int l = 0; l < LU; ++l) a[l] = sc->a[l];
     int sgn = rt_abs(am, a, LU);
     sc->sgn = sgn;
     int bits_a = rt_bitlen_u(am, LU);
@@ -853,7 +936,7 @@ __global__ void k_finalize(int* basis, unsigned char* inbasis, int L, u64* G, in
                            int want_se, Scalars* sc, HostMirror* hm) {
     if (threadIdx.x || blockIdx.x) return;
     if (sc->status == ST_RUN) {
-        int r = sc->p - 1;
+        int r = sc->pg - 1;
         int leaving = basis[r];
         sc->leaving = leaving;
         basis[r] = sc->q;
@@ -865,13 +948,13 @@ __global__ void k_finalize(int* basis, unsigned char* inbasis, int L, u64* G, in
         for (int l = 0; l < L; ++l) sc->D[l] = sc->Dnew[l];
         sc->maxbits_carry = sc->maxbits_new;
         sc->bits_D = rt_bitlen_u(sc->D, L);
-        hm->pivoted = 1; hm->q_done = sc->q; hm->p_done = sc->p; hm->leaving_done = leaving;
+        hm->pivoted = 1; hm->q_done = sc->q; hm->p_done = sc->pg; hm->leaving_done = leaving;
     }
 }
 
 __global__ void k_mirror(Scalars* sc, HostMirror* hm, int L) {
     if (threadIdx.x || blockIdx.x) return;
-    hm->status = sc->status; hm->q = sc->q; hm->p = sc->p; hm->leaving = sc->leaving;
+    hm->status = sc->status; hm->q = sc->q; hm->p = sc->pg; hm->leaving = sc->leaving;
     hm->t_next = rt_ctz(sc->D, L);
     hm->bits_D = sc->bits_D; hm->maxbits_carry = sc->maxbits_carry; hm->predicted = sc->predicted;
     hm->found = sc->found; hm->sgn = sc->sgn; hm->maxbits_tmp = sc->maxbits_tmp;
@@ -1007,12 +1090,12 @@ k_colsum2(const u64* __restrict__ part, int ld, int chunks, int negate, u64* __r
     if ((threadIdx.x & 31) == 0 && bl) atomicMax(&sc->maxbits_tmp, bl);
 }
 
-// basic cost of every row as an (m+1)-vector of LSRC = 1 limb (artificial / inert rows: 0)
-__global__ void k_basic_costs(const int* basis, const long long* cost, int m, u64* s) {
+// basic cost of every local row as an (nloc+1)-vector of LSRC = 1 limb (artificial / inert rows: 0)
+__global__ void k_basic_costs(const int* basis, const long long* cost, int nloc, int row_lo, u64* s) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i > m) return;
+    if (i > nloc) return;
     long long c = 0;
-    if (i >= 1) { int j = basis[i - 1]; c = j >= 0 ? cost[j] : 0; }
+    if (i >= 1) { int j = basis[row_lo + i - 1]; c = j >= 0 ? cost[j] : 0; }
     s[i] = (u64)c;
 }
 // row 0 of the carry <- tmprow (truncated to L limbs; caller has checked it fits)
@@ -1055,7 +1138,7 @@ __global__ void __launch_bounds__(128)
 k_gamma_init_general(const u64* __restrict__ C, size_t ps, int ld, int m, int n,
                      const long long* __restrict__ colptr, const int* __restrict__ rowidx,
                      const long long* __restrict__ vals, const unsigned char* __restrict__ inbasis,
-                     u64* __restrict__ G, const Scalars* sc) {
+                     u64* __restrict__ G, int add_d2, const Scalars* sc) {
     constexpr int LU = L + 2, LG = 2 * L + 5;
     __shared__ u64 sAcc[4][LG];
     int j = blockIdx.x;
@@ -1112,16 +1195,18 @@ k_gamma_init_general(const u64* __restrict__ C, size_t ps, int ld, int m, int n,
             for (int l = 0; l < LG; ++l) other[l] = sAcc[w][l];
             add_n<LG>(acc, other);
         }
-        u64 d[L], d2[2 * L];
+        if (add_d2) {    // row-sharded: only rank 0 contributes the D^2 term to the sum of parts
+            u64 d[L], d2[2 * L];
 #pragma unroll
-        for (int l = 0; l < L; ++l) d[l] = sc->D[l];
-        mul_full_ct<L, L>(d2, d, d);
-        u64 cf = 0;
+            for (int l = 0; l < L; ++l) d[l] = sc->D[l];
+            mul_full_ct<L, L>(d2, d, d);
+            u64 cf = 0;
 #pragma unroll
-        for (int l = 0; l < LG; ++l) {
-            u64 b = l < 2 * L ? d2[l] : 0;
-            u64 v = acc[l] + b; u64 c1 = v < b; u64 v2 = v + cf; u64 c2 = v2 < v;
-            acc[l] = v2; cf = c1 + c2;
+            for (int l = 0; l < LG; ++l) {
+                u64 b = l < 2 * L ? d2[l] : 0;
+                u64 v = acc[l] + b; u64 c1 = v < b; u64 v2 = v + cf; u64 c2 = v2 < v;
+                acc[l] = v2; cf = c1 + c2;
+            }
         }
         store_planar<LG>(G, (size_t)n, (size_t)j, acc);
     }
@@ -1241,11 +1326,11 @@ k_gamma_update(int n, int L, const unsigned char* __restrict__ inbasis, const u6
     rt_store_planar(G, n, j, x, LG);
 }
 
-// b_p != 0 ?  (remove_artificial_basis_variables, phase_one.rs:250)
-__global__ void k_bp_nonzero(const u64* C, size_t ps, int ld, int L, Scalars* sc) {
+// b_p != 0 ?  (remove_artificial_basis_variables, phase_one.rs:250) -- read from the staged row
+__global__ void k_bp_nonzero(const u64* rowp, size_t rs, int L, Scalars* sc) {
     if (threadIdx.x || blockIdx.x) return;
     u64 o = 0;
-    for (int l = 0; l < L; ++l) o |= C[(size_t)l * ps + (size_t)sc->p * ld];
+    for (int l = 0; l < L; ++l) o |= rowp[(size_t)l * rs];
     sc->bp_nonzero = o != 0;
 }
 

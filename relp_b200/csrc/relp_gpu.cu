@@ -5,8 +5,53 @@
 #include <algorithm>
 #include <vector>
 
+#include <dlfcn.h>
+#include <nccl.h>   // types only: the library is opened lazily so that single-GPU use has no NCCL dependency
+
 #include "../../include/relp_gpu.h"
 #include "kernels.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// NCCL, resolved at run time from whichever libnccl.so.2 the process already holds (torch's) or the
+// system one.  Collectives used per pivot: all-gather of the ratio-test
+// candidates, sum all-reduce of the staged pivot row (one non-zero contributor), all-gather of the
+// work-vector partial sums.
+// ------------------------------------------------------------------------------------------------
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi* nccl_api() {
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api.handle ? &api : nullptr;
+    tried = true;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return nullptr;
+    api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+    api.CommInitRank = (decltype(api.CommInitRank))dlsym(h, "ncclCommInitRank");
+    api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
+    api.AllGather = (decltype(api.AllGather))dlsym(h, "ncclAllGather");
+    api.AllReduce = (decltype(api.AllReduce))dlsym(h, "ncclAllReduce");
+    api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
+    if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllGather || !api.AllReduce) return nullptr;
+    api.handle = h;
+    return &api;
+}
+#define NK(call)                                                                              \
+    do {                                                                                      \
+        ncclResult_t r__ = (call);                                                            \
+        if (r__ != ncclSuccess) {                                                             \
+            ctx->err = std::string(#call) + ": " + (nccl_api()->GetErrorString ? nccl_api()->GetErrorString(r__) : "nccl error"); \
+            return RG_ERR_NCCL;                                                               \
+        }                                                                                     \
+    } while (0)
 
 using namespace rg;
 
@@ -103,7 +148,29 @@ extern "C" int rg_create(const rg_options* opts, rg_context** out) {
     CK(cudaHostAlloc(&ctx->hm, sizeof(HostMirror), cudaHostAllocMapped));
     memset(ctx->hm, 0, sizeof(HostMirror));
     CK(cudaHostGetDevicePointer((void**)&ctx->hm_dev, ctx->hm, 0));
+    if (ctx->world > 1) {
+        if (ctx->rank < 0 || ctx->rank >= ctx->world || !opts->nccl_unique_id) {
+            ctx->err = "rg_create: world > 1 needs a valid rank and nccl_unique_id";
+            return RG_ERR_ARG;
+        }
+        NcclApi* api = nccl_api();
+        if (!api) { ctx->err = "rg_create: libnccl.so.2 not found"; return RG_ERR_NCCL; }
+        ncclUniqueId id;
+        memcpy(&id, opts->nccl_unique_id, sizeof(id));
+        ncclComm_t comm;
+        NK(api->CommInitRank(&comm, ctx->world, id, ctx->rank));
+        ctx->nccl_comm = comm;
+    }
     return RG_OK;
+}
+
+extern "C" int rg_nccl_unique_id(void* out, int32_t bytes) {
+    NcclApi* api = nccl_api();
+    if (!api || !out || bytes < (int32_t)sizeof(ncclUniqueId)) return RG_ERR_NCCL;
+    ncclUniqueId id;
+    if (api->GetUniqueId(&id) != ncclSuccess) return RG_ERR_NCCL;
+    memcpy(out, &id, sizeof(id));
+    return (int)sizeof(id);
 }
 
 extern "C" int rg_destroy(rg_context* ctx) {
@@ -114,11 +181,13 @@ extern "C" int rg_destroy(rg_context* ctx) {
     free_dev_on(ctx->carry, ctx->stream); free_dev_on(ctx->A.colptr, ctx->stream); free_dev_on(ctx->A.rowidx, ctx->stream); free_dev_on(ctx->A.vals, ctx->stream);
     free_dev_on(ctx->cost, ctx->stream); free_dev_on(ctx->rhs, ctx->stream); free_dev_on(ctx->basis, ctx->stream); free_dev_on(ctx->inbasis, ctx->stream);
     free_dev_on(ctx->G, ctx->stream); free_dev_on(ctx->cand, ctx->stream); free_dev_on(ctx->score, ctx->stream); free_dev_on(ctx->sc, ctx->stream); free_dev_on(ctx->svec, ctx->stream);
+    free_dev_on(ctx->xsend, ctx->stream); free_dev_on(ctx->xrecv, ctx->stream);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->hm) cudaFreeHost(ctx->hm);
     if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); for (int k = 0; k < 8; ++k) cudaEventDestroy(ctx->evp[k]); }
     if (ctx->evt0) { cudaEventDestroy(ctx->evt0); cudaEventDestroy(ctx->evt1); }
     if (ctx->ev_side0) { cudaEventDestroy(ctx->ev_side0); cudaEventDestroy(ctx->ev_side1); }
+    if (ctx->nccl_comm && nccl_api()) nccl_api()->CommDestroy((ncclComm_t)ctx->nccl_comm);
     if (ctx->side) cudaStreamDestroy(ctx->side);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -134,7 +203,12 @@ extern "C" int rg_load_csc(rg_context* ctx, int32_t m, int32_t n, const int64_t*
     if (ctx->carry) { ctx->err = "rg_load_csc: context already holds a problem"; return RG_ERR_STATE; }
     ctx->m = m; ctx->n = n;
     ctx->ld = ((m + 1 + 15) / 16) * 16;
-    ctx->plane = (size_t)(m + 1) * ctx->ld;
+    {   // block row partition: rank r owns constraint rows [r*q, min(m,(r+1)*q)), q = ceil(m / world)
+        int q = (m + ctx->world - 1) / ctx->world;
+        ctx->row_lo = std::min(m, ctx->rank * q);
+        ctx->nloc = std::max(0, std::min(m, (ctx->rank + 1) * q) - ctx->row_lo);
+    }
+    ctx->plane = (size_t)(ctx->nloc + 1) * ctx->ld;
     long long nnz = colptr[n];
     ctx->A.nnz = nnz;
     for (long long j = 0; j < n; ++j)
@@ -155,7 +229,7 @@ extern "C" int rg_load_csc(rg_context* ctx, int32_t m, int32_t n, const int64_t*
     CK(dev_alloc(&ctx->cand, sizeof(int) * 1024, ctx->stream));
     CK(dev_alloc(&ctx->score, sizeof(double) * std::max(m, n), ctx->stream));
     CK(dev_alloc(&ctx->svec, sizeof(u64) * ctx->ld, ctx->stream));
-    ctx->work_chunks = std::max(1, std::min(16, cdiv(m, 256)));
+    ctx->work_chunks = std::max(1, std::min(16, cdiv(std::max(ctx->nloc, 1), 256)));
     CK(dev_alloc(&ctx->carry, sizeof(u64) * ctx->L * ctx->plane, ctx->stream));
     CK(dev_alloc(&ctx->G, sizeof(u64) * LG_of(ctx->L) * n, ctx->stream));
     CK(cudaMemset(ctx->G, 0, sizeof(u64) * LG_of(ctx->L) * n));
@@ -179,6 +253,22 @@ extern "C" int rg_set_rhs(rg_context* ctx, const int64_t* b) {
         kernel<<<grid, block, 0, ctx->stream>>>(__VA_ARGS__);              \
         ctx->launches++;                                                   \
     } while (0)
+
+// exchange buffers of the row-sharded engine (words of 8 bytes)
+static int ensure_xbuf(rg_context* ctx, size_t send_words, size_t recv_words) {
+    size_t need = std::max(send_words, recv_words) * sizeof(u64);
+    if (need <= ctx->xbytes) return RG_OK;
+    CK(cudaStreamSynchronize(ctx->stream));
+    free_dev_on(ctx->xsend, ctx->stream); free_dev_on(ctx->xrecv, ctx->stream);
+    CK(dev_alloc(&ctx->xsend, need, ctx->stream));
+    CK(dev_alloc(&ctx->xrecv, need, ctx->stream));
+    ctx->xbytes = need;
+    return RG_OK;
+}
+static int all_gather(rg_context* ctx, const void* send, void* recv, size_t words_per_rank) {
+    NK(nccl_api()->AllGather(send, recv, words_per_rank, ncclUint64, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+    return RG_OK;
+}
 
 static int sync_mirror(rg_context* ctx) {
     LAUNCH(k_mirror, 1, 1, ctx->sc, ctx->hm_dev, ctx->L);
@@ -226,17 +316,46 @@ static void launch_select(rg_context* ctx) {
 
 template <int L>
 static void launch_ftran_t(rg_context* ctx, int q) {
-    LAUNCH((k_ftran<L>), cdiv((long long)(ctx->m + 1) * 32, 256), 256, ctx->carry, ctx->plane, ctx->ld,
-           ctx->m + 1, ctx->A.colptr, ctx->A.rowidx, ctx->A.vals, ctx->cost, q, ctx->u, (size_t)ctx->ld,
+    LAUNCH((k_ftran<L>), cdiv((long long)(ctx->nloc + 1) * 32, 256), 256, ctx->carry, ctx->plane, ctx->ld,
+           ctx->nloc + 1, ctx->A.colptr, ctx->A.rowidx, ctx->A.vals, ctx->cost, q, ctx->u, (size_t)ctx->ld,
            ctx->sc);
 }
 static void launch_ftran(rg_context* ctx, int q) { DISPATCH_L(ctx->L, launch_ftran_t, ctx, q); }
 
-static void launch_ratio(rg_context* ctx) {
-    CmpRatio c{ctx->carry, ctx->plane, ctx->ld, ctx->L, ctx->u, (size_t)ctx->ld, LU_of(ctx->L), ctx->basis};
-    LAUNCH(k_score_rows, cdiv(ctx->m, 256), 256, ctx->m, ctx->carry, ctx->plane, ctx->ld, ctx->L, ctx->u,
+static int launch_ratio(rg_context* ctx) {
+    CmpRatio c{ctx->carry, ctx->plane, ctx->ld, ctx->L, ctx->u, (size_t)ctx->ld, LU_of(ctx->L), ctx->basis,
+               ctx->row_lo};
+    const int cnt = std::max(ctx->nloc, 1);
+    LAUNCH(k_score_rows, cdiv(cnt, 256), 256, ctx->nloc, ctx->carry, ctx->plane, ctx->ld, ctx->L, ctx->u,
            (size_t)ctx->ld, LU_of(ctx->L), ctx->score, ctx->sc);
-    LAUNCH((k_select_scored<CmpRatio>), 1, 1024, ctx->m, c, ctx->score, 1, ctx->sc);
+    if (ctx->world == 1) {
+        LAUNCH((k_select_scored<CmpRatio>), 1, 1024, ctx->nloc, c, ctx->score, 1, ctx->sc);
+        LAUNCH(k_take_a, 1, 1, ctx->u, (size_t)ctx->ld, ctx->L, ctx->sc);
+        return RG_OK;
+    }
+    // row-sharded: local candidate -> all-gather -> identical deterministic reduction on every rank
+    LAUNCH((k_select_scored<CmpRatio>), 1, 1024, ctx->nloc, c, ctx->score, 3, ctx->sc);
+    RG_TRY(ensure_xbuf(ctx, RG_CAND_WORDS, (size_t)RG_CAND_WORDS * ctx->world));
+    LAUNCH(k_ratio_pack, 1, 1, ctx->carry, ctx->plane, ctx->ld, ctx->L, ctx->u, (size_t)ctx->ld, ctx->basis,
+           ctx->xsend, ctx->sc);
+    RG_TRY(all_gather(ctx, ctx->xsend, ctx->xrecv, RG_CAND_WORDS));
+    LAUNCH(k_ratio_merge, 1, 1, ctx->xrecv, ctx->world, ctx->L, ctx->sc);
+    return RG_OK;
+}
+// pivot row given (artificial removal, trait-shaped bring_into_basis): set p / pg and the pivot element
+static int launch_fixed_row(rg_context* ctx, int row) {
+    int local = (row >= ctx->row_lo && row < ctx->row_lo + ctx->nloc) ? row - ctx->row_lo + 1 : -1;
+    LAUNCH(k_set_rows, 1, 1, ctx->sc, local, row + 1);
+    if (ctx->world == 1) {
+        LAUNCH(k_take_a, 1, 1, ctx->u, (size_t)ctx->ld, ctx->L, ctx->sc);
+        return RG_OK;
+    }
+    RG_TRY(ensure_xbuf(ctx, RG_CAND_WORDS, (size_t)RG_CAND_WORDS * ctx->world));
+    LAUNCH(k_ratio_pack, 1, 1, ctx->carry, ctx->plane, ctx->ld, ctx->L, ctx->u, (size_t)ctx->ld, ctx->basis,
+           ctx->xsend, ctx->sc);
+    RG_TRY(all_gather(ctx, ctx->xsend, ctx->xrecv, RG_CAND_WORDS));
+    LAUNCH(k_ratio_merge, 1, 1, ctx->xrecv, ctx->world, ctx->L, ctx->sc);
+    return RG_OK;
 }
 
 template <int L>
@@ -244,36 +363,65 @@ static void launch_copyrow_t(rg_context* ctx) {
     LAUNCH((k_copyrow<L>), cdiv(ctx->ld, 256), 256, ctx->carry, ctx->plane, ctx->ld, ctx->rowp,
            (size_t)ctx->ld, ctx->sc);
 }
-static void launch_copyrow(rg_context* ctx) { DISPATCH_L(ctx->L, launch_copyrow_t, ctx); }
+template <int L>
+static void launch_rowbits_t(rg_context* ctx) {
+    LAUNCH((k_rowbits<L>), cdiv(ctx->ld, 256), 256, ctx->rowp, (size_t)ctx->ld, ctx->ld, ctx->sc);
+}
+static int launch_copyrow(rg_context* ctx) {
+    DISPATCH_L(ctx->L, launch_copyrow_t, ctx);
+    if (ctx->world > 1)   // exact: exactly one rank contributes non-zero words
+        NK(nccl_api()->AllReduce(ctx->rowp, ctx->rowp, (size_t)ctx->L * ctx->ld, ncclUint64, ncclSum,
+                                 (ncclComm_t)ctx->nccl_comm, ctx->stream));
+    DISPATCH_L(ctx->L, launch_rowbits_t, ctx);
+    return RG_OK;
+}
 
 template <int L>
-static void launch_work_t(rg_context* ctx) {
+static int launch_work_t(rg_context* ctx) {
     constexpr int LU = L + 2, LW = 2 * L + 4;
-    int rpc = cdiv(ctx->m, ctx->work_chunks);
+    int rpc = cdiv(std::max(ctx->nloc, 1), ctx->work_chunks);
     dim3 grid(cdiv(ctx->ld, 128), ctx->work_chunks);
-    LAUNCH((k_colsum1<L, LU, LW>), grid, 128, ctx->carry, ctx->plane, ctx->ld, ctx->m, rpc, ctx->u,
+    LAUNCH((k_colsum1<L, LU, LW>), grid, 128, ctx->carry, ctx->plane, ctx->ld, ctx->nloc, rpc, ctx->u,
            (size_t)ctx->ld, ctx->omega_part, ctx->sc);
+    if (ctx->world == 1) {
+        LAUNCH((k_colsum2<LW>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, ctx->work_chunks, 0,
+               ctx->omega, ctx->sc);
+        return RG_OK;
+    }
+    size_t words = (size_t)LW * ctx->ld;
+    RG_TRY(ensure_xbuf(ctx, words, words * ctx->world));
     LAUNCH((k_colsum2<LW>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, ctx->work_chunks, 0,
-           ctx->omega, ctx->sc);
+           ctx->xsend, ctx->sc);
+    RG_TRY(all_gather(ctx, ctx->xsend, ctx->xrecv, words));
+    LAUNCH((k_colsum2<LW>), cdiv(ctx->ld, 64), 64, ctx->xrecv, ctx->ld, ctx->world, 0, ctx->omega, ctx->sc);
+    return RG_OK;
 }
-static void launch_work(rg_context* ctx) { DISPATCH_L(ctx->L, launch_work_t, ctx); }
+static int launch_work(rg_context* ctx) {
+    switch (ctx->L) {
+        case 1: return launch_work_t<1>(ctx);
+        case 2: return launch_work_t<2>(ctx);
+        case 4: return launch_work_t<4>(ctx);
+        case 8: return launch_work_t<8>(ctx);
+        default: return launch_work_t<16>(ctx);
+    }
+}
 
 template <int L>
 static void launch_update_t(rg_context* ctx, int E) {
     constexpr int CP = L <= 4 ? 2 : 1;
-    dim3 grid(cdiv(ctx->ld, 256 * CP), cdiv(ctx->m + 1, 32));
+    dim3 grid(cdiv(ctx->ld, 256 * CP), cdiv(ctx->nloc + 1, 32));
     if (E == 0) {
-        LAUNCH((k_update<L, 0, CP>), grid, 256, ctx->carry, ctx->plane, ctx->ld, ctx->m + 1, ctx->u,
+        LAUNCH((k_update<L, 0, CP>), grid, 256, ctx->carry, ctx->plane, ctx->ld, ctx->nloc + 1, ctx->u,
                (size_t)ctx->ld, ctx->rowp, (size_t)ctx->ld, ctx->sc);
     } else if (E == 1) {
-        LAUNCH((k_update<L, 1, CP>), grid, 256, ctx->carry, ctx->plane, ctx->ld, ctx->m + 1, ctx->u,
+        LAUNCH((k_update<L, 1, CP>), grid, 256, ctx->carry, ctx->plane, ctx->ld, ctx->nloc + 1, ctx->u,
                (size_t)ctx->ld, ctx->rowp, (size_t)ctx->ld, ctx->sc);
     } else if (E == 2) {
-        LAUNCH((k_update<L, 2, CP>), grid, 256, ctx->carry, ctx->plane, ctx->ld, ctx->m + 1, ctx->u,
+        LAUNCH((k_update<L, 2, CP>), grid, 256, ctx->carry, ctx->plane, ctx->ld, ctx->nloc + 1, ctx->u,
                (size_t)ctx->ld, ctx->rowp, (size_t)ctx->ld, ctx->sc);
     } else {
-        dim3 g2(cdiv(ctx->ld, 128), ctx->m + 1);
-        LAUNCH(k_update_generic, g2, 128, ctx->carry, ctx->plane, ctx->ld, ctx->m + 1, L, ctx->u,
+        dim3 g2(cdiv(ctx->ld, 128), ctx->nloc + 1);
+        LAUNCH(k_update_generic, g2, 128, ctx->carry, ctx->plane, ctx->ld, ctx->nloc + 1, L, ctx->u,
                (size_t)ctx->ld, ctx->rowp, (size_t)ctx->ld, ctx->sc);
     }
 }
@@ -350,14 +498,14 @@ static int do_pivot(rg_context* ctx, int q, int fixed_row, bool want_se, bool re
         if (prof) cudaEventRecord(ctx->evp[0], ctx->stream);
         LAUNCH(k_reset_iter, 1, 1, ctx->sc);
         launch_ftran(ctx, q);
-        if (fixed_row < 0) launch_ratio(ctx);
-        else LAUNCH(k_set_pq, 1, 1, ctx->sc, -2, fixed_row + 1);
-        launch_copyrow(ctx);
+        if (fixed_row < 0) RG_TRY(launch_ratio(ctx));
+        else RG_TRY(launch_fixed_row(ctx, fixed_row));
+        RG_TRY(launch_copyrow(ctx));
         if (prof) cudaEventRecord(ctx->evp[1], ctx->stream);
-        if (want_se) launch_work(ctx);
+        if (want_se) RG_TRY(launch_work(ctx));
         if (prof) cudaEventRecord(ctx->evp[2], ctx->stream);
         int E = (ctx->t_cur + 63) / 64;
-        LAUNCH(k_scalars, 1, 1, ctx->u, (size_t)ctx->ld, ctx->L, E, ctx->sc);
+        LAUNCH(k_scalars, 1, 1, ctx->L, E, ctx->sc);
         if (want_se) {   // steepest-edge scalars on the side stream, overlapped with K1
             cudaEventRecord(ctx->ev_side0, ctx->stream);
             cudaStreamWaitEvent(ctx->side, ctx->ev_side0, 0);
@@ -424,9 +572,11 @@ extern "C" int rg_init_identity_basis(rg_context* ctx, const int32_t* basis, con
     else CK(cudaMemset(ctx->cost, 0, sizeof(long long) * n));
     CK(cudaMemsetAsync(ctx->inbasis, 0, n, ctx->stream));
     LAUNCH(k_zero, 148 * 8, 256, ctx->carry, (size_t)ctx->L * ctx->plane);
-    LAUNCH(k_init_identity, cdiv(m, 256), 256, ctx->carry, ctx->plane, ctx->ld, m, ctx->L, ctx->rhs,
-           ctx->basis, ctx->sc);
-    LAUNCH(k_init_scalars, 1, 1, ctx->carry, ctx->plane, m, ctx->L, ctx->rhs, ctx->basis, ctx->sc);
+    LAUNCH(k_init_identity, cdiv(std::max(ctx->nloc, 1), 256), 256, ctx->carry, ctx->plane, ctx->ld, ctx->nloc,
+           ctx->row_lo, ctx->L, ctx->rhs);
+    LAUNCH(k_init_row0, cdiv(m, 256), 256, ctx->carry, ctx->plane, m, ctx->L, ctx->basis);
+    LAUNCH(k_init_scalars, 1, 1, ctx->carry, ctx->plane, m, ctx->L, ctx->rhs, ctx->basis, ctx->row_lo, ctx->nloc,
+           ctx->rank, ctx->world, ctx->sc);
     LAUNCH(k_set_inbasis, cdiv(m, 256), 256, ctx->inbasis, ctx->basis, m);
     ctx->identity_carry = true;
     ctx->rule_ready = false; ctx->have_column = false; ctx->selected = false;
@@ -442,14 +592,34 @@ extern "C" int rg_init_identity_basis(rg_context* ctx, const int32_t* basis, con
 }
 
 template <int L>
-static void launch_phase_sums_t(rg_context* ctx) {
+static int launch_phase_sums_t(rg_context* ctx) {
     constexpr int LU = L + 2;
-    int rpc = cdiv(ctx->m, ctx->work_chunks);
+    int rpc = cdiv(std::max(ctx->nloc, 1), ctx->work_chunks);
     dim3 grid(cdiv(ctx->ld, 128), ctx->work_chunks);
-    LAUNCH((k_colsum1<L, 1, LU>), grid, 128, ctx->carry, ctx->plane, ctx->ld, ctx->m, rpc, ctx->svec,
+    LAUNCH((k_colsum1<L, 1, LU>), grid, 128, ctx->carry, ctx->plane, ctx->ld, ctx->nloc, rpc, ctx->svec,
            (size_t)ctx->ld, ctx->omega_part, ctx->sc);
-    LAUNCH((k_colsum2<LU>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, ctx->work_chunks, 1,
-           ctx->tmprow, ctx->sc);
+    if (ctx->world == 1) {
+        LAUNCH((k_colsum2<LU>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, ctx->work_chunks, 1,
+               ctx->tmprow, ctx->sc);
+        return RG_OK;
+    }
+    size_t words = (size_t)LU * ctx->ld;
+    RG_TRY(ensure_xbuf(ctx, words, words * ctx->world));
+    LAUNCH((k_colsum2<LU>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, ctx->work_chunks, 0,
+           ctx->xsend, ctx->sc);
+    RG_TRY(all_gather(ctx, ctx->xsend, ctx->xrecv, words));
+    LAUNCH(k_reset_tmpbits, 1, 1, ctx->sc);
+    LAUNCH((k_colsum2<LU>), cdiv(ctx->ld, 64), 64, ctx->xrecv, ctx->ld, ctx->world, 1, ctx->tmprow, ctx->sc);
+    return RG_OK;
+}
+static int launch_phase_sums(rg_context* ctx) {
+    switch (ctx->L) {
+        case 1: return launch_phase_sums_t<1>(ctx);
+        case 2: return launch_phase_sums_t<2>(ctx);
+        case 4: return launch_phase_sums_t<4>(ctx);
+        case 8: return launch_phase_sums_t<8>(ctx);
+        default: return launch_phase_sums_t<16>(ctx);
+    }
 }
 
 extern "C" int rg_phase_switch(rg_context* ctx, const int64_t* cost) {
@@ -458,9 +628,10 @@ extern "C" int rg_phase_switch(rg_context* ctx, const int64_t* cost) {
     CK(cudaMemcpy(ctx->cost, cost, sizeof(long long) * ctx->n, cudaMemcpyHostToDevice));
     set_status(ctx, ST_RUN);
     for (;;) {
-        LAUNCH(k_basic_costs, cdiv(ctx->m + 1, 256), 256, ctx->basis, ctx->cost, ctx->m, ctx->svec);
+        LAUNCH(k_basic_costs, cdiv(ctx->nloc + 1, 256), 256, ctx->basis, ctx->cost, ctx->nloc, ctx->row_lo,
+               ctx->svec);
         LAUNCH(k_reset_tmpbits, 1, 1, ctx->sc);
-        DISPATCH_L(ctx->L, launch_phase_sums_t, ctx);
+        RG_TRY(launch_phase_sums(ctx));
         RG_TRY(sync_mirror(ctx));
         if (ctx->hm->maxbits_tmp > 64 * ctx->L - 1) { RG_TRY(promote(ctx)); continue; }
         break;
@@ -477,9 +648,29 @@ extern "C" int rg_phase_switch(rg_context* ctx, const int64_t* cost) {
 // pivot rule
 // ------------------------------------------------------------------------------------------------
 template <int L>
-static void launch_gamma_general_t(rg_context* ctx) {
-    LAUNCH((k_gamma_init_general<L>), ctx->n, 128, ctx->carry, ctx->plane, ctx->ld, ctx->m, ctx->n,
-           ctx->A.colptr, ctx->A.rowidx, ctx->A.vals, ctx->inbasis, ctx->G, ctx->sc);
+static int launch_gamma_general_t(rg_context* ctx) {
+    constexpr int LG = 2 * L + 5;
+    if (ctx->world == 1) {
+        LAUNCH((k_gamma_init_general<L>), ctx->n, 128, ctx->carry, ctx->plane, ctx->ld, ctx->nloc, ctx->n,
+               ctx->A.colptr, ctx->A.rowidx, ctx->A.vals, ctx->inbasis, ctx->G, 1, ctx->sc);
+        return RG_OK;
+    }
+    size_t words = (size_t)LG * ctx->n;
+    RG_TRY(ensure_xbuf(ctx, words, words * ctx->world));
+    LAUNCH((k_gamma_init_general<L>), ctx->n, 128, ctx->carry, ctx->plane, ctx->ld, ctx->nloc, ctx->n,
+           ctx->A.colptr, ctx->A.rowidx, ctx->A.vals, ctx->inbasis, ctx->xsend, ctx->rank == 0 ? 1 : 0, ctx->sc);
+    RG_TRY(all_gather(ctx, ctx->xsend, ctx->xrecv, words));
+    LAUNCH((k_colsum2<LG>), cdiv(ctx->n, 64), 64, ctx->xrecv, ctx->n, ctx->world, 0, ctx->G, ctx->sc);
+    return RG_OK;
+}
+static int launch_gamma_general(rg_context* ctx) {
+    switch (ctx->L) {
+        case 1: return launch_gamma_general_t<1>(ctx);
+        case 2: return launch_gamma_general_t<2>(ctx);
+        case 4: return launch_gamma_general_t<4>(ctx);
+        case 8: return launch_gamma_general_t<8>(ctx);
+        default: return launch_gamma_general_t<16>(ctx);
+    }
 }
 
 extern "C" int rg_rule_new(rg_context* ctx, int32_t rule) {
@@ -493,7 +684,7 @@ extern "C" int rg_rule_new(rg_context* ctx, int32_t rule) {
             LAUNCH(k_gamma_init_identity, cdiv(ctx->n, 256), 256, ctx->n, ctx->A.colptr, ctx->A.vals,
                    ctx->inbasis, ctx->G, LG_of(ctx->L));
         } else {
-            DISPATCH_L(ctx->L, launch_gamma_general_t, ctx);
+            RG_TRY(launch_gamma_general(ctx));
         }
     }
     cudaMemsetAsync(&ctx->sc->last_selected, 0xff, sizeof(int), ctx->stream);
@@ -538,7 +729,7 @@ extern "C" int rg_select_primal_pivot_row(rg_context* ctx, int32_t* status, int3
     if (!ctx->have_column) { ctx->err = "no pivot column generated"; return RG_ERR_STATE; }
     CK(cudaSetDevice(ctx->device));
     set_status(ctx, ST_RUN);
-    launch_ratio(ctx);
+    RG_TRY(launch_ratio(ctx));
     RG_TRY(sync_mirror(ctx));
     *status = ctx->hm->status == ST_UNBOUNDED ? RG_STEP_UNBOUNDED : RG_STEP_PIVOTED;
     *row = ctx->hm->p - 1;
@@ -601,10 +792,13 @@ extern "C" int rg_remove_artificial_row(rg_context* ctx, int32_t row, rg_pivot_i
     CK(cudaSetDevice(ctx->device));
     set_status(ctx, ST_RUN);
     LAUNCH(k_reset_iter, 1, 1, ctx->sc);
-    LAUNCH(k_set_pq, 1, 1, ctx->sc, -2, row + 1);
-    LAUNCH(k_bp_nonzero, 1, 1, ctx->carry, ctx->plane, ctx->ld, ctx->L, ctx->sc);
+    {
+        int local = (row >= ctx->row_lo && row < ctx->row_lo + ctx->nloc) ? row - ctx->row_lo + 1 : -1;
+        LAUNCH(k_set_rows, 1, 1, ctx->sc, local, row + 1);
+    }
     launch_price(ctx);
-    launch_copyrow(ctx);
+    RG_TRY(launch_copyrow(ctx));
+    LAUNCH(k_bp_nonzero, 1, 1, ctx->rowp, (size_t)ctx->ld, ctx->L, ctx->sc);
     DISPATCH_L(ctx->L, launch_rowdot_t, ctx);
     PriceView v{ctx->kappa, LU_of(ctx->L), ctx->n, ctx->inbasis};
     launch_argbest(ctx, ctx->n, CmpArtificial{v, ctx->nu, ctx->sc}, 2);
@@ -662,10 +856,32 @@ extern "C" int rg_get_basis(rg_context* ctx, int32_t* basis) {
     CK(cudaMemcpy(basis, ctx->basis, sizeof(int) * ctx->m, cudaMemcpyDeviceToHost));
     return RG_OK;
 }
+// export one number per constraint row (rows are block-distributed when world > 1): local gather into
+// a padded block, all-gather, compact on the host
+static int export_rows(rg_context* ctx, const u64* base, size_t stride, size_t idx0, size_t step, int nl,
+                       uint64_t* out) {
+    if (ctx->world == 1) return export_planar(ctx, base, stride, idx0, step, ctx->m, nl, out);
+    const int q = (ctx->m + ctx->world - 1) / ctx->world;
+    size_t words = (size_t)q * nl;
+    RG_TRY(ensure_xbuf(ctx, words, words * ctx->world));
+    CK(cudaMemsetAsync(ctx->xsend, 0, words * sizeof(u64), ctx->stream));
+    if (ctx->nloc > 0)
+        LAUNCH(k_gather, cdiv(ctx->nloc, 256), 256, ctx->xsend, base, stride, idx0, step, ctx->nloc, nl);
+    RG_TRY(all_gather(ctx, ctx->xsend, ctx->xrecv, words));
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::vector<u64> host(words * ctx->world);
+    CK(cudaMemcpy(host.data(), ctx->xrecv, host.size() * sizeof(u64), cudaMemcpyDeviceToHost));
+    for (int r = 0; r < ctx->world; ++r) {
+        int lo = std::min(ctx->m, r * q), hi = std::min(ctx->m, (r + 1) * q);
+        if (hi > lo) memcpy(out + (size_t)lo * nl, host.data() + (size_t)r * words, (size_t)(hi - lo) * nl * sizeof(u64));
+    }
+    return RG_OK;
+}
+
 extern "C" int rg_get_b(rg_context* ctx, uint64_t* out) {
     if (!ctx || !ctx->carry || !out) return RG_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
-    return export_planar(ctx, ctx->carry, ctx->plane, (size_t)ctx->ld, (size_t)ctx->ld, ctx->m, ctx->L, out);
+    return export_rows(ctx, ctx->carry, ctx->plane, (size_t)ctx->ld, (size_t)ctx->ld, ctx->L, out);
 }
 extern "C" int rg_get_minus_objective(rg_context* ctx, uint64_t* out) {
     if (!ctx || !ctx->carry || !out) return RG_ERR_ARG;
@@ -680,13 +896,19 @@ extern "C" int rg_get_minus_pi(rg_context* ctx, uint64_t* out) {
 extern "C" int rg_get_basis_inverse_row(rg_context* ctx, int32_t row, uint64_t* out) {
     if (!ctx || !ctx->carry || !out || row < 0 || row >= ctx->m) return RG_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
-    return export_planar(ctx, ctx->carry, ctx->plane, (size_t)(row + 1) * ctx->ld + 1, 1, ctx->m, ctx->L, out);
+    // stage the row like a pivot row (owner copies, sum all-reduce replicates it), then export it
+    set_status(ctx, ST_RUN);
+    int local = (row >= ctx->row_lo && row < ctx->row_lo + ctx->nloc) ? row - ctx->row_lo + 1 : -1;
+    LAUNCH(k_set_rows, 1, 1, ctx->sc, local, row + 1);
+    RG_TRY(launch_copyrow(ctx));
+    ctx->have_column = false;
+    return export_planar(ctx, ctx->rowp, (size_t)ctx->ld, 1, 1, ctx->m, ctx->L, out);
 }
 extern "C" int rg_get_pivot_column(rg_context* ctx, uint64_t* out) {
     if (!ctx || !ctx->carry || !out) return RG_ERR_ARG;
     if (!ctx->have_column) { ctx->err = "no pivot column generated"; return RG_ERR_STATE; }
     CK(cudaSetDevice(ctx->device));
-    return export_planar(ctx, ctx->u, (size_t)ctx->ld, 1, 1, ctx->m, LU_of(ctx->L), out);
+    return export_rows(ctx, ctx->u, (size_t)ctx->ld, 1, 1, LU_of(ctx->L), out);
 }
 extern "C" int rg_get_relative_costs(rg_context* ctx, uint64_t* out) {
     if (!ctx || !ctx->carry || !out) return RG_ERR_ARG;

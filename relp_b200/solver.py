@@ -109,13 +109,30 @@ class GpuResult:
         self.device_ms = 0.0
 
 
+def nccl_unique_id():
+    """A fresh 128-byte NCCL id (call on rank 0, broadcast to the other ranks)."""
+    lib = _lib.load()
+    buf = C.create_string_buffer(128)
+    rc = lib.rg_nccl_unique_id(buf, 128)
+    if rc < 0:
+        raise RuntimeError("rg_nccl_unique_id failed (libnccl.so.2 not loadable?)")
+    return buf.raw
+
+
 def solve_relaxation(problem, rule="steepest_edge", fused=True, initial_limbs=0, device=0,
-                     max_pivots=0, profile=False):
+                     max_pivots=0, profile=False, rank=0, world=1, nccl_id=None):
+    """Solves `problem`.  world > 1: row-sharded over `world` GPUs (one process per GPU; every rank
+    passes the same problem and the same `nccl_id` and receives the same result)."""
     lib = _lib.load()
     cprob, keep = problem._as_c()
+    idbuf = None
+    if world > 1:
+        assert nccl_id is not None and len(nccl_id) == 128
+        idbuf = C.create_string_buffer(bytes(nccl_id), 128)
     opts = _lib.rh_options(device=device, initial_limbs=initial_limbs, rule=RULES[rule],
                            fused=1 if fused else 0, max_pivots=max_pivots,
-                           profile=1 if profile else 0)
+                           profile=1 if profile else 0, rank=rank, world=world, reserved=0,
+                           nccl_unique_id=C.cast(idbuf, C.c_void_p) if idbuf is not None else None)
     handle = C.c_void_p()
     rc = lib.rh_solve_relaxation(C.byref(cprob), C.byref(opts), C.byref(handle))
     try:

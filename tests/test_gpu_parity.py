@@ -157,3 +157,19 @@ def test_max_flow_random_graph():
     from relp_b200.generators import max_flow
     prob = max_flow(n_vertices=24, out_degree=3, seed=3, max_capacity=9)
     check(problem=prob, rules=["steepest_edge", "dantzig"], modes=(True,))
+
+
+def test_row_sharded_two_gpus():
+    """Row-sharded engine (NCCL) against the oracle on 2 GPUs of the box (skipped with fewer)."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29613",
+                        os.path.join(root, "scripts", "mgpu_check.py")], capture_output=True, text=True,
+                       timeout=900, cwd=root)
+    assert r.returncode == 0 and "MGPU PARITY OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
