@@ -163,9 +163,11 @@ def workload_config(args, world):
     w = WORKLOADS[args.workload]
     return {"workload": f"{args.workload}: synthetic bounded integer LP m={w['m']} n={w['n_struct']}+{w['m']} "
                         f"slacks, K={w['k_bounding']} bounding rows, coefficients in [-100,100], "
-                        f"{'dense' if w['dense'] else '8 nnz/col sparse'} never-binding rows, seed=rank",
+                        f"{'dense' if w['dense'] else '8 nnz/col sparse'} never-binding rows, seed=0",
             "pivot_rule": args.rule, "step": "one exact solve to optimality (time-to-optimal)",
-            "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (row sharding: see DESIGN.md)",
+            "parallelism": "single GPU" if world == 1 else
+            f"carry row-sharded over {world} GPUs (one process per GPU, NCCL: all-gather of ratio-test candidates "
+            f"and work-vector partials, all-reduce of the pivot row); pricing and rule update replicated",
             "l2": "carry (>= 268 MB at 2 limbs) exceeds the 126 MB L2; no flush needed"}
 
 
@@ -197,7 +199,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    prob = make_problem(args.workload, rank)
+    prob = make_problem(args.workload, 0)     # N > 1: the SAME LP, its carry row-sharded over the ranks
     # pinned host buffers for the end-to-end leg
     for name in ("colptr", "rowidx", "vals", "cost", "rhs"):
         t = torch.from_numpy(getattr(prob, name)).pin_memory()
@@ -210,8 +212,19 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def share_id():
+        if world == 1:
+            return None
+        t = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            t = torch.tensor(list(relp_b200.solver.nccl_unique_id()), dtype=torch.uint8, device="cuda")
+        dist.broadcast(t, 0)
+        return bytes(t.cpu().tolist())
+
     def step():
-        return relp_b200.solve_relaxation(prob, rule=args.rule, device=local, profile=True)
+        nid = share_id()
+        return relp_b200.solve_relaxation(prob, rule=args.rule, device=local, profile=True, rank=rank,
+                                          world=world, nccl_id=nid)
 
     for _ in range(args.warmup):
         g = step()
@@ -250,14 +263,14 @@ def main():
         sm = stats.clone()
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         dev_ms_max, e2e_max = mx[0].item(), mx[1].item()
-        pivots_all, launches_all = sm[2].item(), sm[3].item()
+        pivots_all, launches_all = float(pivots), sm[3].item()   # one job: every rank walks the same pivots
     else:
         dev_ms_max, e2e_max, pivots_all, launches_all = dev_ms, e2e_s, float(pivots), float(launches)
 
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
         w = WORKLOADS[args.workload]
-        entries = (w["m"] + 1) ** 2
+        entries = (w["m"] + 1) * (-(-w["m"] // world) + 1)     # carry entries one K1 launch of one rank touches
         by_limbs = {}
         dom, dom_ms = None, -1.0
         for k in range(5):
@@ -276,7 +289,8 @@ def main():
         line = {
             "metric": "exact simplex pivots/sec", "value": pivots_all / (dev_ms_max * 1e-3), "unit": "pivots/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak" if world == 1 else "strong",
             "vs_baseline": None, "dtype": "int (two's complement multi-limb u64, 2-16 limbs)",
             "data": "synthetic", "config": workload_config(args, world),
             "time_to_optimal_ms": dev_ms_max / args.steps, "pivots_per_solve": pivots / args.steps,

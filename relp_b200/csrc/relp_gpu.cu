@@ -1,6 +1,8 @@
 // C-ABI implementation of the B200-native exact simplex engine (include/relp_gpu.h).
 // Host orchestration only: every arithmetic step runs in the kernels of kernels.cuh.
 #include <cstdio>
+#include <cstdlib>
+#include <ctime>
 #include <cstring>
 #include <algorithm>
 #include <vector>
@@ -139,12 +141,12 @@ extern "C" int rg_create(const rg_options* opts, rg_context** out) {
     *out = ctx;
     CK(cudaSetDevice(ctx->device));
     pool_setup(ctx->device);
-    CK(cudaStreamCreate(&ctx->stream));   // blocking: orders with the synchronous copies on the null stream
+    CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));   // every copy is issued on this stream
     CK(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&ctx->ev_side0, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_side1, cudaEventDisableTiming));
     CK(dev_alloc(&ctx->sc, sizeof(Scalars), ctx->stream));
-    CK(cudaMemset(ctx->sc, 0, sizeof(Scalars)));
+    CK(cudaMemsetAsync(ctx->sc, 0, sizeof(Scalars), ctx->stream));
     CK(cudaHostAlloc(&ctx->hm, sizeof(HostMirror), cudaHostAllocMapped));
     memset(ctx->hm, 0, sizeof(HostMirror));
     CK(cudaHostGetDevicePointer((void**)&ctx->hm_dev, ctx->hm, 0));
@@ -155,11 +157,27 @@ extern "C" int rg_create(const rg_options* opts, rg_context** out) {
         }
         NcclApi* api = nccl_api();
         if (!api) { ctx->err = "rg_create: libnccl.so.2 not found"; return RG_ERR_NCCL; }
-        ncclUniqueId id;
-        memcpy(&id, opts->nccl_unique_id, sizeof(id));
-        ncclComm_t comm;
-        NK(api->CommInitRank(&comm, ctx->world, id, ctx->rank));
-        ctx->nccl_comm = comm;
+        // One communicator per (process, world, rank), created by the first context and reused by
+        // later ones: NCCL connects its channels lazily (~0.5 s on the first collective).  Every
+        // rank takes the same branch because every rank issues the same call sequence.
+        static ncclComm_t cached = nullptr;
+        static int cached_world = 0, cached_rank = -1, cached_dev = -1;
+        if (!cached || cached_world != ctx->world || cached_rank != ctx->rank || cached_dev != ctx->device) {
+            ncclUniqueId id;
+            memcpy(&id, opts->nccl_unique_id, sizeof(id));
+            ncclComm_t comm;
+            NK(api->CommInitRank(&comm, ctx->world, id, ctx->rank));
+            cached = comm; cached_world = ctx->world; cached_rank = ctx->rank; cached_dev = ctx->device;
+            // warm the all-gather and all-reduce paths (connection setup) outside any solve
+            u64* w = nullptr;
+            CK(dev_alloc(&w, sizeof(u64) * 64 * (ctx->world + 1), ctx->stream));
+            CK(cudaMemsetAsync(w, 0, sizeof(u64) * 64 * (ctx->world + 1), ctx->stream));
+            NK(api->AllGather(w, w + 64, 64, ncclUint64, comm, ctx->stream));
+            NK(api->AllReduce(w, w, 64, ncclUint64, ncclSum, comm, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            free_dev_on(w, ctx->stream);
+        }
+        ctx->nccl_comm = cached;
     }
     return RG_OK;
 }
@@ -187,7 +205,7 @@ extern "C" int rg_destroy(rg_context* ctx) {
     if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); for (int k = 0; k < 8; ++k) cudaEventDestroy(ctx->evp[k]); }
     if (ctx->evt0) { cudaEventDestroy(ctx->evt0); cudaEventDestroy(ctx->evt1); }
     if (ctx->ev_side0) { cudaEventDestroy(ctx->ev_side0); cudaEventDestroy(ctx->ev_side1); }
-    if (ctx->nccl_comm && nccl_api()) nccl_api()->CommDestroy((ncclComm_t)ctx->nccl_comm);
+    // the communicator is process-cached (see rg_create) and intentionally not destroyed here
     if (ctx->side) cudaStreamDestroy(ctx->side);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -217,13 +235,13 @@ extern "C" int rg_load_csc(rg_context* ctx, int32_t m, int32_t n, const int64_t*
     CK(dev_alloc(&ctx->A.colptr, sizeof(long long) * (n + 1), ctx->stream));
     CK(dev_alloc(&ctx->A.rowidx, sizeof(int) * std::max<long long>(nnz, 1), ctx->stream));
     CK(dev_alloc(&ctx->A.vals, sizeof(long long) * std::max<long long>(nnz, 1), ctx->stream));
-    CK(cudaMemcpy(ctx->A.colptr, colptr, sizeof(long long) * (n + 1), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(ctx->A.rowidx, rowidx, sizeof(int) * nnz, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(ctx->A.vals, vals, sizeof(long long) * nnz, cudaMemcpyHostToDevice));
+    CK(cudaMemcpyAsync(ctx->A.colptr, colptr, sizeof(long long) * (n + 1), cudaMemcpyHostToDevice, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpyAsync(ctx->A.rowidx, rowidx, sizeof(int) * nnz, cudaMemcpyHostToDevice, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpyAsync(ctx->A.vals, vals, sizeof(long long) * nnz, cudaMemcpyHostToDevice, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream));
     CK(dev_alloc(&ctx->cost, sizeof(long long) * n, ctx->stream));
-    CK(cudaMemset(ctx->cost, 0, sizeof(long long) * n));
+    CK(cudaMemsetAsync(ctx->cost, 0, sizeof(long long) * n, ctx->stream));
     CK(dev_alloc(&ctx->rhs, sizeof(long long) * m, ctx->stream));
-    CK(cudaMemset(ctx->rhs, 0, sizeof(long long) * m));
+    CK(cudaMemsetAsync(ctx->rhs, 0, sizeof(long long) * m, ctx->stream));
     CK(dev_alloc(&ctx->basis, sizeof(int) * m, ctx->stream));
     CK(dev_alloc(&ctx->inbasis, n, ctx->stream));
     CK(dev_alloc(&ctx->cand, sizeof(int) * 1024, ctx->stream));
@@ -232,7 +250,7 @@ extern "C" int rg_load_csc(rg_context* ctx, int32_t m, int32_t n, const int64_t*
     ctx->work_chunks = std::max(1, std::min(16, cdiv(std::max(ctx->nloc, 1), 256)));
     CK(dev_alloc(&ctx->carry, sizeof(u64) * ctx->L * ctx->plane, ctx->stream));
     CK(dev_alloc(&ctx->G, sizeof(u64) * LG_of(ctx->L) * n, ctx->stream));
-    CK(cudaMemset(ctx->G, 0, sizeof(u64) * LG_of(ctx->L) * n));
+    CK(cudaMemsetAsync(ctx->G, 0, sizeof(u64) * LG_of(ctx->L) * n, ctx->stream));
     RG_TRY(alloc_width_buffers(ctx, ctx->L));
     CK(cudaStreamSynchronize(ctx->stream));
     return RG_OK;
@@ -241,7 +259,7 @@ extern "C" int rg_load_csc(rg_context* ctx, int32_t m, int32_t n, const int64_t*
 extern "C" int rg_set_rhs(rg_context* ctx, const int64_t* b) {
     if (!ctx || !ctx->rhs || !b) return RG_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
-    CK(cudaMemcpy(ctx->rhs, b, sizeof(long long) * ctx->m, cudaMemcpyHostToDevice));
+    CK(cudaMemcpyAsync(ctx->rhs, b, sizeof(long long) * ctx->m, cudaMemcpyHostToDevice, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream));
     return RG_OK;
 }
 
@@ -265,8 +283,21 @@ static int ensure_xbuf(rg_context* ctx, size_t send_words, size_t recv_words) {
     ctx->xbytes = need;
     return RG_OK;
 }
+static double g_nccl_host_s = 0;
+static long long g_nccl_calls = 0;
 static int all_gather(rg_context* ctx, const void* send, void* recv, size_t words_per_rank) {
+    static const bool hostprof = getenv("RG_HOSTPROF") != nullptr;
+    timespec a, b;
+    if (hostprof) clock_gettime(CLOCK_MONOTONIC, &a);
     NK(nccl_api()->AllGather(send, recv, words_per_rank, ncclUint64, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+    if (hostprof) {
+        clock_gettime(CLOCK_MONOTONIC, &b);
+        double dt = (b.tv_sec - a.tv_sec) + 1e-9 * (b.tv_nsec - a.tv_nsec);
+        g_nccl_host_s += dt;
+        if (dt > 0.001) fprintf(stderr, "[hostprof rank %d] all_gather call %lld words %zu took %.3f ms\n", ctx->rank, g_nccl_calls, words_per_rank, dt * 1e3);
+        if (++g_nccl_calls % 400 == 0)
+            fprintf(stderr, "[hostprof rank %d] %lld all_gather calls, %.3f s on the host\n", ctx->rank, g_nccl_calls, g_nccl_host_s);
+    }
     return RG_OK;
 }
 
@@ -491,18 +522,28 @@ static int promote(rg_context* ctx) {
 // ------------------------------------------------------------------------------------------------
 // one basis change on the device.  q < 0: use the selected column sc->q.  fixed_row < 0: ratio test.
 // ------------------------------------------------------------------------------------------------
+static double g_hostprof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+static inline double now_s() {
+    timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
 static int do_pivot(rg_context* ctx, int q, int fixed_row, bool want_se, bool reselect) {
+    static const bool hostprof = getenv("RG_HOSTPROF") != nullptr;
     for (;;) {
+        double h0 = hostprof ? now_s() : 0;
         ctx->hm->pivoted = 0;
         const bool prof = ctx->profile;
         if (prof) cudaEventRecord(ctx->evp[0], ctx->stream);
         LAUNCH(k_reset_iter, 1, 1, ctx->sc);
         launch_ftran(ctx, q);
+        double h1 = hostprof ? now_s() : 0;
         if (fixed_row < 0) RG_TRY(launch_ratio(ctx));
         else RG_TRY(launch_fixed_row(ctx, fixed_row));
+        double h2 = hostprof ? now_s() : 0;
         RG_TRY(launch_copyrow(ctx));
+        double h3 = hostprof ? now_s() : 0;
         if (prof) cudaEventRecord(ctx->evp[1], ctx->stream);
         if (want_se) RG_TRY(launch_work(ctx));
+        double h4 = hostprof ? now_s() : 0;
         if (prof) cudaEventRecord(ctx->evp[2], ctx->stream);
         int E = (ctx->t_cur + 63) / 64;
         LAUNCH(k_scalars, 1, 1, ctx->L, E, ctx->sc);
@@ -523,7 +564,16 @@ static int do_pivot(rg_context* ctx, int q, int fixed_row, bool want_se, bool re
         if (prof) cudaEventRecord(ctx->evp[3], ctx->stream);
         if (reselect) { launch_price(ctx); launch_select(ctx); }
         if (prof) cudaEventRecord(ctx->evp[4], ctx->stream);
+        double h5 = hostprof ? now_s() : 0;
         RG_TRY(sync_mirror(ctx));
+        if (hostprof) {
+            double h6 = now_s();
+            g_hostprof[0] += h1 - h0; g_hostprof[1] += h2 - h1; g_hostprof[2] += h3 - h2; g_hostprof[3] += h4 - h3;
+            g_hostprof[4] += h5 - h4; g_hostprof[5] += h6 - h5; g_hostprof[6] += 1;
+            if (((long long)g_hostprof[6]) % 200 == 0)
+                fprintf(stderr, "[hostprof rank %d] n=%.0f ftran %.3f ratio %.3f copyrow %.3f work %.3f rest %.3f sync %.3f (s)\n",
+                        ctx->rank, g_hostprof[6], g_hostprof[0], g_hostprof[1], g_hostprof[2], g_hostprof[3], g_hostprof[4], g_hostprof[5]);
+        }
         if (ctx->hm->status == ST_PROMOTE) {
             RG_TRY(promote(ctx));
             if (q < 0) {
@@ -567,9 +617,13 @@ extern "C" int rg_init_identity_basis(rg_context* ctx, const int32_t* basis, con
     const int m = ctx->m, n = ctx->n;
     for (int i = 0; i < m; ++i)
         if (basis[i] >= n) { ctx->err = "rg_init_identity_basis: column id out of range"; return RG_ERR_ARG; }
-    CK(cudaMemcpy(ctx->basis, basis, sizeof(int) * m, cudaMemcpyHostToDevice));
-    if (cost) CK(cudaMemcpy(ctx->cost, cost, sizeof(long long) * n, cudaMemcpyHostToDevice));
-    else CK(cudaMemset(ctx->cost, 0, sizeof(long long) * n));
+    CK(cudaMemcpyAsync(ctx->basis, basis, sizeof(int) * m, cudaMemcpyHostToDevice, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream));
+    if (cost) {
+        CK(cudaMemcpyAsync(ctx->cost, cost, sizeof(long long) * n, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    } else {
+        CK(cudaMemsetAsync(ctx->cost, 0, sizeof(long long) * n, ctx->stream));
+    }
     CK(cudaMemsetAsync(ctx->inbasis, 0, n, ctx->stream));
     LAUNCH(k_zero, 148 * 8, 256, ctx->carry, (size_t)ctx->L * ctx->plane);
     LAUNCH(k_init_identity, cdiv(std::max(ctx->nloc, 1), 256), 256, ctx->carry, ctx->plane, ctx->ld, ctx->nloc,
@@ -625,7 +679,7 @@ static int launch_phase_sums(rg_context* ctx) {
 extern "C" int rg_phase_switch(rg_context* ctx, const int64_t* cost) {
     if (!ctx || !ctx->carry || !cost) return RG_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
-    CK(cudaMemcpy(ctx->cost, cost, sizeof(long long) * ctx->n, cudaMemcpyHostToDevice));
+    CK(cudaMemcpyAsync(ctx->cost, cost, sizeof(long long) * ctx->n, cudaMemcpyHostToDevice, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream));
     set_status(ctx, ST_RUN);
     for (;;) {
         LAUNCH(k_basic_costs, cdiv(ctx->nloc + 1, 256), 256, ctx->basis, ctx->cost, ctx->nloc, ctx->row_lo,
@@ -832,7 +886,7 @@ static int export_planar(rg_context* ctx, const u64* base, size_t stride, size_t
     CK(dev_alloc(&tmp, sizeof(u64) * (size_t)count * nl, ctx->stream));
     LAUNCH(k_gather, cdiv(count, 256), 256, tmp, base, stride, idx0, step, count, nl);
     CK(cudaStreamSynchronize(ctx->stream));
-    CK(cudaMemcpy(out, tmp, sizeof(u64) * (size_t)count * nl, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpyAsync(out, tmp, sizeof(u64) * (size_t)count * nl, cudaMemcpyDeviceToHost, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream));
     cudaFreeAsync(tmp, ctx->stream);
     return RG_OK;
 }
@@ -846,14 +900,14 @@ extern "C" int rg_get_denominator(rg_context* ctx, uint64_t* out) {
     if (!ctx || !ctx->carry || !out) return RG_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
-    CK(cudaMemcpy(out, ctx->sc->D, sizeof(u64) * ctx->L, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpyAsync(out, ctx->sc->D, sizeof(u64) * ctx->L, cudaMemcpyDeviceToHost, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream));
     return RG_OK;
 }
 extern "C" int rg_get_basis(rg_context* ctx, int32_t* basis) {
     if (!ctx || !ctx->carry || !basis) return RG_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
-    CK(cudaMemcpy(basis, ctx->basis, sizeof(int) * ctx->m, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpyAsync(basis, ctx->basis, sizeof(int) * ctx->m, cudaMemcpyDeviceToHost, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream));
     return RG_OK;
 }
 // export one number per constraint row (rows are block-distributed when world > 1): local gather into
@@ -870,7 +924,7 @@ static int export_rows(rg_context* ctx, const u64* base, size_t stride, size_t i
     RG_TRY(all_gather(ctx, ctx->xsend, ctx->xrecv, words));
     CK(cudaStreamSynchronize(ctx->stream));
     std::vector<u64> host(words * ctx->world);
-    CK(cudaMemcpy(host.data(), ctx->xrecv, host.size() * sizeof(u64), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpyAsync(host.data(), ctx->xrecv, host.size() * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream));
     for (int r = 0; r < ctx->world; ++r) {
         int lo = std::min(ctx->m, r * q), hi = std::min(ctx->m, (r + 1) * q);
         if (hi > lo) memcpy(out + (size_t)lo * nl, host.data() + (size_t)r * words, (size_t)(hi - lo) * nl * sizeof(u64));
@@ -975,7 +1029,7 @@ extern "C" int rg_debug_scalars(rg_context* ctx, void* out, int64_t bytes) {
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
     size_t nbytes = std::min<size_t>((size_t)bytes, sizeof(Scalars));
-    CK(cudaMemcpy(out, ctx->sc, nbytes, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpyAsync(out, ctx->sc, nbytes, cudaMemcpyDeviceToHost, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream));
     return (int)sizeof(Scalars);
 }
 extern "C" int rg_debug_vector(rg_context* ctx, int32_t which, uint64_t* out) {

@@ -10,6 +10,7 @@ import torch.distributed as dist
 import relp_b200
 from relp_b200.generators import bounded_lp, max_flow
 from relp_b200.solver import nccl_unique_id
+from relp_b200.sharding import share_unique_id
 
 
 def share_id(rank):
