@@ -113,6 +113,17 @@ int rg_load_csc(rg_context* ctx, int32_t m, int32_t n, const int64_t* colptr,
 /* right_hand_side() (:96); must be >= 0 (GeneralForm::make_b_non_negative guarantees it). */
 int rg_set_rhs(rg_context* ctx, const int64_t* b);
 
+/* Weights of a prescaled rational problem (host prescale; all 1 and not needed
+ * for integer problems).  Row i of the rational problem was multiplied by r_i; column j of the integer
+ * image equals the scaled column divided by w_j (unit slack / bound columns keep +-1 entries: w_j = r_i),
+ * the artificial of row i is the unit column (weight r_i).  With W = lcm of all weights:
+ *   colfac[j] = W / w_j,  colw[j] = w_j,  artfac[i] = W / r_i,
+ *   artcost[i] = phase-one cost numerator of the artificial of row i (a common positive multiple of 1/r_i).
+ * They keep Dantzig and steepest-edge choices identical to the rational problem's.  Call after rg_load_csc
+ * and before rg_init_identity_basis.  All values must be in [1, 2^31). */
+int rg_set_weights(rg_context* ctx, const int64_t* colfac, const int64_t* artfac, const int64_t* colw,
+                   const int64_t* artcost);
+
 /* ---- carry constructors (tableau/inverse_maintenance/mod.rs:30-130; carry/mod.rs:374-442) ----- */
 /* create_for_fully_artificial / create_for_partially_artificial / from_basis_pivots with an identity
  * basis: `basis[i]` is the column id basic in row i (negative = artificial of that row, whose phase-one

@@ -28,6 +28,11 @@ typedef struct rh_problem {
     const int32_t* pivot_rows;    /*   -1 = trait not implemented => Fully artificial start         */
     const int32_t* pivot_cols;
     int32_t full_initial_basis;   /* FullInitialBasis (phase_one.rs:101-110): skip phase one */
+    /* weights of a prescaled rational problem (rg_set_weights); all NULL for integer problems */
+    const int64_t* colfac;        /* n */
+    const int64_t* artfac;        /* m */
+    const int64_t* colw;          /* n */
+    const int64_t* artcost;       /* m */
 } rh_problem;
 
 enum { RH_OPTIMAL = 0, RH_UNBOUNDED = 1, RH_INFEASIBLE = 2 };

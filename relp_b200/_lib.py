@@ -33,7 +33,9 @@ class rh_problem(C.Structure):
                 ("vals", C.POINTER(C.c_int64)), ("cost", C.POINTER(C.c_int64)),
                 ("rhs", C.POINTER(C.c_int64)), ("n_pivots", C.c_int32),
                 ("pivot_rows", C.POINTER(C.c_int32)), ("pivot_cols", C.POINTER(C.c_int32)),
-                ("full_initial_basis", C.c_int32)]
+                ("full_initial_basis", C.c_int32),
+                ("colfac", C.POINTER(C.c_int64)), ("artfac", C.POINTER(C.c_int64)),
+                ("colw", C.POINTER(C.c_int64)), ("artcost", C.POINTER(C.c_int64))]
 
 
 class rh_trace_entry(C.Structure):
@@ -58,6 +60,8 @@ SYMBOLS = {
     "rg_load_csc": (C.c_int, [P, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int32),
                               C.POINTER(C.c_int64)]),
     "rg_set_rhs": (C.c_int, [P, C.POINTER(C.c_int64)]),
+    "rg_set_weights": (C.c_int, [P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                 C.POINTER(C.c_int64)]),
     "rg_init_identity_basis": (C.c_int, [P, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "rg_phase_switch": (C.c_int, [P, C.POINTER(C.c_int64)]),
     "rg_rule_new": (C.c_int, [P, C.c_int32]),

@@ -62,9 +62,9 @@ struct Csc {
 
 // widths derived from the carry limb count L
 __host__ __device__ constexpr int LU_of(int L) { return L + 2; }          // pivot column, costs, row dots
-__host__ __device__ constexpr int LW_of(int L) { return 2 * L + 4; }      // work vector
-__host__ __device__ constexpr int LS_of(int L) { return 2 * L + 6; }      // work vector . column
-__host__ __device__ constexpr int LG_of(int L) { return 2 * L + 5; }      // Ghat = gamma * D^2
+__host__ __device__ constexpr int LW_of(int L) { return 2 * L + 5; }      // work vector
+__host__ __device__ constexpr int LS_of(int L) { return 2 * L + 7; }      // work vector . column
+__host__ __device__ constexpr int LG_of(int L) { return 2 * L + 6; }      // Ghat = gamma * D^2 W^2 / w_j^2
 
 }  // namespace rg
 
@@ -91,6 +91,14 @@ struct rg_context {
     int work_chunks = 0;
     u64* tmprow = nullptr;      // LU planes x ld      phase-switch row
     u64* svec = nullptr;        // 1 plane x ld        basic costs (phase switch)
+    u64* us2 = nullptr;         // LU+1 planes x ld    pivot column times row factors^2 (weighted problems)
+    // weights of a prescaled rational problem; all 1 for integer problems
+    bool weighted = false;
+    long long* wf = nullptr;      // n: W / w_j
+    long long* wcol = nullptr;    // n: w_j
+    long long* artf = nullptr;    // m: W / (weight of the artificial of row i)
+    long long* artcost = nullptr; // m: phase-one cost numerator of the artificial of row i
+    long long* rowf = nullptr;    // m: factor of the variable currently basic in row i
     rg::Csc A;
     long long* cost = nullptr;  // n
     long long* rhs = nullptr;   // m

@@ -50,6 +50,8 @@ public:
         check(nullptr, rg_create(&opts, &ctx), "rg_create");
         check(ctx, rg_load_csc(ctx, m, n, mp.p->colptr, mp.p->rowidx, mp.p->vals), "rg_load_csc");
         check(ctx, rg_set_rhs(ctx, mp.p->rhs), "rg_set_rhs");
+        if (mp.p->colfac)
+            check(ctx, rg_set_weights(ctx, mp.p->colfac, mp.p->artfac, mp.p->colw, mp.p->artcost), "rg_set_weights");
     }
     ~GpuCarry() { rg_destroy(ctx); }
     GpuCarry(const GpuCarry&) = delete;

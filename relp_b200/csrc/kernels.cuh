@@ -86,18 +86,30 @@ __global__ void k_init_identity(u64* C, size_t ps, int ld, int nloc, int row_lo,
     C[r + (g + 1)] = 1;
 }
 // cost row (replicated on every rank): -1 under artificial rows
-__global__ void k_init_row0(u64* C, size_t ps, int m, int L, const int* basis) {
+__global__ void k_init_row0(u64* C, size_t ps, int m, int L, const int* basis, const long long* artcost) {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= m) return;
-    if (basis[g] < 0) for (int l = 0; l < L; ++l) C[l * ps + (g + 1)] = ~0ull;   // -1
+    if (basis[g] < 0) {
+        long long c = artcost ? -artcost[g] : -1;    // -(phase-one cost of the artificial of row g)
+        C[g + 1] = (u64)c;
+        for (int l = 1; l < L; ++l) C[l * ps + (g + 1)] = c < 0 ? ~0ull : 0ull;
+    }
+}
+// factor of the variable basic in each row (weighted problems): W / weight
+__global__ void k_init_rowf(const int* basis, const long long* wf, const long long* artf, long long* rowf, int m) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= m) return;
+    int j = basis[g];
+    rowf[g] = j >= 0 ? wf[j] : artf[g];
 }
 // (0,0) = -sum_{artificial rows} b   and scalar state
 __global__ void k_init_scalars(u64* C, size_t ps, int m, int L, const long long* rhs, const int* basis,
-                               int row_lo, int nloc, int rank, int world, Scalars* sc) {
+                               const long long* artcost, int row_lo, int nloc, int rank, int world, Scalars* sc) {
     if (threadIdx.x || blockIdx.x) return;
     u64 buf[3 * RG_MAXL];
     u64* acc = buf; u64* t = buf + RG_MAXL; u64* mg = buf + 2 * RG_MAXL;
-    for (int l = 0; l < L; ++l) acc[l] = 0;
+    const int LA = L < 3 ? 3 : L;          // the objective is accumulated in at least 3 limbs
+    for (int l = 0; l < LA; ++l) acc[l] = 0;
     int maxbits = 1;
     for (int i = 0; i < m; ++i) {
         long long b = rhs[i];
@@ -105,14 +117,19 @@ __global__ void k_init_scalars(u64* C, size_t ps, int m, int L, const long long*
         int bl = mag ? 64 - __clzll(mag) : 0;
         if (bl > maxbits) maxbits = bl;
         if (basis[i] < 0) {
-            for (int l = 0; l < L; ++l) t[l] = l == 0 ? (u64)b : (b < 0 ? ~0ull : 0ull);
-            rt_sub(acc, t, L);
+            // acc -= cost_i * b_i   (both non-negative, product up to 126 bits)
+            u64 c = artcost ? (u64)artcost[i] : 1ull;
+            int cb = c ? 64 - __clzll(c) : 0;
+            if (cb > maxbits) maxbits = cb;
+            u64 lo = c * mag, hi = __umul64hi(c, mag);
+            for (int l = 0; l < LA; ++l) t[l] = l == 0 ? lo : (l == 1 ? hi : 0);
+            rt_sub(acc, t, LA);
         }
     }
-    for (int l = 0; l < L; ++l) C[l * ps] = acc[l];
-    rt_abs(mg, acc, L);
-    int bl = rt_bitlen_u(mg, L);
+    rt_abs(mg, acc, LA);
+    int bl = rt_bitlen_u(mg, LA);
     if (bl > maxbits) maxbits = bl;
+    for (int l = 0; l < L; ++l) C[l * ps] = acc[l];   // the host re-initialises at a wider L if maxbits does not fit
     sc->status = ST_RUN;
     sc->q = -1; sc->p = -1; sc->pg = -1; sc->leaving = 0; sc->sgn = 1;
     sc->row_lo = row_lo; sc->nloc = nloc; sc->rank = rank; sc->world = world;
@@ -204,14 +221,23 @@ struct CmpFirstMem {
 };
 // Dantzig (pivot_rule.rs:163-186): most negative, strict < => lowest index on ties
 struct CmpDantzig {
-    PriceView v;
+    PriceView v; const long long* wcol;     // true reduced cost = w_j * kappa_j / (D * cost scale)
     __device__ bool eligible(int j) const { return !v.inbasis[j] && v.negative(j); }
     __device__ bool better(int j, int k) const {
-        u64 buf[2 * (RG_MAXL + 2)];
-        u64* a = buf; u64* b = buf + RG_MAXL + 2;
+        u64 buf[4 * (RG_MAXL + 3)];
+        u64* a = buf; u64* b = buf + (RG_MAXL + 3); u64* x = buf + 2 * (RG_MAXL + 3); u64* y = buf + 3 * (RG_MAXL + 3);
         rt_load_planar(a, v.LU, v.kappa, v.n, j);
         rt_load_planar(b, v.LU, v.kappa, v.n, k);
-        int c = rt_cmp_s(a, b, v.LU);
+        int c;
+        if (wcol) {     // both negative: compare magnitudes |kappa_j| w_j vs |kappa_k| w_k
+            u64 wj = (u64)wcol[j], wk = (u64)wcol[k];
+            rt_neg(a, v.LU); rt_neg(b, v.LU);
+            rt_mul_full(x, a, v.LU, &wj, 1);
+            rt_mul_full(y, b, v.LU, &wk, 1);
+            c = -rt_cmp_u(x, y, v.LU + 1);
+        } else {
+            c = rt_cmp_s(a, b, v.LU);
+        }
         return c < 0 || (c == 0 && j < k);
     }
 };
@@ -322,7 +348,8 @@ __device__ inline double planar_log2_abs(const u64* base, size_t stride, size_t 
 // mode 2: Dantzig  score = log2|kappa|;  mode 3: steepest edge  score = 2 log2|kappa| - log2 Ghat
 __global__ void __launch_bounds__(256)
 k_score_columns(int n, int mode, const u64* __restrict__ kappa, int LU, const u64* __restrict__ G, int LG,
-                const unsigned char* __restrict__ inbasis, double* __restrict__ score, const Scalars* sc) {
+                const unsigned char* __restrict__ inbasis, const long long* __restrict__ wcol,
+                double* __restrict__ score, const Scalars* sc) {
     if (sc->status != ST_RUN) return;
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
@@ -331,7 +358,7 @@ k_score_columns(int n, int mode, const u64* __restrict__ kappa, int LU, const u6
         int sg;
         double lk = planar_log2_abs(kappa, n, j, LU, &sg);
         if (sg < 0) {
-            if (mode == 2) s = lk;
+            if (mode == 2) s = wcol ? lk + log2((double)wcol[j]) : lk;
             else { int sg2; s = 2.0 * lk - planar_log2_abs(G, n, j, LG, &sg2); }
         }
     }
@@ -700,7 +727,7 @@ __global__ void __launch_bounds__(32) k_scalars_se(int L, const u64* __restrict_
         ax[RG_MAXW], tmp[RG_MAXW], cols[3 * RG_MAXW];
     if (sc->status != ST_RUN) return;
     const int lane = threadIdx.x;
-    const int LU = L + 2, LG = 2 * L + 5;
+    const int LU = L + 2, LG = 2 * L + 6;
     const int t = sc->t;
     const int t2 = 2 * t;
     int E2 = (t2 + 63) >> 6;
@@ -933,7 +960,7 @@ k_update_generic(u64* __restrict__ C, size_t ps, int ld, int nrows, int L, const
 
 // after the update: basis bookkeeping, D <- |a|, steepest-edge weight of the leaving column
 __global__ void k_finalize(int* basis, unsigned char* inbasis, int L, u64* G, int n, int LG,
-                           int want_se, Scalars* sc, HostMirror* hm) {
+                           int want_se, const long long* wf, long long* rowf, Scalars* sc, HostMirror* hm) {
     if (threadIdx.x || blockIdx.x) return;
     if (sc->status == ST_RUN) {
         int r = sc->pg - 1;
@@ -941,6 +968,7 @@ __global__ void k_finalize(int* basis, unsigned char* inbasis, int L, u64* G, in
         sc->leaving = leaving;
         basis[r] = sc->q;
         inbasis[sc->q] = 1;
+        if (rowf) rowf[r] = wf[sc->q];
         if (leaving >= 0) {
             inbasis[leaving] = 0;
             if (want_se) for (int l = 0; l < LG; ++l) G[(size_t)l * n + leaving] = sc->Gq[l];
@@ -1090,6 +1118,26 @@ k_colsum2(const u64* __restrict__ part, int ld, int chunks, int negate, u64* __r
     if ((threadIdx.x & 31) == 0 && bl) atomicMax(&sc->maxbits_tmp, bl);
 }
 
+// weighted problems: s_i = u_i * (W / w_B(i))^2, the factor vector of the work-vector column sum
+template <int L>
+__global__ void __launch_bounds__(256)
+k_scale_u(const u64* __restrict__ u, size_t us, int nloc, const long long* __restrict__ rowf,
+          u64* __restrict__ out, size_t os, const Scalars* sc) {
+    constexpr int LU = L + 2;
+    if (sc->status != ST_RUN) return;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;    // local carry row
+    if (i > nloc) return;
+    u64 x[LU], acc[LU + 1];
+    load_planar<LU>(x, u, us, (size_t)i);
+#pragma unroll
+    for (int l = 0; l <= LU; ++l) acc[l] = 0;
+    if (i >= 1) {
+        long long f = rowf[sc->row_lo + i - 1];
+        mac_small<LU + 1, LU>(acc, x, f * f);
+    }
+    store_planar<LU + 1>(out, os, (size_t)i, acc);
+}
+
 // basic cost of every local row as an (nloc+1)-vector of LSRC = 1 limb (artificial / inert rows: 0)
 __global__ void k_basic_costs(const int* basis, const long long* cost, int nloc, int row_lo, u64* s) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1117,20 +1165,36 @@ __global__ void k_reset_tmpbits(Scalars* sc) {
 //   init (general carry):   Ghat_j = D^2 + sum_i (C[i][1..m] . a_j)^2  block per column
 //   update: Ghat'_j = [a^2 Ghat_j - 2 a nu_j sigma_j + nu_j^2 Ghat_q] / D^2   (after_basis_update :243-296)
 // ---------------------------------------------------------------------------------------------
-__global__ void k_gamma_init_identity(int n, const long long* colptr, const long long* vals,
-                                      const unsigned char* inbasis, u64* G, int LG) {
+__global__ void k_gamma_init_identity(int n, const long long* colptr, const int* rowidx, const long long* vals,
+                                      const unsigned char* inbasis, const long long* wf, const long long* rowf,
+                                      u64* G, int LG) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
-    u64 acc[3] = {0, 0, 0};
+    u64 acc[6] = {0, 0, 0, 0, 0, 0};
     if (!inbasis[j]) {
-        acc[0] = 1;
+        // Ghat_j = (W/w_j)^2 + sum_i (a_ij W / w_B(i))^2     (D = 1)
+        u64 f = wf ? (u64)wf[j] : 1ull;
+        mac3(acc[0], acc[1], acc[2], f, f);
         for (long long k = colptr[j]; k < colptr[j + 1]; ++k) {
             long long v = vals[k];
             u64 mg = v < 0 ? (u64)(-v) : (u64)v;
-            mac3(acc[0], acc[1], acc[2], mg, mg);
+            u64 rf = rowf ? (u64)rowf[rowidx[k]] : 1ull;
+            // t = mg * rf (up to 94 bits), acc += t^2 (up to 188 bits)
+            u64 t0 = mg * rf, t1 = __umul64hi(mg, rf);
+            u64 sq[4] = {0, 0, 0, 0};
+            u64 c0 = 0, c1 = 0, c2 = 0;
+            mac3(c0, c1, c2, t0, t0); sq[0] = c0; c0 = c1; c1 = c2; c2 = 0;
+            mac3(c0, c1, c2, t0, t1); mac3(c0, c1, c2, t1, t0); sq[1] = c0; c0 = c1; c1 = c2; c2 = 0;
+            mac3(c0, c1, c2, t1, t1); sq[2] = c0; sq[3] = c1;
+            u64 cf = 0;
+            for (int l = 0; l < 6; ++l) {
+                u64 b = l < 4 ? sq[l] : 0;
+                u64 x = acc[l] + b; u64 k1 = x < b; u64 x2 = x + cf; u64 k2 = x2 < x;
+                acc[l] = x2; cf = k1 + k2;
+            }
         }
     }
-    for (int l = 0; l < LG; ++l) G[(size_t)l * n + j] = l < 3 ? acc[l] : 0;
+    for (int l = 0; l < LG; ++l) G[(size_t)l * n + j] = l < 6 ? acc[l] : 0;
 }
 
 template <int L>
@@ -1138,8 +1202,9 @@ __global__ void __launch_bounds__(128)
 k_gamma_init_general(const u64* __restrict__ C, size_t ps, int ld, int m, int n,
                      const long long* __restrict__ colptr, const int* __restrict__ rowidx,
                      const long long* __restrict__ vals, const unsigned char* __restrict__ inbasis,
-                     u64* __restrict__ G, int add_d2, const Scalars* sc) {
-    constexpr int LU = L + 2, LG = 2 * L + 5;
+                     u64* __restrict__ G, int add_d2, const long long* __restrict__ wf,
+                     const long long* __restrict__ rowf, const Scalars* sc) {
+    constexpr int LU = L + 2, LG = 2 * L + 6;
     __shared__ u64 sAcc[4][LG];
     int j = blockIdx.x;
     if (j >= n) return;
@@ -1165,12 +1230,25 @@ k_gamma_init_general(const u64* __restrict__ C, size_t ps, int ld, int m, int n,
 #pragma unroll
             for (int l = 0; l < LU; ++l) { u64 v = ~nu[l] + c; c = (c && v == 0) ? 1 : 0; nu[l] = v; }
         }
-        u64 sq[2 * LU];
-        mul_full_ct<LU, LU>(sq, nu, nu);
+        // scale by the row factor W / w_B(i) (1 for integer problems)
+        u64 nus[LU + 1];
+        {
+            u64 rf = rowf ? (u64)rowf[sc->row_lo + i - 1] : 1ull;
+            u64 carry = 0;
+#pragma unroll
+            for (int l = 0; l < LU; ++l) {
+                u64 lo = nu[l] * rf, hi = __umul64hi(nu[l], rf);
+                u64 v = lo + carry; u64 c1 = v < lo;
+                nus[l] = v; carry = hi + c1;
+            }
+            nus[LU] = carry;
+        }
+        u64 sq[2 * LU + 2];
+        mul_full_ct<LU + 1, LU + 1>(sq, nus, nus);
         u64 cf = 0;
 #pragma unroll
         for (int l = 0; l < LG; ++l) {
-            u64 b = l < 2 * LU ? sq[l] : 0;
+            u64 b = l < 2 * LU + 2 ? sq[l] : 0;
             u64 v = acc[l] + b; u64 c1 = v < b; u64 v2 = v + cf; u64 c2 = v2 < v;
             acc[l] = v2; cf = c1 + c2;
         }
@@ -1196,14 +1274,25 @@ k_gamma_init_general(const u64* __restrict__ C, size_t ps, int ld, int m, int n,
             add_n<LG>(acc, other);
         }
         if (add_d2) {    // row-sharded: only rank 0 contributes the D^2 term to the sum of parts
-            u64 d[L], d2[2 * L];
+            // + (D W / w_j)^2
+            u64 d[L + 1], d2[2 * L + 2];
+            {
+                u64 f = wf ? (u64)wf[j] : 1ull;
+                u64 carry = 0;
 #pragma unroll
-            for (int l = 0; l < L; ++l) d[l] = sc->D[l];
-            mul_full_ct<L, L>(d2, d, d);
+                for (int l = 0; l < L; ++l) {
+                    u64 x = sc->D[l];
+                    u64 lo = x * f, hi = __umul64hi(x, f);
+                    u64 v = lo + carry; u64 c1 = v < lo;
+                    d[l] = v; carry = hi + c1;
+                }
+                d[L] = carry;
+            }
+            mul_full_ct<L + 1, L + 1>(d2, d, d);
             u64 cf = 0;
 #pragma unroll
             for (int l = 0; l < LG; ++l) {
-                u64 b = l < 2 * L ? d2[l] : 0;
+                u64 b = l < 2 * L + 2 ? d2[l] : 0;
                 u64 v = acc[l] + b; u64 c1 = v < b; u64 v2 = v + cf; u64 c2 = v2 < v;
                 acc[l] = v2; cf = c1 + c2;
             }
@@ -1218,7 +1307,7 @@ template <int L>
 __global__ void __launch_bounds__(128)
 k_gamma_update_t(int n, const unsigned char* __restrict__ inbasis, const u64* __restrict__ nu,
                  const u64* __restrict__ sigma, u64* __restrict__ G, const Scalars* sc) {
-    constexpr int LU = L + 2, LS = 2 * L + 6, LG = 2 * L + 5, WX = LG + 4, N = 2 * WX;
+    constexpr int LU = L + 2, LS = 2 * L + 7, LG = 2 * L + 6, WX = LG + 4, N = 2 * WX;
     if (sc->status != ST_RUN) return;
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
@@ -1295,7 +1384,7 @@ k_gamma_update(int n, int L, const unsigned char* __restrict__ inbasis, const u6
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     if (inbasis[j] || j == sc->leaving) return;   // entering: None; leaving: set by k_finalize
-    const int LU = L + 2, LS = 2 * L + 6, LG = 2 * L + 5;
+    const int LU = L + 2, LS = 2 * L + 7, LG = 2 * L + 6;
     const int WX = LG + sc->E2;
     u64 buf[7 * RG_MAXW];
     u64* raw = buf; u64* nv = buf + RG_MAXW; u64* sg = buf + 2 * RG_MAXW; u64* g = buf + 3 * RG_MAXW;

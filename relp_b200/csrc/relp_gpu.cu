@@ -114,6 +114,7 @@ static int alloc_width_buffers(rg_context* ctx, int L) {
     CK(dev_alloc(&ctx->omega, sizeof(u64) * LW_of(L) * ld, ctx->stream));
     CK(dev_alloc(&ctx->omega_part, sizeof(u64) * ctx->work_chunks * LW_of(L) * ld, ctx->stream));
     CK(dev_alloc(&ctx->tmprow, sizeof(u64) * LU_of(L) * ld, ctx->stream));
+    CK(dev_alloc(&ctx->us2, sizeof(u64) * (LU_of(L) + 1) * ld, ctx->stream));
     CK(dev_alloc(&ctx->kappa, sizeof(u64) * LU_of(L) * n, ctx->stream));
     CK(dev_alloc(&ctx->nu, sizeof(u64) * LU_of(L) * n, ctx->stream));
     CK(dev_alloc(&ctx->sigma, sizeof(u64) * LS_of(L) * n, ctx->stream));
@@ -124,8 +125,8 @@ static int alloc_width_buffers(rg_context* ctx, int L) {
 }
 static void free_width_buffers(rg_context* ctx) {
     free_dev_on(ctx->u, ctx->stream); free_dev_on(ctx->rowp, ctx->stream); free_dev_on(ctx->omega, ctx->stream); free_dev_on(ctx->omega_part, ctx->stream);
-    free_dev_on(ctx->tmprow, ctx->stream); free_dev_on(ctx->kappa, ctx->stream); free_dev_on(ctx->nu, ctx->stream); free_dev_on(ctx->sigma, ctx->stream);
-    ctx->u = ctx->rowp = ctx->omega = ctx->omega_part = ctx->tmprow = nullptr;
+    free_dev_on(ctx->tmprow, ctx->stream); free_dev_on(ctx->us2, ctx->stream); free_dev_on(ctx->kappa, ctx->stream); free_dev_on(ctx->nu, ctx->stream); free_dev_on(ctx->sigma, ctx->stream);
+    ctx->u = ctx->rowp = ctx->omega = ctx->omega_part = ctx->tmprow = ctx->us2 = nullptr;
     ctx->kappa = ctx->nu = ctx->sigma = nullptr;
 }
 
@@ -200,6 +201,8 @@ extern "C" int rg_destroy(rg_context* ctx) {
     free_dev_on(ctx->cost, ctx->stream); free_dev_on(ctx->rhs, ctx->stream); free_dev_on(ctx->basis, ctx->stream); free_dev_on(ctx->inbasis, ctx->stream);
     free_dev_on(ctx->G, ctx->stream); free_dev_on(ctx->cand, ctx->stream); free_dev_on(ctx->score, ctx->stream); free_dev_on(ctx->sc, ctx->stream); free_dev_on(ctx->svec, ctx->stream);
     free_dev_on(ctx->xsend, ctx->stream); free_dev_on(ctx->xrecv, ctx->stream);
+    free_dev_on(ctx->wf, ctx->stream); free_dev_on(ctx->wcol, ctx->stream); free_dev_on(ctx->artf, ctx->stream);
+    free_dev_on(ctx->artcost, ctx->stream); free_dev_on(ctx->rowf, ctx->stream);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->hm) cudaFreeHost(ctx->hm);
     if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); for (int k = 0; k < 8; ++k) cudaEventDestroy(ctx->evp[k]); }
@@ -247,6 +250,11 @@ extern "C" int rg_load_csc(rg_context* ctx, int32_t m, int32_t n, const int64_t*
     CK(dev_alloc(&ctx->cand, sizeof(int) * 1024, ctx->stream));
     CK(dev_alloc(&ctx->score, sizeof(double) * std::max(m, n), ctx->stream));
     CK(dev_alloc(&ctx->svec, sizeof(u64) * ctx->ld, ctx->stream));
+    CK(dev_alloc(&ctx->wf, sizeof(long long) * n, ctx->stream));
+    CK(dev_alloc(&ctx->wcol, sizeof(long long) * n, ctx->stream));
+    CK(dev_alloc(&ctx->artf, sizeof(long long) * m, ctx->stream));
+    CK(dev_alloc(&ctx->artcost, sizeof(long long) * m, ctx->stream));
+    CK(dev_alloc(&ctx->rowf, sizeof(long long) * m, ctx->stream));
     ctx->work_chunks = std::max(1, std::min(16, cdiv(std::max(ctx->nloc, 1), 256)));
     CK(dev_alloc(&ctx->carry, sizeof(u64) * ctx->L * ctx->plane, ctx->stream));
     CK(dev_alloc(&ctx->G, sizeof(u64) * LG_of(ctx->L) * n, ctx->stream));
@@ -260,6 +268,27 @@ extern "C" int rg_set_rhs(rg_context* ctx, const int64_t* b) {
     if (!ctx || !ctx->rhs || !b) return RG_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemcpyAsync(ctx->rhs, b, sizeof(long long) * ctx->m, cudaMemcpyHostToDevice, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream));
+    return RG_OK;
+}
+
+extern "C" int rg_set_weights(rg_context* ctx, const int64_t* colfac, const int64_t* artfac,
+                              const int64_t* colw, const int64_t* artcost) {
+    if (!ctx || !ctx->carry || !colfac || !artfac || !colw || !artcost) return RG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    for (int j = 0; j < ctx->n; ++j)
+        if (colfac[j] <= 0 || colfac[j] >= (1ll << 31) || colw[j] <= 0 || colw[j] >= (1ll << 31)) {
+            ctx->err = "rg_set_weights: weights must be in [1, 2^31)"; return RG_ERR_ARG;
+        }
+    for (int i = 0; i < ctx->m; ++i)
+        if (artfac[i] <= 0 || artfac[i] >= (1ll << 31) || artcost[i] < 0) {
+            ctx->err = "rg_set_weights: artificial factors must be in [1, 2^31), costs >= 0"; return RG_ERR_ARG;
+        }
+    CK(cudaMemcpyAsync(ctx->wf, colfac, sizeof(long long) * ctx->n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->wcol, colw, sizeof(long long) * ctx->n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->artf, artfac, sizeof(long long) * ctx->m, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->artcost, artcost, sizeof(long long) * ctx->m, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->weighted = true;
     return RG_OK;
 }
 
@@ -278,6 +307,8 @@ static int ensure_xbuf(rg_context* ctx, size_t send_words, size_t recv_words) {
     if (need <= ctx->xbytes) return RG_OK;
     CK(cudaStreamSynchronize(ctx->stream));
     free_dev_on(ctx->xsend, ctx->stream); free_dev_on(ctx->xrecv, ctx->stream);
+    free_dev_on(ctx->wf, ctx->stream); free_dev_on(ctx->wcol, ctx->stream); free_dev_on(ctx->artf, ctx->stream);
+    free_dev_on(ctx->artcost, ctx->stream); free_dev_on(ctx->rowf, ctx->stream);
     CK(dev_alloc(&ctx->xsend, need, ctx->stream));
     CK(dev_alloc(&ctx->xrecv, need, ctx->stream));
     ctx->xbytes = need;
@@ -333,12 +364,13 @@ static void launch_select(rg_context* ctx) {
         case RG_RULE_FIRST_PROFITABLE_WITH_MEMORY: launch_argbest(ctx, ctx->n, CmpFirstMem{v, ctx->sc}, 0); break;
         case RG_RULE_DANTZIG:
             LAUNCH(k_score_columns, cdiv(ctx->n, 256), 256, ctx->n, 2, ctx->kappa, LU_of(ctx->L), ctx->G,
-                   LG_of(ctx->L), ctx->inbasis, ctx->score, ctx->sc);
-            LAUNCH((k_select_scored<CmpDantzig>), 1, 1024, ctx->n, CmpDantzig{v}, ctx->score, 0, ctx->sc);
+                   LG_of(ctx->L), ctx->inbasis, ctx->weighted ? ctx->wcol : nullptr, ctx->score, ctx->sc);
+            LAUNCH((k_select_scored<CmpDantzig>), 1, 1024, ctx->n,
+                   (CmpDantzig{v, ctx->weighted ? ctx->wcol : nullptr}), ctx->score, 0, ctx->sc);
             break;
         default:
             LAUNCH(k_score_columns, cdiv(ctx->n, 256), 256, ctx->n, 3, ctx->kappa, LU_of(ctx->L), ctx->G,
-                   LG_of(ctx->L), ctx->inbasis, ctx->score, ctx->sc);
+                   LG_of(ctx->L), ctx->inbasis, nullptr, ctx->score, ctx->sc);
             LAUNCH((k_select_scored<CmpSteepest>), 1, 1024, ctx->n, CmpSteepest{v, ctx->G, LG_of(ctx->L)},
                    ctx->score, 0, ctx->sc);
             break;
@@ -409,11 +441,18 @@ static int launch_copyrow(rg_context* ctx) {
 
 template <int L>
 static int launch_work_t(rg_context* ctx) {
-    constexpr int LU = L + 2, LW = 2 * L + 4;
+    constexpr int LU = L + 2, LW = 2 * L + 5;
     int rpc = cdiv(std::max(ctx->nloc, 1), ctx->work_chunks);
     dim3 grid(cdiv(ctx->ld, 128), ctx->work_chunks);
-    LAUNCH((k_colsum1<L, LU, LW>), grid, 128, ctx->carry, ctx->plane, ctx->ld, ctx->nloc, rpc, ctx->u,
-           (size_t)ctx->ld, ctx->omega_part, ctx->sc);
+    if (ctx->weighted) {
+        LAUNCH((k_scale_u<L>), cdiv(ctx->nloc + 1, 256), 256, ctx->u, (size_t)ctx->ld, ctx->nloc, ctx->rowf,
+               ctx->us2, (size_t)ctx->ld, ctx->sc);
+        LAUNCH((k_colsum1<L, LU + 1, LW>), grid, 128, ctx->carry, ctx->plane, ctx->ld, ctx->nloc, rpc, ctx->us2,
+               (size_t)ctx->ld, ctx->omega_part, ctx->sc);
+    } else {
+        LAUNCH((k_colsum1<L, LU, LW>), grid, 128, ctx->carry, ctx->plane, ctx->ld, ctx->nloc, rpc, ctx->u,
+               (size_t)ctx->ld, ctx->omega_part, ctx->sc);
+    }
     if (ctx->world == 1) {
         LAUNCH((k_colsum2<LW>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, ctx->work_chunks, 0,
                ctx->omega, ctx->sc);
@@ -460,7 +499,7 @@ static void launch_update(rg_context* ctx, int E) { DISPATCH_L(ctx->L, launch_up
 
 template <int L>
 static void launch_se_dots_t(rg_context* ctx) {
-    constexpr int LU = L + 2, LW = 2 * L + 4, LS = 2 * L + 6;
+    constexpr int LU = L + 2, LW = LW_of(L), LS = LS_of(L);
     LAUNCH((k_coldot<L, LU>), cdiv(ctx->n, 256), 256, ctx->rowp, (size_t)ctx->ld, ctx->n, ctx->A.colptr,
            ctx->A.rowidx, ctx->A.vals, ctx->inbasis, ctx->cost, 0, L, ctx->nu, ctx->sc);
     LAUNCH((k_coldot<LW, LS>), cdiv(ctx->n, 256), 256, ctx->omega, (size_t)ctx->ld, ctx->n, ctx->A.colptr,
@@ -559,7 +598,8 @@ static int do_pivot(rg_context* ctx, int q, int fixed_row, bool want_se, bool re
         if (prof) cudaEventRecord(ctx->ev1, ctx->stream);
         if (want_se) cudaStreamWaitEvent(ctx->stream, ctx->ev_side1, 0);
         LAUNCH(k_finalize, 1, 1, ctx->basis, ctx->inbasis, ctx->L, ctx->G, ctx->n, LG_of(ctx->L),
-               want_se ? 1 : 0, ctx->sc, ctx->hm_dev);
+               want_se ? 1 : 0, ctx->weighted ? ctx->wf : nullptr, ctx->weighted ? ctx->rowf : nullptr, ctx->sc,
+               ctx->hm_dev);
         if (want_se) launch_se_update(ctx);
         if (prof) cudaEventRecord(ctx->evp[3], ctx->stream);
         if (reselect) { launch_price(ctx); launch_select(ctx); }
@@ -625,12 +665,20 @@ extern "C" int rg_init_identity_basis(rg_context* ctx, const int32_t* basis, con
         CK(cudaMemsetAsync(ctx->cost, 0, sizeof(long long) * n, ctx->stream));
     }
     CK(cudaMemsetAsync(ctx->inbasis, 0, n, ctx->stream));
-    LAUNCH(k_zero, 148 * 8, 256, ctx->carry, (size_t)ctx->L * ctx->plane);
-    LAUNCH(k_init_identity, cdiv(std::max(ctx->nloc, 1), 256), 256, ctx->carry, ctx->plane, ctx->ld, ctx->nloc,
-           ctx->row_lo, ctx->L, ctx->rhs);
-    LAUNCH(k_init_row0, cdiv(m, 256), 256, ctx->carry, ctx->plane, m, ctx->L, ctx->basis);
-    LAUNCH(k_init_scalars, 1, 1, ctx->carry, ctx->plane, m, ctx->L, ctx->rhs, ctx->basis, ctx->row_lo, ctx->nloc,
-           ctx->rank, ctx->world, ctx->sc);
+    for (;;) {
+        LAUNCH(k_zero, 148 * 8, 256, ctx->carry, (size_t)ctx->L * ctx->plane);
+        LAUNCH(k_init_identity, cdiv(std::max(ctx->nloc, 1), 256), 256, ctx->carry, ctx->plane, ctx->ld,
+               ctx->nloc, ctx->row_lo, ctx->L, ctx->rhs);
+        LAUNCH(k_init_row0, cdiv(m, 256), 256, ctx->carry, ctx->plane, m, ctx->L, ctx->basis,
+               ctx->weighted ? ctx->artcost : nullptr);
+        LAUNCH(k_init_scalars, 1, 1, ctx->carry, ctx->plane, m, ctx->L, ctx->rhs, ctx->basis,
+               ctx->weighted ? ctx->artcost : nullptr, ctx->row_lo, ctx->nloc, ctx->rank, ctx->world, ctx->sc);
+        RG_TRY(sync_mirror(ctx));
+        if (ctx->hm->maxbits_carry <= 64 * ctx->L - 1) break;
+        RG_TRY(promote(ctx));      // the initial objective does not fit: start at the next width
+    }
+    if (ctx->weighted)
+        LAUNCH(k_init_rowf, cdiv(m, 256), 256, ctx->basis, ctx->wf, ctx->artf, ctx->rowf, m);
     LAUNCH(k_set_inbasis, cdiv(m, 256), 256, ctx->inbasis, ctx->basis, m);
     ctx->identity_carry = true;
     ctx->rule_ready = false; ctx->have_column = false; ctx->selected = false;
@@ -703,16 +751,18 @@ extern "C" int rg_phase_switch(rg_context* ctx, const int64_t* cost) {
 // ------------------------------------------------------------------------------------------------
 template <int L>
 static int launch_gamma_general_t(rg_context* ctx) {
-    constexpr int LG = 2 * L + 5;
+    constexpr int LG = 2 * L + 6;
     if (ctx->world == 1) {
         LAUNCH((k_gamma_init_general<L>), ctx->n, 128, ctx->carry, ctx->plane, ctx->ld, ctx->nloc, ctx->n,
-               ctx->A.colptr, ctx->A.rowidx, ctx->A.vals, ctx->inbasis, ctx->G, 1, ctx->sc);
+               ctx->A.colptr, ctx->A.rowidx, ctx->A.vals, ctx->inbasis, ctx->G, 1, ctx->weighted ? ctx->wf : nullptr,
+               ctx->weighted ? ctx->rowf : nullptr, ctx->sc);
         return RG_OK;
     }
     size_t words = (size_t)LG * ctx->n;
     RG_TRY(ensure_xbuf(ctx, words, words * ctx->world));
     LAUNCH((k_gamma_init_general<L>), ctx->n, 128, ctx->carry, ctx->plane, ctx->ld, ctx->nloc, ctx->n,
-           ctx->A.colptr, ctx->A.rowidx, ctx->A.vals, ctx->inbasis, ctx->xsend, ctx->rank == 0 ? 1 : 0, ctx->sc);
+           ctx->A.colptr, ctx->A.rowidx, ctx->A.vals, ctx->inbasis, ctx->xsend, ctx->rank == 0 ? 1 : 0,
+           ctx->weighted ? ctx->wf : nullptr, ctx->weighted ? ctx->rowf : nullptr, ctx->sc);
     RG_TRY(all_gather(ctx, ctx->xsend, ctx->xrecv, words));
     LAUNCH((k_colsum2<LG>), cdiv(ctx->n, 64), 64, ctx->xrecv, ctx->n, ctx->world, 0, ctx->G, ctx->sc);
     return RG_OK;
@@ -735,8 +785,9 @@ extern "C" int rg_rule_new(rg_context* ctx, int32_t rule) {
     LAUNCH(k_set_pq, 1, 1, ctx->sc, -1, -1);
     if (rule == RG_RULE_STEEPEST_EDGE) {
         if (ctx->identity_carry) {
-            LAUNCH(k_gamma_init_identity, cdiv(ctx->n, 256), 256, ctx->n, ctx->A.colptr, ctx->A.vals,
-                   ctx->inbasis, ctx->G, LG_of(ctx->L));
+            LAUNCH(k_gamma_init_identity, cdiv(ctx->n, 256), 256, ctx->n, ctx->A.colptr, ctx->A.rowidx,
+                   ctx->A.vals, ctx->inbasis, ctx->weighted ? ctx->wf : nullptr,
+                   ctx->weighted ? ctx->rowf : nullptr, ctx->G, LG_of(ctx->L));
         } else {
             RG_TRY(launch_gamma_general(ctx));
         }

@@ -1,0 +1,271 @@
+"""Host-side front-end feeding the engine from MPS/SIF files (SURVEY.md section 8f "next" rows 1-3).
+
+This is NOT a restatement of relp's parser / presolve: it is the minimum needed to hand the netlib
+configurations to the hot path.  It reads fixed/free MPS, canonicalises to the row/column layout of the
+reference's `MatrixData` (src/algorithm/two_phase/matrix_provider/matrix_data.rs:46-61,291-329:
+equality, range, <=, >= rows; variable-bound rows; x >= 0 with optional upper bounds) WITHOUT presolve,
+and prescales the rational rows to integers for the device.
+
+Because no presolve is applied, the canonical problem differs from the one relp solves after its
+presolve; optimal objective values are identical (they are unique), traces are compared GPU-vs-oracle on
+the same canonical problem.
+"""
+from fractions import Fraction
+from math import gcd
+
+import numpy as np
+
+from .solver import IntegerProblem
+
+INF = None
+
+
+def parse_mps(text):
+    """Returns dict(name, rows=[(name, type)], objective, columns={col: {row: Fraction}}, col_order,
+    rhs={row: Fraction}, ranges={row: Fraction}, bounds={col: [lo, hi]}); decimal numbers are read
+    exactly (src/io/mps/number/parse.rs:46-119 semantics: integer * 10^-k)."""
+    section = None
+    rows, row_type = [], {}
+    objective = None
+    columns, col_order = {}, []
+    rhs, ranges, bounds = {}, {}, {}
+    name = ""
+    integer_marker = False
+    for raw in text.splitlines():
+        if not raw.strip() or raw.lstrip().startswith("*"):
+            continue
+        if not raw[0].isspace():
+            parts = raw.split()
+            section = parts[0].upper()
+            if section == "NAME" and len(parts) > 1:
+                name = parts[1]
+            if section == "ENDATA":
+                break
+            continue
+        f = raw.split()
+        if section == "ROWS":
+            t, r = f[0].upper(), f[1]
+            if t == "N":
+                if objective is None:
+                    objective = r
+                continue
+            rows.append(r)
+            row_type[r] = t
+        elif section == "COLUMNS":
+            if len(f) >= 3 and f[1] == "'MARKER'":
+                integer_marker = "INTORG" in raw
+                continue
+            col = f[0]
+            if col not in columns:
+                columns[col] = {}
+                col_order.append(col)
+            for k in range(1, len(f) - 1, 2):
+                v = Fraction(f[k + 1])
+                if v != 0:
+                    columns[col][f[k]] = columns[col].get(f[k], 0) + v
+        elif section == "RHS":
+            start = 1 if len(f) % 2 == 1 else 0
+            for k in range(start, len(f) - 1, 2):
+                rhs[f[k]] = Fraction(f[k + 1])
+        elif section == "RANGES":
+            start = 1 if len(f) % 2 == 1 else 0
+            for k in range(start, len(f) - 1, 2):
+                ranges[f[k]] = Fraction(f[k + 1])
+        elif section == "BOUNDS":
+            t = f[0].upper()
+            if t in ("FR", "MI", "PL", "BV"):
+                col = f[2] if len(f) >= 3 else f[1]
+                val = None
+            else:
+                col, val = (f[2], Fraction(f[3])) if len(f) >= 4 else (f[1], Fraction(f[2]))
+            lo, hi = bounds.get(col, [Fraction(0), INF])
+            if t == "UP":
+                hi = val
+                if val < 0 and lo == 0:
+                    lo = INF
+            elif t == "LO":
+                lo = val
+            elif t == "FX":
+                lo = hi = val
+            elif t == "FR":
+                lo, hi = INF, INF
+            elif t == "MI":
+                lo = INF
+            elif t == "PL":
+                hi = INF
+            elif t == "BV":
+                lo, hi = Fraction(0), Fraction(1)
+            elif t in ("LI",):
+                lo = val
+            elif t in ("UI",):
+                hi = val
+            bounds[col] = [lo, hi]
+    return dict(name=name, rows=rows, row_type=row_type, objective=objective, columns=columns,
+                col_order=col_order, rhs=rhs, ranges=ranges, bounds=bounds)
+
+
+class CanonicalLP:
+    """min c x + constant over the MatrixData layout; `recover` maps a reduced solution back."""
+
+    def __init__(self):
+        self.constraint_columns = []
+        self.b = []
+        self.ranges = []
+        self.counts = (0, 0, 0, 0)
+        self.costs = []
+        self.upper = []
+        self.constant = Fraction(0)
+        self.var_map = []      # per canonical column: (original column, +1 / -1, shift)
+        self.name = ""
+
+
+def canonicalize(mps):
+    """MPS dict -> CanonicalLP (no presolve)."""
+    lp = CanonicalLP()
+    lp.name = mps["name"]
+    rows, row_type = mps["rows"], mps["row_type"]
+    obj = mps["objective"]
+    rhs = {r: mps["rhs"].get(r, Fraction(0)) for r in rows}
+    lp.constant = -mps["rhs"].get(obj, Fraction(0))
+    # row intervals [lo, hi]
+    interval = {}
+    for r in rows:
+        t, b = row_type[r], rhs[r]
+        lo, hi = (b, b) if t == "E" else ((INF, b) if t == "L" else (b, INF))
+        if r in mps["ranges"]:
+            rg = mps["ranges"][r]
+            if t == "G":
+                hi = b + abs(rg)
+            elif t == "L":
+                lo = b - abs(rg)
+            else:
+                lo, hi = (b, b + abs(rg)) if rg >= 0 else (b - abs(rg), b)
+        interval[r] = [lo, hi]
+    # variables -> x' >= 0
+    new_cols = []   # (entries {row: v}, cost, upper, (orig, sign, shift))
+    for col in mps["col_order"]:
+        entries = dict(mps["columns"][col])
+        cost = entries.pop(obj, Fraction(0))
+        entries = {r: v for r, v in entries.items() if r in interval}
+        lo, hi = mps["bounds"].get(col, [Fraction(0), INF])
+        if lo is not INF:
+            shift = lo
+            up = None if hi is INF else hi - lo
+            if shift != 0:
+                lp.constant += cost * shift
+                for r, v in entries.items():
+                    for k in (0, 1):
+                        if interval[r][k] is not INF:
+                            interval[r][k] -= v * shift
+            if up is not None and up == 0:
+                continue   # fixed variable: substituted out
+            new_cols.append((entries, cost, up, (col, 1, shift)))
+        elif hi is not INF:
+            # x = hi - x'
+            lp.constant += cost * hi
+            for r, v in entries.items():
+                for k in (0, 1):
+                    if interval[r][k] is not INF:
+                        interval[r][k] -= v * hi
+            new_cols.append(({r: -v for r, v in entries.items()}, -cost, None, (col, -1, hi)))
+        else:
+            new_cols.append((entries, cost, None, (col, 1, Fraction(0))))
+            new_cols.append(({r: -v for r, v in entries.items()}, -cost, None, (col, -1, Fraction(0))))
+    # classify rows, make b >= 0
+    groups = {"E": [], "R": [], "L": [], "G": []}
+    flip = {}
+    for r in rows:
+        lo, hi = interval[r]
+        if lo is not INF and hi is not INF and lo == hi:
+            flip[r] = lo < 0
+            groups["E"].append((r, -lo if flip[r] else lo, None))
+        elif lo is not INF and hi is not INF:
+            f = hi < 0
+            flip[r] = f
+            nlo, nhi = (-hi, -lo) if f else (lo, hi)
+            groups["R"].append((r, nhi, nhi - nlo))
+        elif hi is not INF:          # a x <= hi
+            f = hi < 0
+            flip[r] = f
+            groups["G" if f else "L"].append((r, -hi if f else hi, None))
+        else:                        # a x >= lo
+            f = lo < 0
+            flip[r] = f
+            groups["L" if f else "G"].append((r, -lo if f else lo, None))
+    order = groups["E"] + groups["R"] + groups["L"] + groups["G"]
+    row_index = {r: i for i, (r, _, _) in enumerate(order)}
+    lp.b = [b for _, b, _ in order]
+    lp.ranges = [rg for _, _, rg in groups["R"]]
+    lp.counts = (len(groups["E"]), len(groups["R"]), len(groups["L"]), len(groups["G"]))
+    for entries, cost, up, vm in new_cols:
+        col = sorted((row_index[r], (-v if flip[r] else v)) for r, v in entries.items())
+        lp.constraint_columns.append(col)
+        lp.costs.append(cost)
+        lp.upper.append(up)
+        lp.var_map.append(vm)
+    return lp
+
+
+def _lcm(a, b):
+    return a * b // gcd(a, b)
+
+
+class ScaledProblem:
+    """Integer image of a rational provider + the weights that keep the pivoting rules invariant.
+
+    rows are multiplied by r_i = lcm of the denominators in row i (coefficients and right-hand side);
+    single-entry +-1 columns of row i (slacks, bound slacks) and the artificial columns stay UNIT
+    columns, which is a column scaling by 1/r_i and is compensated by weights.
+    """
+
+    def __init__(self):
+        self.problem = None            # IntegerProblem
+        self.row_scale = []            # r_i
+        self.col_weight = []           # w_j (1 for structural columns, r_i for unit columns of row i)
+        self.cost_scale = 1            # integer costs = cost_scale * c_j / w_j
+        self.W = 1                     # lcm of all weights
+
+
+def prescale(m, n, columns, costs, rhs, pivots, full_initial_basis=False):
+    """columns: list of [(row, Fraction)], costs, rhs: Fractions."""
+    sp = ScaledProblem()
+    r = [1] * m
+    for j in range(n):
+        col = columns[j]
+        if len(col) == 1 and abs(col[0][1]) == 1:
+            continue                   # unit column: stays +-1, gets a weight instead
+        for i, v in col:
+            r[i] = _lcm(r[i], Fraction(v).denominator)
+    for i in range(m):
+        r[i] = _lcm(r[i], Fraction(rhs[i]).denominator)
+    w = [1] * n
+    int_cols = []
+    for j in range(n):
+        col = columns[j]
+        if len(col) == 1 and abs(col[0][1]) == 1:
+            w[j] = r[col[0][0]]
+            int_cols.append([(col[0][0], int(col[0][1]))])
+        else:
+            ic = []
+            for i, v in col:
+                x = Fraction(v) * r[i]
+                assert x.denominator == 1
+                ic.append((i, int(x)))
+            int_cols.append(ic)
+    W = 1
+    for x in w + r:
+        W = _lcm(W, x)
+    cs = 1
+    for j in range(n):
+        cs = _lcm(cs, (Fraction(costs[j]) / w[j]).denominator)
+    int_cost = [int(Fraction(costs[j]) * cs / w[j]) for j in range(n)]
+    int_rhs = [int(Fraction(rhs[i]) * r[i]) for i in range(m)]
+    prob = IntegerProblem.from_columns(m, int_cols, int_cost, int_rhs, pivots, full_initial_basis)
+    prob.col_weight = np.array(w, dtype=np.int64)
+    prob.row_scale = np.array(r, dtype=np.int64)
+    prob.W = W
+    prob.cost_scale = cs
+    if W >= 2 ** 31:
+        raise ValueError("weight lcm exceeds 2^31: rows need a coarser common scale")
+    sp.problem, sp.row_scale, sp.col_weight, sp.cost_scale, sp.W = prob, r, w, cs, W
+    return sp

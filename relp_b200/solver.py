@@ -39,6 +39,11 @@ class IntegerProblem:
         self.full_initial_basis = bool(full_initial_basis)
         if self.full_initial_basis:
             assert self.pivots is not None and len(self.pivots) == self.m
+        # weights of a prescaled rational problem (relp_b200.frontend.prescale); None = integer problem
+        self.col_weight = None     # w_j
+        self.row_scale = None      # r_i
+        self.W = 1                 # lcm of all weights
+        self.cost_scale = 1        # integer costs = cost_scale * c_j / w_j
 
     @classmethod
     def from_columns(cls, m, columns, cost, rhs, pivots=None, full_initial_basis=False):
@@ -78,6 +83,25 @@ class IntegerProblem:
             p.pivot_rows = rows.ctypes.data_as(C.POINTER(C.c_int32))
             p.pivot_cols = cols.ctypes.data_as(C.POINTER(C.c_int32))
         p.full_initial_basis = 1 if self.full_initial_basis else 0
+        if self.col_weight is not None:
+            from math import gcd
+            w = [int(x) for x in self.col_weight]
+            r = [int(x) for x in self.row_scale]
+            W = int(self.W)
+            real_rows = set(rc[0] for rc in self.pivots) if self.pivots is not None else set()
+            w1 = 1
+            for i in range(self.m):
+                if i not in real_rows:
+                    w1 = w1 * r[i] // gcd(w1, r[i])
+            colfac = np.array([W // x for x in w], dtype=np.int64)
+            artfac = np.array([W // x for x in r], dtype=np.int64)
+            colw = np.array(w, dtype=np.int64)
+            artcost = np.array([w1 // x for x in r], dtype=np.int64)
+            keep += [colfac, artfac, colw, artcost]
+            p.colfac = colfac.ctypes.data_as(C.POINTER(C.c_int64))
+            p.artfac = artfac.ctypes.data_as(C.POINTER(C.c_int64))
+            p.colw = colw.ctypes.data_as(C.POINTER(C.c_int64))
+            p.artcost = artcost.ctypes.data_as(C.POINTER(C.c_int64))
         return p, keep
 
 
@@ -150,7 +174,7 @@ def solve_relaxation(problem, rule="steepest_edge", fused=True, initial_limbs=0,
         dn = lib.rh_result_denominator(handle)
         D = limbs_to_int([dn[k] for k in range(L)])
         res.denominator = D
-        res.objective = Fraction(-limbs_to_int([mo[k] for k in range(L)]), D)
+        res.objective = Fraction(-limbs_to_int([mo[k] for k in range(L)]), D) / int(problem.cost_scale)
         bs = lib.rh_result_basis(handle)
         bw = lib.rh_result_b(handle)
         res.basis = [bs[i] for i in range(problem.m)]
@@ -158,7 +182,8 @@ def solve_relaxation(problem, rule="steepest_edge", fused=True, initial_limbs=0,
         for i in range(problem.m):
             v = limbs_to_int([bw[i * L + k] for k in range(L)])
             if v != 0 and res.basis[i] >= 0:
-                bfs.append((res.basis[i], Fraction(v, D)))
+                wj = 1 if problem.col_weight is None else int(problem.col_weight[res.basis[i]])
+                bfs.append((res.basis[i], Fraction(v, D) / wj))
         bfs.sort(key=lambda t: t[0])
         res.bfs = bfs
         res.nr_artificial = lib.rh_result_nr_artificial(handle)
