@@ -110,6 +110,9 @@ int rg_nccl_unique_id(void* out, int32_t bytes);
 /* All provider columns as integer CSC (column(j), :52), row indices ascending within a column.  */
 int rg_load_csc(rg_context* ctx, int32_t m, int32_t n, const int64_t* colptr,
                 const int32_t* rowidx, const int64_t* vals);
+/* Optional dense block: provider columns [0, nd) given as int8, column-major nd x m (implicit row indices;
+ * config 5).  Their CSC ranges in rg_load_csc must be empty.  Call right after rg_load_csc. */
+int rg_load_dense_i8(rg_context* ctx, int32_t nd, const int8_t* colmajor);
 /* right_hand_side() (:96); must be >= 0 (GeneralForm::make_b_non_negative guarantees it). */
 int rg_set_rhs(rg_context* ctx, const int64_t* b);
 

@@ -33,6 +33,10 @@ typedef struct rh_problem {
     const int64_t* artfac;        /* m */
     const int64_t* colw;          /* n */
     const int64_t* artcost;       /* m */
+    /* optional dense int8 block for provider columns [0, n_dense) (rg_load_dense_i8) */
+    int32_t n_dense;
+    int32_t reserved0;
+    const int8_t* dense;          /* column-major n_dense x m */
 } rh_problem;
 
 enum { RH_OPTIMAL = 0, RH_UNBOUNDED = 1, RH_INFEASIBLE = 2 };

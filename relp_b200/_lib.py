@@ -35,7 +35,8 @@ class rh_problem(C.Structure):
                 ("pivot_rows", C.POINTER(C.c_int32)), ("pivot_cols", C.POINTER(C.c_int32)),
                 ("full_initial_basis", C.c_int32),
                 ("colfac", C.POINTER(C.c_int64)), ("artfac", C.POINTER(C.c_int64)),
-                ("colw", C.POINTER(C.c_int64)), ("artcost", C.POINTER(C.c_int64))]
+                ("colw", C.POINTER(C.c_int64)), ("artcost", C.POINTER(C.c_int64)),
+                ("n_dense", C.c_int32), ("reserved0", C.c_int32), ("dense", C.POINTER(C.c_int8))]
 
 
 class rh_trace_entry(C.Structure):
@@ -59,6 +60,7 @@ SYMBOLS = {
     "rg_nccl_unique_id": (C.c_int, [C.c_void_p, C.c_int32]),
     "rg_load_csc": (C.c_int, [P, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int32),
                               C.POINTER(C.c_int64)]),
+    "rg_load_dense_i8": (C.c_int, [P, C.c_int32, C.POINTER(C.c_int8)]),
     "rg_set_rhs": (C.c_int, [P, C.POINTER(C.c_int64)]),
     "rg_set_weights": (C.c_int, [P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                  C.POINTER(C.c_int64)]),

@@ -100,6 +100,11 @@ struct rg_context {
     long long* artcost = nullptr; // m: phase-one cost numerator of the artificial of row i
     long long* rowf = nullptr;    // m: factor of the variable currently basic in row i
     rg::Csc A;
+    // optional dense int8 block holding provider columns [0, nd): row-major and column-major copies
+    int nd = 0;
+    signed char* Arm = nullptr; size_t ldr = 0;    // [m][ldr]
+    signed char* Acm = nullptr; size_t ldc = 0;    // [nd][ldc]
+    long long* dpart = nullptr; int dslices = 0;   // deferred-carry partial sums of the dense dots
     long long* cost = nullptr;  // n
     long long* rhs = nullptr;   // m
     int* basis = nullptr;       // m column ids

@@ -49,6 +49,7 @@ public:
         opts.nccl_unique_id = o.nccl_unique_id;
         check(nullptr, rg_create(&opts, &ctx), "rg_create");
         check(ctx, rg_load_csc(ctx, m, n, mp.p->colptr, mp.p->rowidx, mp.p->vals), "rg_load_csc");
+        if (mp.p->n_dense > 0) check(ctx, rg_load_dense_i8(ctx, mp.p->n_dense, mp.p->dense), "rg_load_dense_i8");
         check(ctx, rg_set_rhs(ctx, mp.p->rhs), "rg_set_rhs");
         if (mp.p->colfac)
             check(ctx, rg_set_weights(ctx, mp.p->colfac, mp.p->artfac, mp.p->colw, mp.p->artcost), "rg_set_weights");

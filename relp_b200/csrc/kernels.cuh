@@ -164,12 +164,12 @@ __global__ void k_sign_extend(u64* dst, size_t ps, size_t count, int Lold, int L
 // ---------------------------------------------------------------------------------------------
 template <int LV, int LO>
 __global__ void __launch_bounds__(256)
-k_coldot(const u64* __restrict__ vec, size_t vs, int n, const long long* __restrict__ colptr,
+k_coldot(const u64* __restrict__ vec, size_t vs, int n, int j0, const long long* __restrict__ colptr,
          const int* __restrict__ rowidx, const long long* __restrict__ vals,
          const unsigned char* __restrict__ inbasis, const long long* __restrict__ cost, int cmul,
          int LD, u64* __restrict__ out, const Scalars* __restrict__ sc) {
     if (sc->status != ST_RUN) return;
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    int j = j0 + blockIdx.x * blockDim.x + threadIdx.x;     // columns below j0 live in the dense block
     if (j >= n) return;
     u64 acc[LO];
 #pragma unroll
@@ -193,6 +193,181 @@ k_coldot(const u64* __restrict__ vec, size_t vs, int n, const long long* __restr
         }
     }
     store_planar<LO>(out, (size_t)n, (size_t)j, acc);
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Dense int8 column block (config 5: every coefficient stored, implicit row indices).
+// The block is kept twice: row-major (thread-per-column dots read it coalesced) and column-major
+// (the pivot column a_q is contiguous for FTRAN).  Products with an int8 coefficient never need
+// carries inside the loop: each 32-bit limb of the vector is multiplied into its own signed 64-bit
+// accumulator (|sum| <= m * 127 * 2^32 < 2^63 for m < 2^24) and the carries are resolved once.
+// ---------------------------------------------------------------------------------------------
+// stage 1: part[rs][k][j] = sum over the row slice of a_ij * limb32_k(vec[1+i])   (k < 2 LV)
+template <int LV>
+__global__ void __launch_bounds__(128)
+k_densedot1(const u64* __restrict__ vec, size_t vs, int m, int nd, const signed char* __restrict__ Arm,
+            size_t ldr, int rows_per_slice, long long* __restrict__ part, size_t pstride,
+            const unsigned char* __restrict__ inbasis, const Scalars* sc) {
+    constexpr int NV = 2 * LV;
+    constexpr int RB = 32;                         // rows staged per shared-memory tile
+    __shared__ u32 sv[RB][NV];
+    if (sc->status != ST_RUN) return;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = j < nd && !inbasis[j];
+    const int r0 = blockIdx.y * rows_per_slice;
+    const int r1 = min(m, r0 + rows_per_slice);
+    long long acc[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) acc[k] = 0;
+    for (int base = r0; base < r1; base += RB) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < RB * LV; t += blockDim.x) {
+            int r = t / LV, l = t % LV;
+            u64 v = (base + r < r1) ? vec[(size_t)l * vs + 1 + base + r] : 0;
+            sv[r][2 * l] = (u32)v; sv[r][2 * l + 1] = (u32)(v >> 32);
+        }
+        __syncthreads();
+        if (!active) continue;
+        const int rn = min(RB, r1 - base);
+        for (int r = 0; r < rn; ++r) {
+            long long a = Arm[(size_t)(base + r) * ldr + j];
+            if (a == 0) continue;
+#pragma unroll
+            for (int k = 0; k < NV - 1; ++k) acc[k] += a * (long long)(u64)sv[r][k];
+            acc[NV - 1] += a * (long long)(int)sv[r][NV - 1];     // top limb is signed
+        }
+    }
+    if (j < nd) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) part[(size_t)blockIdx.y * pstride + (size_t)k * nd + j] = acc[k];
+    }
+}
+// stage 2: sum the slices, resolve the deferred carries, add cmul * cost_j * D, store LO limbs
+template <int LV, int LO>
+__global__ void __launch_bounds__(128)
+k_densedot2(const long long* __restrict__ part, size_t pstride, int slices, int nd, int n,
+            const unsigned char* __restrict__ inbasis, const long long* __restrict__ cost, int cmul, int LD,
+            u64* __restrict__ out, const Scalars* sc) {
+    constexpr int NV = 2 * LV;
+    if (sc->status != ST_RUN) return;
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nd) return;
+    u64 res[LO];
+#pragma unroll
+    for (int l = 0; l < LO; ++l) res[l] = 0;
+    if (!inbasis[j]) {
+        // value = sum_k acc_k 2^(32k), acc_k signed: propagate with arithmetic shifts
+        long long carry = 0;
+        u32 limbs[2 * LO];
+#pragma unroll
+        for (int k = 0; k < 2 * LO; ++k) {
+            long long a = carry;
+            if (k < NV) for (int s = 0; s < slices; ++s) a += part[(size_t)s * pstride + (size_t)k * nd + j];
+            limbs[k] = (u32)a;
+            carry = a >> 32;                        // arithmetic: keeps the sign
+        }
+#pragma unroll
+        for (int l = 0; l < LO; ++l) res[l] = (u64)limbs[2 * l] | ((u64)limbs[2 * l + 1] << 32);
+        if (cmul) {
+            long long c = cost[j];
+            if (c) {
+                u64 d[LO];
+#pragma unroll
+                for (int l = 0; l < LO; ++l) d[l] = l < LD ? sc->D[l] : 0;
+                mac_small<LO, LO>(res, d, c);
+            }
+        }
+    }
+    store_planar<LO>(out, (size_t)n, (size_t)j, res);
+}
+
+// column-major [nd][ldc] -> row-major [m][ldr]
+__global__ void k_transpose_i8(const signed char* __restrict__ Acm, size_t ldc, signed char* __restrict__ Arm,
+                               size_t ldr, int m, int nd) {
+    __shared__ signed char tile[32][33];
+    int j = blockIdx.x * 32 + threadIdx.y, i = blockIdx.y * 32 + threadIdx.x;
+    tile[threadIdx.y][threadIdx.x] = (j < nd && i < m) ? Acm[(size_t)j * ldc + i] : 0;
+    __syncthreads();
+    int jo = blockIdx.x * 32 + threadIdx.x, io = blockIdx.y * 32 + threadIdx.y;
+    if (jo < nd && io < m) Arm[(size_t)io * ldr + jo] = tile[threadIdx.x][threadIdx.y];
+}
+
+// FTRAN of a dense column q (column-major copy): warp per carry row, lanes over the rows of a_q
+template <int L>
+__global__ void __launch_bounds__(256)
+k_ftran_dense(const u64* __restrict__ C, size_t ps, int ld, int nrows, int m, const signed char* __restrict__ Acm,
+              size_t ldc, const long long* __restrict__ cost, int qarg, int nd, u64* __restrict__ u, size_t us,
+              Scalars* sc) {
+    constexpr int LU = L + 2, NV = 2 * L;
+    if (sc->status != ST_RUN) return;
+    int q = qarg >= 0 ? qarg : sc->q;
+    if (q >= nd) return;                      // sparse column: k_ftran handles it
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (warp >= nrows) return;
+    size_t row = (size_t)warp * ld;
+    const signed char* aq = Acm + (size_t)q * ldc;
+    long long acc[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) acc[k] = 0;
+    for (int k = lane; k < m; k += 32) {
+        long long a = aq[k];
+        u64 x[L];
+        load_planar<L>(x, C, ps, row + 1 + k);
+        u64 any = 0;
+#pragma unroll
+        for (int l = 0; l < L; ++l) any |= x[l];
+        if (a == 0 || any == 0) continue;
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+            acc[2 * l] += a * (long long)(x[l] & 0xffffffffull);
+            if (l < L - 1) acc[2 * l + 1] += a * (long long)(x[l] >> 32);
+            else acc[2 * l + 1] += a * (long long)(int)(x[l] >> 32);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int k = 0; k < NV; ++k) acc[k] += __shfl_down_sync(0xffffffffu, acc[k], o);
+    if (lane == 0) {
+        u64 res[LU];
+        long long carry = 0;
+        u32 limbs[2 * LU];
+#pragma unroll
+        for (int k = 0; k < 2 * LU; ++k) {
+            long long a = carry + (k < NV ? acc[k] : 0);
+            limbs[k] = (u32)a;
+            carry = a >> 32;
+        }
+#pragma unroll
+        for (int l = 0; l < LU; ++l) res[l] = (u64)limbs[2 * l] | ((u64)limbs[2 * l + 1] << 32);
+        if (warp == 0) {
+            long long c = cost[q];
+            if (c) {
+                u64 d[L];
+#pragma unroll
+                for (int l = 0; l < L; ++l) d[l] = sc->D[l];
+                mac_small<LU, L>(res, d, c);
+            }
+        }
+        store_planar<LU>(u, us, (size_t)warp, res);
+        atomicMax(&sc->maxbits_u, bitlen_signed<LU>(res));
+    }
+}
+
+// steepest-edge weights of the dense columns on an identity carry: Ghat_j = (W/w_j)^2 + sum_i a_ij^2
+__global__ void k_gamma_init_identity_dense(int nd, int n, int m, const signed char* __restrict__ Arm,
+                                            size_t ldr, const unsigned char* __restrict__ inbasis,
+                                            u64* __restrict__ G, int LG) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nd) return;
+    u64 acc = 0;
+    if (!inbasis[j]) {
+        acc = 1;
+        for (int i = 0; i < m; ++i) { long long a = Arm[(size_t)i * ldr + j]; acc += (u64)(a * a); }
+    }
+    for (int l = 0; l < LG; ++l) G[(size_t)l * n + j] = l == 0 ? acc : 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -552,10 +727,11 @@ template <int L>
 __global__ void __launch_bounds__(256)
 k_ftran(const u64* __restrict__ C, size_t ps, int ld, int nrows, const long long* __restrict__ colptr,
         const int* __restrict__ rowidx, const long long* __restrict__ vals,
-        const long long* __restrict__ cost, int qarg, u64* __restrict__ u, size_t us, Scalars* sc) {
+        const long long* __restrict__ cost, int qarg, int nd, u64* __restrict__ u, size_t us, Scalars* sc) {
     constexpr int LU = L + 2;
     if (sc->status != ST_RUN) return;
     int q = qarg >= 0 ? qarg : sc->q;
+    if (q < nd) return;                       // dense column: k_ftran_dense handles it
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (warp >= nrows) return;
@@ -1165,10 +1341,10 @@ __global__ void k_reset_tmpbits(Scalars* sc) {
 //   init (general carry):   Ghat_j = D^2 + sum_i (C[i][1..m] . a_j)^2  block per column
 //   update: Ghat'_j = [a^2 Ghat_j - 2 a nu_j sigma_j + nu_j^2 Ghat_q] / D^2   (after_basis_update :243-296)
 // ---------------------------------------------------------------------------------------------
-__global__ void k_gamma_init_identity(int n, const long long* colptr, const int* rowidx, const long long* vals,
+__global__ void k_gamma_init_identity(int n, int j0, const long long* colptr, const int* rowidx, const long long* vals,
                                       const unsigned char* inbasis, const long long* wf, const long long* rowf,
                                       u64* G, int LG) {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    int j = j0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     u64 acc[6] = {0, 0, 0, 0, 0, 0};
     if (!inbasis[j]) {

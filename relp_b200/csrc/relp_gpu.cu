@@ -115,6 +115,8 @@ static int alloc_width_buffers(rg_context* ctx, int L) {
     CK(dev_alloc(&ctx->omega_part, sizeof(u64) * ctx->work_chunks * LW_of(L) * ld, ctx->stream));
     CK(dev_alloc(&ctx->tmprow, sizeof(u64) * LU_of(L) * ld, ctx->stream));
     CK(dev_alloc(&ctx->us2, sizeof(u64) * (LU_of(L) + 1) * ld, ctx->stream));
+    if (ctx->nd > 0)
+        CK(dev_alloc(&ctx->dpart, sizeof(long long) * ctx->dslices * 2 * LW_of(L) * ctx->nd, ctx->stream));
     CK(dev_alloc(&ctx->kappa, sizeof(u64) * LU_of(L) * n, ctx->stream));
     CK(dev_alloc(&ctx->nu, sizeof(u64) * LU_of(L) * n, ctx->stream));
     CK(dev_alloc(&ctx->sigma, sizeof(u64) * LS_of(L) * n, ctx->stream));
@@ -125,8 +127,8 @@ static int alloc_width_buffers(rg_context* ctx, int L) {
 }
 static void free_width_buffers(rg_context* ctx) {
     free_dev_on(ctx->u, ctx->stream); free_dev_on(ctx->rowp, ctx->stream); free_dev_on(ctx->omega, ctx->stream); free_dev_on(ctx->omega_part, ctx->stream);
-    free_dev_on(ctx->tmprow, ctx->stream); free_dev_on(ctx->us2, ctx->stream); free_dev_on(ctx->kappa, ctx->stream); free_dev_on(ctx->nu, ctx->stream); free_dev_on(ctx->sigma, ctx->stream);
-    ctx->u = ctx->rowp = ctx->omega = ctx->omega_part = ctx->tmprow = ctx->us2 = nullptr;
+    free_dev_on(ctx->tmprow, ctx->stream); free_dev_on(ctx->us2, ctx->stream); free_dev_on(ctx->dpart, ctx->stream); free_dev_on(ctx->kappa, ctx->stream); free_dev_on(ctx->nu, ctx->stream); free_dev_on(ctx->sigma, ctx->stream);
+    ctx->u = ctx->rowp = ctx->omega = ctx->omega_part = ctx->tmprow = ctx->us2 = nullptr; ctx->dpart = nullptr;
     ctx->kappa = ctx->nu = ctx->sigma = nullptr;
 }
 
@@ -201,6 +203,7 @@ extern "C" int rg_destroy(rg_context* ctx) {
     free_dev_on(ctx->cost, ctx->stream); free_dev_on(ctx->rhs, ctx->stream); free_dev_on(ctx->basis, ctx->stream); free_dev_on(ctx->inbasis, ctx->stream);
     free_dev_on(ctx->G, ctx->stream); free_dev_on(ctx->cand, ctx->stream); free_dev_on(ctx->score, ctx->stream); free_dev_on(ctx->sc, ctx->stream); free_dev_on(ctx->svec, ctx->stream);
     free_dev_on(ctx->xsend, ctx->stream); free_dev_on(ctx->xrecv, ctx->stream);
+    free_dev_on(ctx->Arm, ctx->stream); free_dev_on(ctx->Acm, ctx->stream);
     free_dev_on(ctx->wf, ctx->stream); free_dev_on(ctx->wcol, ctx->stream); free_dev_on(ctx->artf, ctx->stream);
     free_dev_on(ctx->artcost, ctx->stream); free_dev_on(ctx->rowf, ctx->stream);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
@@ -271,6 +274,29 @@ extern "C" int rg_set_rhs(rg_context* ctx, const int64_t* b) {
     return RG_OK;
 }
 
+extern "C" int rg_load_dense_i8(rg_context* ctx, int32_t nd, const int8_t* colmajor) {
+    if (!ctx || !ctx->carry || nd <= 0 || nd > ctx->n || !colmajor) return RG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->nd) { ctx->err = "rg_load_dense_i8: dense block already loaded"; return RG_ERR_STATE; }
+    const int m = ctx->m;
+    ctx->ldc = ((size_t)m + 15) / 16 * 16;
+    ctx->ldr = ((size_t)nd + 15) / 16 * 16;
+    CK(dev_alloc(&ctx->Acm, ctx->ldc * nd, ctx->stream));
+    CK(dev_alloc(&ctx->Arm, ctx->ldr * m, ctx->stream));
+    CK(cudaMemsetAsync(ctx->Acm, 0, ctx->ldc * nd, ctx->stream));
+    CK(cudaMemsetAsync(ctx->Arm, 0, ctx->ldr * m, ctx->stream));
+    CK(cudaMemcpy2DAsync(ctx->Acm, ctx->ldc, colmajor, (size_t)m, (size_t)m, (size_t)nd, cudaMemcpyHostToDevice,
+                         ctx->stream));
+    dim3 grid(cdiv(nd, 32), cdiv(m, 32)), block(32, 32);
+    k_transpose_i8<<<grid, block, 0, ctx->stream>>>(ctx->Acm, ctx->ldc, ctx->Arm, ctx->ldr, m, nd);
+    ctx->launches++;
+    ctx->nd = nd;
+    ctx->dslices = 4;
+    CK(dev_alloc(&ctx->dpart, sizeof(long long) * ctx->dslices * 2 * LW_of(ctx->L) * nd, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return RG_OK;
+}
+
 extern "C" int rg_set_weights(rg_context* ctx, const int64_t* colfac, const int64_t* artfac,
                               const int64_t* colw, const int64_t* artcost) {
     if (!ctx || !ctx->carry || !colfac || !artfac || !colw || !artcost) return RG_ERR_ARG;
@@ -307,6 +333,7 @@ static int ensure_xbuf(rg_context* ctx, size_t send_words, size_t recv_words) {
     if (need <= ctx->xbytes) return RG_OK;
     CK(cudaStreamSynchronize(ctx->stream));
     free_dev_on(ctx->xsend, ctx->stream); free_dev_on(ctx->xrecv, ctx->stream);
+    free_dev_on(ctx->Arm, ctx->stream); free_dev_on(ctx->Acm, ctx->stream);
     free_dev_on(ctx->wf, ctx->stream); free_dev_on(ctx->wcol, ctx->stream); free_dev_on(ctx->artf, ctx->stream);
     free_dev_on(ctx->artcost, ctx->stream); free_dev_on(ctx->rowf, ctx->stream);
     CK(dev_alloc(&ctx->xsend, need, ctx->stream));
@@ -342,11 +369,25 @@ static int sync_mirror(rg_context* ctx) {
 
 static void set_status(rg_context* ctx, int st) { LAUNCH(k_set_status, 1, 1, ctx->sc, st); }
 
+// out_j = cmul cost_j D + vec[1..m] . a_j for every provider column: dense block + CSC remainder
+template <int LV, int LO>
+static void launch_coldots(rg_context* ctx, const u64* vec, size_t vs, int cmul, u64* out) {
+    if (ctx->nd > 0) {
+        int rps = cdiv(ctx->m, ctx->dslices);
+        size_t pstride = (size_t)2 * LV * ctx->nd;
+        dim3 grid(cdiv(ctx->nd, 128), ctx->dslices);
+        LAUNCH((k_densedot1<LV>), grid, 128, vec, vs, ctx->m, ctx->nd, ctx->Arm, ctx->ldr, rps, ctx->dpart,
+               pstride, ctx->inbasis, ctx->sc);
+        LAUNCH((k_densedot2<LV, LO>), cdiv(ctx->nd, 128), 128, ctx->dpart, pstride, ctx->dslices, ctx->nd, ctx->n,
+               ctx->inbasis, ctx->cost, cmul, ctx->L, out, ctx->sc);
+    }
+    if (ctx->n > ctx->nd)
+        LAUNCH((k_coldot<LV, LO>), cdiv(ctx->n - ctx->nd, 256), 256, vec, vs, ctx->n, ctx->nd, ctx->A.colptr,
+               ctx->A.rowidx, ctx->A.vals, ctx->inbasis, ctx->cost, cmul, ctx->L, out, ctx->sc);
+}
 template <int L>
 static void launch_price_t(rg_context* ctx) {
-    constexpr int LU = L + 2;
-    LAUNCH((k_coldot<L, LU>), cdiv(ctx->n, 256), 256, ctx->carry, ctx->plane, ctx->n, ctx->A.colptr,
-           ctx->A.rowidx, ctx->A.vals, ctx->inbasis, ctx->cost, 1, L, ctx->kappa, ctx->sc);
+    launch_coldots<L, L + 2>(ctx, ctx->carry, ctx->plane, 1, ctx->kappa);
 }
 static void launch_price(rg_context* ctx) { DISPATCH_L(ctx->L, launch_price_t, ctx); }
 
@@ -380,8 +421,12 @@ static void launch_select(rg_context* ctx) {
 template <int L>
 static void launch_ftran_t(rg_context* ctx, int q) {
     LAUNCH((k_ftran<L>), cdiv((long long)(ctx->nloc + 1) * 32, 256), 256, ctx->carry, ctx->plane, ctx->ld,
-           ctx->nloc + 1, ctx->A.colptr, ctx->A.rowidx, ctx->A.vals, ctx->cost, q, ctx->u, (size_t)ctx->ld,
-           ctx->sc);
+           ctx->nloc + 1, ctx->A.colptr, ctx->A.rowidx, ctx->A.vals, ctx->cost, q, ctx->nd, ctx->u,
+           (size_t)ctx->ld, ctx->sc);
+    if (ctx->nd > 0)
+        LAUNCH((k_ftran_dense<L>), cdiv((long long)(ctx->nloc + 1) * 32, 256), 256, ctx->carry, ctx->plane,
+               ctx->ld, ctx->nloc + 1, ctx->m, ctx->Acm, ctx->ldc, ctx->cost, q, ctx->nd, ctx->u,
+               (size_t)ctx->ld, ctx->sc);
 }
 static void launch_ftran(rg_context* ctx, int q) { DISPATCH_L(ctx->L, launch_ftran_t, ctx, q); }
 
@@ -500,10 +545,8 @@ static void launch_update(rg_context* ctx, int E) { DISPATCH_L(ctx->L, launch_up
 template <int L>
 static void launch_se_dots_t(rg_context* ctx) {
     constexpr int LU = L + 2, LW = LW_of(L), LS = LS_of(L);
-    LAUNCH((k_coldot<L, LU>), cdiv(ctx->n, 256), 256, ctx->rowp, (size_t)ctx->ld, ctx->n, ctx->A.colptr,
-           ctx->A.rowidx, ctx->A.vals, ctx->inbasis, ctx->cost, 0, L, ctx->nu, ctx->sc);
-    LAUNCH((k_coldot<LW, LS>), cdiv(ctx->n, 256), 256, ctx->omega, (size_t)ctx->ld, ctx->n, ctx->A.colptr,
-           ctx->A.rowidx, ctx->A.vals, ctx->inbasis, ctx->cost, 0, L, ctx->sigma, ctx->sc);
+    launch_coldots<L, LU>(ctx, ctx->rowp, (size_t)ctx->ld, 0, ctx->nu);
+    launch_coldots<LW, LS>(ctx, ctx->omega, (size_t)ctx->ld, 0, ctx->sigma);
 }
 template <int L>
 static void launch_gamma_update_t(rg_context* ctx) {
@@ -528,9 +571,7 @@ static void launch_se_update(rg_context* ctx) {
 
 template <int L>
 static void launch_rowdot_t(rg_context* ctx) {   // nu_j = rowp . a_j
-    constexpr int LU = L + 2;
-    LAUNCH((k_coldot<L, LU>), cdiv(ctx->n, 256), 256, ctx->rowp, (size_t)ctx->ld, ctx->n, ctx->A.colptr,
-           ctx->A.rowidx, ctx->A.vals, ctx->inbasis, ctx->cost, 0, L, ctx->nu, ctx->sc);
+    launch_coldots<L, L + 2>(ctx, ctx->rowp, (size_t)ctx->ld, 0, ctx->nu);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -785,10 +826,15 @@ extern "C" int rg_rule_new(rg_context* ctx, int32_t rule) {
     LAUNCH(k_set_pq, 1, 1, ctx->sc, -1, -1);
     if (rule == RG_RULE_STEEPEST_EDGE) {
         if (ctx->identity_carry) {
-            LAUNCH(k_gamma_init_identity, cdiv(ctx->n, 256), 256, ctx->n, ctx->A.colptr, ctx->A.rowidx,
-                   ctx->A.vals, ctx->inbasis, ctx->weighted ? ctx->wf : nullptr,
-                   ctx->weighted ? ctx->rowf : nullptr, ctx->G, LG_of(ctx->L));
+            if (ctx->nd > 0)
+                LAUNCH(k_gamma_init_identity_dense, cdiv(ctx->nd, 128), 128, ctx->nd, ctx->n, ctx->m, ctx->Arm,
+                       ctx->ldr, ctx->inbasis, ctx->G, LG_of(ctx->L));
+            if (ctx->n > ctx->nd)
+                LAUNCH(k_gamma_init_identity, cdiv(ctx->n - ctx->nd, 256), 256, ctx->n, ctx->nd, ctx->A.colptr,
+                       ctx->A.rowidx, ctx->A.vals, ctx->inbasis, ctx->weighted ? ctx->wf : nullptr,
+                       ctx->weighted ? ctx->rowf : nullptr, ctx->G, LG_of(ctx->L));
         } else {
+            if (ctx->nd > 0) { ctx->err = "steepest-edge initialisation on a general basis is not implemented for the dense block"; return RG_ERR_STATE; }
             RG_TRY(launch_gamma_general(ctx));
         }
     }

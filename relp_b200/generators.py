@@ -10,7 +10,7 @@ from .solver import IntegerProblem
 
 
 def bounded_lp(m, n_struct, k_bounding=90, nnz_per_col=8, dense=False, seed=0, b_big=None,
-               coupling=1, full_initial_basis=True):
+               coupling=1, full_initial_basis=True, dense_block=None):
     """Bounded integer LP  min c x, A x <= b, x >= 0  with b > 0 (slack basis feasible).
 
     Rows 0..K-1 are 'bounding rows': structural column j carries an entry in {1..100} in its group
@@ -29,6 +29,8 @@ def bounded_lp(m, n_struct, k_bounding=90, nnz_per_col=8, dense=False, seed=0, b
     rest = m - K
     if b_big is None:
         b_big = 10 ** 11 if dense else 10 ** 7
+    if dense_block is None:
+        dense_block = dense and m * n_struct > 2 ** 22    # large dense problems: 1 byte per coefficient
     # bounding block: (1 + coupling) candidate entries per column, duplicates collapse
     grp = (np.arange(n_struct, dtype=np.int64) % K)[:, None]
     others = rng.integers(0, K, size=(n_struct, coupling), dtype=np.int64)
@@ -39,6 +41,28 @@ def bounded_lp(m, n_struct, k_bounding=90, nnz_per_col=8, dense=False, seed=0, b
     top_vals = np.take_along_axis(top_vals, order, axis=1)
     dup = np.zeros_like(top_rows, dtype=bool)
     dup[:, 1:] = top_rows[:, 1:] == top_rows[:, :-1]
+    if dense and dense_block:
+        # structural columns as a dense int8 block (column-major), slacks + costs + rhs as usual
+        block = np.zeros((n_struct, m), dtype=np.int8)
+        block[:, K:] = rng.integers(-100, 101, size=(n_struct, rest), dtype=np.int8)
+        rows_i = np.arange(n_struct)[:, None]
+        # later duplicates overwrite earlier ones exactly like the CSC path keeps the first: write in
+        # reverse column order of the sorted pairs so the first occurrence wins
+        for c in range(top_rows.shape[1] - 1, -1, -1):
+            sel = ~dup[:, c]
+            block[rows_i[sel, 0], top_rows[sel, c]] = top_vals[sel, c].astype(np.int8)
+        n = n_struct + m
+        colptr = np.concatenate([np.zeros(n_struct + 1, dtype=np.int64), np.arange(1, m + 1, dtype=np.int64)])
+        rowidx = np.arange(m, dtype=np.int32)
+        vals = np.ones(m, dtype=np.int64)
+        cost = np.concatenate([-rng.integers(1, 101, size=n_struct, dtype=np.int64),
+                               np.zeros(m, dtype=np.int64)])
+        rhs = np.concatenate([rng.integers(1000, 10001, size=K, dtype=np.int64),
+                              np.full(rest, b_big, dtype=np.int64)])
+        pivots = [(i, n_struct + i) for i in range(m)]
+        prob = IntegerProblem(m, n, colptr, rowidx, vals, cost, rhs, pivots, full_initial_basis)
+        prob.set_dense_block(block)
+        return prob
     if dense:
         low_rows = np.tile(np.arange(K, m, dtype=np.int64), (n_struct, 1))
         low_vals = rng.integers(-100, 101, size=(n_struct, rest), dtype=np.int8).astype(np.int64)

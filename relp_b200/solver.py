@@ -44,6 +44,9 @@ class IntegerProblem:
         self.row_scale = None      # r_i
         self.W = 1                 # lcm of all weights
         self.cost_scale = 1        # integer costs = cost_scale * c_j / w_j
+        # optional dense int8 block: columns [0, n_dense) stored column-major (n_dense, m); their CSC
+        # ranges are empty (config 5: implicit row indices, 1 byte per coefficient)
+        self.dense_block = None
 
     @classmethod
     def from_columns(cls, m, columns, cost, rhs, pivots=None, full_initial_basis=False):
@@ -58,7 +61,16 @@ class IntegerProblem:
         return cls(m, len(columns), colptr, np.array(rowidx, dtype=np.int32),
                    np.array(vals, dtype=np.int64), cost, rhs, pivots, full_initial_basis)
 
+    def set_dense_block(self, block):
+        block = np.ascontiguousarray(block, dtype=np.int8)
+        assert block.ndim == 2 and block.shape[1] == self.m and block.shape[0] <= self.n
+        assert int(self.colptr[block.shape[0]]) == 0, "CSC ranges of the dense columns must be empty"
+        self.dense_block = block
+
     def column(self, j):
+        if self.dense_block is not None and j < self.dense_block.shape[0]:
+            col = self.dense_block[j]
+            return [(int(i), int(col[i])) for i in np.nonzero(col)[0]]
         a, b = int(self.colptr[j]), int(self.colptr[j + 1])
         return [(int(self.rowidx[k]), int(self.vals[k])) for k in range(a, b)]
 
@@ -83,6 +95,10 @@ class IntegerProblem:
             p.pivot_rows = rows.ctypes.data_as(C.POINTER(C.c_int32))
             p.pivot_cols = cols.ctypes.data_as(C.POINTER(C.c_int32))
         p.full_initial_basis = 1 if self.full_initial_basis else 0
+        if self.dense_block is not None:
+            keep.append(self.dense_block)
+            p.n_dense = self.dense_block.shape[0]
+            p.dense = self.dense_block.ctypes.data_as(C.POINTER(C.c_int8))
         if self.col_weight is not None:
             from math import gcd
             w = [int(x) for x in self.col_weight]

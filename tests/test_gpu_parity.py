@@ -173,3 +173,29 @@ def test_row_sharded_two_gpus():
                         os.path.join(root, "scripts", "mgpu_check.py")], capture_output=True, text=True,
                        timeout=900, cwd=root)
     assert r.returncode == 0 and "MGPU PARITY OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_max_flow_300_against_fast_oracle():
+    """Config 3 at a size the C++ oracle solves in a fraction of a second (m = 1494, phase one with
+    ~300 artificial rows, zero-level pivots)."""
+    import relp_b200
+    from oracle import fast_oracle as fo
+    from relp_b200.generators import max_flow
+    prob = max_flow(300, 4, 0)
+    ref = fo.solve_problem(prob, "steepest_edge")
+    g = relp_b200.solve_relaxation(prob, rule="steepest_edge")
+    assert g.status == ref.status == "optimal"
+    assert g.trace == ref.trace
+    assert g.objective == ref.objective and g.bfs == ref.bfs
+    assert g.stats["limbs"] == 2 and g.denominator == 1      # totally unimodular: D stays 1
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_dense_int8_block_matches_csc_and_oracle(seed):
+    """Config 5 data path at oracle size: structural columns as a dense int8 block (implicit indices)."""
+    from relp_b200.generators import bounded_lp
+    prob = bounded_lp(48, 64, k_bounding=14, dense=True, seed=seed, dense_block=True)
+    assert prob.dense_block is not None
+    for limbs in (1, 2):
+        check(problem=prob, rules=["steepest_edge", "dantzig", "first_profitable"], modes=(True, False),
+              initial_limbs=limbs)
