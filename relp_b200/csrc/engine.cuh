@@ -38,7 +38,7 @@ struct Scalars {
     u64 D[RG_MAXL];          // current denominator (positive)
     u64 a[RG_MAXL + 2];      // pivot element numerator u[p] (replicated on every rank)
     u64 Dnew[RG_MAXL];       // |a|: denominator after the pivot
-    u64 Dinv[2 * RG_MAXL + 2];   // inverse of odd(D) mod 2^(64 (L+E)), E <= L
+    u64 Dinv[2 * RG_MAXL + 2];   // inverse of odd(D) mod 2^(64 (L+E)), E <= L (+2 spare)
     u64 A[2 * RG_MAXL + 2];      // |a| * Dinv mod 2^(64 (L+E))
     u64 up[2 * RG_MAXL + 2];     // replacement for u[p]: a - D (makes the pivot row uniform)
     u64 Gq[RG_MAXW];         // steepest edge: Ghat of the entering column
@@ -104,7 +104,8 @@ struct rg_context {
     int nd = 0;
     signed char* Arm = nullptr; size_t ldr = 0;    // [m][ldr]
     signed char* Acm = nullptr; size_t ldc = 0;    // [nd][ldc]
-    long long* dpart = nullptr; int dslices = 0;   // deferred-carry partial sums of the dense dots
+    unsigned long long* dpart = nullptr; int dslices = 0;   // deferred-carry partial sums of the dense dots
+    unsigned long long* dsum = nullptr;            // limb sums of the vector (bias removal)
     long long* cost = nullptr;  // n
     long long* rhs = nullptr;   // m
     int* basis = nullptr;       // m column ids

@@ -203,52 +203,101 @@ k_coldot(const u64* __restrict__ vec, size_t vs, int n, int j0, const long long*
 // carries inside the loop: each 32-bit limb of the vector is multiplied into its own signed 64-bit
 // accumulator (|sum| <= m * 127 * 2^32 < 2^63 for m < 2^24) and the carries are resolved once.
 // ---------------------------------------------------------------------------------------------
-// stage 1: part[rs][k][j] = sum over the row slice of a_ij * limb32_k(vec[1+i])   (k < 2 LV)
+// The int8 coefficient is biased to a' = a + 128 in [0, 255] so that every product is an unsigned
+// 32 x 32 -> 64 multiply-add (one IMAD.WIDE.U32); the bias is removed with the limb sums S_k of the
+// vector (k_vecsum) and the sign of each vector entry rides along as one extra "sign extension" limb.
+//
+// limb sums of vec[1..m]: S[k] = sum_i limb32_k(vec[1+i]) for k < 2 LV, S[2 LV] = sum_i signword_i
+template <int LV>
+__global__ void __launch_bounds__(256) k_vecsum(const u64* __restrict__ vec, size_t vs, int m,
+                                                unsigned long long* __restrict__ S, const Scalars* sc) {
+    constexpr int NV = 2 * LV;
+    __shared__ unsigned long long red[256];
+    if (sc->status != ST_RUN) return;
+    {
+        const int k = blockIdx.x;                  // one block per limb position (NV + 1 blocks)
+        unsigned long long acc = 0;
+        for (int i = threadIdx.x; i < m; i += blockDim.x) {
+            if (k < NV) {
+                u64 v = vec[(size_t)(k >> 1) * vs + 1 + i];
+                acc += (k & 1) ? (v >> 32) : (v & 0xffffffffull);
+            } else {
+                acc += ((i64)vec[(size_t)(LV - 1) * vs + 1 + i] < 0) ? 0xffffffffull : 0ull;
+            }
+        }
+        red[threadIdx.x] = acc;
+        __syncthreads();
+        for (int s2 = 128; s2 > 0; s2 >>= 1) {
+            if (threadIdx.x < s2) red[threadIdx.x] += red[threadIdx.x + s2];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) S[k] = red[0];
+    }
+}
+// stage 1: part[rs][k][j] = sum over the row slice of (a_ij + 128) * limb32_k(vec[1+i])  (k <= 2 LV)
 template <int LV>
 __global__ void __launch_bounds__(128)
 k_densedot1(const u64* __restrict__ vec, size_t vs, int m, int nd, const signed char* __restrict__ Arm,
-            size_t ldr, int rows_per_slice, long long* __restrict__ part, size_t pstride,
+            size_t ldr, int rows_per_slice, unsigned long long* __restrict__ part, size_t pstride,
             const unsigned char* __restrict__ inbasis, const Scalars* sc) {
     constexpr int NV = 2 * LV;
+    constexpr int NW = (NV + 1 + 3) / 4 * 4;       // words per staged row, padded to 16 bytes
     constexpr int RB = 32;                         // rows staged per shared-memory tile
-    __shared__ u32 sv[RB][NV];
+    __shared__ __align__(16) u32 sv[RB][NW];
     if (sc->status != ST_RUN) return;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = j < nd && !inbasis[j];
     const int r0 = blockIdx.y * rows_per_slice;
     const int r1 = min(m, r0 + rows_per_slice);
-    long long acc[NV];
+    unsigned long long acc[NV + 1];
 #pragma unroll
-    for (int k = 0; k < NV; ++k) acc[k] = 0;
+    for (int k = 0; k <= NV; ++k) acc[k] = 0;
     for (int base = r0; base < r1; base += RB) {
         __syncthreads();
-        for (int t = threadIdx.x; t < RB * LV; t += blockDim.x) {
-            int r = t / LV, l = t % LV;
-            u64 v = (base + r < r1) ? vec[(size_t)l * vs + 1 + base + r] : 0;
-            sv[r][2 * l] = (u32)v; sv[r][2 * l + 1] = (u32)(v >> 32);
+        for (int t = threadIdx.x; t < RB * (LV + 1); t += blockDim.x) {
+            int r = t / (LV + 1), l = t % (LV + 1);
+            bool in = base + r < r1;
+            if (l < LV) {
+                u64 v = in ? vec[(size_t)l * vs + 1 + base + r] : 0;
+                sv[r][2 * l] = (u32)v; sv[r][2 * l + 1] = (u32)(v >> 32);
+            } else {
+                u64 top = in ? vec[(size_t)(LV - 1) * vs + 1 + base + r] : 0;
+                sv[r][NV] = (i64)top < 0 ? 0xffffffffu : 0u;
+            }
         }
         __syncthreads();
         if (!active) continue;
-        const int rn = min(RB, r1 - base);
-        for (int r = 0; r < rn; ++r) {
-            long long a = Arm[(size_t)(base + r) * ldr + j];
-            if (a == 0) continue;
+        // all coefficient loads of the tile are issued before any use (one memory latency per tile);
+        // rows past the slice end hold zero vector limbs, so their (biased) coefficient is harmless
+        u32 av[RB];
 #pragma unroll
-            for (int k = 0; k < NV - 1; ++k) acc[k] += a * (long long)(u64)sv[r][k];
-            acc[NV - 1] += a * (long long)(int)sv[r][NV - 1];     // top limb is signed
+        for (int r = 0; r < RB; ++r)
+            av[r] = (base + r < r1) ? (u32)((int)Arm[(size_t)(base + r) * ldr + j] + 128) : 128u;
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+            const u32 a = av[r];
+            const uint4* row4 = reinterpret_cast<const uint4*>(sv[r]);
+#pragma unroll
+            for (int g = 0; g < NW / 4; ++g) {
+                uint4 x = row4[g];
+                if (4 * g + 0 <= NV) acc[4 * g + 0] += (unsigned long long)a * x.x;
+                if (4 * g + 1 <= NV) acc[4 * g + 1] += (unsigned long long)a * x.y;
+                if (4 * g + 2 <= NV) acc[4 * g + 2] += (unsigned long long)a * x.z;
+                if (4 * g + 3 <= NV) acc[4 * g + 3] += (unsigned long long)a * x.w;
+            }
         }
     }
     if (j < nd) {
 #pragma unroll
-        for (int k = 0; k < NV; ++k) part[(size_t)blockIdx.y * pstride + (size_t)k * nd + j] = acc[k];
+        for (int k = 0; k <= NV; ++k) part[(size_t)blockIdx.y * pstride + (size_t)k * nd + j] = acc[k];
     }
 }
-// stage 2: sum the slices, resolve the deferred carries, add cmul * cost_j * D, store LO limbs
+// stage 2: sum the slices, remove the bias, resolve the deferred carries, add cmul * cost_j * D
 template <int LV, int LO>
 __global__ void __launch_bounds__(128)
-k_densedot2(const long long* __restrict__ part, size_t pstride, int slices, int nd, int n,
-            const unsigned char* __restrict__ inbasis, const long long* __restrict__ cost, int cmul, int LD,
-            u64* __restrict__ out, const Scalars* sc) {
+k_densedot2(const unsigned long long* __restrict__ part, size_t pstride, int slices, int nd, int n,
+            const unsigned long long* __restrict__ S, const unsigned char* __restrict__ inbasis,
+            const long long* __restrict__ cost, int cmul, int LD, u64* __restrict__ out, const Scalars* sc) {
     constexpr int NV = 2 * LV;
     if (sc->status != ST_RUN) return;
     int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -257,15 +306,28 @@ k_densedot2(const long long* __restrict__ part, size_t pstride, int slices, int 
 #pragma unroll
     for (int l = 0; l < LO; ++l) res[l] = 0;
     if (!inbasis[j]) {
-        // value = sum_k acc_k 2^(32k), acc_k signed: propagate with arithmetic shifts
+        // word k of the result: sum_i a_i x_ik = (sum_i a'_i x_ik) - 128 S_k; words >= NV use the sign limb
+        long long hi_word;
+        {
+            unsigned long long a = 0;
+            for (int s2 = 0; s2 < slices; ++s2) a += part[(size_t)s2 * pstride + (size_t)NV * nd + j];
+            hi_word = (long long)(a - 128ull * S[NV]);
+        }
         long long carry = 0;
         u32 limbs[2 * LO];
 #pragma unroll
         for (int k = 0; k < 2 * LO; ++k) {
-            long long a = carry;
-            if (k < NV) for (int s = 0; s < slices; ++s) a += part[(size_t)s * pstride + (size_t)k * nd + j];
-            limbs[k] = (u32)a;
-            carry = a >> 32;                        // arithmetic: keeps the sign
+            long long v;
+            if (k < NV) {
+                unsigned long long a = 0;
+                for (int s2 = 0; s2 < slices; ++s2) a += part[(size_t)s2 * pstride + (size_t)k * nd + j];
+                v = (long long)(a - 128ull * S[k]);
+            } else {
+                v = hi_word;
+            }
+            long long t = carry + v;
+            limbs[k] = (u32)t;
+            carry = t >> 32;                        // arithmetic: keeps the sign
         }
 #pragma unroll
         for (int l = 0; l < LO; ++l) res[l] = (u64)limbs[2 * l] | ((u64)limbs[2 * l + 1] << 32);
@@ -843,10 +905,10 @@ __global__ void k_scalars(int L, int E_host, Scalars* sc) {
         return;
     }
     int t = rt_ctz(sc->D, L);
-    int E = (t + 63) >> 6;
+    int E = E_host;                     // extra limbs of the kernel variant the host launches
     int W = L + E;
     sc->t = t; sc->E = E;
-    if (E != E_host) { sc->status = ST_FATAL; return; }   // host picked the wrong kernel variant
+    if (E < ((t + 63) >> 6)) { sc->status = ST_FATAL; return; }   // variant too narrow for ctz(D)
     for (int l = 0; l < L; ++l) dodd[l] = sc->D[l];
     rt_shr(dodd, L, t);
     rt_inv_odd(inv, dodd, L, W, ws);
@@ -1107,7 +1169,6 @@ k_update_generic(u64* __restrict__ C, size_t ps, int ld, int nrows, int L, const
                  size_t us, const u64* __restrict__ rowp, size_t rs, Scalars* sc) {
     if (sc->status != ST_RUN) return;
     const int E = sc->E;
-    if (E <= 2) return;
     const int W = L + E, LU = L + 2;
     int col = blockIdx.x * blockDim.x + threadIdx.x;
     int i = blockIdx.y;

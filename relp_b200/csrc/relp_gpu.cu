@@ -116,7 +116,7 @@ static int alloc_width_buffers(rg_context* ctx, int L) {
     CK(dev_alloc(&ctx->tmprow, sizeof(u64) * LU_of(L) * ld, ctx->stream));
     CK(dev_alloc(&ctx->us2, sizeof(u64) * (LU_of(L) + 1) * ld, ctx->stream));
     if (ctx->nd > 0)
-        CK(dev_alloc(&ctx->dpart, sizeof(long long) * ctx->dslices * 2 * LW_of(L) * ctx->nd, ctx->stream));
+        CK(dev_alloc(&ctx->dpart, sizeof(long long) * ctx->dslices * (2 * LW_of(L) + 1) * ctx->nd, ctx->stream));
     CK(dev_alloc(&ctx->kappa, sizeof(u64) * LU_of(L) * n, ctx->stream));
     CK(dev_alloc(&ctx->nu, sizeof(u64) * LU_of(L) * n, ctx->stream));
     CK(dev_alloc(&ctx->sigma, sizeof(u64) * LS_of(L) * n, ctx->stream));
@@ -203,7 +203,7 @@ extern "C" int rg_destroy(rg_context* ctx) {
     free_dev_on(ctx->cost, ctx->stream); free_dev_on(ctx->rhs, ctx->stream); free_dev_on(ctx->basis, ctx->stream); free_dev_on(ctx->inbasis, ctx->stream);
     free_dev_on(ctx->G, ctx->stream); free_dev_on(ctx->cand, ctx->stream); free_dev_on(ctx->score, ctx->stream); free_dev_on(ctx->sc, ctx->stream); free_dev_on(ctx->svec, ctx->stream);
     free_dev_on(ctx->xsend, ctx->stream); free_dev_on(ctx->xrecv, ctx->stream);
-    free_dev_on(ctx->Arm, ctx->stream); free_dev_on(ctx->Acm, ctx->stream);
+    free_dev_on(ctx->Arm, ctx->stream); free_dev_on(ctx->Acm, ctx->stream); free_dev_on(ctx->dsum, ctx->stream);
     free_dev_on(ctx->wf, ctx->stream); free_dev_on(ctx->wcol, ctx->stream); free_dev_on(ctx->artf, ctx->stream);
     free_dev_on(ctx->artcost, ctx->stream); free_dev_on(ctx->rowf, ctx->stream);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
@@ -292,7 +292,8 @@ extern "C" int rg_load_dense_i8(rg_context* ctx, int32_t nd, const int8_t* colma
     ctx->launches++;
     ctx->nd = nd;
     ctx->dslices = 4;
-    CK(dev_alloc(&ctx->dpart, sizeof(long long) * ctx->dslices * 2 * LW_of(ctx->L) * nd, ctx->stream));
+    CK(dev_alloc(&ctx->dpart, sizeof(long long) * ctx->dslices * (2 * LW_of(ctx->L) + 1) * nd, ctx->stream));
+    CK(dev_alloc(&ctx->dsum, sizeof(long long) * (2 * LW_of(RG_MAXL) + 2), ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return RG_OK;
 }
@@ -333,7 +334,7 @@ static int ensure_xbuf(rg_context* ctx, size_t send_words, size_t recv_words) {
     if (need <= ctx->xbytes) return RG_OK;
     CK(cudaStreamSynchronize(ctx->stream));
     free_dev_on(ctx->xsend, ctx->stream); free_dev_on(ctx->xrecv, ctx->stream);
-    free_dev_on(ctx->Arm, ctx->stream); free_dev_on(ctx->Acm, ctx->stream);
+    free_dev_on(ctx->Arm, ctx->stream); free_dev_on(ctx->Acm, ctx->stream); free_dev_on(ctx->dsum, ctx->stream);
     free_dev_on(ctx->wf, ctx->stream); free_dev_on(ctx->wcol, ctx->stream); free_dev_on(ctx->artf, ctx->stream);
     free_dev_on(ctx->artcost, ctx->stream); free_dev_on(ctx->rowf, ctx->stream);
     CK(dev_alloc(&ctx->xsend, need, ctx->stream));
@@ -374,12 +375,13 @@ template <int LV, int LO>
 static void launch_coldots(rg_context* ctx, const u64* vec, size_t vs, int cmul, u64* out) {
     if (ctx->nd > 0) {
         int rps = cdiv(ctx->m, ctx->dslices);
-        size_t pstride = (size_t)2 * LV * ctx->nd;
+        size_t pstride = (size_t)(2 * LV + 1) * ctx->nd;
         dim3 grid(cdiv(ctx->nd, 128), ctx->dslices);
+        LAUNCH((k_vecsum<LV>), 2 * LV + 1, 256, vec, vs, ctx->m, ctx->dsum, ctx->sc);
         LAUNCH((k_densedot1<LV>), grid, 128, vec, vs, ctx->m, ctx->nd, ctx->Arm, ctx->ldr, rps, ctx->dpart,
                pstride, ctx->inbasis, ctx->sc);
         LAUNCH((k_densedot2<LV, LO>), cdiv(ctx->nd, 128), 128, ctx->dpart, pstride, ctx->dslices, ctx->nd, ctx->n,
-               ctx->inbasis, ctx->cost, cmul, ctx->L, out, ctx->sc);
+               ctx->dsum, ctx->inbasis, ctx->cost, cmul, ctx->L, out, ctx->sc);
     }
     if (ctx->n > ctx->nd)
         LAUNCH((k_coldot<LV, LO>), cdiv(ctx->n - ctx->nd, 256), 256, vec, vs, ctx->n, ctx->nd, ctx->A.colptr,
@@ -521,24 +523,36 @@ static int launch_work(rg_context* ctx) {
     }
 }
 
-template <int L>
-static void launch_update_t(rg_context* ctx, int E) {
+// K1 variants: E = extra limbs (>= ceil(ctz(D)/64)).  ctz(D) grows by about one bit per structural
+// column in the basis, so wide carries need wide E; the generic run-time-width kernel is the last resort.
+static int pick_update_variant(int L, int E_needed) {
+    static const int opts[] = {0, 1, 2, 3, 4, 6, 8};
+    int emax = L == 1 ? 1 : (L == 2 ? 2 : (L == 4 ? 4 : 8));
+    for (int e : opts) if (e >= E_needed && e <= emax) return e;
+    return -1;   // generic kernel
+}
+template <int L, int E>
+static void launch_update_le(rg_context* ctx) {
     constexpr int CP = L <= 4 ? 2 : 1;
     dim3 grid(cdiv(ctx->ld, 256 * CP), cdiv(ctx->nloc + 1, 32));
-    if (E == 0) {
-        LAUNCH((k_update<L, 0, CP>), grid, 256, ctx->carry, ctx->plane, ctx->ld, ctx->nloc + 1, ctx->u,
-               (size_t)ctx->ld, ctx->rowp, (size_t)ctx->ld, ctx->sc);
-    } else if (E == 1) {
-        LAUNCH((k_update<L, 1, CP>), grid, 256, ctx->carry, ctx->plane, ctx->ld, ctx->nloc + 1, ctx->u,
-               (size_t)ctx->ld, ctx->rowp, (size_t)ctx->ld, ctx->sc);
-    } else if (E == 2) {
-        LAUNCH((k_update<L, 2, CP>), grid, 256, ctx->carry, ctx->plane, ctx->ld, ctx->nloc + 1, ctx->u,
-               (size_t)ctx->ld, ctx->rowp, (size_t)ctx->ld, ctx->sc);
-    } else {
-        dim3 g2(cdiv(ctx->ld, 128), ctx->nloc + 1);
-        LAUNCH(k_update_generic, g2, 128, ctx->carry, ctx->plane, ctx->ld, ctx->nloc + 1, L, ctx->u,
-               (size_t)ctx->ld, ctx->rowp, (size_t)ctx->ld, ctx->sc);
+    LAUNCH((k_update<L, E, CP>), grid, 256, ctx->carry, ctx->plane, ctx->ld, ctx->nloc + 1, ctx->u,
+           (size_t)ctx->ld, ctx->rowp, (size_t)ctx->ld, ctx->sc);
+}
+template <int L>
+static void launch_update_t(rg_context* ctx, int E) {
+    switch (E) {
+        case 0: launch_update_le<L, 0>(ctx); return;
+        case 1: launch_update_le<L, 1>(ctx); return;
+        case 2: if constexpr (L >= 2) { launch_update_le<L, 2>(ctx); return; } break;
+        case 3: if constexpr (L >= 4) { launch_update_le<L, 3>(ctx); return; } break;
+        case 4: if constexpr (L >= 4) { launch_update_le<L, 4>(ctx); return; } break;
+        case 6: if constexpr (L >= 8) { launch_update_le<L, 6>(ctx); return; } break;
+        case 8: if constexpr (L >= 8) { launch_update_le<L, 8>(ctx); return; } break;
+        default: break;
     }
+    dim3 g2(cdiv(ctx->ld, 128), ctx->nloc + 1);
+    LAUNCH(k_update_generic, g2, 128, ctx->carry, ctx->plane, ctx->ld, ctx->nloc + 1, L, ctx->u,
+           (size_t)ctx->ld, ctx->rowp, (size_t)ctx->ld, ctx->sc);
 }
 static void launch_update(rg_context* ctx, int E) { DISPATCH_L(ctx->L, launch_update_t, ctx, E); }
 
@@ -625,7 +639,8 @@ static int do_pivot(rg_context* ctx, int q, int fixed_row, bool want_se, bool re
         if (want_se) RG_TRY(launch_work(ctx));
         double h4 = hostprof ? now_s() : 0;
         if (prof) cudaEventRecord(ctx->evp[2], ctx->stream);
-        int E = (ctx->t_cur + 63) / 64;
+        int E = pick_update_variant(ctx->L, (ctx->t_cur + 63) / 64);
+        if (E < 0) E = (ctx->t_cur + 63) / 64;      // generic run-time-width kernel
         LAUNCH(k_scalars, 1, 1, ctx->L, E, ctx->sc);
         if (want_se) {   // steepest-edge scalars on the side stream, overlapped with K1
             cudaEventRecord(ctx->ev_side0, ctx->stream);
