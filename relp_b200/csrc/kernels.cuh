@@ -207,118 +207,131 @@ k_coldot(const u64* __restrict__ vec, size_t vs, int n, int j0, const long long*
 // 32 x 32 -> 64 multiply-add (one IMAD.WIDE.U32); the bias is removed with the limb sums S_k of the
 // vector (k_vecsum) and the sign of each vector entry rides along as one extra "sign extension" limb.
 //
-// limb sums of vec[1..m]: S[k] = sum_i limb32_k(vec[1+i]) for k < 2 LV, S[2 LV] = sum_i signword_i
+// Effective width: every entry of the vector fits `lveff` limbs (from the tracked bit-length maxima), so
+// only 2*lveff words plus one sign word are multiplied; word 2*lveff carries the sign extension.
+__device__ __forceinline__ int eff_limbs(const int* bits, int LV) {
+    int need = (*bits + 1 + 63) >> 6;              // +1: sign bit
+    return need < 1 ? 1 : (need > LV ? LV : need);
+}
+// limb sums of vec[1..m]: S[k] = sum_i limb32_k(vec[1+i]) for k < 2 lveff, S[2 lveff] = sum_i signword_i
 template <int LV>
-__global__ void __launch_bounds__(256) k_vecsum(const u64* __restrict__ vec, size_t vs, int m,
+__global__ void __launch_bounds__(256) k_vecsum(const u64* __restrict__ vec, size_t vs, int m, const int* bits,
                                                 unsigned long long* __restrict__ S, const Scalars* sc) {
-    constexpr int NV = 2 * LV;
     __shared__ unsigned long long red[256];
     if (sc->status != ST_RUN) return;
-    {
-        const int k = blockIdx.x;                  // one block per limb position (NV + 1 blocks)
-        unsigned long long acc = 0;
-        for (int i = threadIdx.x; i < m; i += blockDim.x) {
-            if (k < NV) {
-                u64 v = vec[(size_t)(k >> 1) * vs + 1 + i];
-                acc += (k & 1) ? (v >> 32) : (v & 0xffffffffull);
-            } else {
-                acc += ((i64)vec[(size_t)(LV - 1) * vs + 1 + i] < 0) ? 0xffffffffull : 0ull;
-            }
+    const int lveff = eff_limbs(bits, LV), NVe = 2 * lveff;
+    const int k = blockIdx.x;                      // one block per word position
+    if (k > NVe) { if (threadIdx.x == 0) S[k] = 0; return; }
+    unsigned long long acc = 0;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        if (k < NVe) {
+            u64 v = vec[(size_t)(k >> 1) * vs + 1 + i];
+            acc += (k & 1) ? (v >> 32) : (v & 0xffffffffull);
+        } else {
+            acc += ((i64)vec[(size_t)(LV - 1) * vs + 1 + i] < 0) ? 0xffffffffull : 0ull;
         }
-        red[threadIdx.x] = acc;
-        __syncthreads();
-        for (int s2 = 128; s2 > 0; s2 >>= 1) {
-            if (threadIdx.x < s2) red[threadIdx.x] += red[threadIdx.x + s2];
-            __syncthreads();
-        }
-        if (threadIdx.x == 0) S[k] = red[0];
     }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s2 = 128; s2 > 0; s2 >>= 1) {
+        if (threadIdx.x < s2) red[threadIdx.x] += red[threadIdx.x + s2];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) S[k] = red[0];
 }
-// stage 1: part[rs][k][j] = sum over the row slice of (a_ij + 128) * limb32_k(vec[1+i])  (k <= 2 LV)
+// stage 1: part[rs][k][j] = sum over the row slice of (a_ij + 128) * word_k(vec[1+i])  (k <= 2 lveff)
+// Block = 64 columns x G word groups of 16: a thread owns 16 accumulators of one column.  Rows whose
+// vector entry is zero are skipped (warp-uniform): the pivot row and the dual row are sparse.
 template <int LV>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(64 * ((2 * LV + 1 + 15) / 16))
 k_densedot1(const u64* __restrict__ vec, size_t vs, int m, int nd, const signed char* __restrict__ Arm,
-            size_t ldr, int rows_per_slice, unsigned long long* __restrict__ part, size_t pstride,
-            const unsigned char* __restrict__ inbasis, const Scalars* sc) {
+            size_t ldr, int rows_per_slice, const int* bits, unsigned long long* __restrict__ part,
+            size_t pstride, const unsigned char* __restrict__ inbasis, const Scalars* sc) {
     constexpr int NV = 2 * LV;
-    constexpr int NW = (NV + 1 + 3) / 4 * 4;       // words per staged row, padded to 16 bytes
-    constexpr int RB = 32;                         // rows staged per shared-memory tile
+    constexpr int G = (NV + 1 + 15) / 16;          // word groups
+    constexpr int NW = G * 16;                     // words per staged row (zero padded)
+    constexpr int RB = 16;                         // rows staged per shared-memory tile
     __shared__ __align__(16) u32 sv[RB][NW];
+    __shared__ int nzrow[RB];
     if (sc->status != ST_RUN) return;
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = j < nd && !inbasis[j];
+    const int lveff = eff_limbs(bits, LV), NVe = 2 * lveff;
+    const int tid = threadIdx.y * 64 + threadIdx.x;
+    const int nthreads = 64 * G;
+    const int j = blockIdx.x * 64 + threadIdx.x;
+    const int g = threadIdx.y;
+    const bool active = j < nd && !inbasis[j] && 16 * g <= NVe;
     const int r0 = blockIdx.y * rows_per_slice;
     const int r1 = min(m, r0 + rows_per_slice);
-    unsigned long long acc[NV + 1];
+    unsigned long long acc[16];
 #pragma unroll
-    for (int k = 0; k <= NV; ++k) acc[k] = 0;
+    for (int k = 0; k < 16; ++k) acc[k] = 0;
     for (int base = r0; base < r1; base += RB) {
         __syncthreads();
-        for (int t = threadIdx.x; t < RB * (LV + 1); t += blockDim.x) {
-            int r = t / (LV + 1), l = t % (LV + 1);
+        if (tid < RB) nzrow[tid] = 0;
+        __syncthreads();
+        for (int t = tid; t < RB * NW / 2; t += nthreads) {     // two words (one u64 limb) per step
+            int r = t / (NW / 2), l = t % (NW / 2);
             bool in = base + r < r1;
-            if (l < LV) {
-                u64 v = in ? vec[(size_t)l * vs + 1 + base + r] : 0;
-                sv[r][2 * l] = (u32)v; sv[r][2 * l + 1] = (u32)(v >> 32);
-            } else {
-                u64 top = in ? vec[(size_t)(LV - 1) * vs + 1 + base + r] : 0;
-                sv[r][NV] = (i64)top < 0 ? 0xffffffffu : 0u;
+            u64 v = 0;
+            if (in) {
+                if (l < lveff) v = vec[(size_t)l * vs + 1 + base + r];
+                else if (l == lveff) v = ((i64)vec[(size_t)(LV - 1) * vs + 1 + base + r] < 0) ? 0xffffffffull : 0ull;
             }
+            sv[r][2 * l] = (u32)v; sv[r][2 * l + 1] = (u32)(v >> 32);
+            if (v) nzrow[r] = 1;
         }
         __syncthreads();
         if (!active) continue;
-        // all coefficient loads of the tile are issued before any use (one memory latency per tile);
-        // rows past the slice end hold zero vector limbs, so their (biased) coefficient is harmless
-        u32 av[RB];
-#pragma unroll
-        for (int r = 0; r < RB; ++r)
-            av[r] = (base + r < r1) ? (u32)((int)Arm[(size_t)(base + r) * ldr + j] + 128) : 128u;
-#pragma unroll
+#pragma unroll 4
         for (int r = 0; r < RB; ++r) {
-            const u32 a = av[r];
-            const uint4* row4 = reinterpret_cast<const uint4*>(sv[r]);
+            if (!nzrow[r]) continue;               // zero vector entry: contributes nothing (bias included)
+            const u32 a = (u32)((int)Arm[(size_t)(base + r) * ldr + j] + 128);
+            const uint4* row4 = reinterpret_cast<const uint4*>(&sv[r][16 * g]);
 #pragma unroll
-            for (int g = 0; g < NW / 4; ++g) {
-                uint4 x = row4[g];
-                if (4 * g + 0 <= NV) acc[4 * g + 0] += (unsigned long long)a * x.x;
-                if (4 * g + 1 <= NV) acc[4 * g + 1] += (unsigned long long)a * x.y;
-                if (4 * g + 2 <= NV) acc[4 * g + 2] += (unsigned long long)a * x.z;
-                if (4 * g + 3 <= NV) acc[4 * g + 3] += (unsigned long long)a * x.w;
+            for (int q4 = 0; q4 < 4; ++q4) {
+                uint4 x = row4[q4];
+                acc[4 * q4 + 0] += (unsigned long long)a * x.x;
+                acc[4 * q4 + 1] += (unsigned long long)a * x.y;
+                acc[4 * q4 + 2] += (unsigned long long)a * x.z;
+                acc[4 * q4 + 3] += (unsigned long long)a * x.w;
             }
         }
     }
     if (j < nd) {
 #pragma unroll
-        for (int k = 0; k <= NV; ++k) part[(size_t)blockIdx.y * pstride + (size_t)k * nd + j] = acc[k];
+        for (int k = 0; k < 16; ++k) {
+            int w = 16 * g + k;
+            if (w <= NV) part[(size_t)blockIdx.y * pstride + (size_t)w * nd + j] = acc[k];
+        }
     }
 }
 // stage 2: sum the slices, remove the bias, resolve the deferred carries, add cmul * cost_j * D
 template <int LV, int LO>
 __global__ void __launch_bounds__(128)
 k_densedot2(const unsigned long long* __restrict__ part, size_t pstride, int slices, int nd, int n,
-            const unsigned long long* __restrict__ S, const unsigned char* __restrict__ inbasis,
+            const int* bits, const unsigned long long* __restrict__ S, const unsigned char* __restrict__ inbasis,
             const long long* __restrict__ cost, int cmul, int LD, u64* __restrict__ out, const Scalars* sc) {
-    constexpr int NV = 2 * LV;
     if (sc->status != ST_RUN) return;
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= nd) return;
+    const int NVe = 2 * eff_limbs(bits, LV);
     u64 res[LO];
 #pragma unroll
     for (int l = 0; l < LO; ++l) res[l] = 0;
     if (!inbasis[j]) {
-        // word k of the result: sum_i a_i x_ik = (sum_i a'_i x_ik) - 128 S_k; words >= NV use the sign limb
+        // word k of the result: sum_i a_i x_ik = (sum_i a'_i x_ik) - 128 S_k; words >= NVe use the sign word
         long long hi_word;
         {
             unsigned long long a = 0;
-            for (int s2 = 0; s2 < slices; ++s2) a += part[(size_t)s2 * pstride + (size_t)NV * nd + j];
-            hi_word = (long long)(a - 128ull * S[NV]);
+            for (int s2 = 0; s2 < slices; ++s2) a += part[(size_t)s2 * pstride + (size_t)NVe * nd + j];
+            hi_word = (long long)(a - 128ull * S[NVe]);
         }
         long long carry = 0;
         u32 limbs[2 * LO];
 #pragma unroll
         for (int k = 0; k < 2 * LO; ++k) {
             long long v;
-            if (k < NV) {
+            if (k < NVe) {
                 unsigned long long a = 0;
                 for (int s2 = 0; s2 < slices; ++s2) a += part[(size_t)s2 * pstride + (size_t)k * nd + j];
                 v = (long long)(a - 128ull * S[k]);
@@ -832,7 +845,7 @@ k_ftran(const u64* __restrict__ C, size_t ps, int ld, int nrows, const long long
 }
 
 __global__ void k_reset_iter(Scalars* sc) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) { sc->maxbits_u = 0; sc->maxbits_rowp = 0; sc->maxbits_new = 0; }
+    if (threadIdx.x == 0 && blockIdx.x == 0) { sc->maxbits_u = 0; sc->maxbits_rowp = 0; sc->maxbits_new = 0; sc->maxbits_tmp = 0; }
 }
 __global__ void k_set_pq(Scalars* sc, int q, int p) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {

@@ -370,18 +370,19 @@ static int sync_mirror(rg_context* ctx) {
 
 static void set_status(rg_context* ctx, int st) { LAUNCH(k_set_status, 1, 1, ctx->sc, st); }
 
-// out_j = cmul cost_j D + vec[1..m] . a_j for every provider column: dense block + CSC remainder
+// out_j = cmul cost_j D + vec[1..m] . a_j for every provider column: dense block + CSC remainder.
+// `bits` points at the device-side bit-length maximum that bounds every entry of `vec`.
 template <int LV, int LO>
-static void launch_coldots(rg_context* ctx, const u64* vec, size_t vs, int cmul, u64* out) {
+static void launch_coldots(rg_context* ctx, const u64* vec, size_t vs, int cmul, u64* out, const int* bits) {
     if (ctx->nd > 0) {
         int rps = cdiv(ctx->m, ctx->dslices);
         size_t pstride = (size_t)(2 * LV + 1) * ctx->nd;
-        dim3 grid(cdiv(ctx->nd, 128), ctx->dslices);
-        LAUNCH((k_vecsum<LV>), 2 * LV + 1, 256, vec, vs, ctx->m, ctx->dsum, ctx->sc);
-        LAUNCH((k_densedot1<LV>), grid, 128, vec, vs, ctx->m, ctx->nd, ctx->Arm, ctx->ldr, rps, ctx->dpart,
+        dim3 grid(cdiv(ctx->nd, 64), ctx->dslices), block(64, (2 * LV + 1 + 15) / 16);
+        LAUNCH((k_vecsum<LV>), 2 * LV + 1, 256, vec, vs, ctx->m, bits, ctx->dsum, ctx->sc);
+        LAUNCH((k_densedot1<LV>), grid, block, vec, vs, ctx->m, ctx->nd, ctx->Arm, ctx->ldr, rps, bits, ctx->dpart,
                pstride, ctx->inbasis, ctx->sc);
         LAUNCH((k_densedot2<LV, LO>), cdiv(ctx->nd, 128), 128, ctx->dpart, pstride, ctx->dslices, ctx->nd, ctx->n,
-               ctx->dsum, ctx->inbasis, ctx->cost, cmul, ctx->L, out, ctx->sc);
+               bits, ctx->dsum, ctx->inbasis, ctx->cost, cmul, ctx->L, out, ctx->sc);
     }
     if (ctx->n > ctx->nd)
         LAUNCH((k_coldot<LV, LO>), cdiv(ctx->n - ctx->nd, 256), 256, vec, vs, ctx->n, ctx->nd, ctx->A.colptr,
@@ -389,7 +390,7 @@ static void launch_coldots(rg_context* ctx, const u64* vec, size_t vs, int cmul,
 }
 template <int L>
 static void launch_price_t(rg_context* ctx) {
-    launch_coldots<L, L + 2>(ctx, ctx->carry, ctx->plane, 1, ctx->kappa);
+    launch_coldots<L, L + 2>(ctx, ctx->carry, ctx->plane, 1, ctx->kappa, &ctx->sc->maxbits_carry);
 }
 static void launch_price(rg_context* ctx) { DISPATCH_L(ctx->L, launch_price_t, ctx); }
 
@@ -559,8 +560,8 @@ static void launch_update(rg_context* ctx, int E) { DISPATCH_L(ctx->L, launch_up
 template <int L>
 static void launch_se_dots_t(rg_context* ctx) {
     constexpr int LU = L + 2, LW = LW_of(L), LS = LS_of(L);
-    launch_coldots<L, LU>(ctx, ctx->rowp, (size_t)ctx->ld, 0, ctx->nu);
-    launch_coldots<LW, LS>(ctx, ctx->omega, (size_t)ctx->ld, 0, ctx->sigma);
+    launch_coldots<L, LU>(ctx, ctx->rowp, (size_t)ctx->ld, 0, ctx->nu, &ctx->sc->maxbits_rowp);
+    launch_coldots<LW, LS>(ctx, ctx->omega, (size_t)ctx->ld, 0, ctx->sigma, &ctx->sc->maxbits_tmp);
 }
 template <int L>
 static void launch_gamma_update_t(rg_context* ctx) {
@@ -585,7 +586,7 @@ static void launch_se_update(rg_context* ctx) {
 
 template <int L>
 static void launch_rowdot_t(rg_context* ctx) {   // nu_j = rowp . a_j
-    launch_coldots<L, L + 2>(ctx, ctx->rowp, (size_t)ctx->ld, 0, ctx->nu);
+    launch_coldots<L, L + 2>(ctx, ctx->rowp, (size_t)ctx->ld, 0, ctx->nu, &ctx->sc->maxbits_rowp);
 }
 
 // ------------------------------------------------------------------------------------------------
