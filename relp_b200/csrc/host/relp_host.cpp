@@ -8,6 +8,8 @@
 // The carry, the pricing data and the steepest-edge weights live on the device; this layer only
 // sequences the calls and keeps the index bookkeeping the reference keeps in `Kind`.
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -265,6 +267,10 @@ extern "C" int rh_solve_relaxation(const rh_problem* problem, const rh_options* 
         relp::check(im.ctx, rg_get_basis(im.ctx, res->basis.data()), "rg_get_basis");
         rg_get_stats(im.ctx, &res->stats);
         res->seconds_total = std::chrono::duration<double>(clk::now() - t0).count();
+        if (getenv("RG_HOSTPROF"))
+            fprintf(stderr, "[hostprof] create+upload %.3f s, loops %.3f s, export %.3f s\n",
+                    std::chrono::duration<double>(t1 - t0).count(), res->seconds,
+                    std::chrono::duration<double>(clk::now() - t2).count());
     } catch (const relp::Error& e) {
         res->err = e.what;
         return e.code;

@@ -174,7 +174,11 @@ def solve_relaxation(problem, rule="steepest_edge", fused=True, initial_limbs=0,
                            profile=1 if profile else 0, rank=rank, world=world, reserved=0,
                            nccl_unique_id=C.cast(idbuf, C.c_void_p) if idbuf is not None else None)
     handle = C.c_void_p()
+    import os, time
+    _t0 = time.perf_counter()
     rc = lib.rh_solve_relaxation(C.byref(cprob), C.byref(opts), C.byref(handle))
+    if os.environ.get("RG_HOSTPROF"):
+        print(f"[hostprof] rh_solve_relaxation call {time.perf_counter() - _t0:.3f} s", flush=True)
     try:
         if rc != 0:
             msg = lib.rh_result_error(handle).decode() if handle else ""
