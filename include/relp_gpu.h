@@ -66,6 +66,10 @@ typedef struct rg_options {
     int32_t initial_limbs;   /* 1, 2, 4, 8 or 16; 0 = default (2) */
     int32_t rank;            /* row-shard rank (0 when single GPU) */
     int32_t world;           /* number of row shards (1 when single GPU) */
+    int32_t dense_carry;     /* 1: always run the dense carry kernels; 0 (default): active-column mode -- carry
+                                columns that still equal D*e_k are neither stored nor touched until a pivot in
+                                their own row makes them general */
+    int32_t reserved;
     const void* nccl_unique_id;  /* world > 1: the 128-byte ncclUniqueId shared by all ranks (rg_nccl_unique_id
                                     on rank 0, broadcast by the host, e.g. torch.distributed) */
 } rg_options;

@@ -58,7 +58,7 @@ typedef struct rh_options {
     int32_t profile;              /* 1: CUDA events around every K1 launch (rg_set_profile) */
     int32_t rank;                 /* row-shard rank / world (world <= 1: single GPU) */
     int32_t world;
-    int32_t reserved;
+    int32_t dense_carry;          /* see rg_options */
     const void* nccl_unique_id;   /* world > 1: see rg_options */
 } rh_options;
 

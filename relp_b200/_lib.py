@@ -11,7 +11,8 @@ LIB_PATH = os.path.join(HERE, "librelp_gpu.so")
 
 class rg_options(C.Structure):
     _fields_ = [("device", C.c_int32), ("initial_limbs", C.c_int32), ("rank", C.c_int32),
-                ("world", C.c_int32), ("nccl_unique_id", C.c_void_p)]
+                ("world", C.c_int32), ("dense_carry", C.c_int32), ("reserved", C.c_int32),
+                ("nccl_unique_id", C.c_void_p)]
 
 
 class rg_stats(C.Structure):
@@ -47,7 +48,7 @@ class rh_trace_entry(C.Structure):
 class rh_options(C.Structure):
     _fields_ = [("device", C.c_int32), ("initial_limbs", C.c_int32), ("rule", C.c_int32),
                 ("fused", C.c_int32), ("max_pivots", C.c_int64), ("profile", C.c_int32),
-                ("rank", C.c_int32), ("world", C.c_int32), ("reserved", C.c_int32),
+                ("rank", C.c_int32), ("world", C.c_int32), ("dense_carry", C.c_int32),
                 ("nccl_unique_id", C.c_void_p)]
 
 

@@ -34,7 +34,7 @@ struct Scalars {
     int pg;              // pivot row as global carry row index (1..m)
     int row_lo, nloc;    // this rank's block of constraint rows [row_lo, row_lo + nloc)
     int rank, world;
-    int pad;
+    int nk;              // number of non-trivial carry columns (entries of klist), column 0 included
     u64 D[RG_MAXL];          // current denominator (positive)
     u64 a[RG_MAXL + 2];      // pivot element numerator u[p] (replicated on every rank)
     u64 Dnew[RG_MAXL];       // |a|: denominator after the pivot
@@ -50,7 +50,7 @@ struct HostMirror {
     int status, q, p, leaving;          // device status; NEXT entering column; last pivot row; last leaving
     int t_next, bits_D, maxbits_carry, predicted;
     int found, sgn, maxbits_tmp, pivoted;   // pivoted: a basis change happened since the host cleared it
-    int q_done, p_done, leaving_done, pad;  // the pivot that was performed (written by k_finalize)
+    int q_done, p_done, leaving_done, nk;   // the pivot that was performed (written by k_finalize); active columns
 };
 
 struct Csc {
@@ -91,6 +91,14 @@ struct rg_context {
     int work_chunks = 0;
     u64* tmprow = nullptr;      // LU planes x ld      phase-switch row
     u64* svec = nullptr;        // 1 plane x ld        basic costs (phase switch)
+    // active-column bookkeeping: carry column k is `trivial` while it equals
+    // D * e_k on rows 1..m; trivial columns are never read or written, the others are listed in klist
+    unsigned char* triv = nullptr;   // ld flags
+    int* klist = nullptr;            // ld column indices
+    long long* aq = nullptr;         // m: the entering column scattered densely (list-mode FTRAN)
+    bool list_mode = false;
+    int nk_host = 1;                 // upper bound of sc->nk known to the host
+    int dense_carry_opt = 0;         // rg_options: 1 = never use the active-column list
     u64* us2 = nullptr;         // LU+1 planes x ld    pivot column times row factors^2 (weighted problems)
     // weights of a prescaled rational problem; all 1 for integer problems
     bool weighted = false;

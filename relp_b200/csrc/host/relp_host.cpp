@@ -49,6 +49,7 @@ public:
         opts.world = o.world > 1 ? o.world : 1;
         opts.rank = o.world > 1 ? o.rank : 0;
         opts.nccl_unique_id = o.nccl_unique_id;
+        opts.dense_carry = o.dense_carry;
         check(nullptr, rg_create(&opts, &ctx), "rg_create");
         check(ctx, rg_load_csc(ctx, m, n, mp.p->colptr, mp.p->rowidx, mp.p->vals), "rg_load_csc");
         if (mp.p->n_dense > 0) check(ctx, rg_load_dense_i8(ctx, mp.p->n_dense, mp.p->dense), "rg_load_dense_i8");

@@ -132,7 +132,7 @@ __global__ void k_init_scalars(u64* C, size_t ps, int m, int L, const long long*
     for (int l = 0; l < L; ++l) C[l * ps] = acc[l];   // the host re-initialises at a wider L if maxbits does not fit
     sc->status = ST_RUN;
     sc->q = -1; sc->p = -1; sc->pg = -1; sc->leaving = 0; sc->sgn = 1;
-    sc->row_lo = row_lo; sc->nloc = nloc; sc->rank = rank; sc->world = world;
+    sc->row_lo = row_lo; sc->nloc = nloc; sc->rank = rank; sc->world = world; sc->nk = 1;
     sc->t = 0; sc->E = 0; sc->t2 = 0; sc->E2 = 0;
     sc->maxbits_carry = maxbits; sc->maxbits_new = 0; sc->maxbits_u = 0; sc->maxbits_rowp = 0;
     sc->bits_D = 1; sc->predicted = 0; sc->last_selected = -1; sc->found = -1;
@@ -844,6 +844,142 @@ k_ftran(const u64* __restrict__ C, size_t ps, int ld, int nrows, const long long
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Active columns.  Carry column k (1..m) is `trivial` while it equals D e_k on
+// rows 1..m: true for every column of an identity start, and a pivot in row p can only destroy it for
+// k = p (the pivot row's own column, because row p of a trivial column k != p is zero).  Trivial
+// columns are never read or written; the others are listed in klist (column 0, the right-hand side,
+// is always listed).  Row 0 (the cost row) is maintained densely for all columns.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_init_active(unsigned char* triv, int* klist, int ld, int m, int all_trivial) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= ld) return;
+    triv[k] = (all_trivial && k >= 1 && k <= m) ? 1 : 0;
+    if (k == 0) klist[0] = 0;
+}
+// before the pivot row is staged: materialise the pivot row's own column if it is still trivial
+__global__ void __launch_bounds__(256)
+k_materialise_pivot_column(u64* __restrict__ C, size_t ps, int ld, int L, const unsigned char* __restrict__ triv,
+                           const Scalars* sc) {
+    if (sc->status != ST_RUN) return;
+    const int k = sc->pg;
+    if (k < 1 || !triv[k]) return;
+    int li = blockIdx.x * blockDim.x + threadIdx.x + 1;      // local carry row
+    if (li > sc->nloc) return;
+    bool diag = sc->row_lo + li == k;
+    for (int l = 0; l < L; ++l) C[(size_t)l * ps + (size_t)li * ld + k] = diag ? sc->D[l] : 0ull;
+}
+__global__ void k_activate_pivot_column(unsigned char* triv, int* klist, Scalars* sc) {
+    if (threadIdx.x || blockIdx.x) return;
+    if (sc->status != ST_RUN) return;
+    const int k = sc->pg;
+    if (k >= 1 && triv[k]) { triv[k] = 0; klist[sc->nk] = k; sc->nk = sc->nk + 1; }
+}
+// leave list mode: materialise every trivial column (thread = column, loops the local rows)
+__global__ void __launch_bounds__(128)
+k_materialise_all(u64* __restrict__ C, size_t ps, int ld, int L, int m, unsigned char* __restrict__ triv,
+                  const Scalars* sc) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < 1 || k > m || !triv[k]) return;
+    for (int li = 1 + blockIdx.y; li <= sc->nloc; li += gridDim.y) {
+        bool diag = sc->row_lo + li == k;
+        for (int l = 0; l < L; ++l) C[(size_t)l * ps + (size_t)li * ld + k] = diag ? sc->D[l] : 0ull;
+    }
+}
+__global__ void k_clear_trivial(unsigned char* triv, int ld) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < ld) triv[k] = 0;
+}
+// entering column scattered densely: aq[r] = a_rq (list-mode FTRAN indexes it by carry column)
+__global__ void k_scatter_col(long long* __restrict__ aq, int m, int nd, const long long* __restrict__ colptr,
+                              const int* __restrict__ rowidx, const long long* __restrict__ vals,
+                              const signed char* __restrict__ Acm, size_t ldc, int qarg, const Scalars* sc) {
+    if (sc->status != ST_RUN) return;
+    int q = qarg >= 0 ? qarg : sc->q;
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < nd) { if (r < m) aq[r] = Acm[(size_t)q * ldc + r]; return; }
+    if (r < m) aq[r] = 0;
+}
+__global__ void k_scatter_col2(long long* __restrict__ aq, int nd, const long long* __restrict__ colptr,
+                               const int* __restrict__ rowidx, const long long* __restrict__ vals, int qarg,
+                               const Scalars* sc) {
+    if (sc->status != ST_RUN) return;
+    int q = qarg >= 0 ? qarg : sc->q;
+    if (q < nd) return;
+    long long k = colptr[q] + blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < colptr[q + 1]) aq[rowidx[k]] = vals[k];
+}
+// list-mode FTRAN: u_i = sum_{k in klist, k >= 1} aq[k-1] C[i][k]  +  [column i trivial] D aq[i-1]
+// (row 0 is dense: its warp walks all columns).  One warp per local carry row.
+template <int L>
+__global__ void __launch_bounds__(256)
+k_ftran_list(const u64* __restrict__ C, size_t ps, int ld, int nrows, int m, const long long* __restrict__ aq,
+             const int* __restrict__ klist, const unsigned char* __restrict__ triv,
+             const long long* __restrict__ cost, int qarg, u64* __restrict__ u, size_t us, Scalars* sc) {
+    constexpr int LU = L + 2;
+    if (sc->status != ST_RUN) return;
+    int q = qarg >= 0 ? qarg : sc->q;
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (warp >= nrows) return;
+    size_t row = (size_t)warp * ld;
+    u64 acc[LU];
+#pragma unroll
+    for (int l = 0; l < LU; ++l) acc[l] = 0;
+    if (warp == 0) {
+        for (int k = 1 + lane; k <= m; k += 32) {
+            long long a = aq[k - 1];
+            if (!a) continue;
+            u64 x[L];
+            load_planar<L>(x, C, ps, row + k);
+            mac_small<LU, L>(acc, x, a);
+        }
+        if (lane == 0) {
+            long long c = cost[q];
+            if (c) {
+                u64 d[L];
+#pragma unroll
+                for (int l = 0; l < L; ++l) d[l] = sc->D[l];
+                mac_small<LU, L>(acc, d, c);
+            }
+        }
+    } else {
+        const int nk = sc->nk;
+        for (int t = 1 + lane; t < nk; t += 32) {        // klist[0] is column 0 (b): not part of B^-1
+            int k = klist[t];
+            long long a = aq[k - 1];
+            if (!a) continue;
+            u64 x[L];
+            load_planar<L>(x, C, ps, row + k);
+            mac_small<LU, L>(acc, x, a);
+        }
+        if (lane == 0) {
+            int g = sc->row_lo + warp;                   // global carry row = its own column index
+            if (g >= 1 && g <= m && triv[g]) {
+                long long a = aq[g - 1];
+                if (a) {
+                    u64 d[L];
+#pragma unroll
+                    for (int l = 0; l < L; ++l) d[l] = sc->D[l];
+                    mac_small<LU, L>(acc, d, a);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        u64 other[LU];
+#pragma unroll
+        for (int l = 0; l < LU; ++l) other[l] = __shfl_down_sync(0xffffffffu, acc[l], o);
+        add_n<LU>(acc, other);
+    }
+    if (lane == 0) {
+        store_planar<LU>(u, us, (size_t)warp, acc);
+        atomicMax(&sc->maxbits_u, bitlen_signed<LU>(acc));
+    }
+}
+
 __global__ void k_reset_iter(Scalars* sc) {
     if (threadIdx.x == 0 && blockIdx.x == 0) { sc->maxbits_u = 0; sc->maxbits_rowp = 0; sc->maxbits_new = 0; sc->maxbits_tmp = 0; }
 }
@@ -864,16 +1000,19 @@ __global__ void k_set_status(Scalars* sc, int st) {
 // the other ranks zero-fill and a sum all-reduce (exact: one non-zero contributor) replicates it.
 template <int L>
 __global__ void __launch_bounds__(256)
-k_copyrow(const u64* __restrict__ C, size_t ps, int ld, u64* __restrict__ rowp, size_t rs,
-          Scalars* sc) {
+k_copyrow(const u64* __restrict__ C, size_t ps, int ld, const unsigned char* __restrict__ triv,
+          u64* __restrict__ rowp, size_t rs, Scalars* sc) {
     if (sc->status != ST_RUN) return;
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k < ld) {
         u64 x[L];
-        if (sc->p >= 1) load_planar<L>(x, C, ps, (size_t)sc->p * ld + k);
+        // trivial columns hold D e_k implicitly; the pivot row's own column was materialised before
+        if (sc->p >= 1 && !(triv && triv[k])) load_planar<L>(x, C, ps, (size_t)sc->p * ld + k);
         else {
+            // implicit entry of a trivial column: D on its own row, 0 elsewhere
+            const bool diag = sc->p >= 1 && triv && triv[k] && k == sc->pg;
 #pragma unroll
-            for (int l = 0; l < L; ++l) x[l] = 0;
+            for (int l = 0; l < L; ++l) x[l] = diag ? sc->D[l] : 0;
         }
         store_planar<L>(rowp, rs, (size_t)k, x);
     }
@@ -1036,8 +1175,8 @@ __global__ void __launch_bounds__(32) k_scalars_se(int L, const u64* __restrict_
 // ---------------------------------------------------------------------------------------------
 template <int L, int E, int CP>
 __global__ void __launch_bounds__(256)
-k_update(u64* __restrict__ C, size_t ps, int ld, int nrows, const u64* __restrict__ u, size_t us,
-         const u64* __restrict__ rowp, size_t rs, Scalars* sc) {
+k_update(u64* __restrict__ C, size_t ps, int ld, int row_first, int nrows, const int* __restrict__ klist,
+         const u64* __restrict__ u, size_t us, const u64* __restrict__ rowp, size_t rs, Scalars* sc) {
     constexpr int W = L + E;
     constexpr int N = 2 * W;          // 32-bit limbs of the working width
     constexpr int LU = L + 2;
@@ -1047,7 +1186,7 @@ k_update(u64* __restrict__ C, size_t ps, int ld, int nrows, const u64* __restric
     if (sc->status != ST_RUN) return;
     if (sc->E != E) return;
     const int tid = threadIdx.x;
-    const int row0 = blockIdx.y * RT;
+    const int row0 = row_first + blockIdx.y * RT;
     if (tid < N) sA[tid] = reinterpret_cast<const u32*>(sc->A)[tid];
     if (tid < RT) {
         int i = row0 + tid;
@@ -1076,7 +1215,10 @@ k_update(u64* __restrict__ C, size_t ps, int ld, int nrows, const u64* __restric
         }
     }
     __syncthreads();
-    const int col = (blockIdx.x * 256 + tid) * CP;
+    // dense mode: CP adjacent columns per thread; list mode (klist != nullptr, CP == 1): the idx-th
+    // non-trivial column -- trivial columns are never touched
+    const int idx = (blockIdx.x * 256 + tid) * CP;
+    const int col = klist ? (idx < sc->nk ? klist[idx] : ld) : idx;
     int maxb = 0;
     if (col < ld) {
         const int t = sc->t;
@@ -1224,8 +1366,8 @@ __global__ void k_finalize(int* basis, unsigned char* inbasis, int L, u64* G, in
             if (want_se) for (int l = 0; l < LG; ++l) G[(size_t)l * n + leaving] = sc->Gq[l];
         }
         for (int l = 0; l < L; ++l) sc->D[l] = sc->Dnew[l];
-        sc->maxbits_carry = sc->maxbits_new;
         sc->bits_D = rt_bitlen_u(sc->D, L);
+        sc->maxbits_carry = max(sc->maxbits_new, sc->bits_D);     // implicit diagonals hold D
         hm->pivoted = 1; hm->q_done = sc->q; hm->p_done = sc->pg; hm->leaving_done = leaving;
     }
 }
@@ -1235,7 +1377,7 @@ __global__ void k_mirror(Scalars* sc, HostMirror* hm, int L) {
     hm->status = sc->status; hm->q = sc->q; hm->p = sc->pg; hm->leaving = sc->leaving;
     hm->t_next = rt_ctz(sc->D, L);
     hm->bits_D = sc->bits_D; hm->maxbits_carry = sc->maxbits_carry; hm->predicted = sc->predicted;
-    hm->found = sc->found; hm->sgn = sc->sgn; hm->maxbits_tmp = sc->maxbits_tmp;
+    hm->found = sc->found; hm->sgn = sc->sgn; hm->maxbits_tmp = sc->maxbits_tmp; hm->nk = sc->nk;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1261,13 +1403,14 @@ __device__ __forceinline__ void mul_full_ct(u64 (&r)[LA + LB], const u64 (&a)[LA
 
 template <int L, int LSRC, int LOUT>
 __global__ void __launch_bounds__(128)
-k_colsum1(const u64* __restrict__ C, size_t ps, int ld, int m, int rows_per_chunk,
+k_colsum1(const u64* __restrict__ C, size_t ps, int ld, int m, int rows_per_chunk, const int* __restrict__ klist,
           const u64* __restrict__ s, size_t ss, u64* __restrict__ part, const Scalars* sc) {
     constexpr int RB = 64;                 // rows whose factors are staged in shared memory at a time
     __shared__ u64 sMag[RB][LSRC];
     __shared__ int sSign[RB];
     if (sc->status != ST_RUN) return;
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int kidx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = klist ? (kidx < sc->nk ? klist[kidx] : ld) : kidx;   // list mode: non-trivial columns only
     const int r0 = 1 + blockIdx.y * rows_per_chunk;
     const int r1 = min(m + 1, r0 + rows_per_chunk);
     u64 acc[LOUT];
@@ -1340,10 +1483,13 @@ k_colsum1(const u64* __restrict__ C, size_t ps, int ld, int m, int rows_per_chun
     if (k < ld) store_planar<LOUT>(part + (size_t)blockIdx.y * LOUT * ld, (size_t)ld, (size_t)k, acc);
 }
 
-template <int LOUT>
+// `triv` (may be null): column k is D e_k implicitly, so its column sum is s_k * D, contributed by the rank
+// that owns row k (s: the factor vector, LSRC limbs, local row index k - row_lo).
+template <int LOUT, int LSRC = 1>
 __global__ void __launch_bounds__(64)
 k_colsum2(const u64* __restrict__ part, int ld, int chunks, int negate, u64* __restrict__ out,
-          Scalars* sc) {
+          Scalars* sc, const unsigned char* __restrict__ triv = nullptr, const u64* __restrict__ s = nullptr,
+          size_t ss = 0, int LD = 0) {
     if (sc->status != ST_RUN) return;
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     int bl = 0;
@@ -1351,6 +1497,27 @@ k_colsum2(const u64* __restrict__ part, int ld, int chunks, int negate, u64* __r
         u64 acc[LOUT];
 #pragma unroll
         for (int l = 0; l < LOUT; ++l) acc[l] = 0;
+        if (triv && triv[k]) {
+            int li = k - sc->row_lo;               // local carry row of the diagonal entry
+            if (li >= 1 && li <= sc->nloc) {
+                u64 x[LSRC];
+                load_planar<LSRC>(x, s, ss, (size_t)li);
+                u64 any = 0;
+#pragma unroll
+                for (int l = 0; l < LSRC; ++l) any |= x[l];
+                if (any) {
+                    // acc = x * D (x signed LSRC limbs, D positive LD limbs): limb-by-limb small products
+                    u64 xe[LOUT];
+                    u64 sg = (i64)x[LSRC - 1] < 0 ? ~0ull : 0ull;
+#pragma unroll
+                    for (int l = 0; l < LOUT; ++l) xe[l] = l < LSRC ? x[l] : sg;
+                    u64 de[LOUT];
+#pragma unroll
+                    for (int l = 0; l < LOUT; ++l) de[l] = l < LD ? sc->D[l] : 0;
+                    mul_lo<LOUT>(acc, xe, de);
+                }
+            }
+        } else
         for (int c = 0; c < chunks; ++c) {
             u64 x[LOUT];
             load_planar<LOUT>(x, part + (size_t)c * LOUT * ld, (size_t)ld, (size_t)k);
@@ -1453,7 +1620,8 @@ k_gamma_init_general(const u64* __restrict__ C, size_t ps, int ld, int m, int n,
                      const long long* __restrict__ colptr, const int* __restrict__ rowidx,
                      const long long* __restrict__ vals, const unsigned char* __restrict__ inbasis,
                      u64* __restrict__ G, int add_d2, const long long* __restrict__ wf,
-                     const long long* __restrict__ rowf, const Scalars* sc) {
+                     const long long* __restrict__ rowf, const unsigned char* __restrict__ triv,
+                     const Scalars* sc) {
     constexpr int LU = L + 2, LG = 2 * L + 6;
     __shared__ u64 sAcc[4][LG];
     int j = blockIdx.x;
@@ -1472,7 +1640,14 @@ k_gamma_init_general(const u64* __restrict__ C, size_t ps, int ld, int m, int n,
         for (int l = 0; l < LU; ++l) nu[l] = 0;
         for (long long k = k0; k < k1; ++k) {
             u64 x[L];
-            load_planar<L>(x, C, ps, (size_t)i * ld + 1 + rowidx[k]);
+            const int ck = 1 + rowidx[k];
+            if (triv && triv[ck]) {                  // implicit D e_ck
+                if (sc->row_lo + i != ck) continue;
+#pragma unroll
+                for (int l = 0; l < L; ++l) x[l] = sc->D[l];
+            } else {
+                load_planar<L>(x, C, ps, (size_t)i * ld + ck);
+            }
             mac_small<LU, L>(nu, x, vals[k]);
         }
         if ((i64)nu[LU - 1] < 0) {

@@ -138,6 +138,7 @@ extern "C" int rg_create(const rg_options* opts, rg_context** out) {
     ctx->device = opts ? opts->device : 0;
     ctx->rank = opts ? opts->rank : 0;
     ctx->world = (opts && opts->world > 0) ? opts->world : 1;
+    ctx->dense_carry_opt = opts ? opts->dense_carry : 0;
     int L = (opts && opts->initial_limbs) ? opts->initial_limbs : 2;
     if (!(L == 1 || L == 2 || L == 4 || L == 8 || L == 16)) { delete ctx; return RG_ERR_ARG; }
     ctx->L = L;
@@ -203,6 +204,7 @@ extern "C" int rg_destroy(rg_context* ctx) {
     free_dev_on(ctx->cost, ctx->stream); free_dev_on(ctx->rhs, ctx->stream); free_dev_on(ctx->basis, ctx->stream); free_dev_on(ctx->inbasis, ctx->stream);
     free_dev_on(ctx->G, ctx->stream); free_dev_on(ctx->cand, ctx->stream); free_dev_on(ctx->score, ctx->stream); free_dev_on(ctx->sc, ctx->stream); free_dev_on(ctx->svec, ctx->stream);
     free_dev_on(ctx->xsend, ctx->stream); free_dev_on(ctx->xrecv, ctx->stream);
+    free_dev_on(ctx->triv, ctx->stream); free_dev_on(ctx->klist, ctx->stream); free_dev_on(ctx->aq, ctx->stream);
     free_dev_on(ctx->Arm, ctx->stream); free_dev_on(ctx->Acm, ctx->stream); free_dev_on(ctx->dsum, ctx->stream);
     free_dev_on(ctx->wf, ctx->stream); free_dev_on(ctx->wcol, ctx->stream); free_dev_on(ctx->artf, ctx->stream);
     free_dev_on(ctx->artcost, ctx->stream); free_dev_on(ctx->rowf, ctx->stream);
@@ -253,6 +255,9 @@ extern "C" int rg_load_csc(rg_context* ctx, int32_t m, int32_t n, const int64_t*
     CK(dev_alloc(&ctx->cand, sizeof(int) * 1024, ctx->stream));
     CK(dev_alloc(&ctx->score, sizeof(double) * std::max(m, n), ctx->stream));
     CK(dev_alloc(&ctx->svec, sizeof(u64) * ctx->ld, ctx->stream));
+    CK(dev_alloc(&ctx->triv, (size_t)ctx->ld, ctx->stream));
+    CK(dev_alloc(&ctx->klist, sizeof(int) * ctx->ld, ctx->stream));
+    CK(dev_alloc(&ctx->aq, sizeof(long long) * m, ctx->stream));
     CK(dev_alloc(&ctx->wf, sizeof(long long) * n, ctx->stream));
     CK(dev_alloc(&ctx->wcol, sizeof(long long) * n, ctx->stream));
     CK(dev_alloc(&ctx->artf, sizeof(long long) * m, ctx->stream));
@@ -334,6 +339,7 @@ static int ensure_xbuf(rg_context* ctx, size_t send_words, size_t recv_words) {
     if (need <= ctx->xbytes) return RG_OK;
     CK(cudaStreamSynchronize(ctx->stream));
     free_dev_on(ctx->xsend, ctx->stream); free_dev_on(ctx->xrecv, ctx->stream);
+    free_dev_on(ctx->triv, ctx->stream); free_dev_on(ctx->klist, ctx->stream); free_dev_on(ctx->aq, ctx->stream);
     free_dev_on(ctx->Arm, ctx->stream); free_dev_on(ctx->Acm, ctx->stream); free_dev_on(ctx->dsum, ctx->stream);
     free_dev_on(ctx->wf, ctx->stream); free_dev_on(ctx->wcol, ctx->stream); free_dev_on(ctx->artf, ctx->stream);
     free_dev_on(ctx->artcost, ctx->stream); free_dev_on(ctx->rowf, ctx->stream);
@@ -360,11 +366,15 @@ static int all_gather(rg_context* ctx, const void* send, void* recv, size_t word
     return RG_OK;
 }
 
+static inline const int* klist_of(rg_context* ctx) { return ctx->list_mode ? ctx->klist : nullptr; }
+static inline const unsigned char* triv_of(rg_context* ctx) { return ctx->list_mode ? ctx->triv : nullptr; }
+
 static int sync_mirror(rg_context* ctx) {
     LAUNCH(k_mirror, 1, 1, ctx->sc, ctx->hm_dev, ctx->L);
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaGetLastError());
     ctx->t_cur = ctx->hm->t_next;
+    ctx->nk_host = ctx->hm->nk;
     return RG_OK;
 }
 
@@ -423,6 +433,16 @@ static void launch_select(rg_context* ctx) {
 
 template <int L>
 static void launch_ftran_t(rg_context* ctx, int q) {
+    if (ctx->list_mode) {
+        LAUNCH(k_scatter_col, cdiv(ctx->m, 256), 256, ctx->aq, ctx->m, ctx->nd, ctx->A.colptr, ctx->A.rowidx,
+               ctx->A.vals, ctx->Acm, ctx->ldc, q, ctx->sc);
+        LAUNCH(k_scatter_col2, cdiv(ctx->m, 256), 256, ctx->aq, ctx->nd, ctx->A.colptr, ctx->A.rowidx, ctx->A.vals,
+               q, ctx->sc);
+        LAUNCH((k_ftran_list<L>), cdiv((long long)(ctx->nloc + 1) * 32, 256), 256, ctx->carry, ctx->plane, ctx->ld,
+               ctx->nloc + 1, ctx->m, ctx->aq, ctx->klist, ctx->triv, ctx->cost, q, ctx->u, (size_t)ctx->ld,
+               ctx->sc);
+        return;
+    }
     LAUNCH((k_ftran<L>), cdiv((long long)(ctx->nloc + 1) * 32, 256), 256, ctx->carry, ctx->plane, ctx->ld,
            ctx->nloc + 1, ctx->A.colptr, ctx->A.rowidx, ctx->A.vals, ctx->cost, q, ctx->nd, ctx->u,
            (size_t)ctx->ld, ctx->sc);
@@ -471,7 +491,7 @@ static int launch_fixed_row(rg_context* ctx, int row) {
 
 template <int L>
 static void launch_copyrow_t(rg_context* ctx) {
-    LAUNCH((k_copyrow<L>), cdiv(ctx->ld, 256), 256, ctx->carry, ctx->plane, ctx->ld, ctx->rowp,
+    LAUNCH((k_copyrow<L>), cdiv(ctx->ld, 256), 256, ctx->carry, ctx->plane, ctx->ld, triv_of(ctx), ctx->rowp,
            (size_t)ctx->ld, ctx->sc);
 }
 template <int L>
@@ -491,25 +511,30 @@ template <int L>
 static int launch_work_t(rg_context* ctx) {
     constexpr int LU = L + 2, LW = 2 * L + 5;
     int rpc = cdiv(std::max(ctx->nloc, 1), ctx->work_chunks);
-    dim3 grid(cdiv(ctx->ld, 128), ctx->work_chunks);
+    const int ncols = ctx->list_mode ? ctx->nk_host + 1 : ctx->ld;
+    dim3 grid(cdiv(ncols, 128), ctx->work_chunks);
+    const u64* src = ctx->u;
     if (ctx->weighted) {
         LAUNCH((k_scale_u<L>), cdiv(ctx->nloc + 1, 256), 256, ctx->u, (size_t)ctx->ld, ctx->nloc, ctx->rowf,
                ctx->us2, (size_t)ctx->ld, ctx->sc);
-        LAUNCH((k_colsum1<L, LU + 1, LW>), grid, 128, ctx->carry, ctx->plane, ctx->ld, ctx->nloc, rpc, ctx->us2,
-               (size_t)ctx->ld, ctx->omega_part, ctx->sc);
+        LAUNCH((k_colsum1<L, LU + 1, LW>), grid, 128, ctx->carry, ctx->plane, ctx->ld, ctx->nloc, rpc,
+               klist_of(ctx), ctx->us2, (size_t)ctx->ld, ctx->omega_part, ctx->sc);
+        src = ctx->us2;
     } else {
-        LAUNCH((k_colsum1<L, LU, LW>), grid, 128, ctx->carry, ctx->plane, ctx->ld, ctx->nloc, rpc, ctx->u,
-               (size_t)ctx->ld, ctx->omega_part, ctx->sc);
+        LAUNCH((k_colsum1<L, LU, LW>), grid, 128, ctx->carry, ctx->plane, ctx->ld, ctx->nloc, rpc,
+               klist_of(ctx), ctx->u, (size_t)ctx->ld, ctx->omega_part, ctx->sc);
     }
-    if (ctx->world == 1) {
-        LAUNCH((k_colsum2<LW>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, ctx->work_chunks, 0,
-               ctx->omega, ctx->sc);
-        return RG_OK;
-    }
+    u64* first_out = ctx->world == 1 ? ctx->omega : ctx->xsend;
     size_t words = (size_t)LW * ctx->ld;
-    RG_TRY(ensure_xbuf(ctx, words, words * ctx->world));
-    LAUNCH((k_colsum2<LW>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, ctx->work_chunks, 0,
-           ctx->xsend, ctx->sc);
+    if (ctx->world > 1) RG_TRY(ensure_xbuf(ctx, words, words * ctx->world));
+    first_out = ctx->world == 1 ? ctx->omega : ctx->xsend;
+    if (ctx->weighted)
+        LAUNCH((k_colsum2<LW, LU + 1>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, ctx->work_chunks, 0,
+               first_out, ctx->sc, triv_of(ctx), src, (size_t)ctx->ld, L);
+    else
+        LAUNCH((k_colsum2<LW, LU>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, ctx->work_chunks, 0,
+               first_out, ctx->sc, triv_of(ctx), src, (size_t)ctx->ld, L);
+    if (ctx->world == 1) return RG_OK;
     RG_TRY(all_gather(ctx, ctx->xsend, ctx->xrecv, words));
     LAUNCH((k_colsum2<LW>), cdiv(ctx->ld, 64), 64, ctx->xrecv, ctx->ld, ctx->world, 0, ctx->omega, ctx->sc);
     return RG_OK;
@@ -535,9 +560,21 @@ static int pick_update_variant(int L, int E_needed) {
 template <int L, int E>
 static void launch_update_le(rg_context* ctx) {
     constexpr int CP = L <= 4 ? 2 : 1;
+    if (ctx->list_mode) {
+        // cost row: dense over all columns; rows 1..nloc: the non-trivial columns only
+        dim3 g0(cdiv(ctx->ld, 256 * CP), 1);
+        LAUNCH((k_update<L, E, CP>), g0, 256, ctx->carry, ctx->plane, ctx->ld, 0, 1, (const int*)nullptr, ctx->u,
+               (size_t)ctx->ld, ctx->rowp, (size_t)ctx->ld, ctx->sc);
+        if (ctx->nloc > 0) {
+            dim3 g1(cdiv(ctx->nk_host + 1, 256), cdiv(ctx->nloc, 32));
+            LAUNCH((k_update<L, E, 1>), g1, 256, ctx->carry, ctx->plane, ctx->ld, 1, ctx->nloc + 1,
+                   (const int*)ctx->klist, ctx->u, (size_t)ctx->ld, ctx->rowp, (size_t)ctx->ld, ctx->sc);
+        }
+        return;
+    }
     dim3 grid(cdiv(ctx->ld, 256 * CP), cdiv(ctx->nloc + 1, 32));
-    LAUNCH((k_update<L, E, CP>), grid, 256, ctx->carry, ctx->plane, ctx->ld, ctx->nloc + 1, ctx->u,
-           (size_t)ctx->ld, ctx->rowp, (size_t)ctx->ld, ctx->sc);
+    LAUNCH((k_update<L, E, CP>), grid, 256, ctx->carry, ctx->plane, ctx->ld, 0, ctx->nloc + 1, (const int*)nullptr,
+           ctx->u, (size_t)ctx->ld, ctx->rowp, (size_t)ctx->ld, ctx->sc);
 }
 template <int L>
 static void launch_update_t(rg_context* ctx, int E) {
@@ -621,9 +658,24 @@ static double g_hostprof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 static inline double now_s() {
     timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec;
 }
+// leave the active-column mode: write every implicit column out and use the dense kernels from now on
+static int switch_to_dense(rg_context* ctx) {
+    if (!ctx->list_mode) return RG_OK;
+    dim3 grid(cdiv(ctx->m + 1, 128), 64);
+    LAUNCH(k_materialise_all, grid, 128, ctx->carry, ctx->plane, ctx->ld, ctx->L, ctx->m, ctx->triv, ctx->sc);
+    LAUNCH(k_clear_trivial, cdiv(ctx->ld, 256), 256, ctx->triv, ctx->ld);
+    ctx->list_mode = false;
+    return RG_OK;
+}
+
 static int do_pivot(rg_context* ctx, int q, int fixed_row, bool want_se, bool reselect) {
     static const bool hostprof = getenv("RG_HOSTPROF") != nullptr;
     for (;;) {
+        if (ctx->list_mode) {
+            int E_need = (ctx->t_cur + 63) / 64;
+            if (ctx->nk_host + 1 > (ctx->m + 1) / 3 || pick_update_variant(ctx->L, E_need) < 0)
+                RG_TRY(switch_to_dense(ctx));
+        }
         double h0 = hostprof ? now_s() : 0;
         ctx->hm->pivoted = 0;
         const bool prof = ctx->profile;
@@ -633,6 +685,11 @@ static int do_pivot(rg_context* ctx, int q, int fixed_row, bool want_se, bool re
         double h1 = hostprof ? now_s() : 0;
         if (fixed_row < 0) RG_TRY(launch_ratio(ctx));
         else RG_TRY(launch_fixed_row(ctx, fixed_row));
+        if (ctx->list_mode) {   // the pivot row's own column stops being trivial: materialise and list it
+            LAUNCH(k_materialise_pivot_column, cdiv(std::max(ctx->nloc, 1), 256), 256, ctx->carry, ctx->plane,
+                   ctx->ld, ctx->L, ctx->triv, ctx->sc);
+            LAUNCH(k_activate_pivot_column, 1, 1, ctx->triv, ctx->klist, ctx->sc);
+        }
         double h2 = hostprof ? now_s() : 0;
         RG_TRY(launch_copyrow(ctx));
         double h3 = hostprof ? now_s() : 0;
@@ -736,6 +793,10 @@ extern "C" int rg_init_identity_basis(rg_context* ctx, const int32_t* basis, con
     }
     if (ctx->weighted)
         LAUNCH(k_init_rowf, cdiv(m, 256), 256, ctx->basis, ctx->wf, ctx->artf, ctx->rowf, m);
+    // identity carry: every column of B^-1 is trivial (active-column mode)
+    ctx->list_mode = !ctx->dense_carry_opt;
+    ctx->nk_host = 1;
+    LAUNCH(k_init_active, cdiv(ctx->ld, 256), 256, ctx->triv, ctx->klist, ctx->ld, m, ctx->list_mode ? 1 : 0);
     LAUNCH(k_set_inbasis, cdiv(m, 256), 256, ctx->inbasis, ctx->basis, m);
     ctx->identity_carry = true;
     ctx->rule_ready = false; ctx->have_column = false; ctx->selected = false;
@@ -754,18 +815,19 @@ template <int L>
 static int launch_phase_sums_t(rg_context* ctx) {
     constexpr int LU = L + 2;
     int rpc = cdiv(std::max(ctx->nloc, 1), ctx->work_chunks);
-    dim3 grid(cdiv(ctx->ld, 128), ctx->work_chunks);
-    LAUNCH((k_colsum1<L, 1, LU>), grid, 128, ctx->carry, ctx->plane, ctx->ld, ctx->nloc, rpc, ctx->svec,
-           (size_t)ctx->ld, ctx->omega_part, ctx->sc);
+    const int ncols = ctx->list_mode ? ctx->nk_host + 1 : ctx->ld;
+    dim3 grid(cdiv(ncols, 128), ctx->work_chunks);
+    LAUNCH((k_colsum1<L, 1, LU>), grid, 128, ctx->carry, ctx->plane, ctx->ld, ctx->nloc, rpc, klist_of(ctx),
+           ctx->svec, (size_t)ctx->ld, ctx->omega_part, ctx->sc);
     if (ctx->world == 1) {
-        LAUNCH((k_colsum2<LU>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, ctx->work_chunks, 1,
-               ctx->tmprow, ctx->sc);
+        LAUNCH((k_colsum2<LU, 1>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, ctx->work_chunks, 1,
+               ctx->tmprow, ctx->sc, triv_of(ctx), ctx->svec, (size_t)ctx->ld, L);
         return RG_OK;
     }
     size_t words = (size_t)LU * ctx->ld;
     RG_TRY(ensure_xbuf(ctx, words, words * ctx->world));
-    LAUNCH((k_colsum2<LU>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, ctx->work_chunks, 0,
-           ctx->xsend, ctx->sc);
+    LAUNCH((k_colsum2<LU, 1>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, ctx->work_chunks, 0,
+           ctx->xsend, ctx->sc, triv_of(ctx), ctx->svec, (size_t)ctx->ld, L);
     RG_TRY(all_gather(ctx, ctx->xsend, ctx->xrecv, words));
     LAUNCH(k_reset_tmpbits, 1, 1, ctx->sc);
     LAUNCH((k_colsum2<LU>), cdiv(ctx->ld, 64), 64, ctx->xrecv, ctx->ld, ctx->world, 1, ctx->tmprow, ctx->sc);
@@ -812,14 +874,14 @@ static int launch_gamma_general_t(rg_context* ctx) {
     if (ctx->world == 1) {
         LAUNCH((k_gamma_init_general<L>), ctx->n, 128, ctx->carry, ctx->plane, ctx->ld, ctx->nloc, ctx->n,
                ctx->A.colptr, ctx->A.rowidx, ctx->A.vals, ctx->inbasis, ctx->G, 1, ctx->weighted ? ctx->wf : nullptr,
-               ctx->weighted ? ctx->rowf : nullptr, ctx->sc);
+               ctx->weighted ? ctx->rowf : nullptr, triv_of(ctx), ctx->sc);
         return RG_OK;
     }
     size_t words = (size_t)LG * ctx->n;
     RG_TRY(ensure_xbuf(ctx, words, words * ctx->world));
     LAUNCH((k_gamma_init_general<L>), ctx->n, 128, ctx->carry, ctx->plane, ctx->ld, ctx->nloc, ctx->n,
            ctx->A.colptr, ctx->A.rowidx, ctx->A.vals, ctx->inbasis, ctx->xsend, ctx->rank == 0 ? 1 : 0,
-           ctx->weighted ? ctx->wf : nullptr, ctx->weighted ? ctx->rowf : nullptr, ctx->sc);
+           ctx->weighted ? ctx->wf : nullptr, ctx->weighted ? ctx->rowf : nullptr, triv_of(ctx), ctx->sc);
     RG_TRY(all_gather(ctx, ctx->xsend, ctx->xrecv, words));
     LAUNCH((k_colsum2<LG>), cdiv(ctx->n, 64), 64, ctx->xrecv, ctx->n, ctx->world, 0, ctx->G, ctx->sc);
     return RG_OK;

@@ -160,7 +160,7 @@ def nccl_unique_id():
 
 
 def solve_relaxation(problem, rule="steepest_edge", fused=True, initial_limbs=0, device=0,
-                     max_pivots=0, profile=False, rank=0, world=1, nccl_id=None):
+                     max_pivots=0, profile=False, rank=0, world=1, nccl_id=None, dense_carry=False):
     """Solves `problem`.  world > 1: row-sharded over `world` GPUs (one process per GPU; every rank
     passes the same problem and the same `nccl_id` and receives the same result)."""
     lib = _lib.load()
@@ -171,7 +171,8 @@ def solve_relaxation(problem, rule="steepest_edge", fused=True, initial_limbs=0,
         idbuf = C.create_string_buffer(bytes(nccl_id), 128)
     opts = _lib.rh_options(device=device, initial_limbs=initial_limbs, rule=RULES[rule],
                            fused=1 if fused else 0, max_pivots=max_pivots,
-                           profile=1 if profile else 0, rank=rank, world=world, reserved=0,
+                           profile=1 if profile else 0, rank=rank, world=world,
+                           dense_carry=1 if dense_carry else 0,
                            nccl_unique_id=C.cast(idbuf, C.c_void_p) if idbuf is not None else None)
     handle = C.c_void_p()
     import os, time

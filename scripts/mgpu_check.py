@@ -48,15 +48,15 @@ def main():
     for name, prob, rules, limbs in cases:
         for rule in rules:
             ref = fo.solve_problem(prob, rule)
-            for fused in (True, False):
+            for fused, dense_carry in ((True, False), (True, True), (False, False)):
                 nid = share_id(rank)
                 g = relp_b200.solve_relaxation(prob, rule=rule, fused=fused, initial_limbs=limbs, device=local,
-                                               rank=rank, world=world, nccl_id=nid)
+                                               rank=rank, world=world, nccl_id=nid, dense_carry=dense_carry)
                 good = (g.status == ref.status and g.trace == ref.trace and
                         (ref.status != "optimal" or (g.objective == ref.objective and g.bfs == ref.bfs)))
                 ok = ok and good
                 if rank == 0:
-                    print(f"{name:22s} {rule:18s} fused={fused} world={world} pivots={g.pivots} "
+                    print(f"{name:22s} {rule:18s} fused={fused} dense={dense_carry} world={world} pivots={g.pivots} "
                           f"limbs={g.stats['limbs']} {'OK' if good else 'MISMATCH'}", flush=True)
     flag = torch.tensor([1 if ok else 0])
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)

@@ -22,9 +22,9 @@ def check_rational(provider, rules=RULES, modes=(True, False), constant=F(0), ex
     sp = scaled_from_provider(provider)
     for rule in rules:
         ref = fo.solve_provider(provider, rule)
-        for fused in modes:
-            g = relp_b200.solve_relaxation(sp.problem, rule=rule, fused=fused)
-            tag = f"rule={rule} fused={fused}"
+        for fused, dense_carry in [(f, d) for f in modes for d in ((False, True) if f else (False,))]:
+            g = relp_b200.solve_relaxation(sp.problem, rule=rule, fused=fused, dense_carry=dense_carry)
+            tag = f"rule={rule} fused={fused} dense_carry={dense_carry}"
             assert g.status == ref.status, tag
             assert g.trace == ref.trace, tag
             if ref.status == "optimal":
