@@ -95,6 +95,9 @@ struct rg_context {
     // D * e_k on rows 1..m; trivial columns are never read or written, the others are listed in klist
     unsigned char* triv = nullptr;   // ld flags
     int* klist = nullptr;            // ld column indices
+    int* kpos = nullptr;             // ld: position of a column in klist
+    int list_chunks = 0;             // row chunks of the column sums in list mode
+    int list_pcols = 0;              // column slots of the list-mode partial sums
     long long* aq = nullptr;         // m: the entering column scattered densely (list-mode FTRAN)
     bool list_mode = false;
     int nk_host = 1;                 // upper bound of sc->nk known to the host

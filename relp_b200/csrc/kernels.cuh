@@ -852,10 +852,11 @@ k_ftran(const u64* __restrict__ C, size_t ps, int ld, int nrows, const long long
 // columns are never read or written; the others are listed in klist (column 0, the right-hand side,
 // is always listed).  Row 0 (the cost row) is maintained densely for all columns.
 // ---------------------------------------------------------------------------------------------
-__global__ void k_init_active(unsigned char* triv, int* klist, int ld, int m, int all_trivial) {
+__global__ void k_init_active(unsigned char* triv, int* klist, int* kpos, int ld, int m, int all_trivial) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= ld) return;
     triv[k] = (all_trivial && k >= 1 && k <= m) ? 1 : 0;
+    kpos[k] = 0;
     if (k == 0) klist[0] = 0;
 }
 // before the pivot row is staged: materialise the pivot row's own column if it is still trivial
@@ -870,11 +871,11 @@ k_materialise_pivot_column(u64* __restrict__ C, size_t ps, int ld, int L, const 
     bool diag = sc->row_lo + li == k;
     for (int l = 0; l < L; ++l) C[(size_t)l * ps + (size_t)li * ld + k] = diag ? sc->D[l] : 0ull;
 }
-__global__ void k_activate_pivot_column(unsigned char* triv, int* klist, Scalars* sc) {
+__global__ void k_activate_pivot_column(unsigned char* triv, int* klist, int* kpos, Scalars* sc) {
     if (threadIdx.x || blockIdx.x) return;
     if (sc->status != ST_RUN) return;
     const int k = sc->pg;
-    if (k >= 1 && triv[k]) { triv[k] = 0; klist[sc->nk] = k; sc->nk = sc->nk + 1; }
+    if (k >= 1 && triv[k]) { triv[k] = 0; klist[sc->nk] = k; kpos[k] = sc->nk; sc->nk = sc->nk + 1; }
 }
 // leave list mode: materialise every trivial column (thread = column, loops the local rows)
 __global__ void __launch_bounds__(128)
@@ -910,6 +911,58 @@ __global__ void k_scatter_col2(long long* __restrict__ aq, int nd, const long lo
     long long k = colptr[q] + blockIdx.x * blockDim.x + threadIdx.x;
     if (k < colptr[q + 1]) aq[rowidx[k]] = vals[k];
 }
+// cost-row entry of the pivot column: u_0 = c_q D + sum_k aq[k-1] C[0][k] over ALL columns (one block)
+template <int L>
+__global__ void __launch_bounds__(1024)
+k_ftran_row0(const u64* __restrict__ C, size_t ps, int m, const long long* __restrict__ aq,
+             const long long* __restrict__ cost, int qarg, u64* __restrict__ u, size_t us, Scalars* sc) {
+    constexpr int LU = L + 2;
+    __shared__ u64 sAcc[32][LU];
+    if (sc->status != ST_RUN) return;
+    int q = qarg >= 0 ? qarg : sc->q;
+    u64 acc[LU];
+#pragma unroll
+    for (int l = 0; l < LU; ++l) acc[l] = 0;
+    for (int k = 1 + threadIdx.x; k <= m; k += blockDim.x) {
+        long long a = aq[k - 1];
+        if (!a) continue;
+        u64 x[L];
+        load_planar<L>(x, C, ps, (size_t)k);
+        mac_small<LU, L>(acc, x, a);
+    }
+    if (threadIdx.x == 0) {
+        long long c = cost[q];
+        if (c) {
+            u64 d[L];
+#pragma unroll
+            for (int l = 0; l < L; ++l) d[l] = sc->D[l];
+            mac_small<LU, L>(acc, d, c);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        u64 other[LU];
+#pragma unroll
+        for (int l = 0; l < LU; ++l) other[l] = __shfl_down_sync(0xffffffffu, acc[l], o);
+        add_n<LU>(acc, other);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+#pragma unroll
+        for (int l = 0; l < LU; ++l) sAcc[warp][l] = acc[l];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (blockDim.x >> 5); ++w) {
+            u64 other[LU];
+#pragma unroll
+            for (int l = 0; l < LU; ++l) other[l] = sAcc[w][l];
+            add_n<LU>(acc, other);
+        }
+        store_planar<LU>(u, us, (size_t)0, acc);
+        atomicMax(&sc->maxbits_u, bitlen_signed<LU>(acc));
+    }
+}
 // list-mode FTRAN: u_i = sum_{k in klist, k >= 1} aq[k-1] C[i][k]  +  [column i trivial] D aq[i-1]
 // (row 0 is dense: its warp walks all columns).  One warp per local carry row.
 template <int L>
@@ -927,24 +980,8 @@ k_ftran_list(const u64* __restrict__ C, size_t ps, int ld, int nrows, int m, con
     u64 acc[LU];
 #pragma unroll
     for (int l = 0; l < LU; ++l) acc[l] = 0;
-    if (warp == 0) {
-        for (int k = 1 + lane; k <= m; k += 32) {
-            long long a = aq[k - 1];
-            if (!a) continue;
-            u64 x[L];
-            load_planar<L>(x, C, ps, row + k);
-            mac_small<LU, L>(acc, x, a);
-        }
-        if (lane == 0) {
-            long long c = cost[q];
-            if (c) {
-                u64 d[L];
-#pragma unroll
-                for (int l = 0; l < L; ++l) d[l] = sc->D[l];
-                mac_small<LU, L>(acc, d, c);
-            }
-        }
-    } else {
+    if (warp == 0) return;      // the dense cost row is handled by k_ftran_row0
+    {
         const int nk = sc->nk;
         for (int t = 1 + lane; t < nk; t += 32) {        // klist[0] is column 0 (b): not part of B^-1
             int k = klist[t];
@@ -1404,7 +1441,7 @@ __device__ __forceinline__ void mul_full_ct(u64 (&r)[LA + LB], const u64 (&a)[LA
 template <int L, int LSRC, int LOUT>
 __global__ void __launch_bounds__(128)
 k_colsum1(const u64* __restrict__ C, size_t ps, int ld, int m, int rows_per_chunk, const int* __restrict__ klist,
-          const u64* __restrict__ s, size_t ss, u64* __restrict__ part, const Scalars* sc) {
+          const u64* __restrict__ s, size_t ss, u64* __restrict__ part, int pcols, const Scalars* sc) {
     constexpr int RB = 64;                 // rows whose factors are staged in shared memory at a time
     __shared__ u64 sMag[RB][LSRC];
     __shared__ int sSign[RB];
@@ -1480,7 +1517,8 @@ k_colsum1(const u64* __restrict__ C, size_t ps, int ld, int m, int rows_per_chun
             }
         }
     }
-    if (k < ld) store_planar<LOUT>(part + (size_t)blockIdx.y * LOUT * ld, (size_t)ld, (size_t)k, acc);
+    // partial sums are indexed by column (dense mode) or by list position (list mode), row stride pcols
+    if (k < ld) store_planar<LOUT>(part + (size_t)blockIdx.y * LOUT * pcols, (size_t)pcols, (size_t)(klist ? kidx : k), acc);
 }
 
 // `triv` (may be null): column k is D e_k implicitly, so its column sum is s_k * D, contributed by the rank
@@ -1489,7 +1527,7 @@ template <int LOUT, int LSRC = 1>
 __global__ void __launch_bounds__(64)
 k_colsum2(const u64* __restrict__ part, int ld, int chunks, int negate, u64* __restrict__ out,
           Scalars* sc, const unsigned char* __restrict__ triv = nullptr, const u64* __restrict__ s = nullptr,
-          size_t ss = 0, int LD = 0) {
+          size_t ss = 0, int LD = 0, const int* __restrict__ kpos = nullptr, int pcols = 0) {
     if (sc->status != ST_RUN) return;
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     int bl = 0;
@@ -1517,11 +1555,14 @@ k_colsum2(const u64* __restrict__ part, int ld, int chunks, int negate, u64* __r
                     mul_lo<LOUT>(acc, xe, de);
                 }
             }
-        } else
-        for (int c = 0; c < chunks; ++c) {
-            u64 x[LOUT];
-            load_planar<LOUT>(x, part + (size_t)c * LOUT * ld, (size_t)ld, (size_t)k);
-            add_n<LOUT>(acc, x);
+        } else {
+            const int pc = kpos ? pcols : ld;             // list mode: partials live at the list position
+            const size_t idx = kpos ? (size_t)kpos[k] : (size_t)k;
+            for (int c = 0; c < chunks; ++c) {
+                u64 x[LOUT];
+                load_planar<LOUT>(x, part + (size_t)c * LOUT * pc, (size_t)pc, idx);
+                add_n<LOUT>(acc, x);
+            }
         }
         if (negate) {
             u64 c = 1;

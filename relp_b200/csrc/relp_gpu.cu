@@ -112,7 +112,11 @@ static int alloc_width_buffers(rg_context* ctx, int L) {
     CK(dev_alloc(&ctx->u, sizeof(u64) * LU_of(L) * ld, ctx->stream));
     CK(dev_alloc(&ctx->rowp, sizeof(u64) * L * ld, ctx->stream));
     CK(dev_alloc(&ctx->omega, sizeof(u64) * LW_of(L) * ld, ctx->stream));
-    CK(dev_alloc(&ctx->omega_part, sizeof(u64) * ctx->work_chunks * LW_of(L) * ld, ctx->stream));
+    {
+        size_t dense_slots = (size_t)ctx->work_chunks * ld;
+        size_t list_slots = (size_t)ctx->list_chunks * ctx->list_pcols;
+        CK(dev_alloc(&ctx->omega_part, sizeof(u64) * LW_of(L) * std::max(dense_slots, list_slots), ctx->stream));
+    }
     CK(dev_alloc(&ctx->tmprow, sizeof(u64) * LU_of(L) * ld, ctx->stream));
     CK(dev_alloc(&ctx->us2, sizeof(u64) * (LU_of(L) + 1) * ld, ctx->stream));
     if (ctx->nd > 0)
@@ -204,7 +208,7 @@ extern "C" int rg_destroy(rg_context* ctx) {
     free_dev_on(ctx->cost, ctx->stream); free_dev_on(ctx->rhs, ctx->stream); free_dev_on(ctx->basis, ctx->stream); free_dev_on(ctx->inbasis, ctx->stream);
     free_dev_on(ctx->G, ctx->stream); free_dev_on(ctx->cand, ctx->stream); free_dev_on(ctx->score, ctx->stream); free_dev_on(ctx->sc, ctx->stream); free_dev_on(ctx->svec, ctx->stream);
     free_dev_on(ctx->xsend, ctx->stream); free_dev_on(ctx->xrecv, ctx->stream);
-    free_dev_on(ctx->triv, ctx->stream); free_dev_on(ctx->klist, ctx->stream); free_dev_on(ctx->aq, ctx->stream);
+    free_dev_on(ctx->triv, ctx->stream); free_dev_on(ctx->klist, ctx->stream); free_dev_on(ctx->kpos, ctx->stream); free_dev_on(ctx->aq, ctx->stream);
     free_dev_on(ctx->Arm, ctx->stream); free_dev_on(ctx->Acm, ctx->stream); free_dev_on(ctx->dsum, ctx->stream);
     free_dev_on(ctx->wf, ctx->stream); free_dev_on(ctx->wcol, ctx->stream); free_dev_on(ctx->artf, ctx->stream);
     free_dev_on(ctx->artcost, ctx->stream); free_dev_on(ctx->rowf, ctx->stream);
@@ -257,6 +261,7 @@ extern "C" int rg_load_csc(rg_context* ctx, int32_t m, int32_t n, const int64_t*
     CK(dev_alloc(&ctx->svec, sizeof(u64) * ctx->ld, ctx->stream));
     CK(dev_alloc(&ctx->triv, (size_t)ctx->ld, ctx->stream));
     CK(dev_alloc(&ctx->klist, sizeof(int) * ctx->ld, ctx->stream));
+    CK(dev_alloc(&ctx->kpos, sizeof(int) * ctx->ld, ctx->stream));
     CK(dev_alloc(&ctx->aq, sizeof(long long) * m, ctx->stream));
     CK(dev_alloc(&ctx->wf, sizeof(long long) * n, ctx->stream));
     CK(dev_alloc(&ctx->wcol, sizeof(long long) * n, ctx->stream));
@@ -264,6 +269,8 @@ extern "C" int rg_load_csc(rg_context* ctx, int32_t m, int32_t n, const int64_t*
     CK(dev_alloc(&ctx->artcost, sizeof(long long) * m, ctx->stream));
     CK(dev_alloc(&ctx->rowf, sizeof(long long) * m, ctx->stream));
     ctx->work_chunks = std::max(1, std::min(16, cdiv(std::max(ctx->nloc, 1), 256)));
+    ctx->list_chunks = std::max(1, cdiv(std::max(ctx->nloc, 1), 64));        // 64 rows per chunk in list mode
+    ctx->list_pcols = ((m + 1) / 3 + 2 + 127) / 128 * 128;                    // the list never exceeds (m+1)/3 + 1
     CK(dev_alloc(&ctx->carry, sizeof(u64) * ctx->L * ctx->plane, ctx->stream));
     CK(dev_alloc(&ctx->G, sizeof(u64) * LG_of(ctx->L) * n, ctx->stream));
     CK(cudaMemsetAsync(ctx->G, 0, sizeof(u64) * LG_of(ctx->L) * n, ctx->stream));
@@ -339,7 +346,7 @@ static int ensure_xbuf(rg_context* ctx, size_t send_words, size_t recv_words) {
     if (need <= ctx->xbytes) return RG_OK;
     CK(cudaStreamSynchronize(ctx->stream));
     free_dev_on(ctx->xsend, ctx->stream); free_dev_on(ctx->xrecv, ctx->stream);
-    free_dev_on(ctx->triv, ctx->stream); free_dev_on(ctx->klist, ctx->stream); free_dev_on(ctx->aq, ctx->stream);
+    free_dev_on(ctx->triv, ctx->stream); free_dev_on(ctx->klist, ctx->stream); free_dev_on(ctx->kpos, ctx->stream); free_dev_on(ctx->aq, ctx->stream);
     free_dev_on(ctx->Arm, ctx->stream); free_dev_on(ctx->Acm, ctx->stream); free_dev_on(ctx->dsum, ctx->stream);
     free_dev_on(ctx->wf, ctx->stream); free_dev_on(ctx->wcol, ctx->stream); free_dev_on(ctx->artf, ctx->stream);
     free_dev_on(ctx->artcost, ctx->stream); free_dev_on(ctx->rowf, ctx->stream);
@@ -438,6 +445,8 @@ static void launch_ftran_t(rg_context* ctx, int q) {
                ctx->A.vals, ctx->Acm, ctx->ldc, q, ctx->sc);
         LAUNCH(k_scatter_col2, cdiv(ctx->m, 256), 256, ctx->aq, ctx->nd, ctx->A.colptr, ctx->A.rowidx, ctx->A.vals,
                q, ctx->sc);
+        LAUNCH((k_ftran_row0<L>), 1, 1024, ctx->carry, ctx->plane, ctx->m, ctx->aq, ctx->cost, q, ctx->u,
+               (size_t)ctx->ld, ctx->sc);
         LAUNCH((k_ftran_list<L>), cdiv((long long)(ctx->nloc + 1) * 32, 256), 256, ctx->carry, ctx->plane, ctx->ld,
                ctx->nloc + 1, ctx->m, ctx->aq, ctx->klist, ctx->triv, ctx->cost, q, ctx->u, (size_t)ctx->ld,
                ctx->sc);
@@ -507,33 +516,45 @@ static int launch_copyrow(rg_context* ctx) {
     return RG_OK;
 }
 
+// column-sum geometry of the current carry mode
+struct ColsumGeom { int chunks, rpc, pcols, ncols; const int* klist; const int* kpos; const unsigned char* triv; };
+static ColsumGeom colsum_geom(rg_context* ctx) {
+    ColsumGeom g;
+    if (ctx->list_mode) {
+        g.chunks = ctx->list_chunks; g.pcols = ctx->list_pcols; g.ncols = ctx->nk_host + 1;
+        g.klist = ctx->klist; g.kpos = ctx->kpos; g.triv = ctx->triv;
+    } else {
+        g.chunks = ctx->work_chunks; g.pcols = ctx->ld; g.ncols = ctx->ld;
+        g.klist = nullptr; g.kpos = nullptr; g.triv = nullptr;
+    }
+    g.rpc = cdiv(std::max(ctx->nloc, 1), g.chunks);
+    return g;
+}
 template <int L>
 static int launch_work_t(rg_context* ctx) {
     constexpr int LU = L + 2, LW = 2 * L + 5;
-    int rpc = cdiv(std::max(ctx->nloc, 1), ctx->work_chunks);
-    const int ncols = ctx->list_mode ? ctx->nk_host + 1 : ctx->ld;
-    dim3 grid(cdiv(ncols, 128), ctx->work_chunks);
+    const ColsumGeom g = colsum_geom(ctx);
+    dim3 grid(cdiv(g.ncols, 128), g.chunks);
     const u64* src = ctx->u;
     if (ctx->weighted) {
         LAUNCH((k_scale_u<L>), cdiv(ctx->nloc + 1, 256), 256, ctx->u, (size_t)ctx->ld, ctx->nloc, ctx->rowf,
                ctx->us2, (size_t)ctx->ld, ctx->sc);
-        LAUNCH((k_colsum1<L, LU + 1, LW>), grid, 128, ctx->carry, ctx->plane, ctx->ld, ctx->nloc, rpc,
-               klist_of(ctx), ctx->us2, (size_t)ctx->ld, ctx->omega_part, ctx->sc);
+        LAUNCH((k_colsum1<L, LU + 1, LW>), grid, 128, ctx->carry, ctx->plane, ctx->ld, ctx->nloc, g.rpc,
+               g.klist, ctx->us2, (size_t)ctx->ld, ctx->omega_part, g.pcols, ctx->sc);
         src = ctx->us2;
     } else {
-        LAUNCH((k_colsum1<L, LU, LW>), grid, 128, ctx->carry, ctx->plane, ctx->ld, ctx->nloc, rpc,
-               klist_of(ctx), ctx->u, (size_t)ctx->ld, ctx->omega_part, ctx->sc);
+        LAUNCH((k_colsum1<L, LU, LW>), grid, 128, ctx->carry, ctx->plane, ctx->ld, ctx->nloc, g.rpc,
+               g.klist, ctx->u, (size_t)ctx->ld, ctx->omega_part, g.pcols, ctx->sc);
     }
-    u64* first_out = ctx->world == 1 ? ctx->omega : ctx->xsend;
     size_t words = (size_t)LW * ctx->ld;
     if (ctx->world > 1) RG_TRY(ensure_xbuf(ctx, words, words * ctx->world));
-    first_out = ctx->world == 1 ? ctx->omega : ctx->xsend;
+    u64* first_out = ctx->world == 1 ? ctx->omega : ctx->xsend;
     if (ctx->weighted)
-        LAUNCH((k_colsum2<LW, LU + 1>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, ctx->work_chunks, 0,
-               first_out, ctx->sc, triv_of(ctx), src, (size_t)ctx->ld, L);
+        LAUNCH((k_colsum2<LW, LU + 1>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, g.chunks, 0,
+               first_out, ctx->sc, g.triv, src, (size_t)ctx->ld, L, g.kpos, g.pcols);
     else
-        LAUNCH((k_colsum2<LW, LU>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, ctx->work_chunks, 0,
-               first_out, ctx->sc, triv_of(ctx), src, (size_t)ctx->ld, L);
+        LAUNCH((k_colsum2<LW, LU>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, g.chunks, 0,
+               first_out, ctx->sc, g.triv, src, (size_t)ctx->ld, L, g.kpos, g.pcols);
     if (ctx->world == 1) return RG_OK;
     RG_TRY(all_gather(ctx, ctx->xsend, ctx->xrecv, words));
     LAUNCH((k_colsum2<LW>), cdiv(ctx->ld, 64), 64, ctx->xrecv, ctx->ld, ctx->world, 0, ctx->omega, ctx->sc);
@@ -688,7 +709,7 @@ static int do_pivot(rg_context* ctx, int q, int fixed_row, bool want_se, bool re
         if (ctx->list_mode) {   // the pivot row's own column stops being trivial: materialise and list it
             LAUNCH(k_materialise_pivot_column, cdiv(std::max(ctx->nloc, 1), 256), 256, ctx->carry, ctx->plane,
                    ctx->ld, ctx->L, ctx->triv, ctx->sc);
-            LAUNCH(k_activate_pivot_column, 1, 1, ctx->triv, ctx->klist, ctx->sc);
+            LAUNCH(k_activate_pivot_column, 1, 1, ctx->triv, ctx->klist, ctx->kpos, ctx->sc);
         }
         double h2 = hostprof ? now_s() : 0;
         RG_TRY(launch_copyrow(ctx));
@@ -796,7 +817,8 @@ extern "C" int rg_init_identity_basis(rg_context* ctx, const int32_t* basis, con
     // identity carry: every column of B^-1 is trivial (active-column mode)
     ctx->list_mode = !ctx->dense_carry_opt;
     ctx->nk_host = 1;
-    LAUNCH(k_init_active, cdiv(ctx->ld, 256), 256, ctx->triv, ctx->klist, ctx->ld, m, ctx->list_mode ? 1 : 0);
+    LAUNCH(k_init_active, cdiv(ctx->ld, 256), 256, ctx->triv, ctx->klist, ctx->kpos, ctx->ld, m,
+           ctx->list_mode ? 1 : 0);
     LAUNCH(k_set_inbasis, cdiv(m, 256), 256, ctx->inbasis, ctx->basis, m);
     ctx->identity_carry = true;
     ctx->rule_ready = false; ctx->have_column = false; ctx->selected = false;
@@ -814,20 +836,19 @@ extern "C" int rg_init_identity_basis(rg_context* ctx, const int32_t* basis, con
 template <int L>
 static int launch_phase_sums_t(rg_context* ctx) {
     constexpr int LU = L + 2;
-    int rpc = cdiv(std::max(ctx->nloc, 1), ctx->work_chunks);
-    const int ncols = ctx->list_mode ? ctx->nk_host + 1 : ctx->ld;
-    dim3 grid(cdiv(ncols, 128), ctx->work_chunks);
-    LAUNCH((k_colsum1<L, 1, LU>), grid, 128, ctx->carry, ctx->plane, ctx->ld, ctx->nloc, rpc, klist_of(ctx),
-           ctx->svec, (size_t)ctx->ld, ctx->omega_part, ctx->sc);
+    const ColsumGeom g = colsum_geom(ctx);
+    dim3 grid(cdiv(g.ncols, 128), g.chunks);
+    LAUNCH((k_colsum1<L, 1, LU>), grid, 128, ctx->carry, ctx->plane, ctx->ld, ctx->nloc, g.rpc, g.klist,
+           ctx->svec, (size_t)ctx->ld, ctx->omega_part, g.pcols, ctx->sc);
     if (ctx->world == 1) {
-        LAUNCH((k_colsum2<LU, 1>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, ctx->work_chunks, 1,
-               ctx->tmprow, ctx->sc, triv_of(ctx), ctx->svec, (size_t)ctx->ld, L);
+        LAUNCH((k_colsum2<LU, 1>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, g.chunks, 1,
+               ctx->tmprow, ctx->sc, g.triv, ctx->svec, (size_t)ctx->ld, L, g.kpos, g.pcols);
         return RG_OK;
     }
     size_t words = (size_t)LU * ctx->ld;
     RG_TRY(ensure_xbuf(ctx, words, words * ctx->world));
-    LAUNCH((k_colsum2<LU, 1>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, ctx->work_chunks, 0,
-           ctx->xsend, ctx->sc, triv_of(ctx), ctx->svec, (size_t)ctx->ld, L);
+    LAUNCH((k_colsum2<LU, 1>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, g.chunks, 0,
+           ctx->xsend, ctx->sc, g.triv, ctx->svec, (size_t)ctx->ld, L, g.kpos, g.pcols);
     RG_TRY(all_gather(ctx, ctx->xsend, ctx->xrecv, words));
     LAUNCH(k_reset_tmpbits, 1, 1, ctx->sc);
     LAUNCH((k_colsum2<LU>), cdiv(ctx->ld, 64), 64, ctx->xrecv, ctx->ld, ctx->world, 1, ctx->tmprow, ctx->sc);
