@@ -250,7 +250,8 @@ k_densedot1(const u64* __restrict__ vec, size_t vs, int m, int nd, const signed 
     constexpr int NV = 2 * LV;
     constexpr int G = (NV + 1 + 15) / 16;          // word groups
     constexpr int NW = G * 16;                     // words per staged row (zero padded)
-    constexpr int RB = 16;                         // rows staged per shared-memory tile
+    constexpr int RB = 64;                         // rows staged per shared-memory tile
+    constexpr int RG = 16;                         // rows whose coefficients are prefetched together
     __shared__ __align__(16) u32 sv[RB][NW];
     __shared__ int nzrow[RB];
     if (sc->status != ST_RUN) return;
@@ -269,31 +270,43 @@ k_densedot1(const u64* __restrict__ vec, size_t vs, int m, int nd, const signed 
         __syncthreads();
         if (tid < RB) nzrow[tid] = 0;
         __syncthreads();
-        for (int t = tid; t < RB * NW / 2; t += nthreads) {     // two words (one u64 limb) per step
-            int r = t / (NW / 2), l = t % (NW / 2);
+        for (int t = tid; t < RB * (lveff + 1); t += nthreads) {     // one u64 limb (two words) per step
+            int r = t / (lveff + 1), l = t % (lveff + 1);
             bool in = base + r < r1;
             u64 v = 0;
             if (in) {
                 if (l < lveff) v = vec[(size_t)l * vs + 1 + base + r];
-                else if (l == lveff) v = ((i64)vec[(size_t)(LV - 1) * vs + 1 + base + r] < 0) ? 0xffffffffull : 0ull;
+                else v = ((i64)vec[(size_t)(LV - 1) * vs + 1 + base + r] < 0) ? 0xffffffffull : 0ull;
             }
             sv[r][2 * l] = (u32)v; sv[r][2 * l + 1] = (u32)(v >> 32);
             if (v) nzrow[r] = 1;
         }
+        // words beyond the sign word of this group's 16-word window must read as zero
+        for (int t = tid; t < RB * (NW / 2 - (lveff + 1)); t += nthreads) {
+            int r = t / (NW / 2 - (lveff + 1)), l = lveff + 1 + t % (NW / 2 - (lveff + 1));
+            sv[r][2 * l] = 0; sv[r][2 * l + 1] = 0;
+        }
         __syncthreads();
         if (!active) continue;
-#pragma unroll 4
-        for (int r = 0; r < RB; ++r) {
-            if (!nzrow[r]) continue;               // zero vector entry: contributes nothing (bias included)
-            const u32 a = (u32)((int)Arm[(size_t)(base + r) * ldr + j] + 128);
-            const uint4* row4 = reinterpret_cast<const uint4*>(&sv[r][16 * g]);
+        for (int rg = 0; rg < RB; rg += RG) {
+            if (base + rg >= r1) break;
+            // the 16 coefficients of this column in rows base+rg .. +15: one 128-bit load (row-blocked A)
+            const int4 pk = *reinterpret_cast<const int4*>(Arm + ((size_t)((base + rg) >> 4) * ldr + j) * 16);
+            signed char cb[16];
+            memcpy(cb, &pk, 16);
 #pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-                uint4 x = row4[q4];
-                acc[4 * q4 + 0] += (unsigned long long)a * x.x;
-                acc[4 * q4 + 1] += (unsigned long long)a * x.y;
-                acc[4 * q4 + 2] += (unsigned long long)a * x.z;
-                acc[4 * q4 + 3] += (unsigned long long)a * x.w;
+            for (int r = 0; r < RG; ++r) {
+                if (!nzrow[rg + r]) continue;             // zero vector entry (warp-uniform; also rows past the end)
+                const u32 a = (u32)((int)cb[r] + 128);
+                const uint4* row4 = reinterpret_cast<const uint4*>(&sv[rg + r][16 * g]);
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    uint4 x = row4[q4];
+                    acc[4 * q4 + 0] += (unsigned long long)a * x.x;
+                    acc[4 * q4 + 1] += (unsigned long long)a * x.y;
+                    acc[4 * q4 + 2] += (unsigned long long)a * x.z;
+                    acc[4 * q4 + 3] += (unsigned long long)a * x.w;
+                }
             }
         }
     }
@@ -357,15 +370,20 @@ k_densedot2(const unsigned long long* __restrict__ part, size_t pstride, int sli
     store_planar<LO>(out, (size_t)n, (size_t)j, res);
 }
 
-// column-major [nd][ldc] -> row-major [m][ldr]
+// column-major [nd][ldc] -> row-blocked [ceil(m/16)][ldr][16]: the 16 coefficients of column j in rows
+// 16b..16b+15 are contiguous, so a thread that owns column j reads 16 rows with one 128-bit load and a
+// warp reads 512 contiguous bytes
 __global__ void k_transpose_i8(const signed char* __restrict__ Acm, size_t ldc, signed char* __restrict__ Arm,
                                size_t ldr, int m, int nd) {
-    __shared__ signed char tile[32][33];
-    int j = blockIdx.x * 32 + threadIdx.y, i = blockIdx.y * 32 + threadIdx.x;
-    tile[threadIdx.y][threadIdx.x] = (j < nd && i < m) ? Acm[(size_t)j * ldc + i] : 0;
-    __syncthreads();
-    int jo = blockIdx.x * 32 + threadIdx.x, io = blockIdx.y * 32 + threadIdx.y;
-    if (jo < nd && io < m) Arm[(size_t)io * ldr + jo] = tile[threadIdx.x][threadIdx.y];
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    int b = blockIdx.y;
+    if (j >= nd) return;
+    signed char v[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = (16 * b + r < m) ? Acm[(size_t)j * ldc + 16 * b + r] : 0;
+    int4 out;
+    memcpy(&out, v, 16);
+    *reinterpret_cast<int4*>(Arm + ((size_t)b * ldr + j) * 16) = out;
 }
 
 // FTRAN of a dense column q (column-major copy): warp per carry row, lanes over the rows of a_q
@@ -440,7 +458,7 @@ __global__ void k_gamma_init_identity_dense(int nd, int n, int m, const signed c
     u64 acc = 0;
     if (!inbasis[j]) {
         acc = 1;
-        for (int i = 0; i < m; ++i) { long long a = Arm[(size_t)i * ldr + j]; acc += (u64)(a * a); }
+        for (int i = 0; i < m; ++i) { long long a = Arm[((size_t)(i >> 4) * ldr + j) * 16 + (i & 15)]; acc += (u64)(a * a); }
     }
     for (int l = 0; l < LG; ++l) G[(size_t)l * n + j] = l == 0 ? acc : 0;
 }

@@ -294,13 +294,14 @@ extern "C" int rg_load_dense_i8(rg_context* ctx, int32_t nd, const int8_t* colma
     ctx->ldc = ((size_t)m + 15) / 16 * 16;
     ctx->ldr = ((size_t)nd + 15) / 16 * 16;
     CK(dev_alloc(&ctx->Acm, ctx->ldc * nd, ctx->stream));
-    CK(dev_alloc(&ctx->Arm, ctx->ldr * m, ctx->stream));
+    const size_t mblk = ((size_t)m + 15) / 16;
+    CK(dev_alloc(&ctx->Arm, ctx->ldr * mblk * 16, ctx->stream));
     CK(cudaMemsetAsync(ctx->Acm, 0, ctx->ldc * nd, ctx->stream));
-    CK(cudaMemsetAsync(ctx->Arm, 0, ctx->ldr * m, ctx->stream));
+    CK(cudaMemsetAsync(ctx->Arm, 0, ctx->ldr * mblk * 16, ctx->stream));
     CK(cudaMemcpy2DAsync(ctx->Acm, ctx->ldc, colmajor, (size_t)m, (size_t)m, (size_t)nd, cudaMemcpyHostToDevice,
                          ctx->stream));
-    dim3 grid(cdiv(nd, 32), cdiv(m, 32)), block(32, 32);
-    k_transpose_i8<<<grid, block, 0, ctx->stream>>>(ctx->Acm, ctx->ldc, ctx->Arm, ctx->ldr, m, nd);
+    dim3 grid(cdiv(nd, 128), (unsigned)mblk);
+    k_transpose_i8<<<grid, 128, 0, ctx->stream>>>(ctx->Acm, ctx->ldc, ctx->Arm, ctx->ldr, m, nd);
     ctx->launches++;
     ctx->nd = nd;
     ctx->dslices = 4;
@@ -392,7 +393,7 @@ static void set_status(rg_context* ctx, int st) { LAUNCH(k_set_status, 1, 1, ctx
 template <int LV, int LO>
 static void launch_coldots(rg_context* ctx, const u64* vec, size_t vs, int cmul, u64* out, const int* bits) {
     if (ctx->nd > 0) {
-        int rps = cdiv(ctx->m, ctx->dslices);
+        int rps = (cdiv(ctx->m, ctx->dslices) + 63) / 64 * 64;     // slices start on 64-row tile boundaries
         size_t pstride = (size_t)(2 * LV + 1) * ctx->nd;
         dim3 grid(cdiv(ctx->nd, 64), ctx->dslices), block(64, (2 * LV + 1 + 15) / 16);
         LAUNCH((k_vecsum<LV>), 2 * LV + 1, 256, vec, vs, ctx->m, bits, ctx->dsum, ctx->sc);
