@@ -80,7 +80,7 @@ typedef struct rg_stats {
     int32_t limbs;               /* current limb count L */
     int32_t max_bits;            /* largest |numerator| bit length currently in the carry */
     int32_t denominator_bits;    /* bit length of D */
-    int32_t reserved;
+    int32_t reserved;            /* active-column mode: number of non-trivial carry columns; 0 in dense mode */
     int64_t kernel_launches;     /* kernels launched by this context so far */
     int64_t pivots_at_limbs[5];  /* pivots performed at L = 1,2,4,8,16 */
     /* profiling (rg_set_profile): CUDA-event time of the rank-1 update kernel (K1) per limb width */

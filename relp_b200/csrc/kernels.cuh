@@ -164,13 +164,13 @@ __global__ void k_sign_extend(u64* dst, size_t ps, size_t count, int Lold, int L
 // ---------------------------------------------------------------------------------------------
 template <int LV, int LO>
 __global__ void __launch_bounds__(256)
-k_coldot(const u64* __restrict__ vec, size_t vs, int n, int j0, const long long* __restrict__ colptr,
+k_coldot(const u64* __restrict__ vec, size_t vs, int n, int j0, int j1, const long long* __restrict__ colptr,
          const int* __restrict__ rowidx, const long long* __restrict__ vals,
          const unsigned char* __restrict__ inbasis, const long long* __restrict__ cost, int cmul,
          int LD, u64* __restrict__ out, const Scalars* __restrict__ sc) {
     if (sc->status != ST_RUN) return;
-    int j = j0 + blockIdx.x * blockDim.x + threadIdx.x;     // columns below j0 live in the dense block
-    if (j >= n) return;
+    int j = j0 + blockIdx.x * blockDim.x + threadIdx.x;     // this rank's CSC columns [j0, j1)
+    if (j >= j1) return;
     u64 acc[LO];
 #pragma unroll
     for (int l = 0; l < LO; ++l) acc[l] = 0;
@@ -244,9 +244,10 @@ __global__ void __launch_bounds__(256) k_vecsum(const u64* __restrict__ vec, siz
 // vector entry is zero are skipped (warp-uniform): the pivot row and the dual row are sparse.
 template <int LV>
 __global__ void __launch_bounds__(64 * ((2 * LV + 1 + 15) / 16))
-k_densedot1(const u64* __restrict__ vec, size_t vs, int m, int nd, const signed char* __restrict__ Arm,
-            size_t ldr, int rows_per_slice, const int* bits, unsigned long long* __restrict__ part,
-            size_t pstride, const unsigned char* __restrict__ inbasis, const Scalars* sc) {
+k_densedot1(const u64* __restrict__ vec, size_t vs, int m, int nd, int jd0, int jd1,
+            const signed char* __restrict__ Arm, size_t ldr, int rows_per_slice, const int* bits,
+            unsigned long long* __restrict__ part, size_t pstride, const unsigned char* __restrict__ inbasis,
+            const Scalars* sc) {
     constexpr int NV = 2 * LV;
     constexpr int G = (NV + 1 + 15) / 16;          // word groups
     constexpr int NW = G * 16;                     // words per staged row (zero padded)
@@ -258,9 +259,9 @@ k_densedot1(const u64* __restrict__ vec, size_t vs, int m, int nd, const signed 
     const int lveff = eff_limbs(bits, LV), NVe = 2 * lveff;
     const int tid = threadIdx.y * 64 + threadIdx.x;
     const int nthreads = 64 * G;
-    const int j = blockIdx.x * 64 + threadIdx.x;
+    const int j = jd0 + blockIdx.x * 64 + threadIdx.x;      // this rank's dense columns [jd0, jd1)
     const int g = threadIdx.y;
-    const bool active = j < nd && !inbasis[j] && 16 * g <= NVe;
+    const bool active = j < jd1 && !inbasis[j] && 16 * g <= NVe;
     const int r0 = blockIdx.y * rows_per_slice;
     const int r1 = min(m, r0 + rows_per_slice);
     unsigned long long acc[16];
@@ -310,7 +311,7 @@ k_densedot1(const u64* __restrict__ vec, size_t vs, int m, int nd, const signed 
             }
         }
     }
-    if (j < nd) {
+    if (j < jd1) {
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
             int w = 16 * g + k;
@@ -321,12 +322,13 @@ k_densedot1(const u64* __restrict__ vec, size_t vs, int m, int nd, const signed 
 // stage 2: sum the slices, remove the bias, resolve the deferred carries, add cmul * cost_j * D
 template <int LV, int LO>
 __global__ void __launch_bounds__(128)
-k_densedot2(const unsigned long long* __restrict__ part, size_t pstride, int slices, int nd, int n,
-            const int* bits, const unsigned long long* __restrict__ S, const unsigned char* __restrict__ inbasis,
-            const long long* __restrict__ cost, int cmul, int LD, u64* __restrict__ out, const Scalars* sc) {
+k_densedot2(const unsigned long long* __restrict__ part, size_t pstride, int slices, int nd, int n, int jd0,
+            int jd1, const int* bits, const unsigned long long* __restrict__ S,
+            const unsigned char* __restrict__ inbasis, const long long* __restrict__ cost, int cmul, int LD,
+            u64* __restrict__ out, const Scalars* sc) {
     if (sc->status != ST_RUN) return;
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= nd) return;
+    int j = jd0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= jd1) return;
     const int NVe = 2 * eff_limbs(bits, LV);
     u64 res[LO];
 #pragma unroll
@@ -615,12 +617,12 @@ __device__ inline double planar_log2_abs(const u64* base, size_t stride, size_t 
 
 // mode 2: Dantzig  score = log2|kappa|;  mode 3: steepest edge  score = 2 log2|kappa| - log2 Ghat
 __global__ void __launch_bounds__(256)
-k_score_columns(int n, int mode, const u64* __restrict__ kappa, int LU, const u64* __restrict__ G, int LG,
+k_score_columns(int n, int c0, int c1, int mode, const u64* __restrict__ kappa, int LU, const u64* __restrict__ G, int LG,
                 const unsigned char* __restrict__ inbasis, const long long* __restrict__ wcol,
                 double* __restrict__ score, const Scalars* sc) {
     if (sc->status != ST_RUN) return;
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
+    int j = c0 + blockIdx.x * blockDim.x + threadIdx.x;     // this rank's columns [c0, c1)
+    if (j >= c1) return;
     double s = SCORE_NONE;
     if (!inbasis[j]) {
         int sg;
@@ -652,14 +654,14 @@ k_score_rows(int m, const u64* __restrict__ C, size_t ps, int ld, int L, const u
 
 // single block: max score, then exact comparison among the candidates within SCORE_EPS
 template <class Cmp>
-__global__ void __launch_bounds__(1024) k_select_scored(int count, Cmp cmp, const double* __restrict__ score,
-                                                        int mode, Scalars* sc) {
+__global__ void __launch_bounds__(1024) k_select_scored(int off, int count, Cmp cmp,
+                                                        const double* __restrict__ score, int mode, Scalars* sc) {
     __shared__ double sd[1024];
     __shared__ int sm[1024];
     if (sc->status != ST_RUN) return;
     int tid = threadIdx.x;
     double best = SCORE_NONE;
-    for (int j = tid; j < count; j += blockDim.x) best = fmax(best, score[j]);
+    for (int j = off + tid; j < off + count; j += blockDim.x) best = fmax(best, score[j]);
     sd[tid] = best;
     __syncthreads();
     for (int s = blockDim.x >> 1; s > 0; s >>= 1) {
@@ -670,7 +672,7 @@ __global__ void __launch_bounds__(1024) k_select_scored(int count, Cmp cmp, cons
     int cand = -1;
     if (top > SCORE_NONE) {
         double thr = top >= 1.0e299 ? 1.0e299 : top - SCORE_EPS;
-        for (int j = tid; j < count; j += blockDim.x) {
+        for (int j = off + tid; j < off + count; j += blockDim.x) {
             if (score[j] >= thr && (cand < 0 || cmp.better(j, cand))) cand = j;
         }
     }
@@ -695,6 +697,8 @@ __global__ void __launch_bounds__(1024) k_select_scored(int count, Cmp cmp, cons
         } else if (mode == 3) {          // local candidate of a row-sharded ratio test
             sc->p = bestj < 0 ? -1 : bestj + 1;
             sc->pg = bestj < 0 ? -1 : sc->row_lo + bestj + 1;
+        } else if (mode == 4) {          // local candidate of a column-sharded pricing
+            sc->q = bestj;
         } else {
             sc->found = bestj;
         }
@@ -775,11 +779,11 @@ __device__ __forceinline__ int block_best(int best, const Cmp& cmp, int* sm) {
 }
 
 template <class Cmp>
-__global__ void __launch_bounds__(256) k_argbest1(int n, Cmp cmp, int* cand, const Scalars* sc) {
+__global__ void __launch_bounds__(256) k_argbest1(int off, int n, Cmp cmp, int* cand, const Scalars* sc) {
     __shared__ int sm[256];
     if (sc->status != ST_RUN) return;
     int best = -1;
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    for (int j = off + blockIdx.x * blockDim.x + threadIdx.x; j < off + n; j += gridDim.x * blockDim.x) {
         if (cmp.eligible(j) && (best < 0 || cmp.better(j, best))) best = j;
     }
     best = block_best(best, cmp, sm);
@@ -805,10 +809,88 @@ __global__ void __launch_bounds__(256) k_argbest2(int nblocks, Cmp cmp, const in
         } else if (mode == 1) {
             sc->p = best + 1;
             if (best < 0) sc->status = ST_UNBOUNDED;
+        } else if (mode == 4) {
+            sc->q = best;
         } else {
             sc->found = best;
         }
     }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// column-sharded pricing: every rank prices its own block of columns and keeps
+// their steepest-edge weights; the local candidates are all-gathered and reduced identically on
+// every rank with the rule's own exact order.
+// candidate layout (u64 words): 0 valid, 1 column, 2 weight w_j, 3.. kappa (RG_MAXL+2), then Ghat (2 RG_MAXL+6)
+// ---------------------------------------------------------------------------------------------
+#define RG_COLCAND_WORDS (3 + (RG_MAXL + 2) + (2 * RG_MAXL + 6))
+__global__ void k_column_pack(const u64* __restrict__ kappa, int LU, const u64* __restrict__ G, int LG, int n,
+                              const long long* __restrict__ wcol, int use_found, u64* __restrict__ send,
+                              const Scalars* sc) {
+    if (threadIdx.x || blockIdx.x) return;
+    for (int k = 0; k < RG_COLCAND_WORDS; ++k) send[k] = 0;
+    if (sc->status != ST_RUN) return;
+    int j = use_found ? sc->found : sc->q;
+    if (j < 0) return;
+    send[0] = 1; send[1] = (u64)j; send[2] = wcol ? (u64)wcol[j] : 1ull;
+    for (int l = 0; l < LU; ++l) send[3 + l] = kappa[(size_t)l * n + j];
+    for (int l = 0; l < LG; ++l) send[3 + (RG_MAXL + 2) + l] = G[(size_t)l * n + j];
+}
+__global__ void k_column_merge(const u64* __restrict__ recv, int world, int rule, int L, int n, int want_found,
+                               Scalars* sc) {
+    if (threadIdx.x || blockIdx.x) return;
+    if (sc->status != ST_RUN) return;
+    const int LU = L + 2, LG = 2 * L + 6;
+    u64 buf[6 * RG_MAXW];
+    u64* x = buf; u64* y = buf + RG_MAXW; u64* sj = buf + 2 * RG_MAXW; u64* sk = buf + 3 * RG_MAXW;
+    u64* pj = buf + 4 * RG_MAXW; u64* pk = buf + 5 * RG_MAXW;
+    int best = -1;
+    for (int r = 0; r < world; ++r) {
+        const u64* c = recv + (size_t)r * RG_COLCAND_WORDS;
+        if (!c[0]) continue;
+        if (best < 0) { best = r; continue; }
+        const u64* b = recv + (size_t)best * RG_COLCAND_WORDS;
+        const int j = (int)c[1], k = (int)b[1];
+        bool better;
+        if (rule == 0 || want_found) better = j < k;                             // first profitable / first hit
+        else if (rule == 1) {                                                    // ... with memory
+            int last = sc->last_selected;
+            int kj = j > last ? j - last : j + n - last, kk = k > last ? k - last : k + n - last;
+            better = kj < kk;
+        } else if (rule == 2) {                                                  // Dantzig: |kappa| w, ties lowest j
+            for (int l = 0; l < LU; ++l) { x[l] = c[3 + l]; y[l] = b[3 + l]; }
+            rt_neg(x, LU); rt_neg(y, LU);
+            u64 wj = c[2], wk = b[2];
+            rt_mul_full(sj, x, LU, &wj, 1);
+            rt_mul_full(sk, y, LU, &wk, 1);
+            int cmpv = rt_cmp_u(sj, sk, LU + 1);
+            better = cmpv > 0 || (cmpv == 0 && j < k);
+        } else {                                                                 // steepest edge, ties highest j
+            for (int l = 0; l < LU; ++l) x[l] = c[3 + l];
+            rt_abs(y, x, LU); int ly = rt_trim(y, LU);
+            rt_mul_full(sj, y, ly, y, ly); int lsj = rt_trim(sj, 2 * ly);
+            for (int l = 0; l < LU; ++l) x[l] = b[3 + l];
+            rt_abs(y, x, LU); ly = rt_trim(y, LU);
+            rt_mul_full(sk, y, ly, y, ly); int lsk = rt_trim(sk, 2 * ly);
+            const u64* gk = b + 3 + (RG_MAXL + 2); const u64* gj = c + 3 + (RG_MAXL + 2);
+            int lgk = rt_trim(gk, LG), lgj = rt_trim(gj, LG);
+            rt_mul_full(pj, sj, lsj, gk, lgk); int lpj = lsj + lgk;
+            rt_mul_full(pk, sk, lsk, gj, lgj); int lpk = lsk + lgj;
+            int nn = lpj > lpk ? lpj : lpk;
+            for (int i = lpj; i < nn; ++i) pj[i] = 0;
+            for (int i = lpk; i < nn; ++i) pk[i] = 0;
+            int cmpv = rt_cmp_u(pj, pk, nn);
+            better = cmpv > 0 || (cmpv == 0 && j > k);
+        }
+        if (better) best = r;
+    }
+    if (want_found) { sc->found = best < 0 ? -1 : (int)recv[(size_t)best * RG_COLCAND_WORDS + 1]; return; }
+    if (best < 0) { sc->q = -1; sc->status = ST_OPTIMAL; return; }
+    const u64* b = recv + (size_t)best * RG_COLCAND_WORDS;
+    sc->q = (int)b[1];
+    sc->last_selected = sc->q;
+    for (int l = 0; l < LG; ++l) sc->Gq[l] = b[3 + (RG_MAXL + 2) + l];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1213,7 +1295,8 @@ __global__ void __launch_bounds__(32) k_scalars_se(int L, const u64* __restrict_
     __syncwarp();
     warp_mul_lo(tmp, ax, i2, WX, cols);
     for (int k = lane; k < WX; k += 32) sc->S2[k] = tmp[k];
-    for (int k = lane; k < WX; k += 32) { u64 v = k < LG ? G[(size_t)k * n + sc->q] : 0; xn[k] = v; if (k < LG) sc->Gq[k] = v; }
+    // Ghat of the entering column: local array, or (column-sharded pricing) the value the selection merge left in Gq
+    for (int k = lane; k < WX; k += 32) { u64 v = k < LG ? (G ? G[(size_t)k * n + sc->q] : sc->Gq[k]) : 0; xn[k] = v; if (k < LG) sc->Gq[k] = v; }
     __syncwarp();
     warp_mul_lo(tmp, xn, i2, WX, cols);
     for (int k = lane; k < WX; k += 32) sc->S3[k] = tmp[k];
@@ -1789,12 +1872,12 @@ k_gamma_init_general(const u64* __restrict__ C, size_t ps, int ld, int m, int n,
 // IMAD chains); used whenever D^2 has at most 256 trailing zero bits (E2 <= 4).
 template <int L>
 __global__ void __launch_bounds__(128)
-k_gamma_update_t(int n, const unsigned char* __restrict__ inbasis, const u64* __restrict__ nu,
+k_gamma_update_t(int n, int c0, int c1, const unsigned char* __restrict__ inbasis, const u64* __restrict__ nu,
                  const u64* __restrict__ sigma, u64* __restrict__ G, const Scalars* sc) {
     constexpr int LU = L + 2, LS = 2 * L + 7, LG = 2 * L + 6, WX = LG + 4, N = 2 * WX;
     if (sc->status != ST_RUN) return;
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
+    int j = c0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= c1) return;
     if (inbasis[j] || j == sc->leaving) return;   // entering: None; leaving: set by k_finalize
     u32 nv[N], x[N];
     {
@@ -1862,11 +1945,11 @@ k_gamma_update_t(int n, const unsigned char* __restrict__ inbasis, const u64* __
 
 // per-column steepest-edge recurrence (run-time widths: O(n) work, not the hot spot)
 __global__ void __launch_bounds__(128)
-k_gamma_update(int n, int L, const unsigned char* __restrict__ inbasis, const u64* __restrict__ nu,
+k_gamma_update(int n, int c0, int c1, int L, const unsigned char* __restrict__ inbasis, const u64* __restrict__ nu,
                const u64* __restrict__ sigma, u64* __restrict__ G, const Scalars* sc) {
     if (sc->status != ST_RUN) return;
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
+    int j = c0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= c1) return;
     if (inbasis[j] || j == sc->leaving) return;   // entering: None; leaving: set by k_finalize
     const int LU = L + 2, LS = 2 * L + 7, LG = 2 * L + 6;
     const int WX = LG + sc->E2;

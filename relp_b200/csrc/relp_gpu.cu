@@ -124,6 +124,14 @@ static int alloc_width_buffers(rg_context* ctx, int L) {
     CK(dev_alloc(&ctx->kappa, sizeof(u64) * LU_of(L) * n, ctx->stream));
     CK(dev_alloc(&ctx->nu, sizeof(u64) * LU_of(L) * n, ctx->stream));
     CK(dev_alloc(&ctx->sigma, sizeof(u64) * LS_of(L) * n, ctx->stream));
+    if (ctx->world > 1) {   // exchange buffers sized once per width for every collective of the engine
+        size_t words = std::max<size_t>((size_t)LW_of(L) * ld, (size_t)LG_of(L) * n);
+        words = std::max<size_t>(words, (size_t)(LU_of(L) + 1) * (((size_t)ctx->m + ctx->world - 1) / ctx->world));
+        words = std::max<size_t>(words, 128) * ctx->world;
+        CK(dev_alloc(&ctx->xsend, words * sizeof(u64), ctx->stream));
+        CK(dev_alloc(&ctx->xrecv, words * sizeof(u64), ctx->stream));
+        ctx->xbytes = words * sizeof(u64);
+    }
     CK(cudaMemsetAsync(ctx->u, 0, sizeof(u64) * LU_of(L) * ld, ctx->stream));
     CK(cudaMemsetAsync(ctx->rowp, 0, sizeof(u64) * L * ld, ctx->stream));
     CK(cudaMemsetAsync(ctx->kappa, 0, sizeof(u64) * LU_of(L) * n, ctx->stream));
@@ -132,6 +140,8 @@ static int alloc_width_buffers(rg_context* ctx, int L) {
 static void free_width_buffers(rg_context* ctx) {
     free_dev_on(ctx->u, ctx->stream); free_dev_on(ctx->rowp, ctx->stream); free_dev_on(ctx->omega, ctx->stream); free_dev_on(ctx->omega_part, ctx->stream);
     free_dev_on(ctx->tmprow, ctx->stream); free_dev_on(ctx->us2, ctx->stream); free_dev_on(ctx->dpart, ctx->stream); free_dev_on(ctx->kappa, ctx->stream); free_dev_on(ctx->nu, ctx->stream); free_dev_on(ctx->sigma, ctx->stream);
+    free_dev_on(ctx->xsend, ctx->stream); free_dev_on(ctx->xrecv, ctx->stream);
+    ctx->xsend = ctx->xrecv = nullptr; ctx->xbytes = 0;
     ctx->u = ctx->rowp = ctx->omega = ctx->omega_part = ctx->tmprow = ctx->us2 = nullptr; ctx->dpart = nullptr;
     ctx->kappa = ctx->nu = ctx->sigma = nullptr;
 }
@@ -207,7 +217,6 @@ extern "C" int rg_destroy(rg_context* ctx) {
     free_dev_on(ctx->carry, ctx->stream); free_dev_on(ctx->A.colptr, ctx->stream); free_dev_on(ctx->A.rowidx, ctx->stream); free_dev_on(ctx->A.vals, ctx->stream);
     free_dev_on(ctx->cost, ctx->stream); free_dev_on(ctx->rhs, ctx->stream); free_dev_on(ctx->basis, ctx->stream); free_dev_on(ctx->inbasis, ctx->stream);
     free_dev_on(ctx->G, ctx->stream); free_dev_on(ctx->cand, ctx->stream); free_dev_on(ctx->score, ctx->stream); free_dev_on(ctx->sc, ctx->stream); free_dev_on(ctx->svec, ctx->stream);
-    free_dev_on(ctx->xsend, ctx->stream); free_dev_on(ctx->xrecv, ctx->stream);
     free_dev_on(ctx->triv, ctx->stream); free_dev_on(ctx->klist, ctx->stream); free_dev_on(ctx->kpos, ctx->stream); free_dev_on(ctx->aq, ctx->stream);
     free_dev_on(ctx->Arm, ctx->stream); free_dev_on(ctx->Acm, ctx->stream); free_dev_on(ctx->dsum, ctx->stream);
     free_dev_on(ctx->wf, ctx->stream); free_dev_on(ctx->wcol, ctx->stream); free_dev_on(ctx->artf, ctx->stream);
@@ -237,6 +246,11 @@ extern "C" int rg_load_csc(rg_context* ctx, int32_t m, int32_t n, const int64_t*
         int q = (m + ctx->world - 1) / ctx->world;
         ctx->row_lo = std::min(m, ctx->rank * q);
         ctx->nloc = std::max(0, std::min(m, (ctx->rank + 1) * q) - ctx->row_lo);
+    }
+    {   // column blocks for pricing / rule state
+        int cq = (n + ctx->world - 1) / ctx->world;
+        ctx->c0 = std::min(n, ctx->rank * cq);
+        ctx->c1 = std::min(n, (ctx->rank + 1) * cq);
     }
     ctx->plane = (size_t)(ctx->nloc + 1) * ctx->ld;
     long long nnz = colptr[n];
@@ -335,10 +349,16 @@ extern "C" int rg_set_weights(rg_context* ctx, const int64_t* colfac, const int6
 // ------------------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------------------
+static const bool g_check_launch = getenv("RG_CHECK_LAUNCH") != nullptr;
 #define LAUNCH(kernel, grid, block, ...)                                   \
     do {                                                                   \
         kernel<<<grid, block, 0, ctx->stream>>>(__VA_ARGS__);              \
         ctx->launches++;                                                   \
+        if (g_check_launch) {                                              \
+            cudaError_t e__ = cudaGetLastError();                          \
+            if (e__ != cudaSuccess)                                        \
+                fprintf(stderr, "[rank %d] launch of %s failed: %s\n", ctx->rank, #kernel, cudaGetErrorString(e__)); \
+        }                                                                  \
     } while (0)
 
 // exchange buffers of the row-sharded engine (words of 8 bytes)
@@ -346,7 +366,6 @@ static int ensure_xbuf(rg_context* ctx, size_t send_words, size_t recv_words) {
     size_t need = std::max(send_words, recv_words) * sizeof(u64);
     if (need <= ctx->xbytes) return RG_OK;
     CK(cudaStreamSynchronize(ctx->stream));
-    free_dev_on(ctx->xsend, ctx->stream); free_dev_on(ctx->xrecv, ctx->stream);
     free_dev_on(ctx->triv, ctx->stream); free_dev_on(ctx->klist, ctx->stream); free_dev_on(ctx->kpos, ctx->stream); free_dev_on(ctx->aq, ctx->stream);
     free_dev_on(ctx->Arm, ctx->stream); free_dev_on(ctx->Acm, ctx->stream); free_dev_on(ctx->dsum, ctx->stream);
     free_dev_on(ctx->wf, ctx->stream); free_dev_on(ctx->wcol, ctx->stream); free_dev_on(ctx->artf, ctx->stream);
@@ -371,6 +390,7 @@ static int all_gather(rg_context* ctx, const void* send, void* recv, size_t word
         if (++g_nccl_calls % 400 == 0)
             fprintf(stderr, "[hostprof rank %d] %lld all_gather calls, %.3f s on the host\n", ctx->rank, g_nccl_calls, g_nccl_host_s);
     }
+    (void)cudaGetLastError();   // NCCL probes pointers internally; benign failures must not look like ours
     return RG_OK;
 }
 
@@ -392,18 +412,20 @@ static void set_status(rg_context* ctx, int st) { LAUNCH(k_set_status, 1, 1, ctx
 // `bits` points at the device-side bit-length maximum that bounds every entry of `vec`.
 template <int LV, int LO>
 static void launch_coldots(rg_context* ctx, const u64* vec, size_t vs, int cmul, u64* out, const int* bits) {
-    if (ctx->nd > 0) {
+    const int jd0 = std::min(ctx->c0, ctx->nd), jd1 = std::min(ctx->c1, ctx->nd);     // dense block part
+    const int j0 = std::max(ctx->c0, ctx->nd), j1 = ctx->c1;                           // CSC part
+    if (jd1 > jd0) {
         int rps = (cdiv(ctx->m, ctx->dslices) + 63) / 64 * 64;     // slices start on 64-row tile boundaries
         size_t pstride = (size_t)(2 * LV + 1) * ctx->nd;
-        dim3 grid(cdiv(ctx->nd, 64), ctx->dslices), block(64, (2 * LV + 1 + 15) / 16);
+        dim3 grid(cdiv(jd1 - jd0, 64), ctx->dslices), block(64, (2 * LV + 1 + 15) / 16);
         LAUNCH((k_vecsum<LV>), 2 * LV + 1, 256, vec, vs, ctx->m, bits, ctx->dsum, ctx->sc);
-        LAUNCH((k_densedot1<LV>), grid, block, vec, vs, ctx->m, ctx->nd, ctx->Arm, ctx->ldr, rps, bits, ctx->dpart,
-               pstride, ctx->inbasis, ctx->sc);
-        LAUNCH((k_densedot2<LV, LO>), cdiv(ctx->nd, 128), 128, ctx->dpart, pstride, ctx->dslices, ctx->nd, ctx->n,
-               bits, ctx->dsum, ctx->inbasis, ctx->cost, cmul, ctx->L, out, ctx->sc);
+        LAUNCH((k_densedot1<LV>), grid, block, vec, vs, ctx->m, ctx->nd, jd0, jd1, ctx->Arm, ctx->ldr, rps, bits,
+               ctx->dpart, pstride, ctx->inbasis, ctx->sc);
+        LAUNCH((k_densedot2<LV, LO>), cdiv(jd1 - jd0, 128), 128, ctx->dpart, pstride, ctx->dslices, ctx->nd, ctx->n,
+               jd0, jd1, bits, ctx->dsum, ctx->inbasis, ctx->cost, cmul, ctx->L, out, ctx->sc);
     }
-    if (ctx->n > ctx->nd)
-        LAUNCH((k_coldot<LV, LO>), cdiv(ctx->n - ctx->nd, 256), 256, vec, vs, ctx->n, ctx->nd, ctx->A.colptr,
+    if (j1 > j0)
+        LAUNCH((k_coldot<LV, LO>), cdiv(j1 - j0, 256), 256, vec, vs, ctx->n, j0, j1, ctx->A.colptr,
                ctx->A.rowidx, ctx->A.vals, ctx->inbasis, ctx->cost, cmul, ctx->L, out, ctx->sc);
 }
 template <int L>
@@ -413,30 +435,44 @@ static void launch_price_t(rg_context* ctx) {
 static void launch_price(rg_context* ctx) { DISPATCH_L(ctx->L, launch_price_t, ctx); }
 
 template <class Cmp>
-static void launch_argbest(rg_context* ctx, int count, const Cmp& cmp, int mode) {
+static void launch_argbest(rg_context* ctx, int off, int count, const Cmp& cmp, int mode) {
     int nb = std::max(1, std::min(1024, cdiv(count, 256)));
-    LAUNCH((k_argbest1<Cmp>), nb, 256, count, cmp, ctx->cand, ctx->sc);
+    LAUNCH((k_argbest1<Cmp>), nb, 256, off, count, cmp, ctx->cand, ctx->sc);
     LAUNCH((k_argbest2<Cmp>), 1, 256, nb, cmp, ctx->cand, mode, ctx->sc);
 }
+// column-sharded pricing: exchange the local candidates and reduce them identically on every rank
+static int merge_columns(rg_context* ctx, int use_found) {
+    RG_TRY(ensure_xbuf(ctx, RG_COLCAND_WORDS, (size_t)RG_COLCAND_WORDS * ctx->world));
+    LAUNCH(k_column_pack, 1, 1, ctx->kappa, LU_of(ctx->L), ctx->G, LG_of(ctx->L), ctx->n,
+           ctx->weighted ? ctx->wcol : nullptr, use_found, ctx->xsend, ctx->sc);
+    RG_TRY(all_gather(ctx, ctx->xsend, ctx->xrecv, RG_COLCAND_WORDS));
+    LAUNCH(k_column_merge, 1, 1, ctx->xrecv, ctx->world, ctx->rule, ctx->L, ctx->n, use_found, ctx->sc);
+    return RG_OK;
+}
 
-static void launch_select(rg_context* ctx) {
+static int launch_select(rg_context* ctx) {
     PriceView v{ctx->kappa, LU_of(ctx->L), ctx->n, ctx->inbasis};
+    const int off = ctx->c0, cnt = std::max(ctx->c1 - ctx->c0, 0);
+    const int mode = ctx->world == 1 ? 0 : 4;
     switch (ctx->rule) {
-        case RG_RULE_FIRST_PROFITABLE: launch_argbest(ctx, ctx->n, CmpFirst{v}, 0); break;
-        case RG_RULE_FIRST_PROFITABLE_WITH_MEMORY: launch_argbest(ctx, ctx->n, CmpFirstMem{v, ctx->sc}, 0); break;
+        case RG_RULE_FIRST_PROFITABLE: launch_argbest(ctx, off, cnt, CmpFirst{v}, mode); break;
+        case RG_RULE_FIRST_PROFITABLE_WITH_MEMORY: launch_argbest(ctx, off, cnt, CmpFirstMem{v, ctx->sc}, mode); break;
         case RG_RULE_DANTZIG:
-            LAUNCH(k_score_columns, cdiv(ctx->n, 256), 256, ctx->n, 2, ctx->kappa, LU_of(ctx->L), ctx->G,
-                   LG_of(ctx->L), ctx->inbasis, ctx->weighted ? ctx->wcol : nullptr, ctx->score, ctx->sc);
-            LAUNCH((k_select_scored<CmpDantzig>), 1, 1024, ctx->n,
-                   (CmpDantzig{v, ctx->weighted ? ctx->wcol : nullptr}), ctx->score, 0, ctx->sc);
+            LAUNCH(k_score_columns, cdiv(std::max(cnt, 1), 256), 256, ctx->n, ctx->c0, ctx->c1, 2, ctx->kappa,
+                   LU_of(ctx->L), ctx->G, LG_of(ctx->L), ctx->inbasis, ctx->weighted ? ctx->wcol : nullptr,
+                   ctx->score, ctx->sc);
+            LAUNCH((k_select_scored<CmpDantzig>), 1, 1024, off, cnt,
+                   (CmpDantzig{v, ctx->weighted ? ctx->wcol : nullptr}), ctx->score, mode, ctx->sc);
             break;
         default:
-            LAUNCH(k_score_columns, cdiv(ctx->n, 256), 256, ctx->n, 3, ctx->kappa, LU_of(ctx->L), ctx->G,
-                   LG_of(ctx->L), ctx->inbasis, nullptr, ctx->score, ctx->sc);
-            LAUNCH((k_select_scored<CmpSteepest>), 1, 1024, ctx->n, CmpSteepest{v, ctx->G, LG_of(ctx->L)},
-                   ctx->score, 0, ctx->sc);
+            LAUNCH(k_score_columns, cdiv(std::max(cnt, 1), 256), 256, ctx->n, ctx->c0, ctx->c1, 3, ctx->kappa,
+                   LU_of(ctx->L), ctx->G, LG_of(ctx->L), ctx->inbasis, nullptr, ctx->score, ctx->sc);
+            LAUNCH((k_select_scored<CmpSteepest>), 1, 1024, off, cnt, (CmpSteepest{v, ctx->G, LG_of(ctx->L)}),
+                   ctx->score, mode, ctx->sc);
             break;
     }
+    if (ctx->world > 1) RG_TRY(merge_columns(ctx, 0));
+    return RG_OK;
 }
 
 template <int L>
@@ -470,12 +506,12 @@ static int launch_ratio(rg_context* ctx) {
     LAUNCH(k_score_rows, cdiv(cnt, 256), 256, ctx->nloc, ctx->carry, ctx->plane, ctx->ld, ctx->L, ctx->u,
            (size_t)ctx->ld, LU_of(ctx->L), ctx->score, ctx->sc);
     if (ctx->world == 1) {
-        LAUNCH((k_select_scored<CmpRatio>), 1, 1024, ctx->nloc, c, ctx->score, 1, ctx->sc);
+        LAUNCH((k_select_scored<CmpRatio>), 1, 1024, 0, ctx->nloc, c, ctx->score, 1, ctx->sc);
         LAUNCH(k_take_a, 1, 1, ctx->u, (size_t)ctx->ld, ctx->L, ctx->sc);
         return RG_OK;
     }
     // row-sharded: local candidate -> all-gather -> identical deterministic reduction on every rank
-    LAUNCH((k_select_scored<CmpRatio>), 1, 1024, ctx->nloc, c, ctx->score, 3, ctx->sc);
+    LAUNCH((k_select_scored<CmpRatio>), 1, 1024, 0, ctx->nloc, c, ctx->score, 3, ctx->sc);
     RG_TRY(ensure_xbuf(ctx, RG_CAND_WORDS, (size_t)RG_CAND_WORDS * ctx->world));
     LAUNCH(k_ratio_pack, 1, 1, ctx->carry, ctx->plane, ctx->ld, ctx->L, ctx->u, (size_t)ctx->ld, ctx->basis,
            ctx->xsend, ctx->sc);
@@ -511,8 +547,11 @@ static void launch_rowbits_t(rg_context* ctx) {
 static int launch_copyrow(rg_context* ctx) {
     DISPATCH_L(ctx->L, launch_copyrow_t, ctx);
     if (ctx->world > 1)   // exact: exactly one rank contributes non-zero words
+    {
         NK(nccl_api()->AllReduce(ctx->rowp, ctx->rowp, (size_t)ctx->L * ctx->ld, ncclUint64, ncclSum,
                                  (ncclComm_t)ctx->nccl_comm, ctx->stream));
+        (void)cudaGetLastError();
+    }
     DISPATCH_L(ctx->L, launch_rowbits_t, ctx);
     return RG_OK;
 }
@@ -624,8 +663,8 @@ static void launch_se_dots_t(rg_context* ctx) {
 }
 template <int L>
 static void launch_gamma_update_t(rg_context* ctx) {
-    LAUNCH((k_gamma_update_t<L>), cdiv(ctx->n, 128), 128, ctx->n, ctx->inbasis, ctx->nu, ctx->sigma, ctx->G,
-           ctx->sc);
+    LAUNCH((k_gamma_update_t<L>), cdiv(std::max(ctx->c1 - ctx->c0, 1), 128), 128, ctx->n, ctx->c0, ctx->c1,
+           ctx->inbasis, ctx->nu, ctx->sigma, ctx->G, ctx->sc);
 }
 static void launch_se_update(rg_context* ctx) {
     DISPATCH_L(ctx->L, launch_se_dots_t, ctx);
@@ -638,8 +677,8 @@ static void launch_se_update(rg_context* ctx) {
             default: launch_gamma_update_t<8>(ctx); break;
         }
     } else {
-        LAUNCH(k_gamma_update, cdiv(ctx->n, 128), 128, ctx->n, ctx->L, ctx->inbasis, ctx->nu, ctx->sigma, ctx->G,
-               ctx->sc);
+        LAUNCH(k_gamma_update, cdiv(std::max(ctx->c1 - ctx->c0, 1), 128), 128, ctx->n, ctx->c0, ctx->c1, ctx->L,
+               ctx->inbasis, ctx->nu, ctx->sigma, ctx->G, ctx->sc);
     }
 }
 
@@ -725,7 +764,7 @@ static int do_pivot(rg_context* ctx, int q, int fixed_row, bool want_se, bool re
         if (want_se) {   // steepest-edge scalars on the side stream, overlapped with K1
             cudaEventRecord(ctx->ev_side0, ctx->stream);
             cudaStreamWaitEvent(ctx->side, ctx->ev_side0, 0);
-            k_scalars_se<<<1, 32, 0, ctx->side>>>(ctx->L, ctx->G, ctx->n, ctx->sc);
+            k_scalars_se<<<1, 32, 0, ctx->side>>>(ctx->L, ctx->world == 1 ? ctx->G : nullptr, ctx->n, ctx->sc);
             ctx->launches++;
             cudaEventRecord(ctx->ev_side1, ctx->side);
         }
@@ -738,7 +777,7 @@ static int do_pivot(rg_context* ctx, int q, int fixed_row, bool want_se, bool re
                ctx->hm_dev);
         if (want_se) launch_se_update(ctx);
         if (prof) cudaEventRecord(ctx->evp[3], ctx->stream);
-        if (reselect) { launch_price(ctx); launch_select(ctx); }
+        if (reselect) { launch_price(ctx); RG_TRY(launch_select(ctx)); }
         if (prof) cudaEventRecord(ctx->evp[4], ctx->stream);
         double h5 = hostprof ? now_s() : 0;
         RG_TRY(sync_mirror(ctx));
@@ -955,7 +994,7 @@ extern "C" int rg_select_primal_pivot_column(rg_context* ctx, int32_t* status, i
     CK(cudaSetDevice(ctx->device));
     set_status(ctx, ST_RUN);
     launch_price(ctx);
-    launch_select(ctx);
+    RG_TRY(launch_select(ctx));
     RG_TRY(sync_mirror(ctx));
     *status = to_step_status(ctx->hm->status);
     *q = ctx->hm->q;
@@ -1013,7 +1052,7 @@ extern "C" int rg_iterate(rg_context* ctx, int64_t max_pivots, rg_pivot_info* tr
     if (!ctx->selected) {
         set_status(ctx, ST_RUN);
         launch_price(ctx);
-        launch_select(ctx);
+        RG_TRY(launch_select(ctx));
         RG_TRY(sync_mirror(ctx));
         if (ctx->hm->status != ST_RUN) { *status = to_step_status(ctx->hm->status); return RG_OK; }
         ctx->selected = true;
@@ -1052,7 +1091,8 @@ extern "C" int rg_remove_artificial_row(rg_context* ctx, int32_t row, rg_pivot_i
     LAUNCH(k_bp_nonzero, 1, 1, ctx->rowp, (size_t)ctx->ld, ctx->L, ctx->sc);
     DISPATCH_L(ctx->L, launch_rowdot_t, ctx);
     PriceView v{ctx->kappa, LU_of(ctx->L), ctx->n, ctx->inbasis};
-    launch_argbest(ctx, ctx->n, CmpArtificial{v, ctx->nu, ctx->sc}, 2);
+    launch_argbest(ctx, ctx->c0, std::max(ctx->c1 - ctx->c0, 0), CmpArtificial{v, ctx->nu, ctx->sc}, 2);
+    if (ctx->world > 1) RG_TRY(merge_columns(ctx, 1));
     RG_TRY(sync_mirror(ctx));
     int q = ctx->hm->found;
     ctx->selected = false; ctx->have_column = false;
@@ -1165,7 +1205,12 @@ extern "C" int rg_get_relative_costs(rg_context* ctx, uint64_t* out) {
     if (!ctx || !ctx->carry || !out) return RG_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     set_status(ctx, ST_RUN);
-    launch_price(ctx);
+    {   // export every column: price the full range on this rank
+        int c0 = ctx->c0, c1 = ctx->c1;
+        ctx->c0 = 0; ctx->c1 = ctx->n;
+        launch_price(ctx);
+        ctx->c0 = c0; ctx->c1 = c1;
+    }
     ctx->selected = false;
     return export_planar(ctx, ctx->kappa, (size_t)ctx->n, 0, 1, ctx->n, LU_of(ctx->L), out);
 }
@@ -1180,6 +1225,7 @@ extern "C" int rg_get_stats(rg_context* ctx, rg_stats* out) {
     out->pivots = ctx->pivots; out->promotions = ctx->promotions; out->limbs = ctx->L;
     out->kernel_launches = ctx->launches;
     if (ctx->hm) { out->max_bits = ctx->hm->maxbits_carry; out->denominator_bits = ctx->hm->bits_D; }
+    out->reserved = ctx->list_mode ? ctx->nk_host : 0;   // non-trivial carry columns (0: dense mode)
     for (int k = 0; k < 5; ++k) {
         out->pivots_at_limbs[k] = ctx->pivots_at[k];
         out->k1_launches_at_limbs[k] = ctx->k1_launches[k];
