@@ -327,7 +327,8 @@ def main():
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches_all), "clocks": clocks, "roofline": roof, "wall_s": wall,
             "phase_ms_per_step": dict(zip(["column+ratio", "work_vector", "scalars", "k1_update", "se_update",
-                                           "price+select"], [p / args.steps for p in phase[:6]])),
+                                           "price+select", "se_update:finalize+side_stream_wait",
+                                           "se_update:nu_sigma_dots"], [p / args.steps for p in phase[:8]])),
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(prob, args.rule)

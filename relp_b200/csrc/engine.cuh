@@ -72,7 +72,7 @@ struct rg_context {
     int device = 0;
     int rank = 0, world = 1;
     int row_lo = 0, nloc = 0;          // constraint rows owned by this rank
-    int c0 = 0, c1 = 0;                // provider columns priced by this rank (column-sharded pricing)
+    int d0 = 0, d1 = 0, s0 = 0, s1 = 0;  // provider columns priced by this rank: dense-block slice [d0,d1), CSC slice [s0,s1)
     void* nccl_comm = nullptr;         // ncclComm_t (world > 1)
     u64* xsend = nullptr;              // exchange buffers (world > 1)
     u64* xrecv = nullptr;

@@ -470,22 +470,27 @@ __global__ void k_gamma_init_identity_dense(int nd, int n, int m, const signed c
 // ---------------------------------------------------------------------------------------------
 // Comparators expose eligible(j) and better(j,k) (strict total order: key then index rule).
 
+// columns a rank prices: a slice of the dense block plus a slice of the CSC columns (balanced separately)
+struct ColOwn {
+    int nd, d0, d1, s0, s1;
+    __host__ __device__ bool owned(int j) const { return j < nd ? (j >= d0 && j < d1) : (j >= s0 && j < s1); }
+};
 struct PriceView {
     const u64* kappa; int LU; int n;
-    const unsigned char* inbasis;
+    const unsigned char* inbasis; ColOwn own;
     __device__ bool negative(int j) const { return (i64)kappa[(size_t)(LU - 1) * n + j] < 0; }
 };
 
 // FirstProfitable (pivot_rule.rs:95-108): lowest j with negative cost
 struct CmpFirst {
     PriceView v;
-    __device__ bool eligible(int j) const { return !v.inbasis[j] && v.negative(j); }
+    __device__ bool eligible(int j) const { return v.own.owned(j) && !v.inbasis[j] && v.negative(j); }
     __device__ bool better(int j, int k) const { return j < k; }
 };
 // FirstProfitableWithMemory (pivot_rule.rs:126-149): first after `last`, wrapping, never `last`
 struct CmpFirstMem {
     PriceView v; const Scalars* sc;
-    __device__ bool eligible(int j) const { return j != sc->last_selected && !v.inbasis[j] && v.negative(j); }
+    __device__ bool eligible(int j) const { return v.own.owned(j) && j != sc->last_selected && !v.inbasis[j] && v.negative(j); }
     __device__ int key(int j) const { int last = sc->last_selected; return j > last ? j - last : j + v.n - last; }
     __device__ bool better(int j, int k) const { return key(j) < key(k); }
 };
@@ -574,7 +579,7 @@ struct CmpRatio {
 struct CmpArtificial {
     PriceView v; const u64* nu; const Scalars* sc;
     __device__ bool eligible(int j) const {
-        if (v.inbasis[j]) return false;
+        if (!v.own.owned(j) || v.inbasis[j]) return false;
         u64 o = 0;
         for (int l = 0; l < v.LU; ++l) o |= nu[(size_t)l * v.n + j];
         bool neg = (i64)nu[(size_t)(v.LU - 1) * v.n + j] < 0;
@@ -617,14 +622,14 @@ __device__ inline double planar_log2_abs(const u64* base, size_t stride, size_t 
 
 // mode 2: Dantzig  score = log2|kappa|;  mode 3: steepest edge  score = 2 log2|kappa| - log2 Ghat
 __global__ void __launch_bounds__(256)
-k_score_columns(int n, int c0, int c1, int mode, const u64* __restrict__ kappa, int LU, const u64* __restrict__ G, int LG,
+k_score_columns(int n, ColOwn own, int mode, const u64* __restrict__ kappa, int LU, const u64* __restrict__ G, int LG,
                 const unsigned char* __restrict__ inbasis, const long long* __restrict__ wcol,
                 double* __restrict__ score, const Scalars* sc) {
     if (sc->status != ST_RUN) return;
-    int j = c0 + blockIdx.x * blockDim.x + threadIdx.x;     // this rank's columns [c0, c1)
-    if (j >= c1) return;
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
     double s = SCORE_NONE;
-    if (!inbasis[j]) {
+    if (own.owned(j) && !inbasis[j]) {
         int sg;
         double lk = planar_log2_abs(kappa, n, j, LU, &sg);
         if (sg < 0) {
@@ -1872,12 +1877,12 @@ k_gamma_init_general(const u64* __restrict__ C, size_t ps, int ld, int m, int n,
 // IMAD chains); used whenever D^2 has at most 256 trailing zero bits (E2 <= 4).
 template <int L>
 __global__ void __launch_bounds__(128)
-k_gamma_update_t(int n, int c0, int c1, const unsigned char* __restrict__ inbasis, const u64* __restrict__ nu,
+k_gamma_update_t(int n, ColOwn own, const unsigned char* __restrict__ inbasis, const u64* __restrict__ nu,
                  const u64* __restrict__ sigma, u64* __restrict__ G, const Scalars* sc) {
     constexpr int LU = L + 2, LS = 2 * L + 7, LG = 2 * L + 6, WX = LG + 4, N = 2 * WX;
     if (sc->status != ST_RUN) return;
-    int j = c0 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= c1) return;
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n || !own.owned(j)) return;
     if (inbasis[j] || j == sc->leaving) return;   // entering: None; leaving: set by k_finalize
     u32 nv[N], x[N];
     {
@@ -1945,11 +1950,11 @@ k_gamma_update_t(int n, int c0, int c1, const unsigned char* __restrict__ inbasi
 
 // per-column steepest-edge recurrence (run-time widths: O(n) work, not the hot spot)
 __global__ void __launch_bounds__(128)
-k_gamma_update(int n, int c0, int c1, int L, const unsigned char* __restrict__ inbasis, const u64* __restrict__ nu,
+k_gamma_update(int n, ColOwn own, int L, const unsigned char* __restrict__ inbasis, const u64* __restrict__ nu,
                const u64* __restrict__ sigma, u64* __restrict__ G, const Scalars* sc) {
     if (sc->status != ST_RUN) return;
-    int j = c0 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= c1) return;
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n || !own.owned(j)) return;
     if (inbasis[j] || j == sc->leaving) return;   // entering: None; leaving: set by k_finalize
     const int LU = L + 2, LS = 2 * L + 7, LG = 2 * L + 6;
     const int WX = LG + sc->E2;

@@ -247,10 +247,11 @@ extern "C" int rg_load_csc(rg_context* ctx, int32_t m, int32_t n, const int64_t*
         ctx->row_lo = std::min(m, ctx->rank * q);
         ctx->nloc = std::max(0, std::min(m, (ctx->rank + 1) * q) - ctx->row_lo);
     }
-    {   // column blocks for pricing / rule state
+    ctx->d0 = ctx->d1 = 0;          // no dense block yet: all columns are CSC columns
+    {
         int cq = (n + ctx->world - 1) / ctx->world;
-        ctx->c0 = std::min(n, ctx->rank * cq);
-        ctx->c1 = std::min(n, (ctx->rank + 1) * cq);
+        ctx->s0 = std::min(n, ctx->rank * cq);
+        ctx->s1 = std::min(n, (ctx->rank + 1) * cq);
     }
     ctx->plane = (size_t)(ctx->nloc + 1) * ctx->ld;
     long long nnz = colptr[n];
@@ -318,6 +319,14 @@ extern "C" int rg_load_dense_i8(rg_context* ctx, int32_t nd, const int8_t* colma
     k_transpose_i8<<<grid, 128, 0, ctx->stream>>>(ctx->Acm, ctx->ldc, ctx->Arm, ctx->ldr, m, nd);
     ctx->launches++;
     ctx->nd = nd;
+    {   // column ownership: the dense block and the CSC columns are split separately (balanced cost)
+        int dq = (nd + ctx->world - 1) / ctx->world;
+        ctx->d0 = std::min(nd, ctx->rank * dq);
+        ctx->d1 = std::min(nd, (ctx->rank + 1) * dq);
+        int ns = ctx->n - nd, cq = (ns + ctx->world - 1) / ctx->world;
+        ctx->s0 = nd + std::min(ns, ctx->rank * cq);
+        ctx->s1 = nd + std::min(ns, (ctx->rank + 1) * cq);
+    }
     ctx->dslices = 4;
     CK(dev_alloc(&ctx->dpart, sizeof(long long) * ctx->dslices * (2 * LW_of(ctx->L) + 1) * nd, ctx->stream));
     CK(dev_alloc(&ctx->dsum, sizeof(long long) * (2 * LW_of(RG_MAXL) + 2), ctx->stream));
@@ -412,8 +421,8 @@ static void set_status(rg_context* ctx, int st) { LAUNCH(k_set_status, 1, 1, ctx
 // `bits` points at the device-side bit-length maximum that bounds every entry of `vec`.
 template <int LV, int LO>
 static void launch_coldots(rg_context* ctx, const u64* vec, size_t vs, int cmul, u64* out, const int* bits) {
-    const int jd0 = std::min(ctx->c0, ctx->nd), jd1 = std::min(ctx->c1, ctx->nd);     // dense block part
-    const int j0 = std::max(ctx->c0, ctx->nd), j1 = ctx->c1;                           // CSC part
+    const int jd0 = ctx->d0, jd1 = ctx->d1;      // dense block slice
+    const int j0 = ctx->s0, j1 = ctx->s1;        // CSC slice
     if (jd1 > jd0) {
         int rps = (cdiv(ctx->m, ctx->dslices) + 63) / 64 * 64;     // slices start on 64-row tile boundaries
         size_t pstride = (size_t)(2 * LV + 1) * ctx->nd;
@@ -450,22 +459,24 @@ static int merge_columns(rg_context* ctx, int use_found) {
     return RG_OK;
 }
 
+static inline ColOwn own_of(rg_context* ctx) { return ColOwn{ctx->nd, ctx->d0, ctx->d1, ctx->s0, ctx->s1}; }
+
 static int launch_select(rg_context* ctx) {
-    PriceView v{ctx->kappa, LU_of(ctx->L), ctx->n, ctx->inbasis};
-    const int off = ctx->c0, cnt = std::max(ctx->c1 - ctx->c0, 0);
+    PriceView v{ctx->kappa, LU_of(ctx->L), ctx->n, ctx->inbasis, own_of(ctx)};
+    const int off = 0, cnt = ctx->n;
     const int mode = ctx->world == 1 ? 0 : 4;
     switch (ctx->rule) {
         case RG_RULE_FIRST_PROFITABLE: launch_argbest(ctx, off, cnt, CmpFirst{v}, mode); break;
         case RG_RULE_FIRST_PROFITABLE_WITH_MEMORY: launch_argbest(ctx, off, cnt, CmpFirstMem{v, ctx->sc}, mode); break;
         case RG_RULE_DANTZIG:
-            LAUNCH(k_score_columns, cdiv(std::max(cnt, 1), 256), 256, ctx->n, ctx->c0, ctx->c1, 2, ctx->kappa,
+            LAUNCH(k_score_columns, cdiv(std::max(cnt, 1), 256), 256, ctx->n, own_of(ctx), 2, ctx->kappa,
                    LU_of(ctx->L), ctx->G, LG_of(ctx->L), ctx->inbasis, ctx->weighted ? ctx->wcol : nullptr,
                    ctx->score, ctx->sc);
             LAUNCH((k_select_scored<CmpDantzig>), 1, 1024, off, cnt,
                    (CmpDantzig{v, ctx->weighted ? ctx->wcol : nullptr}), ctx->score, mode, ctx->sc);
             break;
         default:
-            LAUNCH(k_score_columns, cdiv(std::max(cnt, 1), 256), 256, ctx->n, ctx->c0, ctx->c1, 3, ctx->kappa,
+            LAUNCH(k_score_columns, cdiv(std::max(cnt, 1), 256), 256, ctx->n, own_of(ctx), 3, ctx->kappa,
                    LU_of(ctx->L), ctx->G, LG_of(ctx->L), ctx->inbasis, nullptr, ctx->score, ctx->sc);
             LAUNCH((k_select_scored<CmpSteepest>), 1, 1024, off, cnt, (CmpSteepest{v, ctx->G, LG_of(ctx->L)}),
                    ctx->score, mode, ctx->sc);
@@ -663,11 +674,13 @@ static void launch_se_dots_t(rg_context* ctx) {
 }
 template <int L>
 static void launch_gamma_update_t(rg_context* ctx) {
-    LAUNCH((k_gamma_update_t<L>), cdiv(std::max(ctx->c1 - ctx->c0, 1), 128), 128, ctx->n, ctx->c0, ctx->c1,
-           ctx->inbasis, ctx->nu, ctx->sigma, ctx->G, ctx->sc);
+    LAUNCH((k_gamma_update_t<L>), cdiv(ctx->n, 128), 128, ctx->n, own_of(ctx), ctx->inbasis, ctx->nu, ctx->sigma,
+           ctx->G, ctx->sc);
 }
 static void launch_se_update(rg_context* ctx) {
+    if (ctx->profile) cudaEventRecord(ctx->evp[5], ctx->stream);    // after finalize + wait for the side stream
     DISPATCH_L(ctx->L, launch_se_dots_t, ctx);
+    if (ctx->profile) cudaEventRecord(ctx->evp[6], ctx->stream);    // after the nu / sigma column dots
     int E2 = (2 * ctx->t_cur + 63) / 64;
     if (E2 <= 4 && ctx->L <= 8) {
         switch (ctx->L) {
@@ -677,8 +690,8 @@ static void launch_se_update(rg_context* ctx) {
             default: launch_gamma_update_t<8>(ctx); break;
         }
     } else {
-        LAUNCH(k_gamma_update, cdiv(std::max(ctx->c1 - ctx->c0, 1), 128), 128, ctx->n, ctx->c0, ctx->c1, ctx->L,
-               ctx->inbasis, ctx->nu, ctx->sigma, ctx->G, ctx->sc);
+        LAUNCH(k_gamma_update, cdiv(ctx->n, 128), 128, ctx->n, own_of(ctx), ctx->L, ctx->inbasis, ctx->nu, ctx->sigma,
+               ctx->G, ctx->sc);
     }
 }
 
@@ -816,6 +829,11 @@ static int do_pivot(rg_context* ctx, int q, int fixed_row, bool want_se, bool re
                 for (int k = 0; k < 6; ++k)
                     if (slot[k] >= 0 && cudaEventElapsedTime(&ms, seq[k], seq[k + 1]) == cudaSuccess)
                         ctx->phase_ms[slot[k]] += ms;
+                if (want_se) {   // inside phase 4: [6] bookkeeping + side-stream wait, [7] nu / sigma dots
+                    if (cudaEventElapsedTime(&ms, ctx->ev1, ctx->evp[5]) == cudaSuccess) ctx->phase_ms[6] += ms;
+                    if (cudaEventElapsedTime(&ms, ctx->evp[5], ctx->evp[6]) == cudaSuccess) ctx->phase_ms[7] += ms;
+                }
+                (void)cudaGetLastError();
             }
             ctx->identity_carry = false;
         }
@@ -1090,8 +1108,8 @@ extern "C" int rg_remove_artificial_row(rg_context* ctx, int32_t row, rg_pivot_i
     RG_TRY(launch_copyrow(ctx));
     LAUNCH(k_bp_nonzero, 1, 1, ctx->rowp, (size_t)ctx->ld, ctx->L, ctx->sc);
     DISPATCH_L(ctx->L, launch_rowdot_t, ctx);
-    PriceView v{ctx->kappa, LU_of(ctx->L), ctx->n, ctx->inbasis};
-    launch_argbest(ctx, ctx->c0, std::max(ctx->c1 - ctx->c0, 0), CmpArtificial{v, ctx->nu, ctx->sc}, 2);
+    PriceView v{ctx->kappa, LU_of(ctx->L), ctx->n, ctx->inbasis, own_of(ctx)};
+    launch_argbest(ctx, 0, ctx->n, CmpArtificial{v, ctx->nu, ctx->sc}, 2);
     if (ctx->world > 1) RG_TRY(merge_columns(ctx, 1));
     RG_TRY(sync_mirror(ctx));
     int q = ctx->hm->found;
@@ -1206,10 +1224,10 @@ extern "C" int rg_get_relative_costs(rg_context* ctx, uint64_t* out) {
     CK(cudaSetDevice(ctx->device));
     set_status(ctx, ST_RUN);
     {   // export every column: price the full range on this rank
-        int c0 = ctx->c0, c1 = ctx->c1;
-        ctx->c0 = 0; ctx->c1 = ctx->n;
+        int d0 = ctx->d0, d1 = ctx->d1, s0 = ctx->s0, s1 = ctx->s1;
+        ctx->d0 = 0; ctx->d1 = ctx->nd; ctx->s0 = ctx->nd; ctx->s1 = ctx->n;
         launch_price(ctx);
-        ctx->c0 = c0; ctx->c1 = c1;
+        ctx->d0 = d0; ctx->d1 = d1; ctx->s0 = s0; ctx->s1 = s1;
     }
     ctx->selected = false;
     return export_planar(ctx, ctx->kappa, (size_t)ctx->n, 0, 1, ctx->n, LU_of(ctx->L), out);
