@@ -57,7 +57,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def window(self, t0, t1):
+        """keep the samples taken inside the timed region [t0, t1] (the sampler itself is started before the
+        warm-up: nvidia-smi's start-up holds driver locks for ~0.5 s and would perturb a short timed region)"""
+        self.t0, self.t1 = t0, t1
 
     def stop(self):
         if self.proc is None:
@@ -68,7 +73,11 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        t0, t1 = getattr(self, "t0", None), getattr(self, "t1", None)
+        inside = [ln for (ts, ln) in self.lines if t0 is None or t0 <= ts <= t1 + 0.1]
+        if not inside:      # region shorter than one sampling period: take the samples nearest to it
+            inside = [ln for (_, ln) in self.lines[-2:]]
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -174,7 +183,7 @@ def workload_config(args, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="sparse4k", choices=sorted(WORKLOADS))
     ap.add_argument("--rule", default="steepest_edge")
@@ -223,14 +232,16 @@ def main():
 
     def step():
         nid = share_id()
-        return relp_b200.solve_relaxation(prob, rule=args.rule, device=local, profile=True, rank=rank,
+        return relp_b200.solve_relaxation(prob, rule=args.rule, device=local, profile=prof_level, rank=rank,
                                           world=world, nccl_id=nid)
 
+    prof_level = 1      # timed steps: CUDA events around K1 only (the roofline kernel)
+
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(args.warmup):
         g = step()
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
     t0 = time.perf_counter()
     pivots = 0
     dev_ms = 0.0
@@ -253,6 +264,7 @@ def main():
             phase[k] += g.stats["phase_ms"][k]
     barrier()
     wall = time.perf_counter() - t0
+    sampler.window(t0, t0 + wall)
     clocks = sampler.stop()
     d2h = g.stats["limbs"] * 8 * (prob.m + 2) + 4 * prob.m
 
@@ -269,6 +281,11 @@ def main():
 
     # one extra (untimed) solve with the active-column mode switched off: the dense rank-1 kernel is the one
     # whose algorithmic bytes are 16 L (m+1)^2; its CUDA-event times give the dense roofline
+    # one extra (untimed) solve with events around every phase of the iteration: the phase table
+    prof_level = 2
+    gp = step()
+    assert gp.trace == g.trace
+    phase = list(gp.stats["phase_ms"])
     gd = None
     if world == 1:
         gd = relp_b200.solve_relaxation(prob, rule=args.rule, device=local, profile=True, dense_carry=True)
@@ -328,7 +345,8 @@ def main():
             "gpu_launches": int(launches_all), "clocks": clocks, "roofline": roof, "wall_s": wall,
             "phase_ms_per_step": dict(zip(["column+ratio", "work_vector", "scalars", "k1_update", "se_update",
                                            "price+select", "se_update:finalize+side_stream_wait",
-                                           "se_update:nu_sigma_dots"], [p / args.steps for p in phase[:8]])),
+                                           "se_update:nu_sigma_dots"], phase[:8])),
+            "phase_note": "one extra untimed solve with CUDA events around every phase (ms per solve)",
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(prob, args.rule)

@@ -199,7 +199,9 @@ int rg_get_relative_costs(rg_context* ctx, uint64_t* out);
  * basic columns) */
 int rg_get_gamma(rg_context* ctx, uint64_t* out);
 int rg_get_stats(rg_context* ctx, rg_stats* out);
-/* measurement hooks (no reference counterpart): per-launch CUDA events around K1, and a stream timer */
+/* measurement hooks (no reference counterpart): on = 1 puts CUDA events around every K1 launch (rg_stats
+ * k1_ms_at_limbs), on = 2 additionally around every phase of an iteration (rg_stats phase_ms); and a
+ * stream timer */
 int rg_set_profile(rg_context* ctx, int32_t on);
 int rg_timer_start(rg_context* ctx);
 int rg_timer_stop(rg_context* ctx);

@@ -55,7 +55,7 @@ typedef struct rh_options {
     int32_t rule;                 /* RG_RULE_*; the reference hard-codes RG_RULE_STEEPEST_EDGE */
     int32_t fused;                /* 1: rg_iterate (one host sync per pivot); 0: trait-shaped calls */
     int64_t max_pivots;           /* 0 = unlimited */
-    int32_t profile;              /* 1: CUDA events around every K1 launch (rg_set_profile) */
+    int32_t profile;              /* 1: CUDA events around K1, 2: around every phase (rg_set_profile) */
     int32_t rank;                 /* row-shard rank / world (world <= 1: single GPU) */
     int32_t world;
     int32_t dense_carry;          /* see rg_options */

@@ -35,6 +35,7 @@ struct Scalars {
     int row_lo, nloc;    // this rank's block of constraint rows [row_lo, row_lo + nloc)
     int rank, world;
     int nk;              // number of non-trivial carry columns (entries of klist), column 0 included
+    int nnz_s;           // list mode: local rows with a non-zero work-vector factor (entries of nzrows)
     u64 D[RG_MAXL];          // current denominator (positive)
     u64 a[RG_MAXL + 2];      // pivot element numerator u[p] (replicated on every rank)
     u64 Dnew[RG_MAXL];       // |a|: denominator after the pivot
@@ -79,7 +80,8 @@ struct rg_context {
     size_t xbytes = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t side = nullptr;          // side stream: steepest-edge scalars overlap the K1 update
-    cudaEvent_t ev_side0 = nullptr, ev_side1 = nullptr;
+    int* nzrows = nullptr;             // list mode: compacted local rows with s_i != 0 (nloc entries)
+    cudaEvent_t ev_side0 = nullptr, ev_side1 = nullptr, ev_side2 = nullptr;
     int m = 0, n = 0;
     int ld = 0;                 // carry leading dimension in entries (multiple of 16)
     int L = 2;                  // current limb count
@@ -139,7 +141,13 @@ struct rg_context {
     int t_cur = 0;                     // ctz(D) of the current denominator (host copy)
     long long pivots = 0, promotions = 0, launches = 0;
     long long pivots_at[5] = {0, 0, 0, 0, 0};
-    bool profile = false;
+    int profile = 0;                   // 0 off, 1 events around K1 only, 2 events around every phase
+    // CUDA graphs of one fused iteration, keyed by everything that shapes the launch sequence
+    struct GraphEntry { long long key; cudaGraphExec_t exec; long long launches; };
+    std::vector<GraphEntry> graphs;
+    bool use_graphs = true;
+    bool capturing = false;
+    int nk_grid = 128;                 // list-mode grid bound (multiple of 128, >= nk + 1)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evt0 = nullptr, evt1 = nullptr;
     cudaEvent_t evp[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     double phase_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // ftran+ratio+copyrow, work, scalars, K1, finalize+SE update, price+select, mirror

@@ -250,7 +250,7 @@ extern "C" int rh_solve_relaxation(const rh_problem* problem, const rh_options* 
     try {
         relp::MatrixProvider mp{problem};
         relp::GpuCarry im(mp, *options);
-        if (options->profile) rg_set_profile(im.ctx, 1);
+        if (options->profile) rg_set_profile(im.ctx, options->profile);
         auto t1 = clk::now();
         rg_timer_start(im.ctx);
         relp::solve_relaxation(mp, *options, im, res->out);

@@ -1123,7 +1123,7 @@ k_ftran_list(const u64* __restrict__ C, size_t ps, int ld, int nrows, int m, con
 }
 
 __global__ void k_reset_iter(Scalars* sc) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) { sc->maxbits_u = 0; sc->maxbits_rowp = 0; sc->maxbits_new = 0; sc->maxbits_tmp = 0; }
+    if (threadIdx.x == 0 && blockIdx.x == 0) { sc->maxbits_u = 0; sc->maxbits_rowp = 0; sc->maxbits_new = 0; sc->maxbits_tmp = 0; sc->nnz_s = 0; }
 }
 __global__ void k_set_pq(Scalars* sc, int q, int p) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
@@ -1326,6 +1326,7 @@ k_update(u64* __restrict__ C, size_t ps, int ld, int row_first, int nrows, const
     constexpr int RT = 32;
     __shared__ u32 sBn[RT][N];
     __shared__ u32 sA[N];
+    __shared__ unsigned char sBnz[RT];     // row factor Bn_i != 0 (u_i != 0)
     if (sc->status != ST_RUN) return;
     if (sc->E != E) return;
     const int tid = threadIdx.x;
@@ -1353,8 +1354,10 @@ k_update(u64* __restrict__ C, size_t ps, int ld, int row_first, int nrows, const
 #pragma unroll
                 for (int k = 0; k < N; ++k) { u32 v = ~bn[k] + c; c = (c && v == 0) ? 1u : 0u; bn[k] = v; }
             }
+            u32 any = 0;
 #pragma unroll
-            for (int k = 0; k < N; ++k) sBn[tid][k] = bn[k];
+            for (int k = 0; k < N; ++k) { sBn[tid][k] = bn[k]; any |= bn[k]; }
+            sBnz[tid] = any != 0;
         }
     }
     __syncthreads();
@@ -1401,8 +1404,10 @@ k_update(u64* __restrict__ C, size_t ps, int ld, int row_first, int nrows, const
                     cv[0][2 * l] = (u32)v; cv[0][2 * l + 1] = (u32)(v >> 32);
                 }
             }
-            // zero skip: C[i][k] == 0 and C[p][k] == 0  =>  C'[i][k] == 0: nothing to compute or store
-            u32 nzc = rpnz;
+            // zero skip: C[i][k] == 0 and (C[p][k] == 0 or u_i == 0)  =>  C'[i][k] == 0: nothing to compute
+            // or store; rows with u_i == 0 (uniform over the block) need one product instead of two
+            const bool two = sBnz[r] != 0;
+            u32 nzc = two ? rpnz : 0u;
 #pragma unroll
             for (int c = 0; c < CP; ++c)
 #pragma unroll
@@ -1415,7 +1420,8 @@ k_update(u64* __restrict__ C, size_t ps, int ld, int row_first, int nrows, const
 #pragma unroll
                 for (int k = 2 * L; k < N; ++k) cv[c][k] = sg;
                 u32 X[N];
-                mp_mul2_lo<N>(X, cv[c], sA, rp[c], sBn[r]);
+                if (two) mp_mul2_lo<N>(X, cv[c], sA, rp[c], sBn[r]);
+                else mp_mul_lo<N>(X, cv[c], sA);
                 u32 o[2 * L];
                 if (E == 0) {
 #pragma unroll
@@ -1627,9 +1633,106 @@ k_colsum1(const u64* __restrict__ C, size_t ps, int ld, int m, int rows_per_chun
     if (k < ld) store_planar<LOUT>(part + (size_t)blockIdx.y * LOUT * pcols, (size_t)pcols, (size_t)(klist ? kidx : k), acc);
 }
 
+// List mode, stage 0: compact the local rows whose factor s_i is non-zero (order is irrelevant: the sums
+// below are exact integers).  sc->nnz_s is zeroed by k_reset_iter.
+template <int LSRC>
+__global__ void __launch_bounds__(256)
+k_nzrows(const u64* __restrict__ s, size_t ss, int nloc, int* __restrict__ nzrows, Scalars* sc) {
+    if (sc->status != ST_RUN) return;
+    int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+    bool nz = false;
+    if (i <= nloc) {
+        u64 o = 0;
+#pragma unroll
+        for (int l = 0; l < LSRC; ++l) o |= s[(size_t)l * ss + i];
+        nz = o != 0;
+    }
+    unsigned mask = __ballot_sync(0xffffffffu, nz);
+    if (mask == 0) return;
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&sc->nnz_s, __popc(mask));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (nz) nzrows[base + __popc(mask & ((1u << lane) - 1))] = i;
+}
+
+// List mode, stage 1+2 in one: one WARP per non-trivial column; lanes stride over the compacted non-zero
+// rows, multiply in sign-magnitude form, and the 32 partial sums are combined with a shuffle tree.
+// Writes out[k] (planar, stride ld) directly; trivial columns are left to k_colsum2.
+template <int L, int LSRC, int LOUT>
+__global__ void __launch_bounds__(128)
+k_colsum_list(const u64* __restrict__ C, size_t ps, int ld, const int* __restrict__ klist,
+              const int* __restrict__ nzrows, const u64* __restrict__ s, size_t ss, u64* __restrict__ out,
+              Scalars* sc) {
+    if (sc->status != ST_RUN) return;
+    const int lane = threadIdx.x & 31;
+    const int kidx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (kidx >= sc->nk) return;
+    const int k = klist[kidx];
+    const int nnz = sc->nnz_s;
+    u64 acc[LOUT];
+#pragma unroll
+    for (int l = 0; l < LOUT; ++l) acc[l] = 0;
+    for (int e = lane; e < nnz; e += 32) {
+        const int i = nzrows[e];
+        u64 x[L];
+        load_planar<L>(x, C, ps, (size_t)i * ld + k);
+        u64 any = 0;
+#pragma unroll
+        for (int l = 0; l < L; ++l) any |= x[l];
+        if (any == 0) continue;
+        u64 sm[LSRC];
+        load_planar<LSRC>(sm, s, ss, (size_t)i);
+        int sgn = 1;
+        if ((i64)sm[LSRC - 1] < 0) {
+            u64 c = 1;
+#pragma unroll
+            for (int l = 0; l < LSRC; ++l) { u64 v = ~sm[l] + c; c = (c && v == 0) ? 1 : 0; sm[l] = v; }
+            sgn = -sgn;
+        }
+        if ((i64)x[L - 1] < 0) {
+            u64 c = 1;
+#pragma unroll
+            for (int l = 0; l < L; ++l) { u64 v = ~x[l] + c; c = (c && v == 0) ? 1 : 0; x[l] = v; }
+            sgn = -sgn;
+        }
+        u64 pr[LSRC + L];
+        mul_full_ct<LSRC, L>(pr, sm, x);
+        if (sgn > 0) {
+            u64 cf = 0;
+#pragma unroll
+            for (int l = 0; l < LOUT; ++l) {
+                u64 b = l < LSRC + L ? pr[l] : 0;
+                u64 v = acc[l] + b; u64 c1 = v < b; u64 v2 = v + cf; u64 c2 = v2 < v;
+                acc[l] = v2; cf = c1 + c2;
+            }
+        } else {
+            u64 bf = 0;
+#pragma unroll
+            for (int l = 0; l < LOUT; ++l) {
+                u64 b = l < LSRC + L ? pr[l] : 0;
+                u64 v = acc[l] - b; u64 b1 = acc[l] < b; u64 v2 = v - bf; u64 b2 = v < bf;
+                acc[l] = v2; bf = b1 + b2;
+            }
+        }
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        u64 o[LOUT];
+#pragma unroll
+        for (int l = 0; l < LOUT; ++l) o[l] = __shfl_down_sync(0xffffffffu, acc[l], off);
+        add_n<LOUT>(acc, o);
+    }
+    if (lane == 0) {
+        store_planar<LOUT>(out, (size_t)ld, (size_t)k, acc);
+        int bl = bitlen_signed<LOUT>(acc);
+        if (bl) atomicMax(&sc->maxbits_tmp, bl);
+    }
+}
+
 // `triv` (may be null): column k is D e_k implicitly, so its column sum is s_k * D, contributed by the rank
 // that owns row k (s: the factor vector, LSRC limbs, local row index k - row_lo).
-template <int LOUT, int LSRC = 1>
+template <int LOUT, int LSRC = 1, int LDT = 0>
 __global__ void __launch_bounds__(64)
 k_colsum2(const u64* __restrict__ part, int ld, int chunks, int negate, u64* __restrict__ out,
           Scalars* sc, const unsigned char* __restrict__ triv = nullptr, const u64* __restrict__ s = nullptr,
@@ -1649,7 +1752,28 @@ k_colsum2(const u64* __restrict__ part, int ld, int chunks, int negate, u64* __r
                 u64 any = 0;
 #pragma unroll
                 for (int l = 0; l < LSRC; ++l) any |= x[l];
-                if (any) {
+                if (any && LDT > 0) {
+                    // acc = x * D in sign-magnitude form: |x| (LSRC limbs) times D (LDT limbs), full product
+                    constexpr int LDC = LDT > 0 ? LDT : 1;
+                    u64 dd[LDC];
+#pragma unroll
+                    for (int l = 0; l < LDC; ++l) dd[l] = sc->D[l];
+                    const bool neg = (i64)x[LSRC - 1] < 0;
+                    if (neg) {
+                        u64 c = 1;
+#pragma unroll
+                        for (int l = 0; l < LSRC; ++l) { u64 v = ~x[l] + c; c = (c && v == 0) ? 1 : 0; x[l] = v; }
+                    }
+                    u64 pr[LSRC + LDC];
+                    mul_full_ct<LSRC, LDC>(pr, x, dd);
+#pragma unroll
+                    for (int l = 0; l < LOUT; ++l) acc[l] = l < LSRC + LDC ? pr[l] : 0;
+                    if (neg) {
+                        u64 c = 1;
+#pragma unroll
+                        for (int l = 0; l < LOUT; ++l) { u64 v = ~acc[l] + c; c = (c && v == 0) ? 1 : 0; acc[l] = v; }
+                    }
+                } else if (any) {
                     // acc = x * D (x signed LSRC limbs, D positive LD limbs): limb-by-limb small products
                     u64 xe[LOUT];
                     u64 sg = (i64)x[LSRC - 1] < 0 ? ~0ull : 0ull;
@@ -1661,10 +1785,21 @@ k_colsum2(const u64* __restrict__ part, int ld, int chunks, int negate, u64* __r
                     mul_lo<LOUT>(acc, xe, de);
                 }
             }
+        } else if (chunks < 0) {
+            k = ld;                                       // already written by k_colsum_list
         } else {
             const int pc = kpos ? pcols : ld;             // list mode: partials live at the list position
             const size_t idx = kpos ? (size_t)kpos[k] : (size_t)k;
-            for (int c = 0; c < chunks; ++c) {
+            int c = 0;
+            for (; c + 4 <= chunks; c += 4) {             // four chunks of loads in flight per thread
+                u64 x0[LOUT], x1[LOUT], x2[LOUT], x3[LOUT];
+                load_planar<LOUT>(x0, part + (size_t)(c + 0) * LOUT * pc, (size_t)pc, idx);
+                load_planar<LOUT>(x1, part + (size_t)(c + 1) * LOUT * pc, (size_t)pc, idx);
+                load_planar<LOUT>(x2, part + (size_t)(c + 2) * LOUT * pc, (size_t)pc, idx);
+                load_planar<LOUT>(x3, part + (size_t)(c + 3) * LOUT * pc, (size_t)pc, idx);
+                add_n<LOUT>(x0, x1); add_n<LOUT>(x2, x3); add_n<LOUT>(acc, x0); add_n<LOUT>(acc, x2);
+            }
+            for (; c < chunks; ++c) {
                 u64 x[LOUT];
                 load_planar<LOUT>(x, part + (size_t)c * LOUT * pc, (size_t)pc, idx);
                 add_n<LOUT>(acc, x);
@@ -1675,8 +1810,10 @@ k_colsum2(const u64* __restrict__ part, int ld, int chunks, int negate, u64* __r
 #pragma unroll
             for (int l = 0; l < LOUT; ++l) { u64 v = ~acc[l] + c; c = (c && v == 0) ? 1 : 0; acc[l] = v; }
         }
-        store_planar<LOUT>(out, (size_t)ld, (size_t)k, acc);
-        bl = bitlen_signed<LOUT>(acc);
+        if (k < ld) {
+            store_planar<LOUT>(out, (size_t)ld, (size_t)k, acc);
+            bl = bitlen_signed<LOUT>(acc);
+        }
     }
     bl = warp_max(bl);
     if ((threadIdx.x & 31) == 0 && bl) atomicMax(&sc->maxbits_tmp, bl);

@@ -146,6 +146,12 @@ static void free_width_buffers(rg_context* ctx) {
     ctx->kappa = ctx->nu = ctx->sigma = nullptr;
 }
 
+static double g_graph_prof[5] = {0, 0, 0, 0, 0};   // capture s, launch s, sync s, captures, launches
+static void drop_graphs(rg_context* ctx) {
+    for (auto& g : ctx->graphs) cudaGraphExecDestroy(g.exec);
+    ctx->graphs.clear();
+}
+
 extern "C" int rg_create(const rg_options* opts, rg_context** out) {
     if (!out) return RG_ERR_ARG;
     rg_context* ctx = new rg_context();
@@ -153,6 +159,7 @@ extern "C" int rg_create(const rg_options* opts, rg_context** out) {
     ctx->rank = opts ? opts->rank : 0;
     ctx->world = (opts && opts->world > 0) ? opts->world : 1;
     ctx->dense_carry_opt = opts ? opts->dense_carry : 0;
+    ctx->use_graphs = getenv("RG_NO_GRAPH") == nullptr;
     int L = (opts && opts->initial_limbs) ? opts->initial_limbs : 2;
     if (!(L == 1 || L == 2 || L == 4 || L == 8 || L == 16)) { delete ctx; return RG_ERR_ARG; }
     ctx->L = L;
@@ -163,6 +170,7 @@ extern "C" int rg_create(const rg_options* opts, rg_context** out) {
     CK(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&ctx->ev_side0, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_side1, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->ev_side2, cudaEventDisableTiming));
     CK(dev_alloc(&ctx->sc, sizeof(Scalars), ctx->stream));
     CK(cudaMemsetAsync(ctx->sc, 0, sizeof(Scalars), ctx->stream));
     CK(cudaHostAlloc(&ctx->hm, sizeof(HostMirror), cudaHostAllocMapped));
@@ -217,15 +225,19 @@ extern "C" int rg_destroy(rg_context* ctx) {
     free_dev_on(ctx->carry, ctx->stream); free_dev_on(ctx->A.colptr, ctx->stream); free_dev_on(ctx->A.rowidx, ctx->stream); free_dev_on(ctx->A.vals, ctx->stream);
     free_dev_on(ctx->cost, ctx->stream); free_dev_on(ctx->rhs, ctx->stream); free_dev_on(ctx->basis, ctx->stream); free_dev_on(ctx->inbasis, ctx->stream);
     free_dev_on(ctx->G, ctx->stream); free_dev_on(ctx->cand, ctx->stream); free_dev_on(ctx->score, ctx->stream); free_dev_on(ctx->sc, ctx->stream); free_dev_on(ctx->svec, ctx->stream);
-    free_dev_on(ctx->triv, ctx->stream); free_dev_on(ctx->klist, ctx->stream); free_dev_on(ctx->kpos, ctx->stream); free_dev_on(ctx->aq, ctx->stream);
+    free_dev_on(ctx->triv, ctx->stream); free_dev_on(ctx->klist, ctx->stream); free_dev_on(ctx->nzrows, ctx->stream); free_dev_on(ctx->kpos, ctx->stream); free_dev_on(ctx->aq, ctx->stream);
     free_dev_on(ctx->Arm, ctx->stream); free_dev_on(ctx->Acm, ctx->stream); free_dev_on(ctx->dsum, ctx->stream);
     free_dev_on(ctx->wf, ctx->stream); free_dev_on(ctx->wcol, ctx->stream); free_dev_on(ctx->artf, ctx->stream);
     free_dev_on(ctx->artcost, ctx->stream); free_dev_on(ctx->rowf, ctx->stream);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    drop_graphs(ctx);
+    if (getenv("RG_HOSTPROF"))
+        fprintf(stderr, "[hostprof] graphs: %.0f captures %.3f s, %.0f launches %.3f s enqueue + %.3f s sync (cumulative)\n",
+                g_graph_prof[3], g_graph_prof[0], g_graph_prof[4], g_graph_prof[1], g_graph_prof[2]);
     if (ctx->hm) cudaFreeHost(ctx->hm);
     if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); for (int k = 0; k < 8; ++k) cudaEventDestroy(ctx->evp[k]); }
     if (ctx->evt0) { cudaEventDestroy(ctx->evt0); cudaEventDestroy(ctx->evt1); }
-    if (ctx->ev_side0) { cudaEventDestroy(ctx->ev_side0); cudaEventDestroy(ctx->ev_side1); }
+    if (ctx->ev_side0) { cudaEventDestroy(ctx->ev_side0); cudaEventDestroy(ctx->ev_side1); cudaEventDestroy(ctx->ev_side2); }
     // the communicator is process-cached (see rg_create) and intentionally not destroyed here
     if (ctx->side) cudaStreamDestroy(ctx->side);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -276,6 +288,7 @@ extern "C" int rg_load_csc(rg_context* ctx, int32_t m, int32_t n, const int64_t*
     CK(dev_alloc(&ctx->svec, sizeof(u64) * ctx->ld, ctx->stream));
     CK(dev_alloc(&ctx->triv, (size_t)ctx->ld, ctx->stream));
     CK(dev_alloc(&ctx->klist, sizeof(int) * ctx->ld, ctx->stream));
+    CK(dev_alloc(&ctx->nzrows, sizeof(int) * ctx->ld, ctx->stream));
     CK(dev_alloc(&ctx->kpos, sizeof(int) * ctx->ld, ctx->stream));
     CK(dev_alloc(&ctx->aq, sizeof(long long) * m, ctx->stream));
     CK(dev_alloc(&ctx->wf, sizeof(long long) * n, ctx->stream));
@@ -375,7 +388,7 @@ static int ensure_xbuf(rg_context* ctx, size_t send_words, size_t recv_words) {
     size_t need = std::max(send_words, recv_words) * sizeof(u64);
     if (need <= ctx->xbytes) return RG_OK;
     CK(cudaStreamSynchronize(ctx->stream));
-    free_dev_on(ctx->triv, ctx->stream); free_dev_on(ctx->klist, ctx->stream); free_dev_on(ctx->kpos, ctx->stream); free_dev_on(ctx->aq, ctx->stream);
+    free_dev_on(ctx->triv, ctx->stream); free_dev_on(ctx->klist, ctx->stream); free_dev_on(ctx->nzrows, ctx->stream); free_dev_on(ctx->kpos, ctx->stream); free_dev_on(ctx->aq, ctx->stream);
     free_dev_on(ctx->Arm, ctx->stream); free_dev_on(ctx->Acm, ctx->stream); free_dev_on(ctx->dsum, ctx->stream);
     free_dev_on(ctx->wf, ctx->stream); free_dev_on(ctx->wcol, ctx->stream); free_dev_on(ctx->artf, ctx->stream);
     free_dev_on(ctx->artcost, ctx->stream); free_dev_on(ctx->rowf, ctx->stream);
@@ -403,6 +416,10 @@ static int all_gather(rg_context* ctx, const void* send, void* recv, size_t word
     return RG_OK;
 }
 
+// profiling events: inside a stream capture they must be external event-record nodes
+static inline void rec_event(rg_context* ctx, cudaEvent_t ev) {
+    cudaEventRecordWithFlags(ev, ctx->stream, ctx->capturing ? cudaEventRecordExternal : cudaEventRecordDefault);
+}
 static inline const int* klist_of(rg_context* ctx) { return ctx->list_mode ? ctx->klist : nullptr; }
 static inline const unsigned char* triv_of(rg_context* ctx) { return ctx->list_mode ? ctx->triv : nullptr; }
 
@@ -572,7 +589,7 @@ struct ColsumGeom { int chunks, rpc, pcols, ncols; const int* klist; const int* 
 static ColsumGeom colsum_geom(rg_context* ctx) {
     ColsumGeom g;
     if (ctx->list_mode) {
-        g.chunks = ctx->list_chunks; g.pcols = ctx->list_pcols; g.ncols = ctx->nk_host + 1;
+        g.chunks = ctx->list_chunks; g.pcols = ctx->list_pcols; g.ncols = ctx->nk_grid;
         g.klist = ctx->klist; g.kpos = ctx->kpos; g.triv = ctx->triv;
     } else {
         g.chunks = ctx->work_chunks; g.pcols = ctx->ld; g.ncols = ctx->ld;
@@ -587,25 +604,42 @@ static int launch_work_t(rg_context* ctx) {
     const ColsumGeom g = colsum_geom(ctx);
     dim3 grid(cdiv(g.ncols, 128), g.chunks);
     const u64* src = ctx->u;
-    if (ctx->weighted) {
-        LAUNCH((k_scale_u<L>), cdiv(ctx->nloc + 1, 256), 256, ctx->u, (size_t)ctx->ld, ctx->nloc, ctx->rowf,
-               ctx->us2, (size_t)ctx->ld, ctx->sc);
-        LAUNCH((k_colsum1<L, LU + 1, LW>), grid, 128, ctx->carry, ctx->plane, ctx->ld, ctx->nloc, g.rpc,
-               g.klist, ctx->us2, (size_t)ctx->ld, ctx->omega_part, g.pcols, ctx->sc);
-        src = ctx->us2;
-    } else {
-        LAUNCH((k_colsum1<L, LU, LW>), grid, 128, ctx->carry, ctx->plane, ctx->ld, ctx->nloc, g.rpc,
-               g.klist, ctx->u, (size_t)ctx->ld, ctx->omega_part, g.pcols, ctx->sc);
-    }
     size_t words = (size_t)LW * ctx->ld;
     if (ctx->world > 1) RG_TRY(ensure_xbuf(ctx, words, words * ctx->world));
     u64* first_out = ctx->world == 1 ? ctx->omega : ctx->xsend;
-    if (ctx->weighted)
+    if (ctx->weighted) {
+        LAUNCH((k_scale_u<L>), cdiv(ctx->nloc + 1, 256), 256, ctx->u, (size_t)ctx->ld, ctx->nloc, ctx->rowf,
+               ctx->us2, (size_t)ctx->ld, ctx->sc);
+        src = ctx->us2;
+    }
+    if (ctx->list_mode) {
+        // non-trivial columns: compacted non-zero rows, one warp per column, written straight to the output;
+        // trivial columns: s_k * D in k_colsum2 (chunks = -1)
+        const int nl = std::max(ctx->nloc, 1);
+        if (ctx->weighted) {
+            LAUNCH((k_nzrows<LU + 1>), cdiv(nl, 256), 256, src, (size_t)ctx->ld, ctx->nloc, ctx->nzrows, ctx->sc);
+            LAUNCH((k_colsum_list<L, LU + 1, LW>), cdiv(g.ncols, 4), 128, ctx->carry, ctx->plane, ctx->ld, g.klist,
+                   ctx->nzrows, src, (size_t)ctx->ld, first_out, ctx->sc);
+            LAUNCH((k_colsum2<LW, LU + 1, L>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, -1, 0,
+                   first_out, ctx->sc, g.triv, src, (size_t)ctx->ld, L, g.kpos, g.pcols);
+        } else {
+            LAUNCH((k_nzrows<LU>), cdiv(nl, 256), 256, src, (size_t)ctx->ld, ctx->nloc, ctx->nzrows, ctx->sc);
+            LAUNCH((k_colsum_list<L, LU, LW>), cdiv(g.ncols, 4), 128, ctx->carry, ctx->plane, ctx->ld, g.klist,
+                   ctx->nzrows, src, (size_t)ctx->ld, first_out, ctx->sc);
+            LAUNCH((k_colsum2<LW, LU, L>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, -1, 0,
+                   first_out, ctx->sc, g.triv, src, (size_t)ctx->ld, L, g.kpos, g.pcols);
+        }
+    } else if (ctx->weighted) {
+        LAUNCH((k_colsum1<L, LU + 1, LW>), grid, 128, ctx->carry, ctx->plane, ctx->ld, ctx->nloc, g.rpc,
+               g.klist, ctx->us2, (size_t)ctx->ld, ctx->omega_part, g.pcols, ctx->sc);
         LAUNCH((k_colsum2<LW, LU + 1>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, g.chunks, 0,
                first_out, ctx->sc, g.triv, src, (size_t)ctx->ld, L, g.kpos, g.pcols);
-    else
+    } else {
+        LAUNCH((k_colsum1<L, LU, LW>), grid, 128, ctx->carry, ctx->plane, ctx->ld, ctx->nloc, g.rpc,
+               g.klist, ctx->u, (size_t)ctx->ld, ctx->omega_part, g.pcols, ctx->sc);
         LAUNCH((k_colsum2<LW, LU>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, g.chunks, 0,
                first_out, ctx->sc, g.triv, src, (size_t)ctx->ld, L, g.kpos, g.pcols);
+    }
     if (ctx->world == 1) return RG_OK;
     RG_TRY(all_gather(ctx, ctx->xsend, ctx->xrecv, words));
     LAUNCH((k_colsum2<LW>), cdiv(ctx->ld, 64), 64, ctx->xrecv, ctx->ld, ctx->world, 0, ctx->omega, ctx->sc);
@@ -638,7 +672,7 @@ static void launch_update_le(rg_context* ctx) {
         LAUNCH((k_update<L, E, CP>), g0, 256, ctx->carry, ctx->plane, ctx->ld, 0, 1, (const int*)nullptr, ctx->u,
                (size_t)ctx->ld, ctx->rowp, (size_t)ctx->ld, ctx->sc);
         if (ctx->nloc > 0) {
-            dim3 g1(cdiv(ctx->nk_host + 1, 256), cdiv(ctx->nloc, 32));
+            dim3 g1(cdiv(ctx->nk_grid, 256), cdiv(ctx->nloc, 32));
             LAUNCH((k_update<L, E, 1>), g1, 256, ctx->carry, ctx->plane, ctx->ld, 1, ctx->nloc + 1,
                    (const int*)ctx->klist, ctx->u, (size_t)ctx->ld, ctx->rowp, (size_t)ctx->ld, ctx->sc);
         }
@@ -678,9 +712,9 @@ static void launch_gamma_update_t(rg_context* ctx) {
            ctx->G, ctx->sc);
 }
 static void launch_se_update(rg_context* ctx) {
-    if (ctx->profile) cudaEventRecord(ctx->evp[5], ctx->stream);    // after finalize + wait for the side stream
+    if (ctx->profile >= 2) rec_event(ctx, ctx->evp[5]);    // after finalize + wait for the side stream
     DISPATCH_L(ctx->L, launch_se_dots_t, ctx);
-    if (ctx->profile) cudaEventRecord(ctx->evp[6], ctx->stream);    // after the nu / sigma column dots
+    if (ctx->profile >= 2) rec_event(ctx, ctx->evp[6]);    // after the nu / sigma column dots
     int E2 = (2 * ctx->t_cur + 63) / 64;
     if (E2 <= 4 && ctx->L <= 8) {
         switch (ctx->L) {
@@ -722,13 +756,13 @@ static int promote(rg_context* ctx) {
     RG_TRY(alloc_width_buffers(ctx, Lnew));
     ctx->promotions++;
     ctx->have_column = false;
+    drop_graphs(ctx);   // buffers moved: captured pointers are stale
     return RG_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
 // one basis change on the device.  q < 0: use the selected column sc->q.  fixed_row < 0: ratio test.
 // ------------------------------------------------------------------------------------------------
-static double g_hostprof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 static inline double now_s() {
     timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec;
 }
@@ -742,65 +776,108 @@ static int switch_to_dense(rg_context* ctx) {
     return RG_OK;
 }
 
+// the launch sequence of one iteration (no synchronisation): pivot column, ratio test, row staging, work
+// vector, scalars, K1, bookkeeping, rule update, pricing of the next iteration
+static int enqueue_iteration(rg_context* ctx, int q, int fixed_row, bool want_se, bool reselect, int E) {
+    const bool prof = ctx->profile >= 2, prof1 = ctx->profile >= 1;
+    if (prof) rec_event(ctx, ctx->evp[0]);
+    LAUNCH(k_reset_iter, 1, 1, ctx->sc);
+    launch_ftran(ctx, q);
+    if (fixed_row < 0) RG_TRY(launch_ratio(ctx));
+    else RG_TRY(launch_fixed_row(ctx, fixed_row));
+    if (ctx->list_mode) {   // the pivot row's own column stops being trivial: materialise and list it
+        LAUNCH(k_materialise_pivot_column, cdiv(std::max(ctx->nloc, 1), 256), 256, ctx->carry, ctx->plane,
+               ctx->ld, ctx->L, ctx->triv, ctx->sc);
+        LAUNCH(k_activate_pivot_column, 1, 1, ctx->triv, ctx->klist, ctx->kpos, ctx->sc);
+    }
+    RG_TRY(launch_copyrow(ctx));
+    if (prof) rec_event(ctx, ctx->evp[1]);
+    if (want_se) {
+        // the pivot scalars need only a, D and the tracked bit lengths: they run on the side stream while
+        // the main stream builds the work vector; K1 joins after k_scalars, the bookkeeping after
+        // k_scalars_se (which overlaps K1)
+        cudaEventRecord(ctx->ev_side0, ctx->stream);
+        cudaStreamWaitEvent(ctx->side, ctx->ev_side0, 0);
+        k_scalars<<<1, 1, 0, ctx->side>>>(ctx->L, E, ctx->sc);
+        cudaEventRecord(ctx->ev_side2, ctx->side);
+        k_scalars_se<<<1, 32, 0, ctx->side>>>(ctx->L, ctx->world == 1 ? ctx->G : nullptr, ctx->n, ctx->sc);
+        ctx->launches += 2;
+        cudaEventRecord(ctx->ev_side1, ctx->side);
+        RG_TRY(launch_work(ctx));
+        if (prof) rec_event(ctx, ctx->evp[2]);
+        cudaStreamWaitEvent(ctx->stream, ctx->ev_side2, 0);
+    } else {
+        if (prof) rec_event(ctx, ctx->evp[2]);
+        LAUNCH(k_scalars, 1, 1, ctx->L, E, ctx->sc);
+    }
+    if (prof1) rec_event(ctx, ctx->ev0);
+    launch_update(ctx, E);
+    if (prof1) rec_event(ctx, ctx->ev1);
+    if (want_se) cudaStreamWaitEvent(ctx->stream, ctx->ev_side1, 0);
+    LAUNCH(k_finalize, 1, 1, ctx->basis, ctx->inbasis, ctx->L, ctx->G, ctx->n, LG_of(ctx->L),
+           want_se ? 1 : 0, ctx->weighted ? ctx->wf : nullptr, ctx->weighted ? ctx->rowf : nullptr, ctx->sc,
+           ctx->hm_dev);
+    if (want_se) launch_se_update(ctx);
+    if (prof) rec_event(ctx, ctx->evp[3]);
+    if (reselect) { launch_price(ctx); RG_TRY(launch_select(ctx)); }
+    if (prof) rec_event(ctx, ctx->evp[4]);
+    return RG_OK;
+}
+
 static int do_pivot(rg_context* ctx, int q, int fixed_row, bool want_se, bool reselect) {
-    static const bool hostprof = getenv("RG_HOSTPROF") != nullptr;
     for (;;) {
         if (ctx->list_mode) {
             int E_need = (ctx->t_cur + 63) / 64;
             if (ctx->nk_host + 1 > (ctx->m + 1) / 3 || pick_update_variant(ctx->L, E_need) < 0)
                 RG_TRY(switch_to_dense(ctx));
         }
-        double h0 = hostprof ? now_s() : 0;
         ctx->hm->pivoted = 0;
-        const bool prof = ctx->profile;
-        if (prof) cudaEventRecord(ctx->evp[0], ctx->stream);
-        LAUNCH(k_reset_iter, 1, 1, ctx->sc);
-        launch_ftran(ctx, q);
-        double h1 = hostprof ? now_s() : 0;
-        if (fixed_row < 0) RG_TRY(launch_ratio(ctx));
-        else RG_TRY(launch_fixed_row(ctx, fixed_row));
-        if (ctx->list_mode) {   // the pivot row's own column stops being trivial: materialise and list it
-            LAUNCH(k_materialise_pivot_column, cdiv(std::max(ctx->nloc, 1), 256), 256, ctx->carry, ctx->plane,
-                   ctx->ld, ctx->L, ctx->triv, ctx->sc);
-            LAUNCH(k_activate_pivot_column, 1, 1, ctx->triv, ctx->klist, ctx->kpos, ctx->sc);
-        }
-        double h2 = hostprof ? now_s() : 0;
-        RG_TRY(launch_copyrow(ctx));
-        double h3 = hostprof ? now_s() : 0;
-        if (prof) cudaEventRecord(ctx->evp[1], ctx->stream);
-        if (want_se) RG_TRY(launch_work(ctx));
-        double h4 = hostprof ? now_s() : 0;
-        if (prof) cudaEventRecord(ctx->evp[2], ctx->stream);
+        ctx->nk_grid = (ctx->nk_host + 2 + 127) / 128 * 128;
         int E = pick_update_variant(ctx->L, (ctx->t_cur + 63) / 64);
         if (E < 0) E = (ctx->t_cur + 63) / 64;      // generic run-time-width kernel
-        LAUNCH(k_scalars, 1, 1, ctx->L, E, ctx->sc);
-        if (want_se) {   // steepest-edge scalars on the side stream, overlapped with K1
-            cudaEventRecord(ctx->ev_side0, ctx->stream);
-            cudaStreamWaitEvent(ctx->side, ctx->ev_side0, 0);
-            k_scalars_se<<<1, 32, 0, ctx->side>>>(ctx->L, ctx->world == 1 ? ctx->G : nullptr, ctx->n, ctx->sc);
-            ctx->launches++;
-            cudaEventRecord(ctx->ev_side1, ctx->side);
-        }
-        if (prof) cudaEventRecord(ctx->ev0, ctx->stream);
-        launch_update(ctx, E);
-        if (prof) cudaEventRecord(ctx->ev1, ctx->stream);
-        if (want_se) cudaStreamWaitEvent(ctx->stream, ctx->ev_side1, 0);
-        LAUNCH(k_finalize, 1, 1, ctx->basis, ctx->inbasis, ctx->L, ctx->G, ctx->n, LG_of(ctx->L),
-               want_se ? 1 : 0, ctx->weighted ? ctx->wf : nullptr, ctx->weighted ? ctx->rowf : nullptr, ctx->sc,
-               ctx->hm_dev);
-        if (want_se) launch_se_update(ctx);
-        if (prof) cudaEventRecord(ctx->evp[3], ctx->stream);
-        if (reselect) { launch_price(ctx); RG_TRY(launch_select(ctx)); }
-        if (prof) cudaEventRecord(ctx->evp[4], ctx->stream);
-        double h5 = hostprof ? now_s() : 0;
-        RG_TRY(sync_mirror(ctx));
-        if (hostprof) {
-            double h6 = now_s();
-            g_hostprof[0] += h1 - h0; g_hostprof[1] += h2 - h1; g_hostprof[2] += h3 - h2; g_hostprof[3] += h4 - h3;
-            g_hostprof[4] += h5 - h4; g_hostprof[5] += h6 - h5; g_hostprof[6] += 1;
-            if (((long long)g_hostprof[6]) % 200 == 0)
-                fprintf(stderr, "[hostprof rank %d] n=%.0f ftran %.3f ratio %.3f copyrow %.3f work %.3f rest %.3f sync %.3f (s)\n",
-                        ctx->rank, g_hostprof[6], g_hostprof[0], g_hostprof[1], g_hostprof[2], g_hostprof[3], g_hostprof[4], g_hostprof[5]);
+        const bool graphable = ctx->use_graphs && ctx->world == 1 && q < 0 && fixed_row < 0 && reselect;
+        if (graphable) {
+            // one CUDA graph per launch shape: limb width, E variant, carry mode, list grid bound, rule, flags
+            long long key = (long long)ctx->L | ((long long)E << 8) | ((long long)(ctx->list_mode ? 1 : 0) << 16) |
+                            ((long long)(want_se ? 1 : 0) << 17) | ((long long)(ctx->profile == 1 ? 1 : 0) << 18) | ((long long)(ctx->profile >= 2 ? 1 : 0) << 22) |
+                            ((long long)(ctx->weighted ? 1 : 0) << 19) | ((long long)ctx->rule << 20) |
+                            ((long long)(want_se && (2 * ctx->t_cur + 63) / 64 > 4 ? 1 : 0) << 23) |
+                            ((long long)(ctx->list_mode ? ctx->nk_grid : 0) << 24);
+            rg_context::GraphEntry* ge = nullptr;
+            for (auto& g : ctx->graphs) if (g.key == key) ge = &g;
+            if (!ge) {
+                if (ctx->graphs.size() >= 8) { cudaGraphExecDestroy(ctx->graphs.front().exec); ctx->graphs.erase(ctx->graphs.begin()); }
+                long long before = ctx->launches;
+                double tc0 = now_s();
+                cudaGraph_t graph = nullptr;
+                CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+                ctx->capturing = true;
+                int rc = enqueue_iteration(ctx, q, fixed_row, want_se, reselect, E);
+                LAUNCH(k_mirror, 1, 1, ctx->sc, ctx->hm_dev, ctx->L);
+                ctx->capturing = false;
+                cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+                if (rc != RG_OK) return rc;
+                if (ce != cudaSuccess) { ctx->err = std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce); return RG_ERR_CUDA; }
+                cudaGraphExec_t exec = nullptr;
+                CK(cudaGraphInstantiate(&exec, graph, 0));
+                cudaGraphDestroy(graph);
+                ctx->graphs.push_back({key, exec, ctx->launches - before});
+                ctx->launches = before;
+                ge = &ctx->graphs.back();
+                g_graph_prof[0] += now_s() - tc0; g_graph_prof[3] += 1;
+            }
+            double tl0 = now_s();
+            CK(cudaGraphLaunch(ge->exec, ctx->stream));
+            double tl1 = now_s();
+            ctx->launches += ge->launches;
+            CK(cudaStreamSynchronize(ctx->stream));
+            g_graph_prof[1] += tl1 - tl0; g_graph_prof[2] += now_s() - tl1; g_graph_prof[4] += 1;
+            CK(cudaGetLastError());
+            ctx->t_cur = ctx->hm->t_next;
+            ctx->nk_host = ctx->hm->nk;
+        } else {
+            RG_TRY(enqueue_iteration(ctx, q, fixed_row, want_se, reselect, E));
+            RG_TRY(sync_mirror(ctx));
         }
         if (ctx->hm->status == ST_PROMOTE) {
             RG_TRY(promote(ctx));
@@ -824,6 +901,10 @@ static int do_pivot(rg_context* ctx, int q, int fixed_row, bool want_se, bool re
                     ctx->k1_launches[log2i(ctx->L)]++;
                     ctx->phase_ms[3] += ms;
                 }
+                (void)cudaGetLastError();
+            }
+            if (ctx->profile >= 2) {
+                float ms = 0;
                 cudaEvent_t seq[7] = {ctx->evp[0], ctx->evp[1], ctx->evp[2], ctx->ev0, ctx->ev1, ctx->evp[3], ctx->evp[4]};
                 const int slot[6] = {0, 1, 2, -1, 4, 5};
                 for (int k = 0; k < 6; ++k)
@@ -845,6 +926,7 @@ static int do_pivot(rg_context* ctx, int q, int fixed_row, bool want_se, bool re
 // constructors
 // ------------------------------------------------------------------------------------------------
 extern "C" int rg_init_identity_basis(rg_context* ctx, const int32_t* basis, const int64_t* cost) {
+    if (ctx) drop_graphs(ctx);   // state the captured launch sequence depends on may change
     if (!ctx || !ctx->carry || !basis) return RG_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     const int m = ctx->m, n = ctx->n;
@@ -923,6 +1005,7 @@ static int launch_phase_sums(rg_context* ctx) {
 }
 
 extern "C" int rg_phase_switch(rg_context* ctx, const int64_t* cost) {
+    if (ctx) drop_graphs(ctx);   // state the captured launch sequence depends on may change
     if (!ctx || !ctx->carry || !cost) return RG_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemcpyAsync(ctx->cost, cost, sizeof(long long) * ctx->n, cudaMemcpyHostToDevice, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream));
@@ -976,6 +1059,7 @@ static int launch_gamma_general(rg_context* ctx) {
 }
 
 extern "C" int rg_rule_new(rg_context* ctx, int32_t rule) {
+    if (ctx) drop_graphs(ctx);   // state the captured launch sequence depends on may change
     if (!ctx || !ctx->carry || rule < 0 || rule > 3) return RG_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     ctx->rule = rule;
@@ -1096,6 +1180,7 @@ extern "C" int rg_iterate(rg_context* ctx, int64_t max_pivots, rg_pivot_info* tr
 }
 
 extern "C" int rg_remove_artificial_row(rg_context* ctx, int32_t row, rg_pivot_info* info) {
+    if (ctx) drop_graphs(ctx);   // state the captured launch sequence depends on may change
     if (!ctx || !ctx->carry || row < 0 || row >= ctx->m || !info) return RG_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     set_status(ctx, ST_RUN);
@@ -1261,7 +1346,7 @@ extern "C" int rg_set_profile(rg_context* ctx, int32_t on) {
         CK(cudaEventCreate(&ctx->ev0)); CK(cudaEventCreate(&ctx->ev1));
         for (int k = 0; k < 8; ++k) CK(cudaEventCreate(&ctx->evp[k]));
     }
-    ctx->profile = on != 0;
+    ctx->profile = on < 0 ? 0 : (on > 2 ? 2 : on);
     return RG_OK;
 }
 extern "C" int rg_timer_start(rg_context* ctx) {

@@ -171,7 +171,7 @@ def solve_relaxation(problem, rule="steepest_edge", fused=True, initial_limbs=0,
         idbuf = C.create_string_buffer(bytes(nccl_id), 128)
     opts = _lib.rh_options(device=device, initial_limbs=initial_limbs, rule=RULES[rule],
                            fused=1 if fused else 0, max_pivots=max_pivots,
-                           profile=1 if profile else 0, rank=rank, world=world,
+                           profile=int(profile), rank=rank, world=world,
                            dense_carry=1 if dense_carry else 0,
                            nccl_unique_id=C.cast(idbuf, C.c_void_p) if idbuf is not None else None)
     handle = C.c_void_p()

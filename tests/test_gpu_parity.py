@@ -199,3 +199,26 @@ def test_dense_int8_block_matches_csc_and_oracle(seed):
     for limbs in (1, 2):
         check(problem=prob, rules=["steepest_edge", "dantzig", "first_profitable"], modes=(True, False),
               initial_limbs=limbs)
+
+
+@pytest.mark.parametrize("dense_carry", [0, 1])
+def test_graph_replay_matches_eager_launches(dense_carry, monkeypatch):
+    """The fused loop replays one CUDA graph per launch shape; RG_NO_GRAPH=1 enqueues the same kernels
+    eagerly.  Both must give the oracle's trace (and so each other's), across promotions and list growth."""
+    from relp_b200.generators import bounded_lp
+    import relp_b200
+    prob = bounded_lp(160, 240, k_bounding=16, nnz_per_col=4, seed=5)
+    runs = []
+    for no_graph in (False, True):
+        if no_graph:
+            monkeypatch.setenv("RG_NO_GRAPH", "1")
+        else:
+            monkeypatch.delenv("RG_NO_GRAPH", raising=False)
+        for rule in ("steepest_edge", "dantzig"):
+            g = relp_b200.solve_relaxation(prob, rule=rule, fused=True, initial_limbs=1, dense_carry=dense_carry)
+            runs.append((rule, g.status, g.trace, g.objective, g.bfs))
+    half = len(runs) // 2
+    assert runs[:half] == runs[half:]
+    for rule, status, trace, objective, bfs in runs[:half]:
+        ores, otrace = oracle_trace(provider_from_problem(prob), rule)
+        assert status == ores.status and trace == otrace and objective == ores.objective and bfs == ores.bfs
