@@ -46,12 +46,19 @@ class ClockSampler:
         self.lines = []
 
     def start(self):
+        if os.environ.get("BENCH_NO_SAMPLER"):
+            return
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", os.environ.get("BENCH_SAMPLER_MS", "200"),
                  "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
+            # nvidia-smi takes a second or two to attach (driver locks held meanwhile): wait for its first
+            # sample so that its start-up does not fall into the warm-up / timed region
+            t_end = time.perf_counter() + 15.0
+            while not self.lines and time.perf_counter() < t_end and self.proc.poll() is None:
+                time.sleep(0.05)
         except Exception:
             self.proc = None
 
@@ -345,7 +352,7 @@ def main():
             "gpu_launches": int(launches_all), "clocks": clocks, "roofline": roof, "wall_s": wall,
             "phase_ms_per_step": dict(zip(["column+ratio", "work_vector", "scalars", "k1_update", "se_update",
                                            "price+select", "se_update:finalize+side_stream_wait",
-                                           "se_update:nu_sigma_dots"], phase[:8])),
+                                           "se_update:gamma_recurrence"], phase[:8])),
             "phase_note": "one extra untimed solve with CUDA events around every phase (ms per solve)",
         }
         if not args.no_cpu_baseline and world == 1:

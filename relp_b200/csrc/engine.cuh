@@ -81,7 +81,8 @@ struct rg_context {
     cudaStream_t stream = nullptr;
     cudaStream_t side = nullptr;          // side stream: steepest-edge scalars overlap the K1 update
     int* nzrows = nullptr;             // list mode: compacted local rows with s_i != 0 (nloc entries)
-    cudaEvent_t ev_side0 = nullptr, ev_side1 = nullptr, ev_side2 = nullptr;
+    cudaEvent_t ev_side0 = nullptr, ev_side1 = nullptr, ev_side2 = nullptr, ev_work = nullptr, ev_side3 = nullptr;
+    cudaStream_t side2 = nullptr;      // second side stream: nu / sigma column dots, concurrent with K1
     int m = 0, n = 0;
     int ld = 0;                 // carry leading dimension in entries (multiple of 16)
     int L = 2;                  // current limb count
@@ -119,6 +120,8 @@ struct rg_context {
     signed char* Arm = nullptr; size_t ldr = 0;    // [m][ldr]
     signed char* Acm = nullptr; size_t ldc = 0;    // [nd][ldc]
     unsigned long long* dpart = nullptr; int dslices = 0;   // deferred-carry partial sums of the dense dots
+    int* dR = nullptr; size_t dR_words = 0;        // tensor-core dense dots: slice-by-column s32 products
+    unsigned char* dSl = nullptr; int* dchunk = nullptr; size_t dmp = 0;   // byte slices of the vector, chunk flags
     unsigned long long* dsum = nullptr;            // limb sums of the vector (bias removal)
     long long* cost = nullptr;  // n
     long long* rhs = nullptr;   // m

@@ -372,6 +372,151 @@ k_densedot2(const unsigned long long* __restrict__ part, size_t pstride, int sli
     store_planar<LO>(out, (size_t)n, (size_t)j, res);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Tensor-core form of the dense dots (exact): the multi-limb vector is cut into BYTE slices, and
+//     R[s][j] = sum_i slice_s(vec_i) * a_ij        (u8 x s8 -> s32, mma.sync.m16n8k32)
+// is an integer GEMM [slices x rows] x [rows x columns]; dot_j = sum_s R[s][j] 2^(8 s) is recombined with
+// carries afterwards.  vec_i is taken in two's complement over nb bytes (nb from the tracked bit-length
+// maximum): vec_i = sum_{s<nb} byte_s 2^(8s) - neg_i 2^(8 nb), so one extra 0/1 slice row carries the sign
+// and every slice row is unsigned.  |R| <= rows * 255 * 128 < 2^31 for rows <= 65536 per k-slice.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int eff_bytes(const int* bits, int LV) {
+    int need = (*bits + 1 + 7) >> 3;               // +1: sign bit
+    return need < 1 ? 1 : (need > 8 * LV ? 8 * LV : need);
+}
+// slice rows Sl[s][i] (row pitch mp, a multiple of 64; rows i >= m are zero) and one flag per 64-row chunk
+template <int LV>
+__global__ void __launch_bounds__(64)
+k_dense_slices(const u64* __restrict__ vec, size_t vs, int m, const int* bits, unsigned char* __restrict__ Sl,
+               size_t mp, int* __restrict__ chunknz, const Scalars* sc) {
+    if (sc->status != ST_RUN) return;
+    const int nb = eff_bytes(bits, LV);
+    const int nrows = ((nb + 1 + 7) >> 3) << 3;    // byte rows + sign row, padded to an n-tile of 8
+    const int i = blockIdx.x * 64 + threadIdx.x;
+    const bool in = i < m;
+    const bool neg = in && (i64)vec[(size_t)(LV - 1) * vs + 1 + i] < 0;
+    u64 any = 0;
+    const int nl = (nb + 7) >> 3;
+    for (int l = 0; l < nl; ++l) {
+        u64 v = in ? vec[(size_t)l * vs + 1 + i] : 0;
+        any |= v;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            int sidx = 8 * l + b;
+            if (sidx < nb) Sl[(size_t)sidx * mp + i] = (unsigned char)(v >> (8 * b));
+        }
+    }
+    for (int sidx = nb; sidx < nrows; ++sidx) Sl[(size_t)sidx * mp + i] = (sidx == nb && neg) ? 1 : 0;
+    int nz = __syncthreads_or(any != 0);
+    if (threadIdx.x == 0) chunknz[blockIdx.x] = nz;
+}
+
+__device__ __forceinline__ void mma_s8u8(int (&d)[4], u32 a0, u32 a1, u32 a2, u32 a3, u32 b0, u32 b1) {
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// CTA = 8 warps x 16 matrix columns (MMA M dimension); N dimension = NTC tiles of 8 slice rows; K = rows.
+// A fragments come straight from the column-major int8 block (16 contiguous rows per lane, two MMAs per
+// 128-bit load: the k order inside a chunk is a fixed permutation applied to both operands); the slice
+// chunk is staged once per CTA in shared memory.  Chunks whose vector entries are all zero are skipped.
+template <int NTC>
+__global__ void __launch_bounds__(256)
+k_dense_mma(const signed char* __restrict__ Acm, size_t ldc, int jd0, int jd1, const unsigned char* __restrict__ Sl,
+            size_t mp, const int* __restrict__ chunknz, const int* bits, int LV, int rows_per_kslice,
+            int* __restrict__ R, size_t rstride_k, int rpitch, const Scalars* sc) {
+    __shared__ __align__(16) unsigned char sB[NTC * 8][64];
+    if (sc->status != ST_RUN) return;
+    const int nb = eff_bytes(bits, LV);
+    const int nt_eff = (nb + 1 + 7) >> 3;
+    const int tile0 = blockIdx.z * NTC;
+    if (tile0 >= nt_eff) return;
+    const int ntl = min(NTC, nt_eff - tile0);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int c0 = jd0 + blockIdx.x * 128 + warp * 16 + g, c1 = c0 + 8;
+    const bool v0 = c0 < jd1, v1 = c1 < jd1;
+    int acc[NTC][4];
+#pragma unroll
+    for (int nt = 0; nt < NTC; ++nt) { acc[nt][0] = 0; acc[nt][1] = 0; acc[nt][2] = 0; acc[nt][3] = 0; }
+    const int r_begin = blockIdx.y * rows_per_kslice;
+    const int r_end = min((int)mp, r_begin + rows_per_kslice);
+    const signed char* p0 = Acm + (size_t)(v0 ? c0 : jd0) * ldc + 16 * t;
+    const signed char* p1 = Acm + (size_t)(v1 ? c1 : jd0) * ldc + 16 * t;
+    for (int R0 = r_begin; R0 < r_end; R0 += 64) {
+        if (!chunknz[R0 >> 6]) continue;           // uniform over the CTA
+        const uint4 X0 = *reinterpret_cast<const uint4*>(p0 + R0);
+        const uint4 X1 = *reinterpret_cast<const uint4*>(p1 + R0);
+        __syncthreads();
+        for (int e = threadIdx.x; e < ntl * 32; e += 256) {
+            int row = e >> 2, part = e & 3;
+            *reinterpret_cast<uint4*>(&sB[row][16 * part]) =
+                *reinterpret_cast<const uint4*>(Sl + (size_t)(tile0 * 8 + row) * mp + R0 + 16 * part);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int nt = 0; nt < NTC; ++nt) {
+            if (nt < ntl) {
+                const uint4 B = *reinterpret_cast<const uint4*>(&sB[nt * 8 + g][16 * t]);
+                mma_s8u8(acc[nt], X0.x, X1.x, X0.y, X1.y, B.x, B.y);
+                mma_s8u8(acc[nt], X0.z, X1.z, X0.w, X1.w, B.z, B.w);
+            }
+        }
+    }
+    int* base = R + (size_t)blockIdx.y * rstride_k;
+#pragma unroll
+    for (int nt = 0; nt < NTC; ++nt) {
+        if (nt < ntl) {
+            const size_t s0 = (size_t)(tile0 + nt) * 8 + 2 * t;
+            if (v0) { base[s0 * rpitch + (c0 - jd0)] = acc[nt][0]; base[(s0 + 1) * rpitch + (c0 - jd0)] = acc[nt][1]; }
+            if (v1) { base[s0 * rpitch + (c1 - jd0)] = acc[nt][2]; base[(s0 + 1) * rpitch + (c1 - jd0)] = acc[nt][3]; }
+        }
+    }
+}
+// recombination: dot_j = sum_{s<nb} R[s][j] 2^(8s) - R[nb][j] 2^(8 nb)  (+ cmul * cost_j * D), k-slices summed
+template <int LV, int LO>
+__global__ void __launch_bounds__(128)
+k_dense_combine(const int* __restrict__ R, size_t rstride_k, int kslices, int rpitch, int n, int jd0, int jd1,
+                const int* bits, const unsigned char* __restrict__ inbasis, const long long* __restrict__ cost,
+                int cmul, int LD, u64* __restrict__ out, const Scalars* sc) {
+    if (sc->status != ST_RUN) return;
+    int j = jd0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= jd1) return;
+    const int nb = eff_bytes(bits, LV);
+    u64 res[LO];
+#pragma unroll
+    for (int l = 0; l < LO; ++l) res[l] = 0;
+    if (!inbasis[j]) {
+        long long carry = 0;
+#pragma unroll
+        for (int l = 0; l < LO; ++l) {
+            u64 limb = 0;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                const int sidx = 8 * l + b;
+                long long v = 0;
+                if (sidx <= nb) {
+                    for (int k = 0; k < kslices; ++k) v += R[(size_t)k * rstride_k + (size_t)sidx * rpitch + (j - jd0)];
+                    if (sidx == nb) v = -v;
+                }
+                long long tt = carry + v;
+                limb |= (u64)(tt & 0xff) << (8 * b);
+                carry = tt >> 8;                    // arithmetic: keeps the sign
+            }
+            res[l] = limb;
+        }
+        if (cmul) {
+            long long c = cost[j];
+            if (c) {
+                u64 d[LO];
+#pragma unroll
+                for (int l = 0; l < LO; ++l) d[l] = l < LD ? sc->D[l] : 0;
+                mac_small<LO, LO>(res, d, c);
+            }
+        }
+    }
+    store_planar<LO>(out, (size_t)n, (size_t)j, res);
+}
+
 // column-major [nd][ldc] -> row-blocked [ceil(m/16)][ldr][16]: the 16 coefficients of column j in rows
 // 16b..16b+15 are contiguous, so a thread that owns column j reads 16 rows with one 128-bit load and a
 // warp reads 512 contiguous bytes
@@ -660,7 +805,9 @@ k_score_rows(int m, const u64* __restrict__ C, size_t ps, int ld, int L, const u
 // single block: max score, then exact comparison among the candidates within SCORE_EPS
 template <class Cmp>
 __global__ void __launch_bounds__(1024) k_select_scored(int off, int count, Cmp cmp,
-                                                        const double* __restrict__ score, int mode, Scalars* sc) {
+                                                        const double* __restrict__ score, int mode, Scalars* sc,
+                                                        const u64* __restrict__ take_u = nullptr,
+                                                        size_t take_us = 0, int take_LU = 0) {
     __shared__ double sd[1024];
     __shared__ int sm[1024];
     if (sc->status != ST_RUN) return;
@@ -699,6 +846,8 @@ __global__ void __launch_bounds__(1024) k_select_scored(int off, int count, Cmp 
             sc->p = bestj < 0 ? -1 : bestj + 1;
             sc->pg = bestj < 0 ? -1 : sc->row_lo + bestj + 1;
             if (bestj < 0) sc->status = ST_UNBOUNDED;
+            else if (take_u)     // the pivot element a = u[p] (what k_take_a does)
+                for (int l = 0; l < take_LU; ++l) sc->a[l] = take_u[(size_t)l * take_us + bestj + 1];
         } else if (mode == 3) {          // local candidate of a row-sharded ratio test
             sc->p = bestj < 0 ? -1 : bestj + 1;
             sc->pg = bestj < 0 ? -1 : sc->row_lo + bestj + 1;
@@ -1265,18 +1414,17 @@ __global__ void __launch_bounds__(32) k_scalars_se(int L, const u64* __restrict_
     int E2 = (t2 + 63) >> 6;
     if (E2 < 4) E2 = 4;
     const int WX = LG + E2;
+    const int W0 = min(L + sc->E, WX);
     if (lane == 0) {
         sc->t2 = t2; sc->E2 = E2;
         for (int l = 0; l < WX; ++l) { am[l] = l < L ? sc->Dnew[l] : 0; dodd[l] = l < L ? sc->D[l] : 0; }
         rt_shr(dodd, L, t);
-        u64 d0 = dodd[0], y = d0;
-        for (int it = 0; it < 6; ++it) y *= 2 - d0 * y;
-        for (int l = 0; l < WX; ++l) x[l] = 0;
-        x[0] = y;
+        // seed: k_scalars (same stream, just before) left 1/odd(D) mod 2^(64 (L+E)) in sc->Dinv
+        for (int l = 0; l < WX; ++l) x[l] = l < W0 ? sc->Dinv[l] : 0;
     }
     __syncwarp();
     // Newton: x <- x (2 - d x), doubling the number of correct limbs
-    for (int have = 1; have < WX; have *= 2) {
+    for (int have = W0; have < WX; have *= 2) {
         int want = have * 2 < WX ? have * 2 : WX;
         warp_mul_lo(tt, dodd, x, want, cols);
         if (lane == 0) {
@@ -1658,22 +1806,25 @@ k_nzrows(const u64* __restrict__ s, size_t ss, int nloc, int* __restrict__ nzrow
 
 // List mode, stage 1+2 in one: one WARP per non-trivial column; lanes stride over the compacted non-zero
 // rows, multiply in sign-magnitude form, and the 32 partial sums are combined with a shuffle tree.
-// Writes out[k] (planar, stride ld) directly; trivial columns are left to k_colsum2.
 template <int L, int LSRC, int LOUT>
 __global__ void __launch_bounds__(128)
 k_colsum_list(const u64* __restrict__ C, size_t ps, int ld, const int* __restrict__ klist,
-              const int* __restrict__ nzrows, const u64* __restrict__ s, size_t ss, u64* __restrict__ out,
-              Scalars* sc) {
+              const int* __restrict__ nzrows, const u64* __restrict__ s, size_t ss, u64* __restrict__ part,
+              int pcols, const Scalars* sc) {
     if (sc->status != ST_RUN) return;
     const int lane = threadIdx.x & 31;
     const int kidx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (kidx >= sc->nk) return;
     const int k = klist[kidx];
+    // blockIdx.y: segment of the non-zero row list (sparse factors: most segments are a handful of rows;
+    // dense factors: enough warps in flight to hide the latency of the scattered loads)
     const int nnz = sc->nnz_s;
+    const int seg_len = (nnz + gridDim.y - 1) / gridDim.y;
+    const int e0 = blockIdx.y * seg_len, e1 = min(nnz, e0 + seg_len);
     u64 acc[LOUT];
 #pragma unroll
     for (int l = 0; l < LOUT; ++l) acc[l] = 0;
-    for (int e = lane; e < nnz; e += 32) {
+    for (int e = e0 + lane; e < e1; e += 32) {
         const int i = nzrows[e];
         u64 x[L];
         load_planar<L>(x, C, ps, (size_t)i * ld + k);
@@ -1723,11 +1874,8 @@ k_colsum_list(const u64* __restrict__ C, size_t ps, int ld, const int* __restric
         for (int l = 0; l < LOUT; ++l) o[l] = __shfl_down_sync(0xffffffffu, acc[l], off);
         add_n<LOUT>(acc, o);
     }
-    if (lane == 0) {
-        store_planar<LOUT>(out, (size_t)ld, (size_t)k, acc);
-        int bl = bitlen_signed<LOUT>(acc);
-        if (bl) atomicMax(&sc->maxbits_tmp, bl);
-    }
+    // partial sums are indexed by list position, one slab per segment (summed by k_colsum2)
+    if (lane == 0) store_planar<LOUT>(part + (size_t)blockIdx.y * LOUT * pcols, (size_t)pcols, (size_t)kidx, acc);
 }
 
 // `triv` (may be null): column k is D e_k implicitly, so its column sum is s_k * D, contributed by the rank
@@ -1785,8 +1933,6 @@ k_colsum2(const u64* __restrict__ part, int ld, int chunks, int negate, u64* __r
                     mul_lo<LOUT>(acc, xe, de);
                 }
             }
-        } else if (chunks < 0) {
-            k = ld;                                       // already written by k_colsum_list
         } else {
             const int pc = kpos ? pcols : ld;             // list mode: partials live at the list position
             const size_t idx = kpos ? (size_t)kpos[k] : (size_t)k;

@@ -5,6 +5,7 @@
 #include <ctime>
 #include <cstring>
 #include <algorithm>
+#include <mutex>
 #include <vector>
 
 #include <dlfcn.h>
@@ -106,6 +107,38 @@ static cudaError_t dev_alloc(T** p, size_t bytes, cudaStream_t st) {
 }
 static void free_dev_on(void* p, cudaStream_t st) { if (p) cudaFreeAsync(p, st); }
 
+// geometry of the tensor-core dense dots for a vector of LV limbs over this rank's dense columns
+struct DenseGeom { int ncols, ntc, zs, ks, rps, rpitch; size_t rstride_k; };
+static DenseGeom dense_geom(rg_context* ctx, int LV) {
+    DenseGeom g;
+    g.ncols = ctx->d1 - ctx->d0;
+    const int nt_max = LV + 1;                         // n-tiles of 8 slice rows: ceil((8 LV + 1) / 8)
+    g.ntc = nt_max <= 20 ? nt_max : (nt_max + 1) / 2;  // per CTA (accumulator registers)
+    g.zs = cdiv(nt_max, g.ntc);
+    const int mp = (int)ctx->dmp;
+    int ks = 296 / std::max(1, cdiv(std::max(g.ncols, 1), 128) * g.zs);
+    ks = std::max(1, std::min(8, ks));
+    ks = std::max(ks, cdiv(mp, 32768));
+    g.rps = (cdiv(mp, ks) + 63) / 64 * 64;
+    g.ks = cdiv(mp, g.rps);
+    g.rpitch = std::max(g.ncols, 1);
+    g.rstride_k = (size_t)nt_max * 8 * g.rpitch;
+    return g;
+}
+static int alloc_dense_scratch(rg_context* ctx, int L) {
+    if (ctx->nd <= 0) return RG_OK;
+    ctx->dmp = ((size_t)ctx->m + 63) / 64 * 64;
+    size_t words = 0;
+    for (int LV : {L, LW_of(L)}) {
+        DenseGeom g = dense_geom(ctx, LV);
+        words = std::max(words, g.rstride_k * g.ks);
+    }
+    CK(dev_alloc(&ctx->dR, sizeof(int) * words, ctx->stream));
+    ctx->dR_words = words;
+    CK(dev_alloc(&ctx->dSl, (size_t)(LW_of(L) + 1) * 8 * ctx->dmp, ctx->stream));
+    CK(dev_alloc(&ctx->dchunk, sizeof(int) * (ctx->dmp / 64), ctx->stream));
+    return RG_OK;
+}
 static int alloc_width_buffers(rg_context* ctx, int L) {
     const size_t ld = ctx->ld;
     const size_t n = ctx->n;
@@ -119,8 +152,10 @@ static int alloc_width_buffers(rg_context* ctx, int L) {
     }
     CK(dev_alloc(&ctx->tmprow, sizeof(u64) * LU_of(L) * ld, ctx->stream));
     CK(dev_alloc(&ctx->us2, sizeof(u64) * (LU_of(L) + 1) * ld, ctx->stream));
-    if (ctx->nd > 0)
+    if (ctx->nd > 0) {
         CK(dev_alloc(&ctx->dpart, sizeof(long long) * ctx->dslices * (2 * LW_of(L) + 1) * ctx->nd, ctx->stream));
+        RG_TRY(alloc_dense_scratch(ctx, L));
+    }
     CK(dev_alloc(&ctx->kappa, sizeof(u64) * LU_of(L) * n, ctx->stream));
     CK(dev_alloc(&ctx->nu, sizeof(u64) * LU_of(L) * n, ctx->stream));
     CK(dev_alloc(&ctx->sigma, sizeof(u64) * LS_of(L) * n, ctx->stream));
@@ -139,14 +174,16 @@ static int alloc_width_buffers(rg_context* ctx, int L) {
 }
 static void free_width_buffers(rg_context* ctx) {
     free_dev_on(ctx->u, ctx->stream); free_dev_on(ctx->rowp, ctx->stream); free_dev_on(ctx->omega, ctx->stream); free_dev_on(ctx->omega_part, ctx->stream);
-    free_dev_on(ctx->tmprow, ctx->stream); free_dev_on(ctx->us2, ctx->stream); free_dev_on(ctx->dpart, ctx->stream); free_dev_on(ctx->kappa, ctx->stream); free_dev_on(ctx->nu, ctx->stream); free_dev_on(ctx->sigma, ctx->stream);
+    free_dev_on(ctx->tmprow, ctx->stream); free_dev_on(ctx->us2, ctx->stream); free_dev_on(ctx->dpart, ctx->stream); free_dev_on(ctx->dR, ctx->stream); free_dev_on(ctx->dSl, ctx->stream); free_dev_on(ctx->dchunk, ctx->stream); free_dev_on(ctx->kappa, ctx->stream); free_dev_on(ctx->nu, ctx->stream); free_dev_on(ctx->sigma, ctx->stream);
     free_dev_on(ctx->xsend, ctx->stream); free_dev_on(ctx->xrecv, ctx->stream);
     ctx->xsend = ctx->xrecv = nullptr; ctx->xbytes = 0;
-    ctx->u = ctx->rowp = ctx->omega = ctx->omega_part = ctx->tmprow = ctx->us2 = nullptr; ctx->dpart = nullptr;
+    ctx->u = ctx->rowp = ctx->omega = ctx->omega_part = ctx->tmprow = ctx->us2 = nullptr; ctx->dpart = nullptr; ctx->dR = nullptr; ctx->dSl = nullptr; ctx->dchunk = nullptr;
     ctx->kappa = ctx->nu = ctx->sigma = nullptr;
 }
 
 static double g_graph_prof[5] = {0, 0, 0, 0, 0};   // capture s, launch s, sync s, captures, launches
+static std::mutex g_hm_mutex;
+static std::vector<HostMirror*> g_hm_free[16];   // per device: recycled pinned mirrors
 static void drop_graphs(rg_context* ctx) {
     for (auto& g : ctx->graphs) cudaGraphExecDestroy(g.exec);
     ctx->graphs.clear();
@@ -171,9 +208,19 @@ extern "C" int rg_create(const rg_options* opts, rg_context** out) {
     CK(cudaEventCreateWithFlags(&ctx->ev_side0, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_side1, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_side2, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->ev_work, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->ev_side3, cudaEventDisableTiming));
+    CK(cudaStreamCreateWithFlags(&ctx->side2, cudaStreamNonBlocking));
     CK(dev_alloc(&ctx->sc, sizeof(Scalars), ctx->stream));
     CK(cudaMemsetAsync(ctx->sc, 0, sizeof(Scalars), ctx->stream));
-    CK(cudaHostAlloc(&ctx->hm, sizeof(HostMirror), cudaHostAllocMapped));
+    {   // pinned mirror: cudaHostAlloc / cudaFreeHost synchronise the whole device, so mirrors are recycled
+        std::lock_guard<std::mutex> lock(g_hm_mutex);
+        if (!g_hm_free[ctx->device & 15].empty()) {
+            ctx->hm = g_hm_free[ctx->device & 15].back();
+            g_hm_free[ctx->device & 15].pop_back();
+        }
+    }
+    if (!ctx->hm) CK(cudaHostAlloc(&ctx->hm, sizeof(HostMirror), cudaHostAllocMapped));
     memset(ctx->hm, 0, sizeof(HostMirror));
     CK(cudaHostGetDevicePointer((void**)&ctx->hm_dev, ctx->hm, 0));
     if (ctx->world > 1) {
@@ -234,10 +281,14 @@ extern "C" int rg_destroy(rg_context* ctx) {
     if (getenv("RG_HOSTPROF"))
         fprintf(stderr, "[hostprof] graphs: %.0f captures %.3f s, %.0f launches %.3f s enqueue + %.3f s sync (cumulative)\n",
                 g_graph_prof[3], g_graph_prof[0], g_graph_prof[4], g_graph_prof[1], g_graph_prof[2]);
-    if (ctx->hm) cudaFreeHost(ctx->hm);
+    if (ctx->hm) {
+        std::lock_guard<std::mutex> lock(g_hm_mutex);
+        g_hm_free[ctx->device & 15].push_back(ctx->hm);
+    }
     if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); for (int k = 0; k < 8; ++k) cudaEventDestroy(ctx->evp[k]); }
     if (ctx->evt0) { cudaEventDestroy(ctx->evt0); cudaEventDestroy(ctx->evt1); }
-    if (ctx->ev_side0) { cudaEventDestroy(ctx->ev_side0); cudaEventDestroy(ctx->ev_side1); cudaEventDestroy(ctx->ev_side2); }
+    if (ctx->ev_side0) { cudaEventDestroy(ctx->ev_side0); cudaEventDestroy(ctx->ev_side1); cudaEventDestroy(ctx->ev_side2); cudaEventDestroy(ctx->ev_work); cudaEventDestroy(ctx->ev_side3); }
+    if (ctx->side2) cudaStreamDestroy(ctx->side2);
     // the communicator is process-cached (see rg_create) and intentionally not destroyed here
     if (ctx->side) cudaStreamDestroy(ctx->side);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -321,10 +372,10 @@ extern "C" int rg_load_dense_i8(rg_context* ctx, int32_t nd, const int8_t* colma
     const int m = ctx->m;
     ctx->ldc = ((size_t)m + 15) / 16 * 16;
     ctx->ldr = ((size_t)nd + 15) / 16 * 16;
-    CK(dev_alloc(&ctx->Acm, ctx->ldc * nd, ctx->stream));
+    CK(dev_alloc(&ctx->Acm, ctx->ldc * nd + 64, ctx->stream));   // +64: the last column's 64-row chunk may overhang
     const size_t mblk = ((size_t)m + 15) / 16;
     CK(dev_alloc(&ctx->Arm, ctx->ldr * mblk * 16, ctx->stream));
-    CK(cudaMemsetAsync(ctx->Acm, 0, ctx->ldc * nd, ctx->stream));
+    CK(cudaMemsetAsync(ctx->Acm, 0, ctx->ldc * nd + 64, ctx->stream));
     CK(cudaMemsetAsync(ctx->Arm, 0, ctx->ldr * mblk * 16, ctx->stream));
     CK(cudaMemcpy2DAsync(ctx->Acm, ctx->ldc, colmajor, (size_t)m, (size_t)m, (size_t)nd, cudaMemcpyHostToDevice,
                          ctx->stream));
@@ -343,6 +394,7 @@ extern "C" int rg_load_dense_i8(rg_context* ctx, int32_t nd, const int8_t* colma
     ctx->dslices = 4;
     CK(dev_alloc(&ctx->dpart, sizeof(long long) * ctx->dslices * (2 * LW_of(ctx->L) + 1) * nd, ctx->stream));
     CK(dev_alloc(&ctx->dsum, sizeof(long long) * (2 * LW_of(RG_MAXL) + 2), ctx->stream));
+    RG_TRY(alloc_dense_scratch(ctx, ctx->L));
     CK(cudaStreamSynchronize(ctx->stream));
     return RG_OK;
 }
@@ -440,7 +492,20 @@ template <int LV, int LO>
 static void launch_coldots(rg_context* ctx, const u64* vec, size_t vs, int cmul, u64* out, const int* bits) {
     const int jd0 = ctx->d0, jd1 = ctx->d1;      // dense block slice
     const int j0 = ctx->s0, j1 = ctx->s1;        // CSC slice
-    if (jd1 > jd0) {
+    static const bool imad_path = getenv("RG_DENSE_IMAD") != nullptr;
+    if (jd1 > jd0 && !imad_path) {
+        // tensor-core path: byte slices of the vector x int8 block (exact s32 accumulation), then recombination
+        constexpr int NT_MAX = LV + 1;
+        constexpr int NTC = NT_MAX <= 20 ? NT_MAX : (NT_MAX + 1) / 2;
+        const DenseGeom g = dense_geom(ctx, LV);
+        LAUNCH((k_dense_slices<LV>), (unsigned)(ctx->dmp / 64), 64, vec, vs, ctx->m, bits, ctx->dSl, ctx->dmp,
+               ctx->dchunk, ctx->sc);
+        dim3 grid(cdiv(g.ncols, 128), g.ks, g.zs);
+        LAUNCH((k_dense_mma<NTC>), grid, 256, ctx->Acm, ctx->ldc, jd0, jd1, ctx->dSl, ctx->dmp, ctx->dchunk, bits, LV,
+               g.rps, ctx->dR, g.rstride_k, g.rpitch, ctx->sc);
+        LAUNCH((k_dense_combine<LV, LO>), cdiv(g.ncols, 128), 128, ctx->dR, g.rstride_k, g.ks, g.rpitch, ctx->n, jd0,
+               jd1, bits, ctx->inbasis, ctx->cost, cmul, ctx->L, out, ctx->sc);
+    } else if (jd1 > jd0) {
         int rps = (cdiv(ctx->m, ctx->dslices) + 63) / 64 * 64;     // slices start on 64-row tile boundaries
         size_t pstride = (size_t)(2 * LV + 1) * ctx->nd;
         dim3 grid(cdiv(jd1 - jd0, 64), ctx->dslices), block(64, (2 * LV + 1 + 15) / 16);
@@ -451,7 +516,7 @@ static void launch_coldots(rg_context* ctx, const u64* vec, size_t vs, int cmul,
                jd0, jd1, bits, ctx->dsum, ctx->inbasis, ctx->cost, cmul, ctx->L, out, ctx->sc);
     }
     if (j1 > j0)
-        LAUNCH((k_coldot<LV, LO>), cdiv(j1 - j0, 256), 256, vec, vs, ctx->n, j0, j1, ctx->A.colptr,
+        LAUNCH((k_coldot<LV, LO>), cdiv(j1 - j0, 64), 64, vec, vs, ctx->n, j0, j1, ctx->A.colptr,
                ctx->A.rowidx, ctx->A.vals, ctx->inbasis, ctx->cost, cmul, ctx->L, out, ctx->sc);
 }
 template <int L>
@@ -486,14 +551,14 @@ static int launch_select(rg_context* ctx) {
         case RG_RULE_FIRST_PROFITABLE: launch_argbest(ctx, off, cnt, CmpFirst{v}, mode); break;
         case RG_RULE_FIRST_PROFITABLE_WITH_MEMORY: launch_argbest(ctx, off, cnt, CmpFirstMem{v, ctx->sc}, mode); break;
         case RG_RULE_DANTZIG:
-            LAUNCH(k_score_columns, cdiv(std::max(cnt, 1), 256), 256, ctx->n, own_of(ctx), 2, ctx->kappa,
+            LAUNCH(k_score_columns, cdiv(std::max(cnt, 1), 64), 64, ctx->n, own_of(ctx), 2, ctx->kappa,
                    LU_of(ctx->L), ctx->G, LG_of(ctx->L), ctx->inbasis, ctx->weighted ? ctx->wcol : nullptr,
                    ctx->score, ctx->sc);
             LAUNCH((k_select_scored<CmpDantzig>), 1, 1024, off, cnt,
                    (CmpDantzig{v, ctx->weighted ? ctx->wcol : nullptr}), ctx->score, mode, ctx->sc);
             break;
         default:
-            LAUNCH(k_score_columns, cdiv(std::max(cnt, 1), 256), 256, ctx->n, own_of(ctx), 3, ctx->kappa,
+            LAUNCH(k_score_columns, cdiv(std::max(cnt, 1), 64), 64, ctx->n, own_of(ctx), 3, ctx->kappa,
                    LU_of(ctx->L), ctx->G, LG_of(ctx->L), ctx->inbasis, nullptr, ctx->score, ctx->sc);
             LAUNCH((k_select_scored<CmpSteepest>), 1, 1024, off, cnt, (CmpSteepest{v, ctx->G, LG_of(ctx->L)}),
                    ctx->score, mode, ctx->sc);
@@ -534,8 +599,8 @@ static int launch_ratio(rg_context* ctx) {
     LAUNCH(k_score_rows, cdiv(cnt, 256), 256, ctx->nloc, ctx->carry, ctx->plane, ctx->ld, ctx->L, ctx->u,
            (size_t)ctx->ld, LU_of(ctx->L), ctx->score, ctx->sc);
     if (ctx->world == 1) {
-        LAUNCH((k_select_scored<CmpRatio>), 1, 1024, 0, ctx->nloc, c, ctx->score, 1, ctx->sc);
-        LAUNCH(k_take_a, 1, 1, ctx->u, (size_t)ctx->ld, ctx->L, ctx->sc);
+        LAUNCH((k_select_scored<CmpRatio>), 1, 1024, 0, ctx->nloc, c, ctx->score, 1, ctx->sc, (const u64*)ctx->u,
+               (size_t)ctx->ld, LU_of(ctx->L));    // also takes the pivot element a = u[p]
         return RG_OK;
     }
     // row-sharded: local candidate -> all-gather -> identical deterministic reduction on every rank
@@ -613,20 +678,22 @@ static int launch_work_t(rg_context* ctx) {
         src = ctx->us2;
     }
     if (ctx->list_mode) {
-        // non-trivial columns: compacted non-zero rows, one warp per column, written straight to the output;
-        // trivial columns: s_k * D in k_colsum2 (chunks = -1)
+        // non-trivial columns: compacted non-zero rows, one warp per (column, row-list segment); k_colsum2
+        // sums the segments and adds the trivial columns (s_k * D)
         const int nl = std::max(ctx->nloc, 1);
+        const int nseg = std::max(1, std::min(ctx->list_chunks, nl / 512));
+        dim3 lgrid(cdiv(g.ncols, 4), nseg);
         if (ctx->weighted) {
             LAUNCH((k_nzrows<LU + 1>), cdiv(nl, 256), 256, src, (size_t)ctx->ld, ctx->nloc, ctx->nzrows, ctx->sc);
-            LAUNCH((k_colsum_list<L, LU + 1, LW>), cdiv(g.ncols, 4), 128, ctx->carry, ctx->plane, ctx->ld, g.klist,
-                   ctx->nzrows, src, (size_t)ctx->ld, first_out, ctx->sc);
-            LAUNCH((k_colsum2<LW, LU + 1, L>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, -1, 0,
+            LAUNCH((k_colsum_list<L, LU + 1, LW>), lgrid, 128, ctx->carry, ctx->plane, ctx->ld, g.klist,
+                   ctx->nzrows, src, (size_t)ctx->ld, ctx->omega_part, g.pcols, ctx->sc);
+            LAUNCH((k_colsum2<LW, LU + 1, L>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, nseg, 0,
                    first_out, ctx->sc, g.triv, src, (size_t)ctx->ld, L, g.kpos, g.pcols);
         } else {
             LAUNCH((k_nzrows<LU>), cdiv(nl, 256), 256, src, (size_t)ctx->ld, ctx->nloc, ctx->nzrows, ctx->sc);
-            LAUNCH((k_colsum_list<L, LU, LW>), cdiv(g.ncols, 4), 128, ctx->carry, ctx->plane, ctx->ld, g.klist,
-                   ctx->nzrows, src, (size_t)ctx->ld, first_out, ctx->sc);
-            LAUNCH((k_colsum2<LW, LU, L>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, -1, 0,
+            LAUNCH((k_colsum_list<L, LU, LW>), lgrid, 128, ctx->carry, ctx->plane, ctx->ld, g.klist,
+                   ctx->nzrows, src, (size_t)ctx->ld, ctx->omega_part, g.pcols, ctx->sc);
+            LAUNCH((k_colsum2<LW, LU, L>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, nseg, 0,
                    first_out, ctx->sc, g.triv, src, (size_t)ctx->ld, L, g.kpos, g.pcols);
         }
     } else if (ctx->weighted) {
@@ -708,13 +775,19 @@ static void launch_se_dots_t(rg_context* ctx) {
 }
 template <int L>
 static void launch_gamma_update_t(rg_context* ctx) {
-    LAUNCH((k_gamma_update_t<L>), cdiv(ctx->n, 128), 128, ctx->n, own_of(ctx), ctx->inbasis, ctx->nu, ctx->sigma,
+    LAUNCH((k_gamma_update_t<L>), cdiv(ctx->n, 64), 64, ctx->n, own_of(ctx), ctx->inbasis, ctx->nu, ctx->sigma,
            ctx->G, ctx->sc);
 }
-static void launch_se_update(rg_context* ctx) {
-    if (ctx->profile >= 2) rec_event(ctx, ctx->evp[5]);    // after finalize + wait for the side stream
+// nu_j = rowp . a_j and sigma_j = omega . a_j read only staged vectors and the constraint matrix, so they run
+// on the second side stream concurrently with K1 (LAUNCH goes to ctx->stream: swapped for the duration)
+static void launch_se_dots(rg_context* ctx) {
+    cudaStream_t main_stream = ctx->stream;
+    ctx->stream = ctx->side2;
     DISPATCH_L(ctx->L, launch_se_dots_t, ctx);
-    if (ctx->profile >= 2) rec_event(ctx, ctx->evp[6]);    // after the nu / sigma column dots
+    ctx->stream = main_stream;
+}
+static void launch_se_update(rg_context* ctx) {
+    if (ctx->profile >= 2) rec_event(ctx, ctx->evp[5]);    // after finalize + wait for the side streams
     int E2 = (2 * ctx->t_cur + 63) / 64;
     if (E2 <= 4 && ctx->L <= 8) {
         switch (ctx->L) {
@@ -727,6 +800,7 @@ static void launch_se_update(rg_context* ctx) {
         LAUNCH(k_gamma_update, cdiv(ctx->n, 128), 128, ctx->n, own_of(ctx), ctx->L, ctx->inbasis, ctx->nu, ctx->sigma,
                ctx->G, ctx->sc);
     }
+    if (ctx->profile >= 2) rec_event(ctx, ctx->evp[6]);    // after the recurrence
 }
 
 template <int L>
@@ -805,6 +879,10 @@ static int enqueue_iteration(rg_context* ctx, int q, int fixed_row, bool want_se
         cudaEventRecord(ctx->ev_side1, ctx->side);
         RG_TRY(launch_work(ctx));
         if (prof) rec_event(ctx, ctx->evp[2]);
+        cudaEventRecord(ctx->ev_work, ctx->stream);
+        cudaStreamWaitEvent(ctx->side2, ctx->ev_work, 0);
+        launch_se_dots(ctx);
+        cudaEventRecord(ctx->ev_side3, ctx->side2);
         cudaStreamWaitEvent(ctx->stream, ctx->ev_side2, 0);
     } else {
         if (prof) rec_event(ctx, ctx->evp[2]);
@@ -813,7 +891,10 @@ static int enqueue_iteration(rg_context* ctx, int q, int fixed_row, bool want_se
     if (prof1) rec_event(ctx, ctx->ev0);
     launch_update(ctx, E);
     if (prof1) rec_event(ctx, ctx->ev1);
-    if (want_se) cudaStreamWaitEvent(ctx->stream, ctx->ev_side1, 0);
+    if (want_se) {
+        cudaStreamWaitEvent(ctx->stream, ctx->ev_side1, 0);
+        cudaStreamWaitEvent(ctx->stream, ctx->ev_side3, 0);
+    }
     LAUNCH(k_finalize, 1, 1, ctx->basis, ctx->inbasis, ctx->L, ctx->G, ctx->n, LG_of(ctx->L),
            want_se ? 1 : 0, ctx->weighted ? ctx->wf : nullptr, ctx->weighted ? ctx->rowf : nullptr, ctx->sc,
            ctx->hm_dev);
