@@ -35,70 +35,114 @@ def make_problem(name, seed):
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    """Samples SM clocks and throttle reasons during the timed region: NVML in-process (the same counters
+    nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.* prints; querying only these keeps
+    the driver-lock contention with the solve low), falling back to an `nvidia-smi -lms` subprocess."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+               ("sw_power_cap", 0x4))
 
     def __init__(self, device):
         self.device = device
         self.proc = None
-        self.lines = []
+        self.nvml = None
+        self.stop_flag = False
+        self.samples = []          # (time, sm_mhz, sm_max_mhz, [reasons])
+        self.period = float(os.environ.get("BENCH_SAMPLER_MS", "100")) / 1e3
+        self.t0 = self.t1 = None
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [x for x in vis.split(",") if x.strip()]
+            if self.device < len(ids) and ids[self.device].strip().isdigit():
+                return int(ids[self.device])
+        return self.device
 
     def start(self):
         if os.environ.get("BENCH_NO_SAMPLER"):
             return
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.nvml = pynvml
+            self._nvml_sample()    # fail here rather than in the thread
+            self.th = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", os.environ.get("BENCH_SAMPLER_MS", "200"),
-                 "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
+                 str(int(self.period * 1e3)), "-i", str(self._physical_index())],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._smi_loop, daemon=True)
             self.th.start()
             # nvidia-smi takes a second or two to attach (driver locks held meanwhile): wait for its first
             # sample so that its start-up does not fall into the warm-up / timed region
             t_end = time.perf_counter() + 15.0
-            while not self.lines and time.perf_counter() < t_end and self.proc.poll() is None:
+            while not self.samples and time.perf_counter() < t_end and self.proc.poll() is None:
                 time.sleep(0.05)
         except Exception:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append((time.perf_counter(), line.strip()))
-
-    def window(self, t0, t1):
-        """keep the samples taken inside the timed region [t0, t1] (the sampler itself is started before the
-        warm-up: nvidia-smi's start-up holds driver locks for ~0.5 s and would perturb a short timed region)"""
-        self.t0, self.t1 = t0, t1
-
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
+    def _nvml_sample(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
         try:
-            self.proc.wait(timeout=2)
+            mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
         except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        t0, t1 = getattr(self, "t0", None), getattr(self, "t1", None)
-        inside = [ln for (ts, ln) in self.lines if t0 is None or t0 <= ts <= t1 + 0.1]
-        if not inside:      # region shorter than one sampling period: take the samples nearest to it
-            inside = [ln for (_, ln) in self.lines[-2:]]
-        for ln in inside:
-            f = [x.strip() for x in ln.split(",")]
+            mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        self.samples.append((time.perf_counter(), float(sm), float(mx), [nm for nm, bit in self.REASONS if mask & bit]))
+
+    def _nvml_loop(self):
+        while not self.stop_flag:
+            try:
+                self._nvml_sample()
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def _smi_loop(self):
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
+                sm, mx = float(f[1]), float(f[2])
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
-                               f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
+            rs = [nm for (nm, _), v in zip(self.REASONS, f[5:9]) if v.lower().startswith("active")]
+            self.samples.append((time.perf_counter(), sm, mx, rs))
+
+    def window(self, t0, t1):
+        """keep the samples taken inside the timed region [t0, t1] (the sampler is started before the warm-up)"""
+        self.t0, self.t1 = t0, t1
+
+    def stop(self):
+        self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        if self.nvml is None and self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        inside = [x for x in self.samples if self.t0 is None or self.t0 <= x[0] <= self.t1 + self.period]
+        if not inside:      # region shorter than one sampling period: take the samples nearest to it
+            inside = self.samples[-2:]
+        sm = sorted(x[1] for x in inside)
+        mx = [x[2] for x in inside]
+        reasons = sorted({r for x in inside for r in x[3]})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi -lms"}
 
 
 def measured_peak_hbm():

@@ -117,12 +117,9 @@ struct rg_context {
     rg::Csc A;
     // optional dense int8 block holding provider columns [0, nd): row-major and column-major copies
     int nd = 0;
-    signed char* Arm = nullptr; size_t ldr = 0;    // [m][ldr]
     signed char* Acm = nullptr; size_t ldc = 0;    // [nd][ldc]
-    unsigned long long* dpart = nullptr; int dslices = 0;   // deferred-carry partial sums of the dense dots
     int* dR = nullptr; size_t dR_words = 0;        // tensor-core dense dots: slice-by-column s32 products
     unsigned char* dSl = nullptr; int* dchunk = nullptr; size_t dmp = 0;   // byte slices of the vector, chunk flags
-    unsigned long long* dsum = nullptr;            // limb sums of the vector (bias removal)
     long long* cost = nullptr;  // n
     long long* rhs = nullptr;   // m
     int* basis = nullptr;       // m column ids

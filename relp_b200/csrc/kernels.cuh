@@ -197,182 +197,8 @@ k_coldot(const u64* __restrict__ vec, size_t vs, int n, int j0, int j1, const lo
 
 
 // ---------------------------------------------------------------------------------------------
-// Dense int8 column block (config 5: every coefficient stored, implicit row indices).
-// The block is kept twice: row-major (thread-per-column dots read it coalesced) and column-major
-// (the pivot column a_q is contiguous for FTRAN).  Products with an int8 coefficient never need
-// carries inside the loop: each 32-bit limb of the vector is multiplied into its own signed 64-bit
-// accumulator (|sum| <= m * 127 * 2^32 < 2^63 for m < 2^24) and the carries are resolved once.
-// ---------------------------------------------------------------------------------------------
-// The int8 coefficient is biased to a' = a + 128 in [0, 255] so that every product is an unsigned
-// 32 x 32 -> 64 multiply-add (one IMAD.WIDE.U32); the bias is removed with the limb sums S_k of the
-// vector (k_vecsum) and the sign of each vector entry rides along as one extra "sign extension" limb.
-//
-// Effective width: every entry of the vector fits `lveff` limbs (from the tracked bit-length maxima), so
-// only 2*lveff words plus one sign word are multiplied; word 2*lveff carries the sign extension.
-__device__ __forceinline__ int eff_limbs(const int* bits, int LV) {
-    int need = (*bits + 1 + 63) >> 6;              // +1: sign bit
-    return need < 1 ? 1 : (need > LV ? LV : need);
-}
-// limb sums of vec[1..m]: S[k] = sum_i limb32_k(vec[1+i]) for k < 2 lveff, S[2 lveff] = sum_i signword_i
-template <int LV>
-__global__ void __launch_bounds__(256) k_vecsum(const u64* __restrict__ vec, size_t vs, int m, const int* bits,
-                                                unsigned long long* __restrict__ S, const Scalars* sc) {
-    __shared__ unsigned long long red[256];
-    if (sc->status != ST_RUN) return;
-    const int lveff = eff_limbs(bits, LV), NVe = 2 * lveff;
-    const int k = blockIdx.x;                      // one block per word position
-    if (k > NVe) { if (threadIdx.x == 0) S[k] = 0; return; }
-    unsigned long long acc = 0;
-    for (int i = threadIdx.x; i < m; i += blockDim.x) {
-        if (k < NVe) {
-            u64 v = vec[(size_t)(k >> 1) * vs + 1 + i];
-            acc += (k & 1) ? (v >> 32) : (v & 0xffffffffull);
-        } else {
-            acc += ((i64)vec[(size_t)(LV - 1) * vs + 1 + i] < 0) ? 0xffffffffull : 0ull;
-        }
-    }
-    red[threadIdx.x] = acc;
-    __syncthreads();
-    for (int s2 = 128; s2 > 0; s2 >>= 1) {
-        if (threadIdx.x < s2) red[threadIdx.x] += red[threadIdx.x + s2];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) S[k] = red[0];
-}
-// stage 1: part[rs][k][j] = sum over the row slice of (a_ij + 128) * word_k(vec[1+i])  (k <= 2 lveff)
-// Block = 64 columns x G word groups of 16: a thread owns 16 accumulators of one column.  Rows whose
-// vector entry is zero are skipped (warp-uniform): the pivot row and the dual row are sparse.
-template <int LV>
-__global__ void __launch_bounds__(64 * ((2 * LV + 1 + 15) / 16))
-k_densedot1(const u64* __restrict__ vec, size_t vs, int m, int nd, int jd0, int jd1,
-            const signed char* __restrict__ Arm, size_t ldr, int rows_per_slice, const int* bits,
-            unsigned long long* __restrict__ part, size_t pstride, const unsigned char* __restrict__ inbasis,
-            const Scalars* sc) {
-    constexpr int NV = 2 * LV;
-    constexpr int G = (NV + 1 + 15) / 16;          // word groups
-    constexpr int NW = G * 16;                     // words per staged row (zero padded)
-    constexpr int RB = 64;                         // rows staged per shared-memory tile
-    constexpr int RG = 16;                         // rows whose coefficients are prefetched together
-    __shared__ __align__(16) u32 sv[RB][NW];
-    __shared__ int nzrow[RB];
-    if (sc->status != ST_RUN) return;
-    const int lveff = eff_limbs(bits, LV), NVe = 2 * lveff;
-    const int tid = threadIdx.y * 64 + threadIdx.x;
-    const int nthreads = 64 * G;
-    const int j = jd0 + blockIdx.x * 64 + threadIdx.x;      // this rank's dense columns [jd0, jd1)
-    const int g = threadIdx.y;
-    const bool active = j < jd1 && !inbasis[j] && 16 * g <= NVe;
-    const int r0 = blockIdx.y * rows_per_slice;
-    const int r1 = min(m, r0 + rows_per_slice);
-    unsigned long long acc[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) acc[k] = 0;
-    for (int base = r0; base < r1; base += RB) {
-        __syncthreads();
-        if (tid < RB) nzrow[tid] = 0;
-        __syncthreads();
-        for (int t = tid; t < RB * (lveff + 1); t += nthreads) {     // one u64 limb (two words) per step
-            int r = t / (lveff + 1), l = t % (lveff + 1);
-            bool in = base + r < r1;
-            u64 v = 0;
-            if (in) {
-                if (l < lveff) v = vec[(size_t)l * vs + 1 + base + r];
-                else v = ((i64)vec[(size_t)(LV - 1) * vs + 1 + base + r] < 0) ? 0xffffffffull : 0ull;
-            }
-            sv[r][2 * l] = (u32)v; sv[r][2 * l + 1] = (u32)(v >> 32);
-            if (v) nzrow[r] = 1;
-        }
-        // words beyond the sign word of this group's 16-word window must read as zero
-        for (int t = tid; t < RB * (NW / 2 - (lveff + 1)); t += nthreads) {
-            int r = t / (NW / 2 - (lveff + 1)), l = lveff + 1 + t % (NW / 2 - (lveff + 1));
-            sv[r][2 * l] = 0; sv[r][2 * l + 1] = 0;
-        }
-        __syncthreads();
-        if (!active) continue;
-        for (int rg = 0; rg < RB; rg += RG) {
-            if (base + rg >= r1) break;
-            // the 16 coefficients of this column in rows base+rg .. +15: one 128-bit load (row-blocked A)
-            const int4 pk = *reinterpret_cast<const int4*>(Arm + ((size_t)((base + rg) >> 4) * ldr + j) * 16);
-            signed char cb[16];
-            memcpy(cb, &pk, 16);
-#pragma unroll
-            for (int r = 0; r < RG; ++r) {
-                if (!nzrow[rg + r]) continue;             // zero vector entry (warp-uniform; also rows past the end)
-                const u32 a = (u32)((int)cb[r] + 128);
-                const uint4* row4 = reinterpret_cast<const uint4*>(&sv[rg + r][16 * g]);
-#pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) {
-                    uint4 x = row4[q4];
-                    acc[4 * q4 + 0] += (unsigned long long)a * x.x;
-                    acc[4 * q4 + 1] += (unsigned long long)a * x.y;
-                    acc[4 * q4 + 2] += (unsigned long long)a * x.z;
-                    acc[4 * q4 + 3] += (unsigned long long)a * x.w;
-                }
-            }
-        }
-    }
-    if (j < jd1) {
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            int w = 16 * g + k;
-            if (w <= NV) part[(size_t)blockIdx.y * pstride + (size_t)w * nd + j] = acc[k];
-        }
-    }
-}
-// stage 2: sum the slices, remove the bias, resolve the deferred carries, add cmul * cost_j * D
-template <int LV, int LO>
-__global__ void __launch_bounds__(128)
-k_densedot2(const unsigned long long* __restrict__ part, size_t pstride, int slices, int nd, int n, int jd0,
-            int jd1, const int* bits, const unsigned long long* __restrict__ S,
-            const unsigned char* __restrict__ inbasis, const long long* __restrict__ cost, int cmul, int LD,
-            u64* __restrict__ out, const Scalars* sc) {
-    if (sc->status != ST_RUN) return;
-    int j = jd0 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= jd1) return;
-    const int NVe = 2 * eff_limbs(bits, LV);
-    u64 res[LO];
-#pragma unroll
-    for (int l = 0; l < LO; ++l) res[l] = 0;
-    if (!inbasis[j]) {
-        // word k of the result: sum_i a_i x_ik = (sum_i a'_i x_ik) - 128 S_k; words >= NVe use the sign word
-        long long hi_word;
-        {
-            unsigned long long a = 0;
-            for (int s2 = 0; s2 < slices; ++s2) a += part[(size_t)s2 * pstride + (size_t)NVe * nd + j];
-            hi_word = (long long)(a - 128ull * S[NVe]);
-        }
-        long long carry = 0;
-        u32 limbs[2 * LO];
-#pragma unroll
-        for (int k = 0; k < 2 * LO; ++k) {
-            long long v;
-            if (k < NVe) {
-                unsigned long long a = 0;
-                for (int s2 = 0; s2 < slices; ++s2) a += part[(size_t)s2 * pstride + (size_t)k * nd + j];
-                v = (long long)(a - 128ull * S[k]);
-            } else {
-                v = hi_word;
-            }
-            long long t = carry + v;
-            limbs[k] = (u32)t;
-            carry = t >> 32;                        // arithmetic: keeps the sign
-        }
-#pragma unroll
-        for (int l = 0; l < LO; ++l) res[l] = (u64)limbs[2 * l] | ((u64)limbs[2 * l + 1] << 32);
-        if (cmul) {
-            long long c = cost[j];
-            if (c) {
-                u64 d[LO];
-#pragma unroll
-                for (int l = 0; l < LO; ++l) d[l] = l < LD ? sc->D[l] : 0;
-                mac_small<LO, LO>(res, d, c);
-            }
-        }
-    }
-    store_planar<LO>(out, (size_t)n, (size_t)j, res);
-}
-
-// ---------------------------------------------------------------------------------------------
+// Dense int8 column block (config 5: every coefficient stored column-major, implicit row indices; the
+// pivot column a_q is contiguous for FTRAN and the dots below read 16 contiguous rows per lane).
 // Tensor-core form of the dense dots (exact): the multi-limb vector is cut into BYTE slices, and
 //     R[s][j] = sum_i slice_s(vec_i) * a_ij        (u8 x s8 -> s32, mma.sync.m16n8k32)
 // is an integer GEMM [slices x rows] x [rows x columns]; dot_j = sum_s R[s][j] 2^(8 s) is recombined with
@@ -517,21 +343,6 @@ k_dense_combine(const int* __restrict__ R, size_t rstride_k, int kslices, int rp
     store_planar<LO>(out, (size_t)n, (size_t)j, res);
 }
 
-// column-major [nd][ldc] -> row-blocked [ceil(m/16)][ldr][16]: the 16 coefficients of column j in rows
-// 16b..16b+15 are contiguous, so a thread that owns column j reads 16 rows with one 128-bit load and a
-// warp reads 512 contiguous bytes
-__global__ void k_transpose_i8(const signed char* __restrict__ Acm, size_t ldc, signed char* __restrict__ Arm,
-                               size_t ldr, int m, int nd) {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    int b = blockIdx.y;
-    if (j >= nd) return;
-    signed char v[16];
-#pragma unroll
-    for (int r = 0; r < 16; ++r) v[r] = (16 * b + r < m) ? Acm[(size_t)j * ldc + 16 * b + r] : 0;
-    int4 out;
-    memcpy(&out, v, 16);
-    *reinterpret_cast<int4*>(Arm + ((size_t)b * ldr + j) * 16) = out;
-}
 
 // FTRAN of a dense column q (column-major copy): warp per carry row, lanes over the rows of a_q
 template <int L>
@@ -597,17 +408,21 @@ k_ftran_dense(const u64* __restrict__ C, size_t ps, int ld, int nrows, int m, co
 }
 
 // steepest-edge weights of the dense columns on an identity carry: Ghat_j = (W/w_j)^2 + sum_i a_ij^2
-__global__ void k_gamma_init_identity_dense(int nd, int n, int m, const signed char* __restrict__ Arm,
-                                            size_t ldr, const unsigned char* __restrict__ inbasis,
-                                            u64* __restrict__ G, int LG) {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128)
+k_gamma_init_identity_dense(int nd, int n, int m, const signed char* __restrict__ Acm, size_t ldc,
+                            const unsigned char* __restrict__ inbasis, u64* __restrict__ G, int LG) {
+    const int lane = threadIdx.x & 31;
+    const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);    // one warp per dense column
     if (j >= nd) return;
     u64 acc = 0;
     if (!inbasis[j]) {
-        acc = 1;
-        for (int i = 0; i < m; ++i) { long long a = Arm[((size_t)(i >> 4) * ldr + j) * 16 + (i & 15)]; acc += (u64)(a * a); }
+        for (int i = lane; i < m; i += 32) { long long a = Acm[(size_t)j * ldc + i]; acc += (u64)(a * a); }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
+        acc += 1;
     }
-    for (int l = 0; l < LG; ++l) G[(size_t)l * n + j] = l == 0 ? acc : 0;
+    if (lane == 0)
+        for (int l = 0; l < LG; ++l) G[(size_t)l * n + j] = l == 0 ? acc : 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1535,10 +1350,42 @@ k_update(u64* __restrict__ C, size_t ps, int ld, int row_first, int nrows, const
 #pragma unroll
             for (int k = 0; k < 2 * L; ++k) rpnz |= rp[c][k];
         const int rend = min(RT, nrows - row0);
+        // software prefetch (L <= 8): the next row's entry is in flight while this one is processed -- most
+        // entries are skipped as zeros, so the loop is a dependent load chain without it
+        constexpr bool PF = L <= 8;
+        u64 nx[PF ? CP : 1][PF ? L : 1];
+        if (PF && rend > 0) {
+            const size_t off0 = (size_t)row0 * ld + col;
+#pragma unroll
+            for (int l = 0; l < (PF ? L : 0); ++l) {
+                if (CP == 2) {
+                    ulonglong2 v = *reinterpret_cast<const ulonglong2*>(C + (size_t)l * ps + off0);
+                    nx[0][l] = v.x; nx[(PF ? CP : 1) - 1][l] = v.y;
+                } else nx[0][l] = C[(size_t)l * ps + off0];
+            }
+        }
         for (int r = 0; r < rend; ++r) {
             size_t off = (size_t)(row0 + r) * ld + col;
             u32 cv[CP][N];
-            if (CP == 2) {
+            if (PF) {
+#pragma unroll
+                for (int c = 0; c < CP; ++c)
+#pragma unroll
+                    for (int l = 0; l < L; ++l) {
+                        u64 v = nx[PF ? c : 0][PF ? l : 0];
+                        cv[c][2 * l] = (u32)v; cv[c][2 * l + 1] = (u32)(v >> 32);
+                    }
+                if (r + 1 < rend) {
+                    const size_t offn = off + ld;
+#pragma unroll
+                    for (int l = 0; l < (PF ? L : 0); ++l) {
+                        if (CP == 2) {
+                            ulonglong2 v = *reinterpret_cast<const ulonglong2*>(C + (size_t)l * ps + offn);
+                            nx[0][l] = v.x; nx[(PF ? CP : 1) - 1][l] = v.y;
+                        } else nx[0][l] = C[(size_t)l * ps + offn];
+                    }
+                }
+            } else if (CP == 2) {
 #pragma unroll
                 for (int l = 0; l < L; ++l) {
                     ulonglong2 v = *reinterpret_cast<const ulonglong2*>(C + (size_t)l * ps + off);

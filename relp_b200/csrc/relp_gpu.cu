@@ -152,10 +152,7 @@ static int alloc_width_buffers(rg_context* ctx, int L) {
     }
     CK(dev_alloc(&ctx->tmprow, sizeof(u64) * LU_of(L) * ld, ctx->stream));
     CK(dev_alloc(&ctx->us2, sizeof(u64) * (LU_of(L) + 1) * ld, ctx->stream));
-    if (ctx->nd > 0) {
-        CK(dev_alloc(&ctx->dpart, sizeof(long long) * ctx->dslices * (2 * LW_of(L) + 1) * ctx->nd, ctx->stream));
-        RG_TRY(alloc_dense_scratch(ctx, L));
-    }
+    if (ctx->nd > 0) RG_TRY(alloc_dense_scratch(ctx, L));
     CK(dev_alloc(&ctx->kappa, sizeof(u64) * LU_of(L) * n, ctx->stream));
     CK(dev_alloc(&ctx->nu, sizeof(u64) * LU_of(L) * n, ctx->stream));
     CK(dev_alloc(&ctx->sigma, sizeof(u64) * LS_of(L) * n, ctx->stream));
@@ -174,10 +171,10 @@ static int alloc_width_buffers(rg_context* ctx, int L) {
 }
 static void free_width_buffers(rg_context* ctx) {
     free_dev_on(ctx->u, ctx->stream); free_dev_on(ctx->rowp, ctx->stream); free_dev_on(ctx->omega, ctx->stream); free_dev_on(ctx->omega_part, ctx->stream);
-    free_dev_on(ctx->tmprow, ctx->stream); free_dev_on(ctx->us2, ctx->stream); free_dev_on(ctx->dpart, ctx->stream); free_dev_on(ctx->dR, ctx->stream); free_dev_on(ctx->dSl, ctx->stream); free_dev_on(ctx->dchunk, ctx->stream); free_dev_on(ctx->kappa, ctx->stream); free_dev_on(ctx->nu, ctx->stream); free_dev_on(ctx->sigma, ctx->stream);
+    free_dev_on(ctx->tmprow, ctx->stream); free_dev_on(ctx->us2, ctx->stream); free_dev_on(ctx->dR, ctx->stream); free_dev_on(ctx->dSl, ctx->stream); free_dev_on(ctx->dchunk, ctx->stream); free_dev_on(ctx->kappa, ctx->stream); free_dev_on(ctx->nu, ctx->stream); free_dev_on(ctx->sigma, ctx->stream);
     free_dev_on(ctx->xsend, ctx->stream); free_dev_on(ctx->xrecv, ctx->stream);
     ctx->xsend = ctx->xrecv = nullptr; ctx->xbytes = 0;
-    ctx->u = ctx->rowp = ctx->omega = ctx->omega_part = ctx->tmprow = ctx->us2 = nullptr; ctx->dpart = nullptr; ctx->dR = nullptr; ctx->dSl = nullptr; ctx->dchunk = nullptr;
+    ctx->u = ctx->rowp = ctx->omega = ctx->omega_part = ctx->tmprow = ctx->us2 = nullptr; ctx->dR = nullptr; ctx->dSl = nullptr; ctx->dchunk = nullptr;
     ctx->kappa = ctx->nu = ctx->sigma = nullptr;
 }
 
@@ -273,7 +270,7 @@ extern "C" int rg_destroy(rg_context* ctx) {
     free_dev_on(ctx->cost, ctx->stream); free_dev_on(ctx->rhs, ctx->stream); free_dev_on(ctx->basis, ctx->stream); free_dev_on(ctx->inbasis, ctx->stream);
     free_dev_on(ctx->G, ctx->stream); free_dev_on(ctx->cand, ctx->stream); free_dev_on(ctx->score, ctx->stream); free_dev_on(ctx->sc, ctx->stream); free_dev_on(ctx->svec, ctx->stream);
     free_dev_on(ctx->triv, ctx->stream); free_dev_on(ctx->klist, ctx->stream); free_dev_on(ctx->nzrows, ctx->stream); free_dev_on(ctx->kpos, ctx->stream); free_dev_on(ctx->aq, ctx->stream);
-    free_dev_on(ctx->Arm, ctx->stream); free_dev_on(ctx->Acm, ctx->stream); free_dev_on(ctx->dsum, ctx->stream);
+    free_dev_on(ctx->Acm, ctx->stream);
     free_dev_on(ctx->wf, ctx->stream); free_dev_on(ctx->wcol, ctx->stream); free_dev_on(ctx->artf, ctx->stream);
     free_dev_on(ctx->artcost, ctx->stream); free_dev_on(ctx->rowf, ctx->stream);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
@@ -371,17 +368,10 @@ extern "C" int rg_load_dense_i8(rg_context* ctx, int32_t nd, const int8_t* colma
     if (ctx->nd) { ctx->err = "rg_load_dense_i8: dense block already loaded"; return RG_ERR_STATE; }
     const int m = ctx->m;
     ctx->ldc = ((size_t)m + 15) / 16 * 16;
-    ctx->ldr = ((size_t)nd + 15) / 16 * 16;
     CK(dev_alloc(&ctx->Acm, ctx->ldc * nd + 64, ctx->stream));   // +64: the last column's 64-row chunk may overhang
-    const size_t mblk = ((size_t)m + 15) / 16;
-    CK(dev_alloc(&ctx->Arm, ctx->ldr * mblk * 16, ctx->stream));
     CK(cudaMemsetAsync(ctx->Acm, 0, ctx->ldc * nd + 64, ctx->stream));
-    CK(cudaMemsetAsync(ctx->Arm, 0, ctx->ldr * mblk * 16, ctx->stream));
     CK(cudaMemcpy2DAsync(ctx->Acm, ctx->ldc, colmajor, (size_t)m, (size_t)m, (size_t)nd, cudaMemcpyHostToDevice,
                          ctx->stream));
-    dim3 grid(cdiv(nd, 128), (unsigned)mblk);
-    k_transpose_i8<<<grid, 128, 0, ctx->stream>>>(ctx->Acm, ctx->ldc, ctx->Arm, ctx->ldr, m, nd);
-    ctx->launches++;
     ctx->nd = nd;
     {   // column ownership: the dense block and the CSC columns are split separately (balanced cost)
         int dq = (nd + ctx->world - 1) / ctx->world;
@@ -391,9 +381,6 @@ extern "C" int rg_load_dense_i8(rg_context* ctx, int32_t nd, const int8_t* colma
         ctx->s0 = nd + std::min(ns, ctx->rank * cq);
         ctx->s1 = nd + std::min(ns, (ctx->rank + 1) * cq);
     }
-    ctx->dslices = 4;
-    CK(dev_alloc(&ctx->dpart, sizeof(long long) * ctx->dslices * (2 * LW_of(ctx->L) + 1) * nd, ctx->stream));
-    CK(dev_alloc(&ctx->dsum, sizeof(long long) * (2 * LW_of(RG_MAXL) + 2), ctx->stream));
     RG_TRY(alloc_dense_scratch(ctx, ctx->L));
     CK(cudaStreamSynchronize(ctx->stream));
     return RG_OK;
@@ -441,7 +428,7 @@ static int ensure_xbuf(rg_context* ctx, size_t send_words, size_t recv_words) {
     if (need <= ctx->xbytes) return RG_OK;
     CK(cudaStreamSynchronize(ctx->stream));
     free_dev_on(ctx->triv, ctx->stream); free_dev_on(ctx->klist, ctx->stream); free_dev_on(ctx->nzrows, ctx->stream); free_dev_on(ctx->kpos, ctx->stream); free_dev_on(ctx->aq, ctx->stream);
-    free_dev_on(ctx->Arm, ctx->stream); free_dev_on(ctx->Acm, ctx->stream); free_dev_on(ctx->dsum, ctx->stream);
+    free_dev_on(ctx->Acm, ctx->stream);
     free_dev_on(ctx->wf, ctx->stream); free_dev_on(ctx->wcol, ctx->stream); free_dev_on(ctx->artf, ctx->stream);
     free_dev_on(ctx->artcost, ctx->stream); free_dev_on(ctx->rowf, ctx->stream);
     CK(dev_alloc(&ctx->xsend, need, ctx->stream));
@@ -492,8 +479,7 @@ template <int LV, int LO>
 static void launch_coldots(rg_context* ctx, const u64* vec, size_t vs, int cmul, u64* out, const int* bits) {
     const int jd0 = ctx->d0, jd1 = ctx->d1;      // dense block slice
     const int j0 = ctx->s0, j1 = ctx->s1;        // CSC slice
-    static const bool imad_path = getenv("RG_DENSE_IMAD") != nullptr;
-    if (jd1 > jd0 && !imad_path) {
+    if (jd1 > jd0) {
         // tensor-core path: byte slices of the vector x int8 block (exact s32 accumulation), then recombination
         constexpr int NT_MAX = LV + 1;
         constexpr int NTC = NT_MAX <= 20 ? NT_MAX : (NT_MAX + 1) / 2;
@@ -505,15 +491,6 @@ static void launch_coldots(rg_context* ctx, const u64* vec, size_t vs, int cmul,
                g.rps, ctx->dR, g.rstride_k, g.rpitch, ctx->sc);
         LAUNCH((k_dense_combine<LV, LO>), cdiv(g.ncols, 128), 128, ctx->dR, g.rstride_k, g.ks, g.rpitch, ctx->n, jd0,
                jd1, bits, ctx->inbasis, ctx->cost, cmul, ctx->L, out, ctx->sc);
-    } else if (jd1 > jd0) {
-        int rps = (cdiv(ctx->m, ctx->dslices) + 63) / 64 * 64;     // slices start on 64-row tile boundaries
-        size_t pstride = (size_t)(2 * LV + 1) * ctx->nd;
-        dim3 grid(cdiv(jd1 - jd0, 64), ctx->dslices), block(64, (2 * LV + 1 + 15) / 16);
-        LAUNCH((k_vecsum<LV>), 2 * LV + 1, 256, vec, vs, ctx->m, bits, ctx->dsum, ctx->sc);
-        LAUNCH((k_densedot1<LV>), grid, block, vec, vs, ctx->m, ctx->nd, jd0, jd1, ctx->Arm, ctx->ldr, rps, bits,
-               ctx->dpart, pstride, ctx->inbasis, ctx->sc);
-        LAUNCH((k_densedot2<LV, LO>), cdiv(jd1 - jd0, 128), 128, ctx->dpart, pstride, ctx->dslices, ctx->nd, ctx->n,
-               jd0, jd1, bits, ctx->dsum, ctx->inbasis, ctx->cost, cmul, ctx->L, out, ctx->sc);
     }
     if (j1 > j0)
         LAUNCH((k_coldot<LV, LO>), cdiv(j1 - j0, 64), 64, vec, vs, ctx->n, j0, j1, ctx->A.colptr,
@@ -916,7 +893,10 @@ static int do_pivot(rg_context* ctx, int q, int fixed_row, bool want_se, bool re
         ctx->nk_grid = (ctx->nk_host + 2 + 127) / 128 * 128;
         int E = pick_update_variant(ctx->L, (ctx->t_cur + 63) / 64);
         if (E < 0) E = (ctx->t_cur + 63) / 64;      // generic run-time-width kernel
-        const bool graphable = ctx->use_graphs && ctx->world == 1 && q < 0 && fixed_row < 0 && reselect;
+        // graphs pay when an iteration is launch-latency bound; with a large dense block the kernels run for
+        // milliseconds and eager launches on three streams overlap better (measured on config 5)
+        const bool small = (double)ctx->m * ((double)ctx->nd + ctx->m) < 1.5e8;
+        const bool graphable = ctx->use_graphs && small && ctx->world == 1 && q < 0 && fixed_row < 0 && reselect;
         if (graphable) {
             // one CUDA graph per launch shape: limb width, E variant, carry mode, list grid bound, rule, flags
             long long key = (long long)ctx->L | ((long long)E << 8) | ((long long)(ctx->list_mode ? 1 : 0) << 16) |
@@ -1149,8 +1129,8 @@ extern "C" int rg_rule_new(rg_context* ctx, int32_t rule) {
     if (rule == RG_RULE_STEEPEST_EDGE) {
         if (ctx->identity_carry) {
             if (ctx->nd > 0)
-                LAUNCH(k_gamma_init_identity_dense, cdiv(ctx->nd, 128), 128, ctx->nd, ctx->n, ctx->m, ctx->Arm,
-                       ctx->ldr, ctx->inbasis, ctx->G, LG_of(ctx->L));
+                LAUNCH(k_gamma_init_identity_dense, cdiv(ctx->nd, 4), 128, ctx->nd, ctx->n, ctx->m, ctx->Acm,
+                       ctx->ldc, ctx->inbasis, ctx->G, LG_of(ctx->L));
             if (ctx->n > ctx->nd)
                 LAUNCH(k_gamma_init_identity, cdiv(ctx->n - ctx->nd, 256), 256, ctx->n, ctx->nd, ctx->A.colptr,
                        ctx->A.rowidx, ctx->A.vals, ctx->inbasis, ctx->weighted ? ctx->wf : nullptr,

@@ -18,7 +18,8 @@ elif which == "mf":
 print("generated", which, prob.m, prob.n, prob.vals.shape, round(time.time() - t, 2), flush=True)
 maxp = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 t = time.time()
-g = relp_b200.solve_relaxation(prob, rule=rule, max_pivots=maxp)
+dense_carry = len(sys.argv) > 5 and sys.argv[5] == "dense_carry"
+g = relp_b200.solve_relaxation(prob, rule=rule, max_pivots=maxp, dense_carry=dense_carry)
 print("status", g.status, "pivots", g.pivots, "loop s", round(g.seconds, 4), "total s", round(g.seconds_total, 3),
       "wall", round(time.time() - t, 3))
 print("pivots/s", round(g.pivots / g.seconds, 1), "stats", g.stats)
