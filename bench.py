@@ -374,8 +374,17 @@ def main():
             ach = list_tab[str(Ldom)]["GB/s"]
             kern = f"k_update<L={Ldom}> active-column mode"
             alg = 16 * Ldom * list_entries
+        # DRAM traffic of one launch from the committed `ncu --set full` capture of exactly this kernel and
+        # workload (profiles/r1_ncu_summaries.md, prof_k1_dense_v3: dram read 1.080858 GB + write 10.13 MB)
+        traffic = None
+        if args.workload == "sparse4k" and world == 1 and Ldom == 8 and kern.endswith("whole carry)"):
+            traffic = 1080858000 + 10126848
         roof = {"bound": "hbm", "kernel": kern, "achieved": ach, "peak": peak, "unit": "GB/s",
-                "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
+                "traffic_note": "ncu dram__bytes_read+write per launch (one capture, profiles/); below the "
+                                "algorithmic bytes because unchanged zero entries are not written back: "
+                                "traffic / time is the honest HBM utilisation",
+                "traffic_frac": (traffic / (dense_tab[str(Ldom)]["avg_ms"] * 1e-3) / 1e9 / peak) if traffic else None,
                 "algorithmic_bytes_per_launch": alg,
                 "dense_mode_by_limbs": dense_tab,
                 "dense_mode_note": "one untimed solve with dense_carry=1; zero entries are read but neither "
