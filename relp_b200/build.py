@@ -21,6 +21,7 @@ HEADERS = [
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",
+    "--split-compile", "0",     # the kernel templates expand to ~300 instantiations: optimise / assemble them in parallel
 ]
 
 

@@ -82,6 +82,7 @@ struct rg_context {
     cudaStream_t side = nullptr;          // side stream: steepest-edge scalars overlap the K1 update
     int* nzrows = nullptr;             // list mode: compacted local rows with s_i != 0 (nloc entries)
     cudaEvent_t ev_side0 = nullptr, ev_side1 = nullptr, ev_side2 = nullptr, ev_work = nullptr, ev_side3 = nullptr;
+    cudaStream_t side3 = nullptr;      // third side stream: steepest-edge scalars (k_scalars_se)
     cudaStream_t side2 = nullptr;      // second side stream: nu / sigma column dots, concurrent with K1
     int m = 0, n = 0;
     int ld = 0;                 // carry leading dimension in entries (multiple of 16)

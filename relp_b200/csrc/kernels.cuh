@@ -1224,22 +1224,27 @@ __global__ void __launch_bounds__(32) k_scalars_se(int L, const u64* __restrict_
     if (sc->status != ST_RUN) return;
     const int lane = threadIdx.x;
     const int LU = L + 2, LG = 2 * L + 6;
-    const int t = sc->t;
+    // self-contained (reads only D and the pivot element a): it runs on its own stream from the moment the
+    // pivot row is chosen, concurrently with k_scalars, the work vector and K1
+    const int t = rt_ctz(sc->D, L);
     const int t2 = 2 * t;
     int E2 = (t2 + 63) >> 6;
     if (E2 < 4) E2 = 4;
     const int WX = LG + E2;
-    const int W0 = min(L + sc->E, WX);
     if (lane == 0) {
         sc->t2 = t2; sc->E2 = E2;
-        for (int l = 0; l < WX; ++l) { am[l] = l < L ? sc->Dnew[l] : 0; dodd[l] = l < L ? sc->D[l] : 0; }
+        for (int l = 0; l < WX; ++l) { tmp[l] = l < LU ? sc->a[l] : 0; dodd[l] = l < L ? sc->D[l] : 0; }
+        rt_abs(am, tmp, LU);                           // |a| (LU limbs; the new denominator)
+        for (int l = LU; l < WX; ++l) am[l] = 0;
         rt_shr(dodd, L, t);
-        // seed: k_scalars (same stream, just before) left 1/odd(D) mod 2^(64 (L+E)) in sc->Dinv
-        for (int l = 0; l < WX; ++l) x[l] = l < W0 ? sc->Dinv[l] : 0;
+        u64 d0 = dodd[0], y = d0;
+        for (int it = 0; it < 6; ++it) y *= 2 - d0 * y;
+        for (int l = 0; l < WX; ++l) x[l] = 0;
+        x[0] = y;
     }
     __syncwarp();
     // Newton: x <- x (2 - d x), doubling the number of correct limbs
-    for (int have = W0; have < WX; have *= 2) {
+    for (int have = 1; have < WX; have *= 2) {
         int want = have * 2 < WX ? have * 2 : WX;
         warp_mul_lo(tt, dodd, x, want, cols);
         if (lane == 0) {
@@ -1277,16 +1282,17 @@ __global__ void __launch_bounds__(32) k_scalars_se(int L, const u64* __restrict_
 // with A = |a| inv(odd D), Bn_i = -sgn(a) u_i inv(odd D): the exact division is fused into two low
 // products.  (Carry::change_basis + update_b + update_minus_pi_and_obj, carry/mod.rs:561-604,295-349;
 // BasisInverseRows::{normalize_pivot_row,row_reduce}, basis_inverse_rows.rs:43-84.)
-// Thread = CP adjacent columns (CP = 2: 128-bit loads/stores); block = 256*CP columns x RT rows.
+// Thread = CP adjacent columns (CP = 2: 128-bit loads/stores); block = blockDim*CP columns x RT rows
+// (dense mode: 256 threads x 32 rows; active-column mode: 128 threads x 8 rows, the list is short and the
+// serial row loop is what bounds the launch).
 // ---------------------------------------------------------------------------------------------
-template <int L, int E, int CP>
+template <int L, int E, int CP, int RT = 32>
 __global__ void __launch_bounds__(256)
 k_update(u64* __restrict__ C, size_t ps, int ld, int row_first, int nrows, const int* __restrict__ klist,
          const u64* __restrict__ u, size_t us, const u64* __restrict__ rowp, size_t rs, Scalars* sc) {
     constexpr int W = L + E;
     constexpr int N = 2 * W;          // 32-bit limbs of the working width
     constexpr int LU = L + 2;
-    constexpr int RT = 32;
     __shared__ u32 sBn[RT][N];
     __shared__ u32 sA[N];
     __shared__ unsigned char sBnz[RT];     // row factor Bn_i != 0 (u_i != 0)
@@ -1326,7 +1332,7 @@ k_update(u64* __restrict__ C, size_t ps, int ld, int row_first, int nrows, const
     __syncthreads();
     // dense mode: CP adjacent columns per thread; list mode (klist != nullptr, CP == 1): the idx-th
     // non-trivial column -- trivial columns are never touched
-    const int idx = (blockIdx.x * 256 + tid) * CP;
+    const int idx = (blockIdx.x * blockDim.x + tid) * CP;
     const int col = klist ? (idx < sc->nk ? klist[idx] : ld) : idx;
     int maxb = 0;
     if (col < ld) {
@@ -2031,7 +2037,12 @@ k_gamma_update_t(int n, ColOwn own, const unsigned char* __restrict__ inbasis, c
             u64 v = l < LG ? G[(size_t)l * n + j] : 0;
             g[2 * l] = (u32)v; g[2 * l + 1] = (u32)(v >> 32);
         }
-        mp_mul_lo<N>(x, g, reinterpret_cast<const u32*>(sc->S1));        // a^2/D^2 Ghat
+        // S1 is staged in registers first: with two or three warps per SM nothing hides the load-use
+        // latency of an operand fetched inside the carry chains
+        u32 s1[N];
+#pragma unroll
+        for (int k = 0; k < N; ++k) s1[k] = reinterpret_cast<const u32*>(sc->S1)[k];
+        mp_mul_lo<N>(x, g, s1);                                               // a^2/D^2 Ghat
         if (any != 0) {
             u32 sg[N], y[N], z[N];
             u64 tops = sigma[(size_t)(LS - 1) * n + j];

@@ -208,6 +208,7 @@ extern "C" int rg_create(const rg_options* opts, rg_context** out) {
     CK(cudaEventCreateWithFlags(&ctx->ev_work, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_side3, cudaEventDisableTiming));
     CK(cudaStreamCreateWithFlags(&ctx->side2, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&ctx->side3, cudaStreamNonBlocking));
     CK(dev_alloc(&ctx->sc, sizeof(Scalars), ctx->stream));
     CK(cudaMemsetAsync(ctx->sc, 0, sizeof(Scalars), ctx->stream));
     {   // pinned mirror: cudaHostAlloc / cudaFreeHost synchronise the whole device, so mirrors are recycled
@@ -286,6 +287,7 @@ extern "C" int rg_destroy(rg_context* ctx) {
     if (ctx->evt0) { cudaEventDestroy(ctx->evt0); cudaEventDestroy(ctx->evt1); }
     if (ctx->ev_side0) { cudaEventDestroy(ctx->ev_side0); cudaEventDestroy(ctx->ev_side1); cudaEventDestroy(ctx->ev_side2); cudaEventDestroy(ctx->ev_work); cudaEventDestroy(ctx->ev_side3); }
     if (ctx->side2) cudaStreamDestroy(ctx->side2);
+    if (ctx->side3) cudaStreamDestroy(ctx->side3);
     // the communicator is process-cached (see rg_create) and intentionally not destroyed here
     if (ctx->side) cudaStreamDestroy(ctx->side);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -713,18 +715,21 @@ static void launch_update_le(rg_context* ctx) {
     if (ctx->list_mode) {
         // cost row: dense over all columns; rows 1..nloc: the non-trivial columns only
         dim3 g0(cdiv(ctx->ld, 256 * CP), 1);
-        LAUNCH((k_update<L, E, CP>), g0, 256, ctx->carry, ctx->plane, ctx->ld, 0, 1, (const int*)nullptr, ctx->u,
+        LAUNCH((k_update<L, E, CP, (L >= 16 ? 8 : 32)>), g0, 256, ctx->carry, ctx->plane, ctx->ld, 0, 1, (const int*)nullptr, ctx->u,
                (size_t)ctx->ld, ctx->rowp, (size_t)ctx->ld, ctx->sc);
         if (ctx->nloc > 0) {
-            dim3 g1(cdiv(ctx->nk_grid, 256), cdiv(ctx->nloc, 32));
-            LAUNCH((k_update<L, E, 1>), g1, 256, ctx->carry, ctx->plane, ctx->ld, 1, ctx->nloc + 1,
+            dim3 g1(cdiv(ctx->nk_grid, 128), cdiv(ctx->nloc, 8));
+            LAUNCH((k_update<L, E, 1, 8>), g1, 128, ctx->carry, ctx->plane, ctx->ld, 1, ctx->nloc + 1,
                    (const int*)ctx->klist, ctx->u, (size_t)ctx->ld, ctx->rowp, (size_t)ctx->ld, ctx->sc);
         }
         return;
     }
-    dim3 grid(cdiv(ctx->ld, 256 * CP), cdiv(ctx->nloc + 1, 32));
-    LAUNCH((k_update<L, E, CP>), grid, 256, ctx->carry, ctx->plane, ctx->ld, 0, ctx->nloc + 1, (const int*)nullptr,
-           ctx->u, (size_t)ctx->ld, ctx->rowp, (size_t)ctx->ld, ctx->sc);
+    // L = 16 is bound by the multiply pipe in either mode: one instantiation (8-row blocks) serves both,
+    // which halves the compile time of the widest variants
+    constexpr int RTD = L >= 16 ? 8 : 32;
+    dim3 grid(cdiv(ctx->ld, 256 * CP), cdiv(ctx->nloc + 1, RTD));
+    LAUNCH((k_update<L, E, CP, RTD>), grid, 256, ctx->carry, ctx->plane, ctx->ld, 0, ctx->nloc + 1,
+           (const int*)nullptr, ctx->u, (size_t)ctx->ld, ctx->rowp, (size_t)ctx->ld, ctx->sc);
 }
 template <int L>
 static void launch_update_t(rg_context* ctx, int E) {
@@ -844,16 +849,17 @@ static int enqueue_iteration(rg_context* ctx, int q, int fixed_row, bool want_se
     RG_TRY(launch_copyrow(ctx));
     if (prof) rec_event(ctx, ctx->evp[1]);
     if (want_se) {
-        // the pivot scalars need only a, D and the tracked bit lengths: they run on the side stream while
-        // the main stream builds the work vector; K1 joins after k_scalars, the bookkeeping after
-        // k_scalars_se (which overlaps K1)
+        // the pivot scalars need only a, D and the tracked bit lengths: k_scalars and k_scalars_se run on
+        // two side streams while the main stream builds the work vector; K1 joins after k_scalars, the
+        // bookkeeping after k_scalars_se
         cudaEventRecord(ctx->ev_side0, ctx->stream);
         cudaStreamWaitEvent(ctx->side, ctx->ev_side0, 0);
+        cudaStreamWaitEvent(ctx->side3, ctx->ev_side0, 0);
         k_scalars<<<1, 1, 0, ctx->side>>>(ctx->L, E, ctx->sc);
         cudaEventRecord(ctx->ev_side2, ctx->side);
-        k_scalars_se<<<1, 32, 0, ctx->side>>>(ctx->L, ctx->world == 1 ? ctx->G : nullptr, ctx->n, ctx->sc);
+        k_scalars_se<<<1, 32, 0, ctx->side3>>>(ctx->L, ctx->world == 1 ? ctx->G : nullptr, ctx->n, ctx->sc);
         ctx->launches += 2;
-        cudaEventRecord(ctx->ev_side1, ctx->side);
+        cudaEventRecord(ctx->ev_side1, ctx->side3);
         RG_TRY(launch_work(ctx));
         if (prof) rec_event(ctx, ctx->evp[2]);
         cudaEventRecord(ctx->ev_work, ctx->stream);
