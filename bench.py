@@ -50,7 +50,7 @@ class ClockSampler:
         self.nvml = None
         self.stop_flag = False
         self.samples = []          # (time, sm_mhz, sm_max_mhz, [reasons])
-        self.period = float(os.environ.get("BENCH_SAMPLER_MS", "100")) / 1e3
+        self.period = float(os.environ.get("BENCH_SAMPLER_MS", "250")) / 1e3
         self.t0 = self.t1 = None
 
     def _physical_index(self):
@@ -198,7 +198,8 @@ def run_reference(args):
     prob = make_problem(args.workload, 0)
     total_p, total_t, last = 0.0, 0.0, None
     for step in range(args.warmup + args.steps):
-        budget = 10.0 if step >= args.warmup else 2.0
+        # bounded sample per step: the whole run stays within a few minutes for any --steps
+        budget = min(10.0, 60.0 / max(args.steps, 1)) if step >= args.warmup else 1.0
         t0 = time.perf_counter()
         last = cpu_baseline(prob, args.rule, budget_s=budget)
         dt = time.perf_counter() - t0
