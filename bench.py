@@ -235,8 +235,8 @@ def workload_config(args, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="sparse4k", choices=sorted(WORKLOADS))
     ap.add_argument("--rule", default="steepest_edge")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])

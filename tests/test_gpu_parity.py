@@ -222,3 +222,31 @@ def test_graph_replay_matches_eager_launches(dense_carry, monkeypatch):
     for rule, status, trace, objective, bfs in runs[:half]:
         ores, otrace = oracle_trace(provider_from_problem(prob), rule)
         assert status == ores.status and trace == otrace and objective == ores.objective and bfs == ores.bfs
+
+
+@pytest.mark.parametrize("limbs", [8, 16])
+def test_dense_block_tensor_core_dots_at_wide_limbs(limbs):
+    """The dense dots run as byte-sliced u8 x s8 tensor-core products.  Starting at 8 / 16 limbs
+    instantiates the widest slice-tile counts (sigma dot of 21 / 37 limbs: 22 / 38 tiles split over two CTA
+    layers) on an oracle-sized problem."""
+    from relp_b200.generators import bounded_lp
+    prob = bounded_lp(48, 64, k_bounding=14, dense=True, seed=7, dense_block=True)
+    check(problem=prob, rules=["steepest_edge"], modes=(True,), initial_limbs=limbs)
+
+
+def test_dense_block_k_split_against_fast_oracle():
+    """More than one 64-row chunk and more than one k-slice of the tensor-core dots (m = 200 -> 4 chunks),
+    promotions from one limb, traces against the C++ oracle and against the CSC form of the same LP."""
+    import relp_b200
+    from oracle import fast_oracle as fo
+    from relp_b200.generators import bounded_lp
+    dense = bounded_lp(200, 120, k_bounding=20, dense=True, seed=3, dense_block=True)
+    csc = bounded_lp(200, 120, k_bounding=20, dense=True, seed=3, dense_block=False)
+    assert dense.dense_block is not None and csc.dense_block is None
+    ref = fo.solve_problem(csc, "steepest_edge")
+    for prob in (dense, csc):
+        g = relp_b200.solve_relaxation(prob, rule="steepest_edge", initial_limbs=1)
+        assert g.status == ref.status == "optimal"
+        assert g.trace == ref.trace
+        assert g.objective == ref.objective and g.bfs == ref.bfs
+    assert g.stats["promotions"] >= 1
