@@ -147,6 +147,7 @@ struct rg_context {
     struct GraphEntry { long long key; cudaGraphExec_t exec; long long launches; };
     std::vector<GraphEntry> graphs;
     bool use_graphs = true;
+    bool graph_nccl = false;           // replay graphs in row-sharded runs too (RG_GRAPH_NCCL=1)
     bool capturing = false;
     int nk_grid = 128;                 // list-mode grid bound (multiple of 128, >= nk + 1)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evt0 = nullptr, evt1 = nullptr;

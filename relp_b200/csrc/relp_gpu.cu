@@ -194,6 +194,7 @@ extern "C" int rg_create(const rg_options* opts, rg_context** out) {
     ctx->world = (opts && opts->world > 0) ? opts->world : 1;
     ctx->dense_carry_opt = opts ? opts->dense_carry : 0;
     ctx->use_graphs = getenv("RG_NO_GRAPH") == nullptr;
+    { const char* e = getenv("RG_GRAPH_NCCL"); ctx->graph_nccl = e && atoi(e) != 0; }
     int L = (opts && opts->initial_limbs) ? opts->initial_limbs : 2;
     if (!(L == 1 || L == 2 || L == 4 || L == 8 || L == 16)) { delete ctx; return RG_ERR_ARG; }
     ctx->L = L;
@@ -426,16 +427,18 @@ static const bool g_check_launch = getenv("RG_CHECK_LAUNCH") != nullptr;
 
 // exchange buffers of the row-sharded engine (words of 8 bytes)
 static int ensure_xbuf(rg_context* ctx, size_t send_words, size_t recv_words) {
+    // the buffers are sized with the width buffers for every collective of the engine; growing them here is
+    // a safety net only (never inside a stream capture: it synchronises and reallocates)
     size_t need = std::max(send_words, recv_words) * sizeof(u64);
     if (need <= ctx->xbytes) return RG_OK;
+    if (ctx->capturing) { ctx->err = "exchange buffer too small inside a graph capture"; return RG_ERR_STATE; }
     CK(cudaStreamSynchronize(ctx->stream));
-    free_dev_on(ctx->triv, ctx->stream); free_dev_on(ctx->klist, ctx->stream); free_dev_on(ctx->nzrows, ctx->stream); free_dev_on(ctx->kpos, ctx->stream); free_dev_on(ctx->aq, ctx->stream);
-    free_dev_on(ctx->Acm, ctx->stream);
-    free_dev_on(ctx->wf, ctx->stream); free_dev_on(ctx->wcol, ctx->stream); free_dev_on(ctx->artf, ctx->stream);
-    free_dev_on(ctx->artcost, ctx->stream); free_dev_on(ctx->rowf, ctx->stream);
+    free_dev_on(ctx->xsend, ctx->stream); free_dev_on(ctx->xrecv, ctx->stream);
+    ctx->xsend = ctx->xrecv = nullptr;
     CK(dev_alloc(&ctx->xsend, need, ctx->stream));
     CK(dev_alloc(&ctx->xrecv, need, ctx->stream));
     ctx->xbytes = need;
+    drop_graphs(ctx);   // captured pointers are stale
     return RG_OK;
 }
 static double g_nccl_host_s = 0;
@@ -902,7 +905,10 @@ static int do_pivot(rg_context* ctx, int q, int fixed_row, bool want_se, bool re
         // graphs pay when an iteration is launch-latency bound; with a large dense block the kernels run for
         // milliseconds and eager launches on three streams overlap better (measured on config 5)
         const bool small = (double)ctx->m * ((double)ctx->nd + ctx->m) < 1.5e8;
-        const bool graphable = ctx->use_graphs && small && ctx->world == 1 && q < 0 && fixed_row < 0 && reselect;
+        // row-sharded runs replay graphs too (NCCL collectives are capturable; every rank derives the same
+        // key from replicated state) when RG_GRAPH_NCCL=1
+        const bool graphable = ctx->use_graphs && small && (ctx->world == 1 || ctx->graph_nccl) && q < 0 &&
+                               fixed_row < 0 && reselect;
         if (graphable) {
             // one CUDA graph per launch shape: limb width, E variant, carry mode, list grid bound, rule, flags
             long long key = (long long)ctx->L | ((long long)E << 8) | ((long long)(ctx->list_mode ? 1 : 0) << 16) |
