@@ -52,6 +52,7 @@ class ClockSampler:
         self.samples = []          # (time, sm_mhz, sm_max_mhz, [reasons])
         self.period = float(os.environ.get("BENCH_SAMPLER_MS", "250")) / 1e3
         self.t0 = self.t1 = None
+        self.max_mhz = None
 
     def _physical_index(self):
         vis = os.environ.get("CUDA_VISIBLE_DEVICES")
@@ -90,22 +91,31 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
-    def _nvml_sample(self):
+    def _nvml_sample(self, with_reasons=True):
+        # NVML queries contend with the CUDA driver for the device lock (sporadic stalls of the solve were
+        # measured with three queries every 100 ms): the max clock is read once, the SM clock every period,
+        # the throttle reasons every 4th period and at the end of the timed region
         n = self.nvml
         sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
-        mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
-        try:
-            mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
-        except Exception:
-            mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
-        self.samples.append((time.perf_counter(), float(sm), float(mx), [nm for nm, bit in self.REASONS if mask & bit]))
+        if self.max_mhz is None:
+            self.max_mhz = float(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM))
+        reasons = []
+        if with_reasons:
+            try:
+                mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+            except Exception:
+                mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+            reasons = [nm for nm, bit in self.REASONS if mask & bit]
+        self.samples.append((time.perf_counter(), float(sm), self.max_mhz, reasons))
 
     def _nvml_loop(self):
+        k = 0
         while not self.stop_flag:
             try:
-                self._nvml_sample()
+                self._nvml_sample(with_reasons=(k % 4 == 0))
             except Exception:
                 pass
+            k += 1
             time.sleep(self.period)
 
     def _smi_loop(self):
@@ -121,8 +131,14 @@ class ClockSampler:
             self.samples.append((time.perf_counter(), sm, mx, rs))
 
     def window(self, t0, t1):
-        """keep the samples taken inside the timed region [t0, t1] (the sampler is started before the warm-up)"""
+        """keep the samples taken inside the timed region [t0, t1] (the sampler is started before the warm-up);
+        called right after the timed region: one last sample with the throttle reasons is taken here"""
         self.t0, self.t1 = t0, t1
+        if self.nvml is not None:
+            try:
+                self._nvml_sample(with_reasons=True)
+            except Exception:
+                pass
 
     def stop(self):
         self.stop_flag = True
