@@ -1,27 +1,35 @@
-"""Builds librelp_gpu.so (CUDA engine + C++ host driver) in-tree for sm_100a."""
+"""Builds librelp_gpu.so (CUDA engine + C++ host driver) in-tree for sm_100a.
+
+The K1 variants (k1_variants.cu, one translation unit per limb width) dominate the compile time, so the
+translation units are compiled in parallel and linked afterwards."""
 import os
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "librelp_gpu.so")
+OBJ = os.path.join(HERE, "_obj")
+CSRC = os.path.join(HERE, "csrc")
+K1_WIDTHS = (16, 8, 4, 2, 1)          # widest first: it is the longest job
 SOURCES = [
-    os.path.join(HERE, "csrc", "relp_gpu.cu"),
-    os.path.join(HERE, "csrc", "host", "relp_host.cpp"),
+    os.path.join(CSRC, "relp_gpu.cu"),
+    os.path.join(CSRC, "k1_variants.cu"),
+    os.path.join(CSRC, "host", "relp_host.cpp"),
 ]
 HEADERS = [
-    os.path.join(HERE, "csrc", "bigint.cuh"),
-    os.path.join(HERE, "csrc", "mp32.cuh"),
-    os.path.join(HERE, "csrc", "engine.cuh"),
-    os.path.join(HERE, "csrc", "kernels.cuh"),
+    os.path.join(CSRC, "bigint.cuh"),
+    os.path.join(CSRC, "mp32.cuh"),
+    os.path.join(CSRC, "engine.cuh"),
+    os.path.join(CSRC, "kernels.cuh"),
+    os.path.join(CSRC, "k1_update.cuh"),
     os.path.join(ROOT, "include", "relp_gpu.h"),
     os.path.join(ROOT, "include", "relp_host.h"),
 ]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
-    "--split-compile", "0",     # the kernel templates expand to ~300 instantiations: optimise / assemble them in parallel
+    "-Xcompiler", "-fPIC",
 ]
 
 
@@ -36,7 +44,27 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+    os.makedirs(OBJ, exist_ok=True)
+    extra = ["-Xptxas", "-v"] if verbose else []
+    jobs = []
+    for L in K1_WIDTHS:
+        obj = os.path.join(OBJ, f"k1_L{L}.o")
+        jobs.append((obj, [nvcc] + NVCC_FLAGS + extra + ["--split-compile", "2", f"-DRG_K1_L={L}", "-c",
+                                                          os.path.join(CSRC, "k1_variants.cu"), "-o", obj]))
+    obj = os.path.join(OBJ, "relp_gpu.o")
+    jobs.append((obj, [nvcc] + NVCC_FLAGS + extra + ["--split-compile", "2", "-c", os.path.join(CSRC, "relp_gpu.cu"),
+                                                      "-o", obj]))
+    obj = os.path.join(OBJ, "relp_host.o")
+    jobs.append((obj, [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, "host", "relp_host.cpp"), "-o", obj]))
+
+    def run(job):
+        print("[relp_b200.build]", " ".join(job[1]), file=sys.stderr)
+        subprocess.run(job[1], check=True)
+        return job[0]
+
+    with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as pool:
+        objs = list(pool.map(run, jobs))
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-o", LIB] + objs
     print("[relp_b200.build]", " ".join(cmd), file=sys.stderr)
     subprocess.run(cmd, check=True)
     return LIB

@@ -1,0 +1,79 @@
+// One translation unit per limb width (compiled with -DRG_K1_L=1|2|4|8|16): the (E, CP, RT) variants of K1.
+// They are the bulk of the library's compile time, so build.py compiles these units in parallel.
+// rg::k1_launch_<L>(ctx, E) enqueues K1 for the current carry mode on ctx->stream and returns false when no
+// fixed-width variant covers E (the caller falls back to the run-time-width kernel).
+#include <cstdio>
+#include <cstdlib>
+#include <cuda_runtime.h>
+
+#include "k1_update.cuh"
+
+#ifndef RG_K1_L
+#error "compile with -DRG_K1_L=<limb width>"
+#endif
+
+using namespace rg;
+
+namespace {
+
+inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+template <int L, int E>
+void launch_le(rg_context* ctx) {
+    constexpr int CP = L <= 4 ? 2 : 1;
+    // L = 16 is bound by the multiply pipe in either mode: one instantiation (8-row blocks) serves both
+    constexpr int RTD = L >= 16 ? 8 : 32;
+    if (ctx->list_mode) {
+        // cost row: dense over all columns; rows 1..nloc: the non-trivial columns only
+        dim3 g0(cdiv(ctx->ld, 256 * CP), 1);
+        k_update<L, E, CP, RTD><<<g0, 256, 0, ctx->stream>>>(ctx->carry, ctx->plane, ctx->ld, 0, 1, (const int*)nullptr,
+                                                             ctx->u, (size_t)ctx->ld, ctx->rowp, (size_t)ctx->ld,
+                                                             ctx->sc);
+        ctx->launches++;
+        if (ctx->nloc > 0) {
+            dim3 g1(cdiv(ctx->nk_grid, 128), cdiv(ctx->nloc, 8));
+            k_update<L, E, 1, 8><<<g1, 128, 0, ctx->stream>>>(ctx->carry, ctx->plane, ctx->ld, 1, ctx->nloc + 1,
+                                                              (const int*)ctx->klist, ctx->u, (size_t)ctx->ld,
+                                                              ctx->rowp, (size_t)ctx->ld, ctx->sc);
+            ctx->launches++;
+        }
+        return;
+    }
+    dim3 grid(cdiv(ctx->ld, 256 * CP), cdiv(ctx->nloc + 1, RTD));
+    k_update<L, E, CP, RTD><<<grid, 256, 0, ctx->stream>>>(ctx->carry, ctx->plane, ctx->ld, 0, ctx->nloc + 1,
+                                                           (const int*)nullptr, ctx->u, (size_t)ctx->ld, ctx->rowp,
+                                                           (size_t)ctx->ld, ctx->sc);
+    ctx->launches++;
+}
+
+template <int L>
+bool launch_t(rg_context* ctx, int E) {
+    switch (E) {
+        case 0: launch_le<L, 0>(ctx); return true;
+        case 1: launch_le<L, 1>(ctx); return true;
+        case 2: if constexpr (L >= 2) { launch_le<L, 2>(ctx); return true; } break;
+        case 3: if constexpr (L >= 4) { launch_le<L, 3>(ctx); return true; } break;
+        case 4: if constexpr (L >= 4) { launch_le<L, 4>(ctx); return true; } break;
+        case 6: if constexpr (L >= 8) { launch_le<L, 6>(ctx); return true; } break;
+        case 8: if constexpr (L >= 8) { launch_le<L, 8>(ctx); return true; } break;
+        default: break;
+    }
+    return false;
+}
+
+}  // namespace
+
+#define RG_K1_CAT2(a, b) a##b
+#define RG_K1_CAT(a, b) RG_K1_CAT2(a, b)
+
+namespace rg {
+bool RG_K1_CAT(k1_launch_, RG_K1_L)(rg_context* ctx, int E) {
+    static const bool check = getenv("RG_CHECK_LAUNCH") != nullptr;
+    bool ok = launch_t<RG_K1_L>(ctx, E);
+    if (check) {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) fprintf(stderr, "[rank %d] launch of k_update failed: %s\n", ctx->rank, cudaGetErrorString(e));
+    }
+    return ok;
+}
+}  // namespace rg

@@ -712,45 +712,28 @@ static int pick_update_variant(int L, int E_needed) {
     for (int e : opts) if (e >= E_needed && e <= emax) return e;
     return -1;   // generic kernel
 }
-template <int L, int E>
-static void launch_update_le(rg_context* ctx) {
-    constexpr int CP = L <= 4 ? 2 : 1;
-    if (ctx->list_mode) {
-        // cost row: dense over all columns; rows 1..nloc: the non-trivial columns only
-        dim3 g0(cdiv(ctx->ld, 256 * CP), 1);
-        LAUNCH((k_update<L, E, CP, (L >= 16 ? 8 : 32)>), g0, 256, ctx->carry, ctx->plane, ctx->ld, 0, 1, (const int*)nullptr, ctx->u,
-               (size_t)ctx->ld, ctx->rowp, (size_t)ctx->ld, ctx->sc);
-        if (ctx->nloc > 0) {
-            dim3 g1(cdiv(ctx->nk_grid, 128), cdiv(ctx->nloc, 8));
-            LAUNCH((k_update<L, E, 1, 8>), g1, 128, ctx->carry, ctx->plane, ctx->ld, 1, ctx->nloc + 1,
-                   (const int*)ctx->klist, ctx->u, (size_t)ctx->ld, ctx->rowp, (size_t)ctx->ld, ctx->sc);
-        }
-        return;
-    }
-    // L = 16 is bound by the multiply pipe in either mode: one instantiation (8-row blocks) serves both,
-    // which halves the compile time of the widest variants
-    constexpr int RTD = L >= 16 ? 8 : 32;
-    dim3 grid(cdiv(ctx->ld, 256 * CP), cdiv(ctx->nloc + 1, RTD));
-    LAUNCH((k_update<L, E, CP, RTD>), grid, 256, ctx->carry, ctx->plane, ctx->ld, 0, ctx->nloc + 1,
-           (const int*)nullptr, ctx->u, (size_t)ctx->ld, ctx->rowp, (size_t)ctx->ld, ctx->sc);
+// the fixed-width variants live in k1_variants.cu, one translation unit per limb width
+namespace rg {
+bool k1_launch_1(rg_context*, int);
+bool k1_launch_2(rg_context*, int);
+bool k1_launch_4(rg_context*, int);
+bool k1_launch_8(rg_context*, int);
+bool k1_launch_16(rg_context*, int);
 }
-template <int L>
-static void launch_update_t(rg_context* ctx, int E) {
-    switch (E) {
-        case 0: launch_update_le<L, 0>(ctx); return;
-        case 1: launch_update_le<L, 1>(ctx); return;
-        case 2: if constexpr (L >= 2) { launch_update_le<L, 2>(ctx); return; } break;
-        case 3: if constexpr (L >= 4) { launch_update_le<L, 3>(ctx); return; } break;
-        case 4: if constexpr (L >= 4) { launch_update_le<L, 4>(ctx); return; } break;
-        case 6: if constexpr (L >= 8) { launch_update_le<L, 6>(ctx); return; } break;
-        case 8: if constexpr (L >= 8) { launch_update_le<L, 8>(ctx); return; } break;
-        default: break;
+static void launch_update(rg_context* ctx, int E) {
+    bool ok = false;
+    switch (ctx->L) {
+        case 1: ok = k1_launch_1(ctx, E); break;
+        case 2: ok = k1_launch_2(ctx, E); break;
+        case 4: ok = k1_launch_4(ctx, E); break;
+        case 8: ok = k1_launch_8(ctx, E); break;
+        default: ok = k1_launch_16(ctx, E); break;
     }
+    if (ok) return;
     dim3 g2(cdiv(ctx->ld, 128), ctx->nloc + 1);
-    LAUNCH(k_update_generic, g2, 128, ctx->carry, ctx->plane, ctx->ld, ctx->nloc + 1, L, ctx->u,
+    LAUNCH(k_update_generic, g2, 128, ctx->carry, ctx->plane, ctx->ld, ctx->nloc + 1, ctx->L, ctx->u,
            (size_t)ctx->ld, ctx->rowp, (size_t)ctx->ld, ctx->sc);
 }
-static void launch_update(rg_context* ctx, int E) { DISPATCH_L(ctx->L, launch_update_t, ctx, E); }
 
 template <int L>
 static void launch_se_dots_t(rg_context* ctx) {
