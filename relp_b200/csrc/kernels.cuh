@@ -309,7 +309,9 @@ k_dense_combine(const int* __restrict__ R, size_t rstride_k, int kslices, int rp
     for (int l = 0; l < LO; ++l) res[l] = 0;
     if (!inbasis[j]) {
         long long carry = 0;
-#pragma unroll
+        // not unrolled over the limbs: 8 LO copies of the slice loop cost minutes of compile time at LO = 39
+        // and nothing at run time (res[] goes through local memory; the kernel is a few microseconds)
+#pragma unroll 1
         for (int l = 0; l < LO; ++l) {
             u64 limb = 0;
 #pragma unroll
