@@ -195,9 +195,23 @@ int rg_get_pivot_column(rg_context* ctx, uint64_t* out);
 /* relative cost numerators of every provider column (Tableau::relative_cost, tableau/mod.rs:106-112),
  * limbs+2 words per entry; basic columns report 0 */
 int rg_get_relative_costs(rg_context* ctx, uint64_t* out);
-/* steepest-edge weights gamma_j * D^2 for every provider column, 2*limbs+5 words per entry (0 for
+/* steepest-edge weights gamma_j * D^2 for every provider column, 2*limbs+6 words per entry (0 for
  * basic columns) */
 int rg_get_gamma(rg_context* ctx, uint64_t* out);
+/* InverseMaintainer::generate_element (tableau/inverse_maintenance/mod.rs:200-215 ->
+ * BasisInverse::generate_element, carry/basis_inverse_rows.rs:179-195): the single entry
+ * (B^-1 a_j)[row], one numerator of limbs+2 words over the current denominator. */
+int rg_get_element(rg_context* ctx, int32_t row, int32_t j, uint64_t* out);
+/* BasisChangeComputationInfo (tableau/mod.rs:205-234) of the last basis change -- what a stock host-side
+ * `PivotRule::after_basis_update` receives (the indices are in rg_pivot_info):
+ *   column  = column_before_change, m entries of limbs+2 words, over `denominator_before`
+ *   work    = work_vector = column^T B_old^-1, m entries of 2*limbs+5 words, over denominator_before^2
+ *             (kept only when the device steepest-edge update ran; otherwise pass NULL)
+ *   row     = basis_inverse_row = row p of the new B^-1, m entries of limbs words, over the current denominator
+ *   denominator_before = limbs words.
+ * Any pointer may be NULL.  Valid until the next call that generates a column or changes the basis. */
+int rg_get_basis_change_info(rg_context* ctx, uint64_t* column, uint64_t* work, uint64_t* row,
+                             uint64_t* denominator_before);
 int rg_get_stats(rg_context* ctx, rg_stats* out);
 /* measurement hooks (no reference counterpart): on = 1 puts CUDA events around every K1 launch (rg_stats
  * k1_ms_at_limbs), on = 2 additionally around every phase of an iteration (rg_stats phase_ms); and a
@@ -205,13 +219,6 @@ int rg_get_stats(rg_context* ctx, rg_stats* out);
 int rg_set_profile(rg_context* ctx, int32_t on);
 int rg_timer_start(rg_context* ctx);
 int rg_timer_stop(rg_context* ctx);
-
-/* ---- test hooks (no reference counterpart; used by tests/ and scripts/ only) -------------------- */
-int rg_debug_scalars(rg_context* ctx, void* out, int64_t bytes);
-int rg_debug_vector(rg_context* ctx, int32_t which, uint64_t* out);
-/* runs one device big-integer primitive on W-limb operands: see relp_gpu.cu */
-int rg_selftest(int32_t op, int32_t W, const uint64_t* a, const uint64_t* b, const uint64_t* c,
-                const uint64_t* d, int64_t s, uint64_t* out);
 
 #ifdef __cplusplus
 }

@@ -15,6 +15,13 @@
 // It mirrors oracle/relp_oracle.py function by function; tests/test_fast_oracle.py pins it to the
 // Python oracle (which is pinned to the reference's golden fixtures).  The Rust reference itself
 // cannot be built in this image (no cargo/rustc, nightly features, un-vendored crates).
+//
+// Storage: the provider's columns are held compactly (CSC with machine-integer numerators and optional
+// denominators, plus an optional dense int8 block with implicit row indices), so that config 5
+// (16384 x 32768 dense coefficients) fits; rationals are formed on the fly.  Dense columns are indexed
+// directly in the sparse-row dots (what an O(1) `get` gives the reference).  Columns are independent in
+// pricing, in the steepest-edge initialisation and in its update, so those loops run over OpenMP
+// threads (fo_set_threads; results are exact rationals and do not depend on the thread count).
 #include <algorithm>
 #include <chrono>
 #include <cstdint>
@@ -24,6 +31,9 @@
 #include <unordered_set>
 #include <utility>
 #include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 typedef unsigned __int128 u128;
 typedef __int128 i128;
@@ -304,42 +314,92 @@ static std::string to_string(const Rational& a) {   // "[-]hexnum/hexden"
 // ------------------------------------------------------------------------------------------------
 typedef std::vector<std::pair<int, Rational>> SparseCol;
 
+// A column of the constraint matrix: a view of compact storage (no per-entry rationals are kept).
+struct Col {
+    const int* idx = nullptr; const i64* num = nullptr; const i64* den = nullptr; int len = 0;   // CSC slice
+    const int8_t* d8 = nullptr; int m = 0;                                                        // dense int8
+    const SparseCol* sc = nullptr;                                                                // materialised
+    bool dense() const { return d8 != nullptr; }
+    size_t size() const { return sc ? sc->size() : (d8 ? (size_t)m : (size_t)len); }
+    template <class F> void for_each(F f) const {     // f(row, value) in ascending row order, zeros skipped
+        if (sc) { for (auto& e : *sc) f(e.first, e.second); return; }
+        if (d8) { for (int i = 0; i < m; ++i) if (d8[i]) f(i, Rational((i64)d8[i])); return; }
+        for (int k = 0; k < len; ++k) f(idx[k], den ? Rational(num[k], den[k]) : Rational(num[k]));
+    }
+};
+
 struct Provider {   // MatrixProvider (matrix_provider/mod.rs:37-134)
     int m = 0, n = 0;
-    std::vector<SparseCol> columns;
+    const i64* colptr = nullptr; const int* rowidx = nullptr; const i64* vnum = nullptr; const i64* vden = nullptr;
+    int nd = 0; const int8_t* dense = nullptr;      // columns [0, nd): column-major nd x m, CSC ranges empty
     std::vector<Rational> cost, rhs;
     bool partial = false, full = false;
     std::vector<std::pair<int, int>> pivots;
+    Col column(int j) const {
+        Col c;
+        if (j < nd) { c.d8 = dense + (size_t)j * m; c.m = m; return c; }
+        c.idx = rowidx + colptr[j]; c.num = vnum + colptr[j]; c.den = vden ? vden + colptr[j] : nullptr;
+        c.len = (int)(colptr[j + 1] - colptr[j]);
+        return c;
+    }
 };
 
 typedef std::map<int, Rational> SparseRow;   // column -> value, ordered (SparseVector semantics)
 
-static Rational dot_dense(const std::vector<Rational>& dense, const SparseCol& col) {
-    // DenseVector::sparse_inner_product (data/linear_algebra/vector/dense.rs:101-112)
+static Rational dot_dense(const std::vector<Rational>& dense, const std::vector<int>* nz, const Col& col) {
+    // DenseVector::sparse_inner_product (data/linear_algebra/vector/dense.rs:101-112).  `nz` (optional):
+    // the indices of the non-zero entries of `dense`, used to walk a dense column by index.
     Rational s;
-    for (auto& e : col) {
-        const Rational& dv = dense[e.first];
-        if (!dv.is_zero()) s = add(s, mul(dv, e.second));
+    if (col.dense() && nz) {
+        for (int i : *nz) if (col.d8[i]) s = add(s, mul(dense[i], Rational((i64)col.d8[i])));
+        return s;
     }
+    col.for_each([&](int i, const Rational& v) {
+        const Rational& dv = dense[i];
+        if (!dv.is_zero()) s = add(s, mul(dv, v));
+    });
     return s;
 }
-static Rational dot_row(const SparseRow& row, const SparseCol& col) {
+static Rational dot_row(const SparseRow& row, const Col& col) {
     // SparseVector::sparse_inner_product (data/linear_algebra/vector/sparse.rs:105-128)
     Rational s;
-    if (row.size() < 4 * col.size()) {
-        // merge join over two sorted sequences
-        auto it = row.begin();
-        size_t k = 0;
-        while (it != row.end() && k < col.size()) {
-            if (it->first < col[k].first) ++it;
-            else if (it->first > col[k].first) ++k;
-            else { s = add(s, mul(it->second, col[k].second)); ++it; ++k; }
+    if (col.dense()) {      // implicit indices: direct lookup per row entry
+        for (auto& kv : row) if (col.d8[kv.first]) s = add(s, mul(kv.second, Rational((i64)col.d8[kv.first])));
+        return s;
+    }
+    if (col.sc) {
+        const SparseCol& c = *col.sc;
+        if (row.size() < 4 * c.size()) {
+            auto it = row.begin();
+            size_t k = 0;
+            while (it != row.end() && k < c.size()) {
+                if (it->first < c[k].first) ++it;
+                else if (it->first > c[k].first) ++k;
+                else { s = add(s, mul(it->second, c[k].second)); ++it; ++k; }
+            }
+            return s;
+        }
+        for (auto& e : c) {
+            auto it = row.find(e.first);
+            if (it != row.end()) s = add(s, mul(it->second, e.second));
         }
         return s;
     }
-    for (auto& e : col) {
-        auto it = row.find(e.first);
-        if (it != row.end()) s = add(s, mul(it->second, e.second));
+    auto val = [&](int k) { return col.den ? Rational(col.num[k], col.den[k]) : Rational(col.num[k]); };
+    if (row.size() < 4 * (size_t)col.len) {
+        // merge join over two sorted sequences
+        auto it = row.begin();
+        int k = 0;
+        while (it != row.end() && k < col.len) {
+            if (it->first < col.idx[k]) ++it;
+            else if (it->first > col.idx[k]) ++k;
+            else { s = add(s, mul(it->second, val(k))); ++it; ++k; }
+        }
+        return s;
+    }
+    for (int k = 0; k < col.len; ++k) {
+        auto it = row.find(col.idx[k]);
+        if (it != row.end()) s = add(s, mul(it->second, val(k)));
     }
     return s;
 }
@@ -356,8 +416,15 @@ struct Carry {   // carry/mod.rs:46-66
     std::vector<SparseRow> rows;
     int m() const { return (int)b.size(); }
 
-    Rational cost_difference(const SparseCol& c) const { return dot_dense(minus_pi, c); }   // :606-611
-    SparseRow generate_column(const SparseCol& c) const {                                    // :613-621
+    std::vector<int> pi_nz;      // indices of the non-zero entries of minus_pi (refreshed by the pricing loops)
+    bool pi_nz_valid = false;
+    void refresh_pi_nz() {
+        pi_nz.clear();
+        for (int i = 0; i < m(); ++i) if (!minus_pi[i].is_zero()) pi_nz.push_back(i);
+        pi_nz_valid = true;
+    }
+    Rational cost_difference(const Col& c) const { return dot_dense(minus_pi, pi_nz_valid ? &pi_nz : nullptr, c); }   // :606-611
+    SparseRow generate_column(const Col& c) const {                                          // :613-621
         SparseRow out;
         for (int i = 0; i < m(); ++i) {
             Rational v = dot_row(rows[i], c);
@@ -365,10 +432,11 @@ struct Carry {   // carry/mod.rs:46-66
         }
         return out;
     }
-    Rational generate_element(int i, const SparseCol& c) const { return dot_row(rows[i], c); }
+    Rational generate_element(int i, const Col& c) const { return dot_row(rows[i], c); }
 
     Info change_basis(int p, int q, SparseRow column, const Rational& relative_cost) {       // :561-604
         Info info;
+        pi_nz_valid = false;
         info.p = p; info.q = q;
         // work vector = column^T B^-1 (basis_inverse_rows.rs:162-177)
         for (auto& ia : column)
@@ -432,22 +500,28 @@ struct Tableau {   // tableau/mod.rs:25-39
         return j < nr_artificial() ? Rational(1) : Rational(0);
     }
     SparseCol identity_col(int j) const { return SparseCol{{column_to_row[j], Rational(1)}}; }
-    const SparseCol& provider_col(int j) const { return use_filtered ? filtered[j] : prov->columns[j]; }
+    Col provider_col(int j) const {
+        if (use_filtered) { Col c; c.sc = &filtered[j]; return c; }
+        return prov->column(j);
+    }
+    static Col view(const SparseCol& sc) { Col c; c.sc = &sc; return c; }
     bool in_basis(int j) const { return basis_columns.count(j) != 0; }
     Rational relative_cost(int j) const {   // tableau/mod.rs:106-112
         int na = nr_artificial();
-        if (j < na) return add(im.cost_difference(identity_col(j)), initial_cost(j));
+        if (j < na) { SparseCol ic = identity_col(j); return add(im.cost_difference(view(ic)), initial_cost(j)); }
         return add(im.cost_difference(provider_col(j - na)), initial_cost(j));
     }
     SparseRow generate_column(int j) const {
         int na = nr_artificial();
-        return j < na ? im.generate_column(identity_col(j)) : im.generate_column(provider_col(j - na));
+        if (j < na) { SparseCol ic = identity_col(j); return im.generate_column(view(ic)); }
+        return im.generate_column(provider_col(j - na));
     }
     Rational generate_element(int i, int j) const {
         int na = nr_artificial();
-        return j < na ? im.generate_element(i, identity_col(j)) : im.generate_element(i, provider_col(j - na));
+        if (j < na) { SparseCol ic = identity_col(j); return im.generate_element(i, view(ic)); }
+        return im.generate_element(i, provider_col(j - na));
     }
-    const SparseCol& original_column_real(int j) const { return provider_col(j - nr_artificial()); }
+    Col original_column_real(int j) const { return provider_col(j - nr_artificial()); }
     // ratio test with Bland tie-break (tableau/mod.rs:287-313)
     int select_primal_pivot_row(const SparseRow& column) const {
         int best = -1, best_leaving = 0;
@@ -474,6 +548,8 @@ struct Tableau {   // tableau/mod.rs:25-39
 // ------------------------------------------------------------------------------------------------
 // pivot rules (strategy/pivot_rule.rs)
 // ------------------------------------------------------------------------------------------------
+static int g_threads = 1;           // OpenMP team size of the column-parallel loops (fo_set_threads)
+
 struct Rule {
     int kind;                       // 0 FirstProfitable, 1 ..WithMemory, 2 Dantzig, 3 steepest edge
     int last_selected = -1;
@@ -488,7 +564,9 @@ struct Rule {
     Rule(int k, const Tableau& t) : kind(k) {
         if (kind == 3) {   // :202-219
             gamma.resize(t.nr_columns()); has.assign(t.nr_columns(), 0);
-            for (int j = t.start_index(); j < t.nr_columns(); ++j)
+            const int lo = t.start_index(), hi = t.nr_columns();
+#pragma omp parallel for schedule(dynamic, 16) num_threads(g_threads)
+            for (int j = lo; j < hi; ++j)
                 if (!t.in_basis(j)) { gamma[j] = initial_gamma(j, t); has[j] = 1; }
         }
     }
@@ -500,7 +578,8 @@ struct Rule {
         }
         return false;
     }
-    bool select(const Tableau& t, int& q, Rational& cost) {
+    bool select(Tableau& t, int& q, Rational& cost) {
+        t.im.refresh_pi_nz();
         if (kind == 0) return find_first(t, t.start_index(), t.nr_columns(), q, cost);   // :95-108
         if (kind == 1) {   // :126-149
             bool ok;
@@ -510,16 +589,30 @@ struct Rule {
             last_selected = ok ? q : -1;
             return ok;
         }
+        // the relative costs (and steepest-edge keys) of all columns are independent: computed by the
+        // thread team, then scanned in index order exactly like the reference's iterator chain
+        const int lo = t.start_index(), hi = t.nr_columns();
+        std::vector<Rational> costs(hi - lo), keys(kind == 3 ? hi - lo : 0);
+        std::vector<char> neg(hi - lo, 0);
+        const Tableau& ct = t;
+#pragma omp parallel for schedule(dynamic, 64) num_threads(g_threads)
+        for (int j = lo; j < hi; ++j) {
+            if (ct.in_basis(j)) continue;
+            Rational c = ct.relative_cost(j);
+            if (c.sign() >= 0) continue;
+            neg[j - lo] = 1;
+            if (kind == 3) keys[j - lo] = div(mul(c, c), gamma[j]);
+            costs[j - lo] = std::move(c);
+        }
         bool found = false;
         Rational best_key;
-        for (int j = t.start_index(); j < t.nr_columns(); ++j) {
-            if (t.in_basis(j)) continue;
-            Rational c = t.relative_cost(j);
-            if (c.sign() >= 0) continue;
+        for (int j = lo; j < hi; ++j) {
+            if (!neg[j - lo]) continue;
+            const Rational& c = costs[j - lo];
             if (kind == 2) {   // Dantzig :163-186: strict < => lowest index on ties
                 if (!found || cmp(c, cost) < 0) { q = j; cost = c; found = true; }
             } else {           // steepest edge :221-241: max_by_key => last maximum wins
-                Rational key = div(mul(c, c), gamma[j]);
+                const Rational& key = keys[j - lo];
                 if (!found || cmp(key, best_key) >= 0) { q = j; cost = c; best_key = key; found = true; }
             }
         }
@@ -531,9 +624,11 @@ struct Rule {
         Rational gamma_q(1);
         for (auto& e : info.column) gamma_q = add(gamma_q, mul(e.second, e.second));
         Rational one(1);
-        for (int j = t.start_index(); j < (int)gamma.size(); ++j) {
+        const int lo = t.start_index(), hi = (int)gamma.size();
+#pragma omp parallel for schedule(dynamic, 16) num_threads(g_threads)
+        for (int j = lo; j < hi; ++j) {
             if (!has[j]) continue;
-            const SparseCol& original = t.original_column_real(j);
+            const Col original = t.original_column_real(j);
             Rational alpha = dot_row(info.row_p, original);
             Rational alternative = one;
             Rational g = gamma[j];
@@ -595,6 +690,7 @@ struct Solver {
         std::vector<std::pair<int, int>> arts;
         for (int i = 0; i < t.nr_rows(); ++i) if (t.im.basis[i] < na) arts.push_back({i, t.im.basis[i]});
         for (auto& pa : arts) {
+            t.im.refresh_pi_nz();
             int pivot_row = pa.first;
             bool nonzero = !t.im.b[pivot_row].is_zero();
             int found = -1; Rational fcost;
@@ -653,7 +749,7 @@ struct Solver {
             t.im.minus_objective = neg(obj);
             for (int j : t.im.basis) t.basis_columns.insert(j);
             int r = loop(t, 1);
-            if (r == 2) return -1;
+            if (r == 2) { final_tableau = std::move(t); return -1; }
             if (r == 1) return -2;   // "Artificial cost can not be unbounded." (phase_one.rs:151)
             if (!t.im.minus_objective.is_zero()) return 2;
             bool any_art = false;
@@ -678,8 +774,9 @@ struct Solver {
                 t.im = std::move(c2);
                 t.filtered.resize(prov.n);
                 for (int j = 0; j < prov.n; ++j)
-                    for (auto& e : prov.columns[j])
-                        if (new_index[e.first] >= 0) t.filtered[j].push_back({new_index[e.first], e.second});
+                    prov.column(j).for_each([&](int i, const Rational& v) {
+                        if (new_index[i] >= 0) t.filtered[j].push_back({new_index[i], v});
+                    });
                 t.use_filtered = true;
             } else {
                 for (int& j : t.im.basis) j -= na;
@@ -728,16 +825,25 @@ struct fo_result {
 
 extern "C" {
 
+int fo_set_threads(int n) {      // n <= 0: all hardware threads
+#ifdef _OPENMP
+    g_threads = n > 0 ? n : omp_get_num_procs();
+#else
+    g_threads = 1;
+#endif
+    return g_threads;
+}
+
+// The arrays must stay alive for the duration of the call (they are viewed, not copied).
+// dense (may be null): provider columns [0, n_dense) as int8, column-major n_dense x m; their CSC ranges are empty.
 int fo_solve(int m, int n, const i64* colptr, const int* rowidx, const i64* val_num, const i64* val_den,
              const i64* cost_num, const i64* cost_den, const i64* rhs_num, const i64* rhs_den,
              int n_pivots, const int* prow, const int* pcol, int full_basis, int rule, long long max_pivots,
-             fo_result** out) {
+             int n_dense, const int8_t* dense, fo_result** out) {
     Provider p;
     p.m = m; p.n = n;
-    p.columns.resize(n);
-    for (int j = 0; j < n; ++j)
-        for (i64 k = colptr[j]; k < colptr[j + 1]; ++k)
-            p.columns[j].push_back({rowidx[k], Rational(val_num[k], val_den ? val_den[k] : 1)});
+    p.colptr = colptr; p.rowidx = rowidx; p.vnum = val_num; p.vden = val_den;
+    p.nd = dense ? n_dense : 0; p.dense = dense;
     p.cost.resize(n); p.rhs.resize(m);
     for (int j = 0; j < n; ++j) p.cost[j] = Rational(cost_num[j], cost_den ? cost_den[j] : 1);
     for (int i = 0; i < m; ++i) p.rhs[i] = Rational(rhs_num[i], rhs_den ? rhs_den[i] : 1);
@@ -751,7 +857,8 @@ int fo_solve(int m, int n, const i64* colptr, const int* rowidx, const i64* val_
     r->status = s.solve(fin, r->rows_removed, r->nr_artificial);
     r->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     for (auto& e : s.trace) { r->trace.push_back(e.phase); r->trace.push_back(e.q); r->trace.push_back(e.p); r->trace.push_back(e.leaving); }
-    if (r->status == 0) {
+    // optimum, or the intermediate basic solution of a phase-two prefix (pivot limit): same exports
+    if (r->status == 0 || (r->status == -1 && fin.prov && !fin.artificial)) {
         r->objective = to_string(neg(fin.im.minus_objective));
         std::vector<std::pair<int, Rational>> bfs;   // Carry::current_bfs (carry/mod.rs:636-645)
         for (int i = 0; i < fin.im.m(); ++i)

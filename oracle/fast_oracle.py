@@ -34,7 +34,10 @@ def load():
     i64p, i32p = C.POINTER(C.c_int64), C.POINTER(C.c_int32)
     lib.fo_solve.restype = C.c_int
     lib.fo_solve.argtypes = [C.c_int, C.c_int, i64p, i32p, i64p, i64p, i64p, i64p, i64p, i64p, C.c_int,
-                             i32p, i32p, C.c_int, C.c_int, C.c_longlong, C.POINTER(P)]
+                             i32p, i32p, C.c_int, C.c_int, C.c_longlong, C.c_int, C.POINTER(C.c_int8),
+                             C.POINTER(P)]
+    lib.fo_set_threads.restype = C.c_int
+    lib.fo_set_threads.argtypes = [C.c_int]
     for name, res in [("fo_status", C.c_int), ("fo_trace_len", C.c_longlong), ("fo_trace", i32p),
                       ("fo_rows_removed_len", C.c_int), ("fo_rows_removed", i32p), ("fo_bfs_len", C.c_int),
                       ("fo_bfs_cols", i32p), ("fo_bfs_values", C.c_char_p), ("fo_objective", C.c_char_p),
@@ -78,9 +81,16 @@ def _split(values):
     return num, den
 
 
+def set_threads(n=0):
+    """OpenMP team size of the column-parallel loops (0 = all hardware threads); returns the size in use.
+    Results do not depend on it (exact arithmetic, index-ordered reductions)."""
+    return load().fo_set_threads(int(n))
+
+
 def solve(m, n, colptr, rowidx, vals, cost, rhs, pivots, full_basis, rule="steepest_edge", max_pivots=0,
-          vals_den=None, cost_den=None, rhs_den=None):
-    """Integer (or num/den) CSC problem -> FastResult.  Trace rows are in the original row space."""
+          vals_den=None, cost_den=None, rhs_den=None, dense_block=None):
+    """Integer (or num/den) CSC problem -> FastResult.  Trace rows are in the original row space.
+    dense_block: optional int8 array (n_dense, m): provider columns [0, n_dense), CSC ranges empty."""
     lib = load()
     p64 = lambda a: None if a is None else a.ctypes.data_as(C.POINTER(C.c_int64))
     p32 = lambda a: None if a is None else a.ctypes.data_as(C.POINTER(C.c_int32))
@@ -95,9 +105,14 @@ def solve(m, n, colptr, rowidx, vals, cost, rhs, pivots, full_basis, rule="steep
         pr = np.array([r for r, _ in pivots], dtype=np.int32)
         pc = np.array([c for _, c in pivots], dtype=np.int32)
     h = C.c_void_p()
+    nd, dptr = 0, None
+    if dense_block is not None:
+        dense_block = np.ascontiguousarray(dense_block, dtype=np.int8)
+        assert dense_block.ndim == 2 and dense_block.shape[1] == m
+        nd, dptr = dense_block.shape[0], dense_block.ctypes.data_as(C.POINTER(C.c_int8))
     rc = lib.fo_solve(m, n, p64(colptr), p32(rowidx), p64(arrs[0]), p64(arrs[1]), p64(arrs[2]), p64(arrs[3]),
                       p64(arrs[4]), p64(arrs[5]), npv, p32(pr), p32(pc), 1 if full_basis else 0,
-                      RULES[rule], max_pivots, C.byref(h))
+                      RULES[rule], max_pivots, nd, dptr, C.byref(h))
     assert rc == 0
     try:
         res = FastResult()
@@ -109,7 +124,8 @@ def solve(m, n, colptr, rowidx, vals, cost, rhs, pivots, full_basis, rule="steep
         res.rows_removed = [rr[i] for i in range(lib.fo_rows_removed_len(h))]
         res.nr_artificial = lib.fo_nr_artificial(h)
         res.seconds = lib.fo_seconds(h)
-        if res.status == "optimal":
+        if res.status == "optimal" or (res.status == "pivot_limit" and lib.fo_objective(h)):
+            # (pivot limit inside phase two: the objective and basic solution of the basis reached)
             res.objective = parse_rational(lib.fo_objective(h))
             cols = lib.fo_bfs_cols(h)
             nb = lib.fo_bfs_len(h)
@@ -125,7 +141,8 @@ def solve_problem(problem, rule="steepest_edge", max_pivots=0):
     """relp_b200.IntegerProblem (duck-typed: m, n, colptr, rowidx, vals, cost, rhs, pivots,
     full_initial_basis) -> FastResult"""
     return solve(problem.m, problem.n, problem.colptr, problem.rowidx, problem.vals, problem.cost,
-                 problem.rhs, problem.pivots, problem.full_initial_basis, rule, max_pivots)
+                 problem.rhs, problem.pivots, problem.full_initial_basis, rule, max_pivots,
+                 dense_block=getattr(problem, "dense_block", None))
 
 
 def solve_provider(provider, rule="steepest_edge", max_pivots=0):

@@ -85,6 +85,9 @@ SYMBOLS = {
     "rg_get_pivot_column": (C.c_int, [P, C.POINTER(C.c_uint64)]),
     "rg_get_relative_costs": (C.c_int, [P, C.POINTER(C.c_uint64)]),
     "rg_get_gamma": (C.c_int, [P, C.POINTER(C.c_uint64)]),
+    "rg_get_element": (C.c_int, [P, C.c_int32, C.c_int32, C.POINTER(C.c_uint64)]),
+    "rg_get_basis_change_info": (C.c_int, [P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                           C.POINTER(C.c_uint64)]),
     "rg_get_stats": (C.c_int, [P, C.POINTER(rg_stats)]),
     "rg_set_profile": (C.c_int, [P, C.c_int32]),
     "rg_timer_start": (C.c_int, [P]),

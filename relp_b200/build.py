@@ -25,6 +25,7 @@ HEADERS = [
     os.path.join(CSRC, "kernels.cuh"),
     os.path.join(CSRC, "k1_update.cuh"),
     os.path.join(ROOT, "include", "relp_gpu.h"),
+    os.path.join(ROOT, "include", "relp_gpu_test.h"),
     os.path.join(ROOT, "include", "relp_host.h"),
 ]
 NVCC_FLAGS = [

@@ -36,9 +36,11 @@ struct Scalars {
     int rank, world;
     int nk;              // number of non-trivial carry columns (entries of klist), column 0 included
     int nnz_s;           // list mode: local rows with a non-zero work-vector factor (entries of nzrows)
+    int fatal;           // why status became ST_FATAL: 1 overflow beyond 16 limbs, 2 kernel variant too narrow, 3 zero pivot element
     u64 D[RG_MAXL];          // current denominator (positive)
     u64 a[RG_MAXL + 2];      // pivot element numerator u[p] (replicated on every rank)
     u64 Dnew[RG_MAXL];       // |a|: denominator after the pivot
+    u64 Dold[RG_MAXL];       // denominator before the last pivot (BasisChangeComputationInfo export)
     u64 Dinv[2 * RG_MAXL + 2];   // inverse of odd(D) mod 2^(64 (L+E)), E <= L (+2 spare)
     u64 A[2 * RG_MAXL + 2];      // |a| * Dinv mod 2^(64 (L+E))
     u64 up[2 * RG_MAXL + 2];     // replacement for u[p]: a - D (makes the pivot row uniform)
@@ -52,6 +54,7 @@ struct HostMirror {
     int t_next, bits_D, maxbits_carry, predicted;
     int found, sgn, maxbits_tmp, pivoted;   // pivoted: a basis change happened since the host cleared it
     int q_done, p_done, leaving_done, nk;   // the pivot that was performed (written by k_finalize); active columns
+    int fatal, pad0, pad1, pad2;            // Scalars::fatal
 };
 
 struct Csc {
@@ -139,6 +142,7 @@ struct rg_context {
     bool have_column = false;
     bool selected = false;             // sc->q holds the entering column chosen for the current basis
     bool identity_carry = false;       // B^-1 == I and D == 1 (fresh init)
+    bool work_valid = false;           // omega holds the work vector of the last basis change
     int t_cur = 0;                     // ctz(D) of the current denominator (host copy)
     long long pivots = 0, promotions = 0, launches = 0;
     long long pivots_at[5] = {0, 0, 0, 0, 0};
@@ -157,4 +161,5 @@ struct rg_context {
     double k1_ms[5] = {0, 0, 0, 0, 0};
     double timer_ms = 0;
     std::string err;
+    std::string launch_err;            // first failed kernel launch since the last synchronising call
 };

@@ -68,12 +68,10 @@ bool launch_t(rg_context* ctx, int E) {
 
 namespace rg {
 bool RG_K1_CAT(k1_launch_, RG_K1_L)(rg_context* ctx, int E) {
-    static const bool check = getenv("RG_CHECK_LAUNCH") != nullptr;
     bool ok = launch_t<RG_K1_L>(ctx, E);
-    if (check) {
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) fprintf(stderr, "[rank %d] launch of k_update failed: %s\n", ctx->rank, cudaGetErrorString(e));
-    }
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess && ctx->launch_err.empty())
+        ctx->launch_err = std::string("launch of k_update failed: ") + cudaGetErrorString(e);
     return ok;
 }
 }  // namespace rg

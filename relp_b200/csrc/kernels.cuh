@@ -131,7 +131,7 @@ __global__ void k_init_scalars(u64* C, size_t ps, int m, int L, const long long*
     sc->row_lo = row_lo; sc->nloc = nloc; sc->rank = rank; sc->world = world; sc->nk = 1;
     sc->t = 0; sc->E = 0; sc->t2 = 0; sc->E2 = 0;
     sc->maxbits_carry = maxbits; sc->maxbits_new = 0; sc->maxbits_u = 0; sc->maxbits_rowp = 0;
-    sc->bits_D = 1; sc->predicted = 0; sc->last_selected = -1; sc->found = -1;
+    sc->bits_D = 1; sc->predicted = 0; sc->last_selected = -1; sc->found = -1; sc->fatal = 0;
     for (int l = 0; l < RG_MAXL; ++l) { sc->D[l] = l == 0; sc->Dnew[l] = 0; }
 }
 
@@ -983,6 +983,7 @@ template <int L>
 __global__ void __launch_bounds__(1024)
 k_ftran_row0(const u64* __restrict__ C, size_t ps, int m, const long long* __restrict__ aq,
              const long long* __restrict__ cost, int qarg, u64* __restrict__ u, size_t us, Scalars* sc) {
+    // cost == nullptr: plain dot of the (m+1)-vector C[.][1..m] with the scattered column (rg_get_element)
     constexpr int LU = L + 2;
     __shared__ u64 sAcc[32][LU];
     if (sc->status != ST_RUN) return;
@@ -997,7 +998,7 @@ k_ftran_row0(const u64* __restrict__ C, size_t ps, int m, const long long* __res
         load_planar<L>(x, C, ps, (size_t)k);
         mac_small<LU, L>(acc, x, a);
     }
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && cost) {
         long long c = cost[q];
         if (c) {
             u64 d[L];
@@ -1027,7 +1028,7 @@ k_ftran_row0(const u64* __restrict__ C, size_t ps, int m, const long long* __res
             add_n<LU>(acc, other);
         }
         store_planar<LU>(u, us, (size_t)0, acc);
-        atomicMax(&sc->maxbits_u, bitlen_signed<LU>(acc));
+        if (cost) atomicMax(&sc->maxbits_u, bitlen_signed<LU>(acc));
     }
 }
 // list-mode FTRAN: u_i = sum_{k in klist, k >= 1} aq[k-1] C[i][k]  +  [column i trivial] D aq[i-1]
@@ -1097,7 +1098,7 @@ __global__ void k_set_rows(Scalars* sc, int p_local, int pg) {
     if (threadIdx.x == 0 && blockIdx.x == 0) { sc->p = p_local; sc->pg = pg; }
 }
 __global__ void k_set_status(Scalars* sc, int st) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) sc->status = st;
+    if (threadIdx.x == 0 && blockIdx.x == 0) { sc->status = st; if (st == ST_RUN) sc->fatal = 0; }
 }
 
 // stage the pivot row (old values) so the update can run in place.  Row-sharded: the owner copies,
@@ -1150,6 +1151,7 @@ __global__ void k_scalars(int L, int E_host, Scalars* sc) {
     for (int l = 0; l < LU; ++l) a[l] = sc->a[l];
     int sgn = rt_abs(am, a, LU);
     sc->sgn = sgn;
+    if (sgn == 0) { sc->status = ST_FATAL; sc->fatal = 3; return; }   // zero pivot element: the caller's row is invalid
     int bits_a = rt_bitlen_u(am, LU);
     int bits_D = rt_bitlen_u(sc->D, L);
     sc->bits_D = bits_D;
@@ -1158,13 +1160,14 @@ __global__ void k_scalars(int L, int E_host, Scalars* sc) {
     sc->predicted = pred;
     if (pred > 64 * L - 1) {
         sc->status = (L >= RG_MAXL) ? ST_FATAL : ST_PROMOTE;
+        sc->fatal = 1;
         return;
     }
     int t = rt_ctz(sc->D, L);
     int E = E_host;                     // extra limbs of the kernel variant the host launches
     int W = L + E;
     sc->t = t; sc->E = E;
-    if (E < ((t + 63) >> 6)) { sc->status = ST_FATAL; return; }   // variant too narrow for ctz(D)
+    if (E < ((t + 63) >> 6)) { sc->status = ST_FATAL; sc->fatal = 2; return; }   // variant too narrow for ctz(D)
     for (int l = 0; l < L; ++l) dodd[l] = sc->D[l];
     rt_shr(dodd, L, t);
     rt_inv_odd(inv, dodd, L, W, ws);
@@ -1320,7 +1323,7 @@ __global__ void k_finalize(int* basis, unsigned char* inbasis, int L, u64* G, in
             inbasis[leaving] = 0;
             if (want_se) for (int l = 0; l < LG; ++l) G[(size_t)l * n + leaving] = sc->Gq[l];
         }
-        for (int l = 0; l < L; ++l) sc->D[l] = sc->Dnew[l];
+        for (int l = 0; l < L; ++l) { sc->Dold[l] = sc->D[l]; sc->D[l] = sc->Dnew[l]; }
         sc->bits_D = rt_bitlen_u(sc->D, L);
         sc->maxbits_carry = max(sc->maxbits_new, sc->bits_D);     // implicit diagonals hold D
         hm->pivoted = 1; hm->q_done = sc->q; hm->p_done = sc->pg; hm->leaving_done = leaving;
@@ -1333,6 +1336,7 @@ __global__ void k_mirror(Scalars* sc, HostMirror* hm, int L) {
     hm->t_next = rt_ctz(sc->D, L);
     hm->bits_D = sc->bits_D; hm->maxbits_carry = sc->maxbits_carry; hm->predicted = sc->predicted;
     hm->found = sc->found; hm->sgn = sc->sgn; hm->maxbits_tmp = sc->maxbits_tmp; hm->nk = sc->nk;
+    hm->fatal = sc->fatal;
 }
 
 // ---------------------------------------------------------------------------------------------

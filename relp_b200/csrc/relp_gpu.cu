@@ -12,6 +12,7 @@
 #include <nccl.h>   // types only: the library is opened lazily so that single-GPU use has no NCCL dependency
 
 #include "../../include/relp_gpu.h"
+#include "../../include/relp_gpu_test.h"
 #include "kernels.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -413,17 +414,23 @@ extern "C" int rg_set_weights(rg_context* ctx, const int64_t* colfac, const int6
 // ------------------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------------------
-static const bool g_check_launch = getenv("RG_CHECK_LAUNCH") != nullptr;
+// every launch is checked; the first failure is kept (with the kernel's name) and reported by the next
+// synchronising call (launch_failed), so a bad launch configuration can never pass silently
 #define LAUNCH(kernel, grid, block, ...)                                   \
     do {                                                                   \
         kernel<<<grid, block, 0, ctx->stream>>>(__VA_ARGS__);              \
         ctx->launches++;                                                   \
-        if (g_check_launch) {                                              \
-            cudaError_t e__ = cudaGetLastError();                          \
-            if (e__ != cudaSuccess)                                        \
-                fprintf(stderr, "[rank %d] launch of %s failed: %s\n", ctx->rank, #kernel, cudaGetErrorString(e__)); \
-        }                                                                  \
+        cudaError_t e__ = cudaPeekAtLastError();                           \
+        if (e__ != cudaSuccess && ctx->launch_err.empty())                 \
+            ctx->launch_err = std::string("launch of " #kernel " failed: ") + cudaGetErrorString(e__); \
     } while (0)
+static int launch_failed(rg_context* ctx) {
+    if (ctx->launch_err.empty()) return RG_OK;
+    ctx->err = ctx->launch_err;
+    ctx->launch_err.clear();
+    (void)cudaGetLastError();
+    return RG_ERR_CUDA;
+}
 
 // exchange buffers of the row-sharded engine (words of 8 bytes)
 static int ensure_xbuf(rg_context* ctx, size_t send_words, size_t recv_words) {
@@ -470,6 +477,7 @@ static inline const unsigned char* triv_of(rg_context* ctx) { return ctx->list_m
 static int sync_mirror(rg_context* ctx) {
     LAUNCH(k_mirror, 1, 1, ctx->sc, ctx->hm_dev, ctx->L);
     CK(cudaStreamSynchronize(ctx->stream));
+    RG_TRY(launch_failed(ctx));
     CK(cudaGetLastError());
     ctx->t_cur = ctx->hm->t_next;
     ctx->nk_host = ctx->hm->nk;
@@ -928,6 +936,7 @@ static int do_pivot(rg_context* ctx, int q, int fixed_row, bool want_se, bool re
             ctx->launches += ge->launches;
             CK(cudaStreamSynchronize(ctx->stream));
             g_graph_prof[1] += tl1 - tl0; g_graph_prof[2] += now_s() - tl1; g_graph_prof[4] += 1;
+            RG_TRY(launch_failed(ctx));
             CK(cudaGetLastError());
             ctx->t_cur = ctx->hm->t_next;
             ctx->nk_host = ctx->hm->nk;
@@ -944,8 +953,10 @@ static int do_pivot(rg_context* ctx, int q, int fixed_row, bool want_se, bool re
             continue;
         }
         if (ctx->hm->status == ST_FATAL) {
-            ctx->err = "numerators exceed 16 limbs (or kernel variant mismatch)";
-            return RG_ERR_OVERFLOW;
+            if (ctx->hm->fatal == 3) { ctx->err = "pivot element is zero (invalid pivot row for this column)"; return RG_ERR_ARG; }
+            ctx->err = ctx->hm->fatal == 2 ? "kernel variant too narrow for the denominator (internal error)"
+                                           : "numerators exceed 16 limbs";
+            return ctx->hm->fatal == 2 ? RG_ERR_STATE : RG_ERR_OVERFLOW;
         }
         if (ctx->hm->pivoted) {
             ctx->pivots++;
@@ -973,6 +984,7 @@ static int do_pivot(rg_context* ctx, int q, int fixed_row, bool want_se, bool re
                 (void)cudaGetLastError();
             }
             ctx->identity_carry = false;
+            ctx->work_valid = want_se;
         }
         return RG_OK;
     }
@@ -1377,6 +1389,54 @@ extern "C" int rg_get_gamma(rg_context* ctx, uint64_t* out) {
     if (!ctx || !ctx->carry || !out) return RG_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     return export_planar(ctx, ctx->G, (size_t)ctx->n, 0, 1, ctx->n, LG_of(ctx->L), out);
+}
+
+// generate_element (tableau/inverse_maintenance/mod.rs:200-215; carry/basis_inverse_rows.rs:179-195): the
+// single entry (B^-1 a_j)[row] = row_row(B^-1) . a_j, numerator over the current denominator.  The row is
+// staged like a pivot row (replicated when row-sharded), the column scattered densely, one block reduces.
+template <int L>
+static void launch_element_t(rg_context* ctx, int j) {
+    LAUNCH(k_scatter_col, cdiv(ctx->m, 256), 256, ctx->aq, ctx->m, ctx->nd, ctx->A.colptr, ctx->A.rowidx,
+           ctx->A.vals, ctx->Acm, ctx->ldc, j, ctx->sc);
+    LAUNCH(k_scatter_col2, cdiv(ctx->m, 256), 256, ctx->aq, ctx->nd, ctx->A.colptr, ctx->A.rowidx, ctx->A.vals, j,
+           ctx->sc);
+    LAUNCH((k_ftran_row0<L>), 1, 1024, ctx->rowp, (size_t)ctx->ld, ctx->m, ctx->aq, (const long long*)nullptr, j,
+           ctx->tmprow, (size_t)ctx->ld, ctx->sc);
+}
+extern "C" int rg_get_element(rg_context* ctx, int32_t row, int32_t j, uint64_t* out) {
+    if (!ctx || !ctx->carry || !out || row < 0 || row >= ctx->m || j < 0 || j >= ctx->n) return RG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    set_status(ctx, ST_RUN);
+    int local = (row >= ctx->row_lo && row < ctx->row_lo + ctx->nloc) ? row - ctx->row_lo + 1 : -1;
+    LAUNCH(k_set_rows, 1, 1, ctx->sc, local, row + 1);
+    RG_TRY(launch_copyrow(ctx));
+    DISPATCH_L(ctx->L, launch_element_t, ctx, j);
+    return export_planar(ctx, ctx->tmprow, (size_t)ctx->ld, 0, 1, 1, LU_of(ctx->L), out);
+}
+
+// BasisChangeComputationInfo (tableau/mod.rs:205-234) of the last basis change, for a host-side PivotRule:
+//   column      column_before_change  = B_old^-1 a_q, m entries of limbs+2 words over `denominator_before`
+//   work        work_vector           = column^T B_old^-1, m entries of 2*limbs+5 words over denominator_before^2
+//                                       (only computed when the steepest-edge update ran; else pass NULL)
+//   row         basis_inverse_row     = row p of the NEW B^-1, m entries of limbs words over the current denominator
+// Any pointer may be NULL.  Valid until the next call that generates a column or changes the basis.
+extern "C" int rg_get_basis_change_info(rg_context* ctx, uint64_t* column, uint64_t* work, uint64_t* row,
+                                        uint64_t* denominator_before) {
+    if (!ctx || !ctx->carry) return RG_ERR_ARG;
+    if (ctx->pivots == 0 || ctx->hm->p_done < 1) { ctx->err = "no basis change has been performed"; return RG_ERR_STATE; }
+    CK(cudaSetDevice(ctx->device));
+    if (denominator_before) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaMemcpyAsync(denominator_before, ctx->sc->Dold, sizeof(u64) * ctx->L, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    if (column) RG_TRY(export_rows(ctx, ctx->u, (size_t)ctx->ld, 1, 1, LU_of(ctx->L), column));
+    if (work) {
+        if (!ctx->work_valid) { ctx->err = "the work vector is only kept when the steepest-edge update ran"; return RG_ERR_STATE; }
+        RG_TRY(export_planar(ctx, ctx->omega, (size_t)ctx->ld, 1, 1, ctx->m, LW_of(ctx->L), work));
+    }
+    if (row) RG_TRY(rg_get_basis_inverse_row(ctx, ctx->hm->p_done - 1, row));
+    return RG_OK;
 }
 extern "C" int rg_get_stats(rg_context* ctx, rg_stats* out) {
     if (!ctx || !out) return RG_ERR_ARG;

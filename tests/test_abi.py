@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def declared_symbols():
     names = set()
-    for h in ("relp_gpu.h", "relp_host.h"):
+    for h in ("relp_gpu.h", "relp_gpu_test.h", "relp_host.h"):
         text = open(os.path.join(ROOT, "include", h)).read()
         text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
         names |= set(re.findall(r"\b(r[gh]_[a-z0-9_]+)\s*\(", text))
