@@ -91,6 +91,10 @@ typedef struct rg_stats {
      * 1 work vector, 2 pivot scalars, 3 K1 update, 4 bookkeeping + steepest-edge update,
      * 5 pricing + column selection */
     double phase_ms[8];
+    /* profiling: algorithmic work of the timed K1 launches per limb width -- bytes (every entry of the active
+     * part of the carry read and written once) and IMAD.WIDE multiply-adds (two low products per entry) */
+    double k1_bytes_at_limbs[5];
+    double k1_imads_at_limbs[5];
 } rg_stats;
 
 typedef struct rg_pivot_info {   /* BasisChangeComputationInfo, tableau/mod.rs:205-234 (indices only) */

@@ -20,7 +20,8 @@ class rg_stats(C.Structure):
                 ("max_bits", C.c_int32), ("denominator_bits", C.c_int32), ("reserved", C.c_int32),
                 ("kernel_launches", C.c_int64), ("pivots_at_limbs", C.c_int64 * 5),
                 ("k1_launches_at_limbs", C.c_int64 * 5), ("k1_ms_at_limbs", C.c_double * 5),
-                ("timer_ms", C.c_double), ("phase_ms", C.c_double * 8)]
+                ("timer_ms", C.c_double), ("phase_ms", C.c_double * 8),
+                ("k1_bytes_at_limbs", C.c_double * 5), ("k1_imads_at_limbs", C.c_double * 5)]
 
 
 class rg_pivot_info(C.Structure):
@@ -97,6 +98,7 @@ SYMBOLS = {
     "rg_selftest": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                               C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_int64,
                               C.POINTER(C.c_uint64)]),
+    "rg_measure_imad_peak": (C.c_int, [C.c_int32, C.c_double, C.POINTER(C.c_double)]),
     "rh_solve_relaxation": (C.c_int, [C.POINTER(rh_problem), C.POINTER(rh_options), C.POINTER(P)]),
     "rh_result_free": (None, [P]),
     "rh_result_error": (C.c_char_p, [P]),

@@ -78,6 +78,7 @@ struct rg_context {
     int row_lo = 0, nloc = 0;          // constraint rows owned by this rank
     int d0 = 0, d1 = 0, s0 = 0, s1 = 0;  // provider columns priced by this rank: dense-block slice [d0,d1), CSC slice [s0,s1)
     void* nccl_comm = nullptr;         // ncclComm_t (world > 1)
+    bool own_comm = false;             // communicator created for this context only (RG_NCCL_NO_CACHE)
     u64* xsend = nullptr;              // exchange buffers (world > 1)
     u64* xrecv = nullptr;
     size_t xbytes = 0;
@@ -90,8 +91,13 @@ struct rg_context {
     int m = 0, n = 0;
     int ld = 0;                 // carry leading dimension in entries (multiple of 16)
     int L = 2;                  // current limb count
-    size_t plane = 0;           // entries per carry plane = (m+1) * ld
+    size_t plane = 0;           // entries per carry plane: (nloc+1) * ld in dense mode, ld (cost row only) in list mode
     u64* carry = nullptr;       // L planes
+    // packed active block (list mode): rows 1..nloc of the non-trivial carry columns,
+    // entry (i, t) = C[i][klist[t]] at i * cap + t in each plane -- every access of the hot kernels is coalesced
+    u64* pk = nullptr;          // L planes x (nloc+1) x cap
+    int cap = 0;                // column capacity (multiple of 32), grown by doubling
+    size_t pplane = 0;          // entries per packed plane = (nloc+1) * cap
     u64* u = nullptr;           // LU planes x ld      current pivot column (rows 0..m)
     u64* rowp = nullptr;        // L  planes x ld      staged pivot row
     u64* omega = nullptr;       // LW planes x ld      work vector
@@ -119,6 +125,8 @@ struct rg_context {
     long long* artcost = nullptr; // m: phase-one cost numerator of the artificial of row i
     long long* rowf = nullptr;    // m: factor of the variable currently basic in row i
     rg::Csc A;
+    std::vector<long long> h_colptr, h_vals;   // host copy of the CSC structure (argument validation)
+    std::vector<int> h_rowidx;
     // optional dense int8 block holding provider columns [0, nd): row-major and column-major copies
     int nd = 0;
     signed char* Acm = nullptr; size_t ldc = 0;    // [nd][ldc]
@@ -159,6 +167,9 @@ struct rg_context {
     double phase_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // ftran+ratio+copyrow, work, scalars, K1, finalize+SE update, price+select, mirror
     long long k1_launches[5] = {0, 0, 0, 0, 0};
     double k1_ms[5] = {0, 0, 0, 0, 0};
+    double k1_bytes[5] = {0, 0, 0, 0, 0};   // algorithmic bytes / IMAD.WIDE of the timed K1 launches (roofline accounting)
+    double k1_imads[5] = {0, 0, 0, 0, 0};
+    double k1_cur_bytes = 0, k1_cur_imads = 0;   // of the launch in flight
     double timer_ms = 0;
     std::string err;
     std::string launch_err;            // first failed kernel launch since the last synchronising call

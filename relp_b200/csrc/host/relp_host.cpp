@@ -50,7 +50,15 @@ public:
         opts.rank = o.world > 1 ? o.rank : 0;
         opts.nccl_unique_id = o.nccl_unique_id;
         opts.dense_carry = o.dense_carry;
-        check(nullptr, rg_create(&opts, &ctx), "rg_create");
+        {
+            int rc = rg_create(&opts, &ctx);
+            if (rc != RG_OK) {          // the destructor will not run: release the half-built context here
+                std::string why = ctx ? rg_last_error(ctx) : "";
+                if (ctx) rg_destroy(ctx);
+                ctx = nullptr;
+                throw Error{rc, "rg_create: " + why};
+            }
+        }
         check(ctx, rg_load_csc(ctx, m, n, mp.p->colptr, mp.p->rowidx, mp.p->vals), "rg_load_csc");
         if (mp.p->n_dense > 0) check(ctx, rg_load_dense_i8(ctx, mp.p->n_dense, mp.p->dense), "rg_load_dense_i8");
         check(ctx, rg_set_rhs(ctx, mp.p->rhs), "rg_set_rhs");
@@ -275,6 +283,12 @@ extern "C" int rh_solve_relaxation(const rh_problem* problem, const rh_options* 
     } catch (const relp::Error& e) {
         res->err = e.what;
         return e.code;
+    } catch (const std::exception& e) {     // nothing may propagate across the C boundary
+        res->err = std::string("host driver: ") + e.what();
+        return RG_ERR_STATE;
+    } catch (...) {
+        res->err = "host driver: unknown exception";
+        return RG_ERR_STATE;
     }
     return RG_OK;
 }

@@ -20,8 +20,8 @@ __device__ __forceinline__ int warp_max(int v) {
 // products.  (Carry::change_basis + update_b + update_minus_pi_and_obj, carry/mod.rs:561-604,295-349;
 // BasisInverseRows::{normalize_pivot_row,row_reduce}, basis_inverse_rows.rs:43-84.)
 // Thread = CP adjacent columns (CP = 2: 128-bit loads/stores); block = blockDim*CP columns x RT rows
-// (dense mode: 256 threads x 32 rows; active-column mode: 128 threads x 8 rows, the list is short and the
-// serial row loop is what bounds the launch).
+// (dense mode: 256 threads x 32 rows; active-column mode: 128 threads x 8 rows over the packed block, the
+// list is short and the serial row loop is what bounds the launch).
 // ---------------------------------------------------------------------------------------------
 template <int L, int E, int CP, int RT = 32>
 __global__ void __launch_bounds__(256)
@@ -67,20 +67,24 @@ k_update(u64* __restrict__ C, size_t ps, int ld, int row_first, int nrows, const
         }
     }
     __syncthreads();
-    // dense mode: CP adjacent columns per thread; list mode (klist != nullptr, CP == 1): the idx-th
-    // non-trivial column -- trivial columns are never touched
+    // dense mode: CP adjacent columns per thread.  List mode (klist != nullptr): C is the PACKED active block
+    // (`ld` = its column capacity) and the thread owns list positions idx .. idx+CP-1, whose pivot-row
+    // entries are gathered once from the densely staged row through klist -- trivial columns are never
+    // touched and every access of the row loop below is a coalesced 64/128-bit one
     const int idx = (blockIdx.x * blockDim.x + tid) * CP;
-    const int col = klist ? (idx < sc->nk ? klist[idx] : ld) : idx;
+    const int ncol = klist ? sc->nk : ld;
     int maxb = 0;
-    if (col < ld) {
+    if (idx < ncol) {
+        const int col = idx;
         const int t = sc->t;
         const int tw = t >> 5, tb = t & 31;
         u32 rp[CP][N];
 #pragma unroll
         for (int c = 0; c < CP; ++c) {
+            const int rc = klist ? (idx + c < ncol ? klist[idx + c] : -1) : idx + c;
 #pragma unroll
             for (int l = 0; l < L; ++l) {
-                u64 v = rowp[(size_t)l * rs + col + c];
+                u64 v = rc >= 0 ? rowp[(size_t)l * rs + rc] : 0ull;
                 rp[c][2 * l] = (u32)v; rp[c][2 * l + 1] = (u32)(v >> 32);
             }
             u32 sg = (int)rp[c][2 * L - 1] < 0 ? ~0u : 0u;

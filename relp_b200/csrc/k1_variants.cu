@@ -31,10 +31,11 @@ void launch_le(rg_context* ctx) {
                                                              ctx->sc);
         ctx->launches++;
         if (ctx->nloc > 0) {
-            dim3 g1(cdiv(ctx->nk_grid, 128), cdiv(ctx->nloc, 8));
-            k_update<L, E, 1, 8><<<g1, 128, 0, ctx->stream>>>(ctx->carry, ctx->plane, ctx->ld, 1, ctx->nloc + 1,
-                                                              (const int*)ctx->klist, ctx->u, (size_t)ctx->ld,
-                                                              ctx->rowp, (size_t)ctx->ld, ctx->sc);
+            // rows 1..nloc: the packed active block (column slot = list position, stride = capacity)
+            dim3 g1(cdiv(ctx->nk_grid, 128 * CP), cdiv(ctx->nloc, 8));
+            k_update<L, E, CP, 8><<<g1, 128, 0, ctx->stream>>>(ctx->pk, ctx->pplane, ctx->cap, 1, ctx->nloc + 1,
+                                                               (const int*)ctx->klist, ctx->u, (size_t)ctx->ld,
+                                                               ctx->rowp, (size_t)ctx->ld, ctx->sc);
             ctx->launches++;
         }
         return;

@@ -71,7 +71,9 @@ __global__ void k_zero(u64* p, size_t n) {
 }
 
 // local rows: b in column 0, 1 on the diagonal (global column index).
-__global__ void k_init_identity(u64* C, size_t ps, int ld, int nloc, int row_lo, int L, const long long* rhs) {
+// (packed active block: only column 0 exists at the start, the unit diagonal is implicit: diag = 0)
+__global__ void k_init_identity(u64* C, size_t ps, int ld, int nloc, int row_lo, int L, const long long* rhs,
+                                int diag) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;   // local constraint row
     if (i >= nloc) return;
     int g = row_lo + i;
@@ -79,7 +81,7 @@ __global__ void k_init_identity(u64* C, size_t ps, int ld, int nloc, int row_lo,
     long long b = rhs[g];
     C[r + 0] = (u64)b;
     for (int l = 1; l < L; ++l) C[l * ps + r + 0] = b < 0 ? ~0ull : 0ull;
-    C[r + (g + 1)] = 1;
+    if (diag) C[r + (g + 1)] = 1;
 }
 // cost row (replicated on every rank): -1 under artificial rows
 __global__ void k_init_row0(u64* C, size_t ps, int m, int L, const int* basis, const long long* artcost) {
@@ -927,8 +929,9 @@ __global__ void k_init_active(unsigned char* triv, int* klist, int* kpos, int ld
     if (k == 0) klist[0] = 0;
 }
 // before the pivot row is staged: materialise the pivot row's own column if it is still trivial
+// (packed block P: the column gets the next free slot, position sc->nk; k_activate_pivot_column lists it)
 __global__ void __launch_bounds__(256)
-k_materialise_pivot_column(u64* __restrict__ C, size_t ps, int ld, int L, const unsigned char* __restrict__ triv,
+k_materialise_pivot_column(u64* __restrict__ P, size_t ps, int cap, int L, const unsigned char* __restrict__ triv,
                            const Scalars* sc) {
     if (sc->status != ST_RUN) return;
     const int k = sc->pg;
@@ -936,7 +939,18 @@ k_materialise_pivot_column(u64* __restrict__ C, size_t ps, int ld, int L, const 
     int li = blockIdx.x * blockDim.x + threadIdx.x + 1;      // local carry row
     if (li > sc->nloc) return;
     bool diag = sc->row_lo + li == k;
-    for (int l = 0; l < L; ++l) C[(size_t)l * ps + (size_t)li * ld + k] = diag ? sc->D[l] : 0ull;
+    const int pos = sc->nk;
+    for (int l = 0; l < L; ++l) P[(size_t)l * ps + (size_t)li * cap + pos] = diag ? sc->D[l] : 0ull;
+}
+// leave list mode: scatter the packed columns into the full carry (thread = list position, block row = carry row)
+__global__ void __launch_bounds__(128)
+k_unpack(u64* __restrict__ C, size_t ps, int ld, const u64* __restrict__ P, size_t pps, int cap, int L,
+         const int* __restrict__ klist, const Scalars* sc) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= sc->nk) return;
+    const int k = klist[t];
+    for (int li = 1 + blockIdx.y; li <= sc->nloc; li += gridDim.y)
+        for (int l = 0; l < L; ++l) C[(size_t)l * ps + (size_t)li * ld + k] = P[(size_t)l * pps + (size_t)li * cap + t];
 }
 __global__ void k_activate_pivot_column(unsigned char* triv, int* klist, int* kpos, Scalars* sc) {
     if (threadIdx.x || blockIdx.x) return;
@@ -1056,7 +1070,7 @@ k_ftran_list(const u64* __restrict__ C, size_t ps, int ld, int nrows, int m, con
             long long a = aq[k - 1];
             if (!a) continue;
             u64 x[L];
-            load_planar<L>(x, C, ps, row + k);
+            load_planar<L>(x, C, ps, row + t);           // packed block: column klist[t] lives at position t
             mac_small<LU, L>(acc, x, a);
         }
         if (lane == 0) {
@@ -1105,14 +1119,17 @@ __global__ void k_set_status(Scalars* sc, int st) {
 // the other ranks zero-fill and a sum all-reduce (exact: one non-zero contributor) replicates it.
 template <int L>
 __global__ void __launch_bounds__(256)
-k_copyrow(const u64* __restrict__ C, size_t ps, int ld, const unsigned char* __restrict__ triv,
-          u64* __restrict__ rowp, size_t rs, Scalars* sc) {
+k_copyrow(const u64* __restrict__ C, size_t ps, int ld, int stride, int m, const unsigned char* __restrict__ triv,
+          const int* __restrict__ kpos, u64* __restrict__ rowp, size_t rs, Scalars* sc) {
+    // dense mode: C = carry, stride = ld, triv = kpos = nullptr.  List mode: C = packed block, stride = cap;
+    // a non-trivial column k sits at position kpos[k]; columns beyond m (padding) are zero.
     if (sc->status != ST_RUN) return;
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k < ld) {
         u64 x[L];
         // trivial columns hold D e_k implicitly; the pivot row's own column was materialised before
-        if (sc->p >= 1 && !(triv && triv[k])) load_planar<L>(x, C, ps, (size_t)sc->p * ld + k);
+        if (sc->p >= 1 && !(triv && triv[k]) && !(kpos && k > m))
+            load_planar<L>(x, C, ps, (size_t)sc->p * stride + (kpos ? kpos[k] : k));
         else {
             // implicit entry of a trivial column: D on its own row, 0 elsewhere
             const bool diag = sc->p >= 1 && triv && triv[k] && k == sc->pg;
@@ -1364,83 +1381,76 @@ template <int L, int LSRC, int LOUT>
 __global__ void __launch_bounds__(128)
 k_colsum1(const u64* __restrict__ C, size_t ps, int ld, int m, int rows_per_chunk, const int* __restrict__ klist,
           const u64* __restrict__ s, size_t ss, u64* __restrict__ part, int pcols, const Scalars* sc) {
-    constexpr int RB = 64;                 // rows whose factors are staged in shared memory at a time
-    __shared__ u64 sMag[RB][LSRC];
-    __shared__ int sSign[RB];
+    // Two's complement accumulation in 32-bit limbs: acc += C[i][k] * s_i mod 2^(32 NW) with the IMAD.WIDE carry
+    // chains of mp32.cuh (every chain runs to the top limb, so the running sums need no carry fix-up between
+    // rows).  NW covers |C| < 2^(64 L), |s| < 2^(64 LSRC) and up to 2^32 rows.
+    constexpr int RB = 32;                 // rows whose factors are staged in shared memory at a time
+    constexpr int WS = (L + LSRC + 1) < LOUT ? (L + LSRC + 1) : LOUT;   // 64-bit limbs of the running sum
+    constexpr int NW = 2 * WS;
+    __shared__ u32 sU[RB][NW];             // factors, sign-extended to NW limbs
+    __shared__ unsigned char sNz[RB];
     if (sc->status != ST_RUN) return;
     const int kidx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int k = klist ? (kidx < sc->nk ? klist[kidx] : ld) : kidx;   // list mode: non-trivial columns only
+    // list mode (klist != nullptr): C is the packed block, `ld` its capacity, column slot = list position
+    const int k = klist ? (kidx < sc->nk ? kidx : ld) : kidx;
     const int r0 = 1 + blockIdx.y * rows_per_chunk;
     const int r1 = min(m + 1, r0 + rows_per_chunk);
-    u64 acc[LOUT];
+    u32 ev[NW], od[NW];
 #pragma unroll
-    for (int l = 0; l < LOUT; ++l) acc[l] = 0;
+    for (int l = 0; l < NW; ++l) { ev[l] = 0; od[l] = 0; }
     for (int base = r0; base < r1; base += RB) {
         __syncthreads();
         if (threadIdx.x < RB) {
             int i = base + threadIdx.x;
-            int sg = 0;
+            u64 o = 0;
             if (i < r1) {
                 u64 x[LSRC];
                 load_planar<LSRC>(x, s, ss, (size_t)i);
-                bool neg = (i64)x[LSRC - 1] < 0;
-                u64 o = 0;
-                if (neg) {
-                    u64 c = 1;
+                const u32 sg = (i64)x[LSRC - 1] < 0 ? ~0u : 0u;
 #pragma unroll
-                    for (int l = 0; l < LSRC; ++l) { u64 v = ~x[l] + c; c = (c && v == 0) ? 1 : 0; x[l] = v; }
+                for (int l = 0; l < WS; ++l) {
+                    if (l < LSRC) { sU[threadIdx.x][2 * l] = (u32)x[l]; sU[threadIdx.x][2 * l + 1] = (u32)(x[l] >> 32); o |= x[l]; }
+                    else { sU[threadIdx.x][2 * l] = sg; sU[threadIdx.x][2 * l + 1] = sg; }
                 }
-#pragma unroll
-                for (int l = 0; l < LSRC; ++l) { sMag[threadIdx.x][l] = x[l]; o |= x[l]; }
-                sg = o == 0 ? 0 : (neg ? -1 : 1);
             }
-            sSign[threadIdx.x] = sg;
+            sNz[threadIdx.x] = o != 0;
         }
         __syncthreads();
         if (k >= ld) continue;
         const int rn = min(RB, r1 - base);
         for (int r = 0; r < rn; ++r) {
-            int sgn = sSign[r];
-            if (sgn == 0) continue;        // rows with a zero factor are never read
+            if (!sNz[r]) continue;         // rows with a zero factor are never read (uniform over the block)
             u64 x[L];
             load_planar<L>(x, C, ps, (size_t)(base + r) * ld + k);
             u64 any = 0;
 #pragma unroll
             for (int l = 0; l < L; ++l) any |= x[l];
             if (any == 0) continue;        // zero entries contribute nothing
-            u64 sm[LSRC];
+            u32 xe[NW];
+            const u32 sg = (i64)x[L - 1] < 0 ? ~0u : 0u;
 #pragma unroll
-            for (int l = 0; l < LSRC; ++l) sm[l] = sMag[r][l];
-            bool neg = (i64)x[L - 1] < 0;
-            if (neg) {
-                u64 c = 1;
-#pragma unroll
-                for (int l = 0; l < L; ++l) { u64 v = ~x[l] + c; c = (c && v == 0) ? 1 : 0; x[l] = v; }
-                sgn = -sgn;
+            for (int l = 0; l < WS; ++l) {
+                xe[2 * l] = l < L ? (u32)x[l] : sg;
+                xe[2 * l + 1] = l < L ? (u32)(x[l] >> 32) : sg;
             }
-            u64 pr[LSRC + L];
-            mul_full_ct<LSRC, L>(pr, sm, x);
-            if (sgn > 0) {
-                u64 cf = 0;
-#pragma unroll
-                for (int l = 0; l < LOUT; ++l) {
-                    u64 b = l < LSRC + L ? pr[l] : 0;
-                    u64 v = acc[l] + b; u64 c1 = v < b; u64 v2 = v + cf; u64 c2 = v2 < v;
-                    acc[l] = v2; cf = c1 + c2;
-                }
-            } else {
-                u64 bf = 0;
-#pragma unroll
-                for (int l = 0; l < LOUT; ++l) {
-                    u64 b = l < LSRC + L ? pr[l] : 0;
-                    u64 v = acc[l] - b; u64 b1 = acc[l] < b; u64 v2 = v - bf; u64 b2 = v < bf;
-                    acc[l] = v2; bf = b1 + b2;
-                }
-            }
+            MpRows<NW, 0>::run(ev, od, xe, sU[r]);
         }
     }
-    // partial sums are indexed by column (dense mode) or by list position (list mode), row stride pcols
-    if (k < ld) store_planar<LOUT>(part + (size_t)blockIdx.y * LOUT * pcols, (size_t)pcols, (size_t)(klist ? kidx : k), acc);
+    if (k < ld) {
+        // merge the even / odd chains, then sign-extend to the LOUT limbs of the partial sums
+        u32 r32[NW];
+        r32[0] = ev[0];
+        asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r32[1]) : "r"(ev[1]), "r"(od[0]));
+#pragma unroll
+        for (int q = 2; q < NW; ++q)
+            asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r32[q]) : "r"(ev[q]), "r"(od[q - 1]));
+        u64 acc[LOUT];
+        const u64 sgo = (int)r32[NW - 1] < 0 ? ~0ull : 0ull;
+#pragma unroll
+        for (int l = 0; l < LOUT; ++l) acc[l] = l < WS ? ((u64)r32[2 * l] | ((u64)r32[2 * l + 1] << 32)) : sgo;
+        // partial sums are indexed by column (dense mode) or by list position (list mode), row stride pcols
+        store_planar<LOUT>(part + (size_t)blockIdx.y * LOUT * pcols, (size_t)pcols, (size_t)k, acc);
+    }
 }
 
 // List mode, stage 0: compact the local rows whose factor s_i is non-zero (order is irrelevant: the sums
@@ -1713,7 +1723,8 @@ k_gamma_init_general(const u64* __restrict__ C, size_t ps, int ld, int m, int n,
                      const long long* __restrict__ vals, const unsigned char* __restrict__ inbasis,
                      u64* __restrict__ G, int add_d2, const long long* __restrict__ wf,
                      const long long* __restrict__ rowf, const unsigned char* __restrict__ triv,
-                     const Scalars* sc) {
+                     const int* __restrict__ kpos, const Scalars* sc) {
+    // list mode (triv != nullptr): C is the packed block, ld its capacity, column ck at position kpos[ck]
     constexpr int LU = L + 2, LG = 2 * L + 6;
     __shared__ u64 sAcc[4][LG];
     int j = blockIdx.x;
@@ -1738,7 +1749,7 @@ k_gamma_init_general(const u64* __restrict__ C, size_t ps, int ld, int m, int n,
 #pragma unroll
                 for (int l = 0; l < L; ++l) x[l] = sc->D[l];
             } else {
-                load_planar<L>(x, C, ps, (size_t)i * ld + ck);
+                load_planar<L>(x, C, ps, (size_t)i * ld + (triv ? kpos[ck] : ck));
             }
             mac_small<LU, L>(nu, x, vals[k]);
         }

@@ -107,6 +107,7 @@ static cudaError_t dev_alloc(T** p, size_t bytes, cudaStream_t st) {
     return cudaMallocAsync((void**)p, bytes ? bytes : 8, st);
 }
 static void free_dev_on(void* p, cudaStream_t st) { if (p) cudaFreeAsync(p, st); }
+static int alloc_carry(rg_context* ctx, bool list_mode);
 
 // geometry of the tensor-core dense dots for a vector of LV limbs over this rank's dense columns
 struct DenseGeom { int ncols, ntc, zs, ks, rps, rpitch; size_t rstride_k; };
@@ -182,6 +183,7 @@ static void free_width_buffers(rg_context* ctx) {
 static double g_graph_prof[5] = {0, 0, 0, 0, 0};   // capture s, launch s, sync s, captures, launches
 static std::mutex g_hm_mutex;
 static std::vector<HostMirror*> g_hm_free[16];   // per device: recycled pinned mirrors
+static void drop_graphs(rg_context* ctx);
 static void drop_graphs(rg_context* ctx) {
     for (auto& g : ctx->graphs) cudaGraphExecDestroy(g.exec);
     ctx->graphs.clear();
@@ -233,14 +235,22 @@ extern "C" int rg_create(const rg_options* opts, rg_context** out) {
         // One communicator per (process, world, rank), created by the first context and reused by
         // later ones: NCCL connects its channels lazily (~0.5 s on the first collective).  Every
         // rank takes the same branch because every rank issues the same call sequence.
+        // The cache is keyed on (world, rank, device) only: a NEW unique id with the same key means the same peer
+        // group re-creating its contexts (every rank takes the same branch, so no rank waits in CommInitRank
+        // alone).  A process that talks to DIFFERENT peer groups must set RG_NCCL_NO_CACHE=1 (one communicator
+        // per context, destroyed with it).  Guarded by a mutex: contexts may be created from several threads.
+        static std::mutex comm_mutex;
+        std::lock_guard<std::mutex> comm_lock(comm_mutex);
         static ncclComm_t cached = nullptr;
         static int cached_world = 0, cached_rank = -1, cached_dev = -1;
-        if (!cached || cached_world != ctx->world || cached_rank != ctx->rank || cached_dev != ctx->device) {
+        const bool no_cache = getenv("RG_NCCL_NO_CACHE") != nullptr;
+        if (no_cache || !cached || cached_world != ctx->world || cached_rank != ctx->rank || cached_dev != ctx->device) {
             ncclUniqueId id;
             memcpy(&id, opts->nccl_unique_id, sizeof(id));
             ncclComm_t comm;
             NK(api->CommInitRank(&comm, ctx->world, id, ctx->rank));
-            cached = comm; cached_world = ctx->world; cached_rank = ctx->rank; cached_dev = ctx->device;
+            if (no_cache) ctx->own_comm = true;
+            else { cached = comm; cached_world = ctx->world; cached_rank = ctx->rank; cached_dev = ctx->device; }
             // warm the all-gather and all-reduce paths (connection setup) outside any solve
             u64* w = nullptr;
             CK(dev_alloc(&w, sizeof(u64) * 64 * (ctx->world + 1), ctx->stream));
@@ -249,8 +259,10 @@ extern "C" int rg_create(const rg_options* opts, rg_context** out) {
             NK(api->AllReduce(w, w, 64, ncclUint64, ncclSum, comm, ctx->stream));
             CK(cudaStreamSynchronize(ctx->stream));
             free_dev_on(w, ctx->stream);
+            ctx->nccl_comm = comm;
+        } else {
+            ctx->nccl_comm = cached;
         }
-        ctx->nccl_comm = cached;
     }
     return RG_OK;
 }
@@ -269,7 +281,7 @@ extern "C" int rg_destroy(rg_context* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     free_width_buffers(ctx);
-    free_dev_on(ctx->carry, ctx->stream); free_dev_on(ctx->A.colptr, ctx->stream); free_dev_on(ctx->A.rowidx, ctx->stream); free_dev_on(ctx->A.vals, ctx->stream);
+    free_dev_on(ctx->carry, ctx->stream); free_dev_on(ctx->pk, ctx->stream); free_dev_on(ctx->A.colptr, ctx->stream); free_dev_on(ctx->A.rowidx, ctx->stream); free_dev_on(ctx->A.vals, ctx->stream);
     free_dev_on(ctx->cost, ctx->stream); free_dev_on(ctx->rhs, ctx->stream); free_dev_on(ctx->basis, ctx->stream); free_dev_on(ctx->inbasis, ctx->stream);
     free_dev_on(ctx->G, ctx->stream); free_dev_on(ctx->cand, ctx->stream); free_dev_on(ctx->score, ctx->stream); free_dev_on(ctx->sc, ctx->stream); free_dev_on(ctx->svec, ctx->stream);
     free_dev_on(ctx->triv, ctx->stream); free_dev_on(ctx->klist, ctx->stream); free_dev_on(ctx->nzrows, ctx->stream); free_dev_on(ctx->kpos, ctx->stream); free_dev_on(ctx->aq, ctx->stream);
@@ -290,7 +302,8 @@ extern "C" int rg_destroy(rg_context* ctx) {
     if (ctx->ev_side0) { cudaEventDestroy(ctx->ev_side0); cudaEventDestroy(ctx->ev_side1); cudaEventDestroy(ctx->ev_side2); cudaEventDestroy(ctx->ev_work); cudaEventDestroy(ctx->ev_side3); }
     if (ctx->side2) cudaStreamDestroy(ctx->side2);
     if (ctx->side3) cudaStreamDestroy(ctx->side3);
-    // the communicator is process-cached (see rg_create) and intentionally not destroyed here
+    // the communicator is process-cached (see rg_create) unless this context owns it
+    if (ctx->own_comm && ctx->nccl_comm && nccl_api()) nccl_api()->CommDestroy((ncclComm_t)ctx->nccl_comm);
     if (ctx->side) cudaStreamDestroy(ctx->side);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -317,12 +330,19 @@ extern "C" int rg_load_csc(rg_context* ctx, int32_t m, int32_t n, const int64_t*
         ctx->s0 = std::min(n, ctx->rank * cq);
         ctx->s1 = std::min(n, (ctx->rank + 1) * cq);
     }
-    ctx->plane = (size_t)(ctx->nloc + 1) * ctx->ld;
     long long nnz = colptr[n];
     ctx->A.nnz = nnz;
-    for (long long j = 0; j < n; ++j)
-        for (long long k = colptr[j]; k < colptr[j + 1]; ++k)
+    if (colptr[0] != 0) { ctx->err = "rg_load_csc: colptr[0] must be 0"; return RG_ERR_ARG; }
+    for (long long j = 0; j < n; ++j) {
+        if (colptr[j + 1] < colptr[j]) { ctx->err = "rg_load_csc: colptr must be non-decreasing"; return RG_ERR_ARG; }
+        for (long long k = colptr[j]; k < colptr[j + 1]; ++k) {
             if (rowidx[k] < 0 || rowidx[k] >= m) { ctx->err = "rg_load_csc: row index out of range"; return RG_ERR_ARG; }
+            if (k > colptr[j] && rowidx[k] <= rowidx[k - 1]) { ctx->err = "rg_load_csc: row indices must ascend within a column"; return RG_ERR_ARG; }
+        }
+    }
+    ctx->h_colptr.assign(colptr, colptr + n + 1);     // host copies of the structure: unit-column validation
+    ctx->h_rowidx.assign(rowidx, rowidx + nnz);
+    ctx->h_vals.assign(vals, vals + nnz);
     CK(dev_alloc(&ctx->A.colptr, sizeof(long long) * (n + 1), ctx->stream));
     CK(dev_alloc(&ctx->A.rowidx, sizeof(int) * std::max<long long>(nnz, 1), ctx->stream));
     CK(dev_alloc(&ctx->A.vals, sizeof(long long) * std::max<long long>(nnz, 1), ctx->stream));
@@ -351,7 +371,7 @@ extern "C" int rg_load_csc(rg_context* ctx, int32_t m, int32_t n, const int64_t*
     ctx->work_chunks = std::max(1, std::min(16, cdiv(std::max(ctx->nloc, 1), 256)));
     ctx->list_chunks = std::max(1, cdiv(std::max(ctx->nloc, 1), 64));        // 64 rows per chunk in list mode
     ctx->list_pcols = ((m + 1) / 3 + 2 + 127) / 128 * 128;                    // the list never exceeds (m+1)/3 + 1
-    CK(dev_alloc(&ctx->carry, sizeof(u64) * ctx->L * ctx->plane, ctx->stream));
+    RG_TRY(alloc_carry(ctx, true));   // cost row + packed block; rg_init_identity_basis picks the real mode
     CK(dev_alloc(&ctx->G, sizeof(u64) * LG_of(ctx->L) * n, ctx->stream));
     CK(cudaMemsetAsync(ctx->G, 0, sizeof(u64) * LG_of(ctx->L) * n, ctx->stream));
     RG_TRY(alloc_width_buffers(ctx, ctx->L));
@@ -473,6 +493,50 @@ static inline void rec_event(rg_context* ctx, cudaEvent_t ev) {
 }
 static inline const int* klist_of(rg_context* ctx) { return ctx->list_mode ? ctx->klist : nullptr; }
 static inline const unsigned char* triv_of(rg_context* ctx) { return ctx->list_mode ? ctx->triv : nullptr; }
+static inline const int* kpos_of(rg_context* ctx) { return ctx->list_mode ? ctx->kpos : nullptr; }
+// rows 1..nloc of the carry in the current mode: the packed active block (list mode) or the dense carry
+struct BlockView { u64* base; size_t ps; int stride; };
+static inline BlockView block_of(rg_context* ctx) {
+    if (ctx->list_mode) return BlockView{ctx->pk, ctx->pplane, ctx->cap};
+    return BlockView{ctx->carry, ctx->plane, ctx->ld};
+}
+// (re)allocates the carry for a mode at the current limb width, zero-filled.  List mode: the cost row
+// (L planes x ld) plus the packed active block; dense mode: the full (nloc+1) x ld carry.
+static int alloc_carry(rg_context* ctx, bool list_mode) {
+    free_dev_on(ctx->carry, ctx->stream); ctx->carry = nullptr;
+    free_dev_on(ctx->pk, ctx->stream); ctx->pk = nullptr;
+    ctx->list_mode = list_mode;
+    if (list_mode) {
+        ctx->plane = (size_t)ctx->ld;
+        ctx->cap = ctx->m >= 1024 ? 128 : 32;
+        ctx->pplane = (size_t)(ctx->nloc + 1) * ctx->cap;
+        CK(dev_alloc(&ctx->pk, sizeof(u64) * ctx->L * ctx->pplane, ctx->stream));
+        CK(cudaMemsetAsync(ctx->pk, 0, sizeof(u64) * ctx->L * ctx->pplane, ctx->stream));
+    } else {
+        ctx->plane = (size_t)(ctx->nloc + 1) * ctx->ld;
+        ctx->cap = 0; ctx->pplane = 0;
+    }
+    CK(dev_alloc(&ctx->carry, sizeof(u64) * ctx->L * ctx->plane, ctx->stream));
+    CK(cudaMemsetAsync(ctx->carry, 0, sizeof(u64) * ctx->L * ctx->plane, ctx->stream));
+    return RG_OK;
+}
+static void drop_graphs(rg_context* ctx);
+// the list outgrew the packed block: double its capacity (2D copy, new slots zero)
+static int grow_packed(rg_context* ctx, int need) {
+    if (!ctx->list_mode || need <= ctx->cap) return RG_OK;
+    int cap2 = ctx->cap;
+    while (cap2 < need) cap2 *= 2;
+    size_t pplane2 = (size_t)(ctx->nloc + 1) * cap2;
+    u64* np = nullptr;
+    CK(dev_alloc(&np, sizeof(u64) * ctx->L * pplane2, ctx->stream));
+    CK(cudaMemsetAsync(np, 0, sizeof(u64) * ctx->L * pplane2, ctx->stream));
+    CK(cudaMemcpy2DAsync(np, sizeof(u64) * cap2, ctx->pk, sizeof(u64) * ctx->cap, sizeof(u64) * ctx->cap,
+                         (size_t)ctx->L * (ctx->nloc + 1), cudaMemcpyDeviceToDevice, ctx->stream));
+    free_dev_on(ctx->pk, ctx->stream);
+    ctx->pk = np; ctx->cap = cap2; ctx->pplane = pplane2;
+    drop_graphs(ctx);   // captured pointers are stale
+    return RG_OK;
+}
 
 static int sync_mirror(rg_context* ctx) {
     LAUNCH(k_mirror, 1, 1, ctx->sc, ctx->hm_dev, ctx->L);
@@ -567,7 +631,7 @@ static void launch_ftran_t(rg_context* ctx, int q) {
                q, ctx->sc);
         LAUNCH((k_ftran_row0<L>), 1, 1024, ctx->carry, ctx->plane, ctx->m, ctx->aq, ctx->cost, q, ctx->u,
                (size_t)ctx->ld, ctx->sc);
-        LAUNCH((k_ftran_list<L>), cdiv((long long)(ctx->nloc + 1) * 32, 256), 256, ctx->carry, ctx->plane, ctx->ld,
+        LAUNCH((k_ftran_list<L>), cdiv((long long)(ctx->nloc + 1) * 32, 256), 256, ctx->pk, ctx->pplane, ctx->cap,
                ctx->nloc + 1, ctx->m, ctx->aq, ctx->klist, ctx->triv, ctx->cost, q, ctx->u, (size_t)ctx->ld,
                ctx->sc);
         return;
@@ -583,10 +647,11 @@ static void launch_ftran_t(rg_context* ctx, int q) {
 static void launch_ftran(rg_context* ctx, int q) { DISPATCH_L(ctx->L, launch_ftran_t, ctx, q); }
 
 static int launch_ratio(rg_context* ctx) {
-    CmpRatio c{ctx->carry, ctx->plane, ctx->ld, ctx->L, ctx->u, (size_t)ctx->ld, LU_of(ctx->L), ctx->basis,
+    const BlockView bv = block_of(ctx);        // b = column 0 = list position 0
+    CmpRatio c{bv.base, bv.ps, bv.stride, ctx->L, ctx->u, (size_t)ctx->ld, LU_of(ctx->L), ctx->basis,
                ctx->row_lo};
     const int cnt = std::max(ctx->nloc, 1);
-    LAUNCH(k_score_rows, cdiv(cnt, 256), 256, ctx->nloc, ctx->carry, ctx->plane, ctx->ld, ctx->L, ctx->u,
+    LAUNCH(k_score_rows, cdiv(cnt, 256), 256, ctx->nloc, bv.base, bv.ps, bv.stride, ctx->L, ctx->u,
            (size_t)ctx->ld, LU_of(ctx->L), ctx->score, ctx->sc);
     if (ctx->world == 1) {
         LAUNCH((k_select_scored<CmpRatio>), 1, 1024, 0, ctx->nloc, c, ctx->score, 1, ctx->sc, (const u64*)ctx->u,
@@ -596,7 +661,7 @@ static int launch_ratio(rg_context* ctx) {
     // row-sharded: local candidate -> all-gather -> identical deterministic reduction on every rank
     LAUNCH((k_select_scored<CmpRatio>), 1, 1024, 0, ctx->nloc, c, ctx->score, 3, ctx->sc);
     RG_TRY(ensure_xbuf(ctx, RG_CAND_WORDS, (size_t)RG_CAND_WORDS * ctx->world));
-    LAUNCH(k_ratio_pack, 1, 1, ctx->carry, ctx->plane, ctx->ld, ctx->L, ctx->u, (size_t)ctx->ld, ctx->basis,
+    LAUNCH(k_ratio_pack, 1, 1, bv.base, bv.ps, bv.stride, ctx->L, ctx->u, (size_t)ctx->ld, ctx->basis,
            ctx->xsend, ctx->sc);
     RG_TRY(all_gather(ctx, ctx->xsend, ctx->xrecv, RG_CAND_WORDS));
     LAUNCH(k_ratio_merge, 1, 1, ctx->xrecv, ctx->world, ctx->L, ctx->sc);
@@ -611,7 +676,8 @@ static int launch_fixed_row(rg_context* ctx, int row) {
         return RG_OK;
     }
     RG_TRY(ensure_xbuf(ctx, RG_CAND_WORDS, (size_t)RG_CAND_WORDS * ctx->world));
-    LAUNCH(k_ratio_pack, 1, 1, ctx->carry, ctx->plane, ctx->ld, ctx->L, ctx->u, (size_t)ctx->ld, ctx->basis,
+    const BlockView bv = block_of(ctx);
+    LAUNCH(k_ratio_pack, 1, 1, bv.base, bv.ps, bv.stride, ctx->L, ctx->u, (size_t)ctx->ld, ctx->basis,
            ctx->xsend, ctx->sc);
     RG_TRY(all_gather(ctx, ctx->xsend, ctx->xrecv, RG_CAND_WORDS));
     LAUNCH(k_ratio_merge, 1, 1, ctx->xrecv, ctx->world, ctx->L, ctx->sc);
@@ -620,8 +686,9 @@ static int launch_fixed_row(rg_context* ctx, int row) {
 
 template <int L>
 static void launch_copyrow_t(rg_context* ctx) {
-    LAUNCH((k_copyrow<L>), cdiv(ctx->ld, 256), 256, ctx->carry, ctx->plane, ctx->ld, triv_of(ctx), ctx->rowp,
-           (size_t)ctx->ld, ctx->sc);
+    const BlockView bv = block_of(ctx);
+    LAUNCH((k_copyrow<L>), cdiv(ctx->ld, 256), 256, bv.base, bv.ps, ctx->ld, bv.stride, ctx->m, triv_of(ctx),
+           kpos_of(ctx), ctx->rowp, (size_t)ctx->ld, ctx->sc);
 }
 template <int L>
 static void launch_rowbits_t(rg_context* ctx) {
@@ -667,35 +734,28 @@ static int launch_work_t(rg_context* ctx) {
                ctx->us2, (size_t)ctx->ld, ctx->sc);
         src = ctx->us2;
     }
-    if (ctx->list_mode) {
-        // non-trivial columns: compacted non-zero rows, one warp per (column, row-list segment); k_colsum2
-        // sums the segments and adds the trivial columns (s_k * D)
-        const int nl = std::max(ctx->nloc, 1);
-        const int nseg = std::max(1, std::min(ctx->list_chunks, nl / 512));
-        dim3 lgrid(cdiv(g.ncols, 4), nseg);
-        if (ctx->weighted) {
-            LAUNCH((k_nzrows<LU + 1>), cdiv(nl, 256), 256, src, (size_t)ctx->ld, ctx->nloc, ctx->nzrows, ctx->sc);
-            LAUNCH((k_colsum_list<L, LU + 1, LW>), lgrid, 128, ctx->carry, ctx->plane, ctx->ld, g.klist,
-                   ctx->nzrows, src, (size_t)ctx->ld, ctx->omega_part, g.pcols, ctx->sc);
-            LAUNCH((k_colsum2<LW, LU + 1, L>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, nseg, 0,
-                   first_out, ctx->sc, g.triv, src, (size_t)ctx->ld, L, g.kpos, g.pcols);
-        } else {
-            LAUNCH((k_nzrows<LU>), cdiv(nl, 256), 256, src, (size_t)ctx->ld, ctx->nloc, ctx->nzrows, ctx->sc);
-            LAUNCH((k_colsum_list<L, LU, LW>), lgrid, 128, ctx->carry, ctx->plane, ctx->ld, g.klist,
-                   ctx->nzrows, src, (size_t)ctx->ld, ctx->omega_part, g.pcols, ctx->sc);
-            LAUNCH((k_colsum2<LW, LU, L>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, nseg, 0,
-                   first_out, ctx->sc, g.triv, src, (size_t)ctx->ld, L, g.kpos, g.pcols);
-        }
-    } else if (ctx->weighted) {
-        LAUNCH((k_colsum1<L, LU + 1, LW>), grid, 128, ctx->carry, ctx->plane, ctx->ld, ctx->nloc, g.rpc,
+    // stage 1: thread = column (dense carry) or list position (packed active block: every load coalesced),
+    // rows in chunks, rows with a zero factor skipped; stage 2 sums the chunks and adds the implicit
+    // trivial columns (s_k * D)
+    const BlockView bv = block_of(ctx);
+    if (ctx->weighted) {
+        LAUNCH((k_colsum1<L, LU + 1, LW>), grid, 128, bv.base, bv.ps, bv.stride, ctx->nloc, g.rpc,
                g.klist, ctx->us2, (size_t)ctx->ld, ctx->omega_part, g.pcols, ctx->sc);
-        LAUNCH((k_colsum2<LW, LU + 1>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, g.chunks, 0,
-               first_out, ctx->sc, g.triv, src, (size_t)ctx->ld, L, g.kpos, g.pcols);
+        if (ctx->list_mode)
+            LAUNCH((k_colsum2<LW, LU + 1, L>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, g.chunks, 0,
+                   first_out, ctx->sc, g.triv, src, (size_t)ctx->ld, L, g.kpos, g.pcols);
+        else
+            LAUNCH((k_colsum2<LW, LU + 1>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, g.chunks, 0,
+                   first_out, ctx->sc, g.triv, src, (size_t)ctx->ld, L, g.kpos, g.pcols);
     } else {
-        LAUNCH((k_colsum1<L, LU, LW>), grid, 128, ctx->carry, ctx->plane, ctx->ld, ctx->nloc, g.rpc,
+        LAUNCH((k_colsum1<L, LU, LW>), grid, 128, bv.base, bv.ps, bv.stride, ctx->nloc, g.rpc,
                g.klist, ctx->u, (size_t)ctx->ld, ctx->omega_part, g.pcols, ctx->sc);
-        LAUNCH((k_colsum2<LW, LU>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, g.chunks, 0,
-               first_out, ctx->sc, g.triv, src, (size_t)ctx->ld, L, g.kpos, g.pcols);
+        if (ctx->list_mode)
+            LAUNCH((k_colsum2<LW, LU, L>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, g.chunks, 0,
+                   first_out, ctx->sc, g.triv, src, (size_t)ctx->ld, L, g.kpos, g.pcols);
+        else
+            LAUNCH((k_colsum2<LW, LU>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, g.chunks, 0,
+                   first_out, ctx->sc, g.triv, src, (size_t)ctx->ld, L, g.kpos, g.pcols);
     }
     if (ctx->world == 1) return RG_OK;
     RG_TRY(all_gather(ctx, ctx->xsend, ctx->xrecv, words));
@@ -794,12 +854,19 @@ static int promote(rg_context* ctx) {
     CK(dev_alloc(&nc, sizeof(u64) * Lnew * ctx->plane, ctx->stream));
     CK(cudaMemcpyAsync(nc, ctx->carry, sizeof(u64) * Lold * ctx->plane, cudaMemcpyDeviceToDevice, ctx->stream));
     LAUNCH(k_sign_extend, 148 * 8, 256, nc, ctx->plane, ctx->plane, Lold, Lnew);
+    u64* npk = nullptr;
+    if (ctx->list_mode) {   // the packed active block widens the same way
+        CK(dev_alloc(&npk, sizeof(u64) * Lnew * ctx->pplane, ctx->stream));
+        CK(cudaMemcpyAsync(npk, ctx->pk, sizeof(u64) * Lold * ctx->pplane, cudaMemcpyDeviceToDevice, ctx->stream));
+        LAUNCH(k_sign_extend, 148 * 8, 256, npk, ctx->pplane, ctx->pplane, Lold, Lnew);
+    }
     u64* ng = nullptr;
     CK(dev_alloc(&ng, sizeof(u64) * LG_of(Lnew) * ctx->n, ctx->stream));
     CK(cudaMemsetAsync(ng, 0, sizeof(u64) * LG_of(Lnew) * ctx->n, ctx->stream));
     CK(cudaMemcpyAsync(ng, ctx->G, sizeof(u64) * LG_of(Lold) * ctx->n, cudaMemcpyDeviceToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     free_dev_on(ctx->carry, ctx->stream); ctx->carry = nc;
+    if (ctx->list_mode) { free_dev_on(ctx->pk, ctx->stream); ctx->pk = npk; }
     free_dev_on(ctx->G, ctx->stream); ctx->G = ng;
     free_width_buffers(ctx);
     ctx->L = Lnew;
@@ -819,10 +886,22 @@ static inline double now_s() {
 // leave the active-column mode: write every implicit column out and use the dense kernels from now on
 static int switch_to_dense(rg_context* ctx) {
     if (!ctx->list_mode) return RG_OK;
+    // the full (nloc+1) x ld carry: cost row copied, packed columns scattered, implicit columns written out
+    const size_t fplane = (size_t)(ctx->nloc + 1) * ctx->ld;
+    u64* full = nullptr;
+    CK(dev_alloc(&full, sizeof(u64) * ctx->L * fplane, ctx->stream));
+    CK(cudaMemsetAsync(full, 0, sizeof(u64) * ctx->L * fplane, ctx->stream));
+    CK(cudaMemcpy2DAsync(full, sizeof(u64) * fplane, ctx->carry, sizeof(u64) * ctx->plane, sizeof(u64) * ctx->ld,
+                         (size_t)ctx->L, cudaMemcpyDeviceToDevice, ctx->stream));
+    dim3 ugrid(cdiv(ctx->nk_host + 1, 128), 64);
+    LAUNCH(k_unpack, ugrid, 128, full, fplane, ctx->ld, ctx->pk, ctx->pplane, ctx->cap, ctx->L, ctx->klist, ctx->sc);
     dim3 grid(cdiv(ctx->m + 1, 128), 64);
-    LAUNCH(k_materialise_all, grid, 128, ctx->carry, ctx->plane, ctx->ld, ctx->L, ctx->m, ctx->triv, ctx->sc);
+    LAUNCH(k_materialise_all, grid, 128, full, fplane, ctx->ld, ctx->L, ctx->m, ctx->triv, ctx->sc);
     LAUNCH(k_clear_trivial, cdiv(ctx->ld, 256), 256, ctx->triv, ctx->ld);
+    free_dev_on(ctx->carry, ctx->stream); free_dev_on(ctx->pk, ctx->stream);
+    ctx->carry = full; ctx->plane = fplane; ctx->pk = nullptr; ctx->cap = 0; ctx->pplane = 0;
     ctx->list_mode = false;
+    drop_graphs(ctx);   // buffers moved
     return RG_OK;
 }
 
@@ -836,8 +915,8 @@ static int enqueue_iteration(rg_context* ctx, int q, int fixed_row, bool want_se
     if (fixed_row < 0) RG_TRY(launch_ratio(ctx));
     else RG_TRY(launch_fixed_row(ctx, fixed_row));
     if (ctx->list_mode) {   // the pivot row's own column stops being trivial: materialise and list it
-        LAUNCH(k_materialise_pivot_column, cdiv(std::max(ctx->nloc, 1), 256), 256, ctx->carry, ctx->plane,
-               ctx->ld, ctx->L, ctx->triv, ctx->sc);
+        LAUNCH(k_materialise_pivot_column, cdiv(std::max(ctx->nloc, 1), 256), 256, ctx->pk, ctx->pplane,
+               ctx->cap, ctx->L, ctx->triv, ctx->sc);
         LAUNCH(k_activate_pivot_column, 1, 1, ctx->triv, ctx->klist, ctx->kpos, ctx->sc);
     }
     RG_TRY(launch_copyrow(ctx));
@@ -888,11 +967,23 @@ static int do_pivot(rg_context* ctx, int q, int fixed_row, bool want_se, bool re
             int E_need = (ctx->t_cur + 63) / 64;
             if (ctx->nk_host + 1 > (ctx->m + 1) / 3 || pick_update_variant(ctx->L, E_need) < 0)
                 RG_TRY(switch_to_dense(ctx));
+            else
+                RG_TRY(grow_packed(ctx, ctx->nk_host + 2));   // this pivot may list one more column
         }
         ctx->hm->pivoted = 0;
         ctx->nk_grid = (ctx->nk_host + 2 + 127) / 128 * 128;
         int E = pick_update_variant(ctx->L, (ctx->t_cur + 63) / 64);
         if (E < 0) E = (ctx->t_cur + 63) / 64;      // generic run-time-width kernel
+        {   // algorithmic work of this K1 launch: every entry of the active block (list mode:
+            // local rows x listed columns incl. the one this pivot lists, plus the dense cost row; dense mode: the
+            // whole local carry) is read and written once (16 L bytes) and costs two low products of
+            // N = 2 (L + E) 32-bit limbs, N (N + 1) / 2 IMAD.WIDE each
+            const double cols = ctx->list_mode ? (double)(ctx->nk_host + 1) : (double)(ctx->m + 1);
+            const double entries = (double)ctx->nloc * cols + (double)(ctx->m + 1);
+            const double N = 2.0 * (ctx->L + E);
+            ctx->k1_cur_bytes = 16.0 * ctx->L * entries;
+            ctx->k1_cur_imads = entries * N * (N + 1.0);
+        }
         // graphs pay when an iteration is launch-latency bound; with a large dense block the kernels run for
         // milliseconds and eager launches on three streams overlap better (measured on config 5)
         const bool small = (double)ctx->m * ((double)ctx->nd + ctx->m) < 1.5e8;
@@ -966,6 +1057,8 @@ static int do_pivot(rg_context* ctx, int q, int fixed_row, bool want_se, bool re
                 if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) {
                     ctx->k1_ms[log2i(ctx->L)] += ms;
                     ctx->k1_launches[log2i(ctx->L)]++;
+                    ctx->k1_bytes[log2i(ctx->L)] += ctx->k1_cur_bytes;
+                    ctx->k1_imads[log2i(ctx->L)] += ctx->k1_cur_imads;
                     ctx->phase_ms[3] += ms;
                 }
                 (void)cudaGetLastError();
@@ -998,8 +1091,19 @@ extern "C" int rg_init_identity_basis(rg_context* ctx, const int32_t* basis, con
     if (!ctx || !ctx->carry || !basis) return RG_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     const int m = ctx->m, n = ctx->n;
-    for (int i = 0; i < m; ++i)
-        if (basis[i] >= n) { ctx->err = "rg_init_identity_basis: column id out of range"; return RG_ERR_ARG; }
+    for (int i = 0; i < m; ++i) {
+        const int j = basis[i];
+        if (j >= n || j < -m) { ctx->err = "rg_init_identity_basis: column id out of range"; return RG_ERR_ARG; }
+        if (j < 0) continue;
+        // a real basic column must be the unit column +e_i (so that B = I, D = 1): anything else needs rg_init_basis
+        const bool unit = j >= ctx->nd && ctx->h_colptr[j + 1] - ctx->h_colptr[j] == 1 &&
+                          ctx->h_rowidx[ctx->h_colptr[j]] == i && ctx->h_vals[ctx->h_colptr[j]] == 1;
+        if (!unit) {
+            ctx->err = "rg_init_identity_basis: basic column " + std::to_string(j) + " is not the unit column of row " +
+                       std::to_string(i) + " (use rg_init_basis for a general basis)";
+            return RG_ERR_ARG;
+        }
+    }
     CK(cudaMemcpyAsync(ctx->basis, basis, sizeof(int) * m, cudaMemcpyHostToDevice, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream));
     if (cost) {
         CK(cudaMemcpyAsync(ctx->cost, cost, sizeof(long long) * n, cudaMemcpyHostToDevice, ctx->stream));
@@ -1008,10 +1112,14 @@ extern "C" int rg_init_identity_basis(rg_context* ctx, const int32_t* basis, con
         CK(cudaMemsetAsync(ctx->cost, 0, sizeof(long long) * n, ctx->stream));
     }
     CK(cudaMemsetAsync(ctx->inbasis, 0, n, ctx->stream));
+    // identity carry: every column of B^-1 is trivial (active-column mode, DESIGN.md section 4.7)
+    RG_TRY(alloc_carry(ctx, !ctx->dense_carry_opt));
     for (;;) {
         LAUNCH(k_zero, 148 * 8, 256, ctx->carry, (size_t)ctx->L * ctx->plane);
-        LAUNCH(k_init_identity, cdiv(std::max(ctx->nloc, 1), 256), 256, ctx->carry, ctx->plane, ctx->ld,
-               ctx->nloc, ctx->row_lo, ctx->L, ctx->rhs);
+        if (ctx->list_mode) LAUNCH(k_zero, 148 * 8, 256, ctx->pk, (size_t)ctx->L * ctx->pplane);
+        const BlockView bv = block_of(ctx);
+        LAUNCH(k_init_identity, cdiv(std::max(ctx->nloc, 1), 256), 256, bv.base, bv.ps, bv.stride,
+               ctx->nloc, ctx->row_lo, ctx->L, ctx->rhs, ctx->list_mode ? 0 : 1);
         LAUNCH(k_init_row0, cdiv(m, 256), 256, ctx->carry, ctx->plane, m, ctx->L, ctx->basis,
                ctx->weighted ? ctx->artcost : nullptr);
         LAUNCH(k_init_scalars, 1, 1, ctx->carry, ctx->plane, m, ctx->L, ctx->rhs, ctx->basis,
@@ -1022,8 +1130,6 @@ extern "C" int rg_init_identity_basis(rg_context* ctx, const int32_t* basis, con
     }
     if (ctx->weighted)
         LAUNCH(k_init_rowf, cdiv(m, 256), 256, ctx->basis, ctx->wf, ctx->artf, ctx->rowf, m);
-    // identity carry: every column of B^-1 is trivial (active-column mode, DESIGN.md section 4.7)
-    ctx->list_mode = !ctx->dense_carry_opt;
     ctx->nk_host = 1;
     LAUNCH(k_init_active, cdiv(ctx->ld, 256), 256, ctx->triv, ctx->klist, ctx->kpos, ctx->ld, m,
            ctx->list_mode ? 1 : 0);
@@ -1046,7 +1152,8 @@ static int launch_phase_sums_t(rg_context* ctx) {
     constexpr int LU = L + 2;
     const ColsumGeom g = colsum_geom(ctx);
     dim3 grid(cdiv(g.ncols, 128), g.chunks);
-    LAUNCH((k_colsum1<L, 1, LU>), grid, 128, ctx->carry, ctx->plane, ctx->ld, ctx->nloc, g.rpc, g.klist,
+    const BlockView bv = block_of(ctx);
+    LAUNCH((k_colsum1<L, 1, LU>), grid, 128, bv.base, bv.ps, bv.stride, ctx->nloc, g.rpc, g.klist,
            ctx->svec, (size_t)ctx->ld, ctx->omega_part, g.pcols, ctx->sc);
     if (ctx->world == 1) {
         LAUNCH((k_colsum2<LU, 1>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, g.chunks, 1,
@@ -1101,17 +1208,18 @@ extern "C" int rg_phase_switch(rg_context* ctx, const int64_t* cost) {
 template <int L>
 static int launch_gamma_general_t(rg_context* ctx) {
     constexpr int LG = 2 * L + 6;
+    const BlockView bv = block_of(ctx);
     if (ctx->world == 1) {
-        LAUNCH((k_gamma_init_general<L>), ctx->n, 128, ctx->carry, ctx->plane, ctx->ld, ctx->nloc, ctx->n,
+        LAUNCH((k_gamma_init_general<L>), ctx->n, 128, bv.base, bv.ps, bv.stride, ctx->nloc, ctx->n,
                ctx->A.colptr, ctx->A.rowidx, ctx->A.vals, ctx->inbasis, ctx->G, 1, ctx->weighted ? ctx->wf : nullptr,
-               ctx->weighted ? ctx->rowf : nullptr, triv_of(ctx), ctx->sc);
+               ctx->weighted ? ctx->rowf : nullptr, triv_of(ctx), kpos_of(ctx), ctx->sc);
         return RG_OK;
     }
     size_t words = (size_t)LG * ctx->n;
     RG_TRY(ensure_xbuf(ctx, words, words * ctx->world));
-    LAUNCH((k_gamma_init_general<L>), ctx->n, 128, ctx->carry, ctx->plane, ctx->ld, ctx->nloc, ctx->n,
+    LAUNCH((k_gamma_init_general<L>), ctx->n, 128, bv.base, bv.ps, bv.stride, ctx->nloc, ctx->n,
            ctx->A.colptr, ctx->A.rowidx, ctx->A.vals, ctx->inbasis, ctx->xsend, ctx->rank == 0 ? 1 : 0,
-           ctx->weighted ? ctx->wf : nullptr, ctx->weighted ? ctx->rowf : nullptr, triv_of(ctx), ctx->sc);
+           ctx->weighted ? ctx->wf : nullptr, ctx->weighted ? ctx->rowf : nullptr, triv_of(ctx), kpos_of(ctx), ctx->sc);
     RG_TRY(all_gather(ctx, ctx->xsend, ctx->xrecv, words));
     LAUNCH((k_colsum2<LG>), cdiv(ctx->n, 64), 64, ctx->xrecv, ctx->n, ctx->world, 0, ctx->G, ctx->sc);
     return RG_OK;
@@ -1343,7 +1451,8 @@ static int export_rows(rg_context* ctx, const u64* base, size_t stride, size_t i
 extern "C" int rg_get_b(rg_context* ctx, uint64_t* out) {
     if (!ctx || !ctx->carry || !out) return RG_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
-    return export_rows(ctx, ctx->carry, ctx->plane, (size_t)ctx->ld, (size_t)ctx->ld, ctx->L, out);
+    const BlockView bv = block_of(ctx);
+    return export_rows(ctx, bv.base, bv.ps, (size_t)bv.stride, (size_t)bv.stride, ctx->L, out);
 }
 extern "C" int rg_get_minus_objective(rg_context* ctx, uint64_t* out) {
     if (!ctx || !ctx->carry || !out) return RG_ERR_ARG;
@@ -1449,6 +1558,8 @@ extern "C" int rg_get_stats(rg_context* ctx, rg_stats* out) {
         out->pivots_at_limbs[k] = ctx->pivots_at[k];
         out->k1_launches_at_limbs[k] = ctx->k1_launches[k];
         out->k1_ms_at_limbs[k] = ctx->k1_ms[k];
+        out->k1_bytes_at_limbs[k] = ctx->k1_bytes[k];
+        out->k1_imads_at_limbs[k] = ctx->k1_imads[k];
     }
     out->timer_ms = ctx->timer_ms;
     for (int k = 0; k < 8; ++k) out->phase_ms[k] = ctx->phase_ms[k];
@@ -1529,6 +1640,56 @@ __global__ void k_selftest(int op, const u64* a, const u64* b, const u64* c, con
         for (int l = 0; l < W; ++l) r[l] = (u64)oo[2 * l] | ((u64)oo[2 * l + 1] << 32);
     }
     for (int l = 0; l < 2 * W; ++l) out[l] = r[l];
+}
+
+
+// Integer-pipe peak micro-benchmark: the IMAD.WIDE carry-chain instruction mix of the K1
+// products (mp_mul_lo<32>: 528 IMAD.WIDE.U32[.X] per product) on register operands, no memory traffic, every SM
+// filled; timed with CUDA events after a warm-up that lets the clocks settle.  Returns IMAD.WIDE per second.
+__global__ void __launch_bounds__(256) k_imad_peak(u32* out, int iters) {
+    constexpr int N = 32;
+    u32 x[N], y[N], r[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) { x[k] = threadIdx.x * 2654435761u + k * 40503u + blockIdx.x; y[k] = x[k] ^ (0x9e3779b9u * (k + 1)); }
+    for (int it = 0; it < iters; ++it) {
+        mp_mul_lo<N>(r, x, y);
+#pragma unroll
+        for (int k = 0; k < N; ++k) x[k] = r[k];
+        mp_mul_lo<N>(r, y, x);
+#pragma unroll
+        for (int k = 0; k < N; ++k) y[k] = r[k];
+    }
+    u32 acc = 0;
+#pragma unroll
+    for (int k = 0; k < N; ++k) acc ^= x[k] ^ y[k];
+    if (acc == 0x12345678u) out[0] = acc;     // keeps the chains alive
+}
+extern "C" int rg_measure_imad_peak(int32_t device, double seconds, double* imad_per_s) {
+    if (!imad_per_s) return RG_ERR_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return RG_ERR_CUDA;
+    u32* out = nullptr;
+    if (cudaMalloc(&out, 64) != cudaSuccess) return RG_ERR_CUDA;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const int blocks = sms * 4, iters = 256;
+    const double per_launch = (double)blocks * 256 * iters * 2 * (32.0 * 33.0 / 2.0);
+    double best = 0;
+    const int reps = seconds > 0 ? (int)(seconds / 0.02) + 4 : 12;
+    for (int r = 0; r < reps; ++r) {
+        cudaEventRecord(e0);
+        k_imad_peak<<<blocks, 256>>>(out, iters);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(out); return RG_ERR_CUDA; }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (r >= 2 && ms > 0) best = std::max(best, per_launch / (ms * 1e-3));
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(out);
+    *imad_per_s = best;
+    return RG_OK;
 }
 
 extern "C" int rg_selftest(int32_t op, int32_t W, const uint64_t* a, const uint64_t* b, const uint64_t* c,

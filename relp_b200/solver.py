@@ -218,6 +218,8 @@ def solve_relaxation(problem, rule="steepest_edge", fused=True, initial_limbs=0,
                          pivots_at_limbs=[st.pivots_at_limbs[k] for k in range(5)],
                          k1_launches_at_limbs=[st.k1_launches_at_limbs[k] for k in range(5)],
                          k1_ms_at_limbs=[st.k1_ms_at_limbs[k] for k in range(5)],
+                         k1_bytes_at_limbs=[st.k1_bytes_at_limbs[k] for k in range(5)],
+                         k1_imads_at_limbs=[st.k1_imads_at_limbs[k] for k in range(5)],
                          phase_ms=[st.phase_ms[k] for k in range(8)],
                          active_columns=st.reserved)
         res.device_ms = lib.rh_result_device_ms(handle)
