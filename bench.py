@@ -169,70 +169,60 @@ def measured_peak_hbm():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def cpu_baseline(problem, rule, budget_s=15.0):
-    """The oracle port timed on this box's host cores (1 thread: relp is single-threaded) on a
-    bounded sample: the first P pivots of the same workload and trace."""
-    try:
-        from oracle import fast_oracle
-        if fast_oracle.available():
-            return fast_oracle.timed_sample(problem, rule, budget_s)
-    except ImportError:
-        pass
-    from oracle import relp_oracle as ro
-    from tests.common import provider_from_problem
-    provider = provider_from_problem(problem)
-    t0 = time.perf_counter()
-    probe = 3
-    trace = ro.Trace(limit=probe)
-    try:
-        ro.solve_relaxation(provider, rule, trace)
-    except ro.PivotLimit:
-        pass
-    t_probe = time.perf_counter() - t0
-    done = len(trace.pivots)
-    per = max(t_probe / max(done, 1), 1e-6)
-    P = int(max(probe, min(10000, budget_s / per)))
-    t0 = time.perf_counter()
-    trace = ro.Trace(limit=P)
-    try:
-        ro.solve_relaxation(provider, rule, trace)
-    except ro.PivotLimit:
-        pass
-    dt = time.perf_counter() - t0
-    n = len(trace.pivots)
-    return {"value": n / dt, "unit": "pivots/s", "cores": 1, "kind": "port",
-            "sample": f"first {n} pivots of the same LP and trace (incl. rule initialisation), "
-                      f"Python fractions.Fraction oracle, {dt:.1f} s"}
+def cpu_baseline(problem, rule, budget_s=15.0, threads=0):
+    """The oracle port (C++ restatement of relp's Carry<RationalBig, BasisInverseRows> path; the Rust reference
+    cannot be built in this image) timed on this box's host cores on a bounded sample: the first P pivots of
+    the same workload and trace, rule initialisation included.  threads = 0: all hardware threads (the column
+    loops of pricing / steepest edge are independent; relp itself is single-threaded)."""
+    from oracle import fast_oracle
+    if not fast_oracle.available():
+        raise RuntimeError("oracle/_build/libfast_oracle.so is missing: run __graft_entry__.build()")
+    used = fast_oracle.set_threads(threads)
+    out = fast_oracle.timed_sample(problem, rule, budget_s)
+    out["cores"] = used
+    out["host_cores"] = os.cpu_count()
+    return out
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU path (oracle port; the Rust reference cannot be built in
-    this image) on the box's host cores, same config/metric."""
+    """--impl reference: the reference's CPU path (oracle port) on the box's host cores with all the host
+    threads it can use, same config / metric.  One step = the first P pivots of the workload's LP (rule
+    initialisation included), P fixed during the warm-up so that a step takes a few seconds."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from oracle import fast_oracle
     prob = make_problem(args.workload, 0)
-    total_p, total_t, last = 0.0, 0.0, None
+    threads = fast_oracle.set_threads(0)
+    per_step_s = max(2.0, min(8.0, 150.0 / max(args.steps + args.warmup, 1)))
+    # size the prefix: the pivots the port completes within the per-step budget (early pivots are the cheapest
+    # ones, so a prefix OVERSTATES the reference's pivots/s over the whole LP); the timed steps repeat exactly
+    # this prefix
+    fast_oracle.set_time_limit(per_step_s)
+    try:
+        probe = fast_oracle.solve_problem(prob, args.rule)
+    finally:
+        fast_oracle.set_time_limit(0)
+    P = max(1, len(probe.trace))
+    total_p, total_t, whole = 0, 0.0, False
     for step in range(args.warmup + args.steps):
-        # bounded sample per step: the whole run stays within a few minutes for any --steps
-        # (the sample is a PREFIX of the trace and early pivots are cheap -- small numbers -- so a short sample
-        # overstates the reference: 69 pivots/s over the first 80 pivots vs 13 over the whole LP; the budget is
-        # therefore kept as large as a few-minute run allows: ~17 s per step up to K = 14, less beyond)
-        budget = min(10.0, 140.0 / max(args.steps, 1)) if step >= args.warmup else 1.0
-        t0 = time.perf_counter()
-        last = cpu_baseline(prob, args.rule, budget_s=budget)
-        dt = time.perf_counter() - t0
+        r = fast_oracle.solve_problem(prob, args.rule, max_pivots=P)
         if step >= args.warmup:
-            total_t += dt
-            total_p += last["value"]
-    value = total_p / max(args.steps, 1)
+            total_p += len(r.trace)
+            total_t += r.seconds
+        whole = r.status != "pivot_limit"
+    value = total_p / max(total_t, 1e-9)
+    sample = (f"{'all' if whole else 'first'} {P if not whole else len(r.trace)} pivots of the same LP and trace per step "
+              f"(incl. rule initialisation), C++ big-rational restatement of Carry<RationalBig, BasisInverseRows> "
+              f"(oracle/fast_oracle.cpp), {threads} OpenMP threads over the independent column loops")
     line = {
         "impl": "reference", "metric": "exact simplex pivots/sec", "value": value, "unit": "pivots/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1000.0 * total_t / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "exact rational (arbitrary precision)", "data": "synthetic",
         "config": workload_config(args, 1),
-        "cpu_baseline": dict(last, value=value),
+        "cpu_baseline": {"value": value, "unit": "pivots/s", "cores": threads, "host_cores": os.cpu_count(),
+                         "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "pivots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -246,9 +236,14 @@ def workload_config(args, world):
                         f"{'dense' if w['dense'] else '8 nnz/col sparse'} never-binding rows, seed=0",
             "pivot_rule": args.rule, "step": "one exact solve to optimality (time-to-optimal)",
             "parallelism": "single GPU" if world == 1 else
-            f"carry row-sharded over {world} GPUs (one process per GPU, NCCL: all-gather of ratio-test candidates "
-            f"and work-vector partials, all-reduce of the pivot row); pricing and rule update replicated",
-            "l2": "carry (>= 268 MB at 2 limbs) exceeds the 126 MB L2; no flush needed"}
+            f"the same LP with its carry row-sharded and its pricing column-sharded over {world} GPUs (one process "
+            f"per GPU, NCCL: all-gather of pricing / ratio-test candidates and work-vector partials, pivot row "
+            f"replicated by the owner)",
+            "l2": ("inputs larger than L2: the int8 constraint block (537 MB) is streamed by every pricing / steepest-"
+                   "edge dot and the active carry block exceeds 126 MB from 8 limbs on; no flush needed"
+                   if w["dense"] else
+                   "every solve re-creates the context and re-uploads the problem, so no step starts with a warm L2; "
+                   "the active carry block is smaller than L2 (stated, not flushed)")}
 
 
 def main():
@@ -256,7 +251,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="sparse4k", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="dense16k", choices=sorted(WORKLOADS))
     ap.add_argument("--rule", default="steepest_edge")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -280,12 +275,18 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     prob = make_problem(args.workload, 0)     # N > 1: the SAME LP, its carry row-sharded over the ranks
-    # pinned host buffers for the end-to-end leg
-    for name in ("colptr", "rowidx", "vals", "cost", "rhs"):
+    # pinned host buffers for the end-to-end leg (every step uploads the whole problem from them)
+    names = ["colptr", "rowidx", "vals", "cost", "rhs"]
+    for name in names:
         t = torch.from_numpy(getattr(prob, name)).pin_memory()
         setattr(prob, name, t.numpy())
         setattr(prob, "_pin_" + name, t)
-    h2d = sum(getattr(prob, n).nbytes for n in ("colptr", "rowidx", "vals", "cost", "rhs"))
+    h2d = sum(getattr(prob, n).nbytes for n in names)
+    if prob.dense_block is not None:
+        t = torch.from_numpy(prob.dense_block).pin_memory()
+        prob.dense_block = t.numpy()
+        prob._pin_dense = t
+        h2d += prob.dense_block.nbytes
 
     def barrier():
         if world > 1:
@@ -318,9 +319,7 @@ def main():
     dev_ms = 0.0
     e2e_s = 0.0
     launches = 0
-    k1_ms = [0.0] * 5
-    k1_n = [0] * 5
-    phase = [0.0] * 8
+    k1 = {key: [0.0] * 5 for key in ("ms", "n", "bytes", "imads")}
     for _ in range(args.steps):
         g = step()
         assert g.status == "optimal"
@@ -329,10 +328,10 @@ def main():
         e2e_s += g.seconds_total
         launches += g.stats["kernel_launches"]
         for k in range(5):
-            k1_ms[k] += g.stats["k1_ms_at_limbs"][k]
-            k1_n[k] += g.stats["k1_launches_at_limbs"][k]
-        for k in range(8):
-            phase[k] += g.stats["phase_ms"][k]
+            k1["ms"][k] += g.stats["k1_ms_at_limbs"][k]
+            k1["n"][k] += g.stats["k1_launches_at_limbs"][k]
+            k1["bytes"][k] += g.stats["k1_bytes_at_limbs"][k]
+            k1["imads"][k] += g.stats["k1_imads_at_limbs"][k]
     barrier()
     wall = time.perf_counter() - t0
     sampler.window(t0, t0 + wall)
@@ -350,67 +349,75 @@ def main():
     else:
         dev_ms_max, e2e_max, pivots_all, launches_all = dev_ms, e2e_s, float(pivots), float(launches)
 
-    # one extra (untimed) solve with the active-column mode switched off: the dense rank-1 kernel is the one
-    # whose algorithmic bytes are 16 L (m+1)^2; its CUDA-event times give the dense roofline
-    # one extra (untimed) solve with events around every phase of the iteration: the phase table
+    # one extra (untimed) solve with CUDA events around every phase of the iteration: the phase table
     prof_level = 2
     gp = step()
     assert gp.trace == g.trace
     phase = list(gp.stats["phase_ms"])
-    gd = None
-    if world == 1:
-        gd = relp_b200.solve_relaxation(prob, rule=args.rule, device=local, profile=True, dense_carry=True)
-        assert gd.trace == g.trace and gd.objective == g.objective   # both carry modes walk the same pivots
 
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
-        w = WORKLOADS[args.workload]
-        rows_local = -(-w["m"] // world) + 1
-        entries = (w["m"] + 1) * rows_local     # carry entries one dense K1 launch of one rank covers
+        # integer-pipe peak of the K1 instruction mix (IMAD.WIDE carry chains), measured live on this GPU
+        import ctypes as C
+        v = C.c_double()
+        lib = _lib.load()
+        imad_peak = None
+        if lib.rg_measure_imad_peak(local, 1.0, C.byref(v)) == 0 and v.value > 0:
+            imad_peak = v.value
 
-        def k1_table(ms, cnt, ent):
-            out = {}
-            for k in range(5):
-                if cnt[k]:
-                    L = 1 << k
-                    avg = ms[k] / cnt[k]
-                    gbs = 16.0 * L * ent / (avg * 1e-3) / 1e9
-                    out[str(L)] = {"launches": cnt[k], "avg_ms": avg, "GB/s": gbs, "frac": gbs / peak}
-            return out
-
-        dense_tab = k1_table(gd.stats["k1_ms_at_limbs"], gd.stats["k1_launches_at_limbs"], entries) if gd else {}
-        dom = max(range(5), key=lambda k: k1_ms[k])
+        # K1 (the rank-1 Bareiss pivot) exactly as the TIMED steps ran it: per limb width, the algorithmic bytes
+        # and multiply-adds of every launch (tracked per pivot from the list length and the exact-division
+        # width in use) over its CUDA-event time.  Roofline time = max(bytes / HBM peak, IMAD / IMAD peak).
+        by_limbs = {}
+        for k in range(5):
+            if k1["n"][k]:
+                t = k1["ms"][k] * 1e-3
+                gbs = k1["bytes"][k] / t / 1e9
+                gim = k1["imads"][k] / t / 1e9
+                ent = {"launches": int(k1["n"][k]), "avg_ms": k1["ms"][k] / k1["n"][k],
+                       "alg_bytes_per_launch": k1["bytes"][k] / k1["n"][k],
+                       "alg_imads_per_launch": k1["imads"][k] / k1["n"][k],
+                       "GB/s": gbs, "hbm_frac": gbs / peak, "GIMAD/s": gim}
+                if imad_peak:
+                    ent["imad_frac"] = gim * 1e9 / imad_peak
+                    ent["roofline_frac"] = max(ent["hbm_frac"], ent["imad_frac"])
+                else:
+                    ent["roofline_frac"] = ent["hbm_frac"]
+                by_limbs[str(1 << k)] = ent
+        dom = max(range(5), key=lambda k: k1["ms"][k])
         Ldom = 1 << dom
-        # active-column mode touches (rows) x (non-trivial columns) entries; report its achieved bandwidth on
-        # that footprint with the final list length as the (upper-bound) column count
-        nk = g.stats.get("active_columns", 0) or 1
-        list_entries = rows_local * nk
-        list_tab = k1_table(k1_ms, k1_n, list_entries)
-        if dense_tab and str(Ldom) in dense_tab:
-            ach = dense_tab[str(Ldom)]["GB/s"]
-            kern = f"k_update<L={Ldom}> dense mode (rank-1 Bareiss pivot of the whole carry)"
-            alg = 16 * Ldom * entries
-        else:
-            ach = list_tab[str(Ldom)]["GB/s"]
-            kern = f"k_update<L={Ldom}> active-column mode"
-            alg = 16 * Ldom * list_entries
-        # DRAM traffic of one launch from the committed `ncu --set full` capture of exactly this kernel and
-        # workload (profiles/r1_ncu_summaries.md, prof_k1_dense_v3: dram read 1.080858 GB + write 10.13 MB)
+        d = by_limbs[str(Ldom)]
+        imad_bound = imad_peak is not None and d.get("imad_frac", 0) >= d["hbm_frac"]
         traffic = None
-        if args.workload == "sparse4k" and world == 1 and Ldom == 8 and kern.endswith("whole carry)"):
-            traffic = 1080858000 + 10126848
-        roof = {"bound": "hbm", "kernel": kern, "achieved": ach, "peak": peak, "unit": "GB/s",
-                "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
-                "traffic_note": "ncu dram__bytes_read+write per launch (one capture, profiles/); below the "
-                                "algorithmic bytes because unchanged zero entries are not written back: "
-                                "traffic / time is the honest HBM utilisation",
-                "traffic_frac": (traffic / (dense_tab[str(Ldom)]["avg_ms"] * 1e-3) / 1e9 / peak) if traffic else None,
-                "algorithmic_bytes_per_launch": alg,
-                "dense_mode_by_limbs": dense_tab,
-                "dense_mode_note": "one untimed solve with dense_carry=1; zero entries are read but neither "
-                                   "multiplied nor written back, so achieved can exceed the copy peak",
-                "active_column_mode_by_limbs": list_tab, "active_columns_final": nk,
-                "share_of_step": sum(k1_ms) / dev_ms if dev_ms else None}
+        traffic_src = None
+        tp = os.path.join(ROOT, "profiles", "r2_k1_traffic.json")
+        if os.path.exists(tp):
+            with open(tp) as f:
+                tj = json.load(f)
+            ent = tj.get(f"{args.workload}:L{Ldom}:world{world}")
+            if ent:
+                traffic = ent["dram_bytes_read"] + ent["dram_bytes_write"]
+                traffic_src = ent
+        mode = "active-column mode (packed block)" if g.stats.get("active_columns", 0) else "dense carry"
+        roof = {"bound": "imad" if imad_bound else "hbm",
+                "kernel": f"k_update<L={Ldom}> {mode}: rank-1 Bareiss pivot of the carry, as run by the timed steps",
+                "achieved": d["GIMAD/s"] if imad_bound else d["GB/s"],
+                "peak": imad_peak / 1e9 if imad_bound else peak,
+                "unit": "GIMAD.WIDE/s" if imad_bound else "GB/s",
+                "frac": d["roofline_frac"],
+                "hbm": {"achieved": d["GB/s"], "peak": peak, "unit": "GB/s", "frac": d["hbm_frac"],
+                        "peak_source": peak_src},
+                "imad": {"achieved": d["GIMAD/s"], "peak": imad_peak / 1e9 if imad_peak else None,
+                         "unit": "GIMAD.WIDE/s", "frac": d.get("imad_frac"),
+                         "peak_source": "rg_measure_imad_peak: IMAD.WIDE carry-chain mix on registers, all SMs, "
+                                        "measured in this run"},
+                "bound_note": "roofline = the slower of limb bytes at HBM bandwidth and limb multiply-adds at "
+                              "integer-pipe peak (north star); 'imad' = integer multiply pipe",
+                "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": d["alg_bytes_per_launch"],
+                "algorithmic_imads_per_launch": d["alg_imads_per_launch"],
+                "by_limbs": by_limbs, "active_columns_final": g.stats.get("active_columns", 0),
+                "share_of_step": sum(k1["ms"]) / dev_ms if dev_ms else None}
         line = {
             "metric": "exact simplex pivots/sec", "value": pivots_all / (dev_ms_max * 1e-3), "unit": "pivots/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -549,6 +549,7 @@ struct Tableau {   // tableau/mod.rs:25-39
 // pivot rules (strategy/pivot_rule.rs)
 // ------------------------------------------------------------------------------------------------
 static int g_threads = 1;           // OpenMP team size of the column-parallel loops (fo_set_threads)
+static double g_time_limit = 0;     // seconds; > 0: a solve stops (as at a pivot limit) once it has run this long
 
 struct Rule {
     int kind;                       // 0 FirstProfitable, 1 ..WithMemory, 2 Dantzig, 3 steepest edge
@@ -664,7 +665,15 @@ struct Solver {
     bool limit_hit = false;
     Solver(const Provider& p, int rk, long long mp) : prov(p), rule_kind(rk), max_pivots(mp) {}
 
-    bool budget() { if (max_pivots > 0 && (long long)trace.size() >= max_pivots) { limit_hit = true; return false; } return true; }
+    std::chrono::steady_clock::time_point t_start = std::chrono::steady_clock::now();
+    bool budget() {
+        if (max_pivots > 0 && (long long)trace.size() >= max_pivots) { limit_hit = true; return false; }
+        if (g_time_limit > 0 &&
+            std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count() > g_time_limit) {
+            limit_hit = true; return false;
+        }
+        return true;
+    }
 
     // returns 0 optimal (no entering), 1 unbounded, 2 limit
     int loop(Tableau& t, int phase) {
@@ -825,6 +834,7 @@ struct fo_result {
 
 extern "C" {
 
+void fo_set_time_limit(double seconds) { g_time_limit = seconds; }   // 0: none
 int fo_set_threads(int n) {      // n <= 0: all hardware threads
 #ifdef _OPENMP
     g_threads = n > 0 ? n : omp_get_num_procs();

@@ -26,6 +26,7 @@ struct Scalars {
     int maxbits_u;       // of the current pivot column (incl. the cost row entry)
     int maxbits_rowp;    // of the staged pivot row
     int maxbits_tmp;     // scratch (phase switch)
+    int maxbits_s;       // of the weighted factor vector s_i = u_i (W / w_B(i))^2 (weighted problems)
     int bits_D;
     int predicted;       // predicted bit length of the update's results
     int last_selected;   // FirstProfitableWithMemory state (-1 = none)
@@ -139,6 +140,7 @@ struct rg_context {
     u64* kappa = nullptr;       // LU planes x n  relative cost numerators
     u64* nu = nullptr;          // LU planes x n  pivot-row . column
     u64* sigma = nullptr;       // LS planes x n  work-vector . column
+    u64* tau = nullptr;         // LU+3 planes x n  factor vector (trivial part) . column: split sigma dot
     u64* G = nullptr;           // LG planes x n  Ghat
     int* cand = nullptr;        // block winners scratch
     double* score = nullptr;    // max(n, m) filter scores

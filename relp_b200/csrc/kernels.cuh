@@ -212,12 +212,15 @@ __device__ __forceinline__ int eff_bytes(const int* bits, int LV) {
 template <int LV>
 __global__ void __launch_bounds__(64)
 k_dense_slices(const u64* __restrict__ vec, size_t vs, int m, const int* bits, unsigned char* __restrict__ Sl,
-               size_t mp, int* __restrict__ chunknz, const Scalars* sc) {
+               size_t mp, int* __restrict__ chunknz, const Scalars* sc,
+               const unsigned char* __restrict__ triv = nullptr, int keep_trivial = 0) {
+    // triv != nullptr: only the entries whose carry column (i + 1) is trivial (keep_trivial = 1) or listed
+    // (keep_trivial = 0) are kept, the others count as zero (split sigma dot, launch_sigma_split)
     if (sc->status != ST_RUN) return;
     const int nb = eff_bytes(bits, LV);
     const int nrows = ((nb + 1 + 7) >> 3) << 3;    // byte rows + sign row, padded to an n-tile of 8
     const int i = blockIdx.x * 64 + threadIdx.x;
-    const bool in = i < m;
+    const bool in = i < m && (!triv || (int)(triv[i + 1] != 0) == keep_trivial);
     const bool neg = in && (i64)vec[(size_t)(LV - 1) * vs + 1 + i] < 0;
     u64 any = 0;
     const int nl = (nb + 7) >> 3;
@@ -343,6 +346,58 @@ k_dense_combine(const int* __restrict__ R, size_t rstride_k, int kslices, int rp
     store_planar<LO>(out, (size_t)n, (size_t)j, res);
 }
 
+
+template <int LA, int LB>
+__device__ __forceinline__ void mul_full_ct(u64 (&r)[LA + LB], const u64 (&a)[LA], const u64 (&b)[LB]);
+
+// split sigma dot (list mode): the work vector restricted to the trivial carry columns is D * s (s = the factor
+// vector, u or its weighted form), so   sigma_j = omega_listed . a_j  +  D * (s_trivial . a_j).
+// This kernel adds the second term: sigma[j] += D * tau[j] for the dense columns j in [jd0, jd1).
+template <int LT, int L, int LS>
+__global__ void __launch_bounds__(128)
+k_sigma_add_dtau(const u64* __restrict__ tau, int n, int jd0, int jd1, const unsigned char* __restrict__ inbasis,
+                 u64* __restrict__ sigma, const Scalars* sc) {
+    static_assert(LT + L <= LS, "D * tau must fit the sigma width");
+    if (sc->status != ST_RUN) return;
+    const int j = jd0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= jd1 || inbasis[j]) return;
+    u64 t[LT], d[L];
+    load_planar<LT>(t, tau, (size_t)n, (size_t)j);
+    u64 any = 0;
+#pragma unroll
+    for (int l = 0; l < LT; ++l) any |= t[l];
+    if (any == 0) return;
+    const bool neg = (i64)t[LT - 1] < 0;
+    if (neg) {
+        u64 c = 1;
+#pragma unroll
+        for (int l = 0; l < LT; ++l) { u64 v = ~t[l] + c; c = (c && v == 0) ? 1 : 0; t[l] = v; }
+    }
+#pragma unroll
+    for (int l = 0; l < L; ++l) d[l] = sc->D[l];
+    u64 p[LT + L];
+    mul_full_ct<LT, L>(p, t, d);          // |tau| * D, D > 0
+    u64 sg[LS];
+    load_planar<LS>(sg, sigma, (size_t)n, (size_t)j);
+    if (!neg) {
+        u64 cf = 0;
+#pragma unroll
+        for (int l = 0; l < LS; ++l) {
+            u64 b = l < LT + L ? p[l] : 0;
+            u64 v = sg[l] + b; u64 c1 = v < b; u64 v2 = v + cf; u64 c2 = v2 < v;
+            sg[l] = v2; cf = c1 + c2;
+        }
+    } else {
+        u64 bf = 0;
+#pragma unroll
+        for (int l = 0; l < LS; ++l) {
+            u64 b = l < LT + L ? p[l] : 0;
+            u64 v = sg[l] - b; u64 b1 = sg[l] < b; u64 v2 = v - bf; u64 b2 = v < bf;
+            sg[l] = v2; bf = b1 + b2;
+        }
+    }
+    store_planar<LS>(sigma, (size_t)n, (size_t)j, sg);
+}
 
 // FTRAN of a dense column q (column-major copy): warp per carry row, lanes over the rows of a_q
 template <int L>
@@ -1100,7 +1155,7 @@ k_ftran_list(const u64* __restrict__ C, size_t ps, int ld, int nrows, int m, con
 }
 
 __global__ void k_reset_iter(Scalars* sc) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) { sc->maxbits_u = 0; sc->maxbits_rowp = 0; sc->maxbits_new = 0; sc->maxbits_tmp = 0; sc->nnz_s = 0; }
+    if (threadIdx.x == 0 && blockIdx.x == 0) { sc->maxbits_u = 0; sc->maxbits_rowp = 0; sc->maxbits_new = 0; sc->maxbits_tmp = 0; sc->nnz_s = 0; sc->maxbits_s = 0; }
 }
 __global__ void k_set_pq(Scalars* sc, int q, int p) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
@@ -1377,79 +1432,135 @@ __device__ __forceinline__ void mul_full_ct(u64 (&r)[LA + LB], const u64 (&a)[LA
     r[LA + LB - 1] = c0;
 }
 
+// Stage 1 in unsigned form (IMAD.WIDE product scanning, 1152 multiply-adds per 16-limb entry instead of the 2485
+// of a two's complement accumulation at the output width):
+//   * the carry entry is biased, x' = C[i][k] + 2^(64L-1) (its top bit flipped): 0 <= x' < 2^(64L);
+//   * the factor is taken as magnitude |s_i| and the rows of a chunk are walked in two passes, s_i > 0 then
+//     s_i < 0, each into its own partial sum  P = sum x'_ik |s_i| - 2^(64L-1) sum |s_i|  (the bias removed with
+//     the chunk's magnitude sum, computed once per block); stage 2 adds the positive and subtracts the negative
+//     partials, so no signed product is ever formed;
+//   * one column of the product at a time: (c2:c1:c0) += x'_i * |s|_j for i + j = k, then limb k is final.
+// Partial slabs: chunk c writes slab 2c (positive rows) and 2c+1 (negative rows).
+template <int NA, int NB, int K, int I>
+struct ColTerms {
+    __device__ static __forceinline__ void run(u32& c0, u32& c1, u32& c2, const u32 (&x)[NA], const u32 (&m)[NB]) {
+        if constexpr (I < NA && K - I >= 0 && K - I < NB)
+            asm volatile("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, %2, 0;"
+                         : "+r"(c0), "+r"(c1), "+r"(c2) : "r"(x[I]), "r"(m[K - I]));
+        if constexpr (I + 1 < NA && I + 1 <= K) ColTerms<NA, NB, K, I + 1>::run(c0, c1, c2, x, m);
+    }
+};
+template <int NA, int NB, int NW, int K>
+struct ColScan {
+    __device__ static __forceinline__ void run(u32 (&acc)[NW], u32& c0, u32& c1, u32& c2, const u32 (&x)[NA],
+                                               const u32 (&m)[NB]) {
+        // the running sum's limb K joins the column accumulator
+        asm volatile("add.cc.u32 %0, %0, %3;\n\taddc.cc.u32 %1, %1, 0;\n\taddc.u32 %2, %2, 0;"
+                     : "+r"(c0), "+r"(c1), "+r"(c2) : "r"(acc[K]));
+        if constexpr (K < NA + NB - 1) ColTerms<NA, NB, K, (K - NB + 1 > 0 ? K - NB + 1 : 0)>::run(c0, c1, c2, x, m);
+        acc[K] = c0; c0 = c1; c1 = c2; c2 = 0;
+        if constexpr (K + 1 < NW) ColScan<NA, NB, NW, K + 1>::run(acc, c0, c1, c2, x, m);
+    }
+};
+
 template <int L, int LSRC, int LOUT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 3)
 k_colsum1(const u64* __restrict__ C, size_t ps, int ld, int m, int rows_per_chunk, const int* __restrict__ klist,
           const u64* __restrict__ s, size_t ss, u64* __restrict__ part, int pcols, const Scalars* sc) {
-    // Two's complement accumulation in 32-bit limbs: acc += C[i][k] * s_i mod 2^(32 NW) with the IMAD.WIDE carry
-    // chains of mp32.cuh (every chain runs to the top limb, so the running sums need no carry fix-up between
-    // rows).  NW covers |C| < 2^(64 L), |s| < 2^(64 LSRC) and up to 2^32 rows.
-    constexpr int RB = 32;                 // rows whose factors are staged in shared memory at a time
-    constexpr int WS = (L + LSRC + 1) < LOUT ? (L + LSRC + 1) : LOUT;   // 64-bit limbs of the running sum
-    constexpr int NW = 2 * WS;
-    __shared__ u32 sU[RB][NW];             // factors, sign-extended to NW limbs
-    __shared__ unsigned char sNz[RB];
+    constexpr int RB = 64;                 // rows whose factors are staged in shared memory at a time
+    constexpr int WS = (L + LSRC + 1) < LOUT ? (L + LSRC + 1) : LOUT;   // 64-bit limbs of a partial sum
+    constexpr int NA = 2 * L, NB = 2 * LSRC, NW = 2 * WS;
+    constexpr int NU = NB + 2;             // limbs of a chunk's magnitude sum (up to 2^32 rows)
+    static_assert(NW >= NA + NB + 1 || WS == LOUT, "partial sums need one limb of headroom");
+    __shared__ u32 sMag[RB][NB];
+    __shared__ signed char sSgn[RB];
+    __shared__ u32 sUsum[2][NU];           // per pass: sum of |s_i| over the chunk's rows of that sign
     if (sc->status != ST_RUN) return;
     const int kidx = blockIdx.x * blockDim.x + threadIdx.x;
     // list mode (klist != nullptr): C is the packed block, `ld` its capacity, column slot = list position
     const int k = klist ? (kidx < sc->nk ? kidx : ld) : kidx;
     const int r0 = 1 + blockIdx.y * rows_per_chunk;
     const int r1 = min(m + 1, r0 + rows_per_chunk);
-    u32 ev[NW], od[NW];
+    for (int t = threadIdx.x; t < 2 * NU; t += blockDim.x) sUsum[t / NU][t % NU] = 0;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        const int want = pass == 0 ? 1 : -1;
+        u32 acc[NW];
 #pragma unroll
-    for (int l = 0; l < NW; ++l) { ev[l] = 0; od[l] = 0; }
-    for (int base = r0; base < r1; base += RB) {
-        __syncthreads();
-        if (threadIdx.x < RB) {
-            int i = base + threadIdx.x;
-            u64 o = 0;
-            if (i < r1) {
-                u64 x[LSRC];
-                load_planar<LSRC>(x, s, ss, (size_t)i);
-                const u32 sg = (i64)x[LSRC - 1] < 0 ? ~0u : 0u;
+        for (int l = 0; l < NW; ++l) acc[l] = 0;
+        for (int base = r0; base < r1; base += RB) {
+            __syncthreads();
+            if (threadIdx.x < RB) {
+                int i = base + threadIdx.x;
+                int sg = 0;
+                if (i < r1) {
+                    u64 x[LSRC];
+                    load_planar<LSRC>(x, s, ss, (size_t)i);
+                    const bool neg = (i64)x[LSRC - 1] < 0;
+                    u64 o = 0;
+                    if (neg) {
+                        u64 c = 1;
 #pragma unroll
-                for (int l = 0; l < WS; ++l) {
-                    if (l < LSRC) { sU[threadIdx.x][2 * l] = (u32)x[l]; sU[threadIdx.x][2 * l + 1] = (u32)(x[l] >> 32); o |= x[l]; }
-                    else { sU[threadIdx.x][2 * l] = sg; sU[threadIdx.x][2 * l + 1] = sg; }
+                        for (int l = 0; l < LSRC; ++l) { u64 v = ~x[l] + c; c = (c && v == 0) ? 1 : 0; x[l] = v; }
+                    }
+#pragma unroll
+                    for (int l = 0; l < LSRC; ++l) {
+                        sMag[threadIdx.x][2 * l] = (u32)x[l]; sMag[threadIdx.x][2 * l + 1] = (u32)(x[l] >> 32); o |= x[l];
+                    }
+                    sg = o == 0 ? 0 : (neg ? -1 : 1);
+                }
+                sSgn[threadIdx.x] = (signed char)sg;
+            }
+            __syncthreads();
+            const int rn = min(RB, r1 - base);
+            if (threadIdx.x == 0) {        // magnitude sum of this pass' rows (bias removal below)
+                for (int r = 0; r < rn; ++r) {
+                    if (sSgn[r] != want) continue;
+                    u32 cf = 0;
+                    for (int l = 0; l < NU; ++l) {
+                        u32 b = l < NB ? sMag[r][l] : 0u;
+                        u32 v = sUsum[pass][l] + b; u32 c1 = v < b; u32 v2 = v + cf; u32 c2 = v2 < v;
+                        sUsum[pass][l] = v2; cf = c1 + c2;
+                    }
                 }
             }
-            sNz[threadIdx.x] = o != 0;
-        }
-        __syncthreads();
-        if (k >= ld) continue;
-        const int rn = min(RB, r1 - base);
-        for (int r = 0; r < rn; ++r) {
-            if (!sNz[r]) continue;         // rows with a zero factor are never read (uniform over the block)
-            u64 x[L];
-            load_planar<L>(x, C, ps, (size_t)(base + r) * ld + k);
-            u64 any = 0;
+            if (k >= ld) continue;
+            for (int r = 0; r < rn; ++r) {
+                if (sSgn[r] != want) continue;     // uniform over the block; rows with a zero factor are never read
+                u32 x[NA], mg[NB];
+                {
+                    u64 xl[L];
+                    load_planar<L>(xl, C, ps, (size_t)(base + r) * ld + k);
+                    xl[L - 1] ^= 0x8000000000000000ull;                      // + 2^(64L-1)
 #pragma unroll
-            for (int l = 0; l < L; ++l) any |= x[l];
-            if (any == 0) continue;        // zero entries contribute nothing
-            u32 xe[NW];
-            const u32 sg = (i64)x[L - 1] < 0 ? ~0u : 0u;
+                    for (int l = 0; l < L; ++l) { x[2 * l] = (u32)xl[l]; x[2 * l + 1] = (u32)(xl[l] >> 32); }
+                }
 #pragma unroll
-            for (int l = 0; l < WS; ++l) {
-                xe[2 * l] = l < L ? (u32)x[l] : sg;
-                xe[2 * l + 1] = l < L ? (u32)(x[l] >> 32) : sg;
+                for (int l = 0; l < NB; ++l) mg[l] = sMag[r][l];
+                u32 c0 = 0, c1 = 0, c2 = 0;
+                ColScan<NA, NB, NW, 0>::run(acc, c0, c1, c2, x, mg);
             }
-            MpRows<NW, 0>::run(ev, od, xe, sU[r]);
         }
-    }
-    if (k < ld) {
-        // merge the even / odd chains, then sign-extend to the LOUT limbs of the partial sums
-        u32 r32[NW];
-        r32[0] = ev[0];
-        asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r32[1]) : "r"(ev[1]), "r"(od[0]));
+        __syncthreads();                   // sUsum[pass] complete
+        if (k < ld) {
+            // remove the bias: acc -= (sum |s_i|) << (64L - 1)   (word offset 2L-1, bit offset 31)
+            u32 bw = 0;
 #pragma unroll
-        for (int q = 2; q < NW; ++q)
-            asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r32[q]) : "r"(ev[q]), "r"(od[q - 1]));
-        u64 acc[LOUT];
-        const u64 sgo = (int)r32[NW - 1] < 0 ? ~0ull : 0ull;
+            for (int q = NA - 1; q < NW; ++q) {
+                const int j = q - (NA - 1);
+                const u32 lo = j - 1 >= 0 && j - 1 < NU ? sUsum[pass][j - 1 < NU ? (j - 1 >= 0 ? j - 1 : 0) : 0] : 0u;
+                const u32 hi = j < NU ? sUsum[pass][j < NU ? j : 0] : 0u;
+                const u32 sub = (hi << 31) | (lo >> 1);
+                u32 v = acc[q] - sub; u32 b1 = acc[q] < sub; u32 v2 = v - bw; u32 b2 = v < bw;
+                acc[q] = v2; bw = b1 + b2;
+            }
+            u64 out[LOUT];
+            const u64 sgo = (int)acc[NW - 1] < 0 ? ~0ull : 0ull;
 #pragma unroll
-        for (int l = 0; l < LOUT; ++l) acc[l] = l < WS ? ((u64)r32[2 * l] | ((u64)r32[2 * l + 1] << 32)) : sgo;
-        // partial sums are indexed by column (dense mode) or by list position (list mode), row stride pcols
-        store_planar<LOUT>(part + (size_t)blockIdx.y * LOUT * pcols, (size_t)pcols, (size_t)k, acc);
+            for (int l = 0; l < LOUT; ++l) out[l] = l < WS ? ((u64)acc[2 * l] | ((u64)acc[2 * l + 1] << 32)) : sgo;
+            // partial sums are indexed by column (dense mode) or by list position (list mode), row stride pcols
+            store_planar<LOUT>(part + (size_t)(2 * blockIdx.y + pass) * LOUT * pcols, (size_t)pcols, (size_t)k, out);
+        }
     }
 }
 
@@ -1552,11 +1663,19 @@ k_colsum_list(const u64* __restrict__ C, size_t ps, int ld, const int* __restric
 
 // `triv` (may be null): column k is D e_k implicitly, so its column sum is s_k * D, contributed by the rank
 // that owns row k (s: the factor vector, LSRC limbs, local row index k - row_lo).
+// alt != 0: the partial slabs alternate in sign (slab 2c: rows with a positive factor, slab 2c+1: negative ones,
+// see k_colsum1): odd slabs are subtracted.
+template <int LN>
+__device__ __forceinline__ void neg_n(u64 (&x)[LN]) {
+    u64 c = 1;
+#pragma unroll
+    for (int l = 0; l < LN; ++l) { u64 v = ~x[l] + c; c = (c && v == 0) ? 1 : 0; x[l] = v; }
+}
 template <int LOUT, int LSRC = 1, int LDT = 0>
 __global__ void __launch_bounds__(64)
 k_colsum2(const u64* __restrict__ part, int ld, int chunks, int negate, u64* __restrict__ out,
           Scalars* sc, const unsigned char* __restrict__ triv = nullptr, const u64* __restrict__ s = nullptr,
-          size_t ss = 0, int LD = 0, const int* __restrict__ kpos = nullptr, int pcols = 0) {
+          size_t ss = 0, int LD = 0, const int* __restrict__ kpos = nullptr, int pcols = 0, int alt = 0) {
     if (sc->status != ST_RUN) return;
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     int bl = 0;
@@ -1615,11 +1734,13 @@ k_colsum2(const u64* __restrict__ part, int ld, int chunks, int negate, u64* __r
                 load_planar<LOUT>(x1, part + (size_t)(c + 1) * LOUT * pc, (size_t)pc, idx);
                 load_planar<LOUT>(x2, part + (size_t)(c + 2) * LOUT * pc, (size_t)pc, idx);
                 load_planar<LOUT>(x3, part + (size_t)(c + 3) * LOUT * pc, (size_t)pc, idx);
+                if (alt) { neg_n<LOUT>(x1); neg_n<LOUT>(x3); }     // c is a multiple of 4: odd slabs are c+1, c+3
                 add_n<LOUT>(x0, x1); add_n<LOUT>(x2, x3); add_n<LOUT>(acc, x0); add_n<LOUT>(acc, x2);
             }
             for (; c < chunks; ++c) {
                 u64 x[LOUT];
                 load_planar<LOUT>(x, part + (size_t)c * LOUT * pc, (size_t)pc, idx);
+                if (alt && (c & 1)) neg_n<LOUT>(x);
                 add_n<LOUT>(acc, x);
             }
         }
@@ -1641,11 +1762,11 @@ k_colsum2(const u64* __restrict__ part, int ld, int chunks, int negate, u64* __r
 template <int L>
 __global__ void __launch_bounds__(256)
 k_scale_u(const u64* __restrict__ u, size_t us, int nloc, const long long* __restrict__ rowf,
-          u64* __restrict__ out, size_t os, const Scalars* sc) {
+          u64* __restrict__ out, size_t os, Scalars* sc) {
     constexpr int LU = L + 2;
     if (sc->status != ST_RUN) return;
     int i = blockIdx.x * blockDim.x + threadIdx.x;    // local carry row
-    if (i > nloc) return;
+    if (i > nloc) i = 0;                              // (keeps the warp converged for the bit-length reduction)
     u64 x[LU], acc[LU + 1];
     load_planar<LU>(x, u, us, (size_t)i);
 #pragma unroll
@@ -1655,6 +1776,8 @@ k_scale_u(const u64* __restrict__ u, size_t us, int nloc, const long long* __res
         mac_small<LU + 1, LU>(acc, x, f * f);
     }
     store_planar<LU + 1>(out, os, (size_t)i, acc);
+    int bl = warp_max(i >= 1 ? bitlen_signed<LU + 1>(acc) : 0);
+    if ((threadIdx.x & 31) == 0 && bl) atomicMax(&sc->maxbits_s, bl);
 }
 
 // basic cost of every local row as an (nloc+1)-vector of LSRC = 1 limb (artificial / inert rows: 0)

@@ -131,7 +131,7 @@ static int alloc_dense_scratch(rg_context* ctx, int L) {
     if (ctx->nd <= 0) return RG_OK;
     ctx->dmp = ((size_t)ctx->m + 63) / 64 * 64;
     size_t words = 0;
-    for (int LV : {L, LW_of(L)}) {
+    for (int LV : {L, LU_of(L), LU_of(L) + 1, LW_of(L)}) {
         DenseGeom g = dense_geom(ctx, LV);
         words = std::max(words, g.rstride_k * g.ks);
     }
@@ -148,8 +148,9 @@ static int alloc_width_buffers(rg_context* ctx, int L) {
     CK(dev_alloc(&ctx->rowp, sizeof(u64) * L * ld, ctx->stream));
     CK(dev_alloc(&ctx->omega, sizeof(u64) * LW_of(L) * ld, ctx->stream));
     {
-        size_t dense_slots = (size_t)ctx->work_chunks * ld;
-        size_t list_slots = (size_t)ctx->list_chunks * ctx->list_pcols;
+        // two partial slabs per row chunk (rows with a positive / a negative factor, see k_colsum1)
+        size_t dense_slots = 2 * (size_t)ctx->work_chunks * ld;
+        size_t list_slots = 2 * (size_t)ctx->list_chunks * ctx->list_pcols;
         CK(dev_alloc(&ctx->omega_part, sizeof(u64) * LW_of(L) * std::max(dense_slots, list_slots), ctx->stream));
     }
     CK(dev_alloc(&ctx->tmprow, sizeof(u64) * LU_of(L) * ld, ctx->stream));
@@ -158,6 +159,7 @@ static int alloc_width_buffers(rg_context* ctx, int L) {
     CK(dev_alloc(&ctx->kappa, sizeof(u64) * LU_of(L) * n, ctx->stream));
     CK(dev_alloc(&ctx->nu, sizeof(u64) * LU_of(L) * n, ctx->stream));
     CK(dev_alloc(&ctx->sigma, sizeof(u64) * LS_of(L) * n, ctx->stream));
+    if (ctx->nd > 0 || true) CK(dev_alloc(&ctx->tau, sizeof(u64) * (LU_of(L) + 3) * n, ctx->stream));
     if (ctx->world > 1) {   // exchange buffers sized once per width for every collective of the engine
         size_t words = std::max<size_t>((size_t)LW_of(L) * ld, (size_t)LG_of(L) * n);
         words = std::max<size_t>(words, (size_t)(LU_of(L) + 1) * (((size_t)ctx->m + ctx->world - 1) / ctx->world));
@@ -173,7 +175,7 @@ static int alloc_width_buffers(rg_context* ctx, int L) {
 }
 static void free_width_buffers(rg_context* ctx) {
     free_dev_on(ctx->u, ctx->stream); free_dev_on(ctx->rowp, ctx->stream); free_dev_on(ctx->omega, ctx->stream); free_dev_on(ctx->omega_part, ctx->stream);
-    free_dev_on(ctx->tmprow, ctx->stream); free_dev_on(ctx->us2, ctx->stream); free_dev_on(ctx->dR, ctx->stream); free_dev_on(ctx->dSl, ctx->stream); free_dev_on(ctx->dchunk, ctx->stream); free_dev_on(ctx->kappa, ctx->stream); free_dev_on(ctx->nu, ctx->stream); free_dev_on(ctx->sigma, ctx->stream);
+    free_dev_on(ctx->tmprow, ctx->stream); free_dev_on(ctx->us2, ctx->stream); free_dev_on(ctx->dR, ctx->stream); free_dev_on(ctx->dSl, ctx->stream); free_dev_on(ctx->dchunk, ctx->stream); free_dev_on(ctx->kappa, ctx->stream); free_dev_on(ctx->nu, ctx->stream); free_dev_on(ctx->sigma, ctx->stream); free_dev_on(ctx->tau, ctx->stream); ctx->tau = nullptr;
     free_dev_on(ctx->xsend, ctx->stream); free_dev_on(ctx->xrecv, ctx->stream);
     ctx->xsend = ctx->xrecv = nullptr; ctx->xbytes = 0;
     ctx->u = ctx->rowp = ctx->omega = ctx->omega_part = ctx->tmprow = ctx->us2 = nullptr; ctx->dR = nullptr; ctx->dSl = nullptr; ctx->dchunk = nullptr;
@@ -552,8 +554,10 @@ static void set_status(rg_context* ctx, int st) { LAUNCH(k_set_status, 1, 1, ctx
 
 // out_j = cmul cost_j D + vec[1..m] . a_j for every provider column: dense block + CSC remainder.
 // `bits` points at the device-side bit-length maximum that bounds every entry of `vec`.
+// mask (dense block only): 0 none, 1 keep the entries of trivial carry columns, 2 keep the listed ones
 template <int LV, int LO>
-static void launch_coldots(rg_context* ctx, const u64* vec, size_t vs, int cmul, u64* out, const int* bits) {
+static void launch_coldots(rg_context* ctx, const u64* vec, size_t vs, int cmul, u64* out, const int* bits,
+                           int mask = 0, bool csc_part = true) {
     const int jd0 = ctx->d0, jd1 = ctx->d1;      // dense block slice
     const int j0 = ctx->s0, j1 = ctx->s1;        // CSC slice
     if (jd1 > jd0) {
@@ -562,14 +566,15 @@ static void launch_coldots(rg_context* ctx, const u64* vec, size_t vs, int cmul,
         constexpr int NTC = NT_MAX <= 20 ? NT_MAX : (NT_MAX + 1) / 2;
         const DenseGeom g = dense_geom(ctx, LV);
         LAUNCH((k_dense_slices<LV>), (unsigned)(ctx->dmp / 64), 64, vec, vs, ctx->m, bits, ctx->dSl, ctx->dmp,
-               ctx->dchunk, ctx->sc);
+               ctx->dchunk, ctx->sc, mask ? (const unsigned char*)ctx->triv : (const unsigned char*)nullptr,
+               mask == 1 ? 1 : 0);
         dim3 grid(cdiv(g.ncols, 128), g.ks, g.zs);
         LAUNCH((k_dense_mma<NTC>), grid, 256, ctx->Acm, ctx->ldc, jd0, jd1, ctx->dSl, ctx->dmp, ctx->dchunk, bits, LV,
                g.rps, ctx->dR, g.rstride_k, g.rpitch, ctx->sc);
         LAUNCH((k_dense_combine<LV, LO>), cdiv(g.ncols, 128), 128, ctx->dR, g.rstride_k, g.ks, g.rpitch, ctx->n, jd0,
                jd1, bits, ctx->inbasis, ctx->cost, cmul, ctx->L, out, ctx->sc);
     }
-    if (j1 > j0)
+    if (j1 > j0 && csc_part)
         LAUNCH((k_coldot<LV, LO>), cdiv(j1 - j0, 64), 64, vec, vs, ctx->n, j0, j1, ctx->A.colptr,
                ctx->A.rowidx, ctx->A.vals, ctx->inbasis, ctx->cost, cmul, ctx->L, out, ctx->sc);
 }
@@ -742,20 +747,20 @@ static int launch_work_t(rg_context* ctx) {
         LAUNCH((k_colsum1<L, LU + 1, LW>), grid, 128, bv.base, bv.ps, bv.stride, ctx->nloc, g.rpc,
                g.klist, ctx->us2, (size_t)ctx->ld, ctx->omega_part, g.pcols, ctx->sc);
         if (ctx->list_mode)
-            LAUNCH((k_colsum2<LW, LU + 1, L>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, g.chunks, 0,
-                   first_out, ctx->sc, g.triv, src, (size_t)ctx->ld, L, g.kpos, g.pcols);
+            LAUNCH((k_colsum2<LW, LU + 1, L>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, 2 * g.chunks, 0,
+                   first_out, ctx->sc, g.triv, src, (size_t)ctx->ld, L, g.kpos, g.pcols, 1);
         else
-            LAUNCH((k_colsum2<LW, LU + 1>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, g.chunks, 0,
-                   first_out, ctx->sc, g.triv, src, (size_t)ctx->ld, L, g.kpos, g.pcols);
+            LAUNCH((k_colsum2<LW, LU + 1>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, 2 * g.chunks, 0,
+                   first_out, ctx->sc, g.triv, src, (size_t)ctx->ld, L, g.kpos, g.pcols, 1);
     } else {
         LAUNCH((k_colsum1<L, LU, LW>), grid, 128, bv.base, bv.ps, bv.stride, ctx->nloc, g.rpc,
                g.klist, ctx->u, (size_t)ctx->ld, ctx->omega_part, g.pcols, ctx->sc);
         if (ctx->list_mode)
-            LAUNCH((k_colsum2<LW, LU, L>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, g.chunks, 0,
-                   first_out, ctx->sc, g.triv, src, (size_t)ctx->ld, L, g.kpos, g.pcols);
+            LAUNCH((k_colsum2<LW, LU, L>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, 2 * g.chunks, 0,
+                   first_out, ctx->sc, g.triv, src, (size_t)ctx->ld, L, g.kpos, g.pcols, 1);
         else
-            LAUNCH((k_colsum2<LW, LU>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, g.chunks, 0,
-                   first_out, ctx->sc, g.triv, src, (size_t)ctx->ld, L, g.kpos, g.pcols);
+            LAUNCH((k_colsum2<LW, LU>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, 2 * g.chunks, 0,
+                   first_out, ctx->sc, g.triv, src, (size_t)ctx->ld, L, g.kpos, g.pcols, 1);
     }
     if (ctx->world == 1) return RG_OK;
     RG_TRY(all_gather(ctx, ctx->xsend, ctx->xrecv, words));
@@ -807,6 +812,22 @@ template <int L>
 static void launch_se_dots_t(rg_context* ctx) {
     constexpr int LU = L + 2, LW = LW_of(L), LS = LS_of(L);
     launch_coldots<L, LU>(ctx, ctx->rowp, (size_t)ctx->ld, 0, ctx->nu, &ctx->sc->maxbits_rowp);
+    if (ctx->list_mode && ctx->d1 > ctx->d0 && ctx->world == 1) {
+        // split sigma dot over the dense block: the work vector on the trivial carry columns
+        // is D * s_k, so the wide (2L+5 limb) vector only has to cover the LISTED columns (a few 64-row chunks: the
+        // others are skipped as zero) and the long dot runs on the (L+2)-limb factor vector s -- half the slices
+        launch_coldots<LW, LS>(ctx, ctx->omega, (size_t)ctx->ld, 0, ctx->sigma, &ctx->sc->maxbits_tmp, 2, true);
+        if (ctx->weighted) {
+            launch_coldots<LU + 1, LU + 3>(ctx, ctx->us2, (size_t)ctx->ld, 0, ctx->tau, &ctx->sc->maxbits_s, 1, false);
+            LAUNCH((k_sigma_add_dtau<LU + 3, L, LS>), cdiv(ctx->d1 - ctx->d0, 128), 128, ctx->tau, ctx->n, ctx->d0, ctx->d1,
+                   ctx->inbasis, ctx->sigma, ctx->sc);
+        } else {
+            launch_coldots<LU, LU + 2>(ctx, ctx->u, (size_t)ctx->ld, 0, ctx->tau, &ctx->sc->maxbits_u, 1, false);
+            LAUNCH((k_sigma_add_dtau<LU + 2, L, LS>), cdiv(ctx->d1 - ctx->d0, 128), 128, ctx->tau, ctx->n, ctx->d0, ctx->d1,
+                   ctx->inbasis, ctx->sigma, ctx->sc);
+        }
+        return;
+    }
     launch_coldots<LW, LS>(ctx, ctx->omega, (size_t)ctx->ld, 0, ctx->sigma, &ctx->sc->maxbits_tmp);
 }
 template <int L>
@@ -1156,14 +1177,14 @@ static int launch_phase_sums_t(rg_context* ctx) {
     LAUNCH((k_colsum1<L, 1, LU>), grid, 128, bv.base, bv.ps, bv.stride, ctx->nloc, g.rpc, g.klist,
            ctx->svec, (size_t)ctx->ld, ctx->omega_part, g.pcols, ctx->sc);
     if (ctx->world == 1) {
-        LAUNCH((k_colsum2<LU, 1>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, g.chunks, 1,
-               ctx->tmprow, ctx->sc, g.triv, ctx->svec, (size_t)ctx->ld, L, g.kpos, g.pcols);
+        LAUNCH((k_colsum2<LU, 1>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, 2 * g.chunks, 1,
+               ctx->tmprow, ctx->sc, g.triv, ctx->svec, (size_t)ctx->ld, L, g.kpos, g.pcols, 1);
         return RG_OK;
     }
     size_t words = (size_t)LU * ctx->ld;
     RG_TRY(ensure_xbuf(ctx, words, words * ctx->world));
-    LAUNCH((k_colsum2<LU, 1>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, g.chunks, 0,
-           ctx->xsend, ctx->sc, g.triv, ctx->svec, (size_t)ctx->ld, L, g.kpos, g.pcols);
+    LAUNCH((k_colsum2<LU, 1>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, 2 * g.chunks, 0,
+           ctx->xsend, ctx->sc, g.triv, ctx->svec, (size_t)ctx->ld, L, g.kpos, g.pcols, 1);
     RG_TRY(all_gather(ctx, ctx->xsend, ctx->xrecv, words));
     LAUNCH(k_reset_tmpbits, 1, 1, ctx->sc);
     LAUNCH((k_colsum2<LU>), cdiv(ctx->ld, 64), 64, ctx->xrecv, ctx->ld, ctx->world, 1, ctx->tmprow, ctx->sc);
