@@ -144,6 +144,13 @@ int rg_set_weights(rg_context* ctx, const int64_t* colfac, const int64_t* artfac
  * every non-artificial basic column is a unit column e_i (a positive slack), so B^-1 = I, D = 1. */
 int rg_init_identity_basis(rg_context* ctx, const int32_t* basis, const int64_t* cost);
 
+/* from_basis / from_basis_pivots on a GENERAL basis (carry/mod.rs:444-497) = BasisInverse::invert
+ * (carry/basis_inverse_rows.rs:104-129, lower_upper/decomposition/mod.rs:27-143): `basis[i]` is the provider
+ * column basic in row i (m distinct columns, non-singular); `cost` the cost vector of the phase started.  The
+ * inverse is built on the device by fraction-free Gauss-Jordan (the engine's own rank-1 update per non-unit
+ * column), D = |det B|.  Enables warm starts.  Single GPU. */
+int rg_init_basis(rg_context* ctx, const int32_t* basis, const int64_t* cost);
+
 /* from_artificial (carry/mod.rs:499-525): install the phase-two costs and rebuild -pi = -c_B^T B^-1 and
  * -obj = -c_B b.  Rows whose artificial is still basic (rank-deficient rows, phase_one.rs:232-278) stay in
  * the carry as inert rows with cost 0, which is value-identical to deleting them

@@ -334,20 +334,41 @@ class Carry:
         return cls(minus_obj, minus_pi, b, basis, rows)
 
     @classmethod
-    def from_basis_pivots(cls, pivots, provider):
-        # carry/mod.rs:480-497 -> from_basis :444-478.  Only identity bases are supported by the
-        # oracle (the slack basis of `FullInitialBasis` providers): BI::invert(I) = I.
-        elements = sorted(pivots, key=lambda rc: rc[0])
-        basis = [c for _, c in elements]
+    def from_basis(cls, basis, provider):
+        """carry/mod.rs:444-478: `basis[i]` is the column basic in row i.  `BI::invert(columns)`
+        (basis_inverse_rows.rs:104-129: every identity column through the inverted basis) restated as an exact
+        Gauss-Jordan inversion; b = B^-1 rhs (:456-466), then -obj and -pi from the basic costs."""
         m = provider.nr_rows()
         assert len(basis) == m
+        # augmented [B | I], B[:, i] = column basis[i]
+        M = [[ZERO] * (2 * m) for _ in range(m)]
         for i, j in enumerate(basis):
-            assert provider.column(j) == [(i, ONE)], "oracle from_basis supports identity bases only"
-        b = provider.right_hand_side()
-        rows = cls.identity_rows(m)
+            for r, v in provider.column(j):
+                M[r][i] = Fraction(v)
+        for r in range(m):
+            M[r][m + r] = ONE
+        for c in range(m):
+            piv = next((r for r in range(c, m) if M[r][c] != 0), None)
+            assert piv is not None, "singular basis"
+            M[c], M[piv] = M[piv], M[c]
+            inv = ONE / M[c][c]
+            M[c] = [v * inv for v in M[c]]
+            for r in range(m):
+                if r != c and M[r][c] != 0:
+                    f = M[r][c]
+                    M[r] = [a - f * x for a, x in zip(M[r], M[c])]
+        rows = [{k: M[i][m + k] for k in range(m) if M[i][m + k] != 0} for i in range(m)]
+        rhs = provider.right_hand_side()
+        b = [sum((v * rhs[k] for k, v in rows[i].items()), ZERO) for i in range(m)]
         minus_obj = cls._minus_obj_from_basis(provider, basis, b)
         minus_pi = cls._minus_pi_from_basis(rows, provider, basis)
-        return cls(minus_obj, minus_pi, b, basis, rows)
+        return cls(minus_obj, minus_pi, b, list(basis), rows)
+
+    @classmethod
+    def from_basis_pivots(cls, pivots, provider):
+        # carry/mod.rs:480-497: sort by row, then from_basis
+        elements = sorted(pivots, key=lambda rc: rc[0])
+        return cls.from_basis([c for _, c in elements], provider)
 
     # ---- queries ------------------------------------------------------------------------
     def cost_difference(self, column: SparseCol) -> Fraction:

@@ -67,6 +67,7 @@ SYMBOLS = {
     "rg_set_weights": (C.c_int, [P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                  C.POINTER(C.c_int64)]),
     "rg_init_identity_basis": (C.c_int, [P, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
+    "rg_init_basis": (C.c_int, [P, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "rg_phase_switch": (C.c_int, [P, C.POINTER(C.c_int64)]),
     "rg_rule_new": (C.c_int, [P, C.c_int32]),
     "rg_select_primal_pivot_column": (C.c_int, [P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),

@@ -1432,6 +1432,13 @@ __device__ __forceinline__ void mul_full_ct(u64 (&r)[LA + LB], const u64 (&a)[LA
     r[LA + LB - 1] = c0;
 }
 
+template <int LN>
+__device__ __forceinline__ void neg_n(u64 (&x)[LN]) {
+    u64 c = 1;
+#pragma unroll
+    for (int l = 0; l < LN; ++l) { u64 v = ~x[l] + c; c = (c && v == 0) ? 1 : 0; x[l] = v; }
+}
+
 // Stage 1 in unsigned form (IMAD.WIDE product scanning, 1152 multiply-adds per 16-limb entry instead of the 2485
 // of a two's complement accumulation at the output width):
 //   * the carry entry is biased, x' = C[i][k] + 2^(64L-1) (its top bit flipped): 0 <= x' < 2^(64L);
@@ -1463,6 +1470,9 @@ struct ColScan {
     }
 };
 
+// Thread mapping: a block is 32 column slots x 4 row groups (one warp each: a warp reads 32 consecutive entries of
+// one row, 256 B per limb plane); the four groups split the rows of the chunk and their partial sums are added
+// through shared memory at the end of a pass, so a chunk still produces one slab per pass.
 template <int L, int LSRC, int LOUT>
 __global__ void __launch_bounds__(128, 3)
 k_colsum1(const u64* __restrict__ C, size_t ps, int ld, int m, int rows_per_chunk, const int* __restrict__ klist,
@@ -1470,18 +1480,22 @@ k_colsum1(const u64* __restrict__ C, size_t ps, int ld, int m, int rows_per_chun
     constexpr int RB = 64;                 // rows whose factors are staged in shared memory at a time
     constexpr int WS = (L + LSRC + 1) < LOUT ? (L + LSRC + 1) : LOUT;   // 64-bit limbs of a partial sum
     constexpr int NA = 2 * L, NB = 2 * LSRC, NW = 2 * WS;
-    constexpr int NU = NB + 2;             // limbs of a chunk's magnitude sum (up to 2^32 rows)
+    constexpr int LQ = LSRC + 1;           // 64-bit limbs of a chunk's magnitude sum (up to 2^32 rows)
+    constexpr int NU = 2 * LQ;
     static_assert(NW >= NA + NB + 1 || WS == LOUT, "partial sums need one limb of headroom");
     __shared__ u32 sMag[RB][NB];
     __shared__ signed char sSgn[RB];
-    __shared__ u32 sUsum[2][NU];           // per pass: sum of |s_i| over the chunk's rows of that sign
+    __shared__ u64 sPart[2][2][LQ];        // [staging warp][pass]: magnitude sums of one batch
+    __shared__ u64 sUsum[2][LQ];           // per pass: sum of |s_i| over the chunk's rows of that sign
+    __shared__ u32 sRed[3][NW][32];        // partial sums of row groups 1..3
     if (sc->status != ST_RUN) return;
-    const int kidx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int kidx = blockIdx.x * 32 + lane;
     // list mode (klist != nullptr): C is the packed block, `ld` its capacity, column slot = list position
     const int k = klist ? (kidx < sc->nk ? kidx : ld) : kidx;
     const int r0 = 1 + blockIdx.y * rows_per_chunk;
     const int r1 = min(m + 1, r0 + rows_per_chunk);
-    for (int t = threadIdx.x; t < 2 * NU; t += blockDim.x) sUsum[t / NU][t % NU] = 0;
+    if (threadIdx.x < 2 * LQ) sUsum[threadIdx.x / LQ][threadIdx.x % LQ] = 0;
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
         const int want = pass == 0 ? 1 : -1;
@@ -1490,11 +1504,13 @@ k_colsum1(const u64* __restrict__ C, size_t ps, int ld, int m, int rows_per_chun
         for (int l = 0; l < NW; ++l) acc[l] = 0;
         for (int base = r0; base < r1; base += RB) {
             __syncthreads();
-            if (threadIdx.x < RB) {
+            if (threadIdx.x < RB) {        // warps 0 and 1 stage the factors of rows base .. base+63
                 int i = base + threadIdx.x;
                 int sg = 0;
+                u64 x[LSRC];
+#pragma unroll
+                for (int l = 0; l < LSRC; ++l) x[l] = 0;
                 if (i < r1) {
-                    u64 x[LSRC];
                     load_planar<LSRC>(x, s, ss, (size_t)i);
                     const bool neg = (i64)x[LSRC - 1] < 0;
                     u64 o = 0;
@@ -1510,23 +1526,40 @@ k_colsum1(const u64* __restrict__ C, size_t ps, int ld, int m, int rows_per_chun
                     sg = o == 0 ? 0 : (neg ? -1 : 1);
                 }
                 sSgn[threadIdx.x] = (signed char)sg;
-            }
-            __syncthreads();
-            const int rn = min(RB, r1 - base);
-            if (threadIdx.x == 0) {        // magnitude sum of this pass' rows (bias removal below)
-                for (int r = 0; r < rn; ++r) {
-                    if (sSgn[r] != want) continue;
-                    u32 cf = 0;
-                    for (int l = 0; l < NU; ++l) {
-                        u32 b = l < NB ? sMag[r][l] : 0u;
-                        u32 v = sUsum[pass][l] + b; u32 c1 = v < b; u32 v2 = v + cf; u32 c2 = v2 < v;
-                        sUsum[pass][l] = v2; cf = c1 + c2;
+                if (pass == 0) {           // magnitude sums of both signs, once per batch (bias removal below)
+#pragma unroll
+                    for (int p2 = 0; p2 < 2; ++p2) {
+                        u64 q[LQ];
+                        const bool mine = sg == (p2 == 0 ? 1 : -1);
+#pragma unroll
+                        for (int l = 0; l < LQ; ++l) q[l] = (mine && l < LSRC) ? x[l] : 0;
+#pragma unroll
+                        for (int off = 16; off >= 1; off >>= 1) {
+                            u64 o2[LQ];
+#pragma unroll
+                            for (int l = 0; l < LQ; ++l) o2[l] = __shfl_down_sync(0xffffffffu, q[l], off);
+                            add_n<LQ>(q, o2);
+                        }
+                        if (lane == 0) {
+#pragma unroll
+                            for (int l = 0; l < LQ; ++l) sPart[grp][p2][l] = q[l];
+                        }
                     }
                 }
             }
+            __syncthreads();
+            if (pass == 0 && threadIdx.x < 2) {      // thread p2 folds the two staging warps' sums into the chunk sum
+                u64 a[LQ], b0[LQ], b1[LQ];
+#pragma unroll
+                for (int l = 0; l < LQ; ++l) { a[l] = sUsum[threadIdx.x][l]; b0[l] = sPart[0][threadIdx.x][l]; b1[l] = sPart[1][threadIdx.x][l]; }
+                add_n<LQ>(a, b0); add_n<LQ>(a, b1);
+#pragma unroll
+                for (int l = 0; l < LQ; ++l) sUsum[threadIdx.x][l] = a[l];
+            }
             if (k >= ld) continue;
-            for (int r = 0; r < rn; ++r) {
-                if (sSgn[r] != want) continue;     // uniform over the block; rows with a zero factor are never read
+            const int rn = min(RB, r1 - base);
+            for (int r = grp; r < rn; r += 4) {
+                if (sSgn[r] != want) continue;     // uniform over the warp; rows with a zero factor are never read
                 u32 x[NA], mg[NB];
                 {
                     u64 xl[L];
@@ -1541,15 +1574,28 @@ k_colsum1(const u64* __restrict__ C, size_t ps, int ld, int m, int rows_per_chun
                 ColScan<NA, NB, NW, 0>::run(acc, c0, c1, c2, x, mg);
             }
         }
-        __syncthreads();                   // sUsum[pass] complete
-        if (k < ld) {
+        // add the four row groups' partial sums (group 0 keeps the result)
+        __syncthreads();
+        if (grp > 0) {
+#pragma unroll
+            for (int l = 0; l < NW; ++l) sRed[grp - 1][l][lane] = acc[l];
+        }
+        __syncthreads();                   // (sUsum[pass] is complete here too)
+        if (grp == 0 && k < ld) {
+#pragma unroll
+            for (int g = 0; g < 3; ++g) {
+                asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(acc[0]) : "r"(sRed[g][0][lane]));
+#pragma unroll
+                for (int l = 1; l < NW; ++l) asm volatile("addc.cc.u32 %0, %0, %1;" : "+r"(acc[l]) : "r"(sRed[g][l][lane]));
+            }
             // remove the bias: acc -= (sum |s_i|) << (64L - 1)   (word offset 2L-1, bit offset 31)
+            const u32* us = reinterpret_cast<const u32*>(sUsum[pass]);
             u32 bw = 0;
 #pragma unroll
             for (int q = NA - 1; q < NW; ++q) {
                 const int j = q - (NA - 1);
-                const u32 lo = j - 1 >= 0 && j - 1 < NU ? sUsum[pass][j - 1 < NU ? (j - 1 >= 0 ? j - 1 : 0) : 0] : 0u;
-                const u32 hi = j < NU ? sUsum[pass][j < NU ? j : 0] : 0u;
+                const u32 lo = (j - 1 >= 0 && j - 1 < NU) ? us[(j - 1 >= 0 && j - 1 < NU) ? j - 1 : 0] : 0u;
+                const u32 hi = j < NU ? us[j < NU ? j : 0] : 0u;
                 const u32 sub = (hi << 31) | (lo >> 1);
                 u32 v = acc[q] - sub; u32 b1 = acc[q] < sub; u32 v2 = v - bw; u32 b2 = v < bw;
                 acc[q] = v2; bw = b1 + b2;
@@ -1561,6 +1607,51 @@ k_colsum1(const u64* __restrict__ C, size_t ps, int ld, int m, int rows_per_chun
             // partial sums are indexed by column (dense mode) or by list position (list mode), row stride pcols
             store_planar<LOUT>(part + (size_t)(2 * blockIdx.y + pass) * LOUT * pcols, (size_t)pcols, (size_t)k, out);
         }
+    }
+}
+
+// Stage 2 for the listed columns (list mode): one block per list position; the threads stride over the partial
+// slabs (odd slabs subtract), the block's sums are folded with warp shuffles and shared memory.
+template <int LOUT>
+__global__ void __launch_bounds__(128)
+k_colsum2_list(const u64* __restrict__ part, int nslabs, int pcols, const int* __restrict__ klist, int ld,
+               int negate, u64* __restrict__ out, Scalars* sc) {
+    __shared__ u64 sW[4][LOUT];
+    if (sc->status != ST_RUN) return;
+    const int t = blockIdx.x;
+    if (t >= sc->nk) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u64 acc[LOUT];
+#pragma unroll
+    for (int l = 0; l < LOUT; ++l) acc[l] = 0;
+    for (int c = threadIdx.x; c < nslabs; c += blockDim.x) {
+        u64 x[LOUT];
+        load_planar<LOUT>(x, part + (size_t)c * LOUT * pcols, (size_t)pcols, (size_t)t);
+        if (c & 1) neg_n<LOUT>(x);
+        add_n<LOUT>(acc, x);
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        u64 o[LOUT];
+#pragma unroll
+        for (int l = 0; l < LOUT; ++l) o[l] = __shfl_down_sync(0xffffffffu, acc[l], off);
+        add_n<LOUT>(acc, o);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int l = 0; l < LOUT; ++l) sW[warp][l] = acc[l];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 4; ++w) {
+            u64 o[LOUT];
+#pragma unroll
+            for (int l = 0; l < LOUT; ++l) o[l] = sW[w][l];
+            add_n<LOUT>(acc, o);
+        }
+        if (negate) neg_n<LOUT>(acc);
+        store_planar<LOUT>(out, (size_t)ld, (size_t)klist[t], acc);
+        atomicMax(&sc->maxbits_tmp, bitlen_signed<LOUT>(acc));
     }
 }
 
@@ -1665,12 +1756,6 @@ k_colsum_list(const u64* __restrict__ C, size_t ps, int ld, const int* __restric
 // that owns row k (s: the factor vector, LSRC limbs, local row index k - row_lo).
 // alt != 0: the partial slabs alternate in sign (slab 2c: rows with a positive factor, slab 2c+1: negative ones,
 // see k_colsum1): odd slabs are subtracted.
-template <int LN>
-__device__ __forceinline__ void neg_n(u64 (&x)[LN]) {
-    u64 c = 1;
-#pragma unroll
-    for (int l = 0; l < LN; ++l) { u64 v = ~x[l] + c; c = (c && v == 0) ? 1 : 0; x[l] = v; }
-}
 template <int LOUT, int LSRC = 1, int LDT = 0>
 __global__ void __launch_bounds__(64)
 k_colsum2(const u64* __restrict__ part, int ld, int chunks, int negate, u64* __restrict__ out,
@@ -1680,6 +1765,7 @@ k_colsum2(const u64* __restrict__ part, int ld, int chunks, int negate, u64* __r
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     int bl = 0;
     if (k < ld) {
+        bool listed = false;
         u64 acc[LOUT];
 #pragma unroll
         for (int l = 0; l < LOUT; ++l) acc[l] = 0;
@@ -1724,6 +1810,10 @@ k_colsum2(const u64* __restrict__ part, int ld, int chunks, int negate, u64* __r
                     mul_lo<LOUT>(acc, xe, de);
                 }
             }
+        } else if (kpos) {
+            // list mode: the listed columns (column 0 and every k with a list position) are summed and stored by
+            // k_colsum2_list; what remains here is padding beyond m: zero
+            listed = k == 0 || kpos[k] > 0;
         } else {
             const int pc = kpos ? pcols : ld;             // list mode: partials live at the list position
             const size_t idx = kpos ? (size_t)kpos[k] : (size_t)k;
@@ -1749,7 +1839,7 @@ k_colsum2(const u64* __restrict__ part, int ld, int chunks, int negate, u64* __r
 #pragma unroll
             for (int l = 0; l < LOUT; ++l) { u64 v = ~acc[l] + c; c = (c && v == 0) ? 1 : 0; acc[l] = v; }
         }
-        if (k < ld) {
+        if (k < ld && !listed) {
             store_planar<LOUT>(out, (size_t)ld, (size_t)k, acc);
             bl = bitlen_signed<LOUT>(acc);
         }
@@ -1950,6 +2040,92 @@ k_gamma_init_general(const u64* __restrict__ C, size_t ps, int ld, int m, int n,
         }
         store_planar<LG>(G, (size_t)n, (size_t)j, acc);
     }
+}
+
+// General-basis initialisation, row by row (any carry mode, CSC and dense-block columns alike): with
+// nu_ij = (row i of the carry) . a_j staged by the column-dot machinery,
+//     Ghat_j = (D W / w_j)^2 + sum_i (nu_ij W / w_B(i))^2          (initial_gamma, pivot_rule.rs:299-305)
+// k_gamma_seed writes the first term, k_gamma_accum adds one row's squares.
+template <int L>
+__global__ void __launch_bounds__(128)
+k_gamma_seed(int n, ColOwn own, const unsigned char* __restrict__ inbasis, const long long* __restrict__ wf,
+             u64* __restrict__ G, const Scalars* sc) {
+    constexpr int LG = 2 * L + 6;
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n || !own.owned(j)) return;
+    u64 acc[LG];
+#pragma unroll
+    for (int l = 0; l < LG; ++l) acc[l] = 0;
+    if (!inbasis[j]) {
+        u64 d[L + 1], d2[2 * L + 2];
+        u64 f = wf ? (u64)wf[j] : 1ull;
+        u64 carry = 0;
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+            u64 x = sc->D[l];
+            u64 lo = x * f, hi = __umul64hi(x, f);
+            u64 v = lo + carry; u64 c1 = v < lo;
+            d[l] = v; carry = hi + c1;
+        }
+        d[L] = carry;
+        mul_full_ct<L + 1, L + 1>(d2, d, d);
+#pragma unroll
+        for (int l = 0; l < 2 * L + 2; ++l) acc[l] = d2[l];
+    }
+    store_planar<LG>(G, (size_t)n, (size_t)j, acc);
+}
+template <int L>
+__global__ void __launch_bounds__(128)
+k_gamma_accum(int n, ColOwn own, const unsigned char* __restrict__ inbasis, const u64* __restrict__ nu,
+              const long long* __restrict__ rowf, int row, u64* __restrict__ G, const Scalars* sc) {
+    constexpr int LU = L + 2, LG = 2 * L + 6;
+    if (sc->status != ST_RUN) return;
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n || !own.owned(j) || inbasis[j]) return;
+    u64 x[LU];
+    load_planar<LU>(x, nu, (size_t)n, (size_t)j);
+    u64 any = 0;
+#pragma unroll
+    for (int l = 0; l < LU; ++l) any |= x[l];
+    if (any == 0) return;
+    if ((i64)x[LU - 1] < 0) {
+        u64 c = 1;
+#pragma unroll
+        for (int l = 0; l < LU; ++l) { u64 v = ~x[l] + c; c = (c && v == 0) ? 1 : 0; x[l] = v; }
+    }
+    u64 xs[LU + 1];
+    {
+        u64 rf = rowf ? (u64)rowf[row] : 1ull;
+        u64 carry = 0;
+#pragma unroll
+        for (int l = 0; l < LU; ++l) {
+            u64 lo = x[l] * rf, hi = __umul64hi(x[l], rf);
+            u64 v = lo + carry; u64 c1 = v < lo;
+            xs[l] = v; carry = hi + c1;
+        }
+        xs[LU] = carry;
+    }
+    u64 sq[2 * LU + 2];
+    mul_full_ct<LU + 1, LU + 1>(sq, xs, xs);
+    u64 g[LG];
+    load_planar<LG>(g, G, (size_t)n, (size_t)j);
+    u64 cf = 0;
+#pragma unroll
+    for (int l = 0; l < LG; ++l) {
+        u64 b = l < 2 * LU + 2 ? sq[l] : 0;
+        u64 v = g[l] + b; u64 c1 = v < b; u64 v2 = v + cf; u64 c2 = v2 < v;
+        g[l] = v2; cf = c1 + c2;
+    }
+    store_planar<LG>(G, (size_t)n, (size_t)j, g);
+}
+// general-basis constructor: rows of the carry gathered through a permutation (new row i = old row perm[i-1]+1)
+__global__ void __launch_bounds__(256)
+k_permute_rows(u64* __restrict__ dst, const u64* __restrict__ src, size_t ps, int ld, int m, int L,
+               const int* __restrict__ perm) {
+    const int i = blockIdx.y;                       // carry row 0..m
+    const int from = i == 0 ? 0 : perm[i - 1] + 1;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < ld; k += gridDim.x * blockDim.x)
+        for (int l = 0; l < L; ++l) dst[(size_t)l * ps + (size_t)i * ld + k] = src[(size_t)l * ps + (size_t)from * ld + k];
 }
 
 // per-column steepest-edge recurrence, fixed width WX = LG + 4 limbs (register resident, 32-bit limb

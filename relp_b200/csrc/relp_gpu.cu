@@ -729,7 +729,7 @@ template <int L>
 static int launch_work_t(rg_context* ctx) {
     constexpr int LU = L + 2, LW = 2 * L + 5;
     const ColsumGeom g = colsum_geom(ctx);
-    dim3 grid(cdiv(g.ncols, 128), g.chunks);
+    dim3 grid(cdiv(g.ncols, 32), g.chunks);        // k_colsum1: 32 column slots x 4 row groups per block
     const u64* src = ctx->u;
     size_t words = (size_t)LW * ctx->ld;
     if (ctx->world > 1) RG_TRY(ensure_xbuf(ctx, words, words * ctx->world));
@@ -747,8 +747,12 @@ static int launch_work_t(rg_context* ctx) {
         LAUNCH((k_colsum1<L, LU + 1, LW>), grid, 128, bv.base, bv.ps, bv.stride, ctx->nloc, g.rpc,
                g.klist, ctx->us2, (size_t)ctx->ld, ctx->omega_part, g.pcols, ctx->sc);
         if (ctx->list_mode)
+        {
             LAUNCH((k_colsum2<LW, LU + 1, L>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, 2 * g.chunks, 0,
                    first_out, ctx->sc, g.triv, src, (size_t)ctx->ld, L, g.kpos, g.pcols, 1);
+            LAUNCH((k_colsum2_list<LW>), g.ncols, 128, ctx->omega_part, 2 * g.chunks, g.pcols, g.klist, ctx->ld, 0,
+                   first_out, ctx->sc);
+        }
         else
             LAUNCH((k_colsum2<LW, LU + 1>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, 2 * g.chunks, 0,
                    first_out, ctx->sc, g.triv, src, (size_t)ctx->ld, L, g.kpos, g.pcols, 1);
@@ -756,8 +760,12 @@ static int launch_work_t(rg_context* ctx) {
         LAUNCH((k_colsum1<L, LU, LW>), grid, 128, bv.base, bv.ps, bv.stride, ctx->nloc, g.rpc,
                g.klist, ctx->u, (size_t)ctx->ld, ctx->omega_part, g.pcols, ctx->sc);
         if (ctx->list_mode)
+        {
             LAUNCH((k_colsum2<LW, LU, L>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, 2 * g.chunks, 0,
                    first_out, ctx->sc, g.triv, src, (size_t)ctx->ld, L, g.kpos, g.pcols, 1);
+            LAUNCH((k_colsum2_list<LW>), g.ncols, 128, ctx->omega_part, 2 * g.chunks, g.pcols, g.klist, ctx->ld, 0,
+                   first_out, ctx->sc);
+        }
         else
             LAUNCH((k_colsum2<LW, LU>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, 2 * g.chunks, 0,
                    first_out, ctx->sc, g.triv, src, (size_t)ctx->ld, L, g.kpos, g.pcols, 1);
@@ -1168,23 +1176,120 @@ extern "C" int rg_init_identity_basis(rg_context* ctx, const int32_t* basis, con
     return RG_OK;
 }
 
+// from_basis (carry/mod.rs:444-478) = BasisInverse::invert on the selected columns: fraction-free Gauss-Jordan
+// on the device.  Unit columns are relabelled (B is unchanged), every other basic column is pivoted in with the
+// engine's own rank-1 update in a row that still holds an artificial; the rows are permuted at the end so that
+// row i holds basis[i], and the costs are installed like at a phase switch.
+extern "C" int rg_init_basis(rg_context* ctx, const int32_t* basis, const int64_t* cost) {
+    if (!ctx || !ctx->carry || !basis || !cost) return RG_ERR_ARG;
+    if (ctx->world > 1) { ctx->err = "rg_init_basis: single GPU only (the final row permutation is not sharded)"; return RG_ERR_STATE; }
+    const int m = ctx->m, n = ctx->n;
+    std::vector<char> seen(n, 0);
+    for (int i = 0; i < m; ++i) {
+        if (basis[i] < 0 || basis[i] >= n || seen[basis[i]]) { ctx->err = "rg_init_basis: basis must hold m distinct provider columns"; return RG_ERR_ARG; }
+        seen[basis[i]] = 1;
+    }
+    // all-artificial identity start, dense carry (the row permutation below breaks the implicit unit columns)
+    const int keep_opt = ctx->dense_carry_opt;
+    ctx->dense_carry_opt = 1;
+    std::vector<int> ids(m);
+    for (int i = 0; i < m; ++i) ids[i] = i - m;
+    int rc = rg_init_identity_basis(ctx, ids.data(), nullptr);
+    ctx->dense_carry_opt = keep_opt;
+    RG_TRY(rc);
+    // unit columns +e_r whose row is free: relabel only
+    std::vector<int> holder(m, -1);          // row -> provider column placed there
+    std::vector<int> pending;
+    for (int i = 0; i < m; ++i) {
+        const int j = basis[i];
+        const bool unit = j >= ctx->nd && ctx->h_colptr[j + 1] - ctx->h_colptr[j] == 1 && ctx->h_vals[ctx->h_colptr[j]] == 1;
+        const int r = unit ? ctx->h_rowidx[ctx->h_colptr[j]] : -1;
+        if (unit && holder[r] < 0) holder[r] = j; else pending.push_back(j);
+    }
+    {
+        std::vector<int> dev_basis(m);
+        for (int r = 0; r < m; ++r) dev_basis[r] = holder[r] >= 0 ? holder[r] : r - m;
+        CK(cudaMemcpyAsync(ctx->basis, dev_basis.data(), sizeof(int) * m, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        LAUNCH(k_set_inbasis, cdiv(m, 256), 256, ctx->inbasis, ctx->basis, m);
+    }
+    // the other columns: pivot each into a free row with a non-zero entry (its own position when possible)
+    std::vector<int> want_row(n, -1);
+    for (int i = 0; i < m; ++i) want_row[basis[i]] = i;
+    std::vector<uint64_t> col;
+    size_t stalled = 0;
+    while (!pending.empty()) {
+        const int j = pending.front();
+        pending.erase(pending.begin());
+        RG_TRY(rg_generate_column(ctx, j));
+        const int LU = LU_of(ctx->L);
+        col.assign((size_t)m * LU, 0);
+        RG_TRY(rg_get_pivot_column(ctx, col.data()));
+        auto nonzero = [&](int r) { for (int l = 0; l < LU; ++l) if (col[(size_t)r * LU + l]) return true; return false; };
+        int r = -1;
+        if (holder[want_row[j]] < 0 && nonzero(want_row[j])) r = want_row[j];
+        for (int t = 0; t < m && r < 0; ++t) if (holder[t] < 0 && nonzero(t)) r = t;
+        if (r < 0) {                      // no free row yet: try again after the others (singular if nobody moves)
+            pending.push_back(j);
+            if (++stalled > pending.size()) { ctx->err = "rg_init_basis: the basis columns are linearly dependent"; return RG_ERR_ARG; }
+            continue;
+        }
+        stalled = 0;
+        rg_pivot_info info;
+        RG_TRY(rg_bring_into_basis(ctx, j, r, 0, &info));
+        holder[r] = j;
+    }
+    // row i must hold basis[i]: gather the carry rows through the permutation
+    std::vector<int> perm(m);
+    bool identity = true;
+    {
+        std::vector<int> row_of(n, -1);
+        for (int r = 0; r < m; ++r) row_of[holder[r]] = r;
+        for (int i = 0; i < m; ++i) { perm[i] = row_of[basis[i]]; identity = identity && perm[i] == i; }
+    }
+    if (!identity) {
+        int* dperm = nullptr;
+        u64* nc = nullptr;
+        CK(dev_alloc(&dperm, sizeof(int) * m, ctx->stream));
+        CK(cudaMemcpyAsync(dperm, perm.data(), sizeof(int) * m, cudaMemcpyHostToDevice, ctx->stream));
+        CK(dev_alloc(&nc, sizeof(u64) * ctx->L * ctx->plane, ctx->stream));
+        dim3 grid(std::max(1, std::min(8, cdiv(ctx->ld, 256))), m + 1);
+        LAUNCH(k_permute_rows, grid, 256, nc, ctx->carry, ctx->plane, ctx->ld, m, ctx->L, dperm);
+        CK(cudaStreamSynchronize(ctx->stream));
+        free_dev_on(ctx->carry, ctx->stream); ctx->carry = nc;
+        free_dev_on(dperm, ctx->stream);
+        CK(cudaMemcpyAsync(ctx->basis, basis, sizeof(int) * m, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    if (ctx->weighted) LAUNCH(k_init_rowf, cdiv(m, 256), 256, ctx->basis, ctx->wf, ctx->artf, ctx->rowf, m);
+    ctx->identity_carry = false;
+    ctx->have_column = false; ctx->selected = false; ctx->rule_ready = false;
+    return rg_phase_switch(ctx, cost);
+}
+
 template <int L>
 static int launch_phase_sums_t(rg_context* ctx) {
     constexpr int LU = L + 2;
     const ColsumGeom g = colsum_geom(ctx);
-    dim3 grid(cdiv(g.ncols, 128), g.chunks);
+    dim3 grid(cdiv(g.ncols, 32), g.chunks);
     const BlockView bv = block_of(ctx);
     LAUNCH((k_colsum1<L, 1, LU>), grid, 128, bv.base, bv.ps, bv.stride, ctx->nloc, g.rpc, g.klist,
            ctx->svec, (size_t)ctx->ld, ctx->omega_part, g.pcols, ctx->sc);
     if (ctx->world == 1) {
         LAUNCH((k_colsum2<LU, 1>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, 2 * g.chunks, 1,
                ctx->tmprow, ctx->sc, g.triv, ctx->svec, (size_t)ctx->ld, L, g.kpos, g.pcols, 1);
+        if (ctx->list_mode)
+            LAUNCH((k_colsum2_list<LU>), g.ncols, 128, ctx->omega_part, 2 * g.chunks, g.pcols, g.klist, ctx->ld, 1,
+                   ctx->tmprow, ctx->sc);
         return RG_OK;
     }
     size_t words = (size_t)LU * ctx->ld;
     RG_TRY(ensure_xbuf(ctx, words, words * ctx->world));
     LAUNCH((k_colsum2<LU, 1>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, 2 * g.chunks, 0,
            ctx->xsend, ctx->sc, g.triv, ctx->svec, (size_t)ctx->ld, L, g.kpos, g.pcols, 1);
+    if (ctx->list_mode)
+        LAUNCH((k_colsum2_list<LU>), g.ncols, 128, ctx->omega_part, 2 * g.chunks, g.pcols, g.klist, ctx->ld, 0,
+               ctx->xsend, ctx->sc);
     RG_TRY(all_gather(ctx, ctx->xsend, ctx->xrecv, words));
     LAUNCH(k_reset_tmpbits, 1, 1, ctx->sc);
     LAUNCH((k_colsum2<LU>), cdiv(ctx->ld, 64), 64, ctx->xrecv, ctx->ld, ctx->world, 1, ctx->tmprow, ctx->sc);
@@ -1255,6 +1360,32 @@ static int launch_gamma_general(rg_context* ctx) {
     }
 }
 
+// steepest-edge weights on a general basis, one carry row at a time: stage the row like a pivot row, dot it with
+// every column (tensor-core path for the dense block), add the squares.  O(m) launches, used at a phase switch.
+template <int L>
+static int launch_gamma_rowwise_t(rg_context* ctx) {
+    LAUNCH((k_gamma_seed<L>), cdiv(ctx->n, 128), 128, ctx->n, own_of(ctx), ctx->inbasis,
+           ctx->weighted ? ctx->wf : nullptr, ctx->G, ctx->sc);
+    for (int row = 0; row < ctx->m; ++row) {
+        int local = (row >= ctx->row_lo && row < ctx->row_lo + ctx->nloc) ? row - ctx->row_lo + 1 : -1;
+        LAUNCH(k_set_rows, 1, 1, ctx->sc, local, row + 1);
+        RG_TRY(launch_copyrow(ctx));
+        launch_rowdot_t<L>(ctx);
+        LAUNCH((k_gamma_accum<L>), cdiv(ctx->n, 128), 128, ctx->n, own_of(ctx), ctx->inbasis, ctx->nu,
+               ctx->weighted ? ctx->rowf : nullptr, row, ctx->G, ctx->sc);
+    }
+    return RG_OK;
+}
+static int launch_gamma_rowwise(rg_context* ctx) {
+    switch (ctx->L) {
+        case 1: return launch_gamma_rowwise_t<1>(ctx);
+        case 2: return launch_gamma_rowwise_t<2>(ctx);
+        case 4: return launch_gamma_rowwise_t<4>(ctx);
+        case 8: return launch_gamma_rowwise_t<8>(ctx);
+        default: return launch_gamma_rowwise_t<16>(ctx);
+    }
+}
+
 extern "C" int rg_rule_new(rg_context* ctx, int32_t rule) {
     if (ctx) drop_graphs(ctx);   // state the captured launch sequence depends on may change
     if (!ctx || !ctx->carry || rule < 0 || rule > 3) return RG_ERR_ARG;
@@ -1272,8 +1403,8 @@ extern "C" int rg_rule_new(rg_context* ctx, int32_t rule) {
                        ctx->A.rowidx, ctx->A.vals, ctx->inbasis, ctx->weighted ? ctx->wf : nullptr,
                        ctx->weighted ? ctx->rowf : nullptr, ctx->G, LG_of(ctx->L));
         } else {
-            if (ctx->nd > 0) { ctx->err = "steepest-edge initialisation on a general basis is not implemented for the dense block"; return RG_ERR_STATE; }
-            RG_TRY(launch_gamma_general(ctx));
+            if (ctx->nd > 0) RG_TRY(launch_gamma_rowwise(ctx));   // dense block: row-wise dots on the tensor cores
+            else RG_TRY(launch_gamma_general(ctx));
         }
     }
     cudaMemsetAsync(&ctx->sc->last_selected, 0xff, sizeof(int), ctx->stream);

@@ -235,3 +235,110 @@ def test_zero_pivot_is_rejected():
             pytest.skip("no zero entry in this fixture")
         # the carry is untouched and still usable
         assert e.b() == t.im.b and e.minus_pi() == t.im.minus_pi
+
+
+# ---- general-basis constructor: from_basis (carry/mod.rs:444-478), BasisInverse::invert ---------------------
+def _state_matches(e, t, m, n, rule=None):
+    im = t.im
+    assert e.minus_objective() == im.minus_objective
+    assert e.minus_pi() == im.minus_pi
+    assert e.b() == im.b
+    assert e.basis() == im.basis_indices
+    for r in range(m):
+        assert e.basis_inverse_row(r) == _dense_row(im.rows[r], m), f"B^-1 row {r}"
+    if rule is not None:
+        g = e.gamma()
+        for j in range(n):
+            if rule.gamma[j] is not None:
+                assert g[j] == rule.gamma[j], f"gamma {j}"
+
+
+def _oracle_tableau_from_basis(provider, basis):
+    """oracle restatement of from_basis: basis[i] is the column basic in row i"""
+    carry = ro.Carry.from_basis_pivots([(i, j) for i, j in enumerate(basis)], provider)
+    return ro.Tableau(provider, carry, list(basis), None)
+
+
+@pytest.mark.parametrize("seed", range(4))
+@pytest.mark.parametrize("shuffle", [False, True])
+def test_init_basis_mid_solve_and_continue(seed, shuffle):
+    """Warm start: the basis an oracle solve has reached after a few pivots is handed to rg_init_basis (rows in
+    the oracle's order, or shuffled: exercises the device row permutation); the rebuilt carry equals the
+    oracle's from_basis carry entry by entry, and the continued solve walks the oracle's pivots."""
+    from relp_b200.generators import bounded_lp
+    from tests.common import provider_from_problem
+    from tests.gpu_engine import Engine
+    prob = bounded_lp(36, 48, k_bounding=10, nnz_per_col=5, seed=40 + seed)
+    provider = provider_from_problem(prob)
+    # reach a mid-solve basis with the oracle (phase two from the slack basis)
+    pivots = provider.pivot_element_indices()
+    t = ro.Tableau(provider, ro.Carry.from_basis_pivots(pivots, provider), [c for _, c in pivots], None)
+    rule = ro.SteepestDescentAlongObjective(t)
+    for _ in range(6):
+        sel = rule.select_primal_pivot_column(t)
+        if sel is None:
+            break
+        col = t.generate_column(sel[0])
+        p = t.select_primal_pivot_row(col)
+        info = t.bring_into_basis(sel[0], p, col, sel[1])
+        rule.after_basis_update(info, t)
+    basis = list(t.im.basis_indices)
+    if shuffle:
+        rng = np.random.default_rng(seed)
+        rng.shuffle(basis)
+    t2 = _oracle_tableau_from_basis(provider, basis)
+    cost = [int(provider.cost_value(j)) for j in range(prob.n)]
+    with Engine(prob, initial_limbs=1) as e:
+        e.init_basis(basis, cost)
+        rule2 = ro.SteepestDescentAlongObjective(t2)
+        e.rule_new("steepest_edge")                 # general-basis steepest-edge initialisation
+        _state_matches(e, t2, prob.m, prob.n, rule2)
+        # continue to the optimum in lockstep
+        steps = 0
+        while True:
+            sel = rule2.select_primal_pivot_column(t2)
+            q = e.select_column()
+            if sel is None:
+                assert q is None
+                break
+            assert q == sel[0]
+            col = t2.generate_column(q)
+            e.generate_column(q)
+            p = t2.select_primal_pivot_row(col)
+            assert e.select_row() == p
+            info = t2.bring_into_basis(q, p, col, sel[1])
+            e.bring_into_basis(q, p, True)
+            rule2.after_basis_update(info, t2)
+            steps += 1
+        _state_matches(e, t2, prob.m, prob.n, rule2)
+
+
+def test_init_basis_rejects_singular_basis():
+    from relp_b200.generators import bounded_lp
+    from tests.gpu_engine import Engine
+    prob = bounded_lp(12, 16, k_bounding=4, nnz_per_col=3, seed=3)
+    ns = prob.n - prob.m
+    # two structural columns with identical support cannot both... use a duplicated column id instead
+    basis = [ns + i for i in range(prob.m)]
+    basis[1] = basis[0]
+    with Engine(prob) as e:
+        with pytest.raises(RuntimeError, match="distinct"):
+            e.init_basis(basis, list(prob.cost))
+
+
+def test_steepest_edge_init_on_general_basis_with_dense_block():
+    """ADVICE r1: PivotRule::new(steepest edge) after phase-one pivots with a dense int8 block loaded (the
+    row-wise tensor-core initialisation).  Rows 0..3 get artificials (their slack pivots are withheld), so phase
+    one pivots before the phase-two rule is created; full trace / objective / solution against the oracle."""
+    import relp_b200
+    from relp_b200.generators import bounded_lp
+    from tests.common import oracle_trace, provider_from_problem
+    prob = bounded_lp(40, 56, k_bounding=12, dense=True, seed=21, dense_block=True, full_initial_basis=False)
+    prob.pivots = [rc for rc in prob.pivots if rc[0] >= 4]
+    provider = provider_from_problem(prob)
+    ores, otrace = oracle_trace(provider, "steepest_edge")
+    assert any(ph == 1 for ph, *_ in otrace)
+    for limbs in (1, 4):
+        g = relp_b200.solve_relaxation(prob, rule="steepest_edge", initial_limbs=limbs)
+        assert g.status == ores.status and g.trace == otrace
+        assert g.objective == ores.objective and g.bfs == ores.bfs

@@ -256,3 +256,15 @@ def test_steepest_edge_recurrence_matches_recompute():
     for prob in (problem_1(), problem_2()):
         r = ro.solve_relaxation(prob, Checked)
         assert r.status == "optimal"
+
+
+def test_from_basis_invert_fixtures():
+    """BasisInverseRows::invert fixtures of the reference (carry/basis_inverse_rows.rs:292-323): identity columns
+    give the identity; [TwoSlack((0,1),(1,1)), Slack((1,1))] gives rows e_0 and (-1, 1)."""
+    p = ro.ExplicitProvider(2, [[(0, 1)], [(1, 1)]], [0, 0], [1, 1])
+    c = ro.Carry.from_basis([0, 1], p)
+    assert rows_dense(c) == [fr(1, 0), fr(0, 1)]
+    p = ro.ExplicitProvider(2, [[(0, 1), (1, 1)], [(1, 1)]], [0, 0], [3, 5])
+    c = ro.Carry.from_basis([0, 1], p)
+    assert rows_dense(c) == [fr(1, 0), fr(-1, 1)]
+    assert c.b == fr(3, 2)
