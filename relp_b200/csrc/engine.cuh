@@ -37,6 +37,7 @@ struct Scalars {
     int rank, world;
     int nk;              // number of non-trivial carry columns (entries of klist), column 0 included
     int nnz_s;           // list mode: local rows with a non-zero work-vector factor (entries of nzrows)
+    int row0_ticket;     // k_ftran_row0: blocks finished (last one folds the slices)
     int fatal;           // why status became ST_FATAL: 1 overflow beyond 16 limbs, 2 kernel variant too narrow, 3 zero pivot element
     u64 D[RG_MAXL];          // current denominator (positive)
     u64 a[RG_MAXL + 2];      // pivot element numerator u[p] (replicated on every rank)
@@ -114,6 +115,7 @@ struct rg_context {
     int list_chunks = 0;             // row chunks of the column sums in list mode
     int list_pcols = 0;              // column slots of the list-mode partial sums
     long long* aq = nullptr;         // m: the entering column scattered densely (list-mode FTRAN)
+    u64* row0_part = nullptr;        // k_ftran_row0 slices: 32 x (RG_MAXL + 2) words
     bool list_mode = false;
     int nk_host = 1;                 // upper bound of sc->nk known to the host
     int dense_carry_opt = 0;         // rg_options: 1 = never use the active-column list

@@ -133,7 +133,7 @@ __global__ void k_init_scalars(u64* C, size_t ps, int m, int L, const long long*
     sc->row_lo = row_lo; sc->nloc = nloc; sc->rank = rank; sc->world = world; sc->nk = 1;
     sc->t = 0; sc->E = 0; sc->t2 = 0; sc->E2 = 0;
     sc->maxbits_carry = maxbits; sc->maxbits_new = 0; sc->maxbits_u = 0; sc->maxbits_rowp = 0;
-    sc->bits_D = 1; sc->predicted = 0; sc->last_selected = -1; sc->found = -1; sc->fatal = 0;
+    sc->bits_D = 1; sc->predicted = 0; sc->last_selected = -1; sc->found = -1; sc->fatal = 0; sc->row0_ticket = 0;
     for (int l = 0; l < RG_MAXL; ++l) { sc->D[l] = l == 0; sc->Dnew[l] = 0; }
 }
 
@@ -314,11 +314,11 @@ k_dense_combine(const int* __restrict__ R, size_t rstride_k, int kslices, int rp
     for (int l = 0; l < LO; ++l) res[l] = 0;
     if (!inbasis[j]) {
         long long carry = 0;
-        // not unrolled over the limbs: 8 LO copies of the slice loop cost minutes of compile time at LO = 39
-        // and nothing at run time (res[] goes through local memory; the kernel is a few microseconds)
-#pragma unroll 1
-        for (int l = 0; l < LO; ++l) {
-            u64 limb = 0;
+        // not unrolled over the limbs: 8 LO copies of the slice loop cost minutes of compile time at LO = 39.
+        // The 8 slice sums of the NEXT limb are fetched while the current limb's carry chain runs (the loop is
+        // otherwise one memory latency per limb).
+        long long cur[8], nxt[8];
+        auto fetch = [&](long long (&dst)[8], int l) {
 #pragma unroll
             for (int b = 0; b < 8; ++b) {
                 const int sidx = 8 * l + b;
@@ -327,11 +327,27 @@ k_dense_combine(const int* __restrict__ R, size_t rstride_k, int kslices, int rp
                     for (int k = 0; k < kslices; ++k) v += R[(size_t)k * rstride_k + (size_t)sidx * rpitch + (j - jd0)];
                     if (sidx == nb) v = -v;
                 }
-                long long tt = carry + v;
+                dst[b] = v;
+            }
+        };
+        fetch(cur, 0);
+#pragma unroll 1
+        for (int l = 0; l < LO; ++l) {
+            if (l + 1 < LO && 8 * (l + 1) <= nb) fetch(nxt, l + 1);
+            else {
+#pragma unroll
+                for (int b = 0; b < 8; ++b) nxt[b] = 0;
+            }
+            u64 limb = 0;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                long long tt = carry + cur[b];
                 limb |= (u64)(tt & 0xff) << (8 * b);
                 carry = tt >> 8;                    // arithmetic: keeps the sign
             }
             res[l] = limb;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) cur[b] = nxt[b];
         }
         if (cmul) {
             long long c = cost[j];
@@ -1047,34 +1063,29 @@ __global__ void k_scatter_col2(long long* __restrict__ aq, int nd, const long lo
     long long k = colptr[q] + blockIdx.x * blockDim.x + threadIdx.x;
     if (k < colptr[q + 1]) aq[rowidx[k]] = vals[k];
 }
-// cost-row entry of the pivot column: u_0 = c_q D + sum_k aq[k-1] C[0][k] over ALL columns (one block)
+// cost-row entry of the pivot column: u_0 = c_q D + sum_k aq[k-1] C[0][k] over ALL columns.  gridDim.x blocks each
+// reduce a slice of the columns into `scratch`; the last block to finish (ticket in sc->row0_ticket, zeroed by
+// k_reset_iter) adds the slices and the cost term.
+// cost == nullptr: plain dot of the (m+1)-vector C[.][1..m] with the scattered column (rg_get_element)
 template <int L>
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(256)
 k_ftran_row0(const u64* __restrict__ C, size_t ps, int m, const long long* __restrict__ aq,
-             const long long* __restrict__ cost, int qarg, u64* __restrict__ u, size_t us, Scalars* sc) {
-    // cost == nullptr: plain dot of the (m+1)-vector C[.][1..m] with the scattered column (rg_get_element)
+             const long long* __restrict__ cost, int qarg, u64* __restrict__ u, size_t us,
+             u64* __restrict__ scratch, Scalars* sc) {
     constexpr int LU = L + 2;
-    __shared__ u64 sAcc[32][LU];
+    __shared__ u64 sAcc[8][LU];
+    __shared__ int sLast;
     if (sc->status != ST_RUN) return;
     int q = qarg >= 0 ? qarg : sc->q;
     u64 acc[LU];
 #pragma unroll
     for (int l = 0; l < LU; ++l) acc[l] = 0;
-    for (int k = 1 + threadIdx.x; k <= m; k += blockDim.x) {
+    for (int k = 1 + blockIdx.x * blockDim.x + threadIdx.x; k <= m; k += gridDim.x * blockDim.x) {
         long long a = aq[k - 1];
         if (!a) continue;
         u64 x[L];
         load_planar<L>(x, C, ps, (size_t)k);
         mac_small<LU, L>(acc, x, a);
-    }
-    if (threadIdx.x == 0 && cost) {
-        long long c = cost[q];
-        if (c) {
-            u64 d[L];
-#pragma unroll
-            for (int l = 0; l < L; ++l) d[l] = sc->D[l];
-            mac_small<LU, L>(acc, d, c);
-        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -1096,9 +1107,34 @@ k_ftran_row0(const u64* __restrict__ C, size_t ps, int m, const long long* __res
             for (int l = 0; l < LU; ++l) other[l] = sAcc[w][l];
             add_n<LU>(acc, other);
         }
-        store_planar<LU>(u, us, (size_t)0, acc);
-        if (cost) atomicMax(&sc->maxbits_u, bitlen_signed<LU>(acc));
+#pragma unroll
+        for (int l = 0; l < LU; ++l) scratch[(size_t)blockIdx.x * LU + l] = acc[l];
+        __threadfence();
+        sLast = atomicAdd(&sc->row0_ticket, 1) == (int)gridDim.x - 1;
     }
+    __syncthreads();
+    if (!sLast || threadIdx.x != 0) return;
+    __threadfence();
+#pragma unroll
+    for (int l = 0; l < LU; ++l) acc[l] = 0;
+    for (int g = 0; g < (int)gridDim.x; ++g) {
+        u64 other[LU];
+#pragma unroll
+        for (int l = 0; l < LU; ++l) other[l] = __ldcg(&scratch[(size_t)g * LU + l]);
+        add_n<LU>(acc, other);
+    }
+    if (cost) {
+        long long c = cost[q];
+        if (c) {
+            u64 d[L];
+#pragma unroll
+            for (int l = 0; l < L; ++l) d[l] = sc->D[l];
+            mac_small<LU, L>(acc, d, c);
+        }
+    }
+    store_planar<LU>(u, us, (size_t)0, acc);
+    if (cost) atomicMax(&sc->maxbits_u, bitlen_signed<LU>(acc));
+    sc->row0_ticket = 0;                  // ready for the next launch (rg_get_element uses the kernel too)
 }
 // list-mode FTRAN: u_i = sum_{k in klist, k >= 1} aq[k-1] C[i][k]  +  [column i trivial] D aq[i-1]
 // (row 0 is dense: its warp walks all columns).  One warp per local carry row.
@@ -1155,7 +1191,7 @@ k_ftran_list(const u64* __restrict__ C, size_t ps, int ld, int nrows, int m, con
 }
 
 __global__ void k_reset_iter(Scalars* sc) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) { sc->maxbits_u = 0; sc->maxbits_rowp = 0; sc->maxbits_new = 0; sc->maxbits_tmp = 0; sc->nnz_s = 0; sc->maxbits_s = 0; }
+    if (threadIdx.x == 0 && blockIdx.x == 0) { sc->maxbits_u = 0; sc->maxbits_rowp = 0; sc->maxbits_new = 0; sc->maxbits_tmp = 0; sc->nnz_s = 0; sc->maxbits_s = 0; sc->row0_ticket = 0; }
 }
 __global__ void k_set_pq(Scalars* sc, int q, int p) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {

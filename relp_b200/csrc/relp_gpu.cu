@@ -286,7 +286,7 @@ extern "C" int rg_destroy(rg_context* ctx) {
     free_dev_on(ctx->carry, ctx->stream); free_dev_on(ctx->pk, ctx->stream); free_dev_on(ctx->A.colptr, ctx->stream); free_dev_on(ctx->A.rowidx, ctx->stream); free_dev_on(ctx->A.vals, ctx->stream);
     free_dev_on(ctx->cost, ctx->stream); free_dev_on(ctx->rhs, ctx->stream); free_dev_on(ctx->basis, ctx->stream); free_dev_on(ctx->inbasis, ctx->stream);
     free_dev_on(ctx->G, ctx->stream); free_dev_on(ctx->cand, ctx->stream); free_dev_on(ctx->score, ctx->stream); free_dev_on(ctx->sc, ctx->stream); free_dev_on(ctx->svec, ctx->stream);
-    free_dev_on(ctx->triv, ctx->stream); free_dev_on(ctx->klist, ctx->stream); free_dev_on(ctx->nzrows, ctx->stream); free_dev_on(ctx->kpos, ctx->stream); free_dev_on(ctx->aq, ctx->stream);
+    free_dev_on(ctx->triv, ctx->stream); free_dev_on(ctx->klist, ctx->stream); free_dev_on(ctx->nzrows, ctx->stream); free_dev_on(ctx->kpos, ctx->stream); free_dev_on(ctx->aq, ctx->stream); free_dev_on(ctx->row0_part, ctx->stream);
     free_dev_on(ctx->Acm, ctx->stream);
     free_dev_on(ctx->wf, ctx->stream); free_dev_on(ctx->wcol, ctx->stream); free_dev_on(ctx->artf, ctx->stream);
     free_dev_on(ctx->artcost, ctx->stream); free_dev_on(ctx->rowf, ctx->stream);
@@ -365,6 +365,7 @@ extern "C" int rg_load_csc(rg_context* ctx, int32_t m, int32_t n, const int64_t*
     CK(dev_alloc(&ctx->nzrows, sizeof(int) * ctx->ld, ctx->stream));
     CK(dev_alloc(&ctx->kpos, sizeof(int) * ctx->ld, ctx->stream));
     CK(dev_alloc(&ctx->aq, sizeof(long long) * m, ctx->stream));
+    CK(dev_alloc(&ctx->row0_part, sizeof(u64) * 32 * (RG_MAXL + 2), ctx->stream));
     CK(dev_alloc(&ctx->wf, sizeof(long long) * n, ctx->stream));
     CK(dev_alloc(&ctx->wcol, sizeof(long long) * n, ctx->stream));
     CK(dev_alloc(&ctx->artf, sizeof(long long) * m, ctx->stream));
@@ -634,8 +635,8 @@ static void launch_ftran_t(rg_context* ctx, int q) {
                ctx->A.vals, ctx->Acm, ctx->ldc, q, ctx->sc);
         LAUNCH(k_scatter_col2, cdiv(ctx->m, 256), 256, ctx->aq, ctx->nd, ctx->A.colptr, ctx->A.rowidx, ctx->A.vals,
                q, ctx->sc);
-        LAUNCH((k_ftran_row0<L>), 1, 1024, ctx->carry, ctx->plane, ctx->m, ctx->aq, ctx->cost, q, ctx->u,
-               (size_t)ctx->ld, ctx->sc);
+        LAUNCH((k_ftran_row0<L>), std::max(1, std::min(32, cdiv(ctx->m, 1024))), 256, ctx->carry, ctx->plane, ctx->m,
+               ctx->aq, ctx->cost, q, ctx->u, (size_t)ctx->ld, ctx->row0_part, ctx->sc);
         LAUNCH((k_ftran_list<L>), cdiv((long long)(ctx->nloc + 1) * 32, 256), 256, ctx->pk, ctx->pplane, ctx->cap,
                ctx->nloc + 1, ctx->m, ctx->aq, ctx->klist, ctx->triv, ctx->cost, q, ctx->u, (size_t)ctx->ld,
                ctx->sc);
@@ -1661,8 +1662,8 @@ static void launch_element_t(rg_context* ctx, int j) {
            ctx->A.vals, ctx->Acm, ctx->ldc, j, ctx->sc);
     LAUNCH(k_scatter_col2, cdiv(ctx->m, 256), 256, ctx->aq, ctx->nd, ctx->A.colptr, ctx->A.rowidx, ctx->A.vals, j,
            ctx->sc);
-    LAUNCH((k_ftran_row0<L>), 1, 1024, ctx->rowp, (size_t)ctx->ld, ctx->m, ctx->aq, (const long long*)nullptr, j,
-           ctx->tmprow, (size_t)ctx->ld, ctx->sc);
+    LAUNCH((k_ftran_row0<L>), std::max(1, std::min(32, cdiv(ctx->m, 1024))), 256, ctx->rowp, (size_t)ctx->ld, ctx->m,
+           ctx->aq, (const long long*)nullptr, j, ctx->tmprow, (size_t)ctx->ld, ctx->row0_part, ctx->sc);
 }
 extern "C" int rg_get_element(rg_context* ctx, int32_t row, int32_t j, uint64_t* out) {
     if (!ctx || !ctx->carry || !out || row < 0 || row >= ctx->m || j < 0 || j >= ctx->n) return RG_ERR_ARG;

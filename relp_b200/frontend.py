@@ -104,6 +104,27 @@ def parse_mps(text):
                 col_order=col_order, rhs=rhs, ranges=ranges, bounds=bounds)
 
 
+class Solution:
+    """`Solution` of the reference (data/linear_program/solution.rs:12-80): objective value and the value of
+    every variable of the ORIGINAL problem by name."""
+
+    def __init__(self, objective, values):
+        self.objective_value = objective
+        self.solution_values = list(values)          # [(name, Fraction)] in the file's column order
+
+    def is_probably_equal_to(self, other, min_equal):
+        """solution.rs:47-79: equal objective, equal variable names and more than `min_equal` of the values
+        equal (LPs with several optimal vertices: the reference's own tests compare like this)."""
+        if self.objective_value != other.objective_value:
+            return False
+        a, b = dict(self.solution_values), dict(other.solution_values)
+        if len(self.solution_values) != len(other.solution_values) or set(a) != set(b):
+            return False
+        if len(a) < 10:
+            return True
+        return sum(1 for k in a if a[k] == b[k]) / len(a) > min_equal
+
+
 class CanonicalLP:
     """min c x + constant over the MatrixData layout; `recover` maps a reduced solution back."""
 
@@ -116,13 +137,37 @@ class CanonicalLP:
         self.upper = []
         self.constant = Fraction(0)
         self.var_map = []      # per canonical column: (original column, +1 / -1, shift)
+        self.col_order = []    # original variable names, file order
+        self.fixed = {}        # original variables fixed by their bounds (substituted out): name -> value
         self.name = ""
+
+
+def recover(lp, bfs, objective):
+    """Solution back-substitution (reference: MatrixData::reconstruct_solution, matrix_data.rs:402-411, keeps the
+    structural columns of the basic feasible solution; GeneralForm::compute_full_solution_with_reduced_solution +
+    reshift_solution, general_form/mod.rs:808-935, undo the shifts, sign flips, free-variable splits and
+    substituted fixed variables of the canonicalisation).
+
+    lp: CanonicalLP; bfs: [(provider column, value)] of the solved MatrixData; objective: its optimum.
+    Returns a `Solution` over the original variables (file order) with the constant added back."""
+    nv = len(lp.constraint_columns)
+    reduced = {j: v for j, v in bfs if j < nv}                 # slack / bound-slack columns are dropped
+    values = {name: Fraction(fixed) for name, fixed in lp.fixed.items()}
+    for k, (orig, sign, shift) in enumerate(lp.var_map):
+        x = reduced.get(k, Fraction(0))
+        if orig in values and orig not in lp.fixed:
+            values[orig] += sign * x                           # second half of a split free variable
+        else:
+            values[orig] = shift + sign * x
+    return Solution(objective + lp.constant, [(name, values[name]) for name in lp.col_order])
 
 
 def canonicalize(mps):
     """MPS dict -> CanonicalLP (no presolve)."""
     lp = CanonicalLP()
     lp.name = mps["name"]
+    lp.col_order = list(mps["col_order"])
+    lp.fixed = {}
     rows, row_type = mps["rows"], mps["row_type"]
     obj = mps["objective"]
     rhs = {r: mps["rhs"].get(r, Fraction(0)) for r in rows}
@@ -158,6 +203,7 @@ def canonicalize(mps):
                         if interval[r][k] is not INF:
                             interval[r][k] -= v * shift
             if up is not None and up == 0:
+                lp.fixed[col] = lo
                 continue   # fixed variable: substituted out
             new_cols.append((entries, cost, up, (col, 1, shift)))
         elif hi is not INF:
