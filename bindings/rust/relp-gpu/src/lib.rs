@@ -5,15 +5,14 @@
 //! (`data.solve_relaxation::<Carry<RationalBig, LUDecomposition<RationalBig>>>()`, tests/netlib/mod.rs:62):
 //!
 //! ```ignore
-//! use relp_gpu::{GpuCarry, solve_relaxation_gpu};
-//! let result = solve_relaxation_gpu(&matrix_data);          // OptimizationResult<RationalBig>
+//! use relp_gpu::{GpuCarry, GpuSteepestEdge};
+//! // with the 10-line twin `solve_relaxation_with::<IM, PR>` added to relp:
+//! let result = matrix_data.solve_relaxation_with::<GpuCarry, GpuSteepestEdge>();
 //! ```
 //!
-//! `solve_relaxation_gpu` is `two_phase::solve_relaxation` (two_phase/mod.rs:25-109) with
-//! `IM = GpuCarry` and `PR = GpuSteepestEdge`; relp hard-codes `SteepestDescentAlongObjective` there
-//! (two_phase/mod.rs:57,68,107) and keeps `phase_one::primal` crate-private (phase_one.rs:123), so the twin
-//! function below restates those 60 lines of control flow against relp's PUBLIC tableau API.  Nothing in
-//! relp's signatures changes.
+//! relp hard-codes `SteepestDescentAlongObjective` in `two_phase::solve_relaxation` (two_phase/mod.rs:57,68,107)
+//! and keeps `phase_one::primal` crate-private (phase_one.rs:123), so choosing the device rule needs that twin
+//! (or the specialisation of the blanket impl for `IM = GpuCarry`); no existing signature changes.
 //!
 //! This crate is NOT compiled in the engine's repository (no Rust toolchain in its build image); see
 //! Cargo.toml.  The C++ host driver `relp_b200/csrc/host/relp_host.cpp` runs the same call sequence under

@@ -114,6 +114,10 @@ const char* rg_last_error(const rg_context* ctx);
  * rank.  Returns the id size (128) or an error. */
 int rg_nccl_unique_id(void* out, int32_t bytes);
 
+/* The block partition used for the carry rows (count = m) and for the priced columns (count = number of dense /
+ * CSC columns): rank r owns [first, first + number).  Pure host arithmetic, no context or device needed. */
+int rg_shard_block(int32_t count, int32_t world, int32_t rank, int32_t* first, int32_t* number);
+
 /* ---- problem upload: MatrixProvider (matrix_provider/mod.rs:37-134) ---------------------------- */
 /* All provider columns as integer CSC (column(j), :52), row indices ascending within a column.  */
 int rg_load_csc(rg_context* ctx, int32_t m, int32_t n, const int64_t* colptr,

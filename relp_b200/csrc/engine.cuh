@@ -120,6 +120,8 @@ struct rg_context {
     int nk_host = 1;                 // upper bound of sc->nk known to the host
     int dense_carry_opt = 0;         // rg_options: 1 = never use the active-column list
     u64* us2 = nullptr;         // LU+1 planes x ld    pivot column times row factors^2 (weighted problems)
+    u64* ufull = nullptr;       // LU+1 planes x ld    row-sharded runs: the whole factor vector (all-gathered blocks)
+    bool ufull_valid = false;
     // weights of a prescaled rational problem; all 1 for integer problems
     bool weighted = false;
     long long* wf = nullptr;      // n: W / w_j
@@ -135,6 +137,7 @@ struct rg_context {
     signed char* Acm = nullptr; size_t ldc = 0;    // [nd][ldc]
     int* dR = nullptr; size_t dR_words = 0;        // tensor-core dense dots: slice-by-column s32 products
     unsigned char* dSl = nullptr; int* dchunk = nullptr; size_t dmp = 0;   // byte slices of the vector, chunk flags
+    int* dR2 = nullptr; unsigned char* dSl2 = nullptr; int* dchunk2 = nullptr;   // second scratch set: pricing dot
     long long* cost = nullptr;  // n
     long long* rhs = nullptr;   // m
     int* basis = nullptr;       // m column ids

@@ -390,7 +390,7 @@ k_sigma_add_dtau(const u64* __restrict__ tau, int n, int jd0, int jd1, const uns
         for (int l = 0; l < LT; ++l) { u64 v = ~t[l] + c; c = (c && v == 0) ? 1 : 0; t[l] = v; }
     }
 #pragma unroll
-    for (int l = 0; l < L; ++l) d[l] = sc->D[l];
+    for (int l = 0; l < L; ++l) d[l] = sc->Dold[l];     // the denominator the work vector was built with
     u64 p[LT + L];
     mul_full_ct<LT, L>(p, t, d);          // |tau| * D, D > 0
     u64 sg[LS];
@@ -505,6 +505,10 @@ k_gamma_init_identity_dense(int nd, int n, int m, const signed char* __restrict_
 struct ColOwn {
     int nd, d0, d1, s0, s1;
     __host__ __device__ bool owned(int j) const { return j < nd ? (j >= d0 && j < d1) : (j >= s0 && j < s1); }
+    // the owned columns enumerated densely: t in [0, count()) -> column (kernels that do real work per column are
+    // launched over this range, so a rank's threads are all busy in column-sharded runs)
+    __host__ __device__ int count() const { return (d1 - d0) + (s1 - s0); }
+    __host__ __device__ int at(int t) const { return t < d1 - d0 ? d0 + t : s0 + (t - (d1 - d0)); }
 };
 struct PriceView {
     const u64* kappa; int LU; int n;
@@ -1191,7 +1195,10 @@ k_ftran_list(const u64* __restrict__ C, size_t ps, int ld, int nrows, int m, con
 }
 
 __global__ void k_reset_iter(Scalars* sc) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) { sc->maxbits_u = 0; sc->maxbits_rowp = 0; sc->maxbits_new = 0; sc->maxbits_tmp = 0; sc->nnz_s = 0; sc->maxbits_s = 0; sc->row0_ticket = 0; }
+    if (threadIdx.x == 0 && blockIdx.x == 0) { sc->maxbits_u = 0; sc->maxbits_rowp = 0; sc->maxbits_new = 0; sc->maxbits_tmp = 0; sc->nnz_s = 0; sc->maxbits_s = 0; sc->row0_ticket = 0;
+        // the denominator this iteration starts from: side-stream kernels (split sigma dot) read it while the main
+        // stream's bookkeeping may already have installed the new one
+        for (int l = 0; l < RG_MAXL; ++l) sc->Dold[l] = sc->D[l]; }
 }
 __global__ void k_set_pq(Scalars* sc, int q, int p) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
@@ -1327,7 +1334,8 @@ __device__ inline void warp_mul_lo(u64* r, const u64* a, const u64* b, int n, u6
 // Ghat' = [a^2 Ghat - 2 a nu sigma + nu^2 Gq] / D^2 is evaluated mod 2^(64 WX) with the 2-adic inverse of
 // odd(D)^2 and a final shift by 2t (pivot_rule.rs:243-296 in integer form).  WX = LG + max(E2, 4) so that
 // the fixed-width update kernel can be used whenever D^2 has at most 256 trailing zero bits.
-__global__ void __launch_bounds__(32) k_scalars_se(int L, const u64* __restrict__ G, int n, Scalars* sc) {
+__global__ void __launch_bounds__(32) k_scalars_se(int L, const u64* __restrict__ G, int n, const int* __restrict__ basis,
+                                                   Scalars* sc) {
     __shared__ u64 am[RG_MAXW], dodd[RG_MAXW], x[RG_MAXW], tt[RG_MAXW], xn[RG_MAXW], i2[RG_MAXW],
         ax[RG_MAXW], tmp[RG_MAXW], cols[3 * RG_MAXW];
     if (sc->status != ST_RUN) return;
@@ -1341,6 +1349,9 @@ __global__ void __launch_bounds__(32) k_scalars_se(int L, const u64* __restrict_
     if (E2 < 4) E2 = 4;
     const int WX = LG + E2;
     if (lane == 0) {
+        // the leaving column is known as soon as the row is: the weight recurrence (side stream) skips it and runs
+        // before k_finalize's bookkeeping
+        if (sc->pg >= 1) sc->leaving = basis[sc->pg - 1];
         sc->t2 = t2; sc->E2 = E2;
         for (int l = 0; l < WX; ++l) { tmp[l] = l < LU ? sc->a[l] : 0; dodd[l] = l < L ? sc->D[l] : 0; }
         rt_abs(am, tmp, LU);                           // |a| (LU limbs; the new denominator)
@@ -1431,7 +1442,7 @@ __global__ void k_finalize(int* basis, unsigned char* inbasis, int L, u64* G, in
             inbasis[leaving] = 0;
             if (want_se) for (int l = 0; l < LG; ++l) G[(size_t)l * n + leaving] = sc->Gq[l];
         }
-        for (int l = 0; l < L; ++l) { sc->Dold[l] = sc->D[l]; sc->D[l] = sc->Dnew[l]; }
+        for (int l = 0; l < L; ++l) sc->D[l] = sc->Dnew[l];
         sc->bits_D = rt_bitlen_u(sc->D, L);
         sc->maxbits_carry = max(sc->maxbits_new, sc->bits_D);     // implicit diagonals hold D
         hm->pivoted = 1; hm->q_done = sc->q; hm->p_done = sc->pg; hm->leaving_done = leaving;
@@ -1904,6 +1915,9 @@ k_scale_u(const u64* __restrict__ u, size_t us, int nloc, const long long* __res
     store_planar<LU + 1>(out, os, (size_t)i, acc);
     int bl = warp_max(i >= 1 ? bitlen_signed<LU + 1>(acc) : 0);
     if ((threadIdx.x & 31) == 0 && bl) atomicMax(&sc->maxbits_s, bl);
+    // row-sharded: the other ranks' rows are not seen here; maxbits_u is already the maximum over all ranks
+    // (k_ratio_merge) and the row factors are below 2^31, so this bounds every rank's entries
+    if (sc->world > 1 && blockIdx.x == 0 && threadIdx.x == 0) atomicMax(&sc->maxbits_s, sc->maxbits_u + 62);
 }
 
 // basic cost of every local row as an (nloc+1)-vector of LSRC = 1 limb (artificial / inert rows: 0)
@@ -2172,8 +2186,9 @@ k_gamma_update_t(int n, ColOwn own, const unsigned char* __restrict__ inbasis, c
                  const u64* __restrict__ sigma, u64* __restrict__ G, const Scalars* sc) {
     constexpr int LU = L + 2, LS = 2 * L + 7, LG = 2 * L + 6, WX = LG + 4, N = 2 * WX;
     if (sc->status != ST_RUN) return;
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n || !own.owned(j)) return;
+    const int tix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tix >= own.count()) return;
+    const int j = own.at(tix);
     if (inbasis[j] || j == sc->leaving) return;   // entering: None; leaving: set by k_finalize
     u32 nv[N], x[N];
     {
@@ -2249,8 +2264,9 @@ __global__ void __launch_bounds__(128)
 k_gamma_update(int n, ColOwn own, int L, const unsigned char* __restrict__ inbasis, const u64* __restrict__ nu,
                const u64* __restrict__ sigma, u64* __restrict__ G, const Scalars* sc) {
     if (sc->status != ST_RUN) return;
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n || !own.owned(j)) return;
+    const int tix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tix >= own.count()) return;
+    const int j = own.at(tix);
     if (inbasis[j] || j == sc->leaving) return;   // entering: None; leaving: set by k_finalize
     const int LU = L + 2, LS = 2 * L + 7, LG = 2 * L + 6;
     const int WX = LG + sc->E2;

@@ -139,6 +139,13 @@ static int alloc_dense_scratch(rg_context* ctx, int L) {
     ctx->dR_words = words;
     CK(dev_alloc(&ctx->dSl, (size_t)(LW_of(L) + 1) * 8 * ctx->dmp, ctx->stream));
     CK(dev_alloc(&ctx->dchunk, sizeof(int) * (ctx->dmp / 64), ctx->stream));
+    {   // a second, smaller set for the pricing dot (L-limb cost row): it runs on the main stream while the
+        // steepest-edge dots and the weight update still occupy the first set on their side stream
+        DenseGeom g = dense_geom(ctx, L);
+        CK(dev_alloc(&ctx->dR2, sizeof(int) * g.rstride_k * g.ks, ctx->stream));
+        CK(dev_alloc(&ctx->dSl2, (size_t)(L + 1) * 8 * ctx->dmp, ctx->stream));
+        CK(dev_alloc(&ctx->dchunk2, sizeof(int) * (ctx->dmp / 64), ctx->stream));
+    }
     return RG_OK;
 }
 static int alloc_width_buffers(rg_context* ctx, int L) {
@@ -155,6 +162,10 @@ static int alloc_width_buffers(rg_context* ctx, int L) {
     }
     CK(dev_alloc(&ctx->tmprow, sizeof(u64) * LU_of(L) * ld, ctx->stream));
     CK(dev_alloc(&ctx->us2, sizeof(u64) * (LU_of(L) + 1) * ld, ctx->stream));
+    if (ctx->world > 1) {
+        CK(dev_alloc(&ctx->ufull, sizeof(u64) * (LU_of(L) + 1) * ld, ctx->stream));
+        CK(cudaMemsetAsync(ctx->ufull, 0, sizeof(u64) * (LU_of(L) + 1) * ld, ctx->stream));
+    }
     if (ctx->nd > 0) RG_TRY(alloc_dense_scratch(ctx, L));
     CK(dev_alloc(&ctx->kappa, sizeof(u64) * LU_of(L) * n, ctx->stream));
     CK(dev_alloc(&ctx->nu, sizeof(u64) * LU_of(L) * n, ctx->stream));
@@ -175,7 +186,9 @@ static int alloc_width_buffers(rg_context* ctx, int L) {
 }
 static void free_width_buffers(rg_context* ctx) {
     free_dev_on(ctx->u, ctx->stream); free_dev_on(ctx->rowp, ctx->stream); free_dev_on(ctx->omega, ctx->stream); free_dev_on(ctx->omega_part, ctx->stream);
-    free_dev_on(ctx->tmprow, ctx->stream); free_dev_on(ctx->us2, ctx->stream); free_dev_on(ctx->dR, ctx->stream); free_dev_on(ctx->dSl, ctx->stream); free_dev_on(ctx->dchunk, ctx->stream); free_dev_on(ctx->kappa, ctx->stream); free_dev_on(ctx->nu, ctx->stream); free_dev_on(ctx->sigma, ctx->stream); free_dev_on(ctx->tau, ctx->stream); ctx->tau = nullptr;
+    free_dev_on(ctx->tmprow, ctx->stream); free_dev_on(ctx->us2, ctx->stream); free_dev_on(ctx->ufull, ctx->stream); ctx->ufull = nullptr; free_dev_on(ctx->dR, ctx->stream); free_dev_on(ctx->dSl, ctx->stream); free_dev_on(ctx->dchunk, ctx->stream);
+    free_dev_on(ctx->dR2, ctx->stream); free_dev_on(ctx->dSl2, ctx->stream); free_dev_on(ctx->dchunk2, ctx->stream);
+    ctx->dR2 = nullptr; ctx->dSl2 = nullptr; ctx->dchunk2 = nullptr; free_dev_on(ctx->kappa, ctx->stream); free_dev_on(ctx->nu, ctx->stream); free_dev_on(ctx->sigma, ctx->stream); free_dev_on(ctx->tau, ctx->stream); ctx->tau = nullptr;
     free_dev_on(ctx->xsend, ctx->stream); free_dev_on(ctx->xrecv, ctx->stream);
     ctx->xsend = ctx->xrecv = nullptr; ctx->xbytes = 0;
     ctx->u = ctx->rowp = ctx->omega = ctx->omega_part = ctx->tmprow = ctx->us2 = nullptr; ctx->dR = nullptr; ctx->dSl = nullptr; ctx->dchunk = nullptr;
@@ -314,6 +327,17 @@ extern "C" int rg_destroy(rg_context* ctx) {
 
 extern "C" const char* rg_last_error(const rg_context* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
+// The partition of the row-sharded engine, pure host arithmetic shared by rg_load_csc /
+// rg_load_dense_i8 and by the Python side (relp_b200/sharding.py calls these, so the gloo tests cover the very
+// functions the device path uses): rank r owns the block [r*q, min(count, (r+1)*q)), q = ceil(count / world).
+extern "C" int rg_shard_block(int32_t count, int32_t world, int32_t rank, int32_t* first, int32_t* number) {
+    if (count < 0 || world < 1 || rank < 0 || rank >= world || !first || !number) return RG_ERR_ARG;
+    const int q = (count + world - 1) / world;
+    *first = std::min(count, rank * q);
+    *number = std::max(0, std::min(count, (rank + 1) * q) - *first);
+    return RG_OK;
+}
+
 extern "C" int rg_load_csc(rg_context* ctx, int32_t m, int32_t n, const int64_t* colptr,
                            const int32_t* rowidx, const int64_t* vals) {
     if (!ctx || m <= 0 || n <= 0 || !colptr) return RG_ERR_ARG;
@@ -321,16 +345,13 @@ extern "C" int rg_load_csc(rg_context* ctx, int32_t m, int32_t n, const int64_t*
     if (ctx->carry) { ctx->err = "rg_load_csc: context already holds a problem"; return RG_ERR_STATE; }
     ctx->m = m; ctx->n = n;
     ctx->ld = ((m + 1 + 15) / 16) * 16;
-    {   // block row partition: rank r owns constraint rows [r*q, min(m,(r+1)*q)), q = ceil(m / world)
-        int q = (m + ctx->world - 1) / ctx->world;
-        ctx->row_lo = std::min(m, ctx->rank * q);
-        ctx->nloc = std::max(0, std::min(m, (ctx->rank + 1) * q) - ctx->row_lo);
-    }
-    ctx->d0 = ctx->d1 = 0;          // no dense block yet: all columns are CSC columns
-    {
-        int cq = (n + ctx->world - 1) / ctx->world;
-        ctx->s0 = std::min(n, ctx->rank * cq);
-        ctx->s1 = std::min(n, (ctx->rank + 1) * cq);
+    {   // block row partition of the carry; block column partition of the pricing
+        int32_t first = 0, number = 0;
+        rg_shard_block(m, ctx->world, ctx->rank, &first, &number);
+        ctx->row_lo = first; ctx->nloc = number;
+        ctx->d0 = ctx->d1 = 0;          // no dense block yet: all columns are CSC columns
+        rg_shard_block(n, ctx->world, ctx->rank, &first, &number);
+        ctx->s0 = first; ctx->s1 = first + number;
     }
     long long nnz = colptr[n];
     ctx->A.nnz = nnz;
@@ -401,12 +422,11 @@ extern "C" int rg_load_dense_i8(rg_context* ctx, int32_t nd, const int8_t* colma
                          ctx->stream));
     ctx->nd = nd;
     {   // column ownership: the dense block and the CSC columns are split separately (balanced cost)
-        int dq = (nd + ctx->world - 1) / ctx->world;
-        ctx->d0 = std::min(nd, ctx->rank * dq);
-        ctx->d1 = std::min(nd, (ctx->rank + 1) * dq);
-        int ns = ctx->n - nd, cq = (ns + ctx->world - 1) / ctx->world;
-        ctx->s0 = nd + std::min(ns, ctx->rank * cq);
-        ctx->s1 = nd + std::min(ns, (ctx->rank + 1) * cq);
+        int32_t first = 0, number = 0;
+        rg_shard_block(nd, ctx->world, ctx->rank, &first, &number);
+        ctx->d0 = first; ctx->d1 = first + number;
+        rg_shard_block(ctx->n - nd, ctx->world, ctx->rank, &first, &number);
+        ctx->s0 = nd + first; ctx->s1 = nd + first + number;
     }
     RG_TRY(alloc_dense_scratch(ctx, ctx->L));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -581,7 +601,10 @@ static void launch_coldots(rg_context* ctx, const u64* vec, size_t vs, int cmul,
 }
 template <int L>
 static void launch_price_t(rg_context* ctx) {
+    // pricing uses its own tensor-core scratch set (see alloc_dense_scratch)
+    if (ctx->dR2) { std::swap(ctx->dR, ctx->dR2); std::swap(ctx->dSl, ctx->dSl2); std::swap(ctx->dchunk, ctx->dchunk2); }
     launch_coldots<L, L + 2>(ctx, ctx->carry, ctx->plane, 1, ctx->kappa, &ctx->sc->maxbits_carry);
+    if (ctx->dR2) { std::swap(ctx->dR, ctx->dR2); std::swap(ctx->dSl, ctx->dSl2); std::swap(ctx->dchunk, ctx->dchunk2); }
 }
 static void launch_price(rg_context* ctx) { DISPATCH_L(ctx->L, launch_price_t, ctx); }
 
@@ -726,6 +749,27 @@ static ColsumGeom colsum_geom(rg_context* ctx) {
     g.rpc = cdiv(std::max(ctx->nloc, 1), g.chunks);
     return g;
 }
+__global__ void k_gather(u64* out, const u64* base, size_t stride, size_t idx0, size_t step, int count, int nl);
+// row-sharded runs: the factor vector (pivot column u, or its weighted form) is computed per row block; the split
+// sigma dot needs it on every rank, so the blocks are all-gathered into `ufull` (planar, LSRCV limbs x ld)
+__global__ void k_assemble_factor(u64* __restrict__ ufull, int ld, const u64* __restrict__ recv, int q, int nl, int m) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;     // global constraint row
+    if (g >= m) return;
+    const u64* src = recv + ((size_t)(g / q) * q + (g % q)) * nl;
+    for (int l = 0; l < nl; ++l) ufull[(size_t)l * ld + 1 + g] = src[l];
+}
+static int gather_factor(rg_context* ctx, const u64* src, int nl) {
+    const int q = cdiv(ctx->m, ctx->world);
+    const size_t words = (size_t)q * nl;
+    RG_TRY(ensure_xbuf(ctx, words, words * ctx->world));
+    CK(cudaMemsetAsync(ctx->xsend, 0, words * sizeof(u64), ctx->stream));
+    if (ctx->nloc > 0)
+        LAUNCH(k_gather, cdiv(ctx->nloc, 256), 256, ctx->xsend, src, (size_t)ctx->ld, (size_t)1, (size_t)1, ctx->nloc, nl);
+    RG_TRY(all_gather(ctx, ctx->xsend, ctx->xrecv, words));
+    LAUNCH(k_assemble_factor, cdiv(ctx->m, 256), 256, ctx->ufull, ctx->ld, ctx->xrecv, q, nl, ctx->m);
+    return RG_OK;
+}
+
 template <int L>
 static int launch_work_t(rg_context* ctx) {
     constexpr int LU = L + 2, LW = 2 * L + 5;
@@ -739,6 +783,12 @@ static int launch_work_t(rg_context* ctx) {
         LAUNCH((k_scale_u<L>), cdiv(ctx->nloc + 1, 256), 256, ctx->u, (size_t)ctx->ld, ctx->nloc, ctx->rowf,
                ctx->us2, (size_t)ctx->ld, ctx->sc);
         src = ctx->us2;
+    }
+    // the split sigma dot of a row-sharded run reads the whole factor vector
+    ctx->ufull_valid = false;
+    if (ctx->world > 1 && ctx->list_mode && ctx->d1 > ctx->d0) {
+        RG_TRY(gather_factor(ctx, src, ctx->weighted ? LU + 1 : LU));
+        ctx->ufull_valid = true;
     }
     // stage 1: thread = column (dense carry) or list position (packed active block: every load coalesced),
     // rows in chunks, rows with a zero factor skipped; stage 2 sums the chunks and adds the implicit
@@ -821,17 +871,18 @@ template <int L>
 static void launch_se_dots_t(rg_context* ctx) {
     constexpr int LU = L + 2, LW = LW_of(L), LS = LS_of(L);
     launch_coldots<L, LU>(ctx, ctx->rowp, (size_t)ctx->ld, 0, ctx->nu, &ctx->sc->maxbits_rowp);
-    if (ctx->list_mode && ctx->d1 > ctx->d0 && ctx->world == 1) {
+    if (ctx->list_mode && ctx->d1 > ctx->d0 && (ctx->world == 1 || ctx->ufull_valid)) {
+        const u64* fvec = ctx->world == 1 ? (ctx->weighted ? ctx->us2 : ctx->u) : ctx->ufull;
         // split sigma dot over the dense block: the work vector on the trivial carry columns
         // is D * s_k, so the wide (2L+5 limb) vector only has to cover the LISTED columns (a few 64-row chunks: the
         // others are skipped as zero) and the long dot runs on the (L+2)-limb factor vector s -- half the slices
         launch_coldots<LW, LS>(ctx, ctx->omega, (size_t)ctx->ld, 0, ctx->sigma, &ctx->sc->maxbits_tmp, 2, true);
         if (ctx->weighted) {
-            launch_coldots<LU + 1, LU + 3>(ctx, ctx->us2, (size_t)ctx->ld, 0, ctx->tau, &ctx->sc->maxbits_s, 1, false);
+            launch_coldots<LU + 1, LU + 3>(ctx, fvec, (size_t)ctx->ld, 0, ctx->tau, &ctx->sc->maxbits_s, 1, false);
             LAUNCH((k_sigma_add_dtau<LU + 3, L, LS>), cdiv(ctx->d1 - ctx->d0, 128), 128, ctx->tau, ctx->n, ctx->d0, ctx->d1,
                    ctx->inbasis, ctx->sigma, ctx->sc);
         } else {
-            launch_coldots<LU, LU + 2>(ctx, ctx->u, (size_t)ctx->ld, 0, ctx->tau, &ctx->sc->maxbits_u, 1, false);
+            launch_coldots<LU, LU + 2>(ctx, fvec, (size_t)ctx->ld, 0, ctx->tau, &ctx->sc->maxbits_u, 1, false);
             LAUNCH((k_sigma_add_dtau<LU + 2, L, LS>), cdiv(ctx->d1 - ctx->d0, 128), 128, ctx->tau, ctx->n, ctx->d0, ctx->d1,
                    ctx->inbasis, ctx->sigma, ctx->sc);
         }
@@ -841,8 +892,8 @@ static void launch_se_dots_t(rg_context* ctx) {
 }
 template <int L>
 static void launch_gamma_update_t(rg_context* ctx) {
-    LAUNCH((k_gamma_update_t<L>), cdiv(ctx->n, 64), 64, ctx->n, own_of(ctx), ctx->inbasis, ctx->nu, ctx->sigma,
-           ctx->G, ctx->sc);
+    LAUNCH((k_gamma_update_t<L>), cdiv(std::max(own_of(ctx).count(), 1), 64), 64, ctx->n, own_of(ctx), ctx->inbasis,
+           ctx->nu, ctx->sigma, ctx->G, ctx->sc);
 }
 // nu_j = rowp . a_j and sigma_j = omega . a_j read only staged vectors and the constraint matrix, so they run
 // on the second side stream concurrently with K1 (LAUNCH goes to ctx->stream: swapped for the duration)
@@ -863,8 +914,8 @@ static void launch_se_update(rg_context* ctx) {
             default: launch_gamma_update_t<8>(ctx); break;
         }
     } else {
-        LAUNCH(k_gamma_update, cdiv(ctx->n, 128), 128, ctx->n, own_of(ctx), ctx->L, ctx->inbasis, ctx->nu, ctx->sigma,
-               ctx->G, ctx->sc);
+        LAUNCH(k_gamma_update, cdiv(std::max(own_of(ctx).count(), 1), 128), 128, ctx->n, own_of(ctx), ctx->L,
+               ctx->inbasis, ctx->nu, ctx->sigma, ctx->G, ctx->sc);
     }
     if (ctx->profile >= 2) rec_event(ctx, ctx->evp[6]);    // after the recurrence
 }
@@ -960,7 +1011,7 @@ static int enqueue_iteration(rg_context* ctx, int q, int fixed_row, bool want_se
         cudaStreamWaitEvent(ctx->side3, ctx->ev_side0, 0);
         k_scalars<<<1, 1, 0, ctx->side>>>(ctx->L, E, ctx->sc);
         cudaEventRecord(ctx->ev_side2, ctx->side);
-        k_scalars_se<<<1, 32, 0, ctx->side3>>>(ctx->L, ctx->world == 1 ? ctx->G : nullptr, ctx->n, ctx->sc);
+        k_scalars_se<<<1, 32, 0, ctx->side3>>>(ctx->L, ctx->world == 1 ? ctx->G : nullptr, ctx->n, ctx->basis, ctx->sc);
         ctx->launches += 2;
         cudaEventRecord(ctx->ev_side1, ctx->side3);
         RG_TRY(launch_work(ctx));
@@ -968,6 +1019,16 @@ static int enqueue_iteration(rg_context* ctx, int q, int fixed_row, bool want_se
         cudaEventRecord(ctx->ev_work, ctx->stream);
         cudaStreamWaitEvent(ctx->side2, ctx->ev_work, 0);
         launch_se_dots(ctx);
+        // the weight recurrence follows the dots on the same side stream (it needs the steepest-edge scalars
+        // too); the main stream runs K1, the bookkeeping and the pricing of the next iteration meanwhile and
+        // joins before the column selection
+        cudaStreamWaitEvent(ctx->side2, ctx->ev_side1, 0);
+        {
+            cudaStream_t main_stream = ctx->stream;
+            ctx->stream = ctx->side2;
+            launch_se_update(ctx);
+            ctx->stream = main_stream;
+        }
         cudaEventRecord(ctx->ev_side3, ctx->side2);
         cudaStreamWaitEvent(ctx->stream, ctx->ev_side2, 0);
     } else {
@@ -977,16 +1038,14 @@ static int enqueue_iteration(rg_context* ctx, int q, int fixed_row, bool want_se
     if (prof1) rec_event(ctx, ctx->ev0);
     launch_update(ctx, E);
     if (prof1) rec_event(ctx, ctx->ev1);
-    if (want_se) {
-        cudaStreamWaitEvent(ctx->stream, ctx->ev_side1, 0);
-        cudaStreamWaitEvent(ctx->stream, ctx->ev_side3, 0);
-    }
+    if (want_se) cudaStreamWaitEvent(ctx->stream, ctx->ev_side1, 0);     // k_finalize stores Ghat_q of k_scalars_se
     LAUNCH(k_finalize, 1, 1, ctx->basis, ctx->inbasis, ctx->L, ctx->G, ctx->n, LG_of(ctx->L),
            want_se ? 1 : 0, ctx->weighted ? ctx->wf : nullptr, ctx->weighted ? ctx->rowf : nullptr, ctx->sc,
            ctx->hm_dev);
-    if (want_se) launch_se_update(ctx);
     if (prof) rec_event(ctx, ctx->evp[3]);
-    if (reselect) { launch_price(ctx); RG_TRY(launch_select(ctx)); }
+    if (reselect) launch_price(ctx);
+    if (want_se) cudaStreamWaitEvent(ctx->stream, ctx->ev_side3, 0);     // dots + weight recurrence done
+    if (reselect) RG_TRY(launch_select(ctx));
     if (prof) rec_event(ctx, ctx->evp[4]);
     return RG_OK;
 }

@@ -6,16 +6,23 @@ The carry rows are block-distributed exactly as `rg_load_csc` does it on the dev
 
 
 def row_block(m, world, rank):
-    """(first row, number of rows) of `rank`'s block."""
-    q = -(-m // world)
-    lo = min(m, rank * q)
-    hi = min(m, (rank + 1) * q)
-    return lo, hi - lo
+    """(first row, number of rows) of `rank`'s block: asks the engine library itself (`rg_shard_block`, the
+    function `rg_load_csc` partitions with), so a device-side partition bug cannot hide behind a restatement."""
+    import ctypes as C
+    from . import _lib
+    first, number = C.c_int32(), C.c_int32()
+    rc = _lib.load().rg_shard_block(m, world, rank, C.byref(first), C.byref(number))
+    if rc != 0:
+        raise ValueError(f"rg_shard_block({m}, {world}, {rank}) failed: {rc}")
+    return first.value, number.value
 
 
 def owner_of_row(m, world, row):
-    q = -(-m // world)
-    return row // q
+    for rank in range(world):
+        lo, n = row_block(m, world, rank)
+        if lo <= row < lo + n:
+            return rank
+    raise ValueError("row out of range")
 
 
 def share_unique_id(dist, make_id, device=None):

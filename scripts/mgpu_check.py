@@ -32,6 +32,10 @@ def main():
         ("bounded dense 30x40", bounded_lp(30, 40, k_bounding=10, dense=True, seed=1), ["steepest_edge"], 1),
         ("max flow 24", max_flow(24, 3, 3, 9), ["steepest_edge", "first_profitable"], 2),
         ("bounded 300x600", bounded_lp(300, 600, k_bounding=40, nnz_per_col=6, seed=2), ["steepest_edge"], 2),
+        ("dense block 200x120", bounded_lp(200, 120, k_bounding=20, dense=True, seed=3, dense_block=True),
+         ["steepest_edge"], 1),
+        ("limb sweep 256x512", bounded_lp(256, 512, k_bounding=160, dense=True, seed=2, dense_block=True),
+         ["steepest_edge"], 1),
     ]
     try:
         from tests.test_gpu_parity import random_matrix_data
