@@ -208,23 +208,21 @@ __device__ inline void rt_mul_full(u64* r, const u64* a, int na, const u64* b, i
         r[i + nb] += carry;   // r[i+nb] was zero or small enough: classic schoolbook invariant
     }
 }
-// low product r[n] = a[n]*b[n] mod 2^(64n); r must not alias a or b
+// r = a*b mod 2^(64 n); r must not alias a or b.  Product scanning: column k is summed into a 3-word accumulator
+// and written once -- no read-modify-write of r through local memory, and the operand loads of a column do not
+// depend on the accumulation chain (the operand-scanning form was bound by its load-add-store chain on r).
 __device__ inline void rt_mul_lo(u64* r, const u64* a, const u64* b, int n) {
-    for (int k = 0; k < n; ++k) r[k] = 0;
-    for (int i = 0; i < n; ++i) {
-        u64 carry = 0;
-        u64 ai = a[i];
-        if (ai == 0) continue;
-        for (int j = 0; i + j < n; ++j) {
-            u64 lo = ai * b[j];
-            u64 hi = __umul64hi(ai, b[j]);
-            u64 v = r[i + j] + lo;
-            u64 c1 = v < lo;
-            u64 v2 = v + carry;
-            u64 c2 = v2 < v;
-            r[i + j] = v2;
-            carry = hi + c1 + c2;
+    u64 c0 = 0, c1 = 0, c2 = 0;
+    for (int k = 0; k < n; ++k) {
+        int i = 0;
+        for (; i + 1 <= k; i += 2) {
+            const u64 a0 = a[i], b0 = b[k - i], a1 = a[i + 1], b1 = b[k - i - 1];
+            mac3(c0, c1, c2, a0, b0);
+            mac3(c0, c1, c2, a1, b1);
         }
+        if (i <= k) mac3(c0, c1, c2, a[i], b[k - i]);
+        r[k] = c0;
+        c0 = c1; c1 = c2; c2 = 0;
     }
 }
 __device__ inline void rt_add(u64* a, const u64* b, int n) {

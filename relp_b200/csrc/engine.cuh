@@ -1,5 +1,6 @@
 // Device-side state shared by all kernels of the exact simplex engine.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstddef>
 #include <cstdint>
@@ -138,6 +139,10 @@ struct rg_context {
     int* dR = nullptr; size_t dR_words = 0;        // tensor-core dense dots: slice-by-column s32 products
     unsigned char* dSl = nullptr; int* dchunk = nullptr; size_t dmp = 0;   // byte slices of the vector, chunk flags
     int* dR2 = nullptr; unsigned char* dSl2 = nullptr; int* dchunk2 = nullptr;   // second scratch set: pricing dot
+    // tcgen05 path of the dense dots (dense_umma.cuh): TMA descriptors of the int8 block and of the two slice buffers
+    CUtensorMap mapA, mapB, mapB2;
+    bool umma_ok = false;
+    unsigned char* dSl_primary = nullptr;      // the first set's slice buffer (tells the sets apart while they are swapped)
     long long* cost = nullptr;  // n
     long long* rhs = nullptr;   // m
     int* basis = nullptr;       // m column ids

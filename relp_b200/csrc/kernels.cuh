@@ -415,6 +415,10 @@ k_sigma_add_dtau(const u64* __restrict__ tau, int n, int jd0, int jd1, const uns
     store_planar<LS>(sigma, (size_t)n, (size_t)j, sg);
 }
 
+}  // namespace rg
+#include "dense_umma.cuh"
+namespace rg {
+
 // FTRAN of a dense column q (column-major copy): warp per carry row, lanes over the rows of a_q
 template <int L>
 __global__ void __launch_bounds__(256)

@@ -121,12 +121,39 @@ static DenseGeom dense_geom(rg_context* ctx, int LV) {
     int ks = 296 / std::max(1, cdiv(std::max(g.ncols, 1), 128) * g.zs);
     ks = std::max(1, std::min(8, ks));
     ks = std::max(ks, cdiv(mp, 32768));
-    g.rps = (cdiv(mp, ks) + 63) / 64 * 64;
+    g.rps = (cdiv(mp, ks) + 127) / 128 * 128;        // whole 128-row K blocks (tcgen05 path) = whole 64-row chunks
     g.ks = cdiv(mp, g.rps);
     g.rpitch = std::max(g.ncols, 1);
     g.rstride_k = (size_t)nt_max * 8 * g.rpitch;
     return g;
 }
+// TMA descriptor of a row-major u8 matrix [outer][inner] (row pitch `pitch` bytes), box 128 x box_outer, 128-byte
+// swizzle.  cuTensorMapEncodeTiled is resolved through the runtime (no link-time dependency on libcuda).
+static bool make_map_u8(CUtensorMap* map, const void* base, size_t inner, size_t outer, size_t pitch, int box_outer) {
+    typedef CUresult (*Fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                           const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                           CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static Fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (Fn)p;
+        (void)cudaGetLastError();
+    }
+    if (!fn) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+    cuuint64_t strides[1] = {(cuuint64_t)pitch};
+    cuuint32_t box[2] = {128u, (cuuint32_t)box_outer};
+    cuuint32_t estr[2] = {1u, 1u};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static int alloc_dense_scratch(rg_context* ctx, int L) {
     if (ctx->nd <= 0) return RG_OK;
     ctx->dmp = ((size_t)ctx->m + 63) / 64 * 64;
@@ -137,14 +164,31 @@ static int alloc_dense_scratch(rg_context* ctx, int L) {
     }
     CK(dev_alloc(&ctx->dR, sizeof(int) * words, ctx->stream));
     ctx->dR_words = words;
-    CK(dev_alloc(&ctx->dSl, (size_t)(LW_of(L) + 1) * 8 * ctx->dmp, ctx->stream));
+    const size_t sl_rows = std::max<size_t>((size_t)(LW_of(L) + 1) * 8, UM_N), sl2_rows = std::max<size_t>((size_t)(L + 1) * 8, UM_N);
+    CK(dev_alloc(&ctx->dSl, sl_rows * ctx->dmp, ctx->stream));
+    CK(cudaMemsetAsync(ctx->dSl, 0, sl_rows * ctx->dmp, ctx->stream));
+    ctx->dSl_primary = ctx->dSl;
     CK(dev_alloc(&ctx->dchunk, sizeof(int) * (ctx->dmp / 64), ctx->stream));
     {   // a second, smaller set for the pricing dot (L-limb cost row): it runs on the main stream while the
         // steepest-edge dots and the weight update still occupy the first set on their side stream
         DenseGeom g = dense_geom(ctx, L);
         CK(dev_alloc(&ctx->dR2, sizeof(int) * g.rstride_k * g.ks, ctx->stream));
-        CK(dev_alloc(&ctx->dSl2, (size_t)(L + 1) * 8 * ctx->dmp, ctx->stream));
+        CK(dev_alloc(&ctx->dSl2, sl2_rows * ctx->dmp, ctx->stream));
+        CK(cudaMemsetAsync(ctx->dSl2, 0, sl2_rows * ctx->dmp, ctx->stream));
         CK(dev_alloc(&ctx->dchunk2, sizeof(int) * (ctx->dmp / 64), ctx->stream));
+    }
+    // tcgen05 path (dense_umma.cuh): worthwhile from a few 128 x 128 tiles on; RG_NO_UMMA=1 keeps the mma.sync kernel
+    const bool no_umma = getenv("RG_NO_UMMA") != nullptr;
+    ctx->umma_ok = !no_umma && ctx->m >= 512 && ctx->nd >= 256 && ctx->ldc >= 128 &&
+                   make_map_u8(&ctx->mapA, ctx->Acm, ctx->ldc, (size_t)ctx->nd, ctx->ldc, UM_M) &&
+                   make_map_u8(&ctx->mapB, ctx->dSl, ctx->dmp, sl_rows, ctx->dmp, UM_N) &&
+                   make_map_u8(&ctx->mapB2, ctx->dSl2, ctx->dmp, sl2_rows, ctx->dmp, UM_N);
+    if (ctx->umma_ok) {
+        static bool attr_done = false;
+        if (!attr_done) {
+            attr_done = cudaFuncSetAttribute(k_dense_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UM_SMEM) == cudaSuccess;
+            if (!attr_done) { ctx->umma_ok = false; (void)cudaGetLastError(); }
+        }
     }
     return RG_OK;
 }
@@ -589,9 +633,21 @@ static void launch_coldots(rg_context* ctx, const u64* vec, size_t vs, int cmul,
         LAUNCH((k_dense_slices<LV>), (unsigned)(ctx->dmp / 64), 64, vec, vs, ctx->m, bits, ctx->dSl, ctx->dmp,
                ctx->dchunk, ctx->sc, mask ? (const unsigned char*)ctx->triv : (const unsigned char*)nullptr,
                mask == 1 ? 1 : 0);
-        dim3 grid(cdiv(g.ncols, 128), g.ks, g.zs);
-        LAUNCH((k_dense_mma<NTC>), grid, 256, ctx->Acm, ctx->ldc, jd0, jd1, ctx->dSl, ctx->dmp, ctx->dchunk, bits, LV,
-               g.rps, ctx->dR, g.rstride_k, g.rpitch, ctx->sc);
+        if (ctx->umma_ok) {
+            // tcgen05: 128 columns x 160 slice rows per CTA, TMA-fed, accumulators in TMEM
+            dim3 ugrid(cdiv(g.ncols, UM_M), g.ks, cdiv(NT_MAX * 8, UM_N));
+            const CUtensorMap& mb = ctx->dSl == ctx->dSl_primary ? ctx->mapB : ctx->mapB2;
+            k_dense_umma<<<ugrid, 128, UM_SMEM, ctx->stream>>>(ctx->mapA, mb, jd0, jd1, ctx->dmp, ctx->dchunk, bits, LV,
+                                                              g.rps, ctx->dR, g.rstride_k, g.rpitch, ctx->sc);
+            ctx->launches++;
+            cudaError_t e__ = cudaPeekAtLastError();
+            if (e__ != cudaSuccess && ctx->launch_err.empty())
+                ctx->launch_err = std::string("launch of k_dense_umma failed: ") + cudaGetErrorString(e__);
+        } else {
+            dim3 grid(cdiv(g.ncols, 128), g.ks, g.zs);
+            LAUNCH((k_dense_mma<NTC>), grid, 256, ctx->Acm, ctx->ldc, jd0, jd1, ctx->dSl, ctx->dmp, ctx->dchunk, bits, LV,
+                   g.rps, ctx->dR, g.rstride_k, g.rpitch, ctx->sc);
+        }
         LAUNCH((k_dense_combine<LV, LO>), cdiv(g.ncols, 128), 128, ctx->dR, g.rstride_k, g.ks, g.rpitch, ctx->n, jd0,
                jd1, bits, ctx->inbasis, ctx->cost, cmul, ctx->L, out, ctx->sc);
     }

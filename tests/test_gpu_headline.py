@@ -223,3 +223,27 @@ def test_limb_sweep_dense_block_wide():
     g, ref = _solve_both(prob, initial_limbs=1)
     _assert_same(g, ref)
     assert g.stats["limbs"] == 16
+
+
+@pytest.mark.parametrize("limbs", [1, 16])
+def test_tcgen05_dense_dots_match_mma_sync_and_oracle(limbs, monkeypatch):
+    """The dense dots run as tcgen05.mma.kind::i8 (TMA-fed, TMEM accumulators; dense_umma.cuh) once the block has
+    a few 128 x 128 tiles; RG_NO_UMMA=1 keeps the mma.sync kernel.  Both must walk the oracle's pivots -- from one
+    limb (promotions) and from 16 limbs (the widest slice layouts: 38 tiles over two TMEM layers)."""
+    import relp_b200
+    from oracle import fast_oracle as fo
+    from relp_b200.generators import bounded_lp
+    prob = bounded_lp(1100, 640, k_bounding=24, dense=True, seed=9, dense_block=True)
+    fo.set_threads(0)
+    ref = fo.solve_problem(prob, "steepest_edge")
+    assert ref.status == "optimal"
+    runs = []
+    for no_umma in (False, True):
+        if no_umma:
+            monkeypatch.setenv("RG_NO_UMMA", "1")
+        else:
+            monkeypatch.delenv("RG_NO_UMMA", raising=False)
+        g = relp_b200.solve_relaxation(prob, rule="steepest_edge", initial_limbs=limbs)
+        _assert_same(g, ref)
+        runs.append(g.trace)
+    assert runs[0] == runs[1]
