@@ -1508,16 +1508,42 @@ struct ColTerms {
         if constexpr (I + 1 < NA && I + 1 <= K) ColTerms<NA, NB, K, I + 1>::run(c0, c1, c2, x, m);
     }
 };
+template <int NA, int NB, int K, int I>
+struct ColPair {     // term I of column K (x_I m_{K-I}) and term I of column K+1 (x_I m_{K+1-I}), then I+1
+    __device__ static __forceinline__ void run(u32& a0, u32& a1, u32& a2, u32& b0, u32& b1, u32& b2, const u32 (&x)[NA],
+                                               const u32 (&m)[NB]) {
+        if constexpr (I < NA && K - I >= 0 && K - I < NB)
+            asm volatile("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, %2, 0;"
+                         : "+r"(a0), "+r"(a1), "+r"(a2) : "r"(x[I]), "r"(m[K - I]));
+        if constexpr (I < NA && K + 1 - I >= 0 && K + 1 - I < NB)
+            asm volatile("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, %2, 0;"
+                         : "+r"(b0), "+r"(b1), "+r"(b2) : "r"(x[I]), "r"(m[K + 1 - I]));
+        if constexpr (I + 1 < NA && I + 1 <= K + 1) ColPair<NA, NB, K, I + 1>::run(a0, a1, a2, b0, b1, b2, x, m);
+    }
+};
+
+// Two columns at a time: columns K and K+1 are summed into independent 3-word accumulators (two IMAD.WIDE chains
+// that ptxas interleaves: a single chain is bound by the latency of the dependent accumulate), then folded:
+// limb K = a0, limb K+1 = a1 + b0, and (a2 + b1 + carry, b2 + carry) seed the next pair.
 template <int NA, int NB, int NW, int K>
 struct ColScan {
-    __device__ static __forceinline__ void run(u32 (&acc)[NW], u32& c0, u32& c1, u32& c2, const u32 (&x)[NA],
+    __device__ static __forceinline__ void run(u32 (&acc)[NW], u32& s0, u32& s1, u32& s2, const u32 (&x)[NA],
                                                const u32 (&m)[NB]) {
-        // the running sum's limb K joins the column accumulator
+        static_assert(NW % 2 == 0 && K % 2 == 0, "columns are taken in pairs");
+        u32 a0 = s0, a1 = s1, a2 = s2, b0 = 0, b1 = 0, b2 = 0;
+        // the running sum's limbs K and K+1 join the column accumulators
         asm volatile("add.cc.u32 %0, %0, %3;\n\taddc.cc.u32 %1, %1, 0;\n\taddc.u32 %2, %2, 0;"
-                     : "+r"(c0), "+r"(c1), "+r"(c2) : "r"(acc[K]));
-        if constexpr (K < NA + NB - 1) ColTerms<NA, NB, K, (K - NB + 1 > 0 ? K - NB + 1 : 0)>::run(c0, c1, c2, x, m);
-        acc[K] = c0; c0 = c1; c1 = c2; c2 = 0;
-        if constexpr (K + 1 < NW) ColScan<NA, NB, NW, K + 1>::run(acc, c0, c1, c2, x, m);
+                     : "+r"(a0), "+r"(a1), "+r"(a2) : "r"(acc[K]));
+        b0 = acc[K + 1];
+        // the terms of the two columns are emitted alternately (the inline-asm statements keep their order)
+        ColPair<NA, NB, K, (K - NB + 1 > 0 ? K - NB + 1 : 0)>::run(a0, a1, a2, b0, b1, b2, x, m);
+        acc[K] = a0;
+        u32 t0, t1, t2;
+        asm volatile("add.cc.u32 %0, %3, %4;\n\taddc.cc.u32 %1, %5, %6;\n\taddc.u32 %2, %7, 0;"
+                     : "=r"(t0), "=r"(t1), "=r"(t2) : "r"(a1), "r"(b0), "r"(a2), "r"(b1), "r"(b2));
+        acc[K + 1] = t0;
+        s0 = t1; s1 = t2; s2 = 0;
+        if constexpr (K + 2 < NW) ColScan<NA, NB, NW, K + 2>::run(acc, s0, s1, s2, x, m);
     }
 };
 
