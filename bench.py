@@ -307,7 +307,7 @@ def main():
         return relp_b200.solve_relaxation(prob, rule=args.rule, device=local, profile=prof_level, rank=rank,
                                           world=world, nccl_id=nid)
 
-    prof_level = 1      # timed steps: CUDA events around K1 only (the roofline kernel)
+    prof_level = int(os.environ.get("BENCH_PROFILE", "1"))   # timed steps: CUDA events around K1 only (the roofline kernel)
 
     sampler = ClockSampler(local)
     sampler.start()

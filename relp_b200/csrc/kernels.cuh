@@ -1692,7 +1692,9 @@ k_colsum1(const u64* __restrict__ C, size_t ps, int ld, int m, int rows_per_chun
 template <int LOUT>
 __global__ void __launch_bounds__(128)
 k_colsum2_list(const u64* __restrict__ part, int nslabs, int pcols, const int* __restrict__ klist, int ld,
-               int negate, u64* __restrict__ out, Scalars* sc) {
+               int negate, u64* __restrict__ out, Scalars* sc, int packed_stride = 0) {
+    // packed_stride != 0 (row-sharded split mode): the sums are written by list position, plane stride packed_stride,
+    // for the small all-gather of the listed columns' partial sums (k_list_sum_scatter finishes them)
     __shared__ u64 sW[4][LOUT];
     if (sc->status != ST_RUN) return;
     const int t = blockIdx.x;
@@ -1727,9 +1729,36 @@ k_colsum2_list(const u64* __restrict__ part, int nslabs, int pcols, const int* _
             add_n<LOUT>(acc, o);
         }
         if (negate) neg_n<LOUT>(acc);
-        store_planar<LOUT>(out, (size_t)ld, (size_t)klist[t], acc);
-        atomicMax(&sc->maxbits_tmp, bitlen_signed<LOUT>(acc));
+        if (packed_stride) store_planar<LOUT>(out, (size_t)packed_stride, (size_t)t, acc);
+        else {
+            store_planar<LOUT>(out, (size_t)ld, (size_t)klist[t], acc);
+            atomicMax(&sc->maxbits_tmp, bitlen_signed<LOUT>(acc));
+        }
     }
+}
+// row-sharded split mode: sum the ranks' packed partial sums of the listed columns and scatter them into the
+// work vector (thread = list position)
+template <int LOUT>
+__global__ void __launch_bounds__(128)
+k_list_sum_scatter(const u64* __restrict__ recv, int world, int packed_stride, const int* __restrict__ klist, int ld,
+                   u64* __restrict__ out, Scalars* sc) {
+    if (sc->status != ST_RUN) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int bl = 0;
+    if (t < sc->nk) {
+        u64 acc[LOUT];
+#pragma unroll
+        for (int l = 0; l < LOUT; ++l) acc[l] = 0;
+        for (int r = 0; r < world; ++r) {
+            u64 x[LOUT];
+            load_planar<LOUT>(x, recv + (size_t)r * LOUT * packed_stride, (size_t)packed_stride, (size_t)t);
+            add_n<LOUT>(acc, x);
+        }
+        store_planar<LOUT>(out, (size_t)ld, (size_t)klist[t], acc);
+        bl = bitlen_signed<LOUT>(acc);
+    }
+    bl = warp_max(bl);
+    if ((threadIdx.x & 31) == 0 && bl) atomicMax(&sc->maxbits_tmp, bl);
 }
 
 // List mode, stage 0: compact the local rows whose factor s_i is non-zero (order is irrelevant: the sums
@@ -1837,7 +1866,10 @@ template <int LOUT, int LSRC = 1, int LDT = 0>
 __global__ void __launch_bounds__(64)
 k_colsum2(const u64* __restrict__ part, int ld, int chunks, int negate, u64* __restrict__ out,
           Scalars* sc, const unsigned char* __restrict__ triv = nullptr, const u64* __restrict__ s = nullptr,
-          size_t ss = 0, int LD = 0, const int* __restrict__ kpos = nullptr, int pcols = 0, int alt = 0) {
+          size_t ss = 0, int LD = 0, const int* __restrict__ kpos = nullptr, int pcols = 0, int alt = 0,
+          int global_s = 0) {
+    // global_s != 0 (row-sharded split mode): `s` is the WHOLE factor vector (all-gathered), so every rank writes
+    // the implicit columns' sums s_k * D itself and no exchange of them is needed
     if (sc->status != ST_RUN) return;
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     int bl = 0;
@@ -1847,8 +1879,8 @@ k_colsum2(const u64* __restrict__ part, int ld, int chunks, int negate, u64* __r
 #pragma unroll
         for (int l = 0; l < LOUT; ++l) acc[l] = 0;
         if (triv && triv[k]) {
-            int li = k - sc->row_lo;               // local carry row of the diagonal entry
-            if (li >= 1 && li <= sc->nloc) {
+            int li = global_s ? k : k - sc->row_lo;   // (local) carry row of the diagonal entry
+            if (li >= 1 && (global_s || li <= sc->nloc)) {
                 u64 x[LSRC];
                 load_planar<LSRC>(x, s, ss, (size_t)li);
                 u64 any = 0;

@@ -842,9 +842,34 @@ static int launch_work_t(rg_context* ctx) {
     }
     // the split sigma dot of a row-sharded run reads the whole factor vector
     ctx->ufull_valid = false;
-    if (ctx->world > 1 && ctx->list_mode && ctx->d1 > ctx->d0) {
+    if (ctx->world > 1 && ctx->list_mode) {
         RG_TRY(gather_factor(ctx, src, ctx->weighted ? LU + 1 : LU));
         ctx->ufull_valid = true;
+    }
+    if (ctx->world > 1 && ctx->ufull_valid) {
+        // row-sharded split mode: the implicit columns' sums come from the all-gathered factor vector on every rank,
+        // and only the LISTED columns' partial sums are exchanged (nk_grid x (2L+5) words per rank instead of the
+        // whole (2L+5) x ld vector)
+        const BlockView bv2 = block_of(ctx);
+        const size_t pwords = (size_t)LW * ctx->nk_grid;
+        RG_TRY(ensure_xbuf(ctx, pwords, pwords * ctx->world));
+        if (ctx->weighted) {
+            LAUNCH((k_colsum1<L, LU + 1, LW>), grid, 128, bv2.base, bv2.ps, bv2.stride, ctx->nloc, g.rpc,
+                   g.klist, ctx->us2, (size_t)ctx->ld, ctx->omega_part, g.pcols, ctx->sc);
+            LAUNCH((k_colsum2<LW, LU + 1, L>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, 2 * g.chunks, 0,
+                   ctx->omega, ctx->sc, g.triv, (const u64*)ctx->ufull, (size_t)ctx->ld, L, g.kpos, g.pcols, 1, 1);
+        } else {
+            LAUNCH((k_colsum1<L, LU, LW>), grid, 128, bv2.base, bv2.ps, bv2.stride, ctx->nloc, g.rpc,
+                   g.klist, ctx->u, (size_t)ctx->ld, ctx->omega_part, g.pcols, ctx->sc);
+            LAUNCH((k_colsum2<LW, LU, L>), cdiv(ctx->ld, 64), 64, ctx->omega_part, ctx->ld, 2 * g.chunks, 0,
+                   ctx->omega, ctx->sc, g.triv, (const u64*)ctx->ufull, (size_t)ctx->ld, L, g.kpos, g.pcols, 1, 1);
+        }
+        LAUNCH((k_colsum2_list<LW>), g.ncols, 128, ctx->omega_part, 2 * g.chunks, g.pcols, g.klist, ctx->ld, 0,
+               ctx->xsend, ctx->sc, ctx->nk_grid);
+        RG_TRY(all_gather(ctx, ctx->xsend, ctx->xrecv, pwords));
+        LAUNCH((k_list_sum_scatter<LW>), cdiv(ctx->nk_grid, 128), 128, ctx->xrecv, ctx->world, ctx->nk_grid, g.klist,
+               ctx->ld, ctx->omega, ctx->sc);
+        return RG_OK;
     }
     // stage 1: thread = column (dense carry) or list position (packed active block: every load coalesced),
     // rows in chunks, rows with a zero factor skipped; stage 2 sums the chunks and adds the implicit
