@@ -319,7 +319,8 @@ def main():
     dev_ms = 0.0
     e2e_s = 0.0
     launches = 0
-    k1 = {key: [0.0] * 5 for key in ("ms", "n", "bytes", "imads")}
+    NW = _lib.RG_NWIDTHS
+    k1 = {key: [0.0] * NW for key in ("ms", "n", "bytes", "imads")}
     for _ in range(args.steps):
         g = step()
         assert g.status == "optimal"
@@ -327,7 +328,7 @@ def main():
         dev_ms += g.device_ms
         e2e_s += g.seconds_total
         launches += g.stats["kernel_launches"]
-        for k in range(5):
+        for k in range(NW):
             k1["ms"][k] += g.stats["k1_ms_at_limbs"][k]
             k1["n"][k] += g.stats["k1_launches_at_limbs"][k]
             k1["bytes"][k] += g.stats["k1_bytes_at_limbs"][k]
@@ -369,7 +370,8 @@ def main():
         # and multiply-adds of every launch (tracked per pivot from the list length and the exact-division
         # width in use) over its CUDA-event time.  Roofline time = max(bytes / HBM peak, IMAD / IMAD peak).
         by_limbs = {}
-        for k in range(5):
+        widths = g.stats["limb_widths"]
+        for k in range(NW):
             if k1["n"][k]:
                 t = k1["ms"][k] * 1e-3
                 gbs = k1["bytes"][k] / t / 1e9
@@ -383,9 +385,9 @@ def main():
                     ent["roofline_frac"] = max(ent["hbm_frac"], ent["imad_frac"])
                 else:
                     ent["roofline_frac"] = ent["hbm_frac"]
-                by_limbs[str(1 << k)] = ent
-        dom = max(range(5), key=lambda k: k1["ms"][k])
-        Ldom = 1 << dom
+                by_limbs[str(widths[k])] = ent
+        dom = max(range(NW), key=lambda k: k1["ms"][k])
+        Ldom = widths[dom]
         d = by_limbs[str(Ldom)]
         imad_bound = imad_peak is not None and d.get("imad_frac", 0) >= d["hbm_frac"]
         traffic = None
@@ -426,7 +428,8 @@ def main():
             "vs_baseline": None, "dtype": "int (two's complement multi-limb u64, 2-16 limbs)",
             "data": "synthetic", "config": workload_config(args, world),
             "time_to_optimal_ms": dev_ms_max / args.steps, "pivots_per_solve": pivots / args.steps,
-            "limb_histogram": g.stats["pivots_at_limbs"],
+            "limb_histogram": dict(zip(map(str, g.stats["limb_widths"]), g.stats["pivots_at_limbs"])),
+            "promotions": g.stats["promotions"], "demotions": g.stats["demotions"],
             "e2e": {"value": pivots_all / e2e_max, "unit": "pivots/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches_all), "clocks": clocks, "roofline": roof, "wall_s": wall,

@@ -63,7 +63,7 @@ enum {
 
 typedef struct rg_options {
     int32_t device;          /* CUDA device ordinal */
-    int32_t initial_limbs;   /* 1, 2, 4, 8 or 16; 0 = default (2) */
+    int32_t initial_limbs;   /* a width of the ladder (1, 2, 4, 8, 10, 12, 14, 16); 0 = default (2) */
     int32_t rank;            /* row-shard rank (0 when single GPU) */
     int32_t world;           /* number of row shards (1 when single GPU) */
     int32_t dense_carry;     /* 1: always run the dense carry kernels; 0 (default): active-column mode -- carry
@@ -74,6 +74,10 @@ typedef struct rg_options {
                                     on rank 0, broadcast by the host, e.g. torch.distributed) */
 } rg_options;
 
+/* The limb-width ladder of the engine: 1, 2, 4, 8, 10, 12, 14, 16 limbs (powers of two up to 512 bits, then
+ * steps of 128 bits).  Per-width statistics are indexed by position in this ladder (rg_stats.limb_widths). */
+#define RG_NWIDTHS 8
+
 typedef struct rg_stats {
     int64_t pivots;              /* basis changes performed */
     int64_t promotions;          /* limb-width promotions (K9) */
@@ -82,10 +86,12 @@ typedef struct rg_stats {
     int32_t denominator_bits;    /* bit length of D */
     int32_t reserved;            /* active-column mode: number of non-trivial carry columns; 0 in dense mode */
     int64_t kernel_launches;     /* kernels launched by this context so far */
-    int64_t pivots_at_limbs[5];  /* pivots performed at L = 1,2,4,8,16 */
+    int64_t demotions;           /* limb-width demotions (numerators shrank by more than a width step) */
+    int32_t limb_widths[RG_NWIDTHS];        /* the ladder: limb count of each per-width slot below */
+    int64_t pivots_at_limbs[RG_NWIDTHS];    /* pivots performed at each width */
     /* profiling (rg_set_profile): CUDA-event time of the rank-1 update kernel (K1) per limb width */
-    int64_t k1_launches_at_limbs[5];
-    double k1_ms_at_limbs[5];
+    int64_t k1_launches_at_limbs[RG_NWIDTHS];
+    double k1_ms_at_limbs[RG_NWIDTHS];
     double timer_ms;             /* rg_timer_start .. rg_timer_stop on the engine's stream */
     /* profiling: CUDA-event time per iteration phase: 0 pivot column + ratio test + row staging,
      * 1 work vector, 2 pivot scalars, 3 K1 update, 4 bookkeeping + steepest-edge update,
@@ -93,8 +99,8 @@ typedef struct rg_stats {
     double phase_ms[8];
     /* profiling: algorithmic work of the timed K1 launches per limb width -- bytes (every entry of the active
      * part of the carry read and written once) and IMAD.WIDE multiply-adds (two low products per entry) */
-    double k1_bytes_at_limbs[5];
-    double k1_imads_at_limbs[5];
+    double k1_bytes_at_limbs[RG_NWIDTHS];
+    double k1_imads_at_limbs[RG_NWIDTHS];
 } rg_stats;
 
 typedef struct rg_pivot_info {   /* BasisChangeComputationInfo, tableau/mod.rs:205-234 (indices only) */

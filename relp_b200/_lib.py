@@ -15,13 +15,17 @@ class rg_options(C.Structure):
                 ("nccl_unique_id", C.c_void_p)]
 
 
+RG_NWIDTHS = 8     # include/relp_gpu.h: the limb-width ladder 1, 2, 4, 8, 10, 12, 14, 16
+
+
 class rg_stats(C.Structure):
     _fields_ = [("pivots", C.c_int64), ("promotions", C.c_int64), ("limbs", C.c_int32),
                 ("max_bits", C.c_int32), ("denominator_bits", C.c_int32), ("reserved", C.c_int32),
-                ("kernel_launches", C.c_int64), ("pivots_at_limbs", C.c_int64 * 5),
-                ("k1_launches_at_limbs", C.c_int64 * 5), ("k1_ms_at_limbs", C.c_double * 5),
+                ("kernel_launches", C.c_int64), ("demotions", C.c_int64),
+                ("limb_widths", C.c_int32 * RG_NWIDTHS), ("pivots_at_limbs", C.c_int64 * RG_NWIDTHS),
+                ("k1_launches_at_limbs", C.c_int64 * RG_NWIDTHS), ("k1_ms_at_limbs", C.c_double * RG_NWIDTHS),
                 ("timer_ms", C.c_double), ("phase_ms", C.c_double * 8),
-                ("k1_bytes_at_limbs", C.c_double * 5), ("k1_imads_at_limbs", C.c_double * 5)]
+                ("k1_bytes_at_limbs", C.c_double * RG_NWIDTHS), ("k1_imads_at_limbs", C.c_double * RG_NWIDTHS)]
 
 
 class rg_pivot_info(C.Structure):

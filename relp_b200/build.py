@@ -12,7 +12,7 @@ ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "librelp_gpu.so")
 OBJ = os.path.join(HERE, "_obj")
 CSRC = os.path.join(HERE, "csrc")
-K1_WIDTHS = (16, 8, 4, 2, 1)          # widest first: it is the longest job
+K1_WIDTHS = (16, 14, 12, 10, 8, 4, 2, 1)          # widest first: it is the longest job
 SOURCES = [
     os.path.join(CSRC, "relp_gpu.cu"),
     os.path.join(CSRC, "k1_variants.cu"),

@@ -7,6 +7,7 @@
 #include <string>
 #include <vector>
 
+#include "../../include/relp_gpu.h"
 #include "bigint.cuh"
 
 namespace rg {
@@ -165,7 +166,11 @@ struct rg_context {
     bool work_valid = false;           // omega holds the work vector of the last basis change
     int t_cur = 0;                     // ctz(D) of the current denominator (host copy)
     long long pivots = 0, promotions = 0, launches = 0;
-    long long pivots_at[5] = {0, 0, 0, 0, 0};
+    long long pivots_at[RG_NWIDTHS] = {};
+    long long demotions = 0;
+    int demote_need = 0;               // upper bound of the carry's bit length after the last pivot (0 = unknown)
+    bool pow2_only = false;            // RG_WIDTH_LADDER=pow2: widths 1, 2, 4, 8, 16 only
+    int demote_floor = 8;              // narrowest width a demotion may reach (RG_DEMOTE_FLOOR)
     int profile = 0;                   // 0 off, 1 events around K1 only, 2 events around every phase
     // CUDA graphs of one fused iteration, keyed by everything that shapes the launch sequence
     struct GraphEntry { long long key; cudaGraphExec_t exec; long long launches; };
@@ -177,10 +182,10 @@ struct rg_context {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evt0 = nullptr, evt1 = nullptr;
     cudaEvent_t evp[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     double phase_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // ftran+ratio+copyrow, work, scalars, K1, finalize+SE update, price+select, mirror
-    long long k1_launches[5] = {0, 0, 0, 0, 0};
-    double k1_ms[5] = {0, 0, 0, 0, 0};
-    double k1_bytes[5] = {0, 0, 0, 0, 0};   // algorithmic bytes / IMAD.WIDE of the timed K1 launches (roofline accounting)
-    double k1_imads[5] = {0, 0, 0, 0, 0};
+    long long k1_launches[RG_NWIDTHS] = {};
+    double k1_ms[RG_NWIDTHS] = {};
+    double k1_bytes[RG_NWIDTHS] = {};   // algorithmic bytes / IMAD.WIDE of the timed K1 launches (roofline accounting)
+    double k1_imads[RG_NWIDTHS] = {};
     double k1_cur_bytes = 0, k1_cur_imads = 0;   // of the launch in flight
     double timer_ms = 0;
     std::string err;

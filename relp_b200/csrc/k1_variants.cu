@@ -1,4 +1,4 @@
-// One translation unit per limb width (compiled with -DRG_K1_L=1|2|4|8|16): the (E, CP, RT) variants of K1.
+// One translation unit per limb width (compiled with -DRG_K1_L=1|2|4|8|10|12|14|16): the (E, CP, RT) variants of K1.
 // They are the bulk of the library's compile time, so build.py compiles these units in parallel.
 // rg::k1_launch_<L>(ctx, E) enqueues K1 for the current carry mode on ctx->stream and returns false when no
 // fixed-width variant covers E (the caller falls back to the run-time-width kernel).
@@ -22,7 +22,7 @@ template <int L, int E>
 void launch_le(rg_context* ctx) {
     constexpr int CP = L <= 4 ? 2 : 1;
     // L = 16 is bound by the multiply pipe in either mode: one instantiation (8-row blocks) serves both
-    constexpr int RTD = L >= 16 ? 8 : 32;
+    constexpr int RTD = L > 8 ? 8 : 32;
     if (ctx->list_mode) {
         // cost row: dense over all columns; rows 1..nloc: the non-trivial columns only
         dim3 g0(cdiv(ctx->ld, 256 * CP), 1);
@@ -55,8 +55,8 @@ bool launch_t(rg_context* ctx, int E) {
         case 2: if constexpr (L >= 2) { launch_le<L, 2>(ctx); return true; } break;
         case 3: if constexpr (L >= 4) { launch_le<L, 3>(ctx); return true; } break;
         case 4: if constexpr (L >= 4) { launch_le<L, 4>(ctx); return true; } break;
-        case 6: if constexpr (L >= 8) { launch_le<L, 6>(ctx); return true; } break;
-        case 8: if constexpr (L >= 8) { launch_le<L, 8>(ctx); return true; } break;
+        case 6: if constexpr (L == 8 || L == 16) { launch_le<L, 6>(ctx); return true; } break;
+        case 8: if constexpr (L == 8 || L == 16) { launch_le<L, 8>(ctx); return true; } break;
         default: break;
     }
     return false;

@@ -75,7 +75,20 @@ using namespace rg;
     } while (0)
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
-static inline int log2i(int L) { int k = 0; while ((1 << k) < L) ++k; return k; }
+// The limb-width ladder (RG_NWIDTHS entries, relp_gpu.h): powers of two up to 8 limbs, then steps of two limbs --
+// above 512 bits a doubling would spend up to 4x the multiply-adds the numbers need (config 5 peaks at 783 bits).
+static const int kWidths[RG_NWIDTHS] = {1, 2, 4, 8, 10, 12, 14, 16};
+static inline int width_index(int L) { for (int k = 0; k < RG_NWIDTHS; ++k) if (kWidths[k] == L) return k; return -1; }
+// pow2_only (RG_WIDTH_LADDER=pow2): the round-1 ladder 1, 2, 4, 8, 16 (tests use it to reach the 16-limb kernels early)
+static inline bool width_allowed(int L, bool pow2_only) { return !pow2_only || (L & (L - 1)) == 0; }
+static inline int next_width(int L, bool pow2_only = false) {
+    for (int k = width_index(L) + 1; k >= 1 && k < RG_NWIDTHS; ++k) if (width_allowed(kWidths[k], pow2_only)) return kWidths[k];
+    return 0;
+}
+static inline int prev_width(int L, bool pow2_only = false) {
+    for (int k = width_index(L) - 1; k >= 0; --k) if (width_allowed(kWidths[k], pow2_only)) return kWidths[k];
+    return 0;
+}
 
 #define DISPATCH_L(Lv, FN, ...)                                   \
     switch (Lv) {                                                 \
@@ -83,8 +96,23 @@ static inline int log2i(int L) { int k = 0; while ((1 << k) < L) ++k; return k; 
         case 2: FN<2>(__VA_ARGS__); break;                        \
         case 4: FN<4>(__VA_ARGS__); break;                        \
         case 8: FN<8>(__VA_ARGS__); break;                        \
+        case 10: FN<10>(__VA_ARGS__); break;                      \
+        case 12: FN<12>(__VA_ARGS__); break;                      \
+        case 14: FN<14>(__VA_ARGS__); break;                      \
         case 16: FN<16>(__VA_ARGS__); break;                      \
         default: break;                                           \
+    }
+// same, for launchers that return a status
+#define DISPATCH_L_RET(Lv, FN, ...)                               \
+    switch (Lv) {                                                 \
+        case 1: return FN<1>(__VA_ARGS__);                        \
+        case 2: return FN<2>(__VA_ARGS__);                        \
+        case 4: return FN<4>(__VA_ARGS__);                        \
+        case 8: return FN<8>(__VA_ARGS__);                        \
+        case 10: return FN<10>(__VA_ARGS__);                      \
+        case 12: return FN<12>(__VA_ARGS__);                      \
+        case 14: return FN<14>(__VA_ARGS__);                      \
+        default: return FN<16>(__VA_ARGS__);                      \
     }
 
 // ------------------------------------------------------------------------------------------------
@@ -242,6 +270,8 @@ static void free_width_buffers(rg_context* ctx) {
 static double g_graph_prof[5] = {0, 0, 0, 0, 0};   // capture s, launch s, sync s, captures, launches
 static std::mutex g_hm_mutex;
 static std::vector<HostMirror*> g_hm_free[16];   // per device: recycled pinned mirrors
+struct ProfEvents { cudaEvent_t e[10]; };
+static std::vector<ProfEvents> g_prof_events[16];   // per device: recycled profiling event sets
 static void drop_graphs(rg_context* ctx);
 static void drop_graphs(rg_context* ctx) {
     for (auto& g : ctx->graphs) cudaGraphExecDestroy(g.exec);
@@ -257,8 +287,10 @@ extern "C" int rg_create(const rg_options* opts, rg_context** out) {
     ctx->dense_carry_opt = opts ? opts->dense_carry : 0;
     ctx->use_graphs = getenv("RG_NO_GRAPH") == nullptr;
     { const char* e = getenv("RG_GRAPH_NCCL"); ctx->graph_nccl = e && atoi(e) != 0; }
+    { const char* e = getenv("RG_WIDTH_LADDER"); ctx->pow2_only = e && strcmp(e, "pow2") == 0; }
+    { const char* e = getenv("RG_DEMOTE_FLOOR"); if (e) ctx->demote_floor = std::max(1, atoi(e)); }   // 99 = never demote
     int L = (opts && opts->initial_limbs) ? opts->initial_limbs : 2;
-    if (!(L == 1 || L == 2 || L == 4 || L == 8 || L == 16)) { delete ctx; return RG_ERR_ARG; }
+    if (width_index(L) < 0) { delete ctx; return RG_ERR_ARG; }
     ctx->L = L;
     *out = ctx;
     CK(cudaSetDevice(ctx->device));
@@ -356,7 +388,12 @@ extern "C" int rg_destroy(rg_context* ctx) {
         std::lock_guard<std::mutex> lock(g_hm_mutex);
         g_hm_free[ctx->device & 15].push_back(ctx->hm);
     }
-    if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); for (int k = 0; k < 8; ++k) cudaEventDestroy(ctx->evp[k]); }
+    if (ctx->ev0) {   // back to the per-device pool (see rg_set_profile)
+        ProfEvents pe; pe.e[0] = ctx->ev0; pe.e[1] = ctx->ev1;
+        for (int k = 0; k < 8; ++k) pe.e[2 + k] = ctx->evp[k];
+        std::lock_guard<std::mutex> lock(g_hm_mutex);
+        g_prof_events[ctx->device & 15].push_back(pe);
+    }
     if (ctx->evt0) { cudaEventDestroy(ctx->evt0); cudaEventDestroy(ctx->evt1); }
     if (ctx->ev_side0) { cudaEventDestroy(ctx->ev_side0); cudaEventDestroy(ctx->ev_side1); cudaEventDestroy(ctx->ev_side2); cudaEventDestroy(ctx->ev_work); cudaEventDestroy(ctx->ev_side3); }
     if (ctx->side2) cudaStreamDestroy(ctx->side2);
@@ -908,20 +945,14 @@ static int launch_work_t(rg_context* ctx) {
     return RG_OK;
 }
 static int launch_work(rg_context* ctx) {
-    switch (ctx->L) {
-        case 1: return launch_work_t<1>(ctx);
-        case 2: return launch_work_t<2>(ctx);
-        case 4: return launch_work_t<4>(ctx);
-        case 8: return launch_work_t<8>(ctx);
-        default: return launch_work_t<16>(ctx);
-    }
+    DISPATCH_L_RET(ctx->L, launch_work_t, ctx);
 }
 
 // K1 variants: E = extra limbs (>= ceil(ctz(D)/64)).  ctz(D) grows by about one bit per structural
 // column in the basis, so wide carries need wide E; the generic run-time-width kernel is the last resort.
 static int pick_update_variant(int L, int E_needed) {
     static const int opts[] = {0, 1, 2, 3, 4, 6, 8};
-    int emax = L == 1 ? 1 : (L == 2 ? 2 : (L == 4 ? 4 : 8));
+    int emax = L == 1 ? 1 : (L == 2 ? 2 : ((L == 4 || (L > 8 && L < 16)) ? 4 : 8));
     for (int e : opts) if (e >= E_needed && e <= emax) return e;
     return -1;   // generic kernel
 }
@@ -931,6 +962,9 @@ bool k1_launch_1(rg_context*, int);
 bool k1_launch_2(rg_context*, int);
 bool k1_launch_4(rg_context*, int);
 bool k1_launch_8(rg_context*, int);
+bool k1_launch_10(rg_context*, int);
+bool k1_launch_12(rg_context*, int);
+bool k1_launch_14(rg_context*, int);
 bool k1_launch_16(rg_context*, int);
 }
 static void launch_update(rg_context* ctx, int E) {
@@ -940,6 +974,9 @@ static void launch_update(rg_context* ctx, int E) {
         case 2: ok = k1_launch_2(ctx, E); break;
         case 4: ok = k1_launch_4(ctx, E); break;
         case 8: ok = k1_launch_8(ctx, E); break;
+        case 10: ok = k1_launch_10(ctx, E); break;
+        case 12: ok = k1_launch_12(ctx, E); break;
+        case 14: ok = k1_launch_14(ctx, E); break;
         default: ok = k1_launch_16(ctx, E); break;
     }
     if (ok) return;
@@ -1009,23 +1046,27 @@ static void launch_rowdot_t(rg_context* ctx) {   // nu_j = rowp . a_j
 // ------------------------------------------------------------------------------------------------
 // K9 promotion
 // ------------------------------------------------------------------------------------------------
-static int promote(rg_context* ctx) {
-    int Lold = ctx->L, Lnew = Lold * 2;
-    if (Lnew > RG_MAXL) { ctx->err = "numerators exceed 16 limbs"; return RG_ERR_OVERFLOW; }
+// Re-widen the persistent state (carry, packed block, steepest-edge weights) to Lnew limbs: wider = sign / zero
+// extension (K9 promotion), narrower = dropping high limbs that hold only sign bits (demotion: the caller has
+// checked the tracked bit lengths).  Everything else is per-pivot scratch and is reallocated at the new width.
+static int change_width(rg_context* ctx, int Lnew) {
+    const int Lold = ctx->L;
+    if (Lnew < 1 || Lnew > RG_MAXL || width_index(Lnew) < 0) { ctx->err = "numerators exceed 16 limbs"; return RG_ERR_OVERFLOW; }
+    const int Lcopy = std::min(Lold, Lnew);
     u64* nc = nullptr;
     CK(dev_alloc(&nc, sizeof(u64) * Lnew * ctx->plane, ctx->stream));
-    CK(cudaMemcpyAsync(nc, ctx->carry, sizeof(u64) * Lold * ctx->plane, cudaMemcpyDeviceToDevice, ctx->stream));
-    LAUNCH(k_sign_extend, 148 * 8, 256, nc, ctx->plane, ctx->plane, Lold, Lnew);
+    CK(cudaMemcpyAsync(nc, ctx->carry, sizeof(u64) * Lcopy * ctx->plane, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (Lnew > Lold) LAUNCH(k_sign_extend, 148 * 8, 256, nc, ctx->plane, ctx->plane, Lold, Lnew);
     u64* npk = nullptr;
-    if (ctx->list_mode) {   // the packed active block widens the same way
+    if (ctx->list_mode) {   // the packed active block re-widens the same way
         CK(dev_alloc(&npk, sizeof(u64) * Lnew * ctx->pplane, ctx->stream));
-        CK(cudaMemcpyAsync(npk, ctx->pk, sizeof(u64) * Lold * ctx->pplane, cudaMemcpyDeviceToDevice, ctx->stream));
-        LAUNCH(k_sign_extend, 148 * 8, 256, npk, ctx->pplane, ctx->pplane, Lold, Lnew);
+        CK(cudaMemcpyAsync(npk, ctx->pk, sizeof(u64) * Lcopy * ctx->pplane, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (Lnew > Lold) LAUNCH(k_sign_extend, 148 * 8, 256, npk, ctx->pplane, ctx->pplane, Lold, Lnew);
     }
     u64* ng = nullptr;
     CK(dev_alloc(&ng, sizeof(u64) * LG_of(Lnew) * ctx->n, ctx->stream));
-    CK(cudaMemsetAsync(ng, 0, sizeof(u64) * LG_of(Lnew) * ctx->n, ctx->stream));
-    CK(cudaMemcpyAsync(ng, ctx->G, sizeof(u64) * LG_of(Lold) * ctx->n, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (Lnew > Lold) CK(cudaMemsetAsync(ng, 0, sizeof(u64) * LG_of(Lnew) * ctx->n, ctx->stream));
+    CK(cudaMemcpyAsync(ng, ctx->G, sizeof(u64) * LG_of(Lcopy) * ctx->n, cudaMemcpyDeviceToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     free_dev_on(ctx->carry, ctx->stream); ctx->carry = nc;
     if (ctx->list_mode) { free_dev_on(ctx->pk, ctx->stream); ctx->pk = npk; }
@@ -1033,9 +1074,15 @@ static int promote(rg_context* ctx) {
     free_width_buffers(ctx);
     ctx->L = Lnew;
     RG_TRY(alloc_width_buffers(ctx, Lnew));
-    ctx->promotions++;
     ctx->have_column = false;
     drop_graphs(ctx);   // buffers moved: captured pointers are stale
+    return RG_OK;
+}
+static int promote(rg_context* ctx) {
+    const int Lnew = next_width(ctx->L, ctx->pow2_only);
+    if (Lnew == 0) { ctx->err = "numerators exceed 16 limbs"; return RG_ERR_OVERFLOW; }
+    RG_TRY(change_width(ctx, Lnew));
+    ctx->promotions++;
     return RG_OK;
 }
 
@@ -1131,7 +1178,29 @@ static int enqueue_iteration(rg_context* ctx, int q, int fixed_row, bool want_se
     return RG_OK;
 }
 
+// Demotion: the numerators of an exact simplex run shrink again once the basis stops growing (config 5: 783 bits at
+// pivot 220, 590 at pivot 345), and every kernel of the iteration costs O(L) bytes and O(L^2) multiply-adds.  After
+// a pivot the replicated upper bound of the carry's bit length (the overflow prediction of that pivot, and D) is
+// known on the host; when it fits the next narrower width with RG_DEMOTE_MARGIN bits to spare, the persistent state
+// is narrowed before the next pivot.  A later overflow prediction promotes again (K9) -- the margin keeps the two
+// from alternating.  Widths below `demote_floor` (default 8 limbs: pivots there are launch-latency bound) stay.
+#define RG_DEMOTE_MARGIN 40
+static int maybe_demote(rg_context* ctx) {
+    const int need = ctx->demote_need;
+    ctx->demote_need = 0;
+    if (need <= 0) return RG_OK;
+    int Lnew = ctx->L;
+    for (int lower = prev_width(Lnew, ctx->pow2_only); lower >= ctx->demote_floor && lower >= 1 && need + RG_DEMOTE_MARGIN <= 64 * lower - 1;
+         lower = prev_width(Lnew, ctx->pow2_only))
+        Lnew = lower;
+    if (Lnew == ctx->L) return RG_OK;
+    RG_TRY(change_width(ctx, Lnew));
+    ctx->demotions++;
+    return RG_OK;
+}
+
 static int do_pivot(rg_context* ctx, int q, int fixed_row, bool want_se, bool reselect) {
+    RG_TRY(maybe_demote(ctx));
     for (;;) {
         if (ctx->list_mode) {
             int E_need = (ctx->t_cur + 63) / 64;
@@ -1220,15 +1289,20 @@ static int do_pivot(rg_context* ctx, int q, int fixed_row, bool want_se, bool re
             return ctx->hm->fatal == 2 ? RG_ERR_STATE : RG_ERR_OVERFLOW;
         }
         if (ctx->hm->pivoted) {
+            static const bool trace_bits = getenv("RG_TRACE_BITS") != nullptr;
+            if (trace_bits && ctx->rank == 0)
+                fprintf(stderr, "RGBITS pivot=%lld L=%d maxbits=%d bitsD=%d t=%d nk=%d predicted=%d\n",
+                        (long long)ctx->pivots, ctx->L, ctx->hm->maxbits_carry, ctx->hm->bits_D, ctx->hm->t_next,
+                        ctx->hm->nk, ctx->hm->predicted);
             ctx->pivots++;
-            ctx->pivots_at[log2i(ctx->L)]++;
+            ctx->pivots_at[width_index(ctx->L)]++;
             if (ctx->profile) {
                 float ms = 0;
                 if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) {
-                    ctx->k1_ms[log2i(ctx->L)] += ms;
-                    ctx->k1_launches[log2i(ctx->L)]++;
-                    ctx->k1_bytes[log2i(ctx->L)] += ctx->k1_cur_bytes;
-                    ctx->k1_imads[log2i(ctx->L)] += ctx->k1_cur_imads;
+                    ctx->k1_ms[width_index(ctx->L)] += ms;
+                    ctx->k1_launches[width_index(ctx->L)]++;
+                    ctx->k1_bytes[width_index(ctx->L)] += ctx->k1_cur_bytes;
+                    ctx->k1_imads[width_index(ctx->L)] += ctx->k1_cur_imads;
                     ctx->phase_ms[3] += ms;
                 }
                 (void)cudaGetLastError();
@@ -1248,6 +1322,7 @@ static int do_pivot(rg_context* ctx, int q, int fixed_row, bool want_se, bool re
             }
             ctx->identity_carry = false;
             ctx->work_valid = want_se;
+            ctx->demote_need = std::max(ctx->hm->predicted, ctx->hm->bits_D + 1);
         }
         return RG_OK;
     }
@@ -1257,6 +1332,7 @@ static int do_pivot(rg_context* ctx, int q, int fixed_row, bool want_se, bool re
 // constructors
 // ------------------------------------------------------------------------------------------------
 extern "C" int rg_init_identity_basis(rg_context* ctx, const int32_t* basis, const int64_t* cost) {
+    if (ctx) ctx->demote_need = 0;   // the carry is rebuilt / re-priced: the last pivot's bit bound no longer covers it
     if (ctx) drop_graphs(ctx);   // state the captured launch sequence depends on may change
     if (!ctx || !ctx->carry || !basis) return RG_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
@@ -1322,6 +1398,7 @@ extern "C" int rg_init_identity_basis(rg_context* ctx, const int32_t* basis, con
 // engine's own rank-1 update in a row that still holds an artificial; the rows are permuted at the end so that
 // row i holds basis[i], and the costs are installed like at a phase switch.
 extern "C" int rg_init_basis(rg_context* ctx, const int32_t* basis, const int64_t* cost) {
+    if (ctx) ctx->demote_need = 0;   // the carry is rebuilt / re-priced: the last pivot's bit bound no longer covers it
     if (!ctx || !ctx->carry || !basis || !cost) return RG_ERR_ARG;
     if (ctx->world > 1) { ctx->err = "rg_init_basis: single GPU only (the final row permutation is not sharded)"; return RG_ERR_STATE; }
     const int m = ctx->m, n = ctx->n;
@@ -1437,16 +1514,11 @@ static int launch_phase_sums_t(rg_context* ctx) {
     return RG_OK;
 }
 static int launch_phase_sums(rg_context* ctx) {
-    switch (ctx->L) {
-        case 1: return launch_phase_sums_t<1>(ctx);
-        case 2: return launch_phase_sums_t<2>(ctx);
-        case 4: return launch_phase_sums_t<4>(ctx);
-        case 8: return launch_phase_sums_t<8>(ctx);
-        default: return launch_phase_sums_t<16>(ctx);
-    }
+    DISPATCH_L_RET(ctx->L, launch_phase_sums_t, ctx);
 }
 
 extern "C" int rg_phase_switch(rg_context* ctx, const int64_t* cost) {
+    if (ctx) ctx->demote_need = 0;   // the carry is rebuilt / re-priced: the last pivot's bit bound no longer covers it
     if (ctx) drop_graphs(ctx);   // state the captured launch sequence depends on may change
     if (!ctx || !ctx->carry || !cost) return RG_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
@@ -1492,13 +1564,7 @@ static int launch_gamma_general_t(rg_context* ctx) {
     return RG_OK;
 }
 static int launch_gamma_general(rg_context* ctx) {
-    switch (ctx->L) {
-        case 1: return launch_gamma_general_t<1>(ctx);
-        case 2: return launch_gamma_general_t<2>(ctx);
-        case 4: return launch_gamma_general_t<4>(ctx);
-        case 8: return launch_gamma_general_t<8>(ctx);
-        default: return launch_gamma_general_t<16>(ctx);
-    }
+    DISPATCH_L_RET(ctx->L, launch_gamma_general_t, ctx);
 }
 
 // steepest-edge weights on a general basis, one carry row at a time: stage the row like a pivot row, dot it with
@@ -1518,13 +1584,7 @@ static int launch_gamma_rowwise_t(rg_context* ctx) {
     return RG_OK;
 }
 static int launch_gamma_rowwise(rg_context* ctx) {
-    switch (ctx->L) {
-        case 1: return launch_gamma_rowwise_t<1>(ctx);
-        case 2: return launch_gamma_rowwise_t<2>(ctx);
-        case 4: return launch_gamma_rowwise_t<4>(ctx);
-        case 8: return launch_gamma_rowwise_t<8>(ctx);
-        default: return launch_gamma_rowwise_t<16>(ctx);
-    }
+    DISPATCH_L_RET(ctx->L, launch_gamma_rowwise_t, ctx);
 }
 
 extern "C" int rg_rule_new(rg_context* ctx, int32_t rule) {
@@ -1847,7 +1907,9 @@ extern "C" int rg_get_stats(rg_context* ctx, rg_stats* out) {
     out->kernel_launches = ctx->launches;
     if (ctx->hm) { out->max_bits = ctx->hm->maxbits_carry; out->denominator_bits = ctx->hm->bits_D; }
     out->reserved = ctx->list_mode ? ctx->nk_host : 0;   // non-trivial carry columns (0: dense mode)
-    for (int k = 0; k < 5; ++k) {
+    out->demotions = ctx->demotions;
+    for (int k = 0; k < RG_NWIDTHS; ++k) {
+        out->limb_widths[k] = kWidths[k];
         out->pivots_at_limbs[k] = ctx->pivots_at[k];
         out->k1_launches_at_limbs[k] = ctx->k1_launches[k];
         out->k1_ms_at_limbs[k] = ctx->k1_ms[k];
@@ -1863,8 +1925,19 @@ extern "C" int rg_set_profile(rg_context* ctx, int32_t on) {
     if (!ctx) return RG_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     if (on && !ctx->ev0) {
-        CK(cudaEventCreate(&ctx->ev0)); CK(cudaEventCreate(&ctx->ev1));
-        for (int k = 0; k < 8; ++k) CK(cudaEventCreate(&ctx->evp[k]));
+        // the profiling events are recycled per device for the life of the process: a context that creates fresh
+        // timing events right after another one destroyed its set was measured to run ~40 % slower (driver-side
+        // event pool churn), which made consecutive profiled solves -- the bench's timed steps -- look slow
+        std::lock_guard<std::mutex> lock(g_hm_mutex);
+        auto& pool = g_prof_events[ctx->device & 15];
+        if (!pool.empty()) {
+            ProfEvents pe = pool.back(); pool.pop_back();
+            ctx->ev0 = pe.e[0]; ctx->ev1 = pe.e[1];
+            for (int k = 0; k < 8; ++k) ctx->evp[k] = pe.e[2 + k];
+        } else {
+            CK(cudaEventCreate(&ctx->ev0)); CK(cudaEventCreate(&ctx->ev1));
+            for (int k = 0; k < 8; ++k) CK(cudaEventCreate(&ctx->evp[k]));
+        }
     }
     ctx->profile = on < 0 ? 0 : (on > 2 ? 2 : on);
     return RG_OK;

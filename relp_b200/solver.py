@@ -214,12 +214,13 @@ def solve_relaxation(problem, rule="steepest_edge", fused=True, initial_limbs=0,
         lib.rh_result_stats(handle, C.byref(st))
         res.stats = dict(pivots=st.pivots, promotions=st.promotions, limbs=st.limbs,
                          max_bits=st.max_bits, denominator_bits=st.denominator_bits,
-                         kernel_launches=st.kernel_launches,
-                         pivots_at_limbs=[st.pivots_at_limbs[k] for k in range(5)],
-                         k1_launches_at_limbs=[st.k1_launches_at_limbs[k] for k in range(5)],
-                         k1_ms_at_limbs=[st.k1_ms_at_limbs[k] for k in range(5)],
-                         k1_bytes_at_limbs=[st.k1_bytes_at_limbs[k] for k in range(5)],
-                         k1_imads_at_limbs=[st.k1_imads_at_limbs[k] for k in range(5)],
+                         kernel_launches=st.kernel_launches, demotions=st.demotions,
+                         limb_widths=[st.limb_widths[k] for k in range(_lib.RG_NWIDTHS)],
+                         pivots_at_limbs=[st.pivots_at_limbs[k] for k in range(_lib.RG_NWIDTHS)],
+                         k1_launches_at_limbs=[st.k1_launches_at_limbs[k] for k in range(_lib.RG_NWIDTHS)],
+                         k1_ms_at_limbs=[st.k1_ms_at_limbs[k] for k in range(_lib.RG_NWIDTHS)],
+                         k1_bytes_at_limbs=[st.k1_bytes_at_limbs[k] for k in range(_lib.RG_NWIDTHS)],
+                         k1_imads_at_limbs=[st.k1_imads_at_limbs[k] for k in range(_lib.RG_NWIDTHS)],
                          phase_ms=[st.phase_ms[k] for k in range(8)],
                          active_columns=st.reserved)
         res.device_ms = lib.rh_result_device_ms(handle)

@@ -157,7 +157,9 @@ def test_config5_full_solve_exact_optimality_certificate():
     prob = _dense16k()
     g = relp_b200.solve_relaxation(prob, rule="steepest_edge")
     assert g.status == "optimal"
-    assert g.stats["limbs"] == 16 and g.stats["promotions"] == 3
+    # 783-bit numerators at the peak: 14 limbs of the ladder, narrowed again as they shrink towards the optimum
+    assert g.stats["max_bits"] <= 64 * g.stats["limbs"] and g.stats["promotions"] >= 5 and g.stats["demotions"] >= 1
+    assert sum(g.stats["pivots_at_limbs"]) == g.pivots and g.stats["pivots_at_limbs"][-1] == 0
     exact_optimality_certificate(prob, g)
 
 
@@ -198,7 +200,8 @@ def _ctz(v):
 
 @pytest.mark.parametrize("factor,kb,min_ctz", [(1, 160, 129), (8, 100, 321), (64, 78, 513)])
 @pytest.mark.parametrize("no_graph", [False, True])
-def test_limb_and_division_width_sweep(factor, kb, min_ctz, no_graph, monkeypatch):
+@pytest.mark.parametrize("ladder", ["pow2", "full"])
+def test_limb_and_division_width_sweep(factor, kb, min_ctz, no_graph, ladder, monkeypatch):
     """Runs that end at 16 limbs with ctz(D) beyond 128 / 256 / 512 bits: the K1 variants E in {3,4}, {6,8}
     and the run-time-width kernels (k_update_generic, k_gamma_update) all execute, with graph replay and
     with eager launches; full trace / objective / solution against the oracle."""
@@ -207,25 +210,42 @@ def test_limb_and_division_width_sweep(factor, kb, min_ctz, no_graph, monkeypatc
         monkeypatch.setenv("RG_NO_GRAPH", "1")
     else:
         monkeypatch.delenv("RG_NO_GRAPH", raising=False)
+    # the power-of-two ladder reaches the 16-limb kernels (and their E in {6, 8} variants); the full ladder walks
+    # 8 -> 10 -> 12 -> 14 (-> 16) and narrows again (demotions down to one limb are allowed here)
+    if ladder == "pow2":
+        monkeypatch.setenv("RG_WIDTH_LADDER", "pow2")
+        monkeypatch.delenv("RG_DEMOTE_FLOOR", raising=False)
+    else:
+        monkeypatch.delenv("RG_WIDTH_LADDER", raising=False)
+        monkeypatch.setenv("RG_DEMOTE_FLOOR", "1")
     base = bounded_lp(256, 512, k_bounding=kb, dense=True, seed=2, dense_block=False)
     prob = scaled_structural(base, factor) if factor > 1 else base
     g, ref = _solve_both(prob, initial_limbs=1)
     assert ref.status == "optimal"
     _assert_same(g, ref)
-    assert g.stats["limbs"] == 16, g.stats
+    if ladder == "pow2":
+        assert g.stats["limbs"] == 16, g.stats
+    else:
+        assert g.stats["limbs"] >= 10 and sum(g.stats["pivots_at_limbs"][4:7]) > 0, g.stats
     assert _ctz(g.denominator) >= min_ctz, (_ctz(g.denominator), g.denominator.bit_length())
 
 
-def test_limb_sweep_dense_block_wide():
+def test_limb_sweep_dense_block_wide(monkeypatch):
     """same sweep through the dense int8 block (tensor-core dots at every width up to 16 limbs)"""
     from relp_b200.generators import bounded_lp
     prob = bounded_lp(256, 512, k_bounding=160, dense=True, seed=2, dense_block=True)
+    monkeypatch.setenv("RG_WIDTH_LADDER", "pow2")
     g, ref = _solve_both(prob, initial_limbs=1)
     _assert_same(g, ref)
     assert g.stats["limbs"] == 16
+    monkeypatch.delenv("RG_WIDTH_LADDER")
+    monkeypatch.setenv("RG_DEMOTE_FLOOR", "1")
+    g, ref = _solve_both(prob, initial_limbs=1)
+    _assert_same(g, ref)
+    assert sum(g.stats["pivots_at_limbs"][4:7]) > 0, g.stats      # 10 / 12 / 14 limbs were used
 
 
-@pytest.mark.parametrize("limbs", [1, 16])
+@pytest.mark.parametrize("limbs", [1, 12, 16])
 def test_tcgen05_dense_dots_match_mma_sync_and_oracle(limbs, monkeypatch):
     """The dense dots run as tcgen05.mma.kind::i8 (TMA-fed, TMEM accumulators; dense_umma.cuh) once the block has
     a few 128 x 128 tiles; RG_NO_UMMA=1 keeps the mma.sync kernel.  Both must walk the oracle's pivots -- from one

@@ -133,7 +133,7 @@ def test_random_rank_deficient(seed):
     check(md2)
 
 
-@pytest.mark.parametrize("limbs", [1, 2, 4, 8, 16])
+@pytest.mark.parametrize("limbs", [1, 2, 4, 8, 10, 12, 14, 16])
 def test_all_limb_widths_agree(limbs):
     rng = np.random.default_rng(77)
     check(random_matrix_data(rng, 7, (2, 1, 2, 1)), rules=["steepest_edge", "dantzig"], modes=(True,),
@@ -224,7 +224,7 @@ def test_graph_replay_matches_eager_launches(dense_carry, monkeypatch):
         assert status == ores.status and trace == otrace and objective == ores.objective and bfs == ores.bfs
 
 
-@pytest.mark.parametrize("limbs", [8, 16])
+@pytest.mark.parametrize("limbs", [8, 12, 16])
 def test_dense_block_tensor_core_dots_at_wide_limbs(limbs):
     """The dense dots run as byte-sliced u8 x s8 tensor-core products.  Starting at 8 / 16 limbs
     instantiates the widest slice-tile counts (sigma dot of 21 / 37 limbs: 22 / 38 tiles split over two CTA
@@ -250,3 +250,21 @@ def test_dense_block_k_split_against_fast_oracle():
         assert g.trace == ref.trace
         assert g.objective == ref.objective and g.bfs == ref.bfs
     assert g.stats["promotions"] >= 1
+
+
+@pytest.mark.parametrize("start", [16, 10, 4])
+def test_width_demotion_walks_down_and_up_again(start, monkeypatch):
+    """The persistent state is narrowed when the numerators fit the next width with a margin (demotion) and widened
+    again by the overflow prediction (K9): starting far too wide, with demotion allowed down to one limb, the run
+    must demote at once (and promote again where the numbers grow past a width) and still walk the oracle's pivots exactly -- fused and
+    trait-shaped, sparse and dense-block columns."""
+    from relp_b200.generators import bounded_lp
+    monkeypatch.setenv("RG_DEMOTE_FLOOR", "1")
+    prob = bounded_lp(40, 60, k_bounding=12, nnz_per_col=4, seed=1)
+    g = check(problem=prob, rules=["steepest_edge", "dantzig"], modes=(True, False), initial_limbs=start)
+    assert g.stats["demotions"] >= 1, g.stats
+    prob = bounded_lp(200, 120, k_bounding=20, dense=True, seed=3, dense_block=True)
+    g = check(problem=prob, rules=["steepest_edge"], modes=(True,), initial_limbs=start)
+    assert g.stats["demotions"] >= 1, g.stats
+    rng = np.random.default_rng(5)
+    check(random_matrix_data(rng, 9, (2, 2, 2, 1)), rules=["steepest_edge"], modes=(True, False), initial_limbs=start)
