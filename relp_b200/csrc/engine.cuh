@@ -169,6 +169,11 @@ struct rg_context {
     long long pivots_at[RG_NWIDTHS] = {};
     long long demotions = 0;
     int demote_need = 0;               // upper bound of the carry's bit length after the last pivot (0 = unknown)
+    u32* bn = nullptr;                 // K1 row factors Bn_i (k_bn_rows): (nloc + 2) rows of 2 (L + 8) + 1 words
+    int k1_items_min_limbs = 8;        // list mode: widths from here on run the warp-granular K1 (RG_K1_ITEMS_MINL)
+    int k1_items_prefetch = 1;         // RG_K1_NOPF=1: no L1 prefetch of the next row's entry
+    bool serial_side = false;          // RG_SERIAL_SIDE=1: the steepest-edge dots start after K1 instead of beside it
+    int k1_items_rows = 8;             // rows per full work item (RG_K1_ITEMS_ROWS, <= 32)
     bool pow2_only = false;            // RG_WIDTH_LADDER=pow2: widths 1, 2, 4, 8, 16 only
     int demote_floor = 8;              // narrowest width a demotion may reach (RG_DEMOTE_FLOOR)
     int profile = 0;                   // 0 off, 1 events around K1 only, 2 events around every phase

@@ -209,4 +209,181 @@ k_update(u64* __restrict__ C, size_t ps, int ld, int row_first, int nrows, const
     if ((tid & 31) == 0 && maxb) atomicMax(&sc->maxbits_new, maxb);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// K1 on the packed active block, warp-granular (list mode, L >= 8).
+//
+// k_bn_rows: the row factors Bn_i = -sgn(a) u_i inv(odd D) mod 2^(32 N) of all local rows, once per pivot (one
+// thread per row), as rows of NP = N + 1 words -- word N flags Bn_i != 0.  k_update computes them per block in a
+// prologue that leaves most of the block idle; here they are a table every work item copies its rows from.
+//
+// k_update_items: one WARP per work item.  An item is (tile of RT rows) x (32 consecutive list positions); the
+// nk mod 32 remainder positions are not given 32-lane items of their own (one lane in 32 busy when nk = 161):
+// a remainder item maps its lanes to (row, position) pairs -- rc positions x floor(32 / rc) rows per pass -- and
+// covers correspondingly more rows.  No block-level synchronisation, no idle warps inside a block, and the
+// 64-thread blocks let the register-limited occupancy move in steps of two warps instead of four.
+// ---------------------------------------------------------------------------------------------
+template <int L, int E>
+__global__ void __launch_bounds__(128)
+k_bn_rows(const u64* __restrict__ u, size_t us, int nloc, u32* __restrict__ bn, Scalars* sc) {
+    constexpr int W = L + E, N = 2 * W, LU = L + 2, NP = N + 1;
+    if (sc->status != ST_RUN) return;
+    if (sc->E != E) return;
+    const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;     // local carry row
+    if (i > nloc) return;
+    u32 ui[N], b[N];
+    if (i == sc->p) {
+#pragma unroll
+        for (int l = 0; l < W; ++l) { u64 v = sc->up[l]; ui[2 * l] = (u32)v; ui[2 * l + 1] = (u32)(v >> 32); }
+    } else {
+        u64 top = u[(size_t)(LU - 1) * us + i];
+        u64 sg = (i64)top < 0 ? ~0ull : 0ull;
+#pragma unroll
+        for (int l = 0; l < W; ++l) {
+            u64 v = l < LU ? u[(size_t)l * us + i] : sg;
+            ui[2 * l] = (u32)v; ui[2 * l + 1] = (u32)(v >> 32);
+        }
+    }
+    u32 anyu = 0;
+#pragma unroll
+    for (int k = 0; k < N; ++k) anyu |= ui[k];
+    u32* out = bn + (size_t)i * NP;
+    if (anyu == 0) {            // u_i == 0 (most rows of a sparse problem): Bn_i = 0 without the product
+#pragma unroll
+        for (int k = 0; k < NP; ++k) out[k] = 0;
+        return;
+    }
+    mp_mul_lo<N>(b, ui, reinterpret_cast<const u32*>(sc->Dinv));
+    if (sc->sgn > 0) {   // Bn = -u Dinv
+        u32 c = 1;
+#pragma unroll
+        for (int k = 0; k < N; ++k) { u32 v = ~b[k] + c; c = (c && v == 0) ? 1u : 0u; b[k] = v; }
+    }
+    u32 any = 0;
+#pragma unroll
+    for (int k = 0; k < N; ++k) { out[k] = b[k]; any |= b[k]; }
+    out[N] = any != 0;
+}
+
+template <int L, int E>
+__global__ void __launch_bounds__(64)
+k_update_items(u64* __restrict__ C, size_t ps, int ld, int nloc, int RT, int prefetch, const int* __restrict__ klist,
+               const u32* __restrict__ bn, const u64* __restrict__ rowp, size_t rs, Scalars* sc) {
+    constexpr int W = L + E, N = 2 * W, NP = N + 1;
+    __shared__ u32 sB[2][32 * NP];      // per warp: the Bn rows of its item (at most 32)
+    __shared__ u32 sA[N];
+    if (sc->status != ST_RUN) return;
+    if (sc->E != E) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < N) sA[tid] = reinterpret_cast<const u32*>(sc->A)[tid];
+    __syncthreads();
+    const int nk = sc->nk;
+    const int full = nk >> 5, rc = nk & 31;
+    const int tiles = (nloc + RT - 1) / RT;
+    const int n_full_items = tiles * full;
+    const int rpp = rc ? 32 / rc : 0;                    // rows per pass of a remainder item
+    const int rows_rem = rpp ? (32 / rpp) * rpp : 1;     // rows of a remainder item (<= 32)
+    const int tiles_rem = rc ? (nloc + rows_rem - 1) / rows_rem : 0;
+    const int w = blockIdx.x * 2 + warp;
+    int row_begin, nrows_item, rstep, rsub, pos;
+    bool active;
+    if (w < n_full_items) {
+        const int tile = w / full, chunk = w - tile * full;
+        row_begin = 1 + tile * RT; nrows_item = min(RT, nloc - tile * RT);
+        rstep = 1; rsub = 0; pos = chunk * 32 + lane; active = true;
+    } else {
+        const int w2 = w - n_full_items;
+        if (w2 >= tiles_rem) return;
+        row_begin = 1 + w2 * rows_rem; nrows_item = min(rows_rem, nloc - w2 * rows_rem);
+        rstep = rpp; rsub = lane / rc; pos = full * 32 + lane - rsub * rc; active = lane < rpp * rc;
+    }
+    // the item's rows of the factor table are contiguous: one coalesced copy
+    u32* sBw = sB[warp];
+    {
+        const u32* src = bn + (size_t)row_begin * NP;
+        const int words = nrows_item * NP;
+        for (int j = lane; j < words; j += 32) sBw[j] = src[j];
+    }
+    __syncwarp();
+    int maxb = 0;
+    if (active) {
+        const int t = sc->t;
+        const int tw = t >> 5, tb = t & 31;
+        u32 rp[N];
+        {
+            const int rcol = klist[pos];
+#pragma unroll
+            for (int l = 0; l < L; ++l) {
+                u64 v = rowp[(size_t)l * rs + rcol];
+                rp[2 * l] = (u32)v; rp[2 * l + 1] = (u32)(v >> 32);
+            }
+            u32 sg = (int)rp[2 * L - 1] < 0 ? ~0u : 0u;
+#pragma unroll
+            for (int k = 2 * L; k < N; ++k) rp[k] = sg;
+        }
+        u32 rpnz = 0;
+#pragma unroll
+        for (int k = 0; k < 2 * L; ++k) rpnz |= rp[k];
+        for (int k = rsub; k < nrows_item; k += rstep) {
+            const size_t off = (size_t)(row_begin + k) * ld + pos;
+            u32 cv[N];
+#pragma unroll
+            for (int l = 0; l < L; ++l) {
+                u64 v = C[(size_t)l * ps + off];
+                cv[2 * l] = (u32)v; cv[2 * l + 1] = (u32)(v >> 32);
+            }
+            if (prefetch && k + rstep < nrows_item) {      // next row's entry on its way to L2 / L1 while this one is computed
+                const size_t offn = off + (size_t)rstep * ld;
+#pragma unroll
+                for (int l = 0; l < L; ++l)
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(__cvta_generic_to_global(C + (size_t)l * ps + offn)));
+            }
+            const u32* bptr = sBw + k * NP;
+            const bool two = bptr[N] != 0;
+            // zero skip: C[i][k] == 0 and (C[p][k] == 0 or u_i == 0)  =>  C'[i][k] == 0
+            u32 nzc = two ? rpnz : 0u;
+#pragma unroll
+            for (int q = 0; q < 2 * L; ++q) nzc |= cv[q];
+            if (nzc == 0) continue;
+            {
+                u32 sg = (int)cv[2 * L - 1] < 0 ? ~0u : 0u;
+#pragma unroll
+                for (int q = 2 * L; q < N; ++q) cv[q] = sg;
+            }
+            u32 X[N];
+            if (two) mp_mul2_lo<N>(X, cv, sA, rp, bptr);
+            else mp_mul_lo<N>(X, cv, sA);
+            u32 o[2 * L];
+            if (E == 0) {
+#pragma unroll
+                for (int q = 0; q < 2 * L; ++q) o[q] = X[q];
+            } else {
+#pragma unroll
+                for (int ww = 0; ww <= 2 * E; ++ww) {
+                    if (tw == ww) {
+#pragma unroll
+                        for (int q = 0; q < 2 * L; ++q) {
+                            u32 lo = X[q + ww < N ? q + ww : N - 1];
+                            u32 hi = (q + ww + 1 < N) ? X[q + ww + 1 < N ? q + ww + 1 : N - 1] : 0u;
+                            o[q] = __funnelshift_r(lo, hi, tb);
+                        }
+                    }
+                }
+            }
+            u32 sgn = (int)o[2 * L - 1] < 0 ? ~0u : 0u;
+            int bl = 0;
+#pragma unroll
+            for (int q = 0; q < 2 * L; ++q) {
+                u32 v = o[q] ^ sgn;
+                if (v) bl = 32 * q + 32 - __clz(v);
+            }
+            maxb = max(maxb, bl + (sgn ? 1 : 0));
+#pragma unroll
+            for (int l = 0; l < L; ++l) C[(size_t)l * ps + off] = (u64)o[2 * l] | ((u64)o[2 * l + 1] << 32);
+        }
+    }
+    maxb = warp_max(maxb);
+    if (lane == 0 && maxb) atomicMax(&sc->maxbits_new, maxb);
+}
+
 }  // namespace rg

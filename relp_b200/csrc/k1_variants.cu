@@ -30,7 +30,29 @@ void launch_le(rg_context* ctx) {
                                                              ctx->u, (size_t)ctx->ld, ctx->rowp, (size_t)ctx->ld,
                                                              ctx->sc);
         ctx->launches++;
-        if (ctx->nloc > 0) {
+        if (ctx->nloc > 0 && L >= ctx->k1_items_min_limbs) {
+            // rows 1..nloc of the packed active block, warp-granular work items (k_update_items)
+            k_bn_rows<L, E><<<cdiv(ctx->nloc, 128), 128, 0, ctx->stream>>>(ctx->u, (size_t)ctx->ld, ctx->nloc, ctx->bn,
+                                                                          ctx->sc);
+            const int RT = ctx->k1_items_rows;
+            long long items = 0;
+            if (ctx->capturing) {
+                // a captured launch is replayed for every list length of its graph key: bound by the key's nk_grid
+                // (a remainder item covers at least 17 rows; RT <= 16)
+                items = (long long)cdiv(ctx->nloc, RT < 16 ? RT : 16) * (ctx->nk_grid >> 5) + cdiv(ctx->nloc, 16);
+            } else {
+                for (int nk = ctx->nk_host; nk <= ctx->nk_host + 1; ++nk) {     // this pivot may list one more column
+                    const int full = nk >> 5, rc = nk & 31;
+                    const int rpp = rc ? 32 / rc : 0, rows_rem = rpp ? (32 / rpp) * rpp : 1;
+                    const long long it = (long long)cdiv(ctx->nloc, RT) * full + (rc ? cdiv(ctx->nloc, rows_rem) : 0);
+                    items = it > items ? it : items;
+                }
+            }
+            k_update_items<L, E><<<cdiv(items, 2), 64, 0, ctx->stream>>>(ctx->pk, ctx->pplane, ctx->cap, ctx->nloc, RT,
+                                                                         ctx->k1_items_prefetch, (const int*)ctx->klist,
+                                                                         ctx->bn, ctx->rowp, (size_t)ctx->ld, ctx->sc);
+            ctx->launches += 2;
+        } else if (ctx->nloc > 0) {
             // rows 1..nloc: the packed active block (column slot = list position, stride = capacity)
             dim3 g1(cdiv(ctx->nk_grid, 128 * CP), cdiv(ctx->nloc, 8));
             k_update<L, E, CP, 8><<<g1, 128, 0, ctx->stream>>>(ctx->pk, ctx->pplane, ctx->cap, 1, ctx->nloc + 1,

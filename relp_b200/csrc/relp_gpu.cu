@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <mutex>
 #include <vector>
+#include <unordered_map>
 
 #include <dlfcn.h>
 #include <nccl.h>   // types only: the library is opened lazily so that single-GPU use has no NCCL dependency
@@ -130,11 +131,72 @@ static void pool_setup(int device) {
     }
     done[device] = true;
 }
+// Large buffers (>= 1 MiB) are additionally recycled by EXACT size in a per-device free list of the process: the
+// repeated solves of a bench / a branch-and-bound driver allocate the same sizes in the same order, and the
+// stream-ordered pool was measured to stall for ~0.8 s now and then when a 400 MB request met a fragmented pool
+// (it maps fresh physical memory although enough is free).  A recycled buffer carries the event recorded on the
+// stream that released it; a taker on another stream waits for it.
+struct BigFree { void* p; size_t bytes; cudaEvent_t ev; cudaStream_t st; };
+static std::mutex g_big_mutex;
+static std::vector<BigFree> g_big_free[16];
+static std::unordered_map<void*, size_t> g_big_live;       // buffers handed out through the recycler
+static size_t g_big_cached[16] = {0};
+static const size_t kBigMin = (size_t)1 << 20, kBigCacheMax = (size_t)48 << 30;
 template <class T>
 static cudaError_t dev_alloc(T** p, size_t bytes, cudaStream_t st) {
-    return cudaMallocAsync((void**)p, bytes ? bytes : 8, st);
+    if (bytes < kBigMin) return cudaMallocAsync((void**)p, bytes ? bytes : 8, st);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+        std::lock_guard<std::mutex> lock(g_big_mutex);
+        auto& fl = g_big_free[dev & 15];
+        for (size_t k = fl.size(); k-- > 0;) {
+            if (fl[k].bytes != bytes) continue;
+            BigFree b = fl[k];
+            fl.erase(fl.begin() + k);
+            g_big_cached[dev & 15] -= bytes;
+            if (b.st != st) cudaStreamWaitEvent(st, b.ev, 0);
+            cudaEventDestroy(b.ev);
+            g_big_live[b.p] = bytes;
+            *p = (T*)b.p;
+            return cudaSuccess;
+        }
+    }
+    cudaError_t e = cudaMallocAsync((void**)p, bytes, st);
+    if (e != cudaSuccess) {     // out of memory with buffers parked in the free list: release them and retry
+        (void)cudaGetLastError();
+        std::lock_guard<std::mutex> lock(g_big_mutex);
+        auto& fl = g_big_free[dev & 15];
+        for (auto& b : fl) { cudaStreamWaitEvent(st, b.ev, 0); cudaEventDestroy(b.ev); cudaFreeAsync(b.p, st); }
+        fl.clear(); g_big_cached[dev & 15] = 0;
+        cudaStreamSynchronize(st);
+        e = cudaMallocAsync((void**)p, bytes, st);
+    }
+    if (e == cudaSuccess) { std::lock_guard<std::mutex> lock(g_big_mutex); g_big_live[(void*)*p] = bytes; }
+    return e;
 }
-static void free_dev_on(void* p, cudaStream_t st) { if (p) cudaFreeAsync(p, st); }
+static void free_dev_on(void* p, cudaStream_t st) {
+    if (!p) return;
+    size_t bytes = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+        std::lock_guard<std::mutex> lock(g_big_mutex);
+        auto it = g_big_live.find(p);
+        if (it != g_big_live.end()) { bytes = it->second; g_big_live.erase(it); }
+        if (bytes && g_big_cached[dev & 15] + bytes <= kBigCacheMax) {
+            BigFree b{p, bytes, nullptr, st};
+            if (cudaEventCreateWithFlags(&b.ev, cudaEventDisableTiming) == cudaSuccess &&
+                cudaEventRecord(b.ev, st) == cudaSuccess) {
+                g_big_free[dev & 15].push_back(b);
+                g_big_cached[dev & 15] += bytes;
+                return;
+            }
+            (void)cudaGetLastError();
+        }
+    }
+    cudaFreeAsync(p, st);
+}
 static int alloc_carry(rg_context* ctx, bool list_mode);
 
 // geometry of the tensor-core dense dots for a vector of LV limbs over this rank's dense columns
@@ -233,6 +295,7 @@ static int alloc_width_buffers(rg_context* ctx, int L) {
         CK(dev_alloc(&ctx->omega_part, sizeof(u64) * LW_of(L) * std::max(dense_slots, list_slots), ctx->stream));
     }
     CK(dev_alloc(&ctx->tmprow, sizeof(u64) * LU_of(L) * ld, ctx->stream));
+    CK(dev_alloc(&ctx->bn, sizeof(u32) * (size_t)(ctx->nloc + 2) * (2 * (L + 8) + 1), ctx->stream));
     CK(dev_alloc(&ctx->us2, sizeof(u64) * (LU_of(L) + 1) * ld, ctx->stream));
     if (ctx->world > 1) {
         CK(dev_alloc(&ctx->ufull, sizeof(u64) * (LU_of(L) + 1) * ld, ctx->stream));
@@ -258,6 +321,7 @@ static int alloc_width_buffers(rg_context* ctx, int L) {
 }
 static void free_width_buffers(rg_context* ctx) {
     free_dev_on(ctx->u, ctx->stream); free_dev_on(ctx->rowp, ctx->stream); free_dev_on(ctx->omega, ctx->stream); free_dev_on(ctx->omega_part, ctx->stream);
+    free_dev_on(ctx->bn, ctx->stream); ctx->bn = nullptr;
     free_dev_on(ctx->tmprow, ctx->stream); free_dev_on(ctx->us2, ctx->stream); free_dev_on(ctx->ufull, ctx->stream); ctx->ufull = nullptr; free_dev_on(ctx->dR, ctx->stream); free_dev_on(ctx->dSl, ctx->stream); free_dev_on(ctx->dchunk, ctx->stream);
     free_dev_on(ctx->dR2, ctx->stream); free_dev_on(ctx->dSl2, ctx->stream); free_dev_on(ctx->dchunk2, ctx->stream);
     ctx->dR2 = nullptr; ctx->dSl2 = nullptr; ctx->dchunk2 = nullptr; free_dev_on(ctx->kappa, ctx->stream); free_dev_on(ctx->nu, ctx->stream); free_dev_on(ctx->sigma, ctx->stream); free_dev_on(ctx->tau, ctx->stream); ctx->tau = nullptr;
@@ -287,6 +351,10 @@ extern "C" int rg_create(const rg_options* opts, rg_context** out) {
     ctx->dense_carry_opt = opts ? opts->dense_carry : 0;
     ctx->use_graphs = getenv("RG_NO_GRAPH") == nullptr;
     { const char* e = getenv("RG_GRAPH_NCCL"); ctx->graph_nccl = e && atoi(e) != 0; }
+    ctx->k1_items_prefetch = getenv("RG_K1_NOPF") == nullptr;
+    ctx->serial_side = getenv("RG_SERIAL_SIDE") != nullptr;
+    { const char* e = getenv("RG_K1_ITEMS_MINL"); if (e) ctx->k1_items_min_limbs = atoi(e); }
+    { const char* e = getenv("RG_K1_ITEMS_ROWS"); if (e) ctx->k1_items_rows = std::min(32, std::max(1, atoi(e))); }
     { const char* e = getenv("RG_WIDTH_LADDER"); ctx->pow2_only = e && strcmp(e, "pow2") == 0; }
     { const char* e = getenv("RG_DEMOTE_FLOOR"); if (e) ctx->demote_floor = std::max(1, atoi(e)); }   // 99 = never demote
     int L = (opts && opts->initial_limbs) ? opts->initial_limbs : 2;
@@ -1145,19 +1213,21 @@ static int enqueue_iteration(rg_context* ctx, int q, int fixed_row, bool want_se
         RG_TRY(launch_work(ctx));
         if (prof) rec_event(ctx, ctx->evp[2]);
         cudaEventRecord(ctx->ev_work, ctx->stream);
-        cudaStreamWaitEvent(ctx->side2, ctx->ev_work, 0);
-        launch_se_dots(ctx);
-        // the weight recurrence follows the dots on the same side stream (it needs the steepest-edge scalars
-        // too); the main stream runs K1, the bookkeeping and the pricing of the next iteration meanwhile and
-        // joins before the column selection
-        cudaStreamWaitEvent(ctx->side2, ctx->ev_side1, 0);
-        {
-            cudaStream_t main_stream = ctx->stream;
-            ctx->stream = ctx->side2;
-            launch_se_update(ctx);
-            ctx->stream = main_stream;
+        if (!ctx->serial_side) {
+            cudaStreamWaitEvent(ctx->side2, ctx->ev_work, 0);
+            launch_se_dots(ctx);
+            // the weight recurrence follows the dots on the same side stream (it needs the steepest-edge scalars
+            // too); the main stream runs K1, the bookkeeping and the pricing of the next iteration meanwhile and
+            // joins before the column selection
+            cudaStreamWaitEvent(ctx->side2, ctx->ev_side1, 0);
+            {
+                cudaStream_t main_stream = ctx->stream;
+                ctx->stream = ctx->side2;
+                launch_se_update(ctx);
+                ctx->stream = main_stream;
+            }
+            cudaEventRecord(ctx->ev_side3, ctx->side2);
         }
-        cudaEventRecord(ctx->ev_side3, ctx->side2);
         cudaStreamWaitEvent(ctx->stream, ctx->ev_side2, 0);
     } else {
         if (prof) rec_event(ctx, ctx->evp[2]);
@@ -1166,6 +1236,19 @@ static int enqueue_iteration(rg_context* ctx, int q, int fixed_row, bool want_se
     if (prof1) rec_event(ctx, ctx->ev0);
     launch_update(ctx, E);
     if (prof1) rec_event(ctx, ctx->ev1);
+    if (want_se && ctx->serial_side) {     // experiment switch: dots and recurrence after K1, not beside it
+        cudaEventRecord(ctx->ev_work, ctx->stream);
+        cudaStreamWaitEvent(ctx->side2, ctx->ev_work, 0);
+        launch_se_dots(ctx);
+        cudaStreamWaitEvent(ctx->side2, ctx->ev_side1, 0);
+        {
+            cudaStream_t main_stream = ctx->stream;
+            ctx->stream = ctx->side2;
+            launch_se_update(ctx);
+            ctx->stream = main_stream;
+        }
+        cudaEventRecord(ctx->ev_side3, ctx->side2);
+    }
     if (want_se) cudaStreamWaitEvent(ctx->stream, ctx->ev_side1, 0);     // k_finalize stores Ghat_q of k_scalars_se
     LAUNCH(k_finalize, 1, 1, ctx->basis, ctx->inbasis, ctx->L, ctx->G, ctx->n, LG_of(ctx->L),
            want_se ? 1 : 0, ctx->weighted ? ctx->wf : nullptr, ctx->weighted ? ctx->rowf : nullptr, ctx->sc,
@@ -1290,10 +1373,14 @@ static int do_pivot(rg_context* ctx, int q, int fixed_row, bool want_se, bool re
         }
         if (ctx->hm->pivoted) {
             static const bool trace_bits = getenv("RG_TRACE_BITS") != nullptr;
-            if (trace_bits && ctx->rank == 0)
-                fprintf(stderr, "RGBITS pivot=%lld L=%d maxbits=%d bitsD=%d t=%d nk=%d predicted=%d\n",
+            if (trace_bits && ctx->rank == 0) {
+                static double t_last = 0;
+                const double t_now = now_s();
+                fprintf(stderr, "RGBITS pivot=%lld L=%d maxbits=%d bitsD=%d t=%d nk=%d predicted=%d dt_us=%.0f\n",
                         (long long)ctx->pivots, ctx->L, ctx->hm->maxbits_carry, ctx->hm->bits_D, ctx->hm->t_next,
-                        ctx->hm->nk, ctx->hm->predicted);
+                        ctx->hm->nk, ctx->hm->predicted, (t_now - t_last) * 1e6);
+                t_last = t_now;
+            }
             ctx->pivots++;
             ctx->pivots_at[width_index(ctx->L)]++;
             if (ctx->profile) {
@@ -1756,7 +1843,7 @@ static int export_planar(rg_context* ctx, const u64* base, size_t stride, size_t
     LAUNCH(k_gather, cdiv(count, 256), 256, tmp, base, stride, idx0, step, count, nl);
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaMemcpyAsync(out, tmp, sizeof(u64) * (size_t)count * nl, cudaMemcpyDeviceToHost, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream));
-    cudaFreeAsync(tmp, ctx->stream);
+    free_dev_on(tmp, ctx->stream);
     return RG_OK;
 }
 
