@@ -386,4 +386,100 @@ k_update_items(u64* __restrict__ C, size_t ps, int ld, int nloc, int RT, int pre
     if (lane == 0 && maxb) atomicMax(&sc->maxbits_new, maxb);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Reduced costs by recurrence (steepest edge): kappa_j = D cbar_j of every priced column follows the cost row of
+// the carry through the pivot,
+//        kappa'_j = ( |a| kappa_j - sgn(a) kappa_q nu_j ) / D,        nu_j = rowp . a_j,
+// i.e. K1 applied to the vector kappa with nu as its pivot row and kappa_q = u[0] as the row factor.  nu is
+// computed for the weight update anyway, so the pricing dot over the constraint matrix (one more pass over the
+// int8 block, its byte slices and their recombination) is not needed after a steepest-edge pivot.  Values are
+// those of Tableau::relative_cost (tableau/mod.rs:106-112) -- exact arithmetic makes the two routes identical.
+// Leaving column: nu is not computed for basic columns; kappa' = -sgn(a) kappa_q (its nu is D).
+// Needs sc->A and sc->Dinv two limbs wider than K1 does (k_scalars provides them).
+// ---------------------------------------------------------------------------------------------
+template <int L, int E>
+__global__ void __launch_bounds__(128)
+k_kappa_update(int n, int d0, int d1, int s0, int s1, const unsigned char* __restrict__ inbasis,
+               const u64* __restrict__ nu, u64* __restrict__ kappa, const u64* __restrict__ u, size_t us,
+               Scalars* sc) {
+    constexpr int LU = L + 2, W = LU + E, N = 2 * W;
+    __shared__ u32 sA[N], sB[N];
+    __shared__ u64 sLeave[LU];
+    if (sc->status != ST_RUN) return;
+    if (sc->E != E) return;
+    const int tid = threadIdx.x;
+    if (tid < N) sA[tid] = reinterpret_cast<const u32*>(sc->A)[tid];
+    if (tid == 96) {       // Bn0 = -sgn(a) kappa_q inv(odd D) mod 2^(32 N), and -sgn(a) kappa_q itself
+        u64 kq[LU];
+#pragma unroll
+        for (int l = 0; l < LU; ++l) kq[l] = u[(size_t)l * us];
+        const u64 sgq = (i64)kq[LU - 1] < 0 ? ~0ull : 0ull;
+        u32 ui[N], b[N];
+#pragma unroll
+        for (int l = 0; l < W; ++l) {
+            u64 v = l < LU ? kq[l] : sgq;
+            ui[2 * l] = (u32)v; ui[2 * l + 1] = (u32)(v >> 32);
+        }
+        mp_mul_lo<N>(b, ui, reinterpret_cast<const u32*>(sc->Dinv));
+        if (sc->sgn > 0) {
+            u32 c = 1;
+#pragma unroll
+            for (int k = 0; k < N; ++k) { u32 v = ~b[k] + c; c = (c && v == 0) ? 1u : 0u; b[k] = v; }
+            u64 c2 = 1;
+#pragma unroll
+            for (int l = 0; l < LU; ++l) { u64 v = ~kq[l] + c2; c2 = (c2 && v == 0) ? 1 : 0; kq[l] = v; }
+        }
+#pragma unroll
+        for (int k = 0; k < N; ++k) sB[k] = b[k];
+#pragma unroll
+        for (int l = 0; l < LU; ++l) sLeave[l] = kq[l];
+    }
+    __syncthreads();
+    const int tix = blockIdx.x * blockDim.x + tid;
+    if (tix >= (d1 - d0) + (s1 - s0)) return;
+    const int j = tix < d1 - d0 ? d0 + tix : s0 + (tix - (d1 - d0));
+    if (j == sc->leaving) {
+#pragma unroll
+        for (int l = 0; l < LU; ++l) kappa[(size_t)l * n + j] = sLeave[l];
+        return;
+    }
+    if (inbasis[j]) return;        // basic columns keep kappa = 0 (the entering column's comes out 0 below)
+    u32 kv[N], nv[N];
+    {
+        const u64 tk = kappa[(size_t)(LU - 1) * n + j], tn = nu[(size_t)(LU - 1) * n + j];
+        const u64 sk = (i64)tk < 0 ? ~0ull : 0ull, sn = (i64)tn < 0 ? ~0ull : 0ull;
+#pragma unroll
+        for (int l = 0; l < W; ++l) {
+            u64 a = l < LU ? kappa[(size_t)l * n + j] : sk;
+            u64 b = l < LU ? nu[(size_t)l * n + j] : sn;
+            kv[2 * l] = (u32)a; kv[2 * l + 1] = (u32)(a >> 32);
+            nv[2 * l] = (u32)b; nv[2 * l + 1] = (u32)(b >> 32);
+        }
+    }
+    u32 X[N];
+    mp_mul2_lo<N>(X, kv, sA, nv, sB);
+    const int t = sc->t;
+    const int tw = t >> 5, tb = t & 31;
+    u32 o[2 * LU];
+    if (E == 0) {
+#pragma unroll
+        for (int q = 0; q < 2 * LU; ++q) o[q] = X[q];
+    } else {
+#pragma unroll
+        for (int ww = 0; ww <= 2 * E; ++ww) {
+            if (tw == ww) {
+#pragma unroll
+                for (int q = 0; q < 2 * LU; ++q) {
+                    u32 lo = X[q + ww < N ? q + ww : N - 1];
+                    u32 hi = (q + ww + 1 < N) ? X[q + ww + 1 < N ? q + ww + 1 : N - 1] : 0u;
+                    o[q] = __funnelshift_r(lo, hi, tb);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int l = 0; l < LU; ++l) kappa[(size_t)l * n + j] = (u64)o[2 * l] | ((u64)o[2 * l + 1] << 32);
+}
+
 }  // namespace rg

@@ -69,6 +69,29 @@ void launch_le(rg_context* ctx) {
     ctx->launches++;
 }
 
+template <int L, int E>
+void launch_kappa_le(rg_context* ctx) {
+    const int cnt = (ctx->d1 - ctx->d0) + (ctx->s1 - ctx->s0);
+    if (cnt <= 0) return;
+    k_kappa_update<L, E><<<cdiv(cnt, 128), 128, 0, ctx->stream>>>(ctx->n, ctx->d0, ctx->d1, ctx->s0, ctx->s1, ctx->inbasis,
+                                                                  ctx->nu, ctx->kappa, ctx->u, (size_t)ctx->ld, ctx->sc);
+    ctx->launches++;
+}
+template <int L>
+bool launch_kappa_t(rg_context* ctx, int E) {
+    switch (E) {
+        case 0: launch_kappa_le<L, 0>(ctx); return true;
+        case 1: launch_kappa_le<L, 1>(ctx); return true;
+        case 2: if constexpr (L >= 2) { launch_kappa_le<L, 2>(ctx); return true; } break;
+        case 3: if constexpr (L >= 4) { launch_kappa_le<L, 3>(ctx); return true; } break;
+        case 4: if constexpr (L >= 4) { launch_kappa_le<L, 4>(ctx); return true; } break;
+        case 6: if constexpr (L == 8 || L == 16) { launch_kappa_le<L, 6>(ctx); return true; } break;
+        case 8: if constexpr (L == 8 || L == 16) { launch_kappa_le<L, 8>(ctx); return true; } break;
+        default: break;
+    }
+    return false;
+}
+
 template <int L>
 bool launch_t(rg_context* ctx, int E) {
     switch (E) {
@@ -95,6 +118,14 @@ bool RG_K1_CAT(k1_launch_, RG_K1_L)(rg_context* ctx, int E) {
     cudaError_t e = cudaPeekAtLastError();
     if (e != cudaSuccess && ctx->launch_err.empty())
         ctx->launch_err = std::string("launch of k_update failed: ") + cudaGetErrorString(e);
+    return ok;
+}
+// the reduced-cost recurrence for the same (L, E) variant, on ctx->stream; false: no fixed-width variant covers E
+bool RG_K1_CAT(k1_kappa_launch_, RG_K1_L)(rg_context* ctx, int E) {
+    bool ok = launch_kappa_t<RG_K1_L>(ctx, E);
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess && ctx->launch_err.empty())
+        ctx->launch_err = std::string("launch of k_kappa_update failed: ") + cudaGetErrorString(e);
     return ok;
 }
 }  // namespace rg

@@ -318,16 +318,26 @@ k_dense_combine(const int* __restrict__ R, size_t rstride_k, int kslices, int rp
         // The 8 slice sums of the NEXT limb are fetched while the current limb's carry chain runs (the loop is
         // otherwise one memory latency per limb).
         long long cur[8], nxt[8];
+        // the 8 loads of a limb are unconditional (slice index clamped, value masked afterwards): guarded loads are
+        // issued one after the other, and this loop is nothing but their latency
         auto fetch = [&](long long (&dst)[8], int l) {
+            long long v[8];
+#pragma unroll
+            for (int b = 0; b < 8; ++b) v[b] = 0;
+            for (int k = 0; k < kslices; ++k) {
+                int w[8];
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    const int sidx = min(8 * l + b, nb);
+                    w[b] = R[(size_t)k * rstride_k + (size_t)sidx * rpitch + (j - jd0)];
+                }
+#pragma unroll
+                for (int b = 0; b < 8; ++b) v[b] += w[b];
+            }
 #pragma unroll
             for (int b = 0; b < 8; ++b) {
                 const int sidx = 8 * l + b;
-                long long v = 0;
-                if (sidx <= nb) {
-                    for (int k = 0; k < kslices; ++k) v += R[(size_t)k * rstride_k + (size_t)sidx * rpitch + (j - jd0)];
-                    if (sidx == nb) v = -v;
-                }
-                dst[b] = v;
+                dst[b] = sidx < nb ? v[b] : (sidx == nb ? -v[b] : 0);
             }
         };
         fetch(cur, 0);
@@ -1289,14 +1299,17 @@ __global__ void k_scalars(int L, int E_host, Scalars* sc) {
     if (E < ((t + 63) >> 6)) { sc->status = ST_FATAL; sc->fatal = 2; return; }   // variant too narrow for ctz(D)
     for (int l = 0; l < L; ++l) dodd[l] = sc->D[l];
     rt_shr(dodd, L, t);
-    rt_inv_odd(inv, dodd, L, W, ws);
+    // two limbs beyond the K1 width: the reduced-cost recurrence (k_kappa_update) divides (L+2)-limb numbers; the
+    // low W limbs are the W-limb inverse / factor (2-adic truncation), so K1 reads the same arrays
+    const int W2 = W + 2;
+    rt_inv_odd(inv, dodd, L, W2, ws);
 #ifdef RG_DEBUG_PRINT
     printf("scalars: right after inv: inv0=%llu dodd0=%llu L=%d W=%d\n", inv[0], dodd[0], L, W);
 #endif
-    for (int l = 0; l < W; ++l) sc->Dinv[l] = inv[l];
-    for (int l = 0; l < W; ++l) ext[l] = l < LU ? am[l] : 0;
-    rt_mul_lo(tmp, ext, inv, W);
-    for (int l = 0; l < W; ++l) sc->A[l] = tmp[l];
+    for (int l = 0; l < W2; ++l) sc->Dinv[l] = inv[l];
+    for (int l = 0; l < W2; ++l) ext[l] = l < LU ? am[l] : 0;
+    rt_mul_lo(tmp, ext, inv, W2);
+    for (int l = 0; l < W2; ++l) sc->A[l] = tmp[l];
 #ifdef RG_DEBUG_PRINT
     printf("scalars: L=%d t=%d E=%d W=%d D0=%llu dodd0=%llu inv0=%llu am0=%llu A0=%llu\n", L, t, E, W, sc->D[0], dodd[0], inv[0], am[0], tmp[0]);
 #endif
@@ -1547,6 +1560,55 @@ struct ColScan {
     }
 };
 
+// Four columns at a time (K .. K+3, four independent IMAD.WIDE chains per thread): with three warps per sub-partition
+// two chains per warp still leave the multiply pipe waiting on the dependent accumulate.  The four 96-bit column sums
+// are folded as A + B 2^32 + C 2^64 + D 2^96 into six words: the low four are limbs K .. K+3, the upper two seed
+// the next group (every column sum is < NB 2^64, so word 6 stays zero).
+template <int NA, int NB, int K, int I>
+struct ColQuadTerms {
+    __device__ static __forceinline__ void run(u32 (&a)[3], u32 (&b)[3], u32 (&c)[3], u32 (&d)[3], const u32 (&x)[NA],
+                                               const u32 (&m)[NB]) {
+        if constexpr (I < NA && K - I >= 0 && K - I < NB)
+            asm volatile("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, %2, 0;"
+                         : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]) : "r"(x[I]), "r"(m[K - I]));
+        if constexpr (I < NA && K + 1 - I >= 0 && K + 1 - I < NB)
+            asm volatile("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, %2, 0;"
+                         : "+r"(b[0]), "+r"(b[1]), "+r"(b[2]) : "r"(x[I]), "r"(m[K + 1 - I]));
+        if constexpr (I < NA && K + 2 - I >= 0 && K + 2 - I < NB)
+            asm volatile("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, %2, 0;"
+                         : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]) : "r"(x[I]), "r"(m[K + 2 - I]));
+        if constexpr (I < NA && K + 3 - I >= 0 && K + 3 - I < NB)
+            asm volatile("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, %2, 0;"
+                         : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]) : "r"(x[I]), "r"(m[K + 3 - I]));
+        if constexpr (I + 1 < NA && I + 1 <= K + 3) ColQuadTerms<NA, NB, K, I + 1>::run(a, b, c, d, x, m);
+    }
+};
+template <int NA, int NB, int NW, int K>
+struct ColScan4 {
+    __device__ static __forceinline__ void run(u32 (&acc)[NW], u32& s0, u32& s1, u32& s2, const u32 (&x)[NA],
+                                               const u32 (&m)[NB]) {
+        if constexpr (K + 4 <= NW) {
+            u32 a[3] = {s0, s1, s2}, b[3] = {acc[K + 1], 0, 0}, c[3] = {acc[K + 2], 0, 0}, d[3] = {acc[K + 3], 0, 0};
+            asm volatile("add.cc.u32 %0, %0, %3;\n\taddc.cc.u32 %1, %1, 0;\n\taddc.u32 %2, %2, 0;"
+                         : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]) : "r"(acc[K]));
+            ColQuadTerms<NA, NB, K, (K - NB + 1 > 0 ? K - NB + 1 : 0)>::run(a, b, c, d, x, m);
+            u32 r1 = a[1], r2 = a[2], r3 = 0, r4 = 0, r5 = 0;
+            asm volatile("add.cc.u32 %0, %0, %5;\n\taddc.cc.u32 %1, %1, %6;\n\taddc.cc.u32 %2, %2, %7;\n\t"
+                         "addc.cc.u32 %3, %3, 0;\n\taddc.u32 %4, %4, 0;"
+                         : "+r"(r1), "+r"(r2), "+r"(r3), "+r"(r4), "+r"(r5) : "r"(b[0]), "r"(b[1]), "r"(b[2]));
+            asm volatile("add.cc.u32 %0, %0, %4;\n\taddc.cc.u32 %1, %1, %5;\n\taddc.cc.u32 %2, %2, %6;\n\taddc.u32 %3, %3, 0;"
+                         : "+r"(r2), "+r"(r3), "+r"(r4), "+r"(r5) : "r"(c[0]), "r"(c[1]), "r"(c[2]));
+            asm volatile("add.cc.u32 %0, %0, %3;\n\taddc.cc.u32 %1, %1, %4;\n\taddc.u32 %2, %2, %5;"
+                         : "+r"(r3), "+r"(r4), "+r"(r5) : "r"(d[0]), "r"(d[1]), "r"(d[2]));
+            acc[K] = a[0]; acc[K + 1] = r1; acc[K + 2] = r2; acc[K + 3] = r3;
+            s0 = r4; s1 = r5; s2 = 0;
+            ColScan4<NA, NB, NW, K + 4>::run(acc, s0, s1, s2, x, m);
+        } else if constexpr (K + 2 <= NW) {
+            ColScan<NA, NB, NW, K>::run(acc, s0, s1, s2, x, m);     // NW = 2 (mod 4): the last two columns as a pair
+        }
+    }
+};
+
 // Thread mapping: a block is 32 column slots x 4 row groups (one warp each: a warp reads 32 consecutive entries of
 // one row, 256 B per limb plane); the four groups split the rows of the chunk and their partial sums are added
 // through shared memory at the end of a pass, so a chunk still produces one slab per pass.
@@ -1648,7 +1710,7 @@ k_colsum1(const u64* __restrict__ C, size_t ps, int ld, int m, int rows_per_chun
 #pragma unroll
                 for (int l = 0; l < NB; ++l) mg[l] = sMag[r][l];
                 u32 c0 = 0, c1 = 0, c2 = 0;
-                ColScan<NA, NB, NW, 0>::run(acc, c0, c1, c2, x, mg);
+                ColScan4<NA, NB, NW, 0>::run(acc, c0, c1, c2, x, mg);
             }
         }
         // add the four row groups' partial sums (group 0 keeps the result)

@@ -317,6 +317,7 @@ static int alloc_width_buffers(rg_context* ctx, int L) {
     CK(cudaMemsetAsync(ctx->u, 0, sizeof(u64) * LU_of(L) * ld, ctx->stream));
     CK(cudaMemsetAsync(ctx->rowp, 0, sizeof(u64) * L * ld, ctx->stream));
     CK(cudaMemsetAsync(ctx->kappa, 0, sizeof(u64) * LU_of(L) * n, ctx->stream));
+    ctx->kappa_valid = false;
     return RG_OK;
 }
 static void free_width_buffers(rg_context* ctx) {
@@ -352,7 +353,7 @@ extern "C" int rg_create(const rg_options* opts, rg_context** out) {
     ctx->use_graphs = getenv("RG_NO_GRAPH") == nullptr;
     { const char* e = getenv("RG_GRAPH_NCCL"); ctx->graph_nccl = e && atoi(e) != 0; }
     ctx->k1_items_prefetch = getenv("RG_K1_NOPF") == nullptr;
-    ctx->serial_side = getenv("RG_SERIAL_SIDE") != nullptr;
+    ctx->kappa_recur = getenv("RG_NO_KAPPA_RECUR") == nullptr;
     { const char* e = getenv("RG_K1_ITEMS_MINL"); if (e) ctx->k1_items_min_limbs = atoi(e); }
     { const char* e = getenv("RG_K1_ITEMS_ROWS"); if (e) ctx->k1_items_rows = std::min(32, std::max(1, atoi(e))); }
     { const char* e = getenv("RG_WIDTH_LADDER"); ctx->pow2_only = e && strcmp(e, "pow2") == 0; }
@@ -370,6 +371,7 @@ extern "C" int rg_create(const rg_options* opts, rg_context** out) {
     CK(cudaEventCreateWithFlags(&ctx->ev_side2, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_work, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_side3, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->ev_nu, cudaEventDisableTiming));
     CK(cudaStreamCreateWithFlags(&ctx->side2, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&ctx->side3, cudaStreamNonBlocking));
     CK(dev_alloc(&ctx->sc, sizeof(Scalars), ctx->stream));
@@ -463,7 +465,7 @@ extern "C" int rg_destroy(rg_context* ctx) {
         g_prof_events[ctx->device & 15].push_back(pe);
     }
     if (ctx->evt0) { cudaEventDestroy(ctx->evt0); cudaEventDestroy(ctx->evt1); }
-    if (ctx->ev_side0) { cudaEventDestroy(ctx->ev_side0); cudaEventDestroy(ctx->ev_side1); cudaEventDestroy(ctx->ev_side2); cudaEventDestroy(ctx->ev_work); cudaEventDestroy(ctx->ev_side3); }
+    if (ctx->ev_side0) { cudaEventDestroy(ctx->ev_side0); cudaEventDestroy(ctx->ev_side1); cudaEventDestroy(ctx->ev_side2); cudaEventDestroy(ctx->ev_work); cudaEventDestroy(ctx->ev_side3); cudaEventDestroy(ctx->ev_nu); }
     if (ctx->side2) cudaStreamDestroy(ctx->side2);
     if (ctx->side3) cudaStreamDestroy(ctx->side3);
     // the communicator is process-cached (see rg_create) unless this context owns it
@@ -753,7 +755,7 @@ static void launch_coldots(rg_context* ctx, const u64* vec, size_t vs, int cmul,
             LAUNCH((k_dense_mma<NTC>), grid, 256, ctx->Acm, ctx->ldc, jd0, jd1, ctx->dSl, ctx->dmp, ctx->dchunk, bits, LV,
                    g.rps, ctx->dR, g.rstride_k, g.rpitch, ctx->sc);
         }
-        LAUNCH((k_dense_combine<LV, LO>), cdiv(g.ncols, 128), 128, ctx->dR, g.rstride_k, g.ks, g.rpitch, ctx->n, jd0,
+        LAUNCH((k_dense_combine<LV, LO>), cdiv(g.ncols, 64), 64, ctx->dR, g.rstride_k, g.ks, g.rpitch, ctx->n, jd0,
                jd1, bits, ctx->inbasis, ctx->cost, cmul, ctx->L, out, ctx->sc);
     }
     if (j1 > j0 && csc_part)
@@ -767,7 +769,7 @@ static void launch_price_t(rg_context* ctx) {
     launch_coldots<L, L + 2>(ctx, ctx->carry, ctx->plane, 1, ctx->kappa, &ctx->sc->maxbits_carry);
     if (ctx->dR2) { std::swap(ctx->dR, ctx->dR2); std::swap(ctx->dSl, ctx->dSl2); std::swap(ctx->dchunk, ctx->dchunk2); }
 }
-static void launch_price(rg_context* ctx) { DISPATCH_L(ctx->L, launch_price_t, ctx); }
+static void launch_price(rg_context* ctx) { DISPATCH_L(ctx->L, launch_price_t, ctx); ctx->kappa_valid = true; }
 
 template <class Cmp>
 static void launch_argbest(rg_context* ctx, int off, int count, const Cmp& cmp, int mode) {
@@ -1034,6 +1036,27 @@ bool k1_launch_10(rg_context*, int);
 bool k1_launch_12(rg_context*, int);
 bool k1_launch_14(rg_context*, int);
 bool k1_launch_16(rg_context*, int);
+bool k1_kappa_launch_1(rg_context*, int);
+bool k1_kappa_launch_2(rg_context*, int);
+bool k1_kappa_launch_4(rg_context*, int);
+bool k1_kappa_launch_8(rg_context*, int);
+bool k1_kappa_launch_10(rg_context*, int);
+bool k1_kappa_launch_12(rg_context*, int);
+bool k1_kappa_launch_14(rg_context*, int);
+bool k1_kappa_launch_16(rg_context*, int);
+}
+// reduced costs by recurrence (k_kappa_update) on ctx->stream; false when no fixed-width variant covers E
+static bool launch_kappa_update(rg_context* ctx, int E) {
+    switch (ctx->L) {
+        case 1: return k1_kappa_launch_1(ctx, E);
+        case 2: return k1_kappa_launch_2(ctx, E);
+        case 4: return k1_kappa_launch_4(ctx, E);
+        case 8: return k1_kappa_launch_8(ctx, E);
+        case 10: return k1_kappa_launch_10(ctx, E);
+        case 12: return k1_kappa_launch_12(ctx, E);
+        case 14: return k1_kappa_launch_14(ctx, E);
+        default: return k1_kappa_launch_16(ctx, E);
+    }
 }
 static void launch_update(rg_context* ctx, int E) {
     bool ok = false;
@@ -1053,25 +1076,42 @@ static void launch_update(rg_context* ctx, int E) {
            (size_t)ctx->ld, ctx->rowp, (size_t)ctx->ld, ctx->sc);
 }
 
+// The steepest-edge dots, in three pieces so that they can run beside the work vector on their own streams:
+//   nu_j = rowp . a_j          (needs the staged pivot row only; tensor-core scratch set 2)
+//   tau_j = s . a_j            (split mode: needs the factor vector only; scratch set 1)
+//   sigma_j = omega . a_j      (needs the work vector; split mode: omega on the listed columns + D tau)
+static inline bool split_sigma(rg_context* ctx) {
+    return ctx->list_mode && ctx->d1 > ctx->d0 && (ctx->world == 1 || ctx->ufull_valid);
+}
 template <int L>
-static void launch_se_dots_t(rg_context* ctx) {
-    constexpr int LU = L + 2, LW = LW_of(L), LS = LS_of(L);
+static void launch_nu_dot_t(rg_context* ctx) {
+    constexpr int LU = L + 2;
+    if (ctx->dR2) { std::swap(ctx->dR, ctx->dR2); std::swap(ctx->dSl, ctx->dSl2); std::swap(ctx->dchunk, ctx->dchunk2); }
     launch_coldots<L, LU>(ctx, ctx->rowp, (size_t)ctx->ld, 0, ctx->nu, &ctx->sc->maxbits_rowp);
-    if (ctx->list_mode && ctx->d1 > ctx->d0 && (ctx->world == 1 || ctx->ufull_valid)) {
-        const u64* fvec = ctx->world == 1 ? (ctx->weighted ? ctx->us2 : ctx->u) : ctx->ufull;
+    if (ctx->dR2) { std::swap(ctx->dR, ctx->dR2); std::swap(ctx->dSl, ctx->dSl2); std::swap(ctx->dchunk, ctx->dchunk2); }
+}
+template <int L>
+static void launch_tau_dot_t(rg_context* ctx) {
+    constexpr int LU = L + 2;
+    const u64* fvec = ctx->world == 1 ? (ctx->weighted ? ctx->us2 : ctx->u) : ctx->ufull;
+    if (ctx->weighted) launch_coldots<LU + 1, LU + 3>(ctx, fvec, (size_t)ctx->ld, 0, ctx->tau, &ctx->sc->maxbits_s, 1, false);
+    else launch_coldots<LU, LU + 2>(ctx, fvec, (size_t)ctx->ld, 0, ctx->tau, &ctx->sc->maxbits_u, 1, false);
+}
+template <int L>
+static void launch_sigma_dot_t(rg_context* ctx, bool tau_done) {
+    constexpr int LU = L + 2, LW = LW_of(L), LS = LS_of(L);
+    if (split_sigma(ctx)) {
         // split sigma dot over the dense block: the work vector on the trivial carry columns
         // is D * s_k, so the wide (2L+5 limb) vector only has to cover the LISTED columns (a few 64-row chunks: the
         // others are skipped as zero) and the long dot runs on the (L+2)-limb factor vector s -- half the slices
+        if (!tau_done) launch_tau_dot_t<L>(ctx);
         launch_coldots<LW, LS>(ctx, ctx->omega, (size_t)ctx->ld, 0, ctx->sigma, &ctx->sc->maxbits_tmp, 2, true);
-        if (ctx->weighted) {
-            launch_coldots<LU + 1, LU + 3>(ctx, fvec, (size_t)ctx->ld, 0, ctx->tau, &ctx->sc->maxbits_s, 1, false);
+        if (ctx->weighted)
             LAUNCH((k_sigma_add_dtau<LU + 3, L, LS>), cdiv(ctx->d1 - ctx->d0, 128), 128, ctx->tau, ctx->n, ctx->d0, ctx->d1,
                    ctx->inbasis, ctx->sigma, ctx->sc);
-        } else {
-            launch_coldots<LU, LU + 2>(ctx, fvec, (size_t)ctx->ld, 0, ctx->tau, &ctx->sc->maxbits_u, 1, false);
+        else
             LAUNCH((k_sigma_add_dtau<LU + 2, L, LS>), cdiv(ctx->d1 - ctx->d0, 128), 128, ctx->tau, ctx->n, ctx->d0, ctx->d1,
                    ctx->inbasis, ctx->sigma, ctx->sc);
-        }
         return;
     }
     launch_coldots<LW, LS>(ctx, ctx->omega, (size_t)ctx->ld, 0, ctx->sigma, &ctx->sc->maxbits_tmp);
@@ -1081,12 +1121,23 @@ static void launch_gamma_update_t(rg_context* ctx) {
     LAUNCH((k_gamma_update_t<L>), cdiv(std::max(own_of(ctx).count(), 1), 64), 64, ctx->n, own_of(ctx), ctx->inbasis,
            ctx->nu, ctx->sigma, ctx->G, ctx->sc);
 }
-// nu_j = rowp . a_j and sigma_j = omega . a_j read only staged vectors and the constraint matrix, so they run
-// on the second side stream concurrently with K1 (LAUNCH goes to ctx->stream: swapped for the duration)
-static void launch_se_dots(rg_context* ctx) {
+// LAUNCH goes to ctx->stream: swapped to the given side stream for the duration
+static void launch_nu_dot(rg_context* ctx, cudaStream_t st) {
     cudaStream_t main_stream = ctx->stream;
-    ctx->stream = ctx->side2;
-    DISPATCH_L(ctx->L, launch_se_dots_t, ctx);
+    ctx->stream = st;
+    DISPATCH_L(ctx->L, launch_nu_dot_t, ctx);
+    ctx->stream = main_stream;
+}
+static void launch_tau_dot(rg_context* ctx, cudaStream_t st) {
+    cudaStream_t main_stream = ctx->stream;
+    ctx->stream = st;
+    DISPATCH_L(ctx->L, launch_tau_dot_t, ctx);
+    ctx->stream = main_stream;
+}
+static void launch_sigma_dot(rg_context* ctx, cudaStream_t st, bool tau_done) {
+    cudaStream_t main_stream = ctx->stream;
+    ctx->stream = st;
+    DISPATCH_L(ctx->L, launch_sigma_dot_t, ctx, tau_done);
     ctx->stream = main_stream;
 }
 static void launch_se_update(rg_context* ctx) {
@@ -1186,6 +1237,11 @@ static int switch_to_dense(rg_context* ctx) {
 // vector, scalars, K1, bookkeeping, rule update, pricing of the next iteration
 static int enqueue_iteration(rg_context* ctx, int q, int fixed_row, bool want_se, bool reselect, int E) {
     const bool prof = ctx->profile >= 2, prof1 = ctx->profile >= 1;
+    // steepest edge: the next reduced costs follow from the current ones and the pivot-row dots nu (k_kappa_update)
+    // when the current ones are valid and a fixed-width division variant is in use; otherwise they are priced
+    // from the new cost row (launch_price)
+    const bool kappa_recur = want_se && reselect && ctx->kappa_valid && ctx->kappa_recur &&
+                             pick_update_variant(ctx->L, E) == E;
     if (prof) rec_event(ctx, ctx->evp[0]);
     LAUNCH(k_reset_iter, 1, 1, ctx->sc);
     launch_ftran(ctx, q);
@@ -1210,24 +1266,37 @@ static int enqueue_iteration(rg_context* ctx, int q, int fixed_row, bool want_se
         k_scalars_se<<<1, 32, 0, ctx->side3>>>(ctx->L, ctx->world == 1 ? ctx->G : nullptr, ctx->n, ctx->basis, ctx->sc);
         ctx->launches += 2;
         cudaEventRecord(ctx->ev_side1, ctx->side3);
+        // nu = rowp . A needs only the staged pivot row: it streams the constraint block on the first side stream
+        // (tensor-core scratch set 2) while the main stream builds the work vector; in the split mode of a
+        // single-GPU unweighted run tau = s . A (the factor vector is the pivot column) does the same on side2
+        launch_nu_dot(ctx, ctx->side);
+        cudaEventRecord(ctx->ev_nu, ctx->side);
+        const bool early_tau = ctx->list_mode && ctx->d1 > ctx->d0 && ctx->world == 1 && !ctx->weighted;
+        if (early_tau) {
+            cudaStreamWaitEvent(ctx->side2, ctx->ev_side0, 0);
+            launch_tau_dot(ctx, ctx->side2);
+        }
         RG_TRY(launch_work(ctx));
         if (prof) rec_event(ctx, ctx->evp[2]);
         cudaEventRecord(ctx->ev_work, ctx->stream);
-        if (!ctx->serial_side) {
-            cudaStreamWaitEvent(ctx->side2, ctx->ev_work, 0);
-            launch_se_dots(ctx);
-            // the weight recurrence follows the dots on the same side stream (it needs the steepest-edge scalars
-            // too); the main stream runs K1, the bookkeeping and the pricing of the next iteration meanwhile and
-            // joins before the column selection
-            cudaStreamWaitEvent(ctx->side2, ctx->ev_side1, 0);
-            {
-                cudaStream_t main_stream = ctx->stream;
-                ctx->stream = ctx->side2;
-                launch_se_update(ctx);
-                ctx->stream = main_stream;
+        cudaStreamWaitEvent(ctx->side2, ctx->ev_work, 0);
+        launch_sigma_dot(ctx, ctx->side2, early_tau);
+        // the reduced-cost and weight recurrences follow on the same side stream (they need nu, the leaving column
+        // and the steepest-edge scalars of k_scalars_se, and A, Dinv of k_scalars); the main stream runs K1 and the
+        // bookkeeping meanwhile and joins before the column selection
+        cudaStreamWaitEvent(ctx->side2, ctx->ev_side1, 0);
+        cudaStreamWaitEvent(ctx->side2, ctx->ev_nu, 0);
+        {
+            cudaStream_t main_stream = ctx->stream;
+            ctx->stream = ctx->side2;
+            if (kappa_recur) {
+                cudaStreamWaitEvent(ctx->side2, ctx->ev_side2, 0);
+                launch_kappa_update(ctx, E);
             }
-            cudaEventRecord(ctx->ev_side3, ctx->side2);
+            launch_se_update(ctx);
+            ctx->stream = main_stream;
         }
+        cudaEventRecord(ctx->ev_side3, ctx->side2);
         cudaStreamWaitEvent(ctx->stream, ctx->ev_side2, 0);
     } else {
         if (prof) rec_event(ctx, ctx->evp[2]);
@@ -1236,25 +1305,16 @@ static int enqueue_iteration(rg_context* ctx, int q, int fixed_row, bool want_se
     if (prof1) rec_event(ctx, ctx->ev0);
     launch_update(ctx, E);
     if (prof1) rec_event(ctx, ctx->ev1);
-    if (want_se && ctx->serial_side) {     // experiment switch: dots and recurrence after K1, not beside it
-        cudaEventRecord(ctx->ev_work, ctx->stream);
-        cudaStreamWaitEvent(ctx->side2, ctx->ev_work, 0);
-        launch_se_dots(ctx);
-        cudaStreamWaitEvent(ctx->side2, ctx->ev_side1, 0);
-        {
-            cudaStream_t main_stream = ctx->stream;
-            ctx->stream = ctx->side2;
-            launch_se_update(ctx);
-            ctx->stream = main_stream;
-        }
-        cudaEventRecord(ctx->ev_side3, ctx->side2);
-    }
     if (want_se) cudaStreamWaitEvent(ctx->stream, ctx->ev_side1, 0);     // k_finalize stores Ghat_q of k_scalars_se
     LAUNCH(k_finalize, 1, 1, ctx->basis, ctx->inbasis, ctx->L, ctx->G, ctx->n, LG_of(ctx->L),
            want_se ? 1 : 0, ctx->weighted ? ctx->wf : nullptr, ctx->weighted ? ctx->rowf : nullptr, ctx->sc,
            ctx->hm_dev);
     if (prof) rec_event(ctx, ctx->evp[3]);
-    if (reselect) launch_price(ctx);
+    if (reselect && !kappa_recur) {
+        if (want_se) cudaStreamWaitEvent(ctx->stream, ctx->ev_nu, 0);      // scratch set 2 is the nu dot's
+        launch_price(ctx);
+    }
+    ctx->kappa_valid = reselect;       // priced for the carry this iteration leaves behind (either route), or stale
     if (want_se) cudaStreamWaitEvent(ctx->stream, ctx->ev_side3, 0);     // dots + weight recurrence done
     if (reselect) RG_TRY(launch_select(ctx));
     if (prof) rec_event(ctx, ctx->evp[4]);
@@ -1419,7 +1479,7 @@ static int do_pivot(rg_context* ctx, int q, int fixed_row, bool want_se, bool re
 // constructors
 // ------------------------------------------------------------------------------------------------
 extern "C" int rg_init_identity_basis(rg_context* ctx, const int32_t* basis, const int64_t* cost) {
-    if (ctx) ctx->demote_need = 0;   // the carry is rebuilt / re-priced: the last pivot's bit bound no longer covers it
+    if (ctx) { ctx->demote_need = 0; ctx->kappa_valid = false; }   // the carry is rebuilt / re-priced: the last pivot's bit bound no longer covers it
     if (ctx) drop_graphs(ctx);   // state the captured launch sequence depends on may change
     if (!ctx || !ctx->carry || !basis) return RG_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
@@ -1485,7 +1545,7 @@ extern "C" int rg_init_identity_basis(rg_context* ctx, const int32_t* basis, con
 // engine's own rank-1 update in a row that still holds an artificial; the rows are permuted at the end so that
 // row i holds basis[i], and the costs are installed like at a phase switch.
 extern "C" int rg_init_basis(rg_context* ctx, const int32_t* basis, const int64_t* cost) {
-    if (ctx) ctx->demote_need = 0;   // the carry is rebuilt / re-priced: the last pivot's bit bound no longer covers it
+    if (ctx) { ctx->demote_need = 0; ctx->kappa_valid = false; }   // the carry is rebuilt / re-priced: the last pivot's bit bound no longer covers it
     if (!ctx || !ctx->carry || !basis || !cost) return RG_ERR_ARG;
     if (ctx->world > 1) { ctx->err = "rg_init_basis: single GPU only (the final row permutation is not sharded)"; return RG_ERR_STATE; }
     const int m = ctx->m, n = ctx->n;
@@ -1605,7 +1665,7 @@ static int launch_phase_sums(rg_context* ctx) {
 }
 
 extern "C" int rg_phase_switch(rg_context* ctx, const int64_t* cost) {
-    if (ctx) ctx->demote_need = 0;   // the carry is rebuilt / re-priced: the last pivot's bit bound no longer covers it
+    if (ctx) { ctx->demote_need = 0; ctx->kappa_valid = false; }   // the carry is rebuilt / re-priced: the last pivot's bit bound no longer covers it
     if (ctx) drop_graphs(ctx);   // state the captured launch sequence depends on may change
     if (!ctx || !ctx->carry || !cost) return RG_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
