@@ -2423,6 +2423,61 @@ k_gamma_update(int n, ColOwn own, int L, const unsigned char* __restrict__ inbas
     rt_store_planar(G, n, j, x, LG);
 }
 
+// The same recurrence with the five products of a column spread over three warps of the block (role = warp):
+//   warp 0: S1 Ghat          warp 1: (nu sigma) S2          warp 2: (nu nu) S3
+// for the block's 32 columns (thread = column within each warp), exchanged through shared memory and folded by
+// warp 0.  One thread per column makes the launch as long as five dependent 40-limb products of a single thread
+// whatever the number of columns (it did not shrink under column sharding); this form is two products long.
+__global__ void __launch_bounds__(96)
+k_gamma_update3(int n, ColOwn own, int L, const unsigned char* __restrict__ inbasis, const u64* __restrict__ nu,
+                const u64* __restrict__ sigma, u64* __restrict__ G, const Scalars* sc) {
+    extern __shared__ u64 sX[];            // [2][WX][32]: results of warps 1 and 2
+    if (sc->status != ST_RUN) return;
+    const int role = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tix = blockIdx.x * 32 + lane;
+    const int LU = L + 2, LS = 2 * L + 7, LG = 2 * L + 6;
+    const int WX = LG + sc->E2;
+    bool act = tix < own.count();
+    const int j = act ? own.at(tix) : 0;
+    if (act && (inbasis[j] || j == sc->leaving)) act = false;   // entering: None; leaving: set by k_finalize
+    u64 buf[4 * RG_MAXW];                  // ONE local buffer, sliced by hand (see bigint.cuh)
+    u64* raw = buf; u64* v = buf + RG_MAXW; u64* y = buf + 2 * RG_MAXW; u64* z = buf + 3 * RG_MAXW;
+    bool nz = false;
+    if (act) {
+        rt_load_planar(raw, LU, nu, n, j);
+        nz = !rt_is_zero(raw, LU);         // alpha_j_bar == 0: gamma unchanged, Ghat' = Ghat a^2 / D^2
+        if (role == 0) {
+            rt_load_planar(raw, LG, G, n, j);
+            for (int l = 0; l < WX; ++l) v[l] = l < LG ? raw[l] : 0;
+            rt_mul_lo(z, sc->S1, v, WX);                  // a^2/D^2 Ghat
+        } else if (nz) {
+            rt_sext(v, WX, raw, LU);
+            if (role == 1) {
+                rt_load_planar(raw, LS, sigma, n, j);
+                rt_sext(y, WX, raw, LS);
+                rt_mul_lo(z, v, y, WX);                   // nu sigma
+                rt_mul_lo(y, sc->S2, z, WX);              // 2a/D^2 nu sigma
+            } else {
+                rt_mul_lo(z, v, v, WX);                   // nu^2
+                rt_mul_lo(y, sc->S3, z, WX);              // Gq/D^2 nu^2
+            }
+            u64* dst = sX + (size_t)(role - 1) * WX * 32 + lane;
+            for (int l = 0; l < WX; ++l) dst[(size_t)l * 32] = y[l];
+        }
+    }
+    __syncthreads();
+    if (act && role == 0) {
+        if (nz) {
+            for (int l = 0; l < WX; ++l) y[l] = sX[(size_t)l * 32 + lane];
+            rt_sub(z, y, WX);
+            for (int l = 0; l < WX; ++l) y[l] = sX[((size_t)WX + l) * 32 + lane];
+            rt_add(z, y, WX);
+        }
+        rt_shr(z, WX, sc->t2);
+        rt_store_planar(G, n, j, z, LG);
+    }
+}
+
 // b_p != 0 ?  (remove_artificial_basis_variables, phase_one.rs:250) -- read from the staged row
 __global__ void k_bp_nonzero(const u64* rowp, size_t rs, int L, Scalars* sc) {
     if (threadIdx.x || blockIdx.x) return;

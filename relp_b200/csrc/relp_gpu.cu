@@ -1151,8 +1151,19 @@ static void launch_se_update(rg_context* ctx) {
             default: launch_gamma_update_t<8>(ctx); break;
         }
     } else {
-        LAUNCH(k_gamma_update, cdiv(std::max(own_of(ctx).count(), 1), 128), 128, ctx->n, own_of(ctx), ctx->L,
-               ctx->inbasis, ctx->nu, ctx->sigma, ctx->G, ctx->sc);
+        static const bool one_thread = getenv("RG_GAMMA1") != nullptr;
+        if (one_thread) {
+            LAUNCH(k_gamma_update, cdiv(std::max(own_of(ctx).count(), 1), 128), 128, ctx->n, own_of(ctx), ctx->L,
+                   ctx->inbasis, ctx->nu, ctx->sigma, ctx->G, ctx->sc);
+        } else {
+            // three warps per 32 columns (k_gamma_update3); shared memory: two WX-limb results per column
+            // sized for any ctz(D) < 64 L (a captured launch is replayed while the division width grows)
+            const int WX = LG_of(ctx->L) + std::max(2 * ctx->L, 4);
+            const size_t smem = (size_t)2 * WX * 32 * sizeof(u64);
+            k_gamma_update3<<<cdiv(std::max(own_of(ctx).count(), 1), 32), 96, smem, ctx->stream>>>(
+                ctx->n, own_of(ctx), ctx->L, ctx->inbasis, ctx->nu, ctx->sigma, ctx->G, ctx->sc);
+            ctx->launches++;
+        }
     }
     if (ctx->profile >= 2) rec_event(ctx, ctx->evp[6]);    // after the recurrence
 }
