@@ -402,7 +402,8 @@ def main():
                 traffic_src = ent
         mode = "active-column mode (packed block)" if g.stats.get("active_columns", 0) else "dense carry"
         roof = {"bound": "imad" if imad_bound else "hbm",
-                "kernel": f"k_update<L={Ldom}> {mode}: rank-1 Bareiss pivot of the carry, as run by the timed steps",
+                "kernel": (f"k_update_items<L={Ldom}> + k_bn_rows + cost-row k_update" if mode.startswith("active") and Ldom >= 8
+                           else f"k_update<L={Ldom}>") + f" {mode}: rank-1 Bareiss pivot of the carry, as run by the timed steps",
                 "achieved": d["GIMAD/s"] if imad_bound else d["GB/s"],
                 "peak": imad_peak / 1e9 if imad_bound else peak,
                 "unit": "GIMAD.WIDE/s" if imad_bound else "GB/s",

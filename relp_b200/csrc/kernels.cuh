@@ -786,11 +786,39 @@ __global__ void k_ratio_pack(const u64* __restrict__ C, size_t ps, int ld, int L
     for (int l = 0; l < L; ++l) send[5 + l] = C[(size_t)l * ps + (size_t)p * ld];
     for (int l = 0; l < LU; ++l) send[5 + RG_MAXL + l] = u[(size_t)l * us + p];
 }
-__global__ void k_ratio_merge(const u64* __restrict__ recv, int world, int L, Scalars* sc) {
-    if (threadIdx.x || blockIdx.x) return;
+// The candidates of all ranks are ordered by exact cross-multiplied comparisons.  One thread per PAIR of ranks
+// (block of 128 threads, world <= 16): a serial scan is world - 1 dependent multi-limb comparisons in one thread,
+// which at eight ranks was a visible share of the pivot; the order is strict and total (distinct basis ids break
+// ties), so the rank that wins all its pairs is the one the scan would keep.
+__device__ __forceinline__ void pair_of(int t, int world, int& i, int& k) {
+    // t-th pair (i < k) in row-major order of the strict upper triangle
+    i = 0;
+    int rowlen = world - 1;
+    while (t >= rowlen && rowlen > 0) { t -= rowlen; ++i; --rowlen; }
+    k = i + 1 + t;
+}
+__global__ void __launch_bounds__(128) k_ratio_merge(const u64* __restrict__ recv, int world, int L, Scalars* sc) {
+    __shared__ unsigned char sBeats[16][16];     // sBeats[i][k]: candidate i precedes candidate k
     if (sc->status != ST_RUN) return;
     const int LU = L + 2;
-    u64 ws[4 * RG_MAXW];
+    const int npairs = world * (world - 1) / 2;
+    if ((int)threadIdx.x < npairs) {
+        int i, k;
+        pair_of(threadIdx.x, world, i, k);
+        const u64* c = recv + (size_t)i * RG_CAND_WORDS;
+        const u64* b = recv + (size_t)k * RG_CAND_WORDS;
+        bool ik = false, ki = false;
+        if (c[0] && b[0]) {
+            u64 ws[4 * RG_MAXW];
+            // ratio_i ? ratio_k :  b_i * u_k  vs  b_k * u_i
+            int cmpv = rt_cmp_prod(c + 5, L, b + 5 + RG_MAXL, LU, b + 5, L, c + 5 + RG_MAXL, LU, ws);
+            ik = cmpv < 0 || (cmpv == 0 && (i64)c[2] < (i64)b[2]);
+            ki = !ik;
+        } else { ik = c[0] != 0; ki = b[0] != 0 && !ik; }
+        sBeats[i][k] = ik; sBeats[k][i] = ki;
+    }
+    __syncthreads();
+    if (threadIdx.x) return;
     int best = -1;
     int mu = 0, mc = 0;
     for (int r = 0; r < world; ++r) {
@@ -798,11 +826,9 @@ __global__ void k_ratio_merge(const u64* __restrict__ recv, int world, int L, Sc
         mu = max(mu, (int)c[3]);
         mc = max(mc, (int)c[4]);
         if (!c[0]) continue;
-        if (best < 0) { best = r; continue; }
-        const u64* b = recv + (size_t)best * RG_CAND_WORDS;
-        // ratio_r ? ratio_best :  b_r * u_best  vs  b_best * u_r
-        int cmpv = rt_cmp_prod(c + 5, L, b + 5 + RG_MAXL, LU, b + 5, L, c + 5 + RG_MAXL, LU, ws);
-        if (cmpv < 0 || (cmpv == 0 && (i64)c[2] < (i64)b[2])) best = r;
+        bool all = true;
+        for (int o = 0; o < world; ++o) if (o != r && !sBeats[r][o]) all = false;
+        if (all) best = r;
     }
     sc->maxbits_u = mu;
     sc->maxbits_carry = mc;
@@ -895,53 +921,72 @@ __global__ void k_column_pack(const u64* __restrict__ kappa, int LU, const u64* 
     for (int l = 0; l < LU; ++l) send[3 + l] = kappa[(size_t)l * n + j];
     for (int l = 0; l < LG; ++l) send[3 + (RG_MAXL + 2) + l] = G[(size_t)l * n + j];
 }
-__global__ void k_column_merge(const u64* __restrict__ recv, int world, int rule, int L, int n, int want_found,
-                               Scalars* sc) {
-    if (threadIdx.x || blockIdx.x) return;
-    if (sc->status != ST_RUN) return;
+// does candidate c (column j) precede candidate b (column k) under the rule?  (strict total order)
+__device__ inline bool column_cand_better(const u64* c, const u64* b, int rule, int want_found, int L, int n, int last,
+                                          u64* buf) {
     const int LU = L + 2, LG = 2 * L + 6;
-    u64 buf[6 * RG_MAXW];
     u64* x = buf; u64* y = buf + RG_MAXW; u64* sj = buf + 2 * RG_MAXW; u64* sk = buf + 3 * RG_MAXW;
     u64* pj = buf + 4 * RG_MAXW; u64* pk = buf + 5 * RG_MAXW;
+    const int j = (int)c[1], k = (int)b[1];
+    if (rule == 0 || want_found) return j < k;                                  // first profitable / first hit
+    if (rule == 1) {                                                             // ... with memory
+        int kj = j > last ? j - last : j + n - last, kk = k > last ? k - last : k + n - last;
+        return kj < kk;
+    }
+    if (rule == 2) {                                                             // Dantzig: |kappa| w, ties lowest j
+        for (int l = 0; l < LU; ++l) { x[l] = c[3 + l]; y[l] = b[3 + l]; }
+        rt_neg(x, LU); rt_neg(y, LU);
+        u64 wj = c[2], wk = b[2];
+        rt_mul_full(sj, x, LU, &wj, 1);
+        rt_mul_full(sk, y, LU, &wk, 1);
+        int cmpv = rt_cmp_u(sj, sk, LU + 1);
+        return cmpv > 0 || (cmpv == 0 && j < k);
+    }
+    // steepest edge, ties highest j
+    for (int l = 0; l < LU; ++l) x[l] = c[3 + l];
+    rt_abs(y, x, LU); int ly = rt_trim(y, LU);
+    rt_mul_full(sj, y, ly, y, ly); int lsj = rt_trim(sj, 2 * ly);
+    for (int l = 0; l < LU; ++l) x[l] = b[3 + l];
+    rt_abs(y, x, LU); ly = rt_trim(y, LU);
+    rt_mul_full(sk, y, ly, y, ly); int lsk = rt_trim(sk, 2 * ly);
+    const u64* gk = b + 3 + (RG_MAXL + 2); const u64* gj = c + 3 + (RG_MAXL + 2);
+    int lgk = rt_trim(gk, LG), lgj = rt_trim(gj, LG);
+    rt_mul_full(pj, sj, lsj, gk, lgk); int lpj = lsj + lgk;
+    rt_mul_full(pk, sk, lsk, gj, lgj); int lpk = lsk + lgj;
+    int nn = lpj > lpk ? lpj : lpk;
+    for (int i = lpj; i < nn; ++i) pj[i] = 0;
+    for (int i = lpk; i < nn; ++i) pk[i] = 0;
+    int cmpv = rt_cmp_u(pj, pk, nn);
+    return cmpv > 0 || (cmpv == 0 && j > k);
+}
+// one thread per pair of ranks (see k_ratio_merge); the winner beats every other valid candidate
+__global__ void __launch_bounds__(128) k_column_merge(const u64* __restrict__ recv, int world, int rule, int L, int n,
+                                                      int want_found, Scalars* sc) {
+    __shared__ unsigned char sBeats[16][16];
+    if (sc->status != ST_RUN) return;
+    const int LG = 2 * L + 6;
+    const int npairs = world * (world - 1) / 2;
+    if ((int)threadIdx.x < npairs) {
+        int i, k;
+        pair_of(threadIdx.x, world, i, k);
+        const u64* c = recv + (size_t)i * RG_COLCAND_WORDS;
+        const u64* b = recv + (size_t)k * RG_COLCAND_WORDS;
+        bool ik = false, ki = false;
+        if (c[0] && b[0]) {
+            u64 buf[6 * RG_MAXW];
+            ik = column_cand_better(c, b, rule, want_found, L, n, sc->last_selected, buf);
+            ki = !ik;
+        } else { ik = c[0] != 0; ki = b[0] != 0 && !ik; }
+        sBeats[i][k] = ik; sBeats[k][i] = ki;
+    }
+    __syncthreads();
+    if (threadIdx.x) return;
     int best = -1;
     for (int r = 0; r < world; ++r) {
-        const u64* c = recv + (size_t)r * RG_COLCAND_WORDS;
-        if (!c[0]) continue;
-        if (best < 0) { best = r; continue; }
-        const u64* b = recv + (size_t)best * RG_COLCAND_WORDS;
-        const int j = (int)c[1], k = (int)b[1];
-        bool better;
-        if (rule == 0 || want_found) better = j < k;                             // first profitable / first hit
-        else if (rule == 1) {                                                    // ... with memory
-            int last = sc->last_selected;
-            int kj = j > last ? j - last : j + n - last, kk = k > last ? k - last : k + n - last;
-            better = kj < kk;
-        } else if (rule == 2) {                                                  // Dantzig: |kappa| w, ties lowest j
-            for (int l = 0; l < LU; ++l) { x[l] = c[3 + l]; y[l] = b[3 + l]; }
-            rt_neg(x, LU); rt_neg(y, LU);
-            u64 wj = c[2], wk = b[2];
-            rt_mul_full(sj, x, LU, &wj, 1);
-            rt_mul_full(sk, y, LU, &wk, 1);
-            int cmpv = rt_cmp_u(sj, sk, LU + 1);
-            better = cmpv > 0 || (cmpv == 0 && j < k);
-        } else {                                                                 // steepest edge, ties highest j
-            for (int l = 0; l < LU; ++l) x[l] = c[3 + l];
-            rt_abs(y, x, LU); int ly = rt_trim(y, LU);
-            rt_mul_full(sj, y, ly, y, ly); int lsj = rt_trim(sj, 2 * ly);
-            for (int l = 0; l < LU; ++l) x[l] = b[3 + l];
-            rt_abs(y, x, LU); ly = rt_trim(y, LU);
-            rt_mul_full(sk, y, ly, y, ly); int lsk = rt_trim(sk, 2 * ly);
-            const u64* gk = b + 3 + (RG_MAXL + 2); const u64* gj = c + 3 + (RG_MAXL + 2);
-            int lgk = rt_trim(gk, LG), lgj = rt_trim(gj, LG);
-            rt_mul_full(pj, sj, lsj, gk, lgk); int lpj = lsj + lgk;
-            rt_mul_full(pk, sk, lsk, gj, lgj); int lpk = lsk + lgj;
-            int nn = lpj > lpk ? lpj : lpk;
-            for (int i = lpj; i < nn; ++i) pj[i] = 0;
-            for (int i = lpk; i < nn; ++i) pk[i] = 0;
-            int cmpv = rt_cmp_u(pj, pk, nn);
-            better = cmpv > 0 || (cmpv == 0 && j > k);
-        }
-        if (better) best = r;
+        if (!recv[(size_t)r * RG_COLCAND_WORDS]) continue;
+        bool all = true;
+        for (int o = 0; o < world; ++o) if (o != r && !sBeats[r][o]) all = false;
+        if (all) best = r;
     }
     if (want_found) { sc->found = best < 0 ? -1 : (int)recv[(size_t)best * RG_COLCAND_WORDS + 1]; return; }
     if (best < 0) { sc->q = -1; sc->status = ST_OPTIMAL; return; }

@@ -349,6 +349,7 @@ extern "C" int rg_create(const rg_options* opts, rg_context** out) {
     ctx->device = opts ? opts->device : 0;
     ctx->rank = opts ? opts->rank : 0;
     ctx->world = (opts && opts->world > 0) ? opts->world : 1;
+    if (ctx->world > 16) { delete ctx; return RG_ERR_ARG; }      // the candidate merges compare rank pairs in one block
     ctx->dense_carry_opt = opts ? opts->dense_carry : 0;
     ctx->use_graphs = getenv("RG_NO_GRAPH") == nullptr;
     { const char* e = getenv("RG_GRAPH_NCCL"); ctx->graph_nccl = e && atoi(e) != 0; }
@@ -783,7 +784,7 @@ static int merge_columns(rg_context* ctx, int use_found) {
     LAUNCH(k_column_pack, 1, 1, ctx->kappa, LU_of(ctx->L), ctx->G, LG_of(ctx->L), ctx->n,
            ctx->weighted ? ctx->wcol : nullptr, use_found, ctx->xsend, ctx->sc);
     RG_TRY(all_gather(ctx, ctx->xsend, ctx->xrecv, RG_COLCAND_WORDS));
-    LAUNCH(k_column_merge, 1, 1, ctx->xrecv, ctx->world, ctx->rule, ctx->L, ctx->n, use_found, ctx->sc);
+    LAUNCH(k_column_merge, 1, 128, ctx->xrecv, ctx->world, ctx->rule, ctx->L, ctx->n, use_found, ctx->sc);
     return RG_OK;
 }
 
@@ -856,7 +857,7 @@ static int launch_ratio(rg_context* ctx) {
     LAUNCH(k_ratio_pack, 1, 1, bv.base, bv.ps, bv.stride, ctx->L, ctx->u, (size_t)ctx->ld, ctx->basis,
            ctx->xsend, ctx->sc);
     RG_TRY(all_gather(ctx, ctx->xsend, ctx->xrecv, RG_CAND_WORDS));
-    LAUNCH(k_ratio_merge, 1, 1, ctx->xrecv, ctx->world, ctx->L, ctx->sc);
+    LAUNCH(k_ratio_merge, 1, 128, ctx->xrecv, ctx->world, ctx->L, ctx->sc);
     return RG_OK;
 }
 // pivot row given (artificial removal, trait-shaped bring_into_basis): set p / pg and the pivot element
@@ -872,7 +873,7 @@ static int launch_fixed_row(rg_context* ctx, int row) {
     LAUNCH(k_ratio_pack, 1, 1, bv.base, bv.ps, bv.stride, ctx->L, ctx->u, (size_t)ctx->ld, ctx->basis,
            ctx->xsend, ctx->sc);
     RG_TRY(all_gather(ctx, ctx->xsend, ctx->xrecv, RG_CAND_WORDS));
-    LAUNCH(k_ratio_merge, 1, 1, ctx->xrecv, ctx->world, ctx->L, ctx->sc);
+    LAUNCH(k_ratio_merge, 1, 128, ctx->xrecv, ctx->world, ctx->L, ctx->sc);
     return RG_OK;
 }
 
@@ -2083,9 +2084,8 @@ extern "C" int rg_set_profile(rg_context* ctx, int32_t on) {
     if (!ctx) return RG_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     if (on && !ctx->ev0) {
-        // the profiling events are recycled per device for the life of the process: a context that creates fresh
-        // timing events right after another one destroyed its set was measured to run ~40 % slower (driver-side
-        // event pool churn), which made consecutive profiled solves -- the bench's timed steps -- look slow
+        // the profiling events are recycled per device for the life of the process (no create / destroy churn per
+        // solve; the slow solves once attributed to it were allocator stalls, see dev_alloc)
         std::lock_guard<std::mutex> lock(g_hm_mutex);
         auto& pool = g_prof_events[ctx->device & 15];
         if (!pool.empty()) {
