@@ -21,87 +21,42 @@ INF = None
 
 
 def parse_mps(text):
-    """Returns dict(name, rows=[(name, type)], objective, columns={col: {row: Fraction}}, col_order,
-    rhs={row: Fraction}, ranges={row: Fraction}, bounds={col: [lo, hi]}); decimal numbers are read
-    exactly (src/io/mps/number/parse.rs:46-119 semantics: integer * 10^-k)."""
-    section = None
-    rows, row_type = [], {}
-    objective = None
-    columns, col_order = {}, []
-    rhs, ranges, bounds = {}, {}, {}
-    name = ""
-    integer_marker = False
-    for raw in text.splitlines():
-        if not raw.strip() or raw.lstrip().startswith("*"):
-            continue
-        if not raw[0].isspace():
-            parts = raw.split()
-            section = parts[0].upper()
-            if section == "NAME" and len(parts) > 1:
-                name = parts[1]
-            if section == "ENDATA":
-                break
-            continue
-        f = raw.split()
-        if section == "ROWS":
-            t, r = f[0].upper(), f[1]
-            if t == "N":
-                if objective is None:
-                    objective = r
-                continue
-            rows.append(r)
-            row_type[r] = t
-        elif section == "COLUMNS":
-            if len(f) >= 3 and f[1] == "'MARKER'":
-                integer_marker = "INTORG" in raw
-                continue
-            col = f[0]
-            if col not in columns:
-                columns[col] = {}
-                col_order.append(col)
-            for k in range(1, len(f) - 1, 2):
-                v = Fraction(f[k + 1])
-                if v != 0:
-                    columns[col][f[k]] = columns[col].get(f[k], 0) + v
-        elif section == "RHS":
-            start = 1 if len(f) % 2 == 1 else 0
-            for k in range(start, len(f) - 1, 2):
-                rhs[f[k]] = Fraction(f[k + 1])
-        elif section == "RANGES":
-            start = 1 if len(f) % 2 == 1 else 0
-            for k in range(start, len(f) - 1, 2):
-                ranges[f[k]] = Fraction(f[k + 1])
-        elif section == "BOUNDS":
-            t = f[0].upper()
-            if t in ("FR", "MI", "PL", "BV"):
-                col = f[2] if len(f) >= 3 else f[1]
-                val = None
-            else:
-                col, val = (f[2], Fraction(f[3])) if len(f) >= 4 else (f[1], Fraction(f[2]))
-            lo, hi = bounds.get(col, [Fraction(0), INF])
-            if t == "UP":
-                hi = val
-                if val < 0 and lo == 0:
-                    lo = INF
-            elif t == "LO":
-                lo = val
-            elif t == "FX":
-                lo = hi = val
-            elif t == "FR":
-                lo, hi = INF, INF
-            elif t == "MI":
-                lo = INF
-            elif t == "PL":
-                hi = INF
-            elif t == "BV":
-                lo, hi = Fraction(0), Fraction(1)
-            elif t in ("LI",):
-                lo = val
-            elif t in ("UI",):
-                hi = val
-            bounds[col] = [lo, hi]
-    return dict(name=name, rows=rows, row_type=row_type, objective=objective, columns=columns,
-                col_order=col_order, rhs=rhs, ranges=ranges, bounds=bounds)
+    """MPS text -> the dict `canonicalize` consumes, through the restatement of relp's own reader (`relp_b200/mps.py`:
+    parse -> `MPS` -> `GeneralForm` data; src/io/mps/{parse,convert}.rs).  The flexible mode is tried first, as
+    `io::mps::parse` does (mod.rs:38-42); files whose names contain blanks need the fixed-column mode.
+
+    Keys: name, objective (cost row name), sense, rows (constraint rows in the reference's order: SORTED BY NAME),
+    row_type, interval {row: [lo, hi]} (None = unbounded side; ranges and duplicate right-hand sides resolved as
+    convert.rs does), columns {col: {row: Fraction}} (cost row entries included), col_order, bounds {col: [lo, hi]}
+    with the reference's bound semantics (GLPK's rule for negative upper bounds)."""
+    from . import mps as reader
+    try:
+        m = reader.parse_free(text)
+    except reader.ParseError:
+        m = reader.parse_fixed(text)
+    gf = m.to_general_form()
+    rows = list(gf.row_names)
+    row_type, interval = {}, {}
+    for r, (_, t), rel, b in zip(rows, m.rows, gf.constraint_types, gf.b):
+        row_type[r] = t
+        if isinstance(rel, tuple):
+            interval[r] = [b - rel[1], b]
+        elif rel == "E":
+            interval[r] = [b, b]
+        elif rel == "L":
+            interval[r] = [INF, b]
+        else:
+            interval[r] = [b, INF]
+    columns, col_order, bounds = {}, [], {}
+    for (cname, _vt, _vals), values, var in zip(m.columns, gf.columns, gf.variables):
+        entries = {rows[i]: v for i, v in values}
+        if var.cost != 0:
+            entries[m.cost_row_name] = var.cost
+        columns[cname] = entries
+        col_order.append(cname)
+        bounds[cname] = [var.lower_bound, var.upper_bound]         # None = unbounded = INF
+    return dict(name=m.name, objective=m.cost_row_name, sense=m.objective, rows=rows, row_type=row_type,
+                interval=interval, columns=columns, col_order=col_order, bounds=bounds, rhs={}, ranges={})
 
 
 class Solution:
@@ -140,6 +95,7 @@ class CanonicalLP:
         self.col_order = []    # original variable names, file order
         self.fixed = {}        # original variables fixed by their bounds (substituted out): name -> value
         self.name = ""
+        self.maximize = False  # OBJSENSE MAX: costs negated for the solve, objective negated back in `recover`
 
 
 def recover(lp, bfs, objective):
@@ -159,7 +115,8 @@ def recover(lp, bfs, objective):
             values[orig] += sign * x                           # second half of a split free variable
         else:
             values[orig] = shift + sign * x
-    return Solution(objective + lp.constant, [(name, values[name]) for name in lp.col_order])
+    total = objective + lp.constant
+    return Solution(-total if getattr(lp, "maximize", False) else total, [(name, values[name]) for name in lp.col_order])
 
 
 def canonicalize(mps):
@@ -168,29 +125,17 @@ def canonicalize(mps):
     lp.name = mps["name"]
     lp.col_order = list(mps["col_order"])
     lp.fixed = {}
-    rows, row_type = mps["rows"], mps["row_type"]
+    rows = mps["rows"]
     obj = mps["objective"]
-    rhs = {r: mps["rhs"].get(r, Fraction(0)) for r in rows}
-    lp.constant = -mps["rhs"].get(obj, Fraction(0))
-    # row intervals [lo, hi]
-    interval = {}
-    for r in rows:
-        t, b = row_type[r], rhs[r]
-        lo, hi = (b, b) if t == "E" else ((INF, b) if t == "L" else (b, INF))
-        if r in mps["ranges"]:
-            rg = mps["ranges"][r]
-            if t == "G":
-                hi = b + abs(rg)
-            elif t == "L":
-                lo = b - abs(rg)
-            else:
-                lo, hi = (b, b + abs(rg)) if rg >= 0 else (b - abs(rg), b)
-        interval[r] = [lo, hi]
+    lp.constant = Fraction(0)          # the reference's reader rejects a right-hand side on the cost row
+    lp.maximize = mps.get("sense", "minimize") == "maximize"
+    sense = -1 if lp.maximize else 1   # a maximisation is solved as the minimisation of the negated costs
+    interval = {r: list(mps["interval"][r]) for r in rows}
     # variables -> x' >= 0
     new_cols = []   # (entries {row: v}, cost, upper, (orig, sign, shift))
     for col in mps["col_order"]:
         entries = dict(mps["columns"][col])
-        cost = entries.pop(obj, Fraction(0))
+        cost = sense * entries.pop(obj, Fraction(0))
         entries = {r: v for r, v in entries.items() if r in interval}
         lo, hi = mps["bounds"].get(col, [Fraction(0), INF])
         if lo is not INF:

@@ -39,23 +39,14 @@ def feasible_in_original(mps, values):
             elif r in act:
                 act[r] += v * x[col]
     for r in mps["rows"]:
-        t, b = mps["row_type"][r], mps["rhs"].get(r, F(0))
-        lo, hi = (b, b) if t == "E" else ((None, b) if t == "L" else (b, None))
-        if r in mps["ranges"]:
-            rg = mps["ranges"][r]
-            if t == "G":
-                hi = b + abs(rg)
-            elif t == "L":
-                lo = b - abs(rg)
-            else:
-                lo, hi = (b, b + abs(rg)) if rg >= 0 else (b - abs(rg), b)
+        lo, hi = mps["interval"][r]
         assert lo is None or act[r] >= lo, r
         assert hi is None or act[r] <= hi, r
     for col in mps["col_order"]:
         lo, hi = mps["bounds"].get(col, [F(0), frontend.INF])
         assert lo is frontend.INF or x[col] >= lo, col
         assert hi is frontend.INF or x[col] <= hi, col
-    return obj - mps["rhs"].get(mps["objective"], F(0))
+    return obj
 
 
 def check_solution(name, bfs, objective, lp, mps):
