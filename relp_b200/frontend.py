@@ -1,14 +1,15 @@
 """Host-side front-end feeding the engine from MPS/SIF files (SURVEY.md section 8f "next" rows 1-3).
 
-This is NOT a restatement of relp's parser / presolve: it is the minimum needed to hand the netlib
-configurations to the hot path.  It reads fixed/free MPS, canonicalises to the row/column layout of the
-reference's `MatrixData` (src/algorithm/two_phase/matrix_provider/matrix_data.rs:46-61,291-329:
-equality, range, <=, >= rows; variable-bound rows; x >= 0 with optional upper bounds) WITHOUT presolve,
-and prescales the rational rows to integers for the device.
+Reading is the restatement of relp's own importer (`relp_b200/mps.py`: parse -> `MPS` -> `GeneralForm` data, rows
+sorted by name, the reference's bound and range semantics).  This module canonicalises that to the row/column
+layout of the reference's `MatrixData` (src/algorithm/two_phase/matrix_provider/matrix_data.rs:46-61,291-329:
+equality, range, <=, >= rows; variable-bound rows; x >= 0 with optional upper bounds) WITHOUT the reference's
+presolve (general_form/presolve/**, not restated), maps solutions back (`recover`) and prescales the rational rows
+to integers for the device.
 
-Because no presolve is applied, the canonical problem differs from the one relp solves after its
-presolve; optimal objective values are identical (they are unique), traces are compared GPU-vs-oracle on
-the same canonical problem.
+Because no presolve is applied, the canonical problem differs from the one relp solves after its presolve; optimal
+objective values and the recovered solutions are identical (tests/test_netlib_cpu.py, test_solution_recovery.py),
+traces are compared GPU-vs-oracle on the same canonical problem.
 """
 from fractions import Fraction
 from math import gcd
