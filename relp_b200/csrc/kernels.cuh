@@ -2523,6 +2523,154 @@ k_gamma_update3(int n, ColOwn own, int L, const unsigned char* __restrict__ inba
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The weight recurrence with a WARP per column (run-time widths, 32-bit limbs).
+// Every low product P = A B mod 2^(32 W) is spread over the lanes by OUTPUT limb: lane l owns the CH consecutive
+// limbs k = CH l .. CH l + CH - 1 and scans their columns, (c2:c1:c0)_k += A_i B_{k-i} for i = 0 .. k, with A_i
+// broadcast from shared memory and a CH-word window of B sliding through registers (one new shared-memory word
+// per i for CH multiply-adds).  The three products of the final sum share one set of column accumulators; the
+// carries are resolved in registers (neighbour words by shuffle, then a ripple that almost always ends after one
+// round).  Latency per column: ~3 W multiply-add steps instead of 5 W^2 / 2 in one thread.
+// ---------------------------------------------------------------------------------------------
+template <int CH>
+__device__ __forceinline__ void wm_cols(u32 (&c0)[CH], u32 (&c1)[CH], u32 (&c2)[CH], const u32* __restrict__ A,
+                                        const u32* __restrict__ B, int W32, int lane) {
+    const int base = CH * lane;
+    if (base >= W32) return;
+    u32 w[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) w[c] = base + c < W32 ? B[base + c] : 0u;
+    const int iend = min(W32, base + CH);
+    for (int i = 0; i < iend; ++i) {
+        const u32 a = A[i];
+#pragma unroll
+        for (int c = 0; c < CH; ++c)
+            asm volatile("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, %2, 0;"
+                         : "+r"(c0[c]), "+r"(c1[c]), "+r"(c2[c]) : "r"(a), "r"(w[c]));
+#pragma unroll
+        for (int c = CH - 1; c >= 1; --c) w[c] = w[c - 1];
+        const int idx = base - i - 1;
+        w[0] = idx >= 0 ? B[idx] : 0u;
+    }
+}
+// limbs of the column sums: r_k = c0_k + c1_{k-1} + c2_{k-2} + carry; every lane of the warp must call this
+template <int CH>
+__device__ __forceinline__ void wm_resolve(u32 (&r)[CH], const u32 (&c0)[CH], const u32 (&c1)[CH], const u32 (&c2)[CH],
+                                           int lane) {
+    static_assert(CH >= 2, "a chunk takes words from the previous lane only");
+    u32 p_c1 = __shfl_up_sync(0xffffffffu, c1[CH - 1], 1);
+    u32 p_c2a = __shfl_up_sync(0xffffffffu, c2[CH - 1], 1);     // joins limb base + 1
+    u32 p_c2b = __shfl_up_sync(0xffffffffu, c2[CH - 2], 1);     // joins limb base
+    if (lane == 0) { p_c1 = 0; p_c2a = 0; p_c2b = 0; }
+    u64 carry = 0;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+        u64 t = (u64)c0[c] + carry;
+        t += c >= 1 ? c1[c - 1] : p_c1;
+        t += c >= 2 ? c2[c - 2] : (c == 1 ? p_c2a : p_c2b);
+        r[c] = (u32)t; carry = t >> 32;
+    }
+    u32 cout = (u32)carry;
+    for (;;) {
+        u32 cin = __shfl_up_sync(0xffffffffu, cout, 1);
+        if (lane == 0) cin = 0;
+        if (!__any_sync(0xffffffffu, cin != 0)) break;
+        u64 cc = cin;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) { u64 t = (u64)r[c] + cc; r[c] = (u32)t; cc = t >> 32; }
+        cout = (u32)cc;
+    }
+}
+template <int CH>
+__global__ void __launch_bounds__(128)
+k_gamma_update_w(int n, ColOwn own, int L, const unsigned char* __restrict__ inbasis, const u64* __restrict__ nu,
+                 const u64* __restrict__ sigma, u64* __restrict__ G, Scalars* sc) {
+    extern __shared__ u32 smw[];
+    if (sc->status != ST_RUN) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int LU = L + 2, LS = 2 * L + 7, LG = 2 * L + 6;
+    const int W32 = 2 * (LG + sc->E2);
+    if (W32 > 32 * CH) {           // the host sized the lanes' chunks for a narrower division width
+        if (threadIdx.x == 0) { sc->status = ST_FATAL; sc->fatal = 2; }
+        return;
+    }
+    const int WP = W32 + 2;        // two zero words behind every number (the final shift reads past the end)
+    u32* S1 = smw; u32* S2n = smw + WP; u32* S3 = smw + 2 * WP;
+    u32* mine = smw + 3 * WP + warp * 6 * WP;
+    u32* NV = mine; u32* SG = mine + WP; u32* GG = mine + 2 * WP; u32* Y1 = mine + 3 * WP; u32* Y2 = mine + 4 * WP;
+    u32* X = mine + 5 * WP;
+    // block-wide: the three uniform scalars, S2 negated (x = S1 Ghat + (-S2) (nu sigma) + S3 (nu nu))
+    for (int k = threadIdx.x; k < W32; k += blockDim.x) {
+        S1[k] = reinterpret_cast<const u32*>(sc->S1)[k];
+        S3[k] = reinterpret_cast<const u32*>(sc->S3)[k];
+    }
+    if (threadIdx.x == 0) {
+        u32 c = 1;
+        for (int k = 0; k < W32; ++k) {
+            u32 v = ~reinterpret_cast<const u32*>(sc->S2)[k] + c;
+            c = (c && v == 0) ? 1u : 0u;
+            S2n[k] = v;
+        }
+    }
+    for (int k = lane; k < 2; k += 32) { X[W32 + k] = 0; }
+    __syncthreads();
+    const int tix = blockIdx.x * 4 + warp;
+    if (tix >= own.count()) return;
+    const int j = own.at(tix);
+    if (inbasis[j] || j == sc->leaving) return;   // entering: None; leaving: set by k_finalize
+    // operands: nu (sign-extended), sigma (sign-extended), Ghat (zero-extended)
+    const u64 nu_top = nu[(size_t)(LU - 1) * n + j], sg_top = sigma[(size_t)(LS - 1) * n + j];
+    const u32 nu_sign = (i64)nu_top < 0 ? ~0u : 0u, sg_sign = (i64)sg_top < 0 ? ~0u : 0u;
+    u32 any = 0;
+    for (int k = lane; k < W32; k += 32) {
+        const int l = k >> 1, hi = k & 1;
+        u32 a = nu_sign, b = sg_sign, g = 0;
+        if (l < LU) { u64 v = nu[(size_t)l * n + j]; a = hi ? (u32)(v >> 32) : (u32)v; any |= a; }
+        if (l < LS) { u64 v = sigma[(size_t)l * n + j]; b = hi ? (u32)(v >> 32) : (u32)v; }
+        if (l < LG) { u64 v = G[(size_t)l * n + j]; g = hi ? (u32)(v >> 32) : (u32)v; }
+        NV[k] = a; SG[k] = b; GG[k] = g;
+    }
+    const bool nz = __any_sync(0xffffffffu, any != 0);     // alpha_j_bar == 0: Ghat' = Ghat a^2 / D^2
+    __syncwarp();
+    u32 c0[CH], c1[CH], c2[CH], r[CH];
+    const int base = CH * lane;
+    if (nz) {
+#pragma unroll
+        for (int c = 0; c < CH; ++c) { c0[c] = 0; c1[c] = 0; c2[c] = 0; }
+        wm_cols<CH>(c0, c1, c2, NV, SG, W32, lane);             // nu sigma
+        wm_resolve<CH>(r, c0, c1, c2, lane);
+#pragma unroll
+        for (int c = 0; c < CH; ++c) if (base + c < W32) Y1[base + c] = r[c];
+#pragma unroll
+        for (int c = 0; c < CH; ++c) { c0[c] = 0; c1[c] = 0; c2[c] = 0; }
+        wm_cols<CH>(c0, c1, c2, NV, NV, W32, lane);             // nu^2
+        wm_resolve<CH>(r, c0, c1, c2, lane);
+#pragma unroll
+        for (int c = 0; c < CH; ++c) if (base + c < W32) Y2[base + c] = r[c];
+        __syncwarp();
+    }
+#pragma unroll
+    for (int c = 0; c < CH; ++c) { c0[c] = 0; c1[c] = 0; c2[c] = 0; }
+    wm_cols<CH>(c0, c1, c2, S1, GG, W32, lane);                 // a^2/D^2 Ghat
+    if (nz) {
+        wm_cols<CH>(c0, c1, c2, S2n, Y1, W32, lane);            // - 2a/D^2 nu sigma
+        wm_cols<CH>(c0, c1, c2, S3, Y2, W32, lane);             // + Gq/D^2 nu^2
+    }
+    wm_resolve<CH>(r, c0, c1, c2, lane);
+#pragma unroll
+    for (int c = 0; c < CH; ++c) if (base + c < W32) X[base + c] = r[c];
+    __syncwarp();
+    // shift right by t2 and store the low LG limbs
+    const int t2 = sc->t2;
+    const int tw = t2 >> 5, tb = t2 & 31;
+    for (int l = lane; l < LG; l += 32) {
+        const int wi = 2 * l + tw;
+        const u32 a0 = wi < WP ? X[wi] : 0u, a1 = wi + 1 < WP ? X[wi + 1] : 0u, a2 = wi + 2 < WP ? X[wi + 2] : 0u;
+        const u32 lo = __funnelshift_r(a0, a1, tb), hi = __funnelshift_r(a1, a2, tb);
+        G[(size_t)l * n + j] = (u64)lo | ((u64)hi << 32);
+    }
+}
+
 // b_p != 0 ?  (remove_artificial_basis_variables, phase_one.rs:250) -- read from the staged row
 __global__ void k_bp_nonzero(const u64* rowp, size_t rs, int L, Scalars* sc) {
     if (threadIdx.x || blockIdx.x) return;

@@ -1153,7 +1153,23 @@ static void launch_se_update(rg_context* ctx) {
         }
     } else {
         static const bool one_thread = getenv("RG_GAMMA1") != nullptr;
-        if (one_thread) {
+        static const bool three_warps = getenv("RG_GAMMA3") != nullptr;
+        if (!one_thread && !three_warps) {
+            // a warp per column (k_gamma_update_w): each lane owns CH consecutive 32-bit output limbs of every product.
+            // A captured launch is replayed while ctz(D) -- and with it the division width -- may grow: widest chunk.
+            const int W32 = 2 * (LG_of(ctx->L) + std::max(E2, 4));
+            const int CH = ctx->capturing ? 5 : std::max(2, cdiv(W32, 32));
+            const int W32max = 32 * CH, WP = W32max + 2;
+            const size_t smem = (size_t)(3 + 4 * 6) * WP * sizeof(u32);
+            const int blocks = cdiv(std::max(own_of(ctx).count(), 1), 4);
+            switch (CH) {
+                case 2: k_gamma_update_w<2><<<blocks, 128, smem, ctx->stream>>>(ctx->n, own_of(ctx), ctx->L, ctx->inbasis, ctx->nu, ctx->sigma, ctx->G, ctx->sc); break;
+                case 3: k_gamma_update_w<3><<<blocks, 128, smem, ctx->stream>>>(ctx->n, own_of(ctx), ctx->L, ctx->inbasis, ctx->nu, ctx->sigma, ctx->G, ctx->sc); break;
+                case 4: k_gamma_update_w<4><<<blocks, 128, smem, ctx->stream>>>(ctx->n, own_of(ctx), ctx->L, ctx->inbasis, ctx->nu, ctx->sigma, ctx->G, ctx->sc); break;
+                default: k_gamma_update_w<5><<<blocks, 128, smem, ctx->stream>>>(ctx->n, own_of(ctx), ctx->L, ctx->inbasis, ctx->nu, ctx->sigma, ctx->G, ctx->sc); break;
+            }
+            ctx->launches++;
+        } else if (one_thread) {
             LAUNCH(k_gamma_update, cdiv(std::max(own_of(ctx).count(), 1), 128), 128, ctx->n, own_of(ctx), ctx->L,
                    ctx->inbasis, ctx->nu, ctx->sigma, ctx->G, ctx->sc);
         } else {
