@@ -57,7 +57,8 @@ def parse_mps(text):
         col_order.append(cname)
         bounds[cname] = [var.lower_bound, var.upper_bound]         # None = unbounded = INF
     return dict(name=m.name, objective=m.cost_row_name, sense=m.objective, rows=rows, row_type=row_type,
-                interval=interval, columns=columns, col_order=col_order, bounds=bounds, rhs={}, ranges={})
+                interval=interval, columns=columns, col_order=col_order, bounds=bounds, rhs={}, ranges={},
+                general_form=m.to_general_form())     # a fresh copy: `canonicalize` standardizes it in place
 
 
 class Solution:
@@ -96,6 +97,7 @@ class CanonicalLP:
         self.col_order = []    # original variable names, file order
         self.fixed = {}        # original variables fixed by their bounds (substituted out): name -> value
         self.name = ""
+        self.general_form = None   # general_form.GeneralForm after `standardize` (reference path)
         self.maximize = False  # OBJSENSE MAX: costs negated for the solve, objective negated back in `recover`
 
 
@@ -109,6 +111,10 @@ def recover(lp, bfs, objective):
     Returns a `Solution` over the original variables (file order) with the constant added back."""
     nv = len(lp.constraint_columns)
     reduced = {j: v for j, v in bfs if j < nv}                 # slack / bound-slack columns are dropped
+    if getattr(lp, "general_form", None) is not None:           # the reference's reconstruction, mod.rs:800-905
+        cost, values = lp.general_form.compute_full_solution_with_reduced_solution(reduced)
+        assert cost == objective + lp.constant
+        return Solution(cost, values)
     values = {name: Fraction(fixed) for name, fixed in lp.fixed.items()}
     for k, (orig, sign, shift) in enumerate(lp.var_map):
         x = reduced.get(k, Fraction(0))
@@ -121,7 +127,28 @@ def recover(lp, bfs, objective):
 
 
 def canonicalize(mps):
-    """MPS dict -> CanonicalLP (no presolve)."""
+    """MPS dict -> CanonicalLP.  With the reference reader's `GeneralForm` data this is the restatement of
+    `GeneralForm::standardize` + `derive_matrix_data` (`relp_b200/general_form.py`; presolve skipped): free variables
+    split with the negative halves appended, upper-bounded-only variables flipped, lower bounds shifted to zero,
+    negative right-hand sides negated, rows ordered ==, ranges, <=, >= (stable).  Dicts without it (hand-built in
+    tests) take the legacy interval-based path below."""
+    if mps.get("general_form") is not None:
+        from .general_form import GeneralForm
+        g = GeneralForm(mps["general_form"])
+        counts = g.standardize()
+        cols, b, ranges, ne, nr, nu, nl, variables = g.derive_matrix_data(counts)
+        lp = CanonicalLP()
+        lp.name = mps["name"]
+        lp.col_order = list(g.variable_names)
+        lp.constraint_columns = [list(c) for c in cols]
+        lp.b, lp.ranges, lp.counts = list(b), list(ranges), (ne, nr, nu, nl)
+        lp.costs = [c for c, _ in variables]
+        lp.upper = [u for _, u in variables]
+        lp.constant = g.fixed_cost
+        lp.var_map = [(g.variable_names[g.from_active_to_original[j]], -1 if v.flipped else 1,
+                       v.shift if v.flipped else -v.shift) for j, v in enumerate(g.variables)]
+        lp.general_form = g
+        return lp
     lp = CanonicalLP()
     lp.name = mps["name"]
     lp.col_order = list(mps["col_order"])
