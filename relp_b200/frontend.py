@@ -126,15 +126,19 @@ def recover(lp, bfs, objective):
     return Solution(-total if getattr(lp, "maximize", False) else total, [(name, values[name]) for name in lp.col_order])
 
 
-def canonicalize(mps):
-    """MPS dict -> CanonicalLP.  With the reference reader's `GeneralForm` data this is the restatement of
-    `GeneralForm::standardize` + `derive_matrix_data` (`relp_b200/general_form.py`; presolve skipped): free variables
-    split with the negative halves appended, upper-bounded-only variables flipped, lower bounds shifted to zero,
-    negative right-hand sides negated, rows ordered ==, ranges, <=, >= (stable).  Dicts without it (hand-built in
-    tests) take the legacy interval-based path below."""
+def canonicalize(mps, presolve=True):
+    """MPS dict -> CanonicalLP.  With the reference reader's `GeneralForm` data this is the reference's own pipeline
+    (tests/netlib/mod.rs:55-59): `GeneralForm::presolve` (`relp_b200/presolve.py`; `presolve=False` skips it),
+    `standardize` and `derive_matrix_data` (`relp_b200/general_form.py`): free variables split with the negative
+    halves appended, upper-bounded-only variables flipped, lower bounds shifted to zero, negative right-hand sides
+    negated, rows ordered ==, ranges, <=, >= (stable).  A presolve that solves the whole problem raises
+    `presolve.FiniteOptimum`, an infeasible / unbounded one `presolve.Infeasible` / `Unbounded`.  Dicts without the
+    general form (hand-built in tests) take the legacy interval-based path below."""
     if mps.get("general_form") is not None:
         from .general_form import GeneralForm
         g = GeneralForm(mps["general_form"])
+        if presolve:
+            g.presolve()
         counts = g.standardize()
         cols, b, ranges, ne, nr, nu, nl, variables = g.derive_matrix_data(counts)
         lp = CanonicalLP()

@@ -10,10 +10,9 @@ half): reference `src/data/linear_program/general_form/mod.rs`
     derive_matrix_data     :262-302
     reshift_solution / compute_full_solution_with_reduced_solution :800-905
 
-This is the reference's pipeline with its presolve step (`general_form/presolve/**`) skipped -- the reference's own
-doc comment at `standardize` lists skipping as a to-do; the presolve rules are not restated.  Differences from a
-presolved run: fixed variables stay as columns with upper bound 0, redundant rows stay.  Values are
-`fractions.Fraction`.  Host-side only.
+`GeneralForm.presolve` (mod.rs:333-505, rules in `relp_b200/presolve.py`) is optional, as in the reference: without
+it fixed variables stay as columns with upper bound 0 and redundant rows stay.  Values are `fractions.Fraction`.
+Host-side only.
 """
 from fractions import Fraction
 
@@ -21,8 +20,9 @@ from fractions import Fraction
 class GeneralForm:
     """Mutable working copy of `mps.GeneralFormData` with the bookkeeping `standardize` needs.
 
-    original_variables: per original variable ("active", j) or ("active_free", j_positive, j_negative) --
-    `OriginalVariable::{Active, ActiveFree}` (no `Removed` variants: presolve is not run)."""
+    original_variables: per original variable ("active", j), ("active_free", j_positive, j_negative) or
+    ("removed", ("solved", value) | ("function", constant, [(original index, coefficient)])) --
+    `OriginalVariable::{Active, ActiveFree, Removed}` (mod.rs:72-99)."""
 
     def __init__(self, data):
         self.objective = data.objective
@@ -36,6 +36,94 @@ class GeneralForm:
         self.fixed_cost = Fraction(data.fixed_cost)
         self.original_variables = [("active", j) for j in range(len(self.variables))]
         self.from_active_to_original = list(range(len(self.variables)))
+
+    # -- presolve, mod.rs:333-505 (rules: relp_b200/presolve.py) ---------------------------------------
+    def presolve(self):
+        """`GeneralForm::presolve` (mod.rs:352-369).  Raises presolve.Infeasible / Unbounded, or FiniteOptimum when
+        every variable was solved.  Must run on a fresh problem, before `standardize` (as in the reference's
+        pipeline, tests/netlib/mod.rs:55-57)."""
+        from . import presolve as ps
+        ch = ps.compute_presolve_changes(self)
+        # update_values_that_remain, mod.rs:404-436
+        for i, v in ch["b"].items():
+            self.b[i] = v
+        for i, t in ch["constraints"].items():
+            self.constraint_types[i] = t
+        self.fixed_cost += ch["fixed_cost"]
+        for j, solution in ch["removed_variables"]:
+            self.original_variables[j] = ("removed", solution)
+        for (j, direction), value in ch["bounds"].items():
+            if direction == ps.LOWER:
+                self.variables[j].lower_bound = value
+            else:
+                self.variables[j].upper_bound = value
+        self.remove_rows_and_columns(ch["constraints_marked_removed"], [j for j, _ in ch["removed_variables"]])
+        self.compute_solution_where_possible()
+        solution = self.get_solution()
+        if solution is not None:
+            raise ps.FiniteOptimum(*solution)
+
+    def remove_rows_and_columns(self, constraints, variables):
+        """mod.rs:438-475"""
+        gone_v, gone_c = set(variables), set(constraints)
+        keep_v = [j for j in range(len(self.variables)) if j not in gone_v]
+        self.columns = [self.columns[j] for j in keep_v]
+        self.variables = [self.variables[j] for j in keep_v]
+        self.from_active_to_original = [self.from_active_to_original[j] for j in keep_v]
+        if variables:
+            for new_index, orig in enumerate(self.from_active_to_original):
+                assert self.original_variables[orig][0] == "active"
+                self.original_variables[orig] = ("active", new_index)
+        new_row, k = {}, 0
+        for i in range(len(self.b)):
+            if i not in gone_c:
+                new_row[i] = k
+                k += 1
+        self.columns = [[(new_row[i], v) for i, v in col if i not in gone_c] for col in self.columns]
+        keep_c = [i for i in range(len(self.b)) if i not in gone_c]
+        self.constraint_types = [self.constraint_types[i] for i in keep_c]
+        self.b = [self.b[i] for i in keep_c]
+        self.row_names = [self.row_names[i] for i in keep_c]
+        self.nr_rows = len(self.b)
+
+    def _solution_value(self, j, cache):
+        """compute_solution_value, mod.rs:712-737: None while it depends on a variable still in the problem"""
+        ov = self.original_variables[j]
+        if ov[0] != "removed":
+            return None
+        sol = ov[1]
+        if sol[0] == "solved":
+            return sol[1]
+        if j not in cache:
+            total = Fraction(0)
+            for k, coefficient in sol[2]:
+                v = self._solution_value(k, cache)
+                if v is None:
+                    total = None
+                    break
+                total += coefficient * v
+            cache[j] = None if total is None else sol[1] - total
+        return cache[j]
+
+    def compute_solution_where_possible(self):
+        """mod.rs:686-710"""
+        cache = {}
+        for j, ov in enumerate(self.original_variables):
+            if ov[0] == "removed" and ov[1][0] == "function":
+                self._solution_value(j, cache)
+        for j, value in cache.items():
+            if value is not None:
+                self.original_variables[j] = ("removed", ("solved", value))
+
+    def get_solution(self):
+        """mod.rs:739-752: (fixed cost, [(name, value)]) once every variable is solved"""
+        values = []
+        for name, ov in zip(self.variable_names, self.original_variables):
+            if ov[0] == "removed" and ov[1][0] == "solved":
+                values.append((name, ov[1][1]))
+            else:
+                return None
+        return self.fixed_cost, values
 
     # -- transform_variables, mod.rs:506-547 -------------------------------------------------------
     def split_free_variables(self):
@@ -147,10 +235,20 @@ class GeneralForm:
             if var.flipped:
                 v = -v
             x[j] = v
-        values = []
-        for name, ov in zip(self.variable_names, self.original_variables):
-            if ov[0] == "active":
-                values.append((name, x[ov[1]]))
-            else:
-                values.append((name, x[ov[1]] - x[ov[2]]))
+        done = {}
+
+        def value_of(k):                                    # compute_solution_value_with_bfs, mod.rs:856-905
+            if k not in done:
+                ov = self.original_variables[k]
+                if ov[0] == "active":
+                    done[k] = x[ov[1]]
+                elif ov[0] == "active_free":
+                    done[k] = x[ov[1]] - x[ov[2]]
+                elif ov[1][0] == "solved":
+                    done[k] = ov[1][1]
+                else:
+                    done[k] = ov[1][1] - sum((c * value_of(q) for q, c in ov[1][2]), Fraction(0))
+            return done[k]
+
+        values = [(name, value_of(k)) for k, name in enumerate(self.variable_names)]
         return cost, values
