@@ -1,15 +1,11 @@
 """Host-side front-end feeding the engine from MPS/SIF files (SURVEY.md section 8f "next" rows 1-3).
 
-Reading is the restatement of relp's own importer (`relp_b200/mps.py`: parse -> `MPS` -> `GeneralForm` data, rows
-sorted by name, the reference's bound and range semantics).  This module canonicalises that to the row/column
-layout of the reference's `MatrixData` (src/algorithm/two_phase/matrix_provider/matrix_data.rs:46-61,291-329:
-equality, range, <=, >= rows; variable-bound rows; x >= 0 with optional upper bounds) WITHOUT the reference's
-presolve (general_form/presolve/**, not restated), maps solutions back (`recover`) and prescales the rational rows
-to integers for the device.
-
-Because no presolve is applied, the canonical problem differs from the one relp solves after its presolve; optimal
-objective values and the recovered solutions are identical (tests/test_netlib_cpu.py, test_solution_recovery.py),
-traces are compared GPU-vs-oracle on the same canonical problem.
+The pipeline is the reference's own (tests/netlib/mod.rs:48-70), restated: `relp_b200/mps.py` reads the file (parse ->
+`MPS` -> `GeneralForm` data, rows sorted by name, the reference's bound and range semantics), `relp_b200/presolve.py`
++ `relp_b200/general_form.py` presolve and standardize it and derive the `MatrixData` layout
+(src/algorithm/two_phase/matrix_provider/matrix_data.rs:46-61,291-329: equality, range, <=, >= rows; variable-bound
+rows; x >= 0 with optional upper bounds).  This module glues them (`parse_mps`, `canonicalize`), maps solutions back
+(`recover`) and prescales the rational rows to integers for the device (`prescale`).
 """
 from fractions import Fraction
 from math import gcd
