@@ -89,7 +89,7 @@ struct rg_context {
     cudaStream_t stream = nullptr;
     cudaStream_t side = nullptr;          // side stream: steepest-edge scalars overlap the K1 update
     int* nzrows = nullptr;             // list mode: compacted local rows with s_i != 0 (nloc entries)
-    cudaEvent_t ev_side0 = nullptr, ev_side1 = nullptr, ev_side2 = nullptr, ev_work = nullptr, ev_side3 = nullptr, ev_nu = nullptr;
+    cudaEvent_t ev_side0 = nullptr, ev_side1 = nullptr, ev_side2 = nullptr, ev_work = nullptr, ev_side3 = nullptr, ev_nu = nullptr, ev_ft0 = nullptr, ev_ft1 = nullptr;
     cudaStream_t side3 = nullptr;      // third side stream: steepest-edge scalars (k_scalars_se)
     cudaStream_t side2 = nullptr;      // second side stream: nu / sigma column dots, concurrent with K1
     int m = 0, n = 0;
@@ -170,12 +170,16 @@ struct rg_context {
     long long demotions = 0;
     int demote_need = 0;               // upper bound of the carry's bit length after the last pivot (0 = unknown)
     u32* bn = nullptr;                 // K1 row factors Bn_i (k_bn_rows): (nloc + 2) rows of 2 (L + 8) + 1 words
-    int k1_items_min_limbs = 8;        // list mode: widths from here on run the warp-granular K1 (RG_K1_ITEMS_MINL)
+    int k1_items_min_limbs = 10;       // list mode: widths from here on run the warp-granular K1 (RG_K1_ITEMS_MINL);
+                                       // at 8 limbs k_update with its register prefetch measured 3 % faster on config 4
     bool kappa_valid = false;          // kappa holds the reduced costs of the current carry (k_kappa_update may run)
+    bool ftran_overlap = true;         // RG_NO_FTRAN_OVERLAP=1: cost-row FTRAN on the main stream
     bool kappa_recur = true;           // RG_NO_KAPPA_RECUR=1: always price from the cost row
     int k1_items_prefetch = 1;         // RG_K1_NOPF=1: no L1 prefetch of the next row's entry
     int k1_items_rows = 8;             // rows per full work item (RG_K1_ITEMS_ROWS, <= 32)
     bool pow2_only = false;            // RG_WIDTH_LADDER=pow2: widths 1, 2, 4, 8, 16 only
+    int demote_margin = 16;            // bits of slack a narrower width must leave (RG_DEMOTE_MARGIN); numerators
+                                       // move by ~6 bits per pivot, a width change costs about half a pivot
     int demote_floor = 8;              // narrowest width a demotion may reach (RG_DEMOTE_FLOOR)
     int profile = 0;                   // 0 off, 1 events around K1 only, 2 events around every phase
     // CUDA graphs of one fused iteration, keyed by everything that shapes the launch sequence

@@ -355,9 +355,11 @@ extern "C" int rg_create(const rg_options* opts, rg_context** out) {
     { const char* e = getenv("RG_GRAPH_NCCL"); ctx->graph_nccl = e && atoi(e) != 0; }
     ctx->k1_items_prefetch = getenv("RG_K1_NOPF") == nullptr;
     ctx->kappa_recur = getenv("RG_NO_KAPPA_RECUR") == nullptr;
+    ctx->ftran_overlap = getenv("RG_NO_FTRAN_OVERLAP") == nullptr;
     { const char* e = getenv("RG_K1_ITEMS_MINL"); if (e) ctx->k1_items_min_limbs = atoi(e); }
     { const char* e = getenv("RG_K1_ITEMS_ROWS"); if (e) ctx->k1_items_rows = std::min(32, std::max(1, atoi(e))); }
     { const char* e = getenv("RG_WIDTH_LADDER"); ctx->pow2_only = e && strcmp(e, "pow2") == 0; }
+    { const char* e = getenv("RG_DEMOTE_MARGIN"); if (e) ctx->demote_margin = std::max(2, atoi(e)); }
     { const char* e = getenv("RG_DEMOTE_FLOOR"); if (e) ctx->demote_floor = std::max(1, atoi(e)); }   // 99 = never demote
     int L = (opts && opts->initial_limbs) ? opts->initial_limbs : 2;
     if (width_index(L) < 0) { delete ctx; return RG_ERR_ARG; }
@@ -373,6 +375,8 @@ extern "C" int rg_create(const rg_options* opts, rg_context** out) {
     CK(cudaEventCreateWithFlags(&ctx->ev_work, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_side3, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_nu, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->ev_ft0, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->ev_ft1, cudaEventDisableTiming));
     CK(cudaStreamCreateWithFlags(&ctx->side2, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&ctx->side3, cudaStreamNonBlocking));
     CK(dev_alloc(&ctx->sc, sizeof(Scalars), ctx->stream));
@@ -466,7 +470,7 @@ extern "C" int rg_destroy(rg_context* ctx) {
         g_prof_events[ctx->device & 15].push_back(pe);
     }
     if (ctx->evt0) { cudaEventDestroy(ctx->evt0); cudaEventDestroy(ctx->evt1); }
-    if (ctx->ev_side0) { cudaEventDestroy(ctx->ev_side0); cudaEventDestroy(ctx->ev_side1); cudaEventDestroy(ctx->ev_side2); cudaEventDestroy(ctx->ev_work); cudaEventDestroy(ctx->ev_side3); cudaEventDestroy(ctx->ev_nu); }
+    if (ctx->ev_side0) { cudaEventDestroy(ctx->ev_side0); cudaEventDestroy(ctx->ev_side1); cudaEventDestroy(ctx->ev_side2); cudaEventDestroy(ctx->ev_work); cudaEventDestroy(ctx->ev_side3); cudaEventDestroy(ctx->ev_nu); cudaEventDestroy(ctx->ev_ft0); cudaEventDestroy(ctx->ev_ft1); }
     if (ctx->side2) cudaStreamDestroy(ctx->side2);
     if (ctx->side3) cudaStreamDestroy(ctx->side3);
     // the communicator is process-cached (see rg_create) unless this context owns it
@@ -822,11 +826,25 @@ static void launch_ftran_t(rg_context* ctx, int q) {
                ctx->A.vals, ctx->Acm, ctx->ldc, q, ctx->sc);
         LAUNCH(k_scatter_col2, cdiv(ctx->m, 256), 256, ctx->aq, ctx->nd, ctx->A.colptr, ctx->A.rowidx, ctx->A.vals,
                q, ctx->sc);
+        // the cost-row dot (a few blocks and a last-block fold: latency) runs on a side stream beside the list FTRAN
+        // (which streams the packed block from HBM); both only read the scattered column
+        const bool overlap = ctx->ftran_overlap && ctx->side3 && ctx->ev_ft0;
+        cudaStream_t main_stream = ctx->stream;
+        if (overlap) {
+            cudaEventRecord(ctx->ev_ft0, main_stream);
+            cudaStreamWaitEvent(ctx->side3, ctx->ev_ft0, 0);
+            ctx->stream = ctx->side3;
+        }
         LAUNCH((k_ftran_row0<L>), std::max(1, std::min(32, cdiv(ctx->m, 1024))), 256, ctx->carry, ctx->plane, ctx->m,
                ctx->aq, ctx->cost, q, ctx->u, (size_t)ctx->ld, ctx->row0_part, ctx->sc);
+        if (overlap) {
+            cudaEventRecord(ctx->ev_ft1, ctx->side3);
+            ctx->stream = main_stream;
+        }
         LAUNCH((k_ftran_list<L>), cdiv((long long)(ctx->nloc + 1) * 32, 256), 256, ctx->pk, ctx->pplane, ctx->cap,
                ctx->nloc + 1, ctx->m, ctx->aq, ctx->klist, ctx->triv, ctx->cost, q, ctx->u, (size_t)ctx->ld,
                ctx->sc);
+        if (overlap) cudaStreamWaitEvent(main_stream, ctx->ev_ft1, 0);
         return;
     }
     LAUNCH((k_ftran<L>), cdiv((long long)(ctx->nloc + 1) * 32, 256), 256, ctx->carry, ctx->plane, ctx->ld,
@@ -1352,16 +1370,15 @@ static int enqueue_iteration(rg_context* ctx, int q, int fixed_row, bool want_se
 // Demotion: the numerators of an exact simplex run shrink again once the basis stops growing (config 5: 783 bits at
 // pivot 220, 590 at pivot 345), and every kernel of the iteration costs O(L) bytes and O(L^2) multiply-adds.  After
 // a pivot the replicated upper bound of the carry's bit length (the overflow prediction of that pivot, and D) is
-// known on the host; when it fits the next narrower width with RG_DEMOTE_MARGIN bits to spare, the persistent state
+// known on the host; when it fits the next narrower width with `demote_margin` (16) bits to spare, the persistent state
 // is narrowed before the next pivot.  A later overflow prediction promotes again (K9) -- the margin keeps the two
 // from alternating.  Widths below `demote_floor` (default 8 limbs: pivots there are launch-latency bound) stay.
-#define RG_DEMOTE_MARGIN 40
 static int maybe_demote(rg_context* ctx) {
     const int need = ctx->demote_need;
     ctx->demote_need = 0;
     if (need <= 0) return RG_OK;
     int Lnew = ctx->L;
-    for (int lower = prev_width(Lnew, ctx->pow2_only); lower >= ctx->demote_floor && lower >= 1 && need + RG_DEMOTE_MARGIN <= 64 * lower - 1;
+    for (int lower = prev_width(Lnew, ctx->pow2_only); lower >= ctx->demote_floor && lower >= 1 && need + ctx->demote_margin <= 64 * lower - 1;
          lower = prev_width(Lnew, ctx->pow2_only))
         Lnew = lower;
     if (Lnew == ctx->L) return RG_OK;
