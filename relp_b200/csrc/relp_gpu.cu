@@ -367,8 +367,14 @@ extern "C" int rg_create(const rg_options* opts, rg_context** out) {
     *out = ctx;
     CK(cudaSetDevice(ctx->device));
     pool_setup(ctx->device);
-    CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));   // every copy is issued on this stream
-    CK(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
+    // the main stream carries the critical path (work vector, K1): it gets the greatest priority so that its blocks
+    // are placed before those of the side streams' dots and recurrences when both have blocks pending
+    int prio_lo = 0, prio_hi = 0;
+    const bool use_prio = getenv("RG_NO_PRIO") == nullptr &&
+                          cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) == cudaSuccess && prio_lo != prio_hi;
+    if (!use_prio) { prio_lo = prio_hi = 0; (void)cudaGetLastError(); }
+    CK(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi));   // every copy is issued on this stream
+    CK(cudaStreamCreateWithPriority(&ctx->side, cudaStreamNonBlocking, prio_lo));
     CK(cudaEventCreateWithFlags(&ctx->ev_side0, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_side1, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_side2, cudaEventDisableTiming));
@@ -377,8 +383,8 @@ extern "C" int rg_create(const rg_options* opts, rg_context** out) {
     CK(cudaEventCreateWithFlags(&ctx->ev_nu, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_ft0, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_ft1, cudaEventDisableTiming));
-    CK(cudaStreamCreateWithFlags(&ctx->side2, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&ctx->side3, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithPriority(&ctx->side2, cudaStreamNonBlocking, prio_lo));
+    CK(cudaStreamCreateWithPriority(&ctx->side3, cudaStreamNonBlocking, prio_lo));
     CK(dev_alloc(&ctx->sc, sizeof(Scalars), ctx->stream));
     CK(cudaMemsetAsync(ctx->sc, 0, sizeof(Scalars), ctx->stream));
     {   // pinned mirror: cudaHostAlloc / cudaFreeHost synchronise the whole device, so mirrors are recycled
