@@ -46,6 +46,7 @@ pub struct rg_pivot_info {
 unsafe extern "C" {
     pub fn rg_create(opts: *const rg_options, out: *mut *mut rg_context) -> c_int;
     pub fn rg_destroy(ctx: *mut rg_context) -> c_int;
+    pub fn rg_release_cached_memory(device: i32) -> i64;
     pub fn rg_last_error(ctx: *const rg_context) -> *const c_char;
     pub fn rg_nccl_unique_id(out: *mut c_void, bytes: i32) -> c_int;
     pub fn rg_load_csc(ctx: *mut rg_context, m: i32, n: i32, colptr: *const i64, rowidx: *const i32,

@@ -120,6 +120,12 @@ const char* rg_last_error(const rg_context* ctx);
  * rank.  Returns the id size (128) or an error. */
 int rg_nccl_unique_id(void* out, int32_t bytes);
 
+/* Device buffers of 1 MiB and more are recycled by exact size in a per-device free list of the process (repeated
+ * solves allocate the same sizes; the stream-ordered pool stalled now and then on large requests).  This returns
+ * the parked buffers of `device` to the driver's pool, e.g. before another library needs the memory; live contexts
+ * are unaffected.  Returns the number of bytes released (>= 0) or an RG_ERR_* code. */
+int64_t rg_release_cached_memory(int32_t device);
+
 /* The block partition used for the carry rows (count = m) and for the priced columns (count = number of dense /
  * CSC columns): rank r owns [first, first + number).  Pure host arithmetic, no context or device needed. */
 int rg_shard_block(int32_t count, int32_t world, int32_t rank, int32_t* first, int32_t* number);

@@ -65,6 +65,7 @@ SYMBOLS = {
     "rg_last_error": (C.c_char_p, [P]),
     "rg_nccl_unique_id": (C.c_int, [C.c_void_p, C.c_int32]),
     "rg_shard_block": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "rg_release_cached_memory": (C.c_int64, [C.c_int32]),
     "rg_load_csc": (C.c_int, [P, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int32),
                               C.POINTER(C.c_int64)]),
     "rg_load_dense_i8": (C.c_int, [P, C.c_int32, C.POINTER(C.c_int8)]),

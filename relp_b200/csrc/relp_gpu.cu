@@ -487,6 +487,26 @@ extern "C" int rg_destroy(rg_context* ctx) {
     return RG_OK;
 }
 
+extern "C" int64_t rg_release_cached_memory(int32_t device) {
+    if (device < 0 || device >= 16) return RG_ERR_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) { (void)cudaGetLastError(); return RG_ERR_CUDA; }
+    std::vector<BigFree> parked;
+    {
+        std::lock_guard<std::mutex> lock(g_big_mutex);
+        parked.swap(g_big_free[device]);
+        g_big_cached[device] = 0;
+    }
+    int64_t bytes = 0;
+    for (auto& b : parked) {
+        cudaEventSynchronize(b.ev);        // the stream that released it may be gone; the event is not
+        cudaEventDestroy(b.ev);
+        cudaFree(b.p);
+        bytes += (int64_t)b.bytes;
+    }
+    (void)cudaGetLastError();
+    return bytes;
+}
+
 extern "C" const char* rg_last_error(const rg_context* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
 // The partition of the row-sharded engine, pure host arithmetic shared by rg_load_csc /

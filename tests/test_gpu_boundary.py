@@ -342,3 +342,22 @@ def test_steepest_edge_init_on_general_basis_with_dense_block():
         g = relp_b200.solve_relaxation(prob, rule="steepest_edge", initial_limbs=limbs)
         assert g.status == ores.status and g.trace == otrace
         assert g.objective == ores.objective and g.bfs == ores.bfs
+
+
+def test_release_cached_memory_returns_the_recycled_buffers():
+    """buffers >= 1 MiB are parked by exact size when a context lets go of them; rg_release_cached_memory hands them
+    back to the driver, and a solve afterwards still works (and parks them again)"""
+    import ctypes as C
+    import relp_b200
+    from relp_b200 import _lib
+    from relp_b200.generators import bounded_lp
+    lib = _lib.load()
+    prob = bounded_lp(1100, 640, k_bounding=24, dense=True, seed=9, dense_block=True)
+    g1 = relp_b200.solve_relaxation(prob, rule="steepest_edge")
+    freed = lib.rg_release_cached_memory(0)
+    assert freed > 0
+    assert lib.rg_release_cached_memory(0) == 0
+    assert lib.rg_release_cached_memory(99) < 0
+    g2 = relp_b200.solve_relaxation(prob, rule="steepest_edge")
+    assert g2.trace == g1.trace and g2.objective == g1.objective
+    assert lib.rg_release_cached_memory(0) > 0
