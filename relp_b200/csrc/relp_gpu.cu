@@ -575,7 +575,10 @@ extern "C" int rg_load_csc(rg_context* ctx, int32_t m, int32_t n, const int64_t*
     CK(dev_alloc(&ctx->artcost, sizeof(long long) * m, ctx->stream));
     CK(dev_alloc(&ctx->rowf, sizeof(long long) * m, ctx->stream));
     ctx->work_chunks = std::max(1, std::min(16, cdiv(std::max(ctx->nloc, 1), 256)));
-    ctx->list_chunks = std::max(1, cdiv(std::max(ctx->nloc, 1), 64));        // 64 rows per chunk in list mode
+    {   // rows per work-vector chunk in list mode (a chunk = one block row of k_colsum1 = two partial slabs)
+        static const int chunk_rows = [] { const char* e = getenv("RG_LIST_CHUNK_ROWS"); int v = e ? atoi(e) : 64; return v >= 16 ? v : 64; }();
+        ctx->list_chunks = std::max(1, cdiv(std::max(ctx->nloc, 1), chunk_rows));
+    }
     ctx->list_pcols = ((m + 1) / 3 + 2 + 127) / 128 * 128;                    // the list never exceeds (m+1)/3 + 1
     RG_TRY(alloc_carry(ctx, true));   // cost row + packed block; rg_init_identity_basis picks the real mode
     CK(dev_alloc(&ctx->G, sizeof(u64) * LG_of(ctx->L) * n, ctx->stream));
