@@ -1672,6 +1672,7 @@ k_colsum1(const u64* __restrict__ C, size_t ps, int ld, int m, int rows_per_chun
     __shared__ u64 sPart[2][2][LQ];        // [staging warp][pass]: magnitude sums of one batch
     __shared__ u64 sUsum[2][LQ];           // per pass: sum of |s_i| over the chunk's rows of that sign
     __shared__ u32 sRed[3][NW][32];        // partial sums of row groups 1..3
+    __shared__ unsigned sMask[2][2];       // [staging warp][pass]: rows of the batch whose factor has that sign
     if (sc->status != ST_RUN) return;
     const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
     const int kidx = blockIdx.x * 32 + lane;
@@ -1687,6 +1688,9 @@ k_colsum1(const u64* __restrict__ C, size_t ps, int ld, int m, int rows_per_chun
 #pragma unroll
         for (int l = 0; l < NW; ++l) acc[l] = 0;
         for (int base = r0; base < r1; base += RB) {
+            // a chunk of a single batch (list mode: 64 rows) keeps its staged factors for the second pass
+            const bool stage = pass == 0 || r1 - r0 > RB;
+            if (stage) {
             __syncthreads();
             if (threadIdx.x < RB) {        // warps 0 and 1 stage the factors of rows base .. base+63
                 int i = base + threadIdx.x;
@@ -1710,6 +1714,11 @@ k_colsum1(const u64* __restrict__ C, size_t ps, int ld, int m, int rows_per_chun
                     sg = o == 0 ? 0 : (neg ? -1 : 1);
                 }
                 sSgn[threadIdx.x] = (signed char)sg;
+                {   // the rows of either sign as bit masks: the row groups below take every fourth row OF THE PASS'S
+                    // SIGN, so they finish together (every fourth row of the batch left them up to 30 % apart)
+                    const unsigned mp = __ballot_sync(0xffffffffu, sg == 1), mn = __ballot_sync(0xffffffffu, sg == -1);
+                    if (lane == 0) { sMask[grp][0] = mp; sMask[grp][1] = mn; }
+                }
                 if (pass == 0) {           // magnitude sums of both signs, once per batch (bias removal below)
 #pragma unroll
                     for (int p2 = 0; p2 < 2; ++p2) {
@@ -1740,10 +1749,12 @@ k_colsum1(const u64* __restrict__ C, size_t ps, int ld, int m, int rows_per_chun
 #pragma unroll
                 for (int l = 0; l < LQ; ++l) sUsum[threadIdx.x][l] = a[l];
             }
+            }
             if (k >= ld) continue;
-            const int rn = min(RB, r1 - base);
-            for (int r = grp; r < rn; r += 4) {
-                if (sSgn[r] != want) continue;     // uniform over the warp; rows with a zero factor are never read
+            const unsigned m0 = sMask[0][pass], m1 = sMask[1][pass];
+            const int n0 = __popc(m0), cnt = n0 + __popc(m1);
+            for (int idx = grp; idx < cnt; idx += 4) {     // rows with a zero factor are never read
+                const int r = idx < n0 ? (int)__fns(m0, 0, idx + 1) : 32 + (int)__fns(m1, 0, idx - n0 + 1);
                 u32 x[NA], mg[NB];
                 {
                     u64 xl[L];
