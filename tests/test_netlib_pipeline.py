@@ -24,11 +24,11 @@ EXPECTED = {
 }
 
 
-def provider(name):
+def provider(name, presolve=True):
     text = open(os.path.join(DIR, name + ".SIF")).read()
     mp = frontend.parse_mps(text)
     mp["general_form"] = reader.parse_fixed(text).to_general_form()      # tests/netlib/mod.rs:53: parse_fixed
-    lp = frontend.canonicalize(mp)
+    lp = frontend.canonicalize(mp, presolve=presolve)
     variables = [ro.Variable(c, u) for c, u in zip(lp.costs, lp.upper)]
     return lp, ro.MatrixData(lp.constraint_columns, lp.b, lp.ranges, *lp.counts, variables)
 
@@ -44,6 +44,23 @@ def test_netlib_objective_through_the_restated_pipeline(name):
     want, tol = EXPECTED[name]
     assert abs(sol.objective_value - F(want)) < F(tol)
     assert [k for k, _ in sol.solution_values] == lp.col_order
+
+
+@pytest.mark.parametrize("name", ["SC50A", "SC50B", "KB2", "SHARE2B", "RECIPELP"])
+def test_presolve_changes_the_problem_but_not_the_solution_value(name):
+    """the presolved and the un-presolved MatrixData have different shapes and the same exact optimum; both
+    reconstructions are feasible points of the original problem with that objective"""
+    from oracle import fast_oracle as fo
+    sols = []
+    for use in (True, False):
+        lp, md = provider(name, presolve=use)
+        ref = fo.solve_provider(md, "steepest_edge")
+        assert ref.status == "optimal"
+        sols.append((len(lp.b), len(lp.costs), frontend.recover(lp, ref.bfs, ref.objective)))
+    (m1, n1, a), (m0, n0, b) = sols
+    assert (m1, n1) != (m0, n0) and m1 <= m0 and n1 <= n0
+    assert a.objective_value == b.objective_value
+    assert [k for k, _ in a.solution_values] == [k for k, _ in b.solution_values]
 
 
 @pytest.mark.gpu
