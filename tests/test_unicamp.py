@@ -78,3 +78,26 @@ def test_unicamp_with_cpu_oracle(name):
 @pytest.mark.parametrize("name", sorted(EXPECTED))
 def test_unicamp_with_gpu_engine(name):
     check(name, solve(name, gpu_solver))
+
+
+def _nazareth():
+    """tests/burkardt/test.rs:155-167: the presolved, standardized problem is unbounded"""
+    text = open(os.path.join(os.path.dirname(DIR), "nazareth.mps")).read()
+    lp = frontend.canonicalize(frontend.parse_mps(text))
+    variables = [ro.Variable(c, u) for c, u in zip(lp.costs, lp.upper)]
+    return ro.MatrixData(lp.constraint_columns, lp.b, lp.ranges, *lp.counts, variables)
+
+
+def test_nazareth_is_unbounded_with_cpu_oracle():
+    from oracle import fast_oracle as fo
+    assert fo.solve_provider(_nazareth(), "steepest_edge").status == "unbounded"
+
+
+@pytest.mark.gpu
+def test_nazareth_is_unbounded_with_gpu_engine():
+    import relp_b200
+    from oracle import fast_oracle as fo
+    md = _nazareth()
+    ref = fo.solve_provider(md, "steepest_edge")
+    g = relp_b200.solve_relaxation(scaled_from_provider(md).problem, rule="steepest_edge")
+    assert g.status == ref.status == "unbounded" and g.trace == ref.trace
