@@ -101,3 +101,22 @@ def test_nazareth_is_unbounded_with_gpu_engine():
     ref = fo.solve_provider(md, "steepest_edge")
     g = relp_b200.solve_relaxation(scaled_from_provider(md).problem, rule="steepest_edge")
     assert g.status == ref.status == "unbounded" and g.trace == ref.trace
+
+
+def _cook():
+    """tests/cook/test.rs:17-39 (Cook et al., small example): optimum -143/2"""
+    text = open(os.path.join(os.path.dirname(DIR), "cook_small_example.mps")).read()
+    lp = frontend.canonicalize(frontend.parse_mps(text))
+    variables = [ro.Variable(c, u) for c, u in zip(lp.costs, lp.upper)]
+    return lp, ro.MatrixData(lp.constraint_columns, lp.b, lp.ranges, *lp.counts, variables)
+
+
+def test_cook_small_example_with_cpu_oracle():
+    lp, md = _cook()
+    assert frontend.recover(lp, *cpu_solver(md)).objective_value == F(-143, 2)
+
+
+@pytest.mark.gpu
+def test_cook_small_example_with_gpu_engine():
+    lp, md = _cook()
+    assert frontend.recover(lp, *gpu_solver(md)).objective_value == F(-143, 2)
