@@ -17,20 +17,27 @@ from .solver import IntegerProblem
 INF = None
 
 
-def parse_mps(text):
+def parse_mps(text, mode="auto"):
     """MPS text -> the dict `canonicalize` consumes, through the restatement of relp's own reader (`relp_b200/mps.py`:
-    parse -> `MPS` -> `GeneralForm` data; src/io/mps/{parse,convert}.rs).  The flexible mode is tried first, as
-    `io::mps::parse` does (mod.rs:38-42); files whose names contain blanks need the fixed-column mode.
+    parse -> `MPS` -> `GeneralForm` data; src/io/mps/{parse,convert}.rs).  mode "free" is `io::import` /
+    `io::mps::parse` (mod.rs:38-42), "fixed" is `parse_fixed` (what the reference's netlib tests call,
+    tests/netlib/mod.rs:53); "auto" tries the flexible mode first and the fixed-column mode when that fails (names
+    with blanks).
 
     Keys: name, objective (cost row name), sense, rows (constraint rows in the reference's order: SORTED BY NAME),
     row_type, interval {row: [lo, hi]} (None = unbounded side; ranges and duplicate right-hand sides resolved as
     convert.rs does), columns {col: {row: Fraction}} (cost row entries included), col_order, bounds {col: [lo, hi]}
     with the reference's bound semantics (GLPK's rule for negative upper bounds)."""
     from . import mps as reader
-    try:
+    if mode == "free":
         m = reader.parse_free(text)
-    except reader.ParseError:
+    elif mode == "fixed":
         m = reader.parse_fixed(text)
+    else:
+        try:
+            m = reader.parse_free(text)
+        except (reader.ParseError, reader.Inconsistency):
+            m = reader.parse_fixed(text)
     gf = m.to_general_form()
     rows = list(gf.row_names)
     row_type, interval = {}, {}

@@ -9,7 +9,7 @@ from fractions import Fraction as F
 
 import pytest
 
-from relp_b200 import frontend, mps as reader
+from relp_b200 import frontend
 from oracle import relp_oracle as ro
 from tests.netlib_util import scaled_from_provider
 
@@ -26,8 +26,7 @@ EXPECTED = {
 
 def provider(name, presolve=True):
     text = open(os.path.join(DIR, name + ".SIF")).read()
-    mp = frontend.parse_mps(text)
-    mp["general_form"] = reader.parse_fixed(text).to_general_form()      # tests/netlib/mod.rs:53: parse_fixed
+    mp = frontend.parse_mps(text, mode="fixed")                          # tests/netlib/mod.rs:53: parse_fixed
     lp = frontend.canonicalize(mp, presolve=presolve)
     variables = [ro.Variable(c, u) for c, u in zip(lp.costs, lp.upper)]
     return lp, ro.MatrixData(lp.constraint_columns, lp.b, lp.ranges, *lp.counts, variables)
